@@ -1,0 +1,104 @@
+"""ctypes binding of libagent0_b200.so (the C ABI declared in include/agent0_b200.h).
+
+There is no CPU fallback: if the shared object is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libagent0_b200.so")
+
+A0_SLOTS = 8
+A0_REC_META_I32 = 14
+A0_MAX_NSTEP = 16
+A0_MAX_ACTIONS = 32
+A0_MAX_QUANTILES = 256
+PTR_FRAMES, PTR_REC_SLOTS, PTR_REC_INFO, PTR_TREE, PTR_MAX_P = range(5)
+
+_vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+
+class LossCommon(C.Structure):
+    """a0_loss_common_t"""
+    _fields_ = [("B", _i32), ("A", _i32), ("action", _vp), ("reward", _vp), ("done", _vp),
+                ("weight", _vp), ("gamma_n", _f32), ("alpha", _f32), ("eps", _f32),
+                ("loss", _vp), ("prio", _vp), ("max_p", _vp)]
+
+
+# name -> (restype, argtypes): every symbol include/agent0_b200.h declares
+SIGNATURES = {
+    "a0_version": (_i32, []),
+    "a0_last_error": (C.c_char_p, []),
+    "a0_rb_create": (_i32, [C.POINTER(_vp), _i64, _i64, _i32, _i32]),
+    "a0_rb_destroy": (_i32, [_vp]),
+    "a0_rb_reset": (_i32, [_vp, _vp]),
+    "a0_rb_ptr": (_vp, [_vp, _i32]),
+    "a0_rb_tree_leaves": (_i64, [_vp]),
+    "a0_rb_append": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp]),
+    "a0_pt_mark": (_i32, [_vp, _vp, _i32, _f32, _vp]),
+    "a0_pt_update": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _vp]),
+    "a0_pt_set": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "a0_pt_sample": (_i32, [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "a0_rb_gather": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "a0_loss_dqn": (_i32, [C.POINTER(LossCommon), _vp, _vp, _vp, _vp, _vp]),
+    "a0_loss_mdqn": (_i32, [C.POINTER(LossCommon), _vp, _vp, _vp, _f32, _f32, _vp, _vp]),
+    "a0_loss_c51": (_i32, [C.POINTER(LossCommon), _vp, _vp, _vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp]),
+    "a0_loss_quantile": (_i32, [C.POINTER(LossCommon), _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
+                                _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared object once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m agent0_b200.build` "
+            "(agent0_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().a0_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t, dtype=None):
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("agent0_b200 kernels need CUDA tensors (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+class _DevView:
+    """Zero-copy torch view of handle-owned device memory via __cuda_array_interface__."""
+
+    def __init__(self, address, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(address), False), "version": 2}
+
+
+def device_view(address, shape, typestr, device):
+    return torch.as_tensor(_DevView(address, shape, typestr), device=device)

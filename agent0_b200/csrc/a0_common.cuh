@@ -1,0 +1,104 @@
+// Shared definitions for the agent0_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/agent0_b200.h"
+
+// Per-record side data (16 B, one vector load).  Rewards stay float64 because the reference
+// accumulates n-step returns in numpy float64 (agent0/deepq/agent.py:65-69).
+struct __align__(16) A0RecInfo {
+  double reward;
+  int32_t action_done;   // action | (done << 31)
+  int32_t link;          // ring position of the next record of the same stream, -1 if none yet
+};
+
+struct a0_replay {
+  int32_t device;
+  int64_t N;             // record capacity
+  int64_t NF;            // frame capacity
+  int32_t F;             // bytes per frame (multiple of 16)
+  int64_t P;             // tree leaves (power of two >= N)
+  int32_t D;             // tree depth, P == 1 << D
+  uint8_t* frames;       // [NF][F]
+  int32_t* rec_slots;    // [N][8]
+  A0RecInfo* rec_info;   // [N]
+  float* tree;           // [2P], node 1 = root, leaf j at P + j
+  float* max_p;          // device scalar
+  int32_t* winner;       // [N] scratch for last-writer-wins, kept at -1 between calls
+  unsigned int* counter; // last-block-done ticket for the sampler epilogue
+};
+
+void a0_set_error(const char* fmt, ...);
+
+#define A0_CUDA(expr)                                                          \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) {                                                   \
+      a0_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                   __FILE__, __LINE__);                                        \
+      return (int)_e;                                                          \
+    }                                                                          \
+  } while (0)
+
+#define A0_REQUIRE(cond, ...)                                                  \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      a0_set_error(__VA_ARGS__);                                               \
+      return A0_EINVAL;                                                        \
+    }                                                                          \
+  } while (0)
+
+#define A0_LAUNCH_CHECK()                                                      \
+  do {                                                                         \
+    cudaError_t _e = cudaGetLastError();                                       \
+    if (_e != cudaSuccess) {                                                   \
+      a0_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                   __FILE__, __LINE__);                                        \
+      return (int)_e;                                                          \
+    }                                                                          \
+  } while (0)
+
+struct A0DeviceGuard {
+  int prev;
+  explicit A0DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); else prev = -1; }
+  ~A0DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---- small device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float a0_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float a0_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// First index of the maximum over the lanes (torch.argmax tie rule on CPU: first occurrence).
+__device__ __forceinline__ int a0_warp_argmax(float v, int i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  return i;
+}
+__device__ __forceinline__ float a0_huber(float x) {
+  float ax = fabsf(x);
+  return ax < 1.0f ? 0.5f * x * x : ax - 0.5f;
+}
+__device__ __forceinline__ float a0_clamp1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+// (loss + eps)^alpha; sqrt when alpha == 0.5, which is what torch's CPU pow does (replay.py:56-58)
+__device__ __forceinline__ float a0_priority(float loss, float eps, float alpha) {
+  float x = loss + eps;
+  return alpha == 0.5f ? sqrtf(x) : powf(x, alpha);
+}
+__device__ __forceinline__ void a0_atomic_max_pos(float* addr, float v) {
+  // valid for non-negative floats: the int ordering equals the float ordering
+  if (v > 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}

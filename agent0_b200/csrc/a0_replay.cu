@@ -1,0 +1,370 @@
+// HBM-resident replay shard: frame ring + record ring.  K1 (append) and K3 (fused gather).
+//
+// Replaces the reference's host deque of lz4 blobs (agent0/deepq/replay.py:18,32-37,45-48) and
+// the actor-side n-step tracker (agent0/deepq/agent.py:64-73).  Data layout in HBM:
+//   frames    u8 [NF][F]      one 84x84 frame per slot, F = 7056 = 441 * 16 B (16-B aligned slots)
+//   rec_slots i32[N][8]       frame slots of the observation stack [0..3] and next stack [4..7]
+//   rec_info     [N] 16 B     {f64 reward, i32 action|done<<31, i32 successor link}
+// A transition costs 7056 B of frame data (one new frame) + 48 B of record instead of the
+// reference's self-contained 56 448 B blob.
+#include <stdarg.h>
+
+#include "a0_common.cuh"
+
+static thread_local char g_err[512] = "";
+void a0_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* a0_last_error(void) { return g_err; }
+extern "C" int a0_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+__global__ void a0_fill_i32(int32_t* p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+__global__ void a0_init_scalars(float* max_p, unsigned int* counter) {
+  *max_p = 1.0f;
+  *counter = 0u;
+}
+
+extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t frame_capacity,
+                            int32_t frame_bytes, int32_t device) {
+  A0_REQUIRE(out != nullptr, "a0_rb_create: out is NULL");
+  A0_REQUIRE(rec_capacity >= 2 && rec_capacity <= (1LL << 30), "a0_rb_create: rec_capacity %lld out of range",
+             (long long)rec_capacity);
+  A0_REQUIRE(frame_capacity >= 8 && frame_capacity <= (1LL << 30), "a0_rb_create: frame_capacity %lld out of range",
+             (long long)frame_capacity);
+  A0_REQUIRE(frame_bytes > 0 && frame_bytes % 16 == 0, "a0_rb_create: frame_bytes %d must be a positive multiple of 16",
+             frame_bytes);
+  A0_REQUIRE((int64_t)frame_bytes * A0_SLOTS <= 200 * 1024, "a0_rb_create: frame_bytes %d too large for the smem-staged gather",
+             frame_bytes);
+  A0DeviceGuard guard(device);
+  a0_replay* h = new a0_replay();
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->N = rec_capacity;
+  h->NF = frame_capacity;
+  h->F = frame_bytes;
+  h->D = 1;
+  while ((1LL << h->D) < rec_capacity) h->D++;
+  h->P = 1LL << h->D;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+  alloc((void**)&h->frames, (size_t)h->NF * h->F);
+  alloc((void**)&h->rec_slots, (size_t)h->N * A0_SLOTS * sizeof(int32_t));
+  alloc((void**)&h->rec_info, (size_t)h->N * sizeof(A0RecInfo));
+  alloc((void**)&h->tree, (size_t)2 * h->P * sizeof(float));
+  alloc((void**)&h->max_p, 256);
+  alloc((void**)&h->winner, (size_t)h->N * sizeof(int32_t));
+  alloc((void**)&h->counter, 256);
+  if (e != cudaSuccess) {
+    a0_set_error("a0_rb_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    a0_rb_destroy(h);
+    return e == cudaErrorMemoryAllocation ? A0_ENOMEM : (int)e;
+  }
+  int rc = a0_rb_reset(h, nullptr);
+  if (rc != 0) { a0_rb_destroy(h); return rc; }
+  A0_CUDA(cudaStreamSynchronize(nullptr));
+  *out = h;
+  return A0_OK;
+}
+
+extern "C" int a0_rb_destroy(a0_replay_t* h) {
+  if (!h) return A0_OK;
+  A0DeviceGuard guard(h->device);
+  cudaFree(h->frames); cudaFree(h->rec_slots); cudaFree(h->rec_info); cudaFree(h->tree);
+  cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->counter);
+  delete h;
+  return A0_OK;
+}
+
+extern "C" int a0_rb_reset(a0_replay_t* h, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_reset: handle is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  A0DeviceGuard guard(h->device);
+  A0_CUDA(cudaMemsetAsync(h->tree, 0, (size_t)2 * h->P * sizeof(float), stream));
+  A0_CUDA(cudaMemsetAsync(h->rec_slots, 0, (size_t)h->N * A0_SLOTS * sizeof(int32_t), stream));
+  A0_CUDA(cudaMemsetAsync(h->rec_info, 0xff, (size_t)h->N * sizeof(A0RecInfo), stream));
+  a0_fill_i32<<<256, 256, 0, stream>>>(h->winner, h->N, -1);
+  A0_LAUNCH_CHECK();
+  a0_init_scalars<<<1, 1, 0, stream>>>(h->max_p, h->counter);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
+extern "C" void* a0_rb_ptr(a0_replay_t* h, int32_t which) {
+  if (!h) return nullptr;
+  switch (which) {
+    case A0_PTR_FRAMES: return h->frames;
+    case A0_PTR_REC_SLOTS: return h->rec_slots;
+    case A0_PTR_REC_INFO: return h->rec_info;
+    case A0_PTR_TREE: return h->tree;
+    case A0_PTR_MAX_P: return h->max_p;
+    default: return nullptr;
+  }
+}
+extern "C" int64_t a0_rb_tree_leaves(a0_replay_t* h) { return h ? h->P : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// K1: append.  Blocks [0, n_new) copy one staged frame each into its ring slot with 16-byte
+// vector loads/stores (a 7056-B frame is 441 uint4, fully coalesced); the remaining blocks scatter
+// record metadata, one thread per record.  HBM-bound: F read (staging) + F write per new frame.
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 128;
+
+__global__ void __launch_bounds__(K1_THREADS)
+a0_k1_append(uint8_t* __restrict__ frames, int32_t F, int64_t NF, const uint8_t* __restrict__ staged,
+             const int32_t* __restrict__ new_pos, int32_t n_new, int32_t* __restrict__ rec_slots,
+             A0RecInfo* __restrict__ rec_info, int64_t N, const int32_t* __restrict__ meta, int32_t m) {
+  if ((int)blockIdx.x < n_new) {
+    const int f = blockIdx.x;
+    const int32_t pos = new_pos[f];
+    if (pos < 0 || pos >= NF) return;
+    const uint4* src = reinterpret_cast<const uint4*>(staged + (size_t)f * F);
+    uint4* dst = reinterpret_cast<uint4*>(frames + (size_t)pos * F);
+    const int nvec = F >> 4;
+    for (int i = threadIdx.x; i < nvec; i += K1_THREADS) dst[i] = __ldg(src + i);
+    return;
+  }
+  const int r = ((int)blockIdx.x - n_new) * K1_THREADS + threadIdx.x;
+  if (r >= m) return;
+  const int32_t* mt = meta + (size_t)r * A0_REC_META_I32;
+  const int32_t pos = mt[0], link_from = mt[1], link_to = mt[2], action_done = mt[3];
+  if (pos < 0 || pos >= N) return;
+  int4* s = reinterpret_cast<int4*>(rec_slots + (size_t)pos * A0_SLOTS);
+  s[0] = make_int4(mt[4], mt[5], mt[6], mt[7]);
+  s[1] = make_int4(mt[8], mt[9], mt[10], mt[11]);
+  A0RecInfo info;
+  info.reward = __hiloint2double(mt[13], mt[12]);
+  info.action_done = action_done;
+  info.link = link_to;
+  rec_info[pos] = info;
+  // predecessor written by an earlier append: only its link word is touched
+  if (link_from >= 0 && link_from < N) rec_info[link_from].link = pos;
+}
+
+extern "C" int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames, const int32_t* new_frame_pos,
+                            int32_t n_new, const int32_t* rec_meta, int32_t m, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_append: handle is NULL");
+  A0_REQUIRE(n_new >= 0 && m >= 0, "a0_rb_append: negative count");
+  if (n_new == 0 && m == 0) return A0_OK;
+  A0_REQUIRE(n_new == 0 || (new_frames && new_frame_pos), "a0_rb_append: NULL frame arguments");
+  A0_REQUIRE(m == 0 || rec_meta, "a0_rb_append: NULL rec_meta");
+  A0_REQUIRE(((uintptr_t)new_frames & 15) == 0, "a0_rb_append: new_frames must be 16-byte aligned");
+  A0DeviceGuard guard(h->device);
+  const int blocks = n_new + (m + K1_THREADS - 1) / K1_THREADS;
+  a0_k1_append<<<blocks, K1_THREADS, 0, (cudaStream_t)stream_>>>(
+      h->frames, h->F, h->NF, new_frames, new_frame_pos, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: fused gather
+// ------------------------------------------------------------------------------------------------
+struct A0GatherArgs {
+  const uint8_t* frames;
+  const int32_t* rec_slots;
+  const A0RecInfo* rec_info;
+  const int64_t* idx;
+  int64_t N, NF;
+  int32_t F, count, n_step;
+  double gamma;
+  uint8_t* frames_out;
+  int64_t* action_out;
+  double* reward64_out;
+  float* reward32_out;
+  uint8_t* done8_out;
+  float* done32_out;
+  int64_t* boot_out;
+};
+
+// Walks the n-step window of sample b and returns the 8 frame slots.  The return is evaluated as
+// the reference does (agent.py:65-69): r = 0; for newest..oldest: r = r*gamma*(1-d) + r_t, every
+// product and sum rounded separately in float64 (no FMA contraction).
+__device__ __forceinline__ bool a0_resolve_window(const A0GatherArgs& g, int b, int32_t (&slot)[A0_SLOTS]) {
+  int64_t p0 = g.idx[b];
+  bool ok = p0 >= 0 && p0 < g.N;
+  if (!ok) p0 = 0;
+  double rew[A0_MAX_NSTEP];
+  int dn[A0_MAX_NSTEP];
+  int64_t p = p0;
+  int32_t action = 0, link = -1;
+  int steps = 0;
+#pragma unroll 1
+  for (int i = 0; i < g.n_step; ++i) {
+    const A0RecInfo info = g.rec_info[p];
+    if (i == 0) action = info.action_done & 0x7fffffff;
+    rew[i] = info.reward;
+    dn[i] = (info.action_done >> 31) & 1;
+    link = info.link;
+    steps = i + 1;
+    if (i + 1 < g.n_step) {
+      if (link < 0 || link >= g.N) { ok = false; break; }   // window not complete: caller error
+      p = link;
+    }
+  }
+  double r = 0.0;
+  int d_any = 0;
+#pragma unroll 1
+  for (int i = steps - 1; i >= 0; --i) {
+    d_any |= dn[i];
+    r = __dadd_rn(__dmul_rn(__dmul_rn(r, g.gamma), (double)(1 - dn[i])), rew[i]);
+  }
+  const int4* s0 = reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
+  const int4* s1 = reinterpret_cast<const int4*>(g.rec_slots + (size_t)p * A0_SLOTS);
+  const int4 a = s0[0], c = s1[1];
+  slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w;
+  slot[4] = c.x; slot[5] = c.y; slot[6] = c.z; slot[7] = c.w;
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j)
+    if (slot[j] < 0 || slot[j] >= g.NF) { slot[j] = 0; ok = false; }
+  if (g.action_out) g.action_out[b] = ok ? (int64_t)action : -1;
+  if (g.reward64_out) g.reward64_out[b] = r;
+  if (g.reward32_out) g.reward32_out[b] = (float)r;          // .float() in Trainer.step (trainer.py:88-90)
+  if (g.done8_out) g.done8_out[b] = (uint8_t)d_any;
+  if (g.done32_out) g.done32_out[b] = (float)d_any;
+  if (g.boot_out) g.boot_out[b] = ok ? (int64_t)link : -1;
+  return ok;
+}
+
+__device__ __forceinline__ uint32_t a0_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Variant 0: one warp per sampled transition; lane 0 drives the TMA engine.  Every *distinct*
+// frame of the two stacks is fetched once with cp.async.bulk (global -> shared, completion on an
+// mbarrier) and written with cp.async.bulk (shared -> global) to every stack position it occupies:
+// (S+n)*F bytes read and 2S*F bytes written per transition, no register staging.
+__global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
+  extern __shared__ __align__(128) uint8_t a0_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x != 0) return;
+  const int b = blockIdx.x;
+  int32_t slot[A0_SLOTS];
+  a0_resolve_window(g, b, slot);
+  const uint32_t F = (uint32_t)g.F;
+  const uint32_t bar_a = a0_smem_u32(&bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  // distinct sources
+  int src_of[A0_SLOTS];
+  int n_unique = 0;
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j) {
+    int s = -1;
+#pragma unroll
+    for (int k = 0; k < A0_SLOTS; ++k)
+      if (k < j && s < 0 && slot[k] == slot[j]) s = src_of[k];
+    if (s < 0) s = n_unique++;
+    src_of[j] = s;
+  }
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(F * (uint32_t)n_unique) : "memory");
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j) {
+    bool first = true;
+#pragma unroll
+    for (int k = 0; k < A0_SLOTS; ++k)
+      if (k < j && slot[k] == slot[j]) first = false;
+    if (first) {
+      const uint8_t* src = g.frames + (size_t)slot[j] * F;
+      const uint32_t dst = a0_smem_u32(a0_smem + (size_t)src_of[j] * F);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"(F), "r"(bar_a) : "memory");
+    }
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  uint8_t* out = g.frames_out + (size_t)b * A0_SLOTS * F;
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j) {
+    const uint32_t src = a0_smem_u32(a0_smem + (size_t)src_of[j] * F);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(out + (size_t)j * F), "r"(src), "r"(F) : "memory");
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Variant 1: same traffic with 16-byte LDG/STG through registers (no shared memory); kept as the
+// measured alternative to the TMA path.
+constexpr int K3_LDG_THREADS = 256;
+__global__ void __launch_bounds__(K3_LDG_THREADS) a0_k3_gather_ldg(const A0GatherArgs g) {
+  __shared__ int32_t s_slot[A0_SLOTS];
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int32_t slot[A0_SLOTS];
+    a0_resolve_window(g, b, slot);
+#pragma unroll
+    for (int j = 0; j < A0_SLOTS; ++j) s_slot[j] = slot[j];
+  }
+  __syncthreads();
+  int32_t slot[A0_SLOTS];
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j) slot[j] = s_slot[j];
+  const int nvec = g.F >> 4;
+  uint4* out = reinterpret_cast<uint4*>(g.frames_out + (size_t)b * A0_SLOTS * g.F);
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j) {
+    bool first = true;
+#pragma unroll
+    for (int k = 0; k < A0_SLOTS; ++k)
+      if (k < j && slot[k] == slot[j]) first = false;
+    if (!first) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(g.frames + (size_t)slot[j] * g.F);
+    for (int i = threadIdx.x; i < nvec; i += K3_LDG_THREADS) {
+      const uint4 v = __ldg(src + i);
+#pragma unroll
+      for (int k = 0; k < A0_SLOTS; ++k)
+        if (k >= j && slot[k] == slot[j]) out[(size_t)k * nvec + i] = v;
+    }
+  }
+}
+
+extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
+                            uint8_t* frames_out, int64_t* action_out, double* reward64_out,
+                            float* reward32_out, uint8_t* done8_out, float* done32_out,
+                            int64_t* boot_out, int32_t variant, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_gather: handle is NULL");
+  A0_REQUIRE(count >= 0, "a0_rb_gather: negative count");
+  if (count == 0) return A0_OK;
+  A0_REQUIRE(idx && frames_out, "a0_rb_gather: idx and frames_out are required");
+  A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_gather: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
+  A0_REQUIRE(((uintptr_t)frames_out & 15) == 0, "a0_rb_gather: frames_out must be 16-byte aligned");
+  A0_REQUIRE(variant == 0 || variant == 1, "a0_rb_gather: unknown variant %d", variant);
+  A0DeviceGuard guard(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  A0GatherArgs g;
+  g.frames = h->frames; g.rec_slots = h->rec_slots; g.rec_info = h->rec_info; g.idx = idx;
+  g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
+  g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
+  g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
+  if (variant == 0) {
+    const size_t smem = (size_t)A0_SLOTS * h->F;
+    static thread_local size_t configured[64] = {0};
+    if (h->device < 64 && configured[h->device] < smem) {
+      A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[h->device] = smem;
+    }
+    a0_k3_gather_tma<<<count, 32, smem, stream>>>(g);
+  } else {
+    a0_k3_gather_ldg<<<count, K3_LDG_THREADS, 0, stream>>>(g);
+  }
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}

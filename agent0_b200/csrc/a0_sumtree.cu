@@ -1,0 +1,222 @@
+// GPU sum-tree for prioritized replay: K2a (batched stratified draws + IS weights) and K2b (leaf
+// writes with bottom-up recomputation).
+//
+// Replaces the reference's flat CPU priority vector: the intended draw torch.multinomial(priority)
+// (agent0/deepq/replay.py:39-43), priority[ids] = (loss+eps)^alpha and max_p (replay.py:55-59),
+// priority[-k:] = max_p**alpha on extend (replay.py:52) and the IS-weight block of Trainer.step
+// (agent0/deepq/trainer.py:91-94), which sums 1 M CPU floats per update.
+//
+// Arithmetic is defined by oracle/sumtree.py and must match it bit for bit:
+//   node = fl32(left + right), recomputed from children;  t = fl32(fl32(fl32(b + u)/B) * root);
+//   go left iff (t < left) || !(right > 0);  going right: t = fl32(t - left).
+// The tree (2P floats, 8 MB at 1 M leaves, 16.8 MB at 2 M) is L2-resident: these kernels are
+// latency-bound, not HBM-bound.
+#include "a0_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K2a.  One warp per draw.  Instead of one dependent L2 round trip per level, the warp fetches the
+// whole 5-level sub-heap below the current node in two loads (lane i: sub-heap node 32+i; lane h-2:
+// sub-heap node h for h = 2..31) and walks it through shuffles, with exactly the scalar arithmetic.
+// ------------------------------------------------------------------------------------------------
+constexpr int K2A_WARPS = 8;
+
+__global__ void __launch_bounds__(K2A_WARPS * 32)
+a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
+              int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
+              int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
+              unsigned int* counter) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = blockIdx.x * K2A_WARPS + warp;
+  const float root = __ldcg(tree + 1);
+  if (g < total) {
+    const int b = g % batch;
+    float t = __fmul_rn(__fdiv_rn(__fadd_rn((float)b, u[g]), (float)batch), root);
+    int64_t v = 1;          // current node, warp-uniform
+    float leaf = root;
+    int left = D;
+    while (left > 0) {
+      const int c = left < 5 ? left : 5;
+      // sub-heap node h lives at tree[(v << l) + (h - (1 << l))], l = floor(log2 h)
+      const int hB = lane + 2;
+      const int lB = 31 - __clz(hB);
+      float regB = 0.0f, regA = 0.0f;
+      if (lB <= c && lB <= 4 && hB < 32) regB = __ldcg(tree + ((v << lB) + (hB - (1 << lB))));
+      if (c == 5) regA = __ldcg(tree + ((v << 5) + lane));
+      int h = 1;
+      for (int s = 0; s < c; ++s) {
+        const int hl = 2 * h;
+        float L, R;
+        if (hl < 32) {
+          L = __shfl_sync(0xffffffffu, regB, hl - 2);
+          R = __shfl_sync(0xffffffffu, regB, hl - 1);
+        } else {
+          L = __shfl_sync(0xffffffffu, regA, hl - 32);
+          R = __shfl_sync(0xffffffffu, regA, hl - 31);
+        }
+        if (t < L || !(R > 0.0f)) { h = hl; leaf = L; }
+        else { t = __fsub_rn(t, L); h = hl + 1; leaf = R; }
+      }
+      v = (v << c) + (h - (1 << c));
+      left -= c;
+    }
+    if (lane == 0) {
+      idx_out[g] = v - P;
+      prio_out[g] = leaf;
+    }
+  }
+  if (weight_out == nullptr) return;
+  // ---- epilogue: the last block to finish turns priorities into normalised IS weights ----------
+  __shared__ bool is_last;
+  __shared__ float red[K2A_WARPS];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(counter, 1u);
+    is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float denom = root + sum_offset;
+  const int nb = total / batch;
+  for (int k = 0; k < nb; ++k) {
+    const float* p = prio_out + (size_t)k * batch;
+    float* w = weight_out + (size_t)k * batch;
+    if (uniform) {
+      for (int j = threadIdx.x; j < batch; j += blockDim.x) w[j] = 1.0f;
+      continue;
+    }
+    float mx = 0.0f;
+    for (int j = threadIdx.x; j < batch; j += blockDim.x) {
+      const float wj = powf(__fmul_rn(top, __fdiv_rn(__ldcg(p + j), denom)), -beta);
+      w[j] = wj;
+      mx = fmaxf(mx, wj);
+    }
+    mx = a0_warp_max(mx);
+    __syncthreads();
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < K2A_WARPS; ++i) mx = fmaxf(mx, red[i]);
+    const float inv = mx + 1e-8f;
+    for (int j = threadIdx.x; j < batch; j += blockDim.x) w[j] = __fdiv_rn(w[j], inv);
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32_t batch, float top, float beta,
+                            float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
+                            float* weight_out, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_pt_sample: handle is NULL");
+  A0_REQUIRE(total >= 0 && batch > 0 && total % batch == 0, "a0_pt_sample: total %d must be a multiple of batch %d", total, batch);
+  if (total == 0) return A0_OK;
+  A0_REQUIRE(u && idx_out && prio_out, "a0_pt_sample: NULL argument");
+  A0DeviceGuard guard(h->device);
+  const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
+  a0_k2a_sample<<<blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_>>>(
+      h->tree, h->P, h->D, u, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b.  One CTA; leaves are written with a deterministic last-writer-wins rule, then every touched
+// ancestor is recomputed from its two children one level at a time (block barrier between levels),
+// so the tree stays bit-reproducible whatever the thread schedule.
+//   mode 0: value = (loss+eps)^alpha, skipped when the leaf is 0; max_p = max(max_p, max loss)
+//   mode 1: pos >= 0 -> max_p^alpha;  pos < 0 -> leaf ~pos = 0
+//   mode 2: value = vals[k]
+// ------------------------------------------------------------------------------------------------
+constexpr int K2B_THREADS = 1024;
+
+__global__ void __launch_bounds__(K2B_THREADS)
+a0_k2b_update(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
+              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+              float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner) {
+  __shared__ float red[K2B_THREADS / 32];
+  const int tid = threadIdx.x;
+  const float maxp_in = *max_p;
+  auto position = [&](int k) -> int64_t {
+    if (mode == 1) { const int32_t p = idx32[k]; return p >= 0 ? p : ~p; }
+    return idx64[k];
+  };
+  // phase 1: claim
+  float local_max = 0.0f;
+  for (int k = tid; k < count; k += K2B_THREADS) {
+    const int64_t pos = position(k);
+    if (pos < 0 || pos >= N) continue;
+    atomicMax(winner + pos, k);
+    if (mode == 0) local_max = fmaxf(local_max, vals[k]);
+  }
+  __syncthreads();
+  // phase 2: write leaves
+  for (int k = tid; k < count; k += K2B_THREADS) {
+    const int64_t pos = position(k);
+    if (pos < 0 || pos >= N) continue;
+    if (__ldcg(winner + pos) != k) continue;
+    float v;
+    if (mode == 0) {
+      if (!(__ldcg(tree + P + pos) > 0.0f)) continue;      // evicted since it was sampled
+      v = a0_priority(vals[k], eps, alpha);
+    } else if (mode == 1) {
+      v = idx32[k] >= 0 ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
+    } else {
+      v = vals[k];
+    }
+    tree[P + pos] = v;
+  }
+  __syncthreads();
+  // phase 3: release claims, recompute ancestors level by level
+  for (int k = tid; k < count; k += K2B_THREADS) {
+    const int64_t pos = position(k);
+    if (pos >= 0 && pos < N) winner[pos] = -1;
+  }
+  for (int lvl = 1; lvl <= D; ++lvl) {
+    for (int k = tid; k < count; k += K2B_THREADS) {
+      const int64_t pos = position(k);
+      if (pos < 0 || pos >= N) continue;
+      const int64_t node = (P + pos) >> lvl;
+      tree[node] = __fadd_rn(__ldcg(tree + 2 * node), __ldcg(tree + 2 * node + 1));
+    }
+    __syncthreads();
+  }
+  if (mode == 0) {
+    local_max = a0_warp_max(local_max);
+    if ((tid & 31) == 0) red[tid >> 5] = local_max;
+    __syncthreads();
+    if (tid == 0) {
+      float mx = maxp_in;
+      for (int i = 0; i < K2B_THREADS / 32; ++i) mx = fmaxf(mx, red[i]);
+      *max_p = mx;
+    }
+  }
+}
+
+static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
+                            int32_t count, int32_t mode, float alpha, float eps, a0_stream_t stream_) {
+  if (count == 0) return A0_OK;
+  A0DeviceGuard guard(h->device);
+  a0_k2b_update<<<1, K2B_THREADS, 0, (cudaStream_t)stream_>>>(h->tree, h->P, h->D, h->N, idx64, idx32, vals, count,
+                                                              mode, alpha, eps, h->max_p, h->winner);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
+extern "C" int a0_pt_update(a0_replay_t* h, const int64_t* idx, const float* loss, int32_t count, float alpha,
+                            float eps, a0_stream_t stream) {
+  A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_update: bad handle or count");
+  A0_REQUIRE(count == 0 || (idx && loss), "a0_pt_update: NULL argument");
+  return a0_launch_update(h, idx, nullptr, loss, count, 0, alpha, eps, stream);
+}
+extern "C" int a0_pt_mark(a0_replay_t* h, const int32_t* pos, int32_t count, float alpha, a0_stream_t stream) {
+  A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_mark: bad handle or count");
+  A0_REQUIRE(count == 0 || pos, "a0_pt_mark: NULL argument");
+  return a0_launch_update(h, nullptr, pos, nullptr, count, 1, alpha, 0.0f, stream);
+}
+extern "C" int a0_pt_set(a0_replay_t* h, const int64_t* idx, const float* value, int32_t count, a0_stream_t stream) {
+  A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_set: bad handle or count");
+  A0_REQUIRE(count == 0 || (idx && value), "a0_pt_set: NULL argument");
+  return a0_launch_update(h, idx, nullptr, value, count, 2, 1.0f, 0.0f, stream);
+}

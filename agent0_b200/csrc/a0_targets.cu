@@ -1,0 +1,419 @@
+// K4: fused target + loss + IS weighting + new-priority kernels for the six deepq learners.
+//
+// Each kernel consumes the *network outputs* the reference's train_step consumes and produces, in
+// one launch: the per-sample loss (what the reference returns as q_loss), the gradient of
+// (loss * weight).sum() with respect to the online-network output (agent0/deepq/agent.py:152-155;
+// the loss is SUM-reduced), and the new priority (loss+eps)^alpha with a device-side
+// running max (agent0/deepq/replay.py:55-59).  The reference runs 10-30 eager ATen kernels per rule
+// and, for the quantile family, materialises [B,N,N] tensors several times (agent.py:110-114);
+// here the pair loop stays in registers.  Inputs are <= 2.4 KB per transition: these kernels are
+// launch/ALU-bound, not HBM-bound.
+#include "a0_common.cuh"
+
+struct A0Common {
+  int32_t B, A;
+  const int64_t* action;
+  const float* reward;
+  const float* done;
+  const float* weight;
+  float gamma_n, alpha, eps;
+  float* loss;
+  float* prio;
+  float* max_p;
+};
+
+static inline A0Common a0_unpack(const a0_loss_common_t* c) {
+  A0Common k;
+  k.B = c->B; k.A = c->A; k.action = c->action; k.reward = c->reward; k.done = c->done;
+  k.weight = c->weight; k.gamma_n = c->gamma_n; k.alpha = c->alpha; k.eps = c->eps;
+  k.loss = c->loss; k.prio = c->prio; k.max_p = c->max_p;
+  return k;
+}
+
+static int a0_check_common(const a0_loss_common_t* c, const char* who) {
+  A0_REQUIRE(c != nullptr, "%s: common block is NULL", who);
+  A0_REQUIRE(c->B >= 0, "%s: negative batch", who);
+  A0_REQUIRE(c->A >= 1 && c->A <= A0_MAX_ACTIONS, "%s: action_dim %d outside [1,%d]", who, c->A, A0_MAX_ACTIONS);
+  A0_REQUIRE(c->action && c->reward && c->done && c->weight && c->loss, "%s: NULL tensor in common block", who);
+  return A0_OK;
+}
+
+__device__ __forceinline__ void a0_emit(const A0Common& c, int b, float loss) {
+  c.loss[b] = loss;
+  if (c.prio) c.prio[b] = a0_priority(loss, c.eps, c.alpha);
+  if (c.max_p) a0_atomic_max_pos(c.max_p, loss);
+}
+
+// T = r + (gamma_n * (1 - d)) * boot, each op rounded (agent.py:181-186)
+__device__ __forceinline__ float a0_td_target(float r, float d, float gamma_n, float boot) {
+  return __fadd_rn(r, __fmul_rn(__fmul_rn(gamma_n, __fsub_rn(1.0f, d)), boot));
+}
+
+// ------------------------------------------------------------------------------------------------
+// DQN (agent.py:173-190) and M-DQN (agent.py:194-215): one warp per sample, lane = action.
+// ------------------------------------------------------------------------------------------------
+constexpr int K4S_WARPS = 4;
+
+// log_softmax_stable (agent.py:116-119) over the lanes: (l - max) - tau * logsumexp((l - max)/tau)
+__device__ __forceinline__ float a0_tau_log_pi(float logit, bool valid, float tau, float* z_out) {
+  const float mx = a0_warp_max(valid ? logit : -INFINITY);
+  const float z = logit - mx;
+  const float s = __fdiv_rn(z, tau);                       // max over lanes of s is 0
+  const float se = a0_warp_sum(valid ? expf(s) : 0.0f);
+  *z_out = z;
+  return z - tau * logf(se);
+}
+
+__global__ void __launch_bounds__(K4S_WARPS * 32)
+a0_k4_dqn(const A0Common c, const float* __restrict__ q, const float* __restrict__ qt_next,
+          const float* __restrict__ qsel, const float* __restrict__ qt_cur, int32_t munchausen, float tau,
+          float lo, float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * K4S_WARPS + (threadIdx.x >> 5);
+  if (b >= c.B) return;
+  const int A = c.A;
+  const bool valid = lane < A;
+  const size_t off = (size_t)b * A + lane;
+  const float tn = valid ? qt_next[off] : 0.0f;
+  const int a = (int)c.action[b];
+  float boot, bonus = 0.0f;
+  if (!munchausen) {
+    const float sel = valid ? (qsel ? qsel[off] : tn) : -INFINITY;
+    const int a_star = a0_warp_argmax(sel, lane);
+    boot = __shfl_sync(0xffffffffu, tn, a_star);
+  } else {
+    float z;
+    const float tlp = a0_tau_log_pi(tn, valid, tau, &z);   // tau * log pi(.|s')
+    const float e = valid ? expf(z) : 0.0f;
+    const float p = __fdiv_rn(e, a0_warp_sum(e));          // softmax at temperature 1
+    boot = a0_warp_sum(valid ? p * (tn - tlp) : 0.0f);
+    float zc;
+    const float tlp_cur = a0_tau_log_pi(valid ? qt_cur[off] : 0.0f, valid, tau, &zc);
+    const float at_a = __shfl_sync(0xffffffffu, tlp_cur, a);
+    bonus = __fmul_rn(tau, fminf(fmaxf(at_a, lo), 0.0f));
+  }
+  const float qa = q[(size_t)b * A + a];
+  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  const float T = munchausen
+      ? __fadd_rn(__fadd_rn(r, bonus), __fmul_rn(__fmul_rn(c.gamma_n, __fsub_rn(1.0f, d)), boot))
+      : a0_td_target(r, d, c.gamma_n, boot);
+  const float x = qa - T;
+  if (valid) grad[off] = lane == a ? w * a0_clamp1(x) : 0.0f;
+  if (lane == 0) a0_emit(c, b, a0_huber(x));
+}
+
+extern "C" int a0_loss_dqn(const a0_loss_common_t* c, const float* q, const float* qt_next, const float* qsel,
+                           float* grad, a0_stream_t stream) {
+  int rc = a0_check_common(c, "a0_loss_dqn");
+  if (rc) return rc;
+  A0_REQUIRE(q && qt_next && grad, "a0_loss_dqn: NULL tensor");
+  if (c->B == 0) return A0_OK;
+  a0_k4_dqn<<<(c->B + K4S_WARPS - 1) / K4S_WARPS, K4S_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      a0_unpack(c), q, qt_next, qsel, nullptr, 0, 0.0f, 0.0f, grad);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
+extern "C" int a0_loss_mdqn(const a0_loss_common_t* c, const float* q, const float* qt_next, const float* qt_cur,
+                            float tau, float lo, float* grad, a0_stream_t stream) {
+  int rc = a0_check_common(c, "a0_loss_mdqn");
+  if (rc) return rc;
+  A0_REQUIRE(q && qt_next && qt_cur && grad, "a0_loss_mdqn: NULL tensor");
+  A0_REQUIRE(tau > 0.0f, "a0_loss_mdqn: tau must be positive");
+  if (c->B == 0) return A0_OK;
+  a0_k4_dqn<<<(c->B + K4S_WARPS - 1) / K4S_WARPS, K4S_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      a0_unpack(c), q, qt_next, nullptr, qt_cur, 1, tau, lo, grad);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C51 (agent.py:219-269): one warp per sample, lane l owns atoms l, l+32, ... (M <= 128).
+// The projection replaces two index_add_ calls (atomicAdd scatter on CUDA, agent.py:258-264) by a
+// fixed-order accumulation: every lane owns destination bins and scans the source atoms in the
+// order the CPU index_add_ applies them (all `lo` terms by ascending atom, then all `up` terms).
+// ------------------------------------------------------------------------------------------------
+constexpr int C51_WARPS = 4;
+constexpr int C51_MAXR = 4;     // atoms per lane: M <= 128
+
+__global__ void __launch_bounds__(C51_WARPS * 32)
+a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __restrict__ tgt_logits,
+          const float* __restrict__ qsel, const float* __restrict__ atoms, int32_t M, float vmin, float vmax,
+          float* __restrict__ grad, float* __restrict__ target_prob) {
+  __shared__ float s_w[C51_WARPS][2][C51_MAXR * 32];   // per-warp source terms: weight to lo / to up
+  __shared__ int s_i[C51_WARPS][2][C51_MAXR * 32];     // per-warp source bins:  lo / up
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * C51_WARPS + wid;
+  if (b >= c.B) return;
+  const int A = c.A;
+  const int R = (M + 31) / 32;
+  float z[C51_MAXR];
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) z[k] = (k < R && lane + 32 * k < M) ? atoms[lane + 32 * k] : 0.0f;
+
+  // ---- action selection ------------------------------------------------------------------------
+  int a_star;
+  if (qsel) {
+    a_star = a0_warp_argmax(lane < A ? qsel[(size_t)b * A + lane] : -INFINITY, lane);
+  } else {
+    // argmax_a sum_j softmax(tgt[b,a,:])_j * z_j (agent.py:226)
+    float best = -INFINITY;
+    a_star = 0;
+    for (int a2 = 0; a2 < A; ++a2) {
+      const float* row = tgt_logits + ((size_t)b * A + a2) * M;
+      float v[C51_MAXR], mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < C51_MAXR; ++k) {
+        v[k] = (k < R && lane + 32 * k < M) ? row[lane + 32 * k] : -INFINITY;
+        mx = fmaxf(mx, v[k]);
+      }
+      mx = a0_warp_max(mx);
+      float se = 0.0f;
+#pragma unroll
+      for (int k = 0; k < C51_MAXR; ++k) { v[k] = (k < R && lane + 32 * k < M) ? expf(v[k] - mx) : 0.0f; se += v[k]; }
+      se = a0_warp_sum(se);
+      float ev = 0.0f;
+#pragma unroll
+      for (int k = 0; k < C51_MAXR; ++k) ev += __fdiv_rn(v[k], se) * z[k];
+      ev = a0_warp_sum(ev);
+      if (ev > best) { best = ev; a_star = a2; }
+    }
+  }
+
+  // ---- softmax of the selected target row --------------------------------------------------------
+  const float* trow = tgt_logits + ((size_t)b * A + a_star) * M;
+  float p[C51_MAXR], mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) {
+    p[k] = (k < R && lane + 32 * k < M) ? trow[lane + 32 * k] : -INFINITY;
+    mx = fmaxf(mx, p[k]);
+  }
+  mx = a0_warp_max(mx);
+  float se = 0.0f;
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) { p[k] = (k < R && lane + 32 * k < M) ? expf(p[k] - mx) : 0.0f; se += p[k]; }
+  se = a0_warp_sum(se);
+
+  // ---- per-source projection terms (agent.py:230-244) ----------------------------------------
+  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  const float gm = __fmul_rn(c.gamma_n, __fsub_rn(1.0f, d));
+  const float delta = (vmax - vmin) / (float)(M - 1);
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) {
+    const int j = lane + 32 * k;
+    if (k < R && j < M) {
+      const float pj = __fdiv_rn(p[k], se);
+      float tz = __fadd_rn(r, __fmul_rn(gm, z[k]));
+      tz = fminf(fmaxf(tz, vmin), vmax);
+      const float base = __fdiv_rn(__fsub_rn(tz, vmin), delta);
+      int lo = (int)floorf(base), up = (int)ceilf(base);
+      if (up > 0 && lo == up) lo -= 1;
+      if (lo < M - 1 && lo == up) up += 1;
+      s_i[wid][0][j] = lo;
+      s_i[wid][1][j] = up;
+      s_w[wid][0][j] = __fmul_rn(pj, __fsub_rn((float)up, base));
+      s_w[wid][1][j] = __fmul_rn(pj, __fsub_rn(base, (float)lo));
+    }
+  }
+  __syncwarp();
+  float m[C51_MAXR];
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) m[k] = 0.0f;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int j = 0; j < M; ++j) {
+      const int bin = s_i[wid][pass][j];
+      const float wj = s_w[wid][pass][j];
+#pragma unroll
+      for (int k = 0; k < C51_MAXR; ++k)
+        if (bin == lane + 32 * k) m[k] = __fadd_rn(m[k], wj);
+    }
+
+  // ---- cross-entropy with the online row, gradient through log_softmax (agent.py:266-268) ------
+  const int a = (int)c.action[b];
+  const float* orow = logits + ((size_t)b * A + a) * M;
+  float l[C51_MAXR], omx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) {
+    l[k] = (k < R && lane + 32 * k < M) ? orow[lane + 32 * k] : -INFINITY;
+    omx = fmaxf(omx, l[k]);
+  }
+  omx = a0_warp_max(omx);
+  float ose = 0.0f;
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) ose += (k < R && lane + 32 * k < M) ? expf(l[k] - omx) : 0.0f;
+  ose = a0_warp_sum(ose);
+  const float lse = logf(ose);
+  float ce = 0.0f, msum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k)
+    if (k < R && lane + 32 * k < M) { ce += m[k] * ((l[k] - omx) - lse); msum += m[k]; }
+  ce = a0_warp_sum(ce);
+  msum = a0_warp_sum(msum);
+  float* grow = grad + (size_t)b * A * M;
+  for (int i = lane; i < A * M; i += 32) {
+    const int a2 = i / M;
+    if (a2 != a) grow[i] = 0.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) {
+    const int j = lane + 32 * k;
+    if (k < R && j < M) {
+      const float sm = expf((l[k] - omx) - lse);
+      grow[(size_t)a * M + j] = w * (sm * msum - m[k]);
+      if (target_prob) target_prob[(size_t)b * M + j] = m[k];
+    }
+  }
+  if (lane == 0) a0_emit(c, b, -ce);
+}
+
+extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const float* tgt_logits,
+                           const float* qsel, const float* atoms, int32_t M, float vmin, float vmax, float* grad,
+                           float* target_prob, a0_stream_t stream) {
+  int rc = a0_check_common(c, "a0_loss_c51");
+  if (rc) return rc;
+  A0_REQUIRE(logits && tgt_logits && atoms && grad, "a0_loss_c51: NULL tensor");
+  A0_REQUIRE(M >= 2 && M <= C51_MAXR * 32, "a0_loss_c51: num_atoms %d outside [2,%d]", M, C51_MAXR * 32);
+  A0_REQUIRE(vmax > vmin, "a0_loss_c51: vmax must exceed vmin");
+  if (c->B == 0) return A0_OK;
+  a0_k4_c51<<<(c->B + C51_WARPS - 1) / C51_WARPS, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, grad, target_prob);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Quantile-Huber family (agent.py:110-114; QR :273-293, IQN :297-327, FQF :340-388).
+// One CTA per sample, thread j owns online quantile q_j and loops over the Ni targets held in
+// shared memory: Ni*Nj pairs (40 000 for QR-200) never leave registers.
+//   loss_b = (1/Ni) sum_i sum_j |tau_j - 1[T_i < q_j]| * huber(q_j - T_i)
+//   grad_j = (w/Ni) sum_i |tau_j - 1[q_j - T_i > 0]| * clamp(q_j - T_i, -1, 1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float a0_block_sum(float v, float* red, int nwarps) {
+  v = a0_warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.0f;
+  for (int i = 0; i < nwarps; ++i) s += red[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(A0_MAX_QUANTILES)
+a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, const float* __restrict__ qt,
+               const float* __restrict__ taus, const float* __restrict__ qsel, int32_t Ni, int32_t Nj,
+               float* __restrict__ grad, const float* __restrict__ q_bar, const float* __restrict__ taus_full,
+               float* __restrict__ fraction_loss, float* __restrict__ grad_taus) {
+  __shared__ float sT[A0_MAX_QUANTILES];
+  __shared__ float sQ[A0_MAX_QUANTILES];
+  __shared__ float sMean[A0_MAX_ACTIONS];
+  __shared__ float red[A0_MAX_QUANTILES / 32];
+  __shared__ int s_astar;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int A = c.A;
+  // element (b, n, a) of an online/target tensor
+  const size_t sN_q = layout == 0 ? 1 : (size_t)A, sA_q = layout == 0 ? (size_t)Nj : 1;
+  const size_t sN_t = layout == 0 ? 1 : (size_t)A, sA_t = layout == 0 ? (size_t)Ni : 1;
+  const float* qb = q + (size_t)b * A * Nj;
+  const float* tb = qt + (size_t)b * A * Ni;
+
+  // ---- action selection ------------------------------------------------------------------------
+  if (qsel) {
+    if (wid == 0) {
+      const int as = a0_warp_argmax(lane < A ? qsel[(size_t)b * A + lane] : -INFINITY, lane);
+      if (lane == 0) s_astar = as;
+    }
+  } else {
+    // QR without double_q: argmax_a mean_i theta'[a][i] (agent.py:279)
+    for (int a2 = wid; a2 < A; a2 += nwarps) {
+      float s = 0.0f;
+      for (int i = lane; i < Ni; i += 32) s += tb[a2 * sA_t + i * sN_t];
+      s = a0_warp_sum(s);
+      if (lane == 0) sMean[a2] = __fdiv_rn(s, (float)Ni);
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const int as = a0_warp_argmax(lane < A ? sMean[lane] : -INFINITY, lane);
+      if (lane == 0) s_astar = as;
+    }
+  }
+  __syncthreads();
+  const int a_star = s_astar;
+  const int a = (int)c.action[b];
+  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  if (tid < Ni) sT[tid] = a0_td_target(r, d, c.gamma_n, tb[a_star * sA_t + tid * sN_t]);
+  float qj = 0.0f, tau = 0.0f;
+  if (tid < Nj) {
+    qj = qb[a * sA_q + tid * sN_q];
+    tau = taus ? taus[(size_t)b * Nj + tid] : __fdiv_rn((float)(2 * tid + 1), 2.0f * (float)Nj);
+    sQ[tid] = qj;
+  }
+  __syncthreads();
+
+  // ---- pair loop ---------------------------------------------------------------------------------
+  float lsum = 0.0f, gsum = 0.0f;
+  if (tid < Nj) {
+#pragma unroll 4
+    for (int i = 0; i < Ni; ++i) {
+      const float uij = qj - sT[i];
+      const float k = fabsf(tau - (uij > 0.0f ? 1.0f : 0.0f));
+      lsum += k * a0_huber(uij);
+      gsum += k * a0_clamp1(uij);
+    }
+  }
+  const float total = a0_block_sum(lsum, red, nwarps);
+  // zero the whole [A, Nj] gradient block of this sample, then fill the taken action's column/row
+  float* gb = grad + (size_t)b * A * Nj;
+  for (int i = tid; i < A * Nj; i += blockDim.x) gb[i] = 0.0f;
+  __syncthreads();
+  if (tid < Nj) gb[a * sA_q + tid * sN_q] = __fdiv_rn(w, (float)Ni) * gsum;
+  if (tid == 0) a0_emit(c, b, __fdiv_rn(total, (float)Ni));
+
+  // ---- FQF fraction loss (agent.py:371-387) ----------------------------------------------------
+  if (q_bar) {
+    const int F = Nj;
+    float gi = 0.0f, contrib = 0.0f;
+    if (tid < F - 1) {
+      const float* qbar_b = q_bar + (size_t)b * (F - 1) * A;
+      const float qi = qbar_b[(size_t)tid * A + a];
+      const float prev = tid == 0 ? sQ[0] : qbar_b[(size_t)(tid - 1) * A + a];
+      const float next = tid == F - 2 ? sQ[F - 1] : qbar_b[(size_t)(tid + 1) * A + a];
+      const float v1 = qi - sQ[tid], v2 = qi - sQ[tid + 1];
+      gi = (qi > prev ? v1 : -v1) + (qi < next ? v2 : -v2);
+      contrib = gi * taus_full[(size_t)b * (F + 1) + tid + 1];
+    }
+    const float fl = a0_block_sum(contrib, red, nwarps);
+    if (tid == 0 && fraction_loss) fraction_loss[b] = fl;
+    if (grad_taus) {
+      float* gt = grad_taus + (size_t)b * (F + 1);
+      if (tid < F - 1) gt[tid + 1] = w * gi;
+      if (tid == 0) { gt[0] = 0.0f; gt[F] = 0.0f; }
+    }
+  }
+}
+
+extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const float* q, const float* qt,
+                                const float* taus, const float* qsel, int32_t Ni, int32_t Nj, float* grad,
+                                const float* q_bar, const float* taus_full, float* fraction_loss,
+                                float* grad_taus, a0_stream_t stream) {
+  int rc = a0_check_common(c, "a0_loss_quantile");
+  if (rc) return rc;
+  A0_REQUIRE(layout == 0 || layout == 1, "a0_loss_quantile: layout must be 0 ([B,A,N]) or 1 ([B,N,A])");
+  A0_REQUIRE(q && qt && grad, "a0_loss_quantile: NULL tensor");
+  A0_REQUIRE(Ni >= 1 && Ni <= A0_MAX_QUANTILES && Nj >= 1 && Nj <= A0_MAX_QUANTILES,
+             "a0_loss_quantile: Ni=%d Nj=%d outside [1,%d]", Ni, Nj, A0_MAX_QUANTILES);
+  A0_REQUIRE(layout == 0 || taus, "a0_loss_quantile: layout 1 needs per-sample taus");
+  A0_REQUIRE(layout == 0 || qsel, "a0_loss_quantile: layout 1 (IQN/FQF) needs qsel (head.qval)");
+  if (q_bar) {
+    A0_REQUIRE(layout == 1 && Ni == Nj && Nj >= 2 && taus_full, "a0_loss_quantile: fraction term needs layout 1, Ni == Nj >= 2 and taus_full");
+  }
+  if (c->B == 0) return A0_OK;
+  int threads = Ni > Nj ? Ni : Nj;
+  threads = ((threads + 31) / 32) * 32;
+  a0_k4_quantile<<<c->B, threads, 0, (cudaStream_t)stream>>>(a0_unpack(c), layout, q, qt, taus, qsel, Ni, Nj, grad,
+                                                             q_bar, taus_full, fraction_loss, grad_taus);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}

@@ -1,0 +1,405 @@
+"""HBM-resident replay shard behind the reference's ``ReplayDataset`` interface.
+
+Drop-in surface (agent0/deepq/replay.py:14-59): ``ReplayDataset(cfg)``, ``extend(transitions)``,
+``__len__``, ``top``, ``beta``, ``max_p``, ``priority`` (an object with ``.sum()``),
+``update_priority(ids, priorities)``.  New: ``sample(batch_size, k_batches)`` replaces the
+DataLoaderX/DataPrefetcher pump (agent0/deepq/trainer.py:63-72, agent0/common/utils.py:31-61) and
+returns device-resident tensors in the reference's 6-tuple order plus the fused IS weights;
+``append_steps`` is the native single-frame ingest for actors that feed the shard directly.
+
+Everything on the data path is a CUDA kernel from libagent0_b200.so (K1 append, K2a sample,
+K2b update, K3 gather); this module only does the host bookkeeping (ring_index.RingIndex) and the
+pinned-memory staging.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ring_index import ContentDeduper, RingIndex, stack_delta
+
+Batch = namedtuple("Batch", ["frames", "actions", "rewards", "terminals", "priorities", "indices",
+                             "weights", "rewards_f32", "terminals_f32", "boot_indices"])
+Batch.__doc__ = """One or more sampled batches, device resident.  Fields 0..5 are the reference's
+collated 6-tuple (frames u8[B,8*F], a i64, r f64, d bool, priority f32, idx i64; SURVEY 8b);
+``weights`` are the IS weights of trainer.py:91-96, ``*_f32`` the .float() casts of trainer.py:88-90."""
+
+def _is_prioritized(cfg):
+    pol = cfg.replay.policy
+    return getattr(pol, "name", str(pol)) == "prioritize"
+
+
+class _LinearSchedule:
+    """beta annealing with the semantics of agent0/common/utils.py:12-28: a call returns the
+    current value and then advances by inc*steps, clamped at ``end``."""
+
+    def __init__(self, start, end, steps):
+        self.inc = (end - start) / float(steps)
+        self.current, self.end = start, end
+        self.bound = min if end > start else max
+
+    def __call__(self, steps=1):
+        val = self.current
+        self.current = self.bound(self.current + self.inc * steps, self.end)
+        return val
+
+
+class _PrioritySum:
+    """Stands in for the reference's ``replay.priority`` tensor where Trainer.step only calls
+    ``.sum()`` on it (trainer.py:92): the sum is the tree root, already on the device."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def sum(self):
+        return self._o.priority_sum()
+
+    def leaves(self):
+        return self._o.tree[self._o.P:self._o.P + self._o.size]
+
+
+class ReplayDataset:
+    def __init__(self, cfg, device=None, frame_capacity=None, native_nstep=False, compat_sum=False,
+                 gather_variant=0, age_limit=None):
+        """cfg: the reference's ExpConfig (or agent0_b200.config.ExpConfig; same attribute names).
+
+        native_nstep=False: ``extend`` receives the reference actor's already n-step-folded
+        entries, so records are gathered with a 1-step window.  native_nstep=True: ``append_steps``
+        receives raw 1-step transitions and K3 folds ``cfg.learner.n_step_q`` steps.
+        compat_sum=True reproduces the reference's IS-weight denominator over never-written slots
+        (SURVEY Q3); the default uses the sum over live priorities.
+        """
+        self.cfg = cfg
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("agent0_b200.ReplayDataset needs a CUDA device (no CPU fallback)")
+        if device is None:
+            dv = getattr(cfg.device, "value", cfg.device)
+            device = torch.device(dv if str(dv).startswith("cuda") else "cuda")
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.size = int(cfg.replay.size)
+        obs_shape = tuple(cfg.obs_shape)
+        self.stack = int(obs_shape[0])
+        assert self.stack == 4, "the kernels are specialised for 4-frame stacks (FrameStack(4))"
+        self.frame_shape = obs_shape[1:]
+        self.F = int(np.prod(self.frame_shape))
+        assert self.F % 16 == 0, "frame bytes must be a multiple of 16"
+        self.n_gather = int(cfg.learner.n_step_q) if native_nstep else 1
+        self.gamma = float(cfg.learner.discount)
+        if frame_capacity is None:
+            frame_capacity = int(self.size * 1.0625) + 65536 if self.size >= 65536 else 4 * self.size + 64
+        self.index = RingIndex(self.size, frame_capacity, self.n_gather, age_limit)
+        self.prioritize = _is_prioritized(cfg)
+        self.alpha = float(cfg.replay.alpha) if self.prioritize else 1.0
+        self.eps = float(cfg.replay.eps)
+        self.compat_sum = bool(compat_sum)
+        self.gather_variant = int(gather_variant)
+        if self.prioritize:
+            self.beta_schedule = _LinearSchedule(cfg.replay.beta0, 1.0, cfg.trainer.total_steps)
+            self.beta = cfg.replay.beta0
+        else:
+            self.beta = 1.0
+        self.num_envs = int(cfg.actor.num_envs)
+
+        h = C.c_void_p()
+        _lib.check(self.lib.a0_rb_create(C.byref(h), self.size, frame_capacity, self.F, self.device.index),
+                   "a0_rb_create")
+        self.h = h
+        self.P = int(self.lib.a0_rb_tree_leaves(h))
+        dev = self.device
+        self.frames = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_FRAMES), (frame_capacity, self.F), "|u1", dev)
+        self.tree = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_TREE), (2 * self.P,), "<f4", dev)
+        self.max_p_tensor = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_MAX_P), (1,), "<f4", dev)
+        self.priority = _PrioritySum(self)
+        self._dedupe = ContentDeduper(self.index, self.F)   # reference-tuple ingest
+        self._last4 = {}               # stream -> i64[4] seqs of the current stack (native ingest)
+        self._staging = [None, None]
+        self._staging_evt = [None, None]
+        self._staging_turn = 0
+        self._lz4 = None
+
+    # ------------------------------------------------------------------ reference surface
+    def __len__(self):
+        return self.index.top
+
+    @property
+    def top(self):
+        return self.index.top
+
+    @property
+    def max_p(self):
+        """Host copy of the running max loss (synchronises; the kernels use the device copy)."""
+        return float(self.max_p_tensor.item())
+
+    def priority_sum(self):
+        root = self.tree[1]
+        if self.compat_sum:
+            return root + float(self.size - self.index.top)
+        return root
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.lib.a0_rb_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ ingest: reference tuples
+    def _decompress(self, blob):
+        want = 2 * self.stack * self.F
+        if isinstance(blob, np.ndarray):
+            return blob.reshape(-1)
+        if len(blob) == want:
+            return np.frombuffer(blob, dtype=np.uint8)
+        if self._lz4 is None:
+            try:
+                from lz4.block import decompress as _d
+                self._lz4 = _d
+            except Exception:
+                self._lz4 = _liblz4_block_decompress
+        return np.frombuffer(self._lz4(blob), dtype=np.uint8)
+
+    def extend(self, transitions, streams=None):
+        """Reference-compatible ingest (replay.py:45-53): a list of (frames, action, reward, done)
+        with frames = the 8-frame blob concat(st, st_next) (raw bytes/ndarray or lz4 block,
+        agent.py:78-81).  Entries arrive step-major, env-minor, so entry i belongs to stream
+        i % num_envs unless ``streams`` says otherwise.  Frames already held for the stream's
+        previous entry are not stored again."""
+        m = len(transitions)
+        if m == 0:
+            return
+        if streams is None:
+            streams = np.arange(m, dtype=np.int64) % self.num_envs
+        streams = np.asarray(streams, dtype=np.int64)
+        frames = np.stack([self._decompress(t[0]) for t in transitions]).reshape(m, 8, self.F)
+        action = np.array([int(t[1]) for t in transitions], dtype=np.int64)
+        reward = np.array([float(t[2]) for t in transitions], dtype=np.float64)
+        done = np.array([bool(t[3]) for t in transitions], dtype=np.bool_)
+        step = self.index.max_chunk
+        for lo in range(0, m, step):
+            hi = min(m, lo + step)
+            self._extend_chunk(streams[lo:hi], frames[lo:hi], action[lo:hi], reward[lo:hi], done[lo:hi])
+        if self.prioritize:
+            self.beta = self.beta_schedule(m)
+
+    def _extend_chunk(self, streams, frames, action, reward, done):
+        fs8, new_src = self._dedupe.resolve(streams, frames)
+        plan = self.index.plan(streams, fs8, new_src, action, reward, done)
+        self._execute(plan, torch.from_numpy(frames.reshape(len(streams) * 8, self.F)))
+        self._dedupe.detach(streams)
+
+    # ------------------------------------------------------------------ ingest: native 1-step
+    def reset_streams(self, streams, stacks):
+        """Give streams their initial observation stack (u8 [k,4,H,W], host or device)."""
+        streams = np.asarray(streams, dtype=np.int64)
+        k = len(streams)
+        ix = self.index
+        seqs = ix.head_fs + np.arange(4 * k, dtype=np.int64)
+        for i, sid in enumerate(streams):
+            self._last4[int(sid)] = seqs[4 * i:4 * i + 4].copy()
+        # frames only, no records
+        plan = ix.plan(np.zeros(0, dtype=np.int64), np.zeros((0, 8), dtype=np.int64),
+                       np.arange(4 * k, dtype=np.int64), [], [], [])
+        self._execute(plan, self._as_flat_frames(stacks, 4 * k))
+
+    def append_steps(self, streams, n_new, new_frames, action, reward, done):
+        """Native ingest.  For each transition (in order) the observation is the stream's current
+        stack and the next observation is that stack shifted by ``n_new`` (0..4) new frames taken,
+        in order, from ``new_frames`` (u8 [sum(n_new), H, W], host or device).  ``done`` follows
+        the reference's rule (terminal | life_loss) & ~truncated (agent.py:57-62)."""
+        streams = np.asarray(streams, dtype=np.int64)
+        n_new = np.asarray(n_new, dtype=np.int64)
+        m = len(streams)
+        total_new = int(n_new.sum())
+        flat = self._as_flat_frames(new_frames, total_new)
+        step = self.index.max_chunk
+        f0 = 0
+        for lo in range(0, m, step):
+            hi = min(m, lo + step)
+            cnt = int(n_new[lo:hi].sum())
+            fs8 = self.index.resolve_shift(streams[lo:hi], n_new[lo:hi], self._last4)
+            plan = self.index.plan(streams[lo:hi], fs8, np.arange(cnt, dtype=np.int64),
+                                   np.asarray(action)[lo:hi], np.asarray(reward)[lo:hi], np.asarray(done)[lo:hi])
+            self._execute(plan, flat[f0:f0 + cnt])
+            f0 += cnt
+        if self.prioritize:
+            self.beta = self.beta_schedule(m)
+
+    def append_vector_step(self, obs, action, reward, done, obs_next, streams=None):
+        """Convenience for a gymnasium-style vector step: derives ``n_new`` by comparing stacks."""
+        E = obs.shape[0]
+        streams = np.arange(E, dtype=np.int64) if streams is None else np.asarray(streams, dtype=np.int64)
+        fresh = [i for i, s in enumerate(streams) if int(s) not in self._last4]
+        if fresh:
+            self.reset_streams(streams[fresh], obs[fresh])
+        k = stack_delta(obs, obs_next)
+        new = np.concatenate([obs_next[e, 4 - k[e]:] for e in range(E)]) if k.sum() else \
+            np.zeros((0,) + tuple(obs.shape[2:]), dtype=np.uint8)
+        self.append_steps(streams, k, new, action, reward, done)
+
+    def _as_flat_frames(self, frames, count):
+        if isinstance(frames, torch.Tensor):
+            t = frames.reshape(count, self.F)
+            assert t.dtype == torch.uint8
+            return t
+        return torch.from_numpy(np.ascontiguousarray(frames, dtype=np.uint8).reshape(count, self.F))
+
+    # ------------------------------------------------------------------ device execution of a plan
+    def _stage(self, nbytes):
+        turn = self._staging_turn
+        self._staging_turn ^= 1
+        if self._staging_evt[turn] is not None:
+            self._staging_evt[turn].synchronize()
+        buf = self._staging[turn]
+        if buf is None or buf[0].numel() < nbytes:
+            cap = max(int(nbytes * 1.25), 1 << 20)
+            buf = (torch.empty(cap, dtype=torch.uint8, pin_memory=True),
+                   torch.empty(cap, dtype=torch.uint8, device=self.device))
+            self._staging[turn] = buf
+        return turn, buf
+
+    def _execute(self, plan, flat_frames):
+        """Stage the plan (one pinned H2D copy) and launch K2b (marks) then K1 (append)."""
+        n_new, m, k = len(plan.new_frame_pos), plan.count, len(plan.marks)
+        if n_new == 0 and m == 0 and k == 0:
+            return
+        on_device = flat_frames.is_cuda
+        F = self.F
+        sec = [0]
+        for nbytes in ((0 if on_device else n_new * F), n_new * 4, m * _lib.A0_REC_META_I32 * 4, k * 4):
+            sec.append(sec[-1] + ((nbytes + 255) // 256) * 256)
+        turn, (pin, dev) = self._stage(sec[-1])
+        pin_np = pin.numpy()
+        if n_new and not on_device:
+            src = flat_frames.numpy()
+            np.take(src, plan.new_frame_src, axis=0, out=pin_np[sec[0]:sec[0] + n_new * F].reshape(n_new, F))
+        pin_np[sec[1]:sec[1] + n_new * 4].view(np.int32)[:] = plan.new_frame_pos
+        pin_np[sec[2]:sec[2] + m * _lib.A0_REC_META_I32 * 4].view(np.int32)[:] = plan.rec_meta.reshape(-1)
+        pin_np[sec[3]:sec[3] + k * 4].view(np.int32)[:] = plan.marks
+        with torch.cuda.device(self.device):
+            dev[:sec[-1]].copy_(pin[:sec[-1]], non_blocking=True)
+            stream = _lib.stream_ptr(self.device)
+            base = dev.data_ptr()
+            if on_device and n_new:
+                src_idx = torch.from_numpy(plan.new_frame_src).to(self.device, non_blocking=True)
+                staged = flat_frames.index_select(0, src_idx) if not _is_arange(plan.new_frame_src, flat_frames.shape[0]) \
+                    else flat_frames
+                staged = staged.contiguous()
+                frames_ptr = staged.data_ptr()
+            else:
+                staged = None
+                frames_ptr = base + sec[0]
+            if k:
+                _lib.check(self.lib.a0_pt_mark(self.h, base + sec[3], k, self.alpha, stream), "a0_pt_mark")
+            _lib.check(self.lib.a0_rb_append(self.h, frames_ptr if n_new else None, base + sec[1] if n_new else None,
+                                             n_new, base + sec[2] if m else None, m, stream), "a0_rb_append")
+            evt = torch.cuda.Event()
+            evt.record()
+            self._staging_evt[turn] = evt
+            if staged is not None:
+                staged.record_stream(torch.cuda.current_stream(self.device))
+
+    # ------------------------------------------------------------------ sample / gather
+    def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None):
+        """Draw ``k_batches`` stratified batches (K2a) and gather them (K3).  ``u`` (f32 device
+        tensor of k*B uniforms) or ``indices`` (i64, explicit record positions) make the draw
+        reproducible for parity tests; otherwise uniforms come from torch's CUDA generator."""
+        B = int(batch_size or self.cfg.learner.batch_size)
+        total = B * int(k_batches)
+        dev = self.device
+        if self.index.top <= 0:
+            raise RuntimeError("sample() on an empty replay shard")
+        with torch.cuda.device(dev):
+            stream = _lib.stream_ptr(dev)
+            weights = torch.empty(total, dtype=torch.float32, device=dev)
+            prio = torch.empty(total, dtype=torch.float32, device=dev)
+            if indices is None:
+                if u is None:
+                    u = torch.rand(total, dtype=torch.float32, device=dev, generator=generator)
+                idx = torch.empty(total, dtype=torch.int64, device=dev)
+                sum_offset = float(self.size - self.index.top) if self.compat_sum else 0.0
+                _lib.check(self.lib.a0_pt_sample(
+                    self.h, _lib.ptr(u, torch.float32), total, B, float(self.index.top), float(self.beta),
+                    sum_offset, 0 if self.prioritize else 1, _lib.ptr(idx), _lib.ptr(prio), _lib.ptr(weights),
+                    stream), "a0_pt_sample")
+            else:
+                idx = indices.to(device=dev, dtype=torch.int64).contiguous()
+                total = idx.numel()
+                prio = self.tree[self.P + idx]
+                weights = self.is_weights(prio, B) if self.prioritize else torch.ones_like(prio)
+            return self.gather(idx, prio, weights)
+
+    def gather(self, idx, prio=None, weights=None):
+        dev = self.device
+        total = idx.numel()
+        with torch.cuda.device(dev):
+            frames = torch.empty((total, 8 * self.F), dtype=torch.uint8, device=dev)
+            act = torch.empty(total, dtype=torch.int64, device=dev)
+            r64 = torch.empty(total, dtype=torch.float64, device=dev)
+            r32 = torch.empty(total, dtype=torch.float32, device=dev)
+            d8 = torch.empty(total, dtype=torch.bool, device=dev)
+            d32 = torch.empty(total, dtype=torch.float32, device=dev)
+            boot = torch.empty(total, dtype=torch.int64, device=dev)
+            _lib.check(self.lib.a0_rb_gather(
+                self.h, _lib.ptr(idx, torch.int64), total, self.n_gather, self.gamma, frames.data_ptr(),
+                act.data_ptr(), r64.data_ptr(), r32.data_ptr(), d8.data_ptr(), d32.data_ptr(), boot.data_ptr(),
+                self.gather_variant, _lib.stream_ptr(dev)), "a0_rb_gather")
+        return Batch(frames, act, r64, d8, prio, idx, weights, r32, d32, boot)
+
+    def is_weights(self, prio, batch):
+        """trainer.py:91-94 with torch ops (used only when indices are given explicitly; the
+        sampled path gets its weights from the K2a epilogue)."""
+        w = (self.index.top * (prio / self.priority_sum())).pow(-self.beta).view(-1, batch)
+        return (w / (w.max(dim=1, keepdim=True)[0] + 1e-8)).view(-1)
+
+    # ------------------------------------------------------------------ priorities
+    def update_priority(self, ids, priorities):
+        """replay.py:55-59: priority[ids] = (loss+eps)^alpha; max_p = max(max_p, loss.max()).
+        Device tensors stay on the device (no sync); host tensors are copied asynchronously."""
+        if not self.prioritize or priorities is None:
+            return
+        dev = self.device
+        ids = torch.as_tensor(ids).to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        loss = torch.as_tensor(priorities).to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.a0_pt_update(self.h, ids.data_ptr(), loss.data_ptr(), ids.numel(), self.alpha,
+                                             self.eps, _lib.stream_ptr(dev)), "a0_pt_update")
+
+    def set_priorities(self, ids, values):
+        dev = self.device
+        ids = torch.as_tensor(ids).to(device=dev, dtype=torch.int64).contiguous()
+        values = torch.as_tensor(values).to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.a0_pt_set(self.h, ids.data_ptr(), values.data_ptr(), ids.numel(),
+                                          _lib.stream_ptr(dev)), "a0_pt_set")
+
+
+def _is_arange(a, n):
+    return len(a) == n and (n == 0 or (a[0] == 0 and a[-1] == n - 1 and bool((np.diff(a) == 1).all())))
+
+
+def _liblz4_block_decompress(blob):
+    """python-lz4 block format (4-byte little-endian size prefix + raw LZ4 block) via the system
+    liblz4, for blobs produced by the reference actor's lz4.block.compress (agent.py:80) when the
+    python package is absent."""
+    lib = _liblz4_block_decompress.lib
+    if lib is None:
+        lib = _liblz4_block_decompress.lib = C.CDLL("liblz4.so.1")
+        lib.LZ4_decompress_safe.restype = C.c_int
+        lib.LZ4_decompress_safe.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    size = int.from_bytes(blob[:4], "little")
+    out = C.create_string_buffer(size)
+    n = lib.LZ4_decompress_safe(bytes(blob[4:]), out, len(blob) - 4, size)
+    if n != size:
+        raise RuntimeError("lz4 block decompression failed")
+    return out.raw
+
+
+_liblz4_block_decompress.lib = None

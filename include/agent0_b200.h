@@ -1,0 +1,170 @@
+/*
+ * agent0_b200 -- C ABI of the B200-native replay-and-target path for zhoubin-me/agent0's deepq.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch types), launches on
+ * the caller's CUDA stream, never synchronises and never allocates on the hot path.  Return value:
+ * 0 on success, a positive cudaError_t on a CUDA failure, a negative A0_E* code on a bad argument;
+ * a0_last_error() gives the message of the calling thread's last failure.
+ *
+ * All `const T* x /\* dev *\/` arguments are DEVICE pointers; batch outputs are caller-allocated.
+ * The ring, the records and the sum-tree are owned by the handle (cudaMalloc once, in a0_rb_create).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   agent0/deepq/replay.py:15-27   ReplayDataset.__init__          -> a0_rb_create / a0_rb_destroy
+ *   agent0/deepq/replay.py:45-53   ReplayDataset.extend            -> a0_rb_append + a0_pt_mark
+ *   agent0/deepq/replay.py:39-43   ReplayDataset.__iter__ (draw)   -> a0_pt_sample
+ *   agent0/deepq/replay.py:32-37   ReplayDataset.__getitem__ + default_collate, and
+ *   agent0/deepq/agent.py:64-73    Actor.sample's n-step tracker   -> a0_rb_gather
+ *   agent0/deepq/trainer.py:91-94  IS weights in Trainer.step      -> a0_pt_sample (epilogue)
+ *   agent0/deepq/replay.py:55-59   ReplayDataset.update_priority   -> a0_pt_update
+ *   agent0/deepq/agent.py:173-190  DQNLearner.train_step           -> a0_loss_dqn
+ *   agent0/deepq/agent.py:194-215  MDQNLearner.train_step          -> a0_loss_mdqn
+ *   agent0/deepq/agent.py:219-269  C51Learner.train_step           -> a0_loss_c51
+ *   agent0/deepq/agent.py:110-114,273-327 huber_qr_loss, QR/IQN    -> a0_loss_quantile
+ *   agent0/deepq/agent.py:340-388  FQFLearner.train_step           -> a0_loss_quantile (+fraction)
+ */
+#ifndef AGENT0_B200_H
+#define AGENT0_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct a0_replay a0_replay_t;    /* opaque shard handle */
+typedef void* a0_stream_t;               /* cudaStream_t */
+
+#define A0_OK 0
+#define A0_EINVAL (-1)
+#define A0_ENOMEM (-2)
+#define A0_STACK 4          /* frames per observation stack (FrameStack(4), atari_wrappers.py:62) */
+#define A0_SLOTS 8          /* obs stack + next-obs stack */
+#define A0_MAX_NSTEP 16
+#define A0_MAX_ACTIONS 32
+#define A0_MAX_QUANTILES 256
+#define A0_REC_META_I32 14  /* int32 words per appended record, see a0_rb_append */
+
+int a0_version(void);
+const char* a0_last_error(void);
+
+/* ---- shard lifetime -------------------------------------------------------------------------
+ * rec_capacity   transitions kept (cfg.replay.size); indices returned by a0_pt_sample are record
+ *                ring positions in [0, rec_capacity)
+ * frame_capacity 84x84 frames kept in the HBM frame ring (>= rec_capacity + slack)
+ * frame_bytes    bytes per frame, a multiple of 16 (84*84 = 7056 = 441*16)                    */
+int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t frame_capacity,
+                 int32_t frame_bytes, int32_t device);
+int a0_rb_destroy(a0_replay_t* h);
+/* zero the tree, max_p = 1 (ReplayDataset.__init__: priority state, replay.py:19-27) */
+int a0_rb_reset(a0_replay_t* h, a0_stream_t stream);
+
+/* device pointers to handle-owned state (tests, checkpointing, zero-copy views) */
+enum { A0_PTR_FRAMES = 0, A0_PTR_REC_SLOTS = 1, A0_PTR_REC_INFO = 2, A0_PTR_TREE = 3,
+       A0_PTR_MAX_P = 4 };
+void* a0_rb_ptr(a0_replay_t* h, int32_t which);
+int64_t a0_rb_tree_leaves(a0_replay_t* h);      /* P = next_pow2(rec_capacity) */
+
+/* ---- K1: append ---------------------------------------------------------------------------------
+ * Copies n_new staged frames into the ring with coalesced 16-byte stores and scatters m records.
+ * new_frames    [n_new][frame_bytes]  staged frames (device)
+ * new_frame_pos [n_new]               destination frame-ring positions
+ * rec_meta      [m][14] int32   {pos, link_from, link_to, action_done, slot[8], reward_lo, reward_hi}
+ *                 pos         record ring position to write
+ *                 link_from   position of the previous record of the same stream, written by an
+ *                             EARLIER append, whose successor link must now point at `pos` (-1: none)
+ *                 link_to     position of the next record of the same stream when it is part of
+ *                             this same append (-1: not known yet)
+ *                 action_done action | done << 31
+ *                 slot[0..3]  frame positions of the observation stack, slot[4..7] of the next one
+ *                 reward      float64 bit pattern (the reference keeps rewards in float64)       */
+int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames /* dev */,
+                 const int32_t* new_frame_pos /* dev */, int32_t n_new,
+                 const int32_t* rec_meta /* dev */, int32_t m, a0_stream_t stream);
+
+/* ---- K2b: sum-tree leaf writes ---------------------------------------------------------------------
+ * a0_pt_mark: pos[k] >= 0 -> leaf = max_p^alpha (a newly sampleable record, replay.py:52);
+ *             pos[k] <  0 -> leaf ~pos[k] = 0   (a record whose frames are being overwritten).
+ * a0_pt_update: leaf[idx[k]] = (loss[k]+eps)^alpha, max_p = max(max_p, max loss) (replay.py:55-59);
+ *             duplicated indices: the last one wins, as in `priority[ids] = ...` on the CPU;
+ *             indices whose leaf is currently 0 (evicted since they were sampled) are skipped.
+ * a0_pt_set:  leaf[idx[k]] = value[k] (restore / tests).
+ * All three recompute every touched ancestor as fl32(left+right), level by level.               */
+int a0_pt_mark(a0_replay_t* h, const int32_t* pos /* dev */, int32_t count, float alpha,
+               a0_stream_t stream);
+int a0_pt_update(a0_replay_t* h, const int64_t* idx /* dev */, const float* loss /* dev */,
+                 int32_t count, float alpha, float eps, a0_stream_t stream);
+int a0_pt_set(a0_replay_t* h, const int64_t* idx /* dev */, const float* value /* dev */,
+              int32_t count, a0_stream_t stream);
+
+/* ---- K2a: batched stratified prioritized draws + IS weights ------------------------------------------
+ * total = k_batches * batch draws; draw j of a batch uses t = ((j + u)/batch) * root and descends
+ * the tree (warp-cooperative, five levels per memory round trip).  Epilogue (trainer.py:91-94):
+ *   w = (top * p / (root + sum_offset))^(-beta);  w /= max_over_the_batch(w) + 1e-8
+ * uniform != 0 writes w = 1 (ReplayEnum.uniform: weights = priorities = 1, trainer.py:95-96).
+ * sum_offset reproduces the reference's denominator over never-written slots when the
+ * caller asks for compat mode; 0 otherwise.                                                     */
+int a0_pt_sample(a0_replay_t* h, const float* u /* dev [total] */, int32_t total, int32_t batch,
+                 float top, float beta, float sum_offset, int32_t uniform,
+                 int64_t* idx_out /* dev [total] */, float* prio_out /* dev [total] */,
+                 float* weight_out /* dev [total] */, a0_stream_t stream);
+
+/* ---- K3: fused gather ---------------------------------------------------------------------------------
+ * For each sampled record position: walk n_step-1 successor links, rebuild the two 4-frame stacks
+ * (each distinct frame is read from HBM once and written to every place it appears), and compute
+ *   Rn = sum_i gamma^i prod_{j<i}(1-d_j) r_i   in float64, Horner newest->oldest, separately rounded
+ *        mul/mul/add (agent.py:65-69), Dn = OR d_i, boot = position of the record that follows the
+ *        window (-1 if not appended yet).
+ * frames_out [count][8][frame_bytes]: the reference's `frames` layout, concat(st, st_next)
+ * (agent.py:80); action i64; reward f64 and f32; done u8 and f32; boot i64.  Any output but
+ * frames_out may be NULL.  variant: 0 = TMA bulk copies through shared memory, 1 = LDG/STG.      */
+int a0_rb_gather(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count, int32_t n_step,
+                 double gamma, uint8_t* frames_out, int64_t* action_out, double* reward64_out,
+                 float* reward32_out, uint8_t* done8_out, float* done32_out, int64_t* boot_out,
+                 int32_t variant, a0_stream_t stream);
+
+/* ---- K4: fused target + loss + IS weighting + new priority -----------------------------------------------
+ * Common arguments: B samples; A actions; action i64[B]; reward f32[B] (n-step return); done f32[B]
+ * in {0,1}; weight f32[B]; gamma_n = float(discount**n_step).  Outputs: loss f32[B] (unweighted,
+ * what the reference returns as q_loss), grad = d[(loss*weight).sum()]/d[online output] (same
+ * shape as the online output, zero outside the taken action), prio f32[B] = (loss+eps)^alpha,
+ * and *max_p = max(*max_p, loss) when max_p != NULL.  qsel f32[B,A] are the action-selection
+ * values (model.qval(next_obs) under double_q); NULL selects from the target output itself.      */
+typedef struct {
+  int32_t B, A;
+  const int64_t* action;
+  const float* reward;
+  const float* done;
+  const float* weight;
+  float gamma_n;
+  float alpha, eps;      /* priority exponent and offset (ReplayConfig) */
+  float* loss;
+  float* prio;           /* may be NULL */
+  float* max_p;          /* may be NULL */
+} a0_loss_common_t;
+
+/* q, qt_next, grad: f32[B,A] */
+int a0_loss_dqn(const a0_loss_common_t* c, const float* q, const float* qt_next, const float* qsel,
+                float* grad, a0_stream_t stream);
+/* qt_next = target(next_obs), qt_cur = target(obs): f32[B,A] */
+int a0_loss_mdqn(const a0_loss_common_t* c, const float* q, const float* qt_next,
+                 const float* qt_cur, float tau, float lo, float* grad, a0_stream_t stream);
+/* logits, tgt_logits, grad: f32[B,A,M]; atoms f32[M]; target_prob (optional) f32[B,M] */
+int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const float* tgt_logits,
+                const float* qsel, const float* atoms, int32_t M, float vmin, float vmax,
+                float* grad, float* target_prob, a0_stream_t stream);
+/* Quantile-Huber family.  layout 0: q f32[B,A,Nj], qt f32[B,A,Ni], taus implicit (2j+1)/2Nj (QR).
+ * layout 1: q f32[B,Nj,A], qt f32[B,Ni,A], taus f32[B,Nj] (IQN, FQF).
+ * FQF fraction term (optional, layout 1, Ni == Nj == F): q_bar f32[B,F-1,A] = quantile values at the
+ * interior fractions, taus_full f32[B,F+1]; outputs fraction_loss f32[B] and grad_taus f32[B,F+1]
+ * = d[(fraction_loss*weight).sum()]/d taus_full.                                                 */
+int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const float* q, const float* qt,
+                     const float* taus, const float* qsel, int32_t Ni, int32_t Nj, float* grad,
+                     const float* q_bar, const float* taus_full, float* fraction_loss,
+                     float* grad_taus, a0_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGENT0_B200_H */

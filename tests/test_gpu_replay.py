@@ -1,0 +1,227 @@
+"""K1/K2/K3 parity on the GPU through the C ABI (via agent0_b200.replay.ReplayDataset).
+
+Bit-exact: gathered uint8 stacks, actions, n-step returns (float64 bits), done flags, bootstrap
+indices, sampled indices and the whole sum-tree.  <=1e-5 relative: IS weights, priorities."""
+import numpy as np
+import pytest
+import torch
+
+from agent0_b200.config import make_config
+from agent0_b200.synth import record_stream
+from oracle import reference_replay as OR
+from oracle.sumtree import SumTree, new_priority
+
+pytestmark = pytest.mark.gpu
+FG = 84 * 84
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _replay(size, n=1, per=True, native=False, E=3, **kw):
+    from agent0_b200.replay import ReplayDataset
+    cfg = make_config("c51", per=per, n_step=n, batch_size=8, replay_size=size, num_envs=E)
+    cfg.trainer.total_steps = 1000
+    return ReplayDataset(cfg, native_nstep=native, **kw)
+
+
+def _tuples(g, lo, hi):
+    return [(g["entry_frames"][i].tobytes(), g["entry_action"][i], g["entry_reward"][i], g["entry_done"][i])
+            for i in range(lo, hi)]
+
+
+@pytest.mark.parametrize("n", [1, 3])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_extend_then_gather_equals_reference_getitem(golden, n, variant):
+    """ReplayDataset.extend(reference tuples) -> gather(i) == reference replay[i] (replay.py:32-37)."""
+    g = golden(f"replay_n{n}")
+    M = len(g["entry_action"])
+    rp = _replay(256, n=n, gather_variant=variant)
+    for lo in range(0, M, 45):
+        rp.extend(_tuples(g, lo, min(M, lo + 45)))
+    assert len(rp) == rp.top == M
+    b = rp.gather(torch.arange(M, device="cuda"))
+    assert np.array_equal(_np(b.frames), g["entry_frames"])
+    assert np.array_equal(_np(b.actions), g["entry_action"])
+    assert np.array_equal(_np(b.rewards).view(np.int64), g["entry_reward"].view(np.int64))
+    assert np.array_equal(_np(b.terminals), g["entry_done"])
+    assert np.array_equal(_np(b.rewards_f32), g["entry_reward"].astype(np.float32))
+    assert np.array_equal(_np(b.terminals_f32), g["entry_done"].astype(np.float32))
+    assert b.frames.dtype == torch.uint8 and b.actions.dtype == torch.int64
+    assert b.rewards.dtype == torch.float64 and b.terminals.dtype == torch.bool
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_native_nstep_gather_equals_reference_actor_entries(golden, n):
+    """Raw 1-step transitions in; K3 folds n steps: must equal Actor.sample's entries
+    (agent.py:64-81) under the Appendix-C index mapping."""
+    g = golden(f"replay_n{n}")
+    E, T = int(g["num_envs"]), int(g["steps"])
+    obs = g["stream_obs"]
+    done = OR.done_rule(g["stream_terminal"], g["stream_life_loss"], g["stream_truncated"])
+    for variant in (0, 1):
+        rp = _replay(256, n=n, native=True, E=E, gather_variant=variant)
+        for k in range(T):
+            rp.append_vector_step(obs[k], g["stream_action"][k], g["stream_reward"][k], done[k], obs[k + 1])
+        assert rp.top == (T - n + 1) * E
+        ks, es = np.meshgrid(np.arange(n - 1, T), np.arange(E), indexing="ij")
+        ref_i = (ks * E + es).reshape(-1)
+        pos = ((ks - n + 1) * E + es).reshape(-1)
+        b = rp.gather(torch.as_tensor(pos, device="cuda"))
+        assert np.array_equal(_np(b.frames), g["entry_frames"][ref_i])
+        assert np.array_equal(_np(b.actions), g["entry_action"][ref_i])
+        assert np.array_equal(_np(b.rewards).view(np.int64), g["entry_reward"][ref_i].view(np.int64))
+        assert np.array_equal(_np(b.terminals), g["entry_done"][ref_i])
+        boot = np.where(ks + 1 < T, (ks + 1) * E + es, -1).reshape(-1)
+        assert np.array_equal(_np(b.boot_indices), boot)
+
+
+def test_device_resident_native_ingest_and_wraparound():
+    """Frames already on the GPU, ring smaller than the stream: every sampleable record must
+    gather what the brute-force history says (oracle pack_nstep), TMA and LDG variants alike."""
+    E, T, n = 4, 90, 3
+    s = record_stream(E, T, seed=77, p_terminal=0.05, p_life_loss=0.05, p_truncated=0.03)
+    fr_ref, a_ref, r_ref, d_ref = OR.pack_nstep(s["obs"], s["action"], s["reward"], s["done"], n, 0.99)
+    from agent0_b200.ring_index import stack_delta
+    rp = _replay(96, n=n, native=True, E=E, frame_capacity=400, age_limit=32)
+    rp.reset_streams(np.arange(E), torch.as_tensor(s["obs"][0]).cuda())
+    for k in range(T):
+        kk = stack_delta(s["obs"][k], s["obs"][k + 1])
+        new = np.concatenate([s["obs"][k + 1][e, 4 - kk[e]:] for e in range(E)])
+        rp.append_steps(np.arange(E), kk, torch.as_tensor(new).cuda(), s["action"][k], s["reward"][k], s["done"][k])
+    ix = rp.index
+    assert ix.tail_q > 0
+    leaves = _np(rp.priority.leaves())
+    live = np.flatnonzero(leaves > 0)
+    assert len(live) == rp.top and np.array_equal(live, np.flatnonzero(ix.sampleable))
+    q = ix.head_q - 1 - ((ix.head_q - 1 - live) % rp.size)
+    k0, e = np.divmod(q, E)
+    ref_i = (k0 + n - 1) * E + e
+    for variant in (0, 1):
+        rp.gather_variant = variant
+        b = rp.gather(torch.as_tensor(live, device="cuda"))
+        assert np.array_equal(_np(b.frames), fr_ref[ref_i])
+        assert np.array_equal(_np(b.rewards).view(np.int64), r_ref[ref_i].view(np.int64))
+        assert np.array_equal(_np(b.terminals), d_ref[ref_i]) and np.array_equal(_np(b.actions), a_ref[ref_i])
+
+
+def test_sumtree_sample_update_bit_exact():
+    """K2a/K2b against oracle/sumtree.py: same leaves, same uniforms -> identical indices and an
+    identical tree, node for node."""
+    N = 5000
+    rp = _replay(N, per=True)
+    rng = np.random.RandomState(0)
+    pr = ((np.abs(rng.randn(N)) + 0.01) ** 0.5).astype(np.float32)
+    pr[rng.rand(N) < 0.3] = 0.0
+    ref = SumTree(N)
+    ref.set(np.arange(N), pr)
+    rp.set_priorities(torch.arange(N), torch.as_tensor(pr))
+    assert np.array_equal(_np(rp.tree)[:2 * ref.P], ref.nodes)
+    rp.index.top = int((pr > 0).sum())
+    for B, K in ((32, 1), (512, 1), (32, 20), (7, 3)):
+        u = rng.rand(B * K).astype(np.float32)
+        idx = torch.empty(B * K, dtype=torch.int64, device="cuda")
+        prio = torch.empty(B * K, device="cuda"); w = torch.empty(B * K, device="cuda")
+        from agent0_b200 import _lib
+        u_dev = torch.as_tensor(u).cuda()
+        _lib.check(rp.lib.a0_pt_sample(rp.h, u_dev.data_ptr(), B * K, B, float(rp.top), 0.6,
+                                       0.0, 0, idx.data_ptr(), prio.data_ptr(), w.data_ptr(),
+                                       _lib.stream_ptr()), "a0_pt_sample")
+        for k in range(K):
+            ridx, rprio = ref.sample_stratified(u[k * B:(k + 1) * B])
+            assert np.array_equal(_np(idx)[k * B:(k + 1) * B], ridx)
+            assert np.array_equal(_np(prio)[k * B:(k + 1) * B], rprio)
+            rw = OR.is_weights(rprio, ref.root, rp.top, 0.6)
+            np.testing.assert_allclose(_np(w)[k * B:(k + 1) * B], rw, rtol=1e-5)
+        assert (_np(prio) > 0).all()
+    # priority update with duplicates (last writer wins), evicted leaves skipped, max_p tracking
+    ids = rng.randint(0, N, 700).astype(np.int64)
+    ids[100:110] = ids[0]
+    loss = (np.abs(rng.randn(700)) * 3).astype(np.float32)
+    rp.update_priority(torch.as_tensor(ids), torch.as_tensor(loss))
+    newp = new_priority(loss, 0.01, 0.5)
+    keep = ref.leaves()[ids] > 0
+    ref.set(ids[keep], newp[keep])
+    assert np.array_equal(_np(rp.tree)[:2 * ref.P], ref.nodes)
+    assert rp.max_p == pytest.approx(max(1.0, float(loss.max())), rel=1e-7)
+    # the law: empirical draw frequencies follow p_i / sum p (the reference's multinomial law)
+    counts = np.zeros(N)
+    for _ in range(40):
+        b = rp.sample(512, k_batches=4)
+        np.add.at(counts, _np(b.indices), 1)
+    law = ref.leaves().astype(np.float64); law /= law.sum()
+    assert np.corrcoef(counts / counts.sum(), law)[0, 1] > 0.95
+
+
+def test_per_bookkeeping_new_entries_beta_and_compat_sum(golden):
+    """extend(): new records get max_p^alpha, beta follows LinearSchedule, IS weights follow
+    trainer.py:91-94 (with the reference's all-slots denominator when compat_sum=True)."""
+    g = golden("replay_n1")
+    rp = _replay(256, per=True, compat_sum=True)
+    assert rp.beta == 0.4
+    rp.extend(_tuples(g, 0, 30))
+    assert rp.beta == 0.4                                   # value before advancing (replay.py:53)
+    leaves = _np(rp.priority.leaves())
+    assert (leaves[:30] == 1.0).all() and (leaves[30:] == 0).all()
+    loss = np.linspace(0.5, 9.0, 30).astype(np.float32)
+    rp.update_priority(torch.arange(30), torch.as_tensor(loss))
+    rp.extend(_tuples(g, 30, 50))
+    assert rp.beta == pytest.approx(0.4 + 0.6 / 1000 * 30)
+    leaves = _np(rp.priority.leaves())
+    np.testing.assert_allclose(leaves[:30], new_priority(loss, 0.01, 0.5), rtol=1e-6)
+    np.testing.assert_allclose(leaves[30:50], np.sqrt(np.float32(9.0)), rtol=1e-6)    # max_p ** alpha
+    u = torch.rand(8, device="cuda")
+    b = rp.sample(8, u=u)
+    sum_all = leaves.sum() + (256 - 50)                     # never-written slots hold 1.0
+    w = OR.is_weights(_np(b.priorities), sum_all, 50, rp.beta)
+    np.testing.assert_allclose(_np(b.weights), w, rtol=1e-5)
+    assert np.array_equal(_np(b.priorities), leaves[_np(b.indices)])
+
+
+def test_uniform_policy_weights_are_one(golden):
+    g = golden("replay_n1")
+    rp = _replay(256, per=False)
+    rp.extend(_tuples(g, 0, 60))
+    b = rp.sample(16, k_batches=2)
+    assert (_np(b.weights) == 1.0).all() and (_np(b.priorities) == 1.0).all()
+    assert _np(b.indices).max() < 60
+    rp.update_priority(b.indices, torch.rand(32))           # no-op for uniform replay
+    assert (_np(rp.priority.leaves())[:60] == 1.0).all()
+
+
+def test_trainer_step_golden_weights_and_priorities(golden):
+    """The reference's real Trainer.step (C51, PER, n=3): same indices -> same batch fields, IS
+    weights and priorities after update_priority."""
+    g = golden("trainer_step")
+    s = record_stream(int(g["num_envs"]), int(g["steps"]), seed=int(g["seed"]), p_terminal=0.05,
+                      p_life_loss=0.05, p_truncated=0.03)
+    fr, a, r, d = OR.pack_nstep(s["obs"], s["action"], s["reward"], s["done"], int(g["n_step"]), 0.99)
+    # the reference deque (maxlen 64) dropped the oldest 26 of the 90 entries
+    drop = len(a) - 64
+    rp = _replay(64, per=True, compat_sum=True, frame_capacity=2048)
+    rp.extend([(fr[i].tobytes(), a[i], r[i], d[i]) for i in range(drop, len(a))])
+    assert rp.top == int(g["top"])
+    for it in range(len(g["batches"])):
+        idx = g["batches"][it] % rp.top
+        b = rp.sample(8, indices=torch.as_tensor(idx))
+        np.testing.assert_allclose(_np(b.weights), g["weights"][it], rtol=1e-5)
+        assert np.array_equal(_np(b.rewards_f32), g["rewards"][it])
+        assert np.array_equal(_np(b.terminals_f32), g["dones"][it])
+        assert np.array_equal(_np(b.actions).astype(np.float32), g["actions"][it])
+        assert np.array_equal(_np(b.frames).astype(np.uint64).sum(axis=1), g["frames_crc"][it])
+        rp.update_priority(b.indices, torch.as_tensor(g["q_loss"][it]))
+        np.testing.assert_allclose(_np(rp.priority.leaves()), g["prio_after"][it], rtol=1e-5)
+        assert rp.max_p == pytest.approx(float(g["max_p_after"][it]), rel=1e-6)
+
+
+def test_empty_and_error_paths():
+    from agent0_b200 import _lib
+    rp = _replay(64)
+    rp.extend([])
+    with pytest.raises(RuntimeError):
+        rp.sample(4)
+    lib = _lib.load()
+    assert lib.a0_rb_gather(rp.h, None, 4, 1, 0.99, None, None, None, None, None, None, None, 0, None) != 0
+    assert b"required" in lib.a0_last_error()
+    assert lib.a0_rb_gather(rp.h, None, 0, 1, 0.99, None, None, None, None, None, None, None, 0, None) == 0
