@@ -18,18 +18,15 @@ def done_rule(terminal, life_loss, truncated):
     return np.logical_and(np.logical_or(terminal, life_loss), np.logical_not(truncated))
 
 
-def pack_nstep(obs, action, reward, done, n_step, discount):
-    """Restates the tracker loop of Actor.sample (agent.py:64-81).
+def pack_nstep_iter(obs, action, reward, done, n_step, discount):
+    """Restates the tracker loop of Actor.sample (agent.py:64-81), one outer step at a time.
 
-    obs[k] u8[E,4,H,W] is the stack before outer step k (len steps+1); action/reward/done
-    are per step [steps,E].  Returns the reference's ``data`` list layout as arrays, entry
-    i = k*E + e (step-major, env-minor): frames u8[M, 8*H*W] = concat(st, st_next),
-    action i64[M], reward f64[M] (n-step return), done bool[M] (OR over the window).
+    obs[k] u8[E,4,H,W] is the stack before outer step k (len steps+1); action/reward/done are per
+    step [steps,E].  Yields, per step k, (st u8[E,4,H,W], at i64[E], Rn f64[E], Dn bool[E],
+    st_next u8[E,4,H,W]) - the five things the reference zips into entries (agent.py:78-81).
     """
-    steps, E = action.shape
     tracker = deque(maxlen=n_step)
-    frames, acts, rews, dones = [], [], [], []
-    for k in range(steps):
+    for k in range(action.shape[0]):
         tracker.append((obs[k], action[k], reward[k], done[k]))
         r_n = np.zeros_like(reward[k])
         d_n = np.zeros_like(reward[k], dtype=np.bool_)
@@ -37,9 +34,17 @@ def pack_nstep(obs, action, reward, done, n_step, discount):
             d_n = np.logical_or(d_n, dt)
             # float64, three separately rounded ops, newest -> oldest (agent.py:69)
             r_n = r_n * discount * (1 - dt) + rt
-        st, at = tracker[0][0], tracker[0][1]
-        for e in range(E):
-            frames.append(np.concatenate((st[e], obs[k + 1][e]), axis=0).reshape(-1))
+        yield tracker[0][0], tracker[0][1], r_n, d_n, obs[k + 1]
+
+
+def pack_nstep(obs, action, reward, done, n_step, discount):
+    """All entries of pack_nstep_iter in the reference's ``data`` list order, entry i = k*E + e
+    (step-major, env-minor): frames u8[M, 8*H*W] = concat(st, st_next), action i64[M],
+    reward f64[M] (n-step return), done bool[M] (OR over the window)."""
+    frames, acts, rews, dones = [], [], [], []
+    for st, at, r_n, d_n, st_next in pack_nstep_iter(obs, action, reward, done, n_step, discount):
+        for e in range(action.shape[1]):
+            frames.append(np.concatenate((st[e], st_next[e]), axis=0).reshape(-1))
             acts.append(at[e]); rews.append(r_n[e]); dones.append(d_n[e])
     return (np.stack(frames), np.array(acts, dtype=np.int64),
             np.array(rews, dtype=np.float64), np.array(dones, dtype=np.bool_))
