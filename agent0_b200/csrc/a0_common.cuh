@@ -15,6 +15,8 @@ struct __align__(16) A0RecInfo {
   int32_t link;          // ring position of the next record of the same stream, -1 if none yet
 };
 
+constexpr int A0_MAX_BATCHES = 4096;   // batches per a0_pt_sample call
+
 struct a0_replay {
   int32_t device;
   int64_t N;             // record capacity
@@ -28,7 +30,8 @@ struct a0_replay {
   float* tree;           // [2P], node 1 = root, leaf j at P + j
   float* max_p;          // device scalar
   int32_t* winner;       // [N] scratch for last-writer-wins, kept at -1 between calls
-  unsigned int* counter; // last-block-done ticket for the sampler epilogue
+  int32_t* dirty;        // [P >> 12] chunk needs its sub-tree recomputed
+  unsigned int* counter; // [A0_MAX_BATCHES] per-batch tickets of the sampler epilogue, +1 rebuild ticket
 };
 
 void a0_set_error(const char* fmt, ...);

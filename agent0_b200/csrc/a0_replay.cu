@@ -29,15 +29,13 @@ __global__ void a0_fill_i32(int32_t* p, int64_t n, int32_t v) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = v;
 }
-__global__ void a0_init_scalars(float* max_p, unsigned int* counter) {
-  *max_p = 1.0f;
-  *counter = 0u;
-}
+__global__ void a0_init_scalars(float* max_p) { *max_p = 1.0f; }
 
 extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t frame_capacity,
                             int32_t frame_bytes, int32_t device) {
   A0_REQUIRE(out != nullptr, "a0_rb_create: out is NULL");
-  A0_REQUIRE(rec_capacity >= 2 && rec_capacity <= (1LL << 30), "a0_rb_create: rec_capacity %lld out of range",
+  // 2^24: record positions survive the reference's .float() round trip of indices (trainer.py:88-90)
+  A0_REQUIRE(rec_capacity >= 2 && rec_capacity <= (1LL << 24), "a0_rb_create: rec_capacity %lld outside [2, 2^24]",
              (long long)rec_capacity);
   A0_REQUIRE(frame_capacity >= 8 && frame_capacity <= (1LL << 30), "a0_rb_create: frame_capacity %lld out of range",
              (long long)frame_capacity);
@@ -63,7 +61,8 @@ extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t fra
   alloc((void**)&h->tree, (size_t)2 * h->P * sizeof(float));
   alloc((void**)&h->max_p, 256);
   alloc((void**)&h->winner, (size_t)h->N * sizeof(int32_t));
-  alloc((void**)&h->counter, 256);
+  alloc((void**)&h->dirty, (size_t)((h->P >> 12) + 1) * sizeof(int32_t));
+  alloc((void**)&h->counter, (size_t)(A0_MAX_BATCHES + 64) * sizeof(unsigned int));
   if (e != cudaSuccess) {
     a0_set_error("a0_rb_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     a0_rb_destroy(h);
@@ -80,7 +79,7 @@ extern "C" int a0_rb_destroy(a0_replay_t* h) {
   if (!h) return A0_OK;
   A0DeviceGuard guard(h->device);
   cudaFree(h->frames); cudaFree(h->rec_slots); cudaFree(h->rec_info); cudaFree(h->tree);
-  cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->counter);
+  cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->dirty); cudaFree(h->counter);
   delete h;
   return A0_OK;
 }
@@ -94,7 +93,9 @@ extern "C" int a0_rb_reset(a0_replay_t* h, a0_stream_t stream_) {
   A0_CUDA(cudaMemsetAsync(h->rec_info, 0xff, (size_t)h->N * sizeof(A0RecInfo), stream));
   a0_fill_i32<<<256, 256, 0, stream>>>(h->winner, h->N, -1);
   A0_LAUNCH_CHECK();
-  a0_init_scalars<<<1, 1, 0, stream>>>(h->max_p, h->counter);
+  A0_CUDA(cudaMemsetAsync(h->dirty, 0, (size_t)((h->P >> 12) + 1) * sizeof(int32_t), stream));
+  A0_CUDA(cudaMemsetAsync(h->counter, 0, (size_t)(A0_MAX_BATCHES + 64) * sizeof(unsigned int), stream));
+  a0_init_scalars<<<1, 1, 0, stream>>>(h->max_p);
   A0_LAUNCH_CHECK();
   return A0_OK;
 }
@@ -239,11 +240,103 @@ __device__ __forceinline__ uint32_t a0_smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// Variant 0: one warp per sampled transition; lane 0 drives the TMA engine.  Every *distinct*
-// frame of the two stacks is fetched once with cp.async.bulk (global -> shared, completion on an
-// mbarrier) and written with cp.async.bulk (shared -> global) to every stack position it occupies:
-// (S+n)*F bytes read and 2S*F bytes written per transition, no register staging.
+// ---- TMA helpers (cp.async.bulk + mbarrier, SASS: UBLKCP / SYNCS) -------------------------------
+__device__ __forceinline__ void a0_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void a0_fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void a0_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void a0_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void a0_bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+
+// Distinct frames of the two stacks: uslot[u] = frame slot, dmask[u] = stack positions it fills.
+__device__ __forceinline__ int a0_unique_frames(const int32_t (&slot)[A0_SLOTS], int32_t (&uslot)[A0_SLOTS],
+                                                uint32_t (&dmask)[A0_SLOTS]) {
+  int U = 0;
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j) {
+    bool found = false;
+#pragma unroll
+    for (int u = 0; u < A0_SLOTS; ++u)
+      if (u < U && !found && uslot[u] == slot[j]) { dmask[u] |= 1u << j; found = true; }
+    if (!found) {
+#pragma unroll
+      for (int u = 0; u < A0_SLOTS; ++u)
+        if (u == U) { uslot[u] = slot[j]; dmask[u] = 1u << j; }
+      ++U;
+    }
+  }
+  return U;
+}
+
+// Variant 0 (default): one warp per sampled transition; lane 0 drives the TMA engine through a ring
+// of K3_RING frame buffers.  Every *distinct* frame of the two stacks is fetched once with
+// cp.async.bulk (global -> shared, completion on that buffer's mbarrier) and written with
+// cp.async.bulk (shared -> global) to every stack position it occupies: (S+n)*F bytes read and
+// 2S*F bytes written per transition, no register staging.  A buffer is refilled as soon as its
+// stores have read it, so 28 KB of shared memory per CTA is enough and 8 CTAs fit on an SM: a
+// 640-transition launch (20 batches of 32) is a single wave.
+constexpr int K3_RING = 4;
 __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
+  extern __shared__ __align__(128) uint8_t a0_smem[];
+  __shared__ __align__(8) uint64_t bars[K3_RING];
+  if (threadIdx.x != 0) return;
+  const int b = blockIdx.x;
+  int32_t slot[A0_SLOTS];
+  a0_resolve_window(g, b, slot);
+  const uint32_t F = (uint32_t)g.F;
+  int32_t uslot[A0_SLOTS];
+  uint32_t dmask[A0_SLOTS];
+  const int U = a0_unique_frames(slot, uslot, dmask);
+  const uint32_t bar0 = a0_smem_u32(&bars[0]);
+  const uint32_t buf0 = a0_smem_u32(a0_smem);
+#pragma unroll
+  for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
+  a0_fence_barrier_init();
+#pragma unroll
+  for (int u = 0; u < K3_RING; ++u)
+    if (u < U) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
+  uint8_t* out = g.frames_out + (size_t)b * A0_SLOTS * F;
+#pragma unroll
+  for (int u = 0; u < A0_SLOTS; ++u) {
+    if (u < U) {
+      const int r = u % K3_RING;
+      a0_mbar_wait(bar0 + 8 * r, (u / K3_RING) & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < A0_SLOTS; ++j)
+        if (dmask[u] & (1u << j)) a0_bulk_store(out + (size_t)j * F, buf0 + r * F, F);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (u + K3_RING < U) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        a0_bulk_load(buf0 + r * F, g.frames + (size_t)uslot[u + K3_RING] * F, F, bar0 + 8 * r);
+      }
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Variant 2: all (up to 8) distinct frames staged at once behind one mbarrier (56 KB of shared
+// memory, 4 CTAs per SM).  Kept as the measured alternative to the ring.
+__global__ void __launch_bounds__(32) a0_k3_gather_tma_full(const A0GatherArgs g) {
   extern __shared__ __align__(128) uint8_t a0_smem[];
   __shared__ __align__(8) uint64_t bar;
   if (threadIdx.x != 0) return;
@@ -251,52 +344,26 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   int32_t slot[A0_SLOTS];
   a0_resolve_window(g, b, slot);
   const uint32_t F = (uint32_t)g.F;
+  int32_t uslot[A0_SLOTS];
+  uint32_t dmask[A0_SLOTS];
+  const int U = a0_unique_frames(slot, uslot, dmask);
   const uint32_t bar_a = a0_smem_u32(&bar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  // distinct sources
-  int src_of[A0_SLOTS];
-  int n_unique = 0;
+  const uint32_t buf0 = a0_smem_u32(a0_smem);
+  a0_mbar_init(bar_a, (uint32_t)U);
+  a0_fence_barrier_init();
 #pragma unroll
-  for (int j = 0; j < A0_SLOTS; ++j) {
-    int s = -1;
-#pragma unroll
-    for (int k = 0; k < A0_SLOTS; ++k)
-      if (k < j && s < 0 && slot[k] == slot[j]) s = src_of[k];
-    if (s < 0) s = n_unique++;
-    src_of[j] = s;
-  }
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(F * (uint32_t)n_unique) : "memory");
-#pragma unroll
-  for (int j = 0; j < A0_SLOTS; ++j) {
-    bool first = true;
-#pragma unroll
-    for (int k = 0; k < A0_SLOTS; ++k)
-      if (k < j && slot[k] == slot[j]) first = false;
-    if (first) {
-      const uint8_t* src = g.frames + (size_t)slot[j] * F;
-      const uint32_t dst = a0_smem_u32(a0_smem + (size_t)src_of[j] * F);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst), "l"(src), "r"(F), "r"(bar_a) : "memory");
-    }
-  }
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
-  }
+  for (int u = 0; u < A0_SLOTS; ++u)
+    if (u < U) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar_a);
+  a0_mbar_wait(bar_a, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   uint8_t* out = g.frames_out + (size_t)b * A0_SLOTS * F;
 #pragma unroll
-  for (int j = 0; j < A0_SLOTS; ++j) {
-    const uint32_t src = a0_smem_u32(a0_smem + (size_t)src_of[j] * F);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(out + (size_t)j * F), "r"(src), "r"(F) : "memory");
-  }
+  for (int u = 0; u < A0_SLOTS; ++u)
+    if (u < U) {
+#pragma unroll
+      for (int j = 0; j < A0_SLOTS; ++j)
+        if (dmask[u] & (1u << j)) a0_bulk_store(out + (size_t)j * F, buf0 + u * F, F);
+    }
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -346,7 +413,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   A0_REQUIRE(idx && frames_out, "a0_rb_gather: idx and frames_out are required");
   A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_gather: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
   A0_REQUIRE(((uintptr_t)frames_out & 15) == 0, "a0_rb_gather: frames_out must be 16-byte aligned");
-  A0_REQUIRE(variant == 0 || variant == 1, "a0_rb_gather: unknown variant %d", variant);
+  A0_REQUIRE(variant >= 0 && variant <= 2, "a0_rb_gather: unknown variant %d", variant);
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   A0GatherArgs g;
@@ -354,14 +421,17 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
   g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
-  if (variant == 0) {
-    const size_t smem = (size_t)A0_SLOTS * h->F;
-    static thread_local size_t configured[64] = {0};
-    if (h->device < 64 && configured[h->device] < smem) {
-      A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[h->device] = smem;
+  if (variant == 0 || variant == 2) {
+    const size_t smem = (size_t)(variant == 0 ? K3_RING : A0_SLOTS) * h->F;
+    static thread_local size_t configured[2][64] = {{0}, {0}};
+    const int vi = variant == 0 ? 0 : 1;
+    if (h->device < 64 && configured[vi][h->device] < smem) {
+      if (variant == 0) A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[vi][h->device] = smem;
     }
-    a0_k3_gather_tma<<<count, 32, smem, stream>>>(g);
+    if (variant == 0) a0_k3_gather_tma<<<count, 32, smem, stream>>>(g);
+    else a0_k3_gather_tma_full<<<count, 32, smem, stream>>>(g);
   } else {
     a0_k3_gather_ldg<<<count, K3_LDG_THREADS, 0, stream>>>(g);
   }

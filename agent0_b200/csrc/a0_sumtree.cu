@@ -65,45 +65,36 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
       prio_out[g] = leaf;
     }
   }
-  if (weight_out == nullptr) return;
-  // ---- epilogue: the last block to finish turns priorities into normalised IS weights ----------
-  __shared__ bool is_last;
-  __shared__ float red[K2A_WARPS];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(counter, 1u);
-    is_last = (ticket == gridDim.x - 1);
+  if (weight_out == nullptr || g >= total) return;
+  // ---- epilogue: the last warp of each batch turns its priorities into normalised IS weights
+  //      (trainer.py:91-94), so all batches of a multi-batch draw finish in parallel -------------
+  const int k = g / batch;
+  unsigned ticket = 0;
+  if (lane == 0) {
+    __threadfence();
+    ticket = atomicAdd(counter + k, 1u);
   }
-  __syncthreads();
-  if (!is_last) return;
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket != (unsigned)batch - 1u) return;
   __threadfence();
-  const float denom = root + sum_offset;
-  const int nb = total / batch;
-  for (int k = 0; k < nb; ++k) {
-    const float* p = prio_out + (size_t)k * batch;
-    float* w = weight_out + (size_t)k * batch;
-    if (uniform) {
-      for (int j = threadIdx.x; j < batch; j += blockDim.x) w[j] = 1.0f;
-      continue;
-    }
+  const float* p = prio_out + (size_t)k * batch;
+  float* w = weight_out + (size_t)k * batch;
+  if (uniform) {
+    for (int j = lane; j < batch; j += 32) w[j] = 1.0f;
+  } else {
+    const float denom = root + sum_offset;
     float mx = 0.0f;
-    for (int j = threadIdx.x; j < batch; j += blockDim.x) {
+    for (int j = lane; j < batch; j += 32) {
       const float wj = powf(__fmul_rn(top, __fdiv_rn(__ldcg(p + j), denom)), -beta);
       w[j] = wj;
       mx = fmaxf(mx, wj);
     }
     mx = a0_warp_max(mx);
-    __syncthreads();
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
-#pragma unroll
-    for (int i = 1; i < K2A_WARPS; ++i) mx = fmaxf(mx, red[i]);
     const float inv = mx + 1e-8f;
-    for (int j = threadIdx.x; j < batch; j += blockDim.x) w[j] = __fdiv_rn(w[j], inv);
+    __syncwarp();
+    for (int j = lane; j < batch; j += 32) w[j] = __fdiv_rn(w[j], inv);
   }
-  if (threadIdx.x == 0) *counter = 0u;
+  if (lane == 0) counter[k] = 0u;
 }
 
 extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32_t batch, float top, float beta,
@@ -113,6 +104,7 @@ extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32
   A0_REQUIRE(total >= 0 && batch > 0 && total % batch == 0, "a0_pt_sample: total %d must be a multiple of batch %d", total, batch);
   if (total == 0) return A0_OK;
   A0_REQUIRE(u && idx_out && prio_out, "a0_pt_sample: NULL argument");
+  A0_REQUIRE(total / batch <= A0_MAX_BATCHES, "a0_pt_sample: at most %d batches per call", A0_MAX_BATCHES);
   A0DeviceGuard guard(h->device);
   const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
   a0_k2a_sample<<<blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_>>>(
@@ -122,19 +114,25 @@ extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2b.  One CTA; leaves are written with a deterministic last-writer-wins rule, then every touched
-// ancestor is recomputed from its two children one level at a time (block barrier between levels),
-// so the tree stays bit-reproducible whatever the thread schedule.
-//   mode 0: value = (loss+eps)^alpha, skipped when the leaf is 0; max_p = max(max_p, max loss)
-//   mode 1: pos >= 0 -> max_p^alpha;  pos < 0 -> leaf ~pos = 0
-//   mode 2: value = vals[k]
+// K2b.  Two launches.
+//  (1) a0_k2b_write, one CTA: leaves are written with a deterministic last-writer-wins rule and the
+//      4096-leaf chunks they fall in are flagged dirty.
+//        mode 0: value = (loss+eps)^alpha, skipped when the leaf is 0; max_p = max(max_p, max loss)
+//        mode 1: pos >= 0 -> max_p^alpha;  pos < 0 -> leaf ~pos = 0
+//        mode 2: value = vals[k]
+//  (2) a0_k2b_rebuild, one CTA per chunk: a dirty chunk's sub-tree is recomputed bottom-up in shared
+//      memory, every node as fl32(left + right); the last CTA to finish recomputes the levels above
+//      the chunk roots.  The work does not depend on how many leaves changed (a 1 M-leaf tree is
+//      4 MB read + 4 MB written, all L2-resident) and the result is bit-reproducible: no atomics
+//      on values, no ordering dependence.
 // ------------------------------------------------------------------------------------------------
 constexpr int K2B_THREADS = 1024;
 
 __global__ void __launch_bounds__(K2B_THREADS)
-a0_k2b_update(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
-              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
-              float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner) {
+a0_k2b_write(float* __restrict__ tree, int64_t P, int32_t chunk_log, int64_t N, const int64_t* __restrict__ idx64,
+             const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+             float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
+             int32_t* __restrict__ dirty) {
   __shared__ float red[K2B_THREADS / 32];
   const int tid = threadIdx.x;
   const float maxp_in = *max_p;
@@ -142,17 +140,15 @@ a0_k2b_update(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     if (mode == 1) { const int32_t p = idx32[k]; return p >= 0 ? p : ~p; }
     return idx64[k];
   };
-  // phase 1: claim
   float local_max = 0.0f;
-  for (int k = tid; k < count; k += K2B_THREADS) {
+  for (int k = tid; k < count; k += K2B_THREADS) {          // claim
     const int64_t pos = position(k);
     if (pos < 0 || pos >= N) continue;
     atomicMax(winner + pos, k);
     if (mode == 0) local_max = fmaxf(local_max, vals[k]);
   }
   __syncthreads();
-  // phase 2: write leaves
-  for (int k = tid; k < count; k += K2B_THREADS) {
+  for (int k = tid; k < count; k += K2B_THREADS) {          // write
     const int64_t pos = position(k);
     if (pos < 0 || pos >= N) continue;
     if (__ldcg(winner + pos) != k) continue;
@@ -166,21 +162,12 @@ a0_k2b_update(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
       v = vals[k];
     }
     tree[P + pos] = v;
+    dirty[pos >> chunk_log] = 1;
   }
   __syncthreads();
-  // phase 3: release claims, recompute ancestors level by level
-  for (int k = tid; k < count; k += K2B_THREADS) {
+  for (int k = tid; k < count; k += K2B_THREADS) {          // release
     const int64_t pos = position(k);
     if (pos >= 0 && pos < N) winner[pos] = -1;
-  }
-  for (int lvl = 1; lvl <= D; ++lvl) {
-    for (int k = tid; k < count; k += K2B_THREADS) {
-      const int64_t pos = position(k);
-      if (pos < 0 || pos >= N) continue;
-      const int64_t node = (P + pos) >> lvl;
-      tree[node] = __fadd_rn(__ldcg(tree + 2 * node), __ldcg(tree + 2 * node + 1));
-    }
-    __syncthreads();
   }
   if (mode == 0) {
     local_max = a0_warp_max(local_max);
@@ -194,12 +181,70 @@ a0_k2b_update(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   }
 }
 
+constexpr int K2R_THREADS = 512;
+constexpr int K2R_MAXLOG = 12;      // chunk of up to 4096 leaves; up to 4096 chunk roots above
+
+// Reduce `n = 1 << levels` values held in buf[0][0..n) up to one value, writing every level to the
+// tree: the node at `levels - l` levels above the inputs, i-th of its row, goes to tree[base(l) + i].
+__device__ __forceinline__ void a0_reduce_levels(float (*buf)[1 << K2R_MAXLOG], int levels, float* tree,
+                                                 int64_t row0, int64_t first) {
+  // inputs sit at tree row `row0 + levels` (depth), starting at column `first << levels`
+  int cur = 0;
+  for (int l = levels - 1; l >= 0; --l) {
+    const int cnt = 1 << l;
+    const int64_t base = ((int64_t)1 << (row0 + l)) + (first << l);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const float v = __fadd_rn(buf[cur][2 * i], buf[cur][2 * i + 1]);
+      buf[cur ^ 1][i] = v;
+      tree[base + i] = v;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+__global__ void __launch_bounds__(K2R_THREADS)
+a0_k2b_rebuild(float* __restrict__ tree, int32_t D, int32_t chunk_log, int32_t* __restrict__ dirty,
+               unsigned int* __restrict__ ticket) {
+  __shared__ float buf[2][1 << K2R_MAXLOG];
+  __shared__ bool is_last;
+  const int c = blockIdx.x;
+  const int top_levels = D - chunk_log;                  // depth of the chunk roots
+  if (__ldcg(dirty + c) != 0) {
+    const int n = 1 << chunk_log;
+    const float* leaves = tree + ((int64_t)1 << D) + ((int64_t)c << chunk_log);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) buf[0][i] = __ldcg(leaves + i);
+    __syncthreads();
+    a0_reduce_levels(buf, chunk_log, tree, top_levels, c);
+    if (threadIdx.x == 0) dirty[c] = 0;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (top_levels > 0) {
+    const int n = 1 << top_levels;
+    const float* roots = tree + ((int64_t)1 << top_levels);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) buf[0][i] = __ldcg(roots + i);
+    __syncthreads();
+    a0_reduce_levels(buf, top_levels, tree, 0, 0);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
                             int32_t count, int32_t mode, float alpha, float eps, a0_stream_t stream_) {
   if (count == 0) return A0_OK;
   A0DeviceGuard guard(h->device);
-  a0_k2b_update<<<1, K2B_THREADS, 0, (cudaStream_t)stream_>>>(h->tree, h->P, h->D, h->N, idx64, idx32, vals, count,
-                                                              mode, alpha, eps, h->max_p, h->winner);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int chunk_log = h->D < K2R_MAXLOG ? h->D : K2R_MAXLOG;
+  a0_k2b_write<<<1, K2B_THREADS, 0, stream>>>(h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
+                                             eps, h->max_p, h->winner, h->dirty);
+  A0_LAUNCH_CHECK();
+  a0_k2b_rebuild<<<(unsigned)(h->P >> chunk_log), K2R_THREADS, 0, stream>>>(h->tree, h->D, chunk_log, h->dirty,
+                                                                           h->counter + A0_MAX_BATCHES);
   A0_LAUNCH_CHECK();
   return A0_OK;
 }

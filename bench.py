@@ -58,7 +58,7 @@ def parse():
     p.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and sweeps")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
-    p.add_argument("--variant", type=int, default=0, help="K3 variant: 0 TMA bulk, 1 LDG/STG")
+    p.add_argument("--variant", type=int, default=0, help="K3 variant: 0 TMA ring, 1 LDG/STG, 2 TMA full staging")
     p.add_argument("--cpu-entries", type=int, default=16384, help="deque entries for the CPU baseline sample")
     p.add_argument("--cpu-workers", type=int, default=-1, help="--impl reference DataLoader workers (-1: all cores)")
     return p.parse_args()
@@ -175,13 +175,17 @@ class HotPath:
         e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
         self.u = e(T)
         self.idx = e(T, dt=torch.int64); self.prio = e(T); self.w = e(T)
-        self.frames = e(T, 8 * F_BYTES, dt=torch.uint8)
+        # timed gathers rotate over enough output buffers (>= ~1 GB) that stores are not absorbed by L2
+        self.n_out = min(INNER, max(1, int(1e9 // (T * 8 * F_BYTES))))
+        self.frames_pool = e(self.n_out, T, 8 * F_BYTES, dt=torch.uint8)
+        self.frames = self.frames_pool[0]
         self.act = e(T, dt=torch.int64); self.r64 = e(T, dt=torch.float64); self.r32 = e(T)
         self.d8 = e(T, dt=torch.uint8); self.d32 = e(T); self.boot = e(T, dt=torch.int64)
         self.loss = e(T); self.newp = e(T)
         self.o = net_outputs(wl["algo"], T, A, torch, dev)
         self.grad = torch.empty_like(self.o["online"])
         self.frac = e(T); self.gtau = e(T, 33)
+        self.idx_pool = None
         self.gamma_n = float(np.float32(0.99 ** self.n))
         self.launches_per_step = 3 + L
 
@@ -193,21 +197,37 @@ class HotPath:
                                     gamma_n=self.gamma_n, alpha=0.5, eps=0.01, loss=p(self.loss), prio=p(self.newp),
                                     max_p=self.rp.max_p_tensor.data_ptr()), s
 
-    def sample(self, st):
+    def sample(self, st=None):
         rp = self.rp
+        st = self._st()
         self._lib.check(self.lib.a0_pt_sample(rp.h, self.u.data_ptr(), self.total, self.B, float(rp.top), float(rp.beta), 0.0,
                                               0 if self.wl["per"] else 1, self.idx.data_ptr(), self.prio.data_ptr(),
                                               self.w.data_ptr(), st), "a0_pt_sample")
 
-    def gather(self, st, count=None, variant=None):
+    def _st(self):
+        return self._lib.stream_ptr(self.dev)      # evaluated at call time: the capture stream inside a graph
+
+    def draw_pool(self, st=None):
+        """INNER independent index sets, so that back-to-back timed gathers never re-read frames."""
+        torch = self.torch
+        self.idx_pool = torch.empty(INNER, self.total, dtype=torch.int64, device=self.dev)
+        for i in range(INNER):
+            self.u.uniform_(); self.sample(st)
+            self.idx_pool[i].copy_(self.idx)
+
+    def gather(self, st=None, count=None, variant=None, pool=None):
         rp = self.rp
-        self._lib.check(self.lib.a0_rb_gather(rp.h, self.idx.data_ptr(), count or self.total, self.n, 0.99, self.frames.data_ptr(),
+        st = self._st()
+        idx_ptr = self.idx.data_ptr() if pool is None else self.idx_pool[pool % INNER].data_ptr()
+        out_ptr = self.frames.data_ptr() if pool is None else self.frames_pool[pool % self.n_out].data_ptr()
+        self._lib.check(self.lib.a0_rb_gather(rp.h, idx_ptr, count or self.total, self.n, 0.99, out_ptr,
                                               self.act.data_ptr(), self.r64.data_ptr(), self.r32.data_ptr(), self.d8.data_ptr(),
                                               self.d32.data_ptr(), self.boot.data_ptr(),
                                               self.variant if variant is None else variant, st), "a0_rb_gather")
 
-    def loss_k(self, k, st):
+    def loss_k(self, k, st=None):
         lib, o, algo = self.lib, self.o, self.wl["algo"]
+        st = self._st()
         c, s = self._common(k)
         p = lambda t: t[s].data_ptr()
         qsel = p(o["qsel"]) if self.wl["double"] or algo in ("iqn", "fqf") else None
@@ -229,19 +249,19 @@ class HotPath:
                                       p(self.grad), p(o["q_bar"]), p(o["taus"]), p(self.frac), p(self.gtau), st)
         self._lib.check(rc, "a0_loss_" + algo)
 
-    def update(self, st):
+    def update(self, st=None):
+        st = self._st()
         if self.wl["per"]:
             self._lib.check(self.lib.a0_pt_update(self.rp.h, self.idx.data_ptr(), self.loss.data_ptr(), self.total, 0.5, 0.01, st),
                             "a0_pt_update")
 
     def step(self):
-        st = self._lib.stream_ptr(self.dev)
         self.u.uniform_()
-        self.sample(st)
-        self.gather(st)
+        self.sample()
+        self.gather()
         for k in range(self.L):
-            self.loss_k(k, st)
-        self.update(st)
+            self.loss_k(k)
+        self.update()
 
 
 def time_graphed(hp, steps, warmup, torch, use_graph, barrier):
@@ -268,17 +288,29 @@ def time_graphed(hp, steps, warmup, torch, use_graph, barrier):
     return e0.elapsed_time(e1) / 1e3
 
 
-def time_kernel(fn, before, reps, torch):
-    """Average device duration of one launch, CUDA events on the launching stream."""
-    tot = 0.0
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for a, b in evs:
-        before()
-        a.record(); fn(); b.record()
+INNER = 20
+
+
+def time_kernel(fn, reps, torch):
+    """Average device duration of one launch: INNER back-to-back launches ``fn(i)`` (i selects
+    distinct pre-drawn inputs where that matters) captured into one CUDA graph so the host launch
+    path is not on the clock; CUDA events on the launching stream around the replays."""
+    fn(0)
     torch.cuda.synchronize()
-    for a, b in evs:
-        tot += a.elapsed_time(b)
-    return tot / reps / 1e3
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(INNER):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    rounds = max(1, reps // INNER)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / (rounds * INNER)
 
 
 def e2e_loop(rp, wl, L, A, steps, warmup, torch):
@@ -370,11 +402,8 @@ def run_ours(args):
     value = total * args.steps * world / secs
 
     # ---- roofline of the dominant kernel (K3), same launch shape, fresh indices every launch -------
-    st = hp._lib.stream_ptr(hp.dev)
-
-    def fresh():
-        hp.u.uniform_(); hp.sample(st)
-    k3 = time_kernel(lambda: hp.gather(st), fresh, max(20, min(args.steps, 200)), torch)
+    hp.draw_pool()
+    k3 = time_kernel(lambda i: hp.gather(pool=i), max(40, min(args.steps, 200)), torch)
     bpt = bytes_per_transition(wl["n"])
     peaks = {}
     try:
@@ -388,7 +417,7 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json"))).get(f"{total}")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "a0_k3_gather_tma" if args.variant == 0 else "a0_k3_gather_ldg",
+    roofline = {"bound": "hbm", "kernel": ["a0_k3_gather_tma", "a0_k3_gather_ldg", "a0_k3_gather_tma_full"][args.variant],
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                 "bytes_per_launch": bpt * total, "launch_us": round(k3 * 1e6, 2), "transitions_per_launch": total}
@@ -442,11 +471,11 @@ def extras(rp, args, torch, peak):
             continue        # the shard was built prioritized; the uniform config is a parity-test case
         hp = HotPath(rp, wl, L, A, torch, variant=args.variant)
         secs = time_graphed(hp, 50, 5, torch, not args.no_graph, lambda: None)
-        st = hp._lib.stream_ptr(hp.dev)
-        k4 = time_kernel(lambda: hp.loss_k(0, st), lambda: None, 50, torch)
-        k3 = time_kernel(lambda: hp.gather(st), lambda: (hp.u.uniform_(), hp.sample(st)), 30, torch)
-        k2a = time_kernel(lambda: hp.sample(st), lambda: hp.u.uniform_(), 30, torch)
-        k2b = time_kernel(lambda: hp.update(st), lambda: None, 30, torch)
+        hp.draw_pool()
+        k4 = time_kernel(lambda i: hp.loss_k(i % L), 60, torch)
+        k3 = time_kernel(lambda i: hp.gather(pool=i), 40, torch)
+        k2a = time_kernel(lambda i: hp.sample(), 40, torch)
+        k2b = time_kernel(lambda i: hp.update(), 40, torch)
         out["workloads"][name] = {"transitions_per_s": round(hp.total * 50 / secs, 1), "ms_per_step": round(secs / 50 * 1e3, 4),
                                   "k4_us_per_batch": round(k4 * 1e6, 2), "k3_us": round(k3 * 1e6, 2),
                                   "k3_GBps": round(bytes_per_transition(wl["n"]) * hp.total / k3 / 1e9, 1),
@@ -454,13 +483,12 @@ def extras(rp, args, torch, peak):
         del hp
     wl = dict(WORKLOADS["c51_b512"])
     hp = HotPath(rp, wl, 128, A, torch)           # buffers for up to 65536 transitions
-    st = hp._lib.stream_ptr(hp.dev)
-    hp.u.uniform_(); hp.sample(st)
+    hp.draw_pool()
     for count in (32, 512, 640, 4096, 10240, 65536):
-        for variant in (0, 1):
-            dt = time_kernel(lambda: hp.gather(st, count=count, variant=variant), lambda: (hp.u.uniform_(), hp.sample(st)), 20, torch)
+        for variant in (0, 2, 1):
+            dt = time_kernel(lambda i: hp.gather(count=count, variant=variant, pool=i), 40, torch)
             gb = bytes_per_transition(3) * count / dt / 1e9
-            out["k3_sweep"].append({"transitions": count, "variant": "tma" if variant == 0 else "ldg", "us": round(dt * 1e6, 2),
+            out["k3_sweep"].append({"transitions": count, "variant": ["tma_ring4", "ldg", "tma_full8"][variant], "us": round(dt * 1e6, 2),
                                     "GBps": round(gb, 1), "frac_of_measured_peak": round(gb / peak, 4)})
     return out
 

@@ -118,7 +118,8 @@ int a0_pt_sample(a0_replay_t* h, const float* u /* dev [total] */, int32_t total
  *        window (-1 if not appended yet).
  * frames_out [count][8][frame_bytes]: the reference's `frames` layout, concat(st, st_next)
  * (agent.py:80); action i64; reward f64 and f32; done u8 and f32; boot i64.  Any output but
- * frames_out may be NULL.  variant: 0 = TMA bulk copies through shared memory, 1 = LDG/STG.      */
+ * frames_out may be NULL.  variant: 0 = TMA bulk copies through a 4-buffer shared-memory ring
+ * (default), 1 = LDG/STG through registers, 2 = TMA with all distinct frames staged at once.     */
 int a0_rb_gather(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count, int32_t n_step,
                  double gamma, uint8_t* frames_out, int64_t* action_out, double* reward64_out,
                  float* reward32_out, uint8_t* done8_out, float* done32_out, int64_t* boot_out,
