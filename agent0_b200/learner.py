@@ -1,0 +1,229 @@
+"""The six deepq learners behind the reference's interface, with the target/loss rules on the fused
+sm_100a kernels (K4) and the Nature-CNN forward/backward left to PyTorch.
+
+Drop-in surface (agent0/deepq/agent.py:96-388): classes ``DQNLearner, MDQNLearner, C51Learner,
+QRLearner, IQNLearner, FQFLearner`` looked up by ``f"{algo.name.upper()}Learner"``
+(agent0/deepq/trainer.py:31-34); ``__init__(cfg)``; attributes ``model``, ``model_target``,
+``optimizer`` (``fqf_optimizer``), ``update_steps``; ``train(data)`` with
+``data = (frames, actions, rewards, terminals, weights, indices)`` returning
+``{"q_loss", "fraction_loss", "indices"}``.
+
+How a step differs from the reference mechanically, not numerically: the reference builds the loss
+with eager ATen ops and calls ``q_loss.mul(weights).sum().backward()`` (agent.py:154); here one K4
+launch produces the per-sample loss *and* d[(loss*weights).sum()]/d[network output], and the CNN's
+backward is started from that gradient (``out.backward(grad)``).  Results stay on the device (the
+reference's ``.cpu()`` calls, agent.py:163-169, are a host sync per update); everything the
+reference's ``Trainer.step`` does with them (``.mean().item()``, ``update_priority``) still works.
+
+Data-parallel use (north_star): pass ``process_group``; gradients are SUM-all-reduced
+over NCCL in one flat bucket and Adam's eps becomes 1e-2/(world*batch), so that G ranks at batch B
+take the step one learner would take at batch G*B (the reference's loss is SUM-reduced).
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import losses as L
+from .model import DeepQNet
+
+
+def _algo_name(cfg):
+    return getattr(cfg.learner.algo, "name", cfg.learner.algo)
+
+
+class BaseLearner:
+    def __init__(self, cfg, process_group=None, device=None, max_p=None):
+        self.cfg = cfg
+        dv = device if device is not None else getattr(cfg.device, "value", cfg.device)
+        self.device = torch.device(dv)
+        if self.device.type != "cuda":
+            raise RuntimeError("agent0_b200 learners run their target/loss rules in CUDA kernels; "
+                               "there is no CPU path (use the reference learner on CPU)")
+        self.model = DeepQNet(cfg).to(self.device)
+        self.model_target = copy.deepcopy(self.model)       # agent.py:100 (no RNG consumed)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        B = cfg.learner.batch_size
+        self.optimizer = torch.optim.Adam(list(self.model.params()), cfg.learner.learning_rate,
+                                          eps=1e-2 / (B * self.world))
+        self.update_steps = 0
+        self.gamma_n = float(np.float32(cfg.learner.discount ** cfg.learner.n_step_q))
+        self.alpha, self.eps = float(cfg.replay.alpha), float(cfg.replay.eps)
+        self.max_p = max_p                      # device scalar shared with the replay shard (optional)
+        self.nan_guard = True                   # agent.py:152-158 (costs one device->host sync per update)
+        self._flatten_grads(list(self.model.params()))
+
+    # ---- one flat gradient bucket: zeroed with one memset, all-reduced with one NCCL call --------
+    def _flatten_grads(self, params):
+        n = sum(p.numel() for p in params)
+        self._flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in params:
+            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def _allreduce(self, flat):
+        if self.world > 1:
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    # ---- helpers ----------------------------------------------------------------------------------
+    def _kw(self):
+        return dict(alpha=self.alpha, eps=self.eps, max_p=self.max_p)
+
+    def split_frames(self, frames):
+        """agent.py:129-135: [B, 8*H*W] -> obs, next_obs in [0,1] (uint8 straight from K3, or the
+        reference Trainer's float tensors)."""
+        c = self.cfg.obs_shape[0]
+        x = frames.reshape(-1, 2 * c, *self.cfg.obs_shape[1:]).float().div(255.0)
+        return torch.split(x, c, 1)
+
+    def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
+        raise NotImplementedError
+
+    def train(self, data):
+        if self.cfg.learner.noisy_net:
+            self.model.reset_noise()
+            self.model_target.reset_noise()
+        frames, actions, rewards, terminals, weights, indices = data
+        dev = self.device
+        obs, next_obs = self.split_frames(frames.to(dev, non_blocking=True))
+        actions = actions.to(dev, non_blocking=True).long()
+        rewards = rewards.to(dev, non_blocking=True).float()
+        terminals = terminals.to(dev, non_blocking=True).float()
+        weights = weights.to(dev, non_blocking=True).float()
+
+        self._flat_grad.zero_()
+        out, net_out = self.train_step(obs, actions, rewards, terminals, next_obs, weights)
+        q_loss, fraction_loss = out.loss, out.fraction_loss
+        skip = bool(torch.isnan(q_loss).any()) if self.nan_guard else False
+        if not skip:
+            net_out.backward(out.grad)                      # == q_loss.mul(weights).sum().backward()
+            self._allreduce(self._flat_grad)
+            self.optimizer.step()
+            self.update_steps += 1
+        else:
+            q_loss = None
+        if self.update_steps % self.cfg.learner.target_update_freq == 0:
+            self.model_target.load_state_dict(self.model.state_dict())   # deepcopy(model), agent.py:160-161
+        return {"q_loss": q_loss, "fraction_loss": fraction_loss,
+                "indices": indices.to(dev, non_blocking=True).long()}
+
+
+class DQNLearner(BaseLearner):
+    """agent.py:172-190."""
+
+    def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
+        with torch.no_grad():
+            qt_next = self.model_target(next_obs)
+            qsel = self.model.qval(next_obs) if self.cfg.learner.double_q else None
+        q = self.model(obs)
+        return L.dqn_loss(q, qt_next, actions, rewards, terminals, weights, self.gamma_n, qsel=qsel, **self._kw()), q
+
+
+class MDQNLearner(BaseLearner):
+    """agent.py:193-215 (both target evaluations come from the target net)."""
+
+    def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
+        c = self.cfg.learner.mdqn
+        with torch.no_grad():
+            qt_next = self.model_target(next_obs)
+            qt_cur = self.model_target(obs)
+        q = self.model(obs)
+        return L.mdqn_loss(q, qt_next, qt_cur, actions, rewards, terminals, weights, self.gamma_n,
+                           tau=c.tau, lo=c.lo, **self._kw()), q
+
+
+class C51Learner(BaseLearner):
+    """agent.py:218-269."""
+
+    def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
+        c = self.cfg.learner.c51
+        with torch.no_grad():
+            tgt = self.model_target(next_obs)
+            qsel = self.model.qval(next_obs) if self.cfg.learner.double_q else None
+        logits = self.model(obs)
+        return L.c51_loss(logits, tgt, self.model.head.atoms, actions, rewards, terminals, weights, self.gamma_n,
+                          c.vmin, c.vmax, qsel=qsel, **self._kw()), logits
+
+
+class QRLearner(BaseLearner):
+    """agent.py:272-293."""
+
+    def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
+        with torch.no_grad():
+            qt_next = self.model_target(next_obs)
+            qsel = self.model.qval(next_obs) if self.cfg.learner.double_q else None
+        q = self.model(obs)
+        return L.qr_loss(q, qt_next, actions, rewards, terminals, weights, self.gamma_n, qsel=qsel, **self._kw()), q
+
+
+class IQNLearner(BaseLearner):
+    """agent.py:296-327.  The tau draws keep the reference's order on torch's CPU generator:
+    K (action selection) -> N_dash (target) -> N (online)."""
+
+    def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
+        c = self.cfg.learner.iqn
+        with torch.no_grad():
+            next_convs = self.model_target.encoder(next_obs)
+            if self.cfg.learner.double_q:
+                qsel = self.model.head.qval(self.model.encoder(next_obs), n=c.K)
+            else:
+                qsel = self.model_target.head.qval(next_convs, n=c.K)
+            qt_next, _ = self.model_target.head(next_convs, n=c.N_dash)
+        q, taus = self.model.head(self.model.encoder(obs), n=c.N)
+        return L.iqn_loss(q, taus, qt_next, qsel, actions, rewards, terminals, weights, self.gamma_n, **self._kw()), q
+
+
+class FQFLearner(BaseLearner):
+    """agent.py:330-388: quantile loss at tau_hat plus the fraction-proposal loss, which has its own
+    RMSprop step taken *before* the q-loss backward (agent.py:139-148)."""
+
+    def __init__(self, cfg, **kw):
+        super().__init__(cfg, **kw)
+        fp = list(self.model.head.fraction_net.parameters())
+        self.fqf_optimizer = torch.optim.RMSprop(fp, lr=cfg.learner.learning_rate / 2e4, alpha=0.95, eps=0.00001)
+        n = sum(p.numel() for p in fp)
+        self._flat_frac = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in fp:
+            p.grad = self._flat_frac[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
+        head = self.model.head
+        convs = self.model.encoder(obs)
+        taus, taus_hat, _ = head.prop_taus(convs.detach())
+        q_hat, _ = head(convs, taus=taus_hat)
+        with torch.no_grad():
+            next_convs = self.model_target.encoder(next_obs)
+            if self.cfg.learner.double_q:
+                qsel = head.qval(self.model.encoder(next_obs))
+            else:
+                qsel = self.model_target.head.qval(next_convs)
+            qt_next, _ = self.model_target.head(next_convs, taus=taus_hat)
+            q_bar, _ = head(convs, taus=taus[:, 1:-1])
+        out = L.fqf_loss(q_hat, taus, taus_hat, qt_next, q_bar, qsel, actions, rewards, terminals, weights,
+                         self.gamma_n, **self._kw())
+        # fraction step first (agent.py:139-148): only fraction_net receives this gradient
+        self._flat_frac.zero_()
+        taus.squeeze(-1).backward(out.grad_taus)
+        self._allreduce(self._flat_frac)
+        if self.cfg.learner.max_grad_norm > 0:
+            nn.utils.clip_grad_norm_(head.fraction_net.parameters(), self.cfg.learner.max_grad_norm)
+        self.fqf_optimizer.step()
+        return out, q_hat
+
+
+LEARNERS = {c.__name__: c for c in (DQNLearner, MDQNLearner, C51Learner, QRLearner, IQNLearner, FQFLearner)}
+
+
+def make_learner(cfg, **kw):
+    """trainer.py:31-34: getattr(agents, f"{algo.name.upper()}Learner")(cfg)."""
+    name = f"{_algo_name(cfg).upper()}Learner"
+    if name not in LEARNERS:
+        raise NotImplementedError(f"No such learner for {_algo_name(cfg)}")
+    return LEARNERS[name](cfg, **kw)

@@ -386,6 +386,36 @@ def gen_loss_fqf(double, B=8, A=4, seed=0):
           f"frac[:2]={fraction_loss.detach().numpy()[:2]}")
 
 
+def gen_learner(algo, double, dueling):
+    """Two real BaseLearner.train() updates on CPU (real DeepQNet, Adam, target sync) from a fixed
+    seed, on batches taken from replay_n3.npz.  Pins the whole learner path: frame split, the
+    train_step rule, the weighted SUM backward, the optimizer step and (FQF) the fraction step."""
+    g = np.load(os.path.join(HERE, "replay_n3.npz"))
+    B = 8
+    cfg = base_cfg(algo=algo, B=B, n=3, double=double, dueling=dueling, per=True)
+    cfg.learner.target_update_freq = 2
+    torch.manual_seed(4242)
+    learner = getattr(agents, f"{algo.upper()}Learner")(cfg)
+    rng = np.random.RandomState(17)
+    out = dict(algo=algo, double_q=double, dueling=dueling, seed=4242, batch=B)
+    for it in range(3):
+        idx = rng.randint(0, len(g["entry_action"]), B)
+        w = (rng.rand(B) + 0.1).astype(np.float32)
+        data = (torch.from_numpy(g["entry_frames"][idx]).float(), torch.from_numpy(g["entry_action"][idx]).float(),
+                torch.from_numpy(g["entry_reward"][idx]).float(), torch.from_numpy(g["entry_done"][idx]).float(),
+                torch.from_numpy(w), torch.from_numpy(idx).float())
+        res = learner.train(data)
+        out[f"idx{it}"] = idx; out[f"w{it}"] = w
+        out[f"q_loss{it}"] = res["q_loss"].numpy()
+        if res["fraction_loss"] is not None:
+            out[f"fraction_loss{it}"] = res["fraction_loss"].numpy()
+    out["param_abs_sum"] = np.array([p.detach().abs().sum().item() for p in learner.model.parameters()])
+    out["target_abs_sum"] = np.array([p.detach().abs().sum().item() for p in learner.model_target.parameters()])
+    out["update_steps"] = learner.update_steps
+    np.savez_compressed(os.path.join(HERE, f"learner_{algo}.npz"), **out)
+    print(f"learner_{algo}: q_loss0[:2]={out['q_loss0'][:2]} q_loss2[:2]={out['q_loss2'][:2]}")
+
+
 def gen_static_fns():
     g = torch.Generator().manual_seed(77)
     q = torch.randn(5, 1, 16, generator=g) * 2
@@ -419,3 +449,6 @@ if __name__ == "__main__":
         gen_loss_iqn(dq)
         gen_loss_fqf(dq)
     gen_static_fns()
+    for algo, dq, du in (("dqn", True, False), ("mdqn", False, True), ("c51", True, True), ("qr", False, False),
+                         ("iqn", True, True), ("fqf", True, False)):
+        gen_learner(algo, dq, du)

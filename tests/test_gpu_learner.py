@@ -1,0 +1,76 @@
+"""The six learners (CUDA K4 + PyTorch CNN) against three real reference ``train()`` updates made
+on CPU from the same seed (tests/golden/learner_*.npz): same initial weights (bit-identical
+constructors, tests/test_model_parity.py), same batches, same IS weights.  The first loss depends
+only on the forward pass and the K4 rule; the next two also on the backward from the kernel's
+gradient, Adam/RMSprop and the target sync.  cuDNN-vs-CPU convolution rounding bounds the match."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"dqn": (True, False), "mdqn": (False, True), "c51": (True, True), "qr": (False, False),
+         "iqn": (True, True), "fqf": (True, False)}
+
+
+@pytest.mark.parametrize("algo", sorted(CASES))
+def test_learner_train_matches_reference_updates(golden, algo):
+    from agent0_b200.config import make_config
+    from agent0_b200.learner import LEARNERS, make_learner
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden(f"learner_{algo}")
+    entries = golden("replay_n3")
+    double, dueling = CASES[algo]
+    B = int(g["batch"])
+    cfg = make_config(algo, per=True, n_step=3, batch_size=B, double_q=double, dueling=dueling, replay_size=256)
+    cfg.learner.target_update_freq = 2
+    torch.manual_seed(int(g["seed"]))
+    learner = make_learner(cfg)
+    assert type(learner) is LEARNERS[f"{algo.upper()}Learner"]
+    for it in range(3):
+        idx = g[f"idx{it}"]
+        data = (torch.from_numpy(entries["entry_frames"][idx]).cuda(),          # uint8 straight from K3
+                torch.from_numpy(entries["entry_action"][idx]).cuda(),
+                torch.from_numpy(entries["entry_reward"][idx]).cuda(),          # float64, cast inside
+                torch.from_numpy(entries["entry_done"][idx]).cuda(),
+                torch.from_numpy(g[f"w{it}"]).cuda(), torch.from_numpy(idx).cuda())
+        res = learner.train(data)
+        rtol = 2e-3 if it == 0 else 5e-2
+        np.testing.assert_allclose(res["q_loss"].cpu().numpy(), g[f"q_loss{it}"], rtol=rtol, atol=2e-7)
+        if algo == "fqf":
+            np.testing.assert_allclose(res["fraction_loss"].cpu().numpy(), g[f"fraction_loss{it}"], rtol=rtol, atol=2e-6)
+        else:
+            assert res["fraction_loss"] is None
+        assert np.array_equal(res["indices"].cpu().numpy(), idx)
+    assert learner.update_steps == int(g["update_steps"]) == 3
+    ours = np.array([p.detach().abs().sum().item() for p in learner.model.parameters()])
+    np.testing.assert_allclose(ours, g["param_abs_sum"], rtol=2e-4)
+    tgt = np.array([p.detach().abs().sum().item() for p in learner.model_target.parameters()])
+    np.testing.assert_allclose(tgt, g["target_abs_sum"], rtol=2e-4)     # synced at update 2, not at 3
+
+
+def test_trainer_step_end_to_end(golden):
+    """Reference tuples -> Trainer.step: extend, K2a/K3 sample of L batches, L learner updates,
+    priority updates; the tree stays consistent and nothing leaves the device."""
+    from agent0_b200.config import make_config
+    from agent0_b200.trainer import Trainer
+    g = golden("replay_n3")
+    cfg = make_config("c51", per=True, n_step=3, batch_size=8, double_q=True, dueling=True, replay_size=256, num_envs=3)
+    cfg.trainer.training_start_steps = 50
+    cfg.learner.learner_steps = 4
+    tr = Trainer(cfg)
+    M = len(g["entry_action"])
+    tup = [(g["entry_frames"][i].tobytes(), g["entry_action"][i], g["entry_reward"][i], g["entry_done"][i]) for i in range(M)]
+    r0 = tr.step(tup[:45])
+    assert r0["loss"] is None and tr.learner.update_steps == 0           # below training_start_steps
+    r1 = tr.step(tup[45:])
+    assert tr.learner.update_steps == 4 and r1["loss"] is not None and np.isfinite(r1["loss"])
+    leaves = tr.replay.priority.leaves().cpu().numpy()
+    assert (leaves[:M] > 0).all() and (leaves[M:] == 0).all()
+    assert (leaves[:M] != 1.0).sum() >= 8                                # priorities were rewritten
+    tree = tr.replay.tree.cpu().numpy()
+    P = tr.replay.P
+    for node in (1, 2, 3, P // 2, P - 1):
+        assert tree[node] == np.float32(tree[2 * node] + tree[2 * node + 1])
+    assert tr.replay.max_p >= 1.0
