@@ -27,6 +27,16 @@ class LossCommon(C.Structure):
                 ("loss", _vp), ("prio", _vp), ("max_p", _vp)]
 
 
+class Plan(C.Structure):
+    """a0_plan_t"""
+    _fields_ = [("m", _i32), ("n_new", _i32), ("n_marks", _i32), ("new_frame_pos", C.POINTER(_i32)),
+                ("rec_meta", C.POINTER(_i32)), ("marks", C.POINTER(_i32))]
+
+
+IX_HEAD_Q, IX_TAIL_Q, IX_HEAD_FS, IX_TOP, IX_REC_CAPACITY, IX_FRAME_CAPACITY, IX_NSTEP, IX_AGE_LIMIT, \
+    IX_MAX_CHUNK, IX_STATE_WORDS = range(10)
+INGEST_FRAMES_ON_DEVICE, INGEST_FRAMES_PINNED = 1, 2
+
 # name -> (restype, argtypes): every symbol include/agent0_b200.h declares
 SIGNATURES = {
     "a0_version": (_i32, []),
@@ -36,6 +46,16 @@ SIGNATURES = {
     "a0_rb_reset": (_i32, [_vp, _vp]),
     "a0_rb_ptr": (_vp, [_vp, _i32]),
     "a0_rb_tree_leaves": (_i64, [_vp]),
+    "a0_ix_create": (_i32, [C.POINTER(_vp), _i64, _i64, _i32, _i64]),
+    "a0_ix_destroy": (_i32, [_vp]),
+    "a0_ix_state": (_i32, [_vp, _vp]),
+    "a0_ix_sampleable": (_vp, [_vp]),
+    "a0_ix_set_stack": (_i32, [_vp, _i64, _vp]),
+    "a0_ix_get_stack": (_i32, [_vp, _i64, _vp]),
+    "a0_ix_resolve_shift": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "a0_ix_plan": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, C.POINTER(Plan)]),
+    "a0_rb_ingest_plan": (_i32, [_vp, C.POINTER(Plan), _vp, _vp, _i32, _f32, _vp]),
+    "a0_rb_ingest_steps": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp]),
     "a0_rb_append": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "a0_pt_mark": (_i32, [_vp, _vp, _i32, _f32, _vp]),
     "a0_pt_update": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _vp]),
@@ -75,7 +95,19 @@ def check(rc, what):
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (inside torch.cuda.graph: the capture stream)."""
+    if _raw_stream is not None:
+        if device is None:
+            idx = torch.cuda.current_device()
+        elif isinstance(device, int):
+            idx = device
+        else:
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+        return _raw_stream(idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

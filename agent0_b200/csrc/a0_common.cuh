@@ -17,6 +17,13 @@ struct __align__(16) A0RecInfo {
 
 constexpr int A0_MAX_BATCHES = 4096;   // batches per a0_pt_sample call
 
+struct A0Staging {        // one half of the double-buffered ingest staging area
+  uint8_t* host;          // page-locked
+  uint8_t* dev;
+  size_t capacity;
+  cudaEvent_t event;      // recorded after the kernels that consume `dev`
+};
+
 struct a0_replay {
   int32_t device;
   int64_t N;             // record capacity
@@ -32,6 +39,8 @@ struct a0_replay {
   int32_t* winner;       // [N] scratch for last-writer-wins, kept at -1 between calls
   int32_t* dirty;        // [P >> 12] chunk needs its sub-tree recomputed
   unsigned int* counter; // [A0_MAX_BATCHES] per-batch tickets of the sampler epilogue, +1 rebuild ticket
+  A0Staging staging[2];
+  int staging_turn;
 };
 
 void a0_set_error(const char* fmt, ...);

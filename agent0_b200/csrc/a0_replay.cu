@@ -80,6 +80,11 @@ extern "C" int a0_rb_destroy(a0_replay_t* h) {
   A0DeviceGuard guard(h->device);
   cudaFree(h->frames); cudaFree(h->rec_slots); cudaFree(h->rec_info); cudaFree(h->tree);
   cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->dirty); cudaFree(h->counter);
+  for (int t = 0; t < 2; ++t) {
+    if (h->staging[t].event) { cudaEventSynchronize(h->staging[t].event); cudaEventDestroy(h->staging[t].event); }
+    if (h->staging[t].host) cudaFreeHost(h->staging[t].host);
+    if (h->staging[t].dev) cudaFree(h->staging[t].dev);
+  }
   delete h;
   return A0_OK;
 }
@@ -187,22 +192,21 @@ struct A0GatherArgs {
   int64_t* boot_out;
 };
 
-// Walks the n-step window of sample b and returns the 8 frame slots.  The return is evaluated as
-// the reference does (agent.py:65-69): r = 0; for newest..oldest: r = r*gamma*(1-d) + r_t, every
-// product and sum rounded separately in float64 (no FMA contraction).
-__device__ __forceinline__ bool a0_resolve_window(const A0GatherArgs& g, int b, int32_t (&slot)[A0_SLOTS]) {
-  int64_t p0 = g.idx[b];
-  bool ok = p0 >= 0 && p0 < g.N;
-  if (!ok) p0 = 0;
+// Walks the n-step window that starts at record p0 (whose info word is already loaded), writes
+// the scalar outputs of sample b and returns the last record of the window.  The return is
+// evaluated as the reference does (agent.py:65-69): r = 0; for newest..oldest:
+// r = r*gamma*(1-d) + r_t, every product and sum rounded separately in float64 (no FMA contraction).
+__device__ __forceinline__ int64_t a0_walk_window(const A0GatherArgs& g, int b, int64_t p0, A0RecInfo info,
+                                                  bool& ok) {
   double rew[A0_MAX_NSTEP];
   int dn[A0_MAX_NSTEP];
   int64_t p = p0;
-  int32_t action = 0, link = -1;
+  const int32_t action = info.action_done & 0x7fffffff;
+  int32_t link = -1;
   int steps = 0;
 #pragma unroll 1
   for (int i = 0; i < g.n_step; ++i) {
-    const A0RecInfo info = g.rec_info[p];
-    if (i == 0) action = info.action_done & 0x7fffffff;
+    if (i > 0) info = g.rec_info[p];
     rew[i] = info.reward;
     dn[i] = (info.action_done >> 31) & 1;
     link = info.link;
@@ -219,20 +223,28 @@ __device__ __forceinline__ bool a0_resolve_window(const A0GatherArgs& g, int b, 
     d_any |= dn[i];
     r = __dadd_rn(__dmul_rn(__dmul_rn(r, g.gamma), (double)(1 - dn[i])), rew[i]);
   }
-  const int4* s0 = reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
-  const int4* s1 = reinterpret_cast<const int4*>(g.rec_slots + (size_t)p * A0_SLOTS);
-  const int4 a = s0[0], c = s1[1];
-  slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w;
-  slot[4] = c.x; slot[5] = c.y; slot[6] = c.z; slot[7] = c.w;
-#pragma unroll
-  for (int j = 0; j < A0_SLOTS; ++j)
-    if (slot[j] < 0 || slot[j] >= g.NF) { slot[j] = 0; ok = false; }
   if (g.action_out) g.action_out[b] = ok ? (int64_t)action : -1;
   if (g.reward64_out) g.reward64_out[b] = r;
   if (g.reward32_out) g.reward32_out[b] = (float)r;          // .float() in Trainer.step (trainer.py:88-90)
   if (g.done8_out) g.done8_out[b] = (uint8_t)d_any;
   if (g.done32_out) g.done32_out[b] = (float)d_any;
   if (g.boot_out) g.boot_out[b] = ok ? (int64_t)link : -1;
+  return p;
+}
+
+// The 8 frame slots of sample b: observation stack of the first record, next stack of the last.
+__device__ __forceinline__ bool a0_resolve_window(const A0GatherArgs& g, int b, int32_t (&slot)[A0_SLOTS]) {
+  int64_t p0 = g.idx[b];
+  bool ok = p0 >= 0 && p0 < g.N;
+  if (!ok) p0 = 0;
+  const int4 a = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
+  const int64_t p = a0_walk_window(g, b, p0, g.rec_info[p0], ok);
+  const int4 c = reinterpret_cast<const int4*>(g.rec_slots + (size_t)p * A0_SLOTS)[1];
+  slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w;
+  slot[4] = c.x; slot[5] = c.y; slot[6] = c.z; slot[7] = c.w;
+#pragma unroll
+  for (int j = 0; j < A0_SLOTS; ++j)
+    if (slot[j] < 0 || slot[j] >= g.NF) { slot[j] = 0; ok = false; }
   return ok;
 }
 
@@ -268,22 +280,25 @@ __device__ __forceinline__ void a0_bulk_store(void* gdst, uint32_t smem_src, uin
 }
 
 // Distinct frames of the two stacks: uslot[u] = frame slot, dmask[u] = stack positions it fills.
+// a0_unique_add registers stack position j (fully unrolled: the arrays stay in registers).
+__device__ __forceinline__ void a0_unique_add(int32_t s, int j, int32_t (&uslot)[A0_SLOTS], uint32_t (&dmask)[A0_SLOTS],
+                                              int& U) {
+  bool found = false;
+#pragma unroll
+  for (int u = 0; u < A0_SLOTS; ++u)
+    if (u < U && !found && uslot[u] == s) { dmask[u] |= 1u << j; found = true; }
+  if (!found) {
+#pragma unroll
+    for (int u = 0; u < A0_SLOTS; ++u)
+      if (u == U) { uslot[u] = s; dmask[u] = 1u << j; }
+    ++U;
+  }
+}
 __device__ __forceinline__ int a0_unique_frames(const int32_t (&slot)[A0_SLOTS], int32_t (&uslot)[A0_SLOTS],
                                                 uint32_t (&dmask)[A0_SLOTS]) {
   int U = 0;
 #pragma unroll
-  for (int j = 0; j < A0_SLOTS; ++j) {
-    bool found = false;
-#pragma unroll
-    for (int u = 0; u < A0_SLOTS; ++u)
-      if (u < U && !found && uslot[u] == slot[j]) { dmask[u] |= 1u << j; found = true; }
-    if (!found) {
-#pragma unroll
-      for (int u = 0; u < A0_SLOTS; ++u)
-        if (u == U) { uslot[u] = slot[j]; dmask[u] = 1u << j; }
-      ++U;
-    }
-  }
+  for (int j = 0; j < A0_SLOTS; ++j) a0_unique_add(slot[j], j, uslot, dmask, U);
   return U;
 }
 
@@ -292,28 +307,57 @@ __device__ __forceinline__ int a0_unique_frames(const int32_t (&slot)[A0_SLOTS],
 // cp.async.bulk (global -> shared, completion on that buffer's mbarrier) and written with
 // cp.async.bulk (shared -> global) to every stack position it occupies: (S+n)*F bytes read and
 // 2S*F bytes written per transition, no register staging.  A buffer is refilled as soon as its
-// stores have read it, so 28 KB of shared memory per CTA is enough and 8 CTAs fit on an SM: a
-// 640-transition launch (20 batches of 32) is a single wave.
+// stores have read it, so 28 KB of shared memory per CTA is enough and 7 CTAs fit on an SM: a
+// 640-transition launch (20 batches of 32) is a single wave.  The loads of the observation stack
+// are issued as soon as the first record is known, so the dependent walk along the n-step links
+// (two more HBM round trips at n = 3) overlaps the first 28 KB of frame traffic.
 constexpr int K3_RING = 4;
 __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   extern __shared__ __align__(128) uint8_t a0_smem[];
   __shared__ __align__(8) uint64_t bars[K3_RING];
   if (threadIdx.x != 0) return;
   const int b = blockIdx.x;
-  int32_t slot[A0_SLOTS];
-  a0_resolve_window(g, b, slot);
   const uint32_t F = (uint32_t)g.F;
-  int32_t uslot[A0_SLOTS];
-  uint32_t dmask[A0_SLOTS];
-  const int U = a0_unique_frames(slot, uslot, dmask);
   const uint32_t bar0 = a0_smem_u32(&bars[0]);
   const uint32_t buf0 = a0_smem_u32(a0_smem);
+  int64_t p0 = g.idx[b];
+  bool ok = p0 >= 0 && p0 < g.N;
+  if (!ok) p0 = 0;
+  const int4 sa = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
+  const A0RecInfo info0 = g.rec_info[p0];
 #pragma unroll
   for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
   a0_fence_barrier_init();
+  int32_t uslot[A0_SLOTS];
+  uint32_t dmask[A0_SLOTS];
+  int U = 0;
+  {
+    int32_t s4[A0_STACK] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+    for (int j = 0; j < A0_STACK; ++j) {
+      if (s4[j] < 0 || s4[j] >= g.NF) { s4[j] = 0; ok = false; }
+      a0_unique_add(s4[j], j, uslot, dmask, U);
+    }
+  }
+  const int U0 = U;                      // <= A0_STACK == K3_RING
 #pragma unroll
   for (int u = 0; u < K3_RING; ++u)
-    if (u < U) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
+    if (u < U0) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
+  // the n-step walk and the next stack, while those loads are in flight
+  const int64_t pl = a0_walk_window(g, b, p0, info0, ok);
+  const int4 sc = reinterpret_cast<const int4*>(g.rec_slots + (size_t)pl * A0_SLOTS)[1];
+  {
+    int32_t s4[A0_STACK] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+    for (int j = 0; j < A0_STACK; ++j) {
+      if (s4[j] < 0 || s4[j] >= g.NF) { s4[j] = 0; ok = false; }
+      a0_unique_add(s4[j], A0_STACK + j, uslot, dmask, U);
+    }
+  }
+  if (!ok && g.action_out) g.action_out[b] = -1;
+#pragma unroll
+  for (int u = 0; u < K3_RING; ++u)
+    if (u >= U0 && u < U) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
   uint8_t* out = g.frames_out + (size_t)b * A0_SLOTS * F;
 #pragma unroll
   for (int u = 0; u < A0_SLOTS; ++u) {

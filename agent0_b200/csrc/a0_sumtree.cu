@@ -114,17 +114,23 @@ extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2b.  Two launches.
-//  (1) a0_k2b_write, one CTA: leaves are written with a deterministic last-writer-wins rule and the
-//      4096-leaf chunks they fall in are flagged dirty.
+// K2b.  Leaves are written with a deterministic last-writer-wins rule:
 //        mode 0: value = (loss+eps)^alpha, skipped when the leaf is 0; max_p = max(max_p, max loss)
 //        mode 1: pos >= 0 -> max_p^alpha;  pos < 0 -> leaf ~pos = 0
 //        mode 2: value = vals[k]
-//  (2) a0_k2b_rebuild, one CTA per chunk: a dirty chunk's sub-tree is recomputed bottom-up in shared
-//      memory, every node as fl32(left + right); the last CTA to finish recomputes the levels above
-//      the chunk roots.  The work does not depend on how many leaves changed (a 1 M-leaf tree is
-//      4 MB read + 4 MB written, all L2-resident) and the result is bit-reproducible: no atomics
-//      on values, no ordering dependence.
+// and every touched ancestor is recomputed as fl32(left + right) -- never a delta, so the tree is
+// bit-reproducible whatever the order of the updates.  Two implementations, same result:
+//  * count <= K2P_MAX = 16384 (the training loop: B..20*B sampled indices, a few hundred marks per
+//    append): a0_k2b_paths, ONE launch of one thread-block cluster (1..8 CTAs x 1024 threads, at
+//    most two indices per thread, held in registers); the phases are separated by the hardware
+//    cluster barrier.  After the leaf writes every index walks to the root
+//    three levels per step: a thread loads the 8 siblings under its great-grandparent (two 16-byte
+//    L2 loads), forms the 4 + 2 + 1 nodes above them and stores them; threads that share
+//    ancestors compute identical values from identical inputs, so the duplicate stores are
+//    benign.  7 dependent L2 round trips for a 2 M-leaf tree instead of 21.
+//  * larger counts (bulk fills): a0_k2b_write (one CTA) marks the 4096-leaf chunks it touched and
+//    a0_k2b_rebuild (one CTA per chunk) recomputes dirty chunks bottom-up in shared memory; the
+//    last CTA to finish recomputes the levels above the chunk roots.  Work independent of count.
 // ------------------------------------------------------------------------------------------------
 constexpr int K2B_THREADS = 1024;
 
@@ -234,11 +240,163 @@ a0_k2b_rebuild(float* __restrict__ tree, int32_t D, int32_t chunk_log, int32_t* 
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
+constexpr int K2P_THREADS = 1024;
+constexpr int K2P_CLUSTER = 8;                      // portable cluster size
+constexpr int K2P_PER_THREAD = 2;
+constexpr int K2P_MAX = K2P_THREADS * K2P_CLUSTER * K2P_PER_THREAD;   // 16384 indices per launch
+
+// All CTAs of the launch form ONE thread-block cluster, so the hardware cluster barrier is a
+// grid-wide barrier; release/acquire at cluster scope orders the L2-level (ld.cg/st.cg) accesses.
+__device__ __forceinline__ void a0_cluster_sync(bool single_cta) {
+  if (single_cta) { __syncthreads(); return; }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(K2P_THREADS)
+a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
+             const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+             float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner) {
+  const bool single = gridDim.x == 1;
+  const int gtid = blockIdx.x * K2P_THREADS + threadIdx.x;
+  const int gstride = gridDim.x * K2P_THREADS;
+  const float maxp_in = __ldcg(max_p);
+  // this thread's (at most K2P_PER_THREAD) indices, kept in registers for all phases
+  int64_t pos[K2P_PER_THREAD];
+  int kk[K2P_PER_THREAD];
+  float val[K2P_PER_THREAD];
+#pragma unroll
+  for (int s = 0; s < K2P_PER_THREAD; ++s) {
+    const int k = gtid + s * gstride;
+    kk[s] = k;
+    pos[s] = -1;
+    val[s] = 0.0f;
+    if (k < count) {
+      int64_t p;
+      bool set = true;
+      if (mode == 1) { const int32_t q = idx32[k]; set = q >= 0; p = set ? q : ~q; }
+      else p = idx64[k];
+      if (p >= 0 && p < N) {
+        pos[s] = p;
+        if (mode == 0) val[s] = vals[k];
+        else if (mode == 1) val[s] = set ? 1.0f : 0.0f;
+        else val[s] = vals[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < K2P_PER_THREAD; ++s)                   // claim
+    if (pos[s] >= 0) atomicMax(winner + pos[s], kk[s]);
+  if (mode == 0) {
+    float mx = 0.0f;
+#pragma unroll
+    for (int s = 0; s < K2P_PER_THREAD; ++s) mx = fmaxf(mx, pos[s] >= 0 ? val[s] : 0.0f);
+    mx = a0_warp_max(mx);
+    if ((threadIdx.x & 31) == 0) a0_atomic_max_pos(max_p, mx);   // max_p = max(max_p, max loss), replay.py:59
+  }
+  a0_cluster_sync(single);
+#pragma unroll
+  for (int s = 0; s < K2P_PER_THREAD; ++s) {                 // write (the highest k wins)
+    if (pos[s] < 0 || __ldcg(winner + pos[s]) != kk[s]) continue;
+    float v;
+    if (mode == 0) {
+      if (!(__ldcg(tree + P + pos[s]) > 0.0f)) continue;    // evicted since it was sampled
+      v = a0_priority(val[s], eps, alpha);
+    } else if (mode == 1) {
+      v = val[s] != 0.0f ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
+    } else {
+      v = val[s];
+    }
+    __stcg(tree + P + pos[s], v);
+  }
+  a0_cluster_sync(single);
+#pragma unroll
+  for (int s = 0; s < K2P_PER_THREAD; ++s)                   // release
+    if (pos[s] >= 0) winner[pos[s]] = -1;
+  // ---- propagate: `depth` is the level of the freshly written nodes, root = level 0 ----------------
+  int depth = D;
+  int shift = 0;                 // node of an index at `depth` = (P + pos) >> shift
+  const int first = D % 3;       // 1 or 2 levels first, then whole groups of three
+  if (first == 1) {
+#pragma unroll
+    for (int s = 0; s < K2P_PER_THREAD; ++s) {
+      if (pos[s] < 0) continue;
+      const int64_t x = (P + pos[s]) & ~(int64_t)1;
+      const float2 c2 = __ldcg(reinterpret_cast<const float2*>(tree + x));
+      __stcg(tree + (x >> 1), __fadd_rn(c2.x, c2.y));
+    }
+  } else if (first == 2) {
+#pragma unroll
+    for (int s = 0; s < K2P_PER_THREAD; ++s) {
+      if (pos[s] < 0) continue;
+      const int64_t x = (P + pos[s]) & ~(int64_t)3;
+      const float4 c4 = __ldcg(reinterpret_cast<const float4*>(tree + x));
+      const float p0 = __fadd_rn(c4.x, c4.y), p1 = __fadd_rn(c4.z, c4.w);
+      __stcg(reinterpret_cast<float2*>(tree + (x >> 1)), make_float2(p0, p1));
+      __stcg(tree + (x >> 2), __fadd_rn(p0, p1));
+    }
+  }
+  depth -= first;
+  shift += first;
+  if (first && depth > 0) a0_cluster_sync(single);
+  while (depth > 0) {            // depth is a multiple of 3 here
+    float4 lo4[K2P_PER_THREAD], hi4[K2P_PER_THREAD];
+    int64_t x[K2P_PER_THREAD];
+#pragma unroll
+    for (int s = 0; s < K2P_PER_THREAD; ++s) {
+      x[s] = ((P + (pos[s] < 0 ? 0 : pos[s])) >> shift) & ~(int64_t)7;
+      if (pos[s] >= 0) {
+        lo4[s] = __ldcg(reinterpret_cast<const float4*>(tree + x[s]));
+        hi4[s] = __ldcg(reinterpret_cast<const float4*>(tree + x[s] + 4));
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < K2P_PER_THREAD; ++s) {
+      if (pos[s] < 0) continue;
+      const float p0 = __fadd_rn(lo4[s].x, lo4[s].y), p1 = __fadd_rn(lo4[s].z, lo4[s].w);
+      const float p2 = __fadd_rn(hi4[s].x, hi4[s].y), p3 = __fadd_rn(hi4[s].z, hi4[s].w);
+      const float g0 = __fadd_rn(p0, p1), g1 = __fadd_rn(p2, p3);
+      __stcg(reinterpret_cast<float4*>(tree + (x[s] >> 1)), make_float4(p0, p1, p2, p3));
+      __stcg(reinterpret_cast<float2*>(tree + (x[s] >> 2)), make_float2(g0, g1));
+      __stcg(tree + (x[s] >> 3), __fadd_rn(g0, g1));
+    }
+    depth -= 3;
+    shift += 3;
+    if (depth > 0) a0_cluster_sync(single);
+  }
+}
+
+static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
+                           int32_t count, int32_t mode, float alpha, float eps, cudaStream_t stream) {
+  int ctas = (count + K2P_THREADS - 1) / K2P_THREADS;
+  ctas = ctas < 1 ? 1 : (ctas > K2P_CLUSTER ? K2P_CLUSTER : ctas);
+  if (ctas > 1 && (ctas & (ctas - 1))) {            // cluster sizes: powers of two
+    int p2 = 1;
+    while (p2 < ctas) p2 <<= 1;
+    ctas = p2;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(K2P_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  A0_CUDA(cudaLaunchKernelEx(&cfg, a0_k2b_paths, h->tree, h->P, h->D, h->N, idx64, idx32, vals, count, mode, alpha, eps,
+                             h->max_p, h->winner));
+  return A0_OK;
+}
+
 static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
                             int32_t count, int32_t mode, float alpha, float eps, a0_stream_t stream_) {
   if (count == 0) return A0_OK;
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (count <= K2P_MAX) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream);
   const int chunk_log = h->D < K2R_MAXLOG ? h->D : K2R_MAXLOG;
   a0_k2b_write<<<1, K2B_THREADS, 0, stream>>>(h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
                                              eps, h->max_p, h->winner, h->dirty);

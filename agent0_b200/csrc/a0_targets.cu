@@ -129,33 +129,60 @@ extern "C" int a0_loss_mdqn(const a0_loss_common_t* c, const float* q, const flo
 
 // ------------------------------------------------------------------------------------------------
 // C51 (agent.py:219-269): one warp per sample, lane l owns atoms l, l+32, ... (M <= 128).
-// The projection replaces two index_add_ calls (atomicAdd scatter on CUDA, agent.py:258-264) by a
-// fixed-order accumulation: every lane owns destination bins and scans the source atoms in the
-// order the CPU index_add_ applies them (all `lo` terms by ascending atom, then all `up` terms).
+// The projection replaces two index_add_ calls (atomicAdd scatter on CUDA, agent.py:258-264).
+// b_j = (clamp(r + g z_j) - vmin)/delta is non-decreasing in j, so the sources that fall into one
+// bin are consecutive atoms: a segmented warp scan over the lanes (keys = destination bin, five
+// shuffle steps) sums every run, and the last lane of a run adds the run total to that bin in
+// shared memory.  Four such phases (lo/up terms x two 32-atom chunks) in a fixed order give a
+// result that does not depend on scheduling; the summation order inside a run is a tree instead
+// of the CPU's left-to-right, which moves a bin by a few ulp (all terms are non-negative).
 // ------------------------------------------------------------------------------------------------
 constexpr int C51_WARPS = 4;
 constexpr int C51_MAXR = 4;     // atoms per lane: M <= 128
+
+// Adds v (keyed by destination bin) into bins[]: runs of equal adjacent keys are reduced with
+// shuffles first.  key < 0 marks a lane without a term.
+__device__ __forceinline__ void a0_c51_scatter(float* bins, int key, float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float vu = __shfl_up_sync(0xffffffffu, v, d);
+    const int ku = __shfl_up_sync(0xffffffffu, key, d);
+    if (lane >= d && ku == key) v = __fadd_rn(v, vu);
+  }
+  const int kn = __shfl_down_sync(0xffffffffu, key, 1);
+  if (key >= 0 && (lane == 31 || kn != key)) atomicAdd(bins + key, v);   // one writer per bin when keys are sorted
+  __syncwarp();
+}
 
 __global__ void __launch_bounds__(C51_WARPS * 32)
 a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __restrict__ tgt_logits,
           const float* __restrict__ qsel, const float* __restrict__ atoms, int32_t M, float vmin, float vmax,
           float* __restrict__ grad, float* __restrict__ target_prob) {
-  __shared__ float s_w[C51_WARPS][2][C51_MAXR * 32];   // per-warp source terms: weight to lo / to up
-  __shared__ int s_i[C51_WARPS][2][C51_MAXR * 32];     // per-warp source bins:  lo / up
+  __shared__ float s_m[C51_WARPS][C51_MAXR * 32];      // projected distribution of this warp's sample
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int b = blockIdx.x * C51_WARPS + wid;
   if (b >= c.B) return;
   const int A = c.A;
   const int R = (M + 31) / 32;
-  float z[C51_MAXR];
+  // independent loads first: everything below hangs off these
+  const int a = (int)c.action[b];
+  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  const float qs = (qsel && lane < A) ? qsel[(size_t)b * A + lane] : -INFINITY;
+  float z[C51_MAXR], l[C51_MAXR];
+  const float* orow = logits + ((size_t)b * A + a) * M;
 #pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k) z[k] = (k < R && lane + 32 * k < M) ? atoms[lane + 32 * k] : 0.0f;
+  for (int k = 0; k < C51_MAXR; ++k) {
+    const bool in = k < R && lane + 32 * k < M;
+    z[k] = in ? atoms[lane + 32 * k] : 0.0f;
+    l[k] = in ? orow[lane + 32 * k] : -INFINITY;
+    s_m[wid][lane + 32 * k] = 0.0f;
+  }
 
   // ---- action selection ------------------------------------------------------------------------
   int a_star;
   if (qsel) {
-    a_star = a0_warp_argmax(lane < A ? qsel[(size_t)b * A + lane] : -INFINITY, lane);
+    a_star = a0_warp_argmax(qs, lane);
   } else {
     // argmax_a sum_j softmax(tgt[b,a,:])_j * z_j (agent.py:226)
     float best = -INFINITY;
@@ -195,49 +222,43 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   for (int k = 0; k < C51_MAXR; ++k) { p[k] = (k < R && lane + 32 * k < M) ? expf(p[k] - mx) : 0.0f; se += p[k]; }
   se = a0_warp_sum(se);
 
-  // ---- per-source projection terms (agent.py:230-244) ----------------------------------------
-  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  // ---- projection (agent.py:230-264) ------------------------------------------------------------
   const float gm = __fmul_rn(c.gamma_n, __fsub_rn(1.0f, d));
   const float delta = (vmax - vmin) / (float)(M - 1);
+  int lo[C51_MAXR], up[C51_MAXR];
+  float wlo[C51_MAXR], wup[C51_MAXR];
 #pragma unroll
   for (int k = 0; k < C51_MAXR; ++k) {
-    const int j = lane + 32 * k;
-    if (k < R && j < M) {
+    lo[k] = up[k] = -1;
+    wlo[k] = wup[k] = 0.0f;
+    if (k < R && lane + 32 * k < M) {
       const float pj = __fdiv_rn(p[k], se);
       float tz = __fadd_rn(r, __fmul_rn(gm, z[k]));
       tz = fminf(fmaxf(tz, vmin), vmax);
       const float base = __fdiv_rn(__fsub_rn(tz, vmin), delta);
-      int lo = (int)floorf(base), up = (int)ceilf(base);
-      if (up > 0 && lo == up) lo -= 1;
-      if (lo < M - 1 && lo == up) up += 1;
-      s_i[wid][0][j] = lo;
-      s_i[wid][1][j] = up;
-      s_w[wid][0][j] = __fmul_rn(pj, __fsub_rn((float)up, base));
-      s_w[wid][1][j] = __fmul_rn(pj, __fsub_rn(base, (float)lo));
+      int lo_ = (int)floorf(base), up_ = (int)ceilf(base);
+      if (up_ > 0 && lo_ == up_) lo_ -= 1;
+      if (lo_ < M - 1 && lo_ == up_) up_ += 1;
+      lo[k] = lo_; up[k] = up_;
+      wlo[k] = __fmul_rn(pj, __fsub_rn((float)up_, base));
+      wup[k] = __fmul_rn(pj, __fsub_rn(base, (float)lo_));
     }
   }
   __syncwarp();
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k)
+    if (k < R) a0_c51_scatter(s_m[wid], lo[k], wlo[k], lane);
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k)
+    if (k < R) a0_c51_scatter(s_m[wid], up[k], wup[k], lane);
   float m[C51_MAXR];
 #pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k) m[k] = 0.0f;
-  for (int pass = 0; pass < 2; ++pass)
-    for (int j = 0; j < M; ++j) {
-      const int bin = s_i[wid][pass][j];
-      const float wj = s_w[wid][pass][j];
-#pragma unroll
-      for (int k = 0; k < C51_MAXR; ++k)
-        if (bin == lane + 32 * k) m[k] = __fadd_rn(m[k], wj);
-    }
+  for (int k = 0; k < C51_MAXR; ++k) m[k] = s_m[wid][lane + 32 * k];
 
   // ---- cross-entropy with the online row, gradient through log_softmax (agent.py:266-268) ------
-  const int a = (int)c.action[b];
-  const float* orow = logits + ((size_t)b * A + a) * M;
-  float l[C51_MAXR], omx = -INFINITY;
+  float omx = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k) {
-    l[k] = (k < R && lane + 32 * k < M) ? orow[lane + 32 * k] : -INFINITY;
-    omx = fmaxf(omx, l[k]);
-  }
+  for (int k = 0; k < C51_MAXR; ++k) omx = fmaxf(omx, l[k]);
   omx = a0_warp_max(omx);
   float ose = 0.0f;
 #pragma unroll
@@ -251,9 +272,9 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   ce = a0_warp_sum(ce);
   msum = a0_warp_sum(msum);
   float* grow = grad + (size_t)b * A * M;
-  for (int i = lane; i < A * M; i += 32) {
-    const int a2 = i / M;
-    if (a2 != a) grow[i] = 0.0f;
+  for (int a2 = 0; a2 < A; ++a2) {
+    if (a2 == a) continue;
+    for (int j = lane; j < M; j += 32) grow[(size_t)a2 * M + j] = 0.0f;
   }
 #pragma unroll
   for (int k = 0; k < C51_MAXR; ++k) {
@@ -353,14 +374,20 @@ a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, co
   __syncthreads();
 
   // ---- pair loop ---------------------------------------------------------------------------------
+  // With a = |u|, c = min(a, 1):  huber(u) = c * (a - c/2),  clamp(u, -1, 1) = copysign(c, u),
+  // |tau - 1[u > 0]| = u > 0 ? 1 - tau : tau   -- nine FP32 instructions per pair.
   float lsum = 0.0f, gsum = 0.0f;
   if (tid < Nj) {
-#pragma unroll 4
+    const float k_pos = 1.0f - tau, g_neg = -tau;
+#pragma unroll 8
     for (int i = 0; i < Ni; ++i) {
       const float uij = qj - sT[i];
-      const float k = fabsf(tau - (uij > 0.0f ? 1.0f : 0.0f));
-      lsum += k * a0_huber(uij);
-      gsum += k * a0_clamp1(uij);
+      const float a_ = fabsf(uij);
+      const float c_ = fminf(a_, 1.0f);
+      const float h = c_ * fmaf(-0.5f, c_, a_);
+      const bool pos = uij > 0.0f;
+      lsum = fmaf(pos ? k_pos : tau, h, lsum);
+      gsum = fmaf(pos ? k_pos : g_neg, c_, gsum);
     }
   }
   const float total = a0_block_sum(lsum, red, nwarps);

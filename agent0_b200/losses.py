@@ -5,6 +5,11 @@ Each function takes the network outputs the reference's ``train_step`` works fro
 (agent0/deepq/agent.py:172-388), ``grad`` is d[(loss*weights).sum()]/d[online output] -- so that
 ``online_out.backward(grad)`` is the reference's ``q_loss.mul(weights).sum().backward()``
 (agent.py:154) -- and ``prio`` = (loss+eps)^alpha (agent0/deepq/replay.py:56-58).
+
+The wrappers are on the per-update path (20 calls per Trainer.step), so they avoid everything
+that costs microseconds without doing work: no device context switch when the tensors already
+live on the current device, the raw stream handle, no re-validation of tensors this module
+allocated itself.
 """
 from __future__ import annotations
 
@@ -18,27 +23,58 @@ from . import _lib
 LossOut = namedtuple("LossOut", ["loss", "grad", "prio", "target_prob", "fraction_loss", "grad_taus"],
                      defaults=[None, None, None])
 
+_f32_t, _i64_t = torch.float32, torch.int64
+_byref = C.byref
+
 
 def _f32(t):
+    """float32, contiguous, detached CUDA tensor (no copy when it already is one)."""
     if t is None:
         return None
-    if t.dtype != torch.float32 or not t.is_contiguous():
-        t = t.detach().to(torch.float32).contiguous()
-    return t.detach()
+    if t.dtype is not _f32_t or not t.is_contiguous():
+        t = t.detach().to(_f32_t).contiguous()
+    elif t.requires_grad:
+        t = t.detach()
+    if not t.is_cuda:
+        raise RuntimeError("agent0_b200 kernels need CUDA tensors (there is no CPU path)")
+    return t
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class _on:
+    """``with torch.cuda.device(d)`` only when d is not already the current device (the context
+    manager costs several microseconds per K4 launch otherwise)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() \
+            else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def _common(B, A, action, reward, done, weight, gamma_n, alpha, eps, max_p):
-    dev = reward.device
-    action = action.to(torch.int64).contiguous()
+    if action.dtype is not _i64_t or not action.is_contiguous():
+        action = action.to(_i64_t).contiguous()
     reward, done, weight = _f32(reward), _f32(done), _f32(weight)
-    loss = torch.empty(B, dtype=torch.float32, device=dev)
-    prio = torch.empty(B, dtype=torch.float32, device=dev)
-    c = _lib.LossCommon(B=B, A=A, action=_lib.ptr(action, torch.int64), reward=_lib.ptr(reward),
-                        done=_lib.ptr(done), weight=_lib.ptr(weight), gamma_n=float(gamma_n),
-                        alpha=float(alpha), eps=float(eps), loss=_lib.ptr(loss), prio=_lib.ptr(prio),
-                        max_p=None if max_p is None else _lib.ptr(max_p, torch.float32))
-    keep = (action, reward, done, weight)
-    return c, loss, prio, keep
+    if action.numel() != B or reward.numel() != B or done.numel() != B or weight.numel() != B:
+        raise ValueError("action/reward/done/weight must hold one value per sample")
+    out = torch.empty((2, B), dtype=_f32_t, device=reward.device)     # loss, prio
+    loss, prio = out[0], out[1]
+    if max_p is not None and max_p.dtype is not _f32_t:
+        raise TypeError("max_p must be a float32 device scalar")
+    c = _lib.LossCommon(B, A, action.data_ptr(), reward.data_ptr(), done.data_ptr(), weight.data_ptr(),
+                        gamma_n, alpha, eps, loss.data_ptr(), prio.data_ptr(), _p(max_p))
+    return c, loss, prio, (action, reward, done, weight)
 
 
 def dqn_loss(q, qt_next, action, reward, done, weight, gamma_n, qsel=None, alpha=0.5, eps=0.01, max_p=None):
@@ -48,9 +84,10 @@ def dqn_loss(q, qt_next, action, reward, done, weight, gamma_n, qsel=None, alpha
     B, A = q.shape
     c, loss, prio, keep = _common(B, A, action, reward, done, weight, gamma_n, alpha, eps, max_p)
     grad = torch.empty_like(q)
-    with torch.cuda.device(q.device):
-        _lib.check(lib.a0_loss_dqn(C.byref(c), _lib.ptr(q), _lib.ptr(qt_next), _lib.ptr(qsel), _lib.ptr(grad),
-                                   _lib.stream_ptr(q.device)), "a0_loss_dqn")
+    dev = q.device
+    with _on(dev):
+        _lib.check(lib.a0_loss_dqn(_byref(c), q.data_ptr(), qt_next.data_ptr(), _p(qsel), grad.data_ptr(),
+                                   _lib.stream_ptr(dev)), "a0_loss_dqn")
     return LossOut(loss, grad, prio)
 
 
@@ -62,9 +99,10 @@ def mdqn_loss(q, qt_next, qt_cur, action, reward, done, weight, gamma_n, tau=0.0
     B, A = q.shape
     c, loss, prio, keep = _common(B, A, action, reward, done, weight, gamma_n, alpha, eps, max_p)
     grad = torch.empty_like(q)
-    with torch.cuda.device(q.device):
-        _lib.check(lib.a0_loss_mdqn(C.byref(c), _lib.ptr(q), _lib.ptr(qt_next), _lib.ptr(qt_cur), float(tau),
-                                    float(lo), _lib.ptr(grad), _lib.stream_ptr(q.device)), "a0_loss_mdqn")
+    dev = q.device
+    with _on(dev):
+        _lib.check(lib.a0_loss_mdqn(_byref(c), q.data_ptr(), qt_next.data_ptr(), qt_cur.data_ptr(), tau, lo,
+                                    grad.data_ptr(), _lib.stream_ptr(dev)), "a0_loss_mdqn")
     return LossOut(loss, grad, prio)
 
 
@@ -73,15 +111,17 @@ def c51_loss(logits, tgt_logits, atoms, action, reward, done, weight, gamma_n, v
     """C51Learner.train_step (agent.py:219-269).  logits/tgt_logits f32[B,A,M]; atoms f32[M]."""
     lib = _lib.load()
     logits, tgt_logits, qsel = _f32(logits), _f32(tgt_logits), _f32(qsel)
-    atoms = _f32(atoms.reshape(-1))
+    atoms = _f32(atoms)
     B, A, M = logits.shape
+    if atoms.numel() != M:
+        raise ValueError("atoms must hold num_atoms values")
     c, loss, prio, keep = _common(B, A, action, reward, done, weight, gamma_n, alpha, eps, max_p)
     grad = torch.empty_like(logits)
-    tp = torch.empty((B, M), dtype=torch.float32, device=logits.device) if want_target_prob else None
-    with torch.cuda.device(logits.device):
-        _lib.check(lib.a0_loss_c51(C.byref(c), _lib.ptr(logits), _lib.ptr(tgt_logits), _lib.ptr(qsel),
-                                   _lib.ptr(atoms), M, float(vmin), float(vmax), _lib.ptr(grad), _lib.ptr(tp),
-                                   _lib.stream_ptr(logits.device)), "a0_loss_c51")
+    dev = logits.device
+    tp = torch.empty((B, M), dtype=_f32_t, device=dev) if want_target_prob else None
+    with _on(dev):
+        _lib.check(lib.a0_loss_c51(_byref(c), logits.data_ptr(), tgt_logits.data_ptr(), _p(qsel), atoms.data_ptr(),
+                                   M, vmin, vmax, grad.data_ptr(), _p(tp), _lib.stream_ptr(dev)), "a0_loss_c51")
     return LossOut(loss, grad, prio, tp)
 
 
@@ -91,15 +131,15 @@ def _quantile(layout, q, qt, taus, qsel, Ni, Nj, A, action, reward, done, weight
     B = q.shape[0]
     c, loss, prio, keep = _common(B, A, action, reward, done, weight, gamma_n, alpha, eps, max_p)
     grad = torch.empty_like(q)
+    dev = q.device
     frac = gt = None
     if q_bar is not None:
-        frac = torch.empty(B, dtype=torch.float32, device=q.device)
-        gt = torch.empty((B, Nj + 1), dtype=torch.float32, device=q.device)
-    with torch.cuda.device(q.device):
-        _lib.check(lib.a0_loss_quantile(C.byref(c), layout, _lib.ptr(q), _lib.ptr(qt), _lib.ptr(taus),
-                                        _lib.ptr(qsel), Ni, Nj, _lib.ptr(grad), _lib.ptr(q_bar),
-                                        _lib.ptr(taus_full), _lib.ptr(frac), _lib.ptr(gt),
-                                        _lib.stream_ptr(q.device)), "a0_loss_quantile")
+        frac = torch.empty(B, dtype=_f32_t, device=dev)
+        gt = torch.empty((B, Nj + 1), dtype=_f32_t, device=dev)
+    with _on(dev):
+        _lib.check(lib.a0_loss_quantile(_byref(c), layout, q.data_ptr(), qt.data_ptr(), _p(taus), _p(qsel), Ni, Nj,
+                                        grad.data_ptr(), _p(q_bar), _p(taus_full), _p(frac), _p(gt),
+                                        _lib.stream_ptr(dev)), "a0_loss_quantile")
     return LossOut(loss, grad, prio, None, frac, gt)
 
 

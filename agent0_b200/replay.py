@@ -7,9 +7,10 @@ DataLoaderX/DataPrefetcher pump (agent0/deepq/trainer.py:63-72, agent0/common/ut
 returns device-resident tensors in the reference's 6-tuple order plus the fused IS weights;
 ``append_steps`` is the native single-frame ingest for actors that feed the shard directly.
 
-Everything on the data path is a CUDA kernel from libagent0_b200.so (K1 append, K2a sample,
-K2b update, K3 gather); this module only does the host bookkeeping (ring_index.RingIndex) and the
-pinned-memory staging.  There is no CPU fallback.
+Everything on the data path is native code from libagent0_b200.so: the CUDA kernels (K1 append,
+K2a sample, K2b update, K3 gather) and the C++ ring index + pinned staging behind
+``a0_rb_ingest_steps`` / ``a0_rb_ingest_plan``; this module marshals arguments.  There is no CPU
+fallback.
 """
 from __future__ import annotations
 
@@ -20,13 +21,23 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ring_index import ContentDeduper, RingIndex, stack_delta
+from .ring_index import ContentDeduper, NativeRingIndex, stack_delta
 
 Batch = namedtuple("Batch", ["frames", "actions", "rewards", "terminals", "priorities", "indices",
                              "weights", "rewards_f32", "terminals_f32", "boot_indices"])
 Batch.__doc__ = """One or more sampled batches, device resident.  Fields 0..5 are the reference's
 collated 6-tuple (frames u8[B,8*F], a i64, r f64, d bool, priority f32, idx i64; SURVEY 8b);
 ``weights`` are the IS weights of trainer.py:91-96, ``*_f32`` the .float() casts of trainer.py:88-90."""
+
+
+
+def split_batches(batch, batch_size):
+    """Per-update views of a multi-batch draw: a list of ``Batch`` tuples, one per learner update
+    (torch.split makes all views of a field in one call)."""
+    cols = [f.split(batch_size) if f is not None else None for f in batch]
+    k = len(cols[0])
+    return [Batch(*[(c[i] if c is not None else None) for c in cols]) for i in range(k)]
+
 
 def _is_prioritized(cfg):
     pol = cfg.replay.policy
@@ -94,7 +105,7 @@ class ReplayDataset:
         self.gamma = float(cfg.learner.discount)
         if frame_capacity is None:
             frame_capacity = int(self.size * 1.0625) + 65536 if self.size >= 65536 else 4 * self.size + 64
-        self.index = RingIndex(self.size, frame_capacity, self.n_gather, age_limit)
+        self.index = NativeRingIndex(self.size, frame_capacity, self.n_gather, age_limit)
         self.prioritize = _is_prioritized(cfg)
         self.alpha = float(cfg.replay.alpha) if self.prioritize else 1.0
         self.eps = float(cfg.replay.eps)
@@ -118,10 +129,6 @@ class ReplayDataset:
         self.max_p_tensor = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_MAX_P), (1,), "<f4", dev)
         self.priority = _PrioritySum(self)
         self._dedupe = ContentDeduper(self.index, self.F)   # reference-tuple ingest
-        self._last4 = {}               # stream -> i64[4] seqs of the current stack (native ingest)
-        self._staging = [None, None]
-        self._staging_evt = [None, None]
-        self._staging_turn = 0
         self._lz4 = None
 
     # ------------------------------------------------------------------ reference surface
@@ -191,11 +198,34 @@ class ReplayDataset:
 
     def _extend_chunk(self, streams, frames, action, reward, done):
         fs8, new_src = self._dedupe.resolve(streams, frames)
-        plan = self.index.plan(streams, fs8, new_src, action, reward, done)
-        self._execute(plan, torch.from_numpy(frames.reshape(len(streams) * 8, self.F)))
+        plan = self.index.plan_native(streams, fs8, len(new_src), action, reward, done)
+        flat = np.ascontiguousarray(frames).reshape(len(streams) * 8, self.F)
+        self._ingest_plan(plan, flat.ctypes.data, new_src, 0)
         self._dedupe.detach(streams)
 
+    def _ingest_plan(self, plan, frames_ptr, new_src, flags):
+        src = None
+        if new_src is not None and len(new_src):
+            new_src = np.ascontiguousarray(new_src, dtype=np.int64)
+            src = new_src.ctypes.data
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.a0_rb_ingest_plan(self.h, C.byref(plan), frames_ptr, src, flags, self.alpha,
+                                                  _lib.stream_ptr(self.device)), "a0_rb_ingest_plan")
+
     # ------------------------------------------------------------------ ingest: native 1-step
+    def _frames_arg(self, frames, count, pinned_stable=False):
+        """(keepalive, pointer, flags) of `count` frames given as a host array, a CPU tensor or a
+        CUDA tensor."""
+        if isinstance(frames, torch.Tensor):
+            assert frames.dtype == torch.uint8 and frames.numel() == count * self.F
+            t = frames if frames.is_contiguous() else frames.contiguous()
+            if t.is_cuda:
+                return t, t.data_ptr(), _lib.INGEST_FRAMES_ON_DEVICE
+            return t, t.data_ptr(), (_lib.INGEST_FRAMES_PINNED if pinned_stable and t.is_pinned() else 0)
+        a = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert a.size == count * self.F
+        return a, a.ctypes.data, 0
+
     def reset_streams(self, streams, stacks):
         """Give streams their initial observation stack (u8 [k,4,H,W], host or device)."""
         streams = np.asarray(streams, dtype=np.int64)
@@ -203,32 +233,32 @@ class ReplayDataset:
         ix = self.index
         seqs = ix.head_fs + np.arange(4 * k, dtype=np.int64)
         for i, sid in enumerate(streams):
-            self._last4[int(sid)] = seqs[4 * i:4 * i + 4].copy()
+            ix.set_stack(int(sid), seqs[4 * i:4 * i + 4])
         # frames only, no records
-        plan = ix.plan(np.zeros(0, dtype=np.int64), np.zeros((0, 8), dtype=np.int64),
-                       np.arange(4 * k, dtype=np.int64), [], [], [])
-        self._execute(plan, self._as_flat_frames(stacks, 4 * k))
+        z = np.zeros(0, dtype=np.int64)
+        plan = ix.plan_native(z, np.zeros((0, 8), dtype=np.int64), 4 * k, z, z.astype(np.float64), z.astype(np.bool_))
+        keep, ptr, flags = self._frames_arg(stacks, 4 * k)
+        self._ingest_plan(plan, ptr, None, flags)
 
-    def append_steps(self, streams, n_new, new_frames, action, reward, done):
+    def append_steps(self, streams, n_new, new_frames, action, reward, done, pinned_stable=False):
         """Native ingest.  For each transition (in order) the observation is the stream's current
         stack and the next observation is that stack shifted by ``n_new`` (0..4) new frames taken,
-        in order, from ``new_frames`` (u8 [sum(n_new), H, W], host or device).  ``done`` follows
-        the reference's rule (terminal | life_loss) & ~truncated (agent.py:57-62)."""
-        streams = np.asarray(streams, dtype=np.int64)
-        n_new = np.asarray(n_new, dtype=np.int64)
+        in order, from ``new_frames`` (u8 [sum(n_new), H, W]: host array, CPU tensor or CUDA
+        tensor).  ``done`` follows the reference's rule (terminal | life_loss) & ~truncated
+        (agent.py:57-62).  One C call: index update, staging, H2D copy, K2b marks and K1 append.
+        ``pinned_stable=True`` lets a page-locked CPU tensor be copied by DMA straight from the
+        caller's buffer, which must then stay untouched until the current stream has passed."""
+        streams = np.ascontiguousarray(streams, dtype=np.int64)
+        n_new = np.ascontiguousarray(n_new, dtype=np.int64)
+        action = np.ascontiguousarray(action, dtype=np.int64)
+        reward = np.ascontiguousarray(reward, dtype=np.float64)
+        done = np.ascontiguousarray(done, dtype=np.bool_)
         m = len(streams)
-        total_new = int(n_new.sum())
-        flat = self._as_flat_frames(new_frames, total_new)
-        step = self.index.max_chunk
-        f0 = 0
-        for lo in range(0, m, step):
-            hi = min(m, lo + step)
-            cnt = int(n_new[lo:hi].sum())
-            fs8 = self.index.resolve_shift(streams[lo:hi], n_new[lo:hi], self._last4)
-            plan = self.index.plan(streams[lo:hi], fs8, np.arange(cnt, dtype=np.int64),
-                                   np.asarray(action)[lo:hi], np.asarray(reward)[lo:hi], np.asarray(done)[lo:hi])
-            self._execute(plan, flat[f0:f0 + cnt])
-            f0 += cnt
+        keep, ptr, flags = self._frames_arg(new_frames, int(n_new.sum()), pinned_stable)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.a0_rb_ingest_steps(
+                self.h, self.index.h, streams.ctypes.data, n_new.ctypes.data, ptr, flags, action.ctypes.data,
+                reward.ctypes.data, done.ctypes.data, m, self.alpha, _lib.stream_ptr(self.device)), "a0_rb_ingest_steps")
         if self.prioritize:
             self.beta = self.beta_schedule(m)
 
@@ -236,75 +266,13 @@ class ReplayDataset:
         """Convenience for a gymnasium-style vector step: derives ``n_new`` by comparing stacks."""
         E = obs.shape[0]
         streams = np.arange(E, dtype=np.int64) if streams is None else np.asarray(streams, dtype=np.int64)
-        fresh = [i for i, s in enumerate(streams) if int(s) not in self._last4]
+        fresh = [i for i, s in enumerate(streams) if not self.index.has_stack(int(s))]
         if fresh:
             self.reset_streams(streams[fresh], obs[fresh])
         k = stack_delta(obs, obs_next)
         new = np.concatenate([obs_next[e, 4 - k[e]:] for e in range(E)]) if k.sum() else \
             np.zeros((0,) + tuple(obs.shape[2:]), dtype=np.uint8)
         self.append_steps(streams, k, new, action, reward, done)
-
-    def _as_flat_frames(self, frames, count):
-        if isinstance(frames, torch.Tensor):
-            t = frames.reshape(count, self.F)
-            assert t.dtype == torch.uint8
-            return t
-        return torch.from_numpy(np.ascontiguousarray(frames, dtype=np.uint8).reshape(count, self.F))
-
-    # ------------------------------------------------------------------ device execution of a plan
-    def _stage(self, nbytes):
-        turn = self._staging_turn
-        self._staging_turn ^= 1
-        if self._staging_evt[turn] is not None:
-            self._staging_evt[turn].synchronize()
-        buf = self._staging[turn]
-        if buf is None or buf[0].numel() < nbytes:
-            cap = max(int(nbytes * 1.25), 1 << 20)
-            buf = (torch.empty(cap, dtype=torch.uint8, pin_memory=True),
-                   torch.empty(cap, dtype=torch.uint8, device=self.device))
-            self._staging[turn] = buf
-        return turn, buf
-
-    def _execute(self, plan, flat_frames):
-        """Stage the plan (one pinned H2D copy) and launch K2b (marks) then K1 (append)."""
-        n_new, m, k = len(plan.new_frame_pos), plan.count, len(plan.marks)
-        if n_new == 0 and m == 0 and k == 0:
-            return
-        on_device = flat_frames.is_cuda
-        F = self.F
-        sec = [0]
-        for nbytes in ((0 if on_device else n_new * F), n_new * 4, m * _lib.A0_REC_META_I32 * 4, k * 4):
-            sec.append(sec[-1] + ((nbytes + 255) // 256) * 256)
-        turn, (pin, dev) = self._stage(sec[-1])
-        pin_np = pin.numpy()
-        if n_new and not on_device:
-            src = flat_frames.numpy()
-            np.take(src, plan.new_frame_src, axis=0, out=pin_np[sec[0]:sec[0] + n_new * F].reshape(n_new, F))
-        pin_np[sec[1]:sec[1] + n_new * 4].view(np.int32)[:] = plan.new_frame_pos
-        pin_np[sec[2]:sec[2] + m * _lib.A0_REC_META_I32 * 4].view(np.int32)[:] = plan.rec_meta.reshape(-1)
-        pin_np[sec[3]:sec[3] + k * 4].view(np.int32)[:] = plan.marks
-        with torch.cuda.device(self.device):
-            dev[:sec[-1]].copy_(pin[:sec[-1]], non_blocking=True)
-            stream = _lib.stream_ptr(self.device)
-            base = dev.data_ptr()
-            if on_device and n_new:
-                src_idx = torch.from_numpy(plan.new_frame_src).to(self.device, non_blocking=True)
-                staged = flat_frames.index_select(0, src_idx) if not _is_arange(plan.new_frame_src, flat_frames.shape[0]) \
-                    else flat_frames
-                staged = staged.contiguous()
-                frames_ptr = staged.data_ptr()
-            else:
-                staged = None
-                frames_ptr = base + sec[0]
-            if k:
-                _lib.check(self.lib.a0_pt_mark(self.h, base + sec[3], k, self.alpha, stream), "a0_pt_mark")
-            _lib.check(self.lib.a0_rb_append(self.h, frames_ptr if n_new else None, base + sec[1] if n_new else None,
-                                             n_new, base + sec[2] if m else None, m, stream), "a0_rb_append")
-            evt = torch.cuda.Event()
-            evt.record()
-            self._staging_evt[turn] = evt
-            if staged is not None:
-                staged.record_stream(torch.cuda.current_stream(self.device))
 
     # ------------------------------------------------------------------ sample / gather
     def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None):
@@ -379,10 +347,6 @@ class ReplayDataset:
         with torch.cuda.device(dev):
             _lib.check(self.lib.a0_pt_set(self.h, ids.data_ptr(), values.data_ptr(), ids.numel(),
                                           _lib.stream_ptr(dev)), "a0_pt_set")
-
-
-def _is_arange(a, n):
-    return len(a) == n and (n == 0 or (a[0] == 0 and a[-1] == n - 1 and bool((np.diff(a) == 1).all())))
 
 
 def _liblz4_block_decompress(blob):

@@ -253,3 +253,95 @@ def stack_delta(prev_stack, next_stack):
         ok = (q[:, :4 - cand] == p[:, cand:]).all(axis=(1, 2))
         k = np.where(ok, cand, k)
     return k
+
+
+class NativeRingIndex:
+    """The same index, implemented in C++ inside libagent0_b200.so (csrc/a0_ingest.cu) so that an
+    append costs microseconds of host time instead of ~0.6 ms of numpy; this is the one
+    ``ReplayDataset`` uses.  ``RingIndex`` above stays as the executable specification:
+    tests/test_ring_index.py drives both with the same streams and requires identical plans."""
+
+    def __init__(self, rec_capacity, frame_capacity, n_step=1, age_limit=None):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._L = C, _lib
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.a0_ix_create(C.byref(h), int(rec_capacity), int(frame_capacity), int(n_step),
+                                         -1 if age_limit is None else int(age_limit)), "a0_ix_create")
+        self.h = h
+        self._state = np.zeros(_lib.IX_STATE_WORDS, dtype=np.int64)
+        self._refresh()
+        st = self._state
+        self.N, self.NF, self.n = int(st[_lib.IX_REC_CAPACITY]), int(st[_lib.IX_FRAME_CAPACITY]), int(st[_lib.IX_NSTEP])
+        self.age_limit, self.max_chunk = int(st[_lib.IX_AGE_LIMIT]), int(st[_lib.IX_MAX_CHUNK])
+        buf = (C.c_uint8 * self.N).from_address(self.lib.a0_ix_sampleable(h))
+        self.sampleable = np.frombuffer(buf, dtype=np.uint8).view(np.bool_)      # live view of host state
+        self._plan = _lib.Plan()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.lib.a0_ix_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _refresh(self):
+        self.lib.a0_ix_state(self.h, self._state.ctypes.data)
+
+    head_q = property(lambda self: (self._refresh(), int(self._state[0]))[1])
+    tail_q = property(lambda self: (self._refresh(), int(self._state[1]))[1])
+    head_fs = property(lambda self: (self._refresh(), int(self._state[2]))[1])
+    top = property(lambda self: (self._refresh(), int(self._state[3]))[1])
+
+    def frame_resident(self, fs):
+        return fs >= self.head_fs - self.NF
+
+    def set_stack(self, stream, seq4):
+        seq4 = np.ascontiguousarray(seq4, dtype=np.int64)
+        self._L.check(self.lib.a0_ix_set_stack(self.h, int(stream), seq4.ctypes.data), "a0_ix_set_stack")
+
+    def get_stack(self, stream):
+        out = np.empty(4, dtype=np.int64)
+        return out if self.lib.a0_ix_get_stack(self.h, int(stream), out.ctypes.data) == 0 else None
+
+    def has_stack(self, stream):
+        return self.get_stack(stream) is not None
+
+    def resolve_shift(self, stream, n_new, last4=None):
+        """``last4`` (dict stream -> i64[4]) is honoured for interface parity with RingIndex: its
+        stacks are pushed into the native index before and read back after the call."""
+        stream = np.ascontiguousarray(stream, dtype=np.int64)
+        n_new = np.ascontiguousarray(n_new, dtype=np.int64)
+        m = len(stream)
+        if last4 is not None:
+            for sid in set(stream.tolist()):
+                self.set_stack(sid, last4[sid])
+        fs8 = np.empty((m, SLOTS), dtype=np.int64)
+        self._L.check(self.lib.a0_ix_resolve_shift(self.h, stream.ctypes.data, n_new.ctypes.data, m, fs8.ctypes.data),
+                      "a0_ix_resolve_shift")
+        if last4 is not None:
+            for sid in set(stream.tolist()):
+                last4[sid] = self.get_stack(sid)
+        return fs8
+
+    def plan_native(self, stream, fs8, n_new, action, reward, done):
+        """a0_ix_plan; returns the ctypes a0_plan_t (arrays owned by the index until its next call)."""
+        stream = np.ascontiguousarray(stream, dtype=np.int64)
+        fs8 = np.ascontiguousarray(fs8, dtype=np.int64)
+        action = np.ascontiguousarray(action, dtype=np.int64)
+        reward = np.ascontiguousarray(reward, dtype=np.float64)
+        done = np.ascontiguousarray(done, dtype=np.bool_).view(np.uint8)
+        m = len(stream)
+        self._L.check(self.lib.a0_ix_plan(self.h, stream.ctypes.data, fs8.ctypes.data, m, int(n_new), action.ctypes.data,
+                                          reward.ctypes.data, done.ctypes.data, self._C.byref(self._plan)), "a0_ix_plan")
+        return self._plan
+
+    def plan(self, stream, fs8, new_src, action, reward, done):
+        new_src = np.asarray(new_src, dtype=np.int64)
+        p = self.plan_native(stream, fs8, len(new_src), action, reward, done)
+        arr = lambda ptr, k: np.ctypeslib.as_array(ptr, shape=(k,)).copy() if k else np.zeros(0, dtype=np.int32)
+        return AppendPlan(new_src, arr(p.new_frame_pos, p.n_new), arr(p.rec_meta, p.m * META_I32).reshape(p.m, META_I32),
+                          arr(p.marks, p.n_marks), p.m)

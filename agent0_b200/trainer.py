@@ -11,7 +11,7 @@ sample several batches ahead with a fork-time snapshot of the priorities (SURVEY
 from __future__ import annotations
 
 from .learner import make_learner
-from .replay import ReplayDataset
+from .replay import ReplayDataset, split_batches
 
 
 class Trainer:
@@ -30,12 +30,9 @@ class Trainer:
         cfg = self.cfg
         L = int(learner_steps or cfg.learner.learner_steps)
         B = cfg.learner.batch_size
-        batch = self.replay.sample(B, k_batches=L)
         out = []
-        for k in range(L):
-            s = slice(k * B, (k + 1) * B)
-            data = (batch.frames[s], batch.actions[s], batch.rewards_f32[s], batch.terminals_f32[s],
-                    batch.weights[s], batch.indices[s])
+        for b in split_batches(self.replay.sample(B, k_batches=L), B):
+            data = (b.frames, b.actions, b.rewards_f32, b.terminals_f32, b.weights, b.indices)
             result = self.learner.train(data)
             self.replay.update_priority(result["indices"], result["q_loss"])
             out.append((result["q_loss"], result["fraction_loss"]))

@@ -329,28 +329,34 @@ def e2e_loop(rp, wl, L, A, steps, warmup, torch):
     h2d = new_per_step * (F_BYTES + 14 * 4 + 4)
     d2h = total * (4 + 8)
 
+    from agent0_b200.replay import split_batches
+    os_ = {k: (v.split(B) if v.dim() and v.shape[0] == total else v) for k, v in o.items()}
+    use_qsel = wl["double"] or algo in ("iqn", "fqf")
+    kw = dict(max_p=rp.max_p_tensor)
+    ones_new = np.ones(new_per_step, dtype=np.int64)
+    zr, zd = np.zeros(new_per_step), np.zeros(new_per_step, dtype=bool)
+
     def one():
-        rp.append_steps(streams, np.ones(new_per_step, dtype=np.int64), host_frames, rng.randint(0, 4, new_per_step),
-                        np.zeros(new_per_step), np.zeros(new_per_step, dtype=bool))
+        # the step's inputs come from pinned host memory; the ingest DMA reads the caller's buffer directly
+        rp.append_steps(streams, ones_new, host_frames, rng.randint(0, 4, new_per_step), zr, zd, pinned_stable=True)
         b = rp.sample(B, k_batches=L)
         outs = []
-        for k in range(L):
-            s = slice(k * B, (k + 1) * B)
-            cm = (b.actions[s], b.rewards_f32[s], b.terminals_f32[s], b.weights[s], gam)
-            kw = dict(max_p=rp.max_p_tensor)
-            qs = o["qsel"][s] if wl["double"] or algo in ("iqn", "fqf") else None
+        for k, bk in enumerate(split_batches(b, B)):
+            cm = (bk.actions, bk.rewards_f32, bk.terminals_f32, bk.weights, gam)
+            qs = os_["qsel"][k] if use_qsel else None
             if algo == "dqn":
-                r = LS.dqn_loss(o["online"][s], o["tgt_next"][s], *cm, qsel=qs, **kw)
+                r = LS.dqn_loss(os_["online"][k], os_["tgt_next"][k], *cm, qsel=qs, **kw)
             elif algo == "mdqn":
-                r = LS.mdqn_loss(o["online"][s], o["tgt_next"][s], o["tgt_cur"][s], *cm, **kw)
+                r = LS.mdqn_loss(os_["online"][k], os_["tgt_next"][k], os_["tgt_cur"][k], *cm, **kw)
             elif algo == "c51":
-                r = LS.c51_loss(o["online"][s], o["tgt_next"][s], o["atoms"], *cm, -10.0, 10.0, qsel=qs, **kw)
+                r = LS.c51_loss(os_["online"][k], os_["tgt_next"][k], os_["atoms"], *cm, -10.0, 10.0, qsel=qs, **kw)
             elif algo == "qr":
-                r = LS.qr_loss(o["online"][s], o["tgt_next"][s], *cm, qsel=qs, **kw)
+                r = LS.qr_loss(os_["online"][k], os_["tgt_next"][k], *cm, qsel=qs, **kw)
             elif algo == "iqn":
-                r = LS.iqn_loss(o["online"][s], o["taus"][s], o["tgt_next"][s], qs, *cm, **kw)
+                r = LS.iqn_loss(os_["online"][k], os_["taus"][k], os_["tgt_next"][k], qs, *cm, **kw)
             else:
-                r = LS.fqf_loss(o["online"][s], o["taus"][s], o["taus_hat"][s], o["tgt_next"][s], o["q_bar"][s], qs, *cm, **kw)
+                r = LS.fqf_loss(os_["online"][k], os_["taus"][k], os_["taus_hat"][k], os_["tgt_next"][k], os_["q_bar"][k], qs,
+                                *cm, **kw)
             outs.append(r.loss)
         loss = torch.cat(outs)
         rp.update_priority(b.indices, loss)

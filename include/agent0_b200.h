@@ -11,7 +11,9 @@
  *
  * Reference interfaces replaced (paths relative to the reference repo):
  *   agent0/deepq/replay.py:15-27   ReplayDataset.__init__          -> a0_rb_create / a0_rb_destroy
- *   agent0/deepq/replay.py:45-53   ReplayDataset.extend            -> a0_rb_append + a0_pt_mark
+ *   agent0/deepq/replay.py:45-53   ReplayDataset.extend            -> a0_ix_plan + a0_rb_ingest_plan
+ *                                                                     (= a0_pt_mark + a0_rb_append), or
+ *                                                                     a0_rb_ingest_steps for 1-step actors
  *   agent0/deepq/replay.py:39-43   ReplayDataset.__iter__ (draw)   -> a0_pt_sample
  *   agent0/deepq/replay.py:32-37   ReplayDataset.__getitem__ + default_collate, and
  *   agent0/deepq/agent.py:64-73    Actor.sample's n-step tracker   -> a0_rb_gather
@@ -33,7 +35,8 @@
 extern "C" {
 #endif
 
-typedef struct a0_replay a0_replay_t;    /* opaque shard handle */
+typedef struct a0_replay a0_replay_t;    /* opaque shard handle (device state) */
+typedef struct a0_index a0_index_t;      /* opaque ring index (host state, no CUDA calls) */
 typedef void* a0_stream_t;               /* cudaStream_t */
 
 #define A0_OK 0
@@ -82,6 +85,60 @@ int64_t a0_rb_tree_leaves(a0_replay_t* h);      /* P = next_pow2(rec_capacity) *
 int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames /* dev */,
                  const int32_t* new_frame_pos /* dev */, int32_t n_new,
                  const int32_t* rec_meta /* dev */, int32_t m, a0_stream_t stream);
+
+/* ---- host ring index ------------------------------------------------------------------------------
+ * Pure host code (usable without a GPU).  Decides, for every appended transition, where its new
+ * frames go, which records become sampleable and which must be evicted because their slot or
+ * their frames are about to be overwritten; the device only executes the plan.  Replaces the
+ * bookkeeping of ReplayDataset.extend (replay.py:45-53) and the "entry k-n+1 is emitted at step k"
+ * rule of the actor's n-step tracker (agent.py:64-73).
+ * n_step: records gathered per sample (1 when the caller appends already-folded reference entries).
+ * age_limit: frames older than this are never referenced by a new record (< 0: default).        */
+int a0_ix_create(a0_index_t** out, int64_t rec_capacity, int64_t frame_capacity, int32_t n_step,
+                 int64_t age_limit);
+int a0_ix_destroy(a0_index_t* ix);
+enum { A0_IX_HEAD_Q = 0, A0_IX_TAIL_Q = 1, A0_IX_HEAD_FS = 2, A0_IX_TOP = 3, A0_IX_REC_CAPACITY = 4,
+       A0_IX_FRAME_CAPACITY = 5, A0_IX_NSTEP = 6, A0_IX_AGE_LIMIT = 7, A0_IX_MAX_CHUNK = 8,
+       A0_IX_STATE_WORDS = 9 };
+int a0_ix_state(a0_index_t* ix, int64_t* out /* [A0_IX_STATE_WORDS] */);
+const uint8_t* a0_ix_sampleable(a0_index_t* ix);          /* host u8[rec_capacity], 1 = sampleable */
+/* current observation stack of a stream, as frame sequence numbers */
+int a0_ix_set_stack(a0_index_t* ix, int64_t stream, const int64_t* seq4);
+int a0_ix_get_stack(a0_index_t* ix, int64_t stream, int64_t* seq4);   /* returns 1 if none yet */
+/* Structural description of m transitions: the observation of transition i is its stream's
+ * current stack, the next observation that stack shifted by n_new[i] (0..4) new frames; new
+ * frames are numbered from head_fs in (transition, frame) order.  fs8_out i64[m][8].            */
+int a0_ix_resolve_shift(a0_index_t* ix, const int64_t* stream, const int64_t* n_new, int32_t m,
+                        int64_t* fs8_out);
+typedef struct {
+  int32_t m, n_new, n_marks;
+  const int32_t* new_frame_pos;   /* [n_new]  frame-ring positions of the new frames            */
+  const int32_t* rec_meta;        /* [m][14]  a0_rb_append layout                               */
+  const int32_t* marks;           /* [n_marks] a0_pt_mark layout: >= 0 sampleable, < 0 ~evicted */
+} a0_plan_t;                      /* arrays are owned by the index, valid until its next call   */
+/* Commit m transitions whose 8 frame sequence numbers are resolved (fs8 i64[m][8]; the n_new
+ * new ones numbered upwards from head_fs).  m must not exceed A0_IX_MAX_CHUNK.                  */
+int a0_ix_plan(a0_index_t* ix, const int64_t* stream, const int64_t* fs8, int32_t m, int32_t n_new,
+               const int64_t* action, const double* reward, const uint8_t* done, a0_plan_t* out);
+
+/* ---- staged ingest: execute a plan on the device ------------------------------------------------
+ * One pinned H2D copy of {frames, positions, record metadata, marks} from a double-buffered
+ * staging area owned by the handle, then a0_pt_mark and a0_rb_append on `stream`.  frames:
+ * host u8[*][frame_bytes]; new_frame_src (host, optional) picks the n_new frames to store, in
+ * allocation order, out of it (NULL: the first n_new).  Flags: FRAMES_ON_DEVICE = frames is a
+ * device pointer already in allocation order; FRAMES_PINNED = frames is page-locked host memory
+ * in allocation order that stays untouched until `stream` has passed this call (it is copied by
+ * DMA straight from there, no staging memcpy).                                                   */
+#define A0_INGEST_FRAMES_ON_DEVICE 1
+#define A0_INGEST_FRAMES_PINNED 2
+int a0_rb_ingest_plan(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames,
+                      const int64_t* new_frame_src, int32_t flags, float alpha, a0_stream_t stream);
+/* a0_ix_resolve_shift + a0_ix_plan + a0_rb_ingest_plan for m 1-step transitions (any m: split
+ * into chunks internally); all arrays are host arrays except new_frames under FRAMES_ON_DEVICE. */
+int a0_rb_ingest_steps(a0_replay_t* h, a0_index_t* ix, const int64_t* stream, const int64_t* n_new,
+                       const uint8_t* new_frames, int32_t flags, const int64_t* action,
+                       const double* reward, const uint8_t* done, int32_t m, float alpha,
+                       a0_stream_t cuda_stream);
 
 /* ---- K2b: sum-tree leaf writes ---------------------------------------------------------------------
  * a0_pt_mark: pos[k] >= 0 -> leaf = max_p^alpha (a newly sampleable record, replay.py:52);

@@ -118,7 +118,8 @@ def test_sumtree_sample_update_bit_exact():
     ref.set(np.arange(N), pr)
     rp.set_priorities(torch.arange(N), torch.as_tensor(pr))
     assert np.array_equal(_np(rp.tree)[:2 * ref.P], ref.nodes)
-    rp.index.top = int((pr > 0).sum())
+    import types
+    rp.index = types.SimpleNamespace(top=int((pr > 0).sum()))      # leaves were set directly, not appended
     for B, K in ((32, 1), (512, 1), (32, 20), (7, 3)):
         u = rng.rand(B * K).astype(np.float32)
         idx = torch.empty(B * K, dtype=torch.int64, device="cuda")
@@ -152,6 +153,30 @@ def test_sumtree_sample_update_bit_exact():
         np.add.at(counts, _np(b.indices), 1)
     law = ref.leaves().astype(np.float64); law /= law.sum()
     assert np.corrcoef(counts / counts.sum(), law)[0, 1] > 0.95
+
+
+@pytest.mark.parametrize("N", [2048, 4096, 70000])
+def test_sumtree_update_paths_all_depths_and_sizes(N):
+    """K2b at tree depths with D % 3 = 2, 0, 2... and at every launch shape: one CTA, a cluster of
+    up to 8 CTAs, and the chunk-rebuild fallback above 16384 indices -- always the oracle's tree."""
+    rp = _replay(N, per=True)
+    rng = np.random.RandomState(N)
+    ref = SumTree(N)
+    pr = (rng.rand(N).astype(np.float32) + 0.1)
+    ref.set(np.arange(N), pr)
+    for lo in range(0, N, 30000):                      # > 16384 per call: write + rebuild kernels
+        hi = min(N, lo + 30000)
+        rp.set_priorities(torch.arange(lo, hi), torch.as_tensor(pr[lo:hi]))
+    assert np.array_equal(_np(rp.tree)[:2 * ref.P], ref.nodes)
+    for count in (1, 31, 1024, 1025, 3000, 10240, 16384, 16385):
+        ids = rng.randint(0, N, count).astype(np.int64)
+        if count > 8:
+            ids[-3:] = ids[0]                               # duplicates: the last one wins
+        loss = (np.abs(rng.randn(count)) * 2).astype(np.float32)
+        rp.update_priority(torch.as_tensor(ids), torch.as_tensor(loss))
+        ref.set(ids, new_priority(loss, 0.01, 0.5))
+        assert np.array_equal(_np(rp.tree)[:2 * ref.P], ref.nodes), count
+    assert rp.max_p >= 1.0
 
 
 def test_per_bookkeeping_new_entries_beta_and_compat_sum(golden):

@@ -3,12 +3,15 @@ the reference's actor packing + deque (golden-pinned in test_oracle_golden.py)."
 import numpy as np
 import pytest
 
-from agent0_b200.ring_index import ContentDeduper, RingIndex, stack_delta
+from agent0_b200.ring_index import ContentDeduper, NativeRingIndex, RingIndex, stack_delta
 from agent0_b200.synth import record_stream
 from oracle import reference_replay as OR
 from tests.ring_sim import SimDevice
 
 F = 64   # small frames keep the CPU suite fast; the index logic is frame-size independent
+
+# every test runs against the numpy specification and the C++ index inside libagent0_b200.so
+IMPLS = pytest.mark.parametrize("Index", [RingIndex, NativeRingIndex], ids=["spec", "native"])
 
 
 def _stream(E, T, seed):
@@ -28,13 +31,14 @@ def test_stack_delta():
         assert np.array_equal(d == 4, special) and set(np.unique(d)) <= {1, 4}
 
 
+@IMPLS
 @pytest.mark.parametrize("n", [1, 3])
-def test_compat_extend_equals_reference_entries(golden, n):
+def test_compat_extend_equals_reference_entries(golden, n, Index):
     """Reference tuples in, gather(i) == reference entry i, bit for bit (full-size golden frames)."""
     g = golden(f"replay_n{n}")
     Fg = 84 * 84
     M = len(g["entry_action"])
-    ix = RingIndex(256, 2048, n_step=1)
+    ix = Index(256, 2048, n_step=1)
     dd = ContentDeduper(ix, Fg)
     dev = SimDevice(256, 2048, Fg)
     E = int(g["num_envs"])
@@ -56,15 +60,16 @@ def test_compat_extend_equals_reference_entries(golden, n):
         assert np.float64(r).view(np.int64) == g["entry_reward"][i].view(np.int64)
 
 
+@IMPLS
 @pytest.mark.parametrize("n", [1, 3])
-def test_native_ingest_equals_reference_entries(golden, n):
+def test_native_ingest_equals_reference_entries(golden, n, Index):
     """1-step records in, n-step gather out == the reference actor's folded entries (Appendix C)."""
     g = golden(f"replay_n{n}")
     Fg = 84 * 84
     E, T = int(g["num_envs"]), int(g["steps"])
     obs = g["stream_obs"]
     done = OR.done_rule(g["stream_terminal"], g["stream_life_loss"], g["stream_truncated"])
-    ix = RingIndex(256, 2048, n_step=n)
+    ix = Index(256, 2048, n_step=n)
     dev = SimDevice(256, 2048, Fg)
     last4 = {}
     streams = np.arange(E, dtype=np.int64)
@@ -95,14 +100,15 @@ def test_native_ingest_equals_reference_entries(golden, n):
     assert dev.leaf[(T - n + 1) * E:T * E].sum() == 0
 
 
+@IMPLS
 @pytest.mark.parametrize("n,N,NF", [(1, 50, 160), (3, 64, 200), (2, 40, 4000)])
-def test_wraparound_validity(n, N, NF):
+def test_wraparound_validity(n, N, NF, Index):
     """Long stream through a small ring: every record the index calls sampleable gathers exactly
     what a brute-force history says; evicted records have zero leaves; `top` counts them."""
     E, T = 3, 160
     s = _stream(E, T, seed=9 + n)
     frames_ref, a_ref, r_ref, d_ref = _entries(s, n)
-    ix = RingIndex(N, NF, n_step=n, age_limit=16)
+    ix = Index(N, NF, n_step=n, age_limit=16)
     dev = SimDevice(N, NF, F)
     last4 = {}
     seqs = ix.head_fs + np.arange(4 * E)
@@ -132,13 +138,14 @@ def test_wraparound_validity(n, N, NF):
     assert seen_full and ix.top > 0 and ix.top <= N
 
 
-def test_compat_wraparound_small_ring():
+@IMPLS
+def test_compat_wraparound_small_ring(Index):
     """Reference-tuple ingest through a ring that wraps several times."""
     E, T, n = 2, 120, 3
     s = _stream(E, T, seed=4)
     frames_ref, a_ref, r_ref, d_ref = _entries(s, n)
     N, NF = 48, 150
-    ix = RingIndex(N, NF, n_step=1, age_limit=12)
+    ix = Index(N, NF, n_step=1, age_limit=12)
     dd = ContentDeduper(ix, F)
     dev = SimDevice(N, NF, F)
     M = len(a_ref)
@@ -154,3 +161,53 @@ def test_compat_wraparound_small_ring():
             got, a, r, d, _ = dev.gather(int(pos), 1, 0.99)
             assert np.array_equal(got, frames_ref[q]) and a == a_ref[q] and d == d_ref[q]
     assert ix.tail_q > 0 and 0 < ix.top <= N
+
+
+@pytest.mark.parametrize("n,N,NF,age", [(1, 64, 300, 16), (3, 48, 220, 12), (4, 200, 5000, 64), (2, 16, 120, 8)])
+def test_native_index_emits_the_same_plans_as_the_specification(n, N, NF, age):
+    """Differential test: random multi-stream appends (uneven chunks, idle streams that resume
+    after the age limit, 0..4 new frames per step) through both implementations; every plan array
+    and the whole index state must agree."""
+    rng = np.random.RandomState(100 + n)
+    spec, nat = RingIndex(N, NF, n, age), NativeRingIndex(N, NF, n, age)
+    assert spec.max_chunk == nat.max_chunk
+    S = 5
+    last4 = {}
+    seqs = np.arange(4 * S, dtype=np.int64)
+    for ix in (spec, nat):
+        p = ix.plan(np.zeros(0, np.int64), np.zeros((0, 8), np.int64), np.arange(4 * S), [], [], [])
+        assert len(p.new_frame_pos) == 4 * S
+    for sid in range(S):
+        last4[sid] = seqs[4 * sid:4 * sid + 4].copy()
+        nat.set_stack(sid, last4[sid])
+    for it in range(300):
+        m = int(rng.randint(1, spec.max_chunk + 1))
+        active = rng.choice(S, size=int(rng.randint(1, S + 1)), replace=False)     # some streams idle for a while
+        stream = rng.choice(active, size=m).astype(np.int64)
+        n_new = rng.choice([0, 1, 1, 1, 2, 4], size=m).astype(np.int64)
+        action = rng.randint(0, 18, m)
+        reward = rng.randn(m)
+        done = rng.rand(m) < 0.1
+        fa = spec.resolve_shift(stream, n_new, last4)
+        fb = nat.resolve_shift(stream, n_new)
+        assert np.array_equal(fa, fb)
+        k = int(n_new.sum())
+        pa = spec.plan(stream, fa, np.arange(k), action, reward, done)
+        pb = nat.plan(stream, fb, np.arange(k), action, reward, done)
+        assert np.array_equal(pa.new_frame_pos, pb.new_frame_pos), it
+        assert np.array_equal(pa.rec_meta, pb.rec_meta), it
+        assert np.array_equal(pa.marks, pb.marks), it
+        assert (spec.head_q, spec.tail_q, spec.head_fs, spec.top) == (nat.head_q, nat.tail_q, nat.head_fs, nat.top)
+        assert np.array_equal(spec.sampleable, nat.sampleable)
+    assert spec.tail_q > 0
+
+
+def test_native_index_argument_errors():
+    nat = NativeRingIndex(64, 300, 1, 16)
+    with pytest.raises(RuntimeError, match="too large"):
+        m = nat.max_chunk + 1
+        nat.plan(np.zeros(m, np.int64), np.zeros((m, 8), np.int64), [], np.zeros(m), np.zeros(m), np.zeros(m, bool))
+    with pytest.raises(RuntimeError, match="no observation stack"):
+        nat.resolve_shift(np.array([7]), np.array([1]))
+    with pytest.raises(RuntimeError):
+        NativeRingIndex(64, 20, 1, 16)        # frame ring smaller than twice the age limit
