@@ -41,6 +41,7 @@ INGEST_FRAMES_ON_DEVICE, INGEST_FRAMES_PINNED = 1, 2
 SIGNATURES = {
     "a0_version": (_i32, []),
     "a0_last_error": (C.c_char_p, []),
+    "a0_set_option": (_i32, [_i32, _i64]),
     "a0_rb_create": (_i32, [C.POINTER(_vp), _i64, _i64, _i32, _i32]),
     "a0_rb_destroy": (_i32, [_vp]),
     "a0_rb_reset": (_i32, [_vp, _vp]),

@@ -73,6 +73,58 @@ void a0_set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
+// ---- launches ---------------------------------------------------------------------------------------
+// Every hot-path kernel is launched with programmatic stream serialization (PDL): it may become
+// resident while its predecessor in the stream drains, executes griddepcontrol.wait as its first
+// instruction (full completion + visibility of everything before it, so stream-order semantics
+// are unchanged) and immediately lets its own successor start launching.  What this removes is
+// the launch gap between the ~25 short dependent kernels of one Trainer.step, eagerly and inside
+// CUDA graphs.  a0_set_option(A0_OPT_PDL, 0) or A0_PDL=0 in the environment turns it off.
+bool a0_pdl_enabled();
+
+#define A0_PDL_PROLOGUE()                                   \
+  do {                                                      \
+    asm volatile("griddepcontrol.wait;" ::: "memory");      \
+    asm volatile("griddepcontrol.launch_dependents;");      \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t a0_launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                    cudaStream_t stream, unsigned cluster, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (a0_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define A0_LAUNCH(...)                                                          \
+  do {                                                                          \
+    cudaError_t _e = a0_launch(__VA_ARGS__);                                    \
+    if (_e != cudaSuccess) {                                                    \
+      a0_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),  \
+                   __FILE__, __LINE__);                                         \
+      return (int)_e;                                                           \
+    }                                                                           \
+  } while (0)
+
 struct A0DeviceGuard {
   int prev;
   explicit A0DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); else prev = -1; }

@@ -8,6 +8,7 @@
 // A transition costs 7056 B of frame data (one new frame) + 48 B of record instead of the
 // reference's self-contained 56 448 B blob.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "a0_common.cuh"
 
@@ -19,7 +20,21 @@ void a0_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* a0_last_error(void) { return g_err; }
-extern "C" int a0_version(void) { return 100; }
+extern "C" int a0_version(void) { return 101; }
+
+static int g_pdl = -1;     // -1: not decided yet (environment), 0 off, 1 on
+bool a0_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("A0_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+extern "C" int a0_set_option(int32_t option, int64_t value) {
+  A0_REQUIRE(option == A0_OPT_PDL, "a0_set_option: unknown option %d", option);
+  g_pdl = value ? 1 : 0;
+  return A0_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // lifetime
@@ -129,6 +144,7 @@ __global__ void __launch_bounds__(K1_THREADS)
 a0_k1_append(uint8_t* __restrict__ frames, int32_t F, int64_t NF, const uint8_t* __restrict__ staged,
              const int32_t* __restrict__ new_pos, int32_t n_new, int32_t* __restrict__ rec_slots,
              A0RecInfo* __restrict__ rec_info, int64_t N, const int32_t* __restrict__ meta, int32_t m) {
+  A0_PDL_PROLOGUE();
   if ((int)blockIdx.x < n_new) {
     const int f = blockIdx.x;
     const int32_t pos = new_pos[f];
@@ -166,9 +182,8 @@ extern "C" int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames, const int
   A0_REQUIRE(((uintptr_t)new_frames & 15) == 0, "a0_rb_append: new_frames must be 16-byte aligned");
   A0DeviceGuard guard(h->device);
   const int blocks = n_new + (m + K1_THREADS - 1) / K1_THREADS;
-  a0_k1_append<<<blocks, K1_THREADS, 0, (cudaStream_t)stream_>>>(
-      h->frames, h->F, h->NF, new_frames, new_frame_pos, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m);
-  A0_LAUNCH_CHECK();
+  A0_LAUNCH(a0_k1_append, (unsigned)blocks, K1_THREADS, 0, (cudaStream_t)stream_, 1, h->frames, h->F, h->NF, new_frames,
+            new_frame_pos, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m);
   return A0_OK;
 }
 
@@ -316,6 +331,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   extern __shared__ __align__(128) uint8_t a0_smem[];
   __shared__ __align__(8) uint64_t bars[K3_RING];
   if (threadIdx.x != 0) return;
+  A0_PDL_PROLOGUE();
   const int b = blockIdx.x;
   const uint32_t F = (uint32_t)g.F;
   const uint32_t bar0 = a0_smem_u32(&bars[0]);
@@ -384,6 +400,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma_full(const A0GatherArgs g
   extern __shared__ __align__(128) uint8_t a0_smem[];
   __shared__ __align__(8) uint64_t bar;
   if (threadIdx.x != 0) return;
+  A0_PDL_PROLOGUE();
   const int b = blockIdx.x;
   int32_t slot[A0_SLOTS];
   a0_resolve_window(g, b, slot);
@@ -417,6 +434,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma_full(const A0GatherArgs g
 constexpr int K3_LDG_THREADS = 256;
 __global__ void __launch_bounds__(K3_LDG_THREADS) a0_k3_gather_ldg(const A0GatherArgs g) {
   __shared__ int32_t s_slot[A0_SLOTS];
+  A0_PDL_PROLOGUE();
   const int b = blockIdx.x;
   if (threadIdx.x == 0) {
     int32_t slot[A0_SLOTS];
@@ -474,11 +492,10 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
       else A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[vi][h->device] = smem;
     }
-    if (variant == 0) a0_k3_gather_tma<<<count, 32, smem, stream>>>(g);
-    else a0_k3_gather_tma_full<<<count, 32, smem, stream>>>(g);
+    if (variant == 0) A0_LAUNCH(a0_k3_gather_tma, (unsigned)count, 32, smem, stream, 1, g);
+    else A0_LAUNCH(a0_k3_gather_tma_full, (unsigned)count, 32, smem, stream, 1, g);
   } else {
-    a0_k3_gather_ldg<<<count, K3_LDG_THREADS, 0, stream>>>(g);
+    A0_LAUNCH(a0_k3_gather_ldg, (unsigned)count, K3_LDG_THREADS, 0, stream, 1, g);
   }
-  A0_LAUNCH_CHECK();
   return A0_OK;
 }

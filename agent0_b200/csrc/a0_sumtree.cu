@@ -25,6 +25,7 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
               int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
               int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
               unsigned int* counter) {
+  A0_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = blockIdx.x * K2A_WARPS + warp;
@@ -107,9 +108,8 @@ extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32
   A0_REQUIRE(total / batch <= A0_MAX_BATCHES, "a0_pt_sample: at most %d batches per call", A0_MAX_BATCHES);
   A0DeviceGuard guard(h->device);
   const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
-  a0_k2a_sample<<<blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_>>>(
-      h->tree, h->P, h->D, u, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter);
-  A0_LAUNCH_CHECK();
+  A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, h->tree, h->P, h->D, u, total, batch,
+            top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter);
   return A0_OK;
 }
 
@@ -140,6 +140,7 @@ a0_k2b_write(float* __restrict__ tree, int64_t P, int32_t chunk_log, int64_t N, 
              float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
              int32_t* __restrict__ dirty) {
   __shared__ float red[K2B_THREADS / 32];
+  A0_PDL_PROLOGUE();
   const int tid = threadIdx.x;
   const float maxp_in = *max_p;
   auto position = [&](int k) -> int64_t {
@@ -214,6 +215,7 @@ a0_k2b_rebuild(float* __restrict__ tree, int32_t D, int32_t chunk_log, int32_t* 
                unsigned int* __restrict__ ticket) {
   __shared__ float buf[2][1 << K2R_MAXLOG];
   __shared__ bool is_last;
+  A0_PDL_PROLOGUE();
   const int c = blockIdx.x;
   const int top_levels = D - chunk_log;                  // depth of the chunk roots
   if (__ldcg(dirty + c) != 0) {
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(K2P_THREADS)
 a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
              float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner) {
+  A0_PDL_PROLOGUE();
   const bool single = gridDim.x == 1;
   const int gtid = blockIdx.x * K2P_THREADS + threadIdx.x;
   const int gstride = gridDim.x * K2P_THREADS;
@@ -374,20 +377,8 @@ static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* 
     while (p2 < ctas) p2 <<= 1;
     ctas = p2;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)ctas);
-  cfg.blockDim = dim3(K2P_THREADS);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)ctas;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  A0_CUDA(cudaLaunchKernelEx(&cfg, a0_k2b_paths, h->tree, h->P, h->D, h->N, idx64, idx32, vals, count, mode, alpha, eps,
-                             h->max_p, h->winner));
+  A0_LAUNCH(a0_k2b_paths, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, h->tree, h->P, h->D, h->N, idx64, idx32, vals,
+            count, mode, alpha, eps, h->max_p, h->winner);
   return A0_OK;
 }
 
@@ -398,12 +389,10 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
   cudaStream_t stream = (cudaStream_t)stream_;
   if (count <= K2P_MAX) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream);
   const int chunk_log = h->D < K2R_MAXLOG ? h->D : K2R_MAXLOG;
-  a0_k2b_write<<<1, K2B_THREADS, 0, stream>>>(h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
-                                             eps, h->max_p, h->winner, h->dirty);
-  A0_LAUNCH_CHECK();
-  a0_k2b_rebuild<<<(unsigned)(h->P >> chunk_log), K2R_THREADS, 0, stream>>>(h->tree, h->D, chunk_log, h->dirty,
-                                                                           h->counter + A0_MAX_BATCHES);
-  A0_LAUNCH_CHECK();
+  A0_LAUNCH(a0_k2b_write, 1, K2B_THREADS, 0, stream, 1, h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
+            eps, h->max_p, h->winner, h->dirty);
+  A0_LAUNCH(a0_k2b_rebuild, (unsigned)(h->P >> chunk_log), K2R_THREADS, 0, stream, 1, h->tree, h->D, chunk_log, h->dirty,
+            h->counter + A0_MAX_BATCHES);
   return A0_OK;
 }
 

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(K4S_WARPS * 32)
 a0_k4_dqn(const A0Common c, const float* __restrict__ q, const float* __restrict__ qt_next,
           const float* __restrict__ qsel, const float* __restrict__ qt_cur, int32_t munchausen, float tau,
           float lo, float* __restrict__ grad) {
+  A0_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * K4S_WARPS + (threadIdx.x >> 5);
   if (b >= c.B) return;
@@ -108,9 +109,8 @@ extern "C" int a0_loss_dqn(const a0_loss_common_t* c, const float* q, const floa
   if (rc) return rc;
   A0_REQUIRE(q && qt_next && grad, "a0_loss_dqn: NULL tensor");
   if (c->B == 0) return A0_OK;
-  a0_k4_dqn<<<(c->B + K4S_WARPS - 1) / K4S_WARPS, K4S_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      a0_unpack(c), q, qt_next, qsel, nullptr, 0, 0.0f, 0.0f, grad);
-  A0_LAUNCH_CHECK();
+  A0_LAUNCH(a0_k4_dqn, (unsigned)((c->B + K4S_WARPS - 1) / K4S_WARPS), K4S_WARPS * 32, 0, (cudaStream_t)stream, 1,
+            a0_unpack(c), q, qt_next, qsel, (const float*)nullptr, 0, 0.0f, 0.0f, grad);
   return A0_OK;
 }
 
@@ -121,9 +121,8 @@ extern "C" int a0_loss_mdqn(const a0_loss_common_t* c, const float* q, const flo
   A0_REQUIRE(q && qt_next && qt_cur && grad, "a0_loss_mdqn: NULL tensor");
   A0_REQUIRE(tau > 0.0f, "a0_loss_mdqn: tau must be positive");
   if (c->B == 0) return A0_OK;
-  a0_k4_dqn<<<(c->B + K4S_WARPS - 1) / K4S_WARPS, K4S_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      a0_unpack(c), q, qt_next, nullptr, qt_cur, 1, tau, lo, grad);
-  A0_LAUNCH_CHECK();
+  A0_LAUNCH(a0_k4_dqn, (unsigned)((c->B + K4S_WARPS - 1) / K4S_WARPS), K4S_WARPS * 32, 0, (cudaStream_t)stream, 1,
+            a0_unpack(c), q, qt_next, (const float*)nullptr, qt_cur, 1, tau, lo, grad);
   return A0_OK;
 }
 
@@ -159,6 +158,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
           const float* __restrict__ qsel, const float* __restrict__ atoms, int32_t M, float vmin, float vmax,
           float* __restrict__ grad, float* __restrict__ target_prob) {
   __shared__ float s_m[C51_WARPS][C51_MAXR * 32];      // projected distribution of this warp's sample
+  A0_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int b = blockIdx.x * C51_WARPS + wid;
@@ -297,9 +297,8 @@ extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const
   A0_REQUIRE(M >= 2 && M <= C51_MAXR * 32, "a0_loss_c51: num_atoms %d outside [2,%d]", M, C51_MAXR * 32);
   A0_REQUIRE(vmax > vmin, "a0_loss_c51: vmax must exceed vmin");
   if (c->B == 0) return A0_OK;
-  a0_k4_c51<<<(c->B + C51_WARPS - 1) / C51_WARPS, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, grad, target_prob);
-  A0_LAUNCH_CHECK();
+  A0_LAUNCH(a0_k4_c51, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1,
+            a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, grad, target_prob);
   return A0_OK;
 }
 
@@ -330,6 +329,7 @@ a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, co
   __shared__ float sMean[A0_MAX_ACTIONS];
   __shared__ float red[A0_MAX_QUANTILES / 32];
   __shared__ int s_astar;
+  A0_PDL_PROLOGUE();
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nwarps = blockDim.x >> 5;
@@ -439,8 +439,7 @@ extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const
   if (c->B == 0) return A0_OK;
   int threads = Ni > Nj ? Ni : Nj;
   threads = ((threads + 31) / 32) * 32;
-  a0_k4_quantile<<<c->B, threads, 0, (cudaStream_t)stream>>>(a0_unpack(c), layout, q, qt, taus, qsel, Ni, Nj, grad,
-                                                             q_bar, taus_full, fraction_loss, grad_taus);
-  A0_LAUNCH_CHECK();
+  A0_LAUNCH(a0_k4_quantile, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, a0_unpack(c), layout, q, qt, taus,
+            qsel, Ni, Nj, grad, q_bar, taus_full, fraction_loss, grad_taus);
   return A0_OK;
 }

@@ -28,6 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import losses as L
+from .dist import FlatGradBucket, adam_eps
 from .model import DeepQNet
 
 
@@ -47,28 +48,15 @@ class BaseLearner:
         self.model_target = copy.deepcopy(self.model)       # agent.py:100 (no RNG consumed)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
-        B = cfg.learner.batch_size
         self.optimizer = torch.optim.Adam(list(self.model.params()), cfg.learner.learning_rate,
-                                          eps=1e-2 / (B * self.world))
+                                          eps=adam_eps(cfg.learner.batch_size, self.world))
         self.update_steps = 0
         self.gamma_n = float(np.float32(cfg.learner.discount ** cfg.learner.n_step_q))
         self.alpha, self.eps = float(cfg.replay.alpha), float(cfg.replay.eps)
         self.max_p = max_p                      # device scalar shared with the replay shard (optional)
         self.nan_guard = True                   # agent.py:152-158 (costs one device->host sync per update)
-        self._flatten_grads(list(self.model.params()))
-
-    # ---- one flat gradient bucket: zeroed with one memset, all-reduced with one NCCL call --------
-    def _flatten_grads(self, params):
-        n = sum(p.numel() for p in params)
-        self._flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)
-        off = 0
-        for p in params:
-            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-
-    def _allreduce(self, flat):
-        if self.world > 1:
-            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        # one flat gradient bucket: zeroed with one memset, all-reduced with one NCCL call
+        self.bucket = FlatGradBucket(list(self.model.params()), process_group)
 
     # ---- helpers ----------------------------------------------------------------------------------
     def _kw(self):
@@ -96,13 +84,13 @@ class BaseLearner:
         terminals = terminals.to(dev, non_blocking=True).float()
         weights = weights.to(dev, non_blocking=True).float()
 
-        self._flat_grad.zero_()
+        self.bucket.zero_()
         out, net_out = self.train_step(obs, actions, rewards, terminals, next_obs, weights)
         q_loss, fraction_loss = out.loss, out.fraction_loss
         skip = bool(torch.isnan(q_loss).any()) if self.nan_guard else False
         if not skip:
             net_out.backward(out.grad)                      # == q_loss.mul(weights).sum().backward()
-            self._allreduce(self._flat_grad)
+            self.bucket.all_reduce()
             self.optimizer.step()
             self.update_steps += 1
         else:
@@ -186,12 +174,7 @@ class FQFLearner(BaseLearner):
         super().__init__(cfg, **kw)
         fp = list(self.model.head.fraction_net.parameters())
         self.fqf_optimizer = torch.optim.RMSprop(fp, lr=cfg.learner.learning_rate / 2e4, alpha=0.95, eps=0.00001)
-        n = sum(p.numel() for p in fp)
-        self._flat_frac = torch.zeros(n, dtype=torch.float32, device=self.device)
-        off = 0
-        for p in fp:
-            p.grad = self._flat_frac[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.frac_bucket = FlatGradBucket(fp, self.pg)
 
     def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
         head = self.model.head
@@ -209,9 +192,9 @@ class FQFLearner(BaseLearner):
         out = L.fqf_loss(q_hat, taus, taus_hat, qt_next, q_bar, qsel, actions, rewards, terminals, weights,
                          self.gamma_n, **self._kw())
         # fraction step first (agent.py:139-148): only fraction_net receives this gradient
-        self._flat_frac.zero_()
+        self.frac_bucket.zero_()
         taus.squeeze(-1).backward(out.grad_taus)
-        self._allreduce(self._flat_frac)
+        self.frac_bucket.all_reduce()
         if self.cfg.learner.max_grad_norm > 0:
             nn.utils.clip_grad_norm_(head.fraction_net.parameters(), self.cfg.learner.max_grad_norm)
         self.fqf_optimizer.step()

@@ -51,6 +51,11 @@ typedef void* a0_stream_t;               /* cudaStream_t */
 
 int a0_version(void);
 const char* a0_last_error(void);
+/* A0_OPT_PDL (default 1; A0_PDL=0 in the environment also clears it): launch every kernel with
+ * programmatic stream serialization so that the launch latency of the ~25 short dependent kernels
+ * of one Trainer.step overlaps the predecessor's tail.  Stream-order semantics are unchanged.   */
+#define A0_OPT_PDL 1
+int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------
  * rec_capacity   transitions kept (cfg.replay.size); indices returned by a0_pt_sample are record
