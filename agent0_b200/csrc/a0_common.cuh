@@ -38,7 +38,8 @@ struct a0_replay {
   float* max_p;          // device scalar
   int32_t* winner;       // [N] scratch for last-writer-wins, kept at -1 between calls
   int32_t* dirty;        // [P >> 12] chunk needs its sub-tree recomputed
-  unsigned int* counter; // [A0_MAX_BATCHES] per-batch tickets of the sampler epilogue, +1 rebuild ticket
+  unsigned int* counter; // [A0_MAX_BATCHES] per-batch tickets of the sampler epilogue, [16] rebuild ticket,
+                         // [A0_MAX_BATCHES] per-batch max weight (float bits); all zero between launches
   A0Staging staging[2];
   int staging_turn;
 };
@@ -74,13 +75,18 @@ void a0_set_error(const char* fmt, ...);
   } while (0)
 
 // ---- launches ---------------------------------------------------------------------------------------
-// Every hot-path kernel is launched with programmatic stream serialization (PDL): it may become
+// Kernels can be launched with programmatic stream serialization (PDL): the kernel may become
 // resident while its predecessor in the stream drains, executes griddepcontrol.wait as its first
 // instruction (full completion + visibility of everything before it, so stream-order semantics
 // are unchanged) and immediately lets its own successor start launching.  What this removes is
-// the launch gap between the ~25 short dependent kernels of one Trainer.step, eagerly and inside
-// CUDA graphs.  a0_set_option(A0_OPT_PDL, 0) or A0_PDL=0 in the environment turns it off.
-bool a0_pdl_enabled();
+// part of the launch gap between the short dependent K4 kernels of one Trainer.step, eagerly and inside
+// CUDA graphs.  a0_set_option(A0_OPT_PDL, mask) / A0_PDL=mask in the environment selects the kernel
+// classes that use it (0 = none).
+// kernel classes for the PDL mask (A0_OPT_PDL): which launches carry the attribute
+enum { A0_PDL_K4 = 1, A0_PDL_K2 = 2, A0_PDL_K3 = 4, A0_PDL_K1 = 8 };
+constexpr int A0_PDL_DEFAULT = A0_PDL_K4;   // measured: K4-only is best at B=32 and B=512 (profiles/r01_kernel_options.json)
+bool a0_pdl_enabled(int kernel_class);
+int a0_option_k2b_levels();
 
 #define A0_PDL_PROLOGUE()                                   \
   do {                                                      \
@@ -90,7 +96,7 @@ bool a0_pdl_enabled();
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t a0_launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
-                                    cudaStream_t stream, unsigned cluster, Args... args) {
+                                    cudaStream_t stream, unsigned cluster, int kernel_class, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
@@ -105,7 +111,7 @@ static inline cudaError_t a0_launch(void (*kernel)(KArgs...), unsigned grid, uns
     attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (a0_pdl_enabled()) {
+  if (a0_pdl_enabled(kernel_class)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -22,18 +22,31 @@ void a0_set_error(const char* fmt, ...) {
 extern "C" const char* a0_last_error(void) { return g_err; }
 extern "C" int a0_version(void) { return 101; }
 
-static int g_pdl = -1;     // -1: not decided yet (environment), 0 off, 1 on
-bool a0_pdl_enabled() {
+static int g_pdl = -1;     // -1: not decided yet (environment); else a mask of A0_PDL_* classes
+bool a0_pdl_enabled(int kernel_class) {
   if (g_pdl < 0) {
     const char* e = getenv("A0_PDL");
-    g_pdl = (e && e[0] == '0') ? 0 : 1;
+    g_pdl = e ? atoi(e) : A0_PDL_DEFAULT;
   }
-  return g_pdl != 0;
+  return (g_pdl & kernel_class) != 0;
+}
+static int g_k2b_levels = 0;
+int a0_option_k2b_levels() {
+  if (g_k2b_levels == 0) {
+    const char* e = getenv("A0_K2B_LEVELS");
+    g_k2b_levels = (e && e[0] == '4') ? 4 : 3;
+  }
+  return g_k2b_levels;
 }
 extern "C" int a0_set_option(int32_t option, int64_t value) {
-  A0_REQUIRE(option == A0_OPT_PDL, "a0_set_option: unknown option %d", option);
-  g_pdl = value ? 1 : 0;
-  return A0_OK;
+  if (option == A0_OPT_PDL) { g_pdl = (int)value & 15; return A0_OK; }
+  if (option == A0_OPT_K2B_LEVELS) {
+    A0_REQUIRE(value == 3 || value == 4, "a0_set_option: A0_OPT_K2B_LEVELS must be 3 or 4");
+    g_k2b_levels = (int)value;
+    return A0_OK;
+  }
+  a0_set_error("a0_set_option: unknown option %d", option);
+  return A0_EINVAL;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -77,7 +90,7 @@ extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t fra
   alloc((void**)&h->max_p, 256);
   alloc((void**)&h->winner, (size_t)h->N * sizeof(int32_t));
   alloc((void**)&h->dirty, (size_t)((h->P >> 12) + 1) * sizeof(int32_t));
-  alloc((void**)&h->counter, (size_t)(A0_MAX_BATCHES + 64) * sizeof(unsigned int));
+  alloc((void**)&h->counter, (size_t)(2 * A0_MAX_BATCHES + 64) * sizeof(unsigned int));
   if (e != cudaSuccess) {
     a0_set_error("a0_rb_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     a0_rb_destroy(h);
@@ -114,7 +127,7 @@ extern "C" int a0_rb_reset(a0_replay_t* h, a0_stream_t stream_) {
   a0_fill_i32<<<256, 256, 0, stream>>>(h->winner, h->N, -1);
   A0_LAUNCH_CHECK();
   A0_CUDA(cudaMemsetAsync(h->dirty, 0, (size_t)((h->P >> 12) + 1) * sizeof(int32_t), stream));
-  A0_CUDA(cudaMemsetAsync(h->counter, 0, (size_t)(A0_MAX_BATCHES + 64) * sizeof(unsigned int), stream));
+  A0_CUDA(cudaMemsetAsync(h->counter, 0, (size_t)(2 * A0_MAX_BATCHES + 64) * sizeof(unsigned int), stream));
   a0_init_scalars<<<1, 1, 0, stream>>>(h->max_p);
   A0_LAUNCH_CHECK();
   return A0_OK;
@@ -182,7 +195,7 @@ extern "C" int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames, const int
   A0_REQUIRE(((uintptr_t)new_frames & 15) == 0, "a0_rb_append: new_frames must be 16-byte aligned");
   A0DeviceGuard guard(h->device);
   const int blocks = n_new + (m + K1_THREADS - 1) / K1_THREADS;
-  A0_LAUNCH(a0_k1_append, (unsigned)blocks, K1_THREADS, 0, (cudaStream_t)stream_, 1, h->frames, h->F, h->NF, new_frames,
+  A0_LAUNCH(a0_k1_append, (unsigned)blocks, K1_THREADS, 0, (cudaStream_t)stream_, 1, A0_PDL_K1, h->frames, h->F, h->NF, new_frames,
             new_frame_pos, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m);
   return A0_OK;
 }
@@ -492,10 +505,10 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
       else A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[vi][h->device] = smem;
     }
-    if (variant == 0) A0_LAUNCH(a0_k3_gather_tma, (unsigned)count, 32, smem, stream, 1, g);
-    else A0_LAUNCH(a0_k3_gather_tma_full, (unsigned)count, 32, smem, stream, 1, g);
+    if (variant == 0) A0_LAUNCH(a0_k3_gather_tma, (unsigned)count, 32, smem, stream, 1, A0_PDL_K3, g);
+    else A0_LAUNCH(a0_k3_gather_tma_full, (unsigned)count, 32, smem, stream, 1, A0_PDL_K3, g);
   } else {
-    A0_LAUNCH(a0_k3_gather_ldg, (unsigned)count, K3_LDG_THREADS, 0, stream, 1, g);
+    A0_LAUNCH(a0_k3_gather_ldg, (unsigned)count, K3_LDG_THREADS, 0, stream, 1, A0_PDL_K3, g);
   }
   return A0_OK;
 }

@@ -24,12 +24,13 @@ __global__ void __launch_bounds__(K2A_WARPS * 32)
 a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
               int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
               int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
-              unsigned int* counter) {
+              unsigned int* counter, float* bmax) {
   A0_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = blockIdx.x * K2A_WARPS + warp;
   const float root = __ldcg(tree + 1);
+  float leaf_w = 0.0f;
   if (g < total) {
     const int b = g % batch;
     float t = __fmul_rn(__fdiv_rn(__fadd_rn((float)b, u[g]), (float)batch), root);
@@ -65,37 +66,77 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
       idx_out[g] = v - P;
       prio_out[g] = leaf;
     }
+    leaf_w = leaf;
   }
-  if (weight_out == nullptr || g >= total) return;
-  // ---- epilogue: the last warp of each batch turns its priorities into normalised IS weights
-  //      (trainer.py:91-94), so all batches of a multi-batch draw finish in parallel -------------
+  if (weight_out == nullptr) return;
+  // ---- epilogue (trainer.py:91-94): every warp turns its own priority into the un-normalised
+  //      weight; the batch maximum is folded with atomicMax on the bit pattern (w > 0) and the last
+  //      arrival of each batch (ticket counter) divides the batch by (max + 1e-8).  All batches of
+  //      a multi-batch draw finish in the same launch.  When the batch size is a multiple of the
+  //      warps per CTA, a CTA lies inside one batch and aggregates in shared memory first (one
+  //      atomic pair per CTA instead of per warp: 512 same-address atomics per batch become 64) and
+  //      the last CTA normalises with all of its threads.
+  if (uniform) {                        // ReplayEnum.uniform: weights = priorities = 1 (trainer.py:95-96)
+    if (g < total && lane == 0) weight_out[g] = 1.0f;
+    return;
+  }
+  const float denom = __fadd_rn(root, sum_offset);
+  if (batch % K2A_WARPS == 0) {         // total % batch == 0, so every warp of the CTA has a draw
+    __shared__ float s_w[K2A_WARPS];
+    __shared__ int s_last;
+    const int k = g / batch;
+    float* w = weight_out + (size_t)k * batch;
+    if (lane == 0) {
+      const float wj = powf(__fmul_rn(top, __fdiv_rn(leaf_w, denom)), -beta);
+      __stcg(weight_out + g, wj);
+      s_w[warp] = wj;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float mx = s_w[0];
+#pragma unroll
+      for (int i = 1; i < K2A_WARPS; ++i) mx = fmaxf(mx, s_w[i]);
+      atomicMax(reinterpret_cast<int*>(bmax + k), __float_as_int(mx));
+      __threadfence();
+      s_last = atomicAdd(counter + k, (unsigned)K2A_WARPS) == (unsigned)(batch - K2A_WARPS);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float inv = __fadd_rn(__ldcg(bmax + k), 1e-8f);
+    for (int j = threadIdx.x; j < batch; j += K2A_WARPS * 32) w[j] = __fdiv_rn(__ldcg(w + j), inv);
+    if (threadIdx.x == 0) { counter[k] = 0u; bmax[k] = 0.0f; }
+    return;
+  }
+  if (g >= total) return;
   const int k = g / batch;
+  float* w = weight_out + (size_t)k * batch;
   unsigned ticket = 0;
   if (lane == 0) {
+    const float wj = powf(__fmul_rn(top, __fdiv_rn(leaf_w, denom)), -beta);
+    __stcg(weight_out + g, wj);
+    atomicMax(reinterpret_cast<int*>(bmax + k), __float_as_int(wj));
     __threadfence();
     ticket = atomicAdd(counter + k, 1u);
   }
   ticket = __shfl_sync(0xffffffffu, ticket, 0);
   if (ticket != (unsigned)batch - 1u) return;
   __threadfence();
-  const float* p = prio_out + (size_t)k * batch;
-  float* w = weight_out + (size_t)k * batch;
-  if (uniform) {
-    for (int j = lane; j < batch; j += 32) w[j] = 1.0f;
-  } else {
-    const float denom = root + sum_offset;
-    float mx = 0.0f;
-    for (int j = lane; j < batch; j += 32) {
-      const float wj = powf(__fmul_rn(top, __fdiv_rn(__ldcg(p + j), denom)), -beta);
-      w[j] = wj;
-      mx = fmaxf(mx, wj);
+  const float inv = __fadd_rn(__ldcg(bmax + k), 1e-8f);
+  for (int j0 = 0; j0 < batch; j0 += 32 * 8) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q * 32 + lane;
+      v[q] = j < batch ? __ldcg(w + j) : 0.0f;
     }
-    mx = a0_warp_max(mx);
-    const float inv = mx + 1e-8f;
-    __syncwarp();
-    for (int j = lane; j < batch; j += 32) w[j] = __fdiv_rn(w[j], inv);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = j0 + q * 32 + lane;
+      if (j < batch) w[j] = __fdiv_rn(v[q], inv);
+    }
   }
-  if (lane == 0) counter[k] = 0u;
+  if (lane == 0) { counter[k] = 0u; bmax[k] = 0.0f; }
 }
 
 extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32_t batch, float top, float beta,
@@ -108,8 +149,9 @@ extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32
   A0_REQUIRE(total / batch <= A0_MAX_BATCHES, "a0_pt_sample: at most %d batches per call", A0_MAX_BATCHES);
   A0DeviceGuard guard(h->device);
   const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
-  A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, h->tree, h->P, h->D, u, total, batch,
-            top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter);
+  A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, A0_PDL_K2, h->tree, h->P, h->D, u, total, batch,
+            top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter,
+            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16));
   return A0_OK;
 }
 
@@ -123,11 +165,13 @@ extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32
 //  * count <= K2P_MAX = 16384 (the training loop: B..20*B sampled indices, a few hundred marks per
 //    append): a0_k2b_paths, ONE launch of one thread-block cluster (1..8 CTAs x 1024 threads, at
 //    most two indices per thread, held in registers); the phases are separated by the hardware
-//    cluster barrier.  After the leaf writes every index walks to the root
-//    three levels per step: a thread loads the 8 siblings under its great-grandparent (two 16-byte
-//    L2 loads), forms the 4 + 2 + 1 nodes above them and stores them; threads that share
-//    ancestors compute identical values from identical inputs, so the duplicate stores are
-//    benign.  7 dependent L2 round trips for a 2 M-leaf tree instead of 21.
+//    cluster barrier.  After the leaf writes every index climbs three levels per phase up to
+//    level 12: a thread loads the 8 siblings under its great-grandparent (two 16-byte L2 loads),
+//    forms the 4 + 2 + 1 nodes above them and stores them; threads that share ancestors compute
+//    identical values from identical inputs, so duplicate stores are benign -- but near the root
+//    thousands of them would hit the same address, so levels 11..0 (4095 nodes) are instead
+//    recomputed densely by CTA 0 in shared memory, one thread per node.  3 sparse phases + one
+//    dense pass for a 1-2 M-leaf tree instead of 20-21 dependent levels.
 //  * larger counts (bulk fills): a0_k2b_write (one CTA) marks the 4096-leaf chunks it touched and
 //    a0_k2b_rebuild (one CTA per chunk) recomputes dirty chunks bottom-up in shared memory; the
 //    last CTA to finish recomputes the levels above the chunk roots.  Work independent of count.
@@ -254,6 +298,56 @@ __device__ __forceinline__ void a0_cluster_sync(bool single_cta) {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// One climb of L levels for all of a thread's indices: load the 2^L siblings under the L-th
+// ancestor (16-byte L2 loads, all issued before any arithmetic), reduce pairwise level by level
+// with fl32 adds and store every level with the widest vectors that fit.
+constexpr int K2P_TOP = 12;              // levels 0..11 (4095 nodes) are rebuilt densely in shared memory
+constexpr int K2P_LEVELS_DEFAULT = 3;   // levels per phase: 8 (3) or 16 (4) siblings per index; A0_OPT_K2B_LEVELS
+
+template <int L>
+__device__ __forceinline__ void a0_climb_all(float* __restrict__ tree, int64_t P, const int64_t (&pos)[K2P_PER_THREAD],
+                                             int shift) {
+  constexpr int W = 1 << L;
+  float v[K2P_PER_THREAD][W];
+  int64_t x[K2P_PER_THREAD];
+#pragma unroll
+  for (int s = 0; s < K2P_PER_THREAD; ++s) {
+    x[s] = ((P + (pos[s] < 0 ? 0 : pos[s])) >> shift) & ~(int64_t)(W - 1);
+    if (pos[s] < 0) continue;
+    if (L == 1) {
+      const float2 t = __ldcg(reinterpret_cast<const float2*>(tree + x[s]));
+      v[s][0] = t.x; v[s][1] = t.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(tree + x[s]) + i);
+        v[s][4 * i] = t.x; v[s][4 * i + 1] = t.y; v[s][4 * i + 2] = t.z; v[s][4 * i + 3] = t.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < K2P_PER_THREAD; ++s) {
+    if (pos[s] < 0) continue;
+#pragma unroll
+    for (int l = 1; l <= L; ++l) {
+      const int cnt = W >> l;
+#pragma unroll
+      for (int i = 0; i < cnt; ++i) v[s][i] = __fadd_rn(v[s][2 * i], v[s][2 * i + 1]);
+      float* dst = tree + (x[s] >> l);
+      if (cnt >= 4) {
+#pragma unroll
+        for (int i = 0; i < cnt / 4; ++i)
+          __stcg(reinterpret_cast<float4*>(dst) + i, make_float4(v[s][4 * i], v[s][4 * i + 1], v[s][4 * i + 2], v[s][4 * i + 3]));
+      } else if (cnt == 2) {
+        __stcg(reinterpret_cast<float2*>(dst), make_float2(v[s][0], v[s][1]));
+      } else {
+        __stcg(dst, v[s][0]);
+      }
+    }
+  }
+}
+
+template <int K2P_LEVELS>
 __global__ void __launch_bounds__(K2P_THREADS)
 a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
@@ -315,56 +409,46 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
 #pragma unroll
   for (int s = 0; s < K2P_PER_THREAD; ++s)                   // release
     if (pos[s] >= 0) winner[pos[s]] = -1;
-  // ---- propagate: `depth` is the level of the freshly written nodes, root = level 0 ----------------
+  // ---- propagate, sparse part: climb from the leaves (level D) to level `top` ---------------------
+  // Near the root every index shares its ancestors with every other one (10 240 stores to the
+  // root per phase serialise in L2), so the per-index climb stops at level `top` <= K2P_TOP and the
+  // levels above are recomputed densely below, one thread per node and no duplicate stores.
+  const int top = D < K2P_TOP ? D : K2P_TOP;
   int depth = D;
   int shift = 0;                 // node of an index at `depth` = (P + pos) >> shift
-  const int first = D % 3;       // 1 or 2 levels first, then whole groups of three
-  if (first == 1) {
-#pragma unroll
-    for (int s = 0; s < K2P_PER_THREAD; ++s) {
-      if (pos[s] < 0) continue;
-      const int64_t x = (P + pos[s]) & ~(int64_t)1;
-      const float2 c2 = __ldcg(reinterpret_cast<const float2*>(tree + x));
-      __stcg(tree + (x >> 1), __fadd_rn(c2.x, c2.y));
+  const int first = (D - top) % K2P_LEVELS;      // a short climb first, then whole groups of K2P_LEVELS
+  if (first) {
+    switch (first) {
+      case 1: a0_climb_all<1>(tree, P, pos, shift); break;
+      case 2: a0_climb_all<2>(tree, P, pos, shift); break;
+      default: if (K2P_LEVELS > 3) a0_climb_all<3>(tree, P, pos, shift); break;
     }
-  } else if (first == 2) {
-#pragma unroll
-    for (int s = 0; s < K2P_PER_THREAD; ++s) {
-      if (pos[s] < 0) continue;
-      const int64_t x = (P + pos[s]) & ~(int64_t)3;
-      const float4 c4 = __ldcg(reinterpret_cast<const float4*>(tree + x));
-      const float p0 = __fadd_rn(c4.x, c4.y), p1 = __fadd_rn(c4.z, c4.w);
-      __stcg(reinterpret_cast<float2*>(tree + (x >> 1)), make_float2(p0, p1));
-      __stcg(tree + (x >> 2), __fadd_rn(p0, p1));
-    }
+    depth -= first;
+    shift += first;
+    a0_cluster_sync(single);
   }
-  depth -= first;
-  shift += first;
-  if (first && depth > 0) a0_cluster_sync(single);
-  while (depth > 0) {            // depth is a multiple of 3 here
-    float4 lo4[K2P_PER_THREAD], hi4[K2P_PER_THREAD];
-    int64_t x[K2P_PER_THREAD];
-#pragma unroll
-    for (int s = 0; s < K2P_PER_THREAD; ++s) {
-      x[s] = ((P + (pos[s] < 0 ? 0 : pos[s])) >> shift) & ~(int64_t)7;
-      if (pos[s] >= 0) {
-        lo4[s] = __ldcg(reinterpret_cast<const float4*>(tree + x[s]));
-        hi4[s] = __ldcg(reinterpret_cast<const float4*>(tree + x[s] + 4));
-      }
+  while (depth > top) {
+    a0_climb_all<K2P_LEVELS>(tree, P, pos, shift);
+    depth -= K2P_LEVELS;
+    shift += K2P_LEVELS;
+    a0_cluster_sync(single);
+  }
+  // ---- dense part: CTA 0 rebuilds levels top-1 .. 0 from the 2^top nodes of level `top` -----------
+  if (blockIdx.x != 0 || top == 0) return;
+  __shared__ float buf[2][1 << K2P_TOP];
+  const int n = 1 << top;
+  for (int i = threadIdx.x; i < n; i += K2P_THREADS) buf[0][i] = __ldcg(tree + n + i);
+  __syncthreads();
+  int cur = 0;
+  for (int l = top - 1; l >= 0; --l) {
+    const int cnt = 1 << l;
+    for (int i = threadIdx.x; i < cnt; i += K2P_THREADS) {
+      const float v = __fadd_rn(buf[cur][2 * i], buf[cur][2 * i + 1]);
+      buf[cur ^ 1][i] = v;
+      tree[cnt + i] = v;
     }
-#pragma unroll
-    for (int s = 0; s < K2P_PER_THREAD; ++s) {
-      if (pos[s] < 0) continue;
-      const float p0 = __fadd_rn(lo4[s].x, lo4[s].y), p1 = __fadd_rn(lo4[s].z, lo4[s].w);
-      const float p2 = __fadd_rn(hi4[s].x, hi4[s].y), p3 = __fadd_rn(hi4[s].z, hi4[s].w);
-      const float g0 = __fadd_rn(p0, p1), g1 = __fadd_rn(p2, p3);
-      __stcg(reinterpret_cast<float4*>(tree + (x[s] >> 1)), make_float4(p0, p1, p2, p3));
-      __stcg(reinterpret_cast<float2*>(tree + (x[s] >> 2)), make_float2(g0, g1));
-      __stcg(tree + (x[s] >> 3), __fadd_rn(g0, g1));
-    }
-    depth -= 3;
-    shift += 3;
-    if (depth > 0) a0_cluster_sync(single);
+    __syncthreads();
+    cur ^= 1;
   }
 }
 
@@ -377,8 +461,12 @@ static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* 
     while (p2 < ctas) p2 <<= 1;
     ctas = p2;
   }
-  A0_LAUNCH(a0_k2b_paths, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, h->tree, h->P, h->D, h->N, idx64, idx32, vals,
-            count, mode, alpha, eps, h->max_p, h->winner);
+  if (a0_option_k2b_levels() == 4)
+    A0_LAUNCH(a0_k2b_paths<4>, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32,
+              vals, count, mode, alpha, eps, h->max_p, h->winner);
+  else
+    A0_LAUNCH(a0_k2b_paths<3>, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32,
+              vals, count, mode, alpha, eps, h->max_p, h->winner);
   return A0_OK;
 }
 
@@ -389,9 +477,9 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
   cudaStream_t stream = (cudaStream_t)stream_;
   if (count <= K2P_MAX) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream);
   const int chunk_log = h->D < K2R_MAXLOG ? h->D : K2R_MAXLOG;
-  A0_LAUNCH(a0_k2b_write, 1, K2B_THREADS, 0, stream, 1, h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
+  A0_LAUNCH(a0_k2b_write, 1, K2B_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
             eps, h->max_p, h->winner, h->dirty);
-  A0_LAUNCH(a0_k2b_rebuild, (unsigned)(h->P >> chunk_log), K2R_THREADS, 0, stream, 1, h->tree, h->D, chunk_log, h->dirty,
+  A0_LAUNCH(a0_k2b_rebuild, (unsigned)(h->P >> chunk_log), K2R_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->D, chunk_log, h->dirty,
             h->counter + A0_MAX_BATCHES);
   return A0_OK;
 }

@@ -109,7 +109,7 @@ extern "C" int a0_loss_dqn(const a0_loss_common_t* c, const float* q, const floa
   if (rc) return rc;
   A0_REQUIRE(q && qt_next && grad, "a0_loss_dqn: NULL tensor");
   if (c->B == 0) return A0_OK;
-  A0_LAUNCH(a0_k4_dqn, (unsigned)((c->B + K4S_WARPS - 1) / K4S_WARPS), K4S_WARPS * 32, 0, (cudaStream_t)stream, 1,
+  A0_LAUNCH(a0_k4_dqn, (unsigned)((c->B + K4S_WARPS - 1) / K4S_WARPS), K4S_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
             a0_unpack(c), q, qt_next, qsel, (const float*)nullptr, 0, 0.0f, 0.0f, grad);
   return A0_OK;
 }
@@ -121,7 +121,7 @@ extern "C" int a0_loss_mdqn(const a0_loss_common_t* c, const float* q, const flo
   A0_REQUIRE(q && qt_next && qt_cur && grad, "a0_loss_mdqn: NULL tensor");
   A0_REQUIRE(tau > 0.0f, "a0_loss_mdqn: tau must be positive");
   if (c->B == 0) return A0_OK;
-  A0_LAUNCH(a0_k4_dqn, (unsigned)((c->B + K4S_WARPS - 1) / K4S_WARPS), K4S_WARPS * 32, 0, (cudaStream_t)stream, 1,
+  A0_LAUNCH(a0_k4_dqn, (unsigned)((c->B + K4S_WARPS - 1) / K4S_WARPS), K4S_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
             a0_unpack(c), q, qt_next, (const float*)nullptr, qt_cur, 1, tau, lo, grad);
   return A0_OK;
 }
@@ -138,6 +138,7 @@ extern "C" int a0_loss_mdqn(const a0_loss_common_t* c, const float* q, const flo
 // ------------------------------------------------------------------------------------------------
 constexpr int C51_WARPS = 4;
 constexpr int C51_MAXR = 4;     // atoms per lane: M <= 128
+constexpr int C51_SPEC_A = 6;   // speculative all-action row fetch up to this many actions
 
 // Adds v (keyed by destination bin) into bins[]: runs of equal adjacent keys are reduced with
 // shuffles first.  key < 0 marks a lane without a term.
@@ -165,7 +166,23 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   if (b >= c.B) return;
   const int A = c.A;
   const int R = (M + 31) / 32;
-  // independent loads first: everything below hangs off these
+  // Every global load of this sample is issued up front.  With few actions and <= 64 atoms (the
+  // Atari case: A = 4..6 after the minimal action set, M = 51) the rows of ALL actions are fetched
+  // speculatively -- A*M*4 B <= 1.2 KB per network output -- so neither the taken action nor the
+  // arg-max action adds a second dependent memory round trip to this latency-bound kernel.
+  const bool spec = A <= C51_SPEC_A && R <= 2;
+  float lo_all[C51_SPEC_A][2], tg_all[C51_SPEC_A][2];
+  if (spec) {
+#pragma unroll
+    for (int a2 = 0; a2 < C51_SPEC_A; ++a2)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const bool in = a2 < A && lane + 32 * k < M;
+        const size_t off = ((size_t)b * A + a2) * M + lane + 32 * k;
+        lo_all[a2][k] = in ? logits[off] : -INFINITY;
+        tg_all[a2][k] = in ? tgt_logits[off] : -INFINITY;
+      }
+  }
   const int a = (int)c.action[b];
   const float r = c.reward[b], d = c.done[b], w = c.weight[b];
   const float qs = (qsel && lane < A) ? qsel[(size_t)b * A + lane] : -INFINITY;
@@ -175,8 +192,14 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   for (int k = 0; k < C51_MAXR; ++k) {
     const bool in = k < R && lane + 32 * k < M;
     z[k] = in ? atoms[lane + 32 * k] : 0.0f;
-    l[k] = in ? orow[lane + 32 * k] : -INFINITY;
+    l[k] = -INFINITY;
+    if (!spec) l[k] = in ? orow[lane + 32 * k] : -INFINITY;
     s_m[wid][lane + 32 * k] = 0.0f;
+  }
+  if (spec) {
+#pragma unroll
+    for (int a2 = 0; a2 < C51_SPEC_A; ++a2)
+      if (a2 == a) { l[0] = lo_all[a2][0]; l[1] = lo_all[a2][1]; }
   }
 
   // ---- action selection ------------------------------------------------------------------------
@@ -192,7 +215,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
       float v[C51_MAXR], mx = -INFINITY;
 #pragma unroll
       for (int k = 0; k < C51_MAXR; ++k) {
-        v[k] = (k < R && lane + 32 * k < M) ? row[lane + 32 * k] : -INFINITY;
+        v[k] = (k < R && lane + 32 * k < M) ? row[lane + 32 * k] : -INFINITY;   // L1/L2 hit when spec
         mx = fmaxf(mx, v[k]);
       }
       mx = a0_warp_max(mx);
@@ -212,10 +235,18 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   const float* trow = tgt_logits + ((size_t)b * A + a_star) * M;
   float p[C51_MAXR], mx = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k) {
-    p[k] = (k < R && lane + 32 * k < M) ? trow[lane + 32 * k] : -INFINITY;
-    mx = fmaxf(mx, p[k]);
+  for (int k = 0; k < C51_MAXR; ++k) p[k] = -INFINITY;
+  if (spec) {
+#pragma unroll
+    for (int a2 = 0; a2 < C51_SPEC_A; ++a2)
+      if (a2 == a_star) { p[0] = tg_all[a2][0]; p[1] = tg_all[a2][1]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < C51_MAXR; ++k)
+      if (k < R && lane + 32 * k < M) p[k] = trow[lane + 32 * k];
   }
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) mx = fmaxf(mx, p[k]);
   mx = a0_warp_max(mx);
   float se = 0.0f;
 #pragma unroll
@@ -297,7 +328,7 @@ extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const
   A0_REQUIRE(M >= 2 && M <= C51_MAXR * 32, "a0_loss_c51: num_atoms %d outside [2,%d]", M, C51_MAXR * 32);
   A0_REQUIRE(vmax > vmin, "a0_loss_c51: vmax must exceed vmin");
   if (c->B == 0) return A0_OK;
-  A0_LAUNCH(a0_k4_c51, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1,
+  A0_LAUNCH(a0_k4_c51, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
             a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, grad, target_prob);
   return A0_OK;
 }
@@ -439,7 +470,7 @@ extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const
   if (c->B == 0) return A0_OK;
   int threads = Ni > Nj ? Ni : Nj;
   threads = ((threads + 31) / 32) * 32;
-  A0_LAUNCH(a0_k4_quantile, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, a0_unpack(c), layout, q, qt, taus,
+  A0_LAUNCH(a0_k4_quantile, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt, taus,
             qsel, Ni, Nj, grad, q_bar, taus_full, fraction_loss, grad_taus);
   return A0_OK;
 }

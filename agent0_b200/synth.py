@@ -96,3 +96,32 @@ def record_stream(num_envs, steps, seed, **kw):
     done = np.logical_and(np.logical_or(term, life), np.logical_not(trunc))
     return dict(obs=np.stack(obs), action=np.stack(act), reward=np.stack(rew),
                 terminal=term, truncated=trunc, life_loss=life, done=done)
+
+
+def fill_shard_synthetic(rp, transitions, num_envs, seed):
+    """Fill a ReplayDataset shard with device-generated uint8 noise frames through the native
+    ingest (K1): ``num_envs`` streams, one new frame per step, a whole new stack with p = 1/100
+    (life loss / reset), done with p = 1/200, rewards in {-1, 0, 1}.  Used by bench.py and the
+    full-size GPU tests; content-independent kernels make noise as good as Atari frames here."""
+    import torch
+    F = rp.F
+    E = int(num_envs)
+    rng = np.random.RandomState(seed)
+    dev = rp.device
+    g = torch.Generator(device=dev).manual_seed(seed)
+    rp.reset_streams(np.arange(E), torch.randint(0, 256, (E * 4, F), dtype=torch.uint8, device=dev, generator=g))
+    steps_total = (transitions + E - 1) // E
+    chunk_steps = max(1, min(rp.index.max_chunk // E, 4096))
+    done_steps = 0
+    while done_steps < steps_total:
+        T = min(chunk_steps, steps_total - done_steps)
+        m = T * E
+        streams = np.tile(np.arange(E, dtype=np.int64), T)
+        n_new = np.where(rng.rand(m) < 0.01, 4, 1).astype(np.int64)
+        frames = torch.randint(0, 256, (int(n_new.sum()), F), dtype=torch.uint8, device=dev, generator=g)
+        action = rng.randint(0, 4, m)
+        reward = rng.choice([-1.0, 0.0, 1.0], m, p=[0.05, 0.9, 0.05])
+        done = rng.rand(m) < (1.0 / 200)
+        rp.append_steps(streams, n_new, frames, action, reward, done)
+        done_steps += T
+    torch.cuda.synchronize(dev)

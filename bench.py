@@ -111,27 +111,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ our arm
 def fill_shard(rp, transitions, E, seed, torch):
-    """Fill the shard with synthetic device-generated frames through the native ingest (K1):
-    E env streams, one new frame per step, a whole new stack with p=1/100 (life loss / reset)."""
-    rng = np.random.RandomState(seed)
-    dev = rp.device
-    g = torch.Generator(device=dev).manual_seed(seed)
-    rp.reset_streams(np.arange(E), torch.randint(0, 256, (E * 4, F_BYTES), dtype=torch.uint8, device=dev, generator=g))
-    steps_total = (transitions + E - 1) // E
-    chunk_steps = max(1, min(rp.index.max_chunk // E, 4096))
-    done_steps = 0
-    while done_steps < steps_total:
-        T = min(chunk_steps, steps_total - done_steps)
-        m = T * E
-        streams = np.tile(np.arange(E, dtype=np.int64), T)
-        n_new = np.where(rng.rand(m) < 0.01, 4, 1).astype(np.int64)
-        frames = torch.randint(0, 256, (int(n_new.sum()), F_BYTES), dtype=torch.uint8, device=dev, generator=g)
-        action = rng.randint(0, 4, m)
-        reward = rng.choice([-1.0, 0.0, 1.0], m, p=[0.05, 0.9, 0.05])
-        done = rng.rand(m) < (1.0 / 200)
-        rp.append_steps(streams, n_new, frames, action, reward, done)
-        done_steps += T
-    torch.cuda.synchronize(dev)
+    from agent0_b200.synth import fill_shard_synthetic
+    return fill_shard_synthetic(rp, transitions, E, seed)
 
 
 def net_outputs(algo, total, A, torch, dev, seed=99):
@@ -263,6 +244,43 @@ class HotPath:
         if rc:
             self._lib.check(rc, "a0_loss_" + self.wl["algo"])
 
+    def loss_all(self):
+        """All L batches in ONE K4 launch (B = L*batch).  Valid only when every batch's network
+        outputs exist before the first update, which a training loop cannot offer; reported as an
+        extra to show how much of the batch-32 step is launch latency."""
+        lib, o, algo, T = self.lib, self.o, self.wl["algo"], self.total
+        if getattr(self, "_k4_all", None) is None:
+            c = self._lib.LossCommon(B=T, A=self.A, action=self.act.data_ptr(), reward=self.r32.data_ptr(),
+                                     done=self.d32.data_ptr(), weight=self.w.data_ptr(), gamma_n=self.gamma_n, alpha=0.5,
+                                     eps=0.01, loss=self.loss.data_ptr(), prio=self.newp.data_ptr(),
+                                     max_p=self.rp.max_p_tensor.data_ptr())
+            self._k4_all = c
+        c = self._k4_all
+        p = lambda t: t.data_ptr()
+        qsel = p(o["qsel"]) if self.wl["double"] or algo in ("iqn", "fqf") else None
+        st = self._st()
+        if algo == "dqn":
+            rc = lib.a0_loss_dqn(C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, p(self.grad), st)
+        elif algo == "mdqn":
+            rc = lib.a0_loss_mdqn(C.byref(c), p(o["online"]), p(o["tgt_next"]), p(o["tgt_cur"]), 0.03, -1.0, p(self.grad), st)
+        elif algo == "c51":
+            rc = lib.a0_loss_c51(C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, p(o["atoms"]), 51, -10.0, 10.0, p(self.grad), None, st)
+        elif algo == "qr":
+            rc = lib.a0_loss_quantile(C.byref(c), 0, p(o["online"]), p(o["tgt_next"]), None, qsel, 200, 200, p(self.grad), None, None, None, None, st)
+        elif algo == "iqn":
+            rc = lib.a0_loss_quantile(C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus"]), qsel, 64, 64, p(self.grad), None, None, None, None, st)
+        else:
+            rc = lib.a0_loss_quantile(C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus_hat"]), qsel, 32, 32, p(self.grad),
+                                      p(o["q_bar"]), p(o["taus"]), p(self.frac), p(self.gtau), st)
+        self._lib.check(rc, "a0_loss_" + algo)
+
+    def step_fused_k4(self):
+        self.u.uniform_()
+        self.sample()
+        self.gather()
+        self.loss_all()
+        self.update()
+
     def update(self, st=None):
         st = self._st()
         if self.wl["per"]:
@@ -278,15 +296,16 @@ class HotPath:
         self.update()
 
 
-def time_graphed(hp, steps, warmup, torch, use_graph, barrier):
+def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
+    step_fn = step_fn or hp.step
     for _ in range(3):
-        hp.step()
+        step_fn()
     torch.cuda.synchronize()
-    runner = hp.step
+    runner = step_fn
     if use_graph:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            hp.step()
+            step_fn()
         runner = g.replay
     for _ in range(warmup):
         runner()
@@ -557,18 +576,20 @@ def extras(rp, args, torch, peak):
     """Secondary numbers: the other BASELINE configs on the same shard, and K3 GB/s by launch size."""
     out = {"workloads": {}, "k3_sweep": []}
     L, A = args.learner_steps, args.actions
-    for name in ("c51_b512", "qr_b512", "iqn_b512", "fqf_b512", "mdqn_b512", "dqn_b32_uniform"):
+    for name in ("c51_b32", "c51_b512", "qr_b512", "iqn_b512", "fqf_b512", "mdqn_b512", "dqn_b32_uniform"):
         wl = WORKLOADS[name]
         if not wl["per"]:
             continue        # the shard was built prioritized; the uniform config is a parity-test case
         hp = HotPath(rp, wl, L, A, torch, variant=args.variant)
         secs = time_graphed(hp, 50, 5, torch, not args.no_graph, lambda: None)
+        secs_fused = time_graphed(hp, 50, 5, torch, not args.no_graph, lambda: None, step_fn=hp.step_fused_k4)
         hp.draw_pool()
         k4 = time_kernel(lambda i: hp.loss_k(i % L), 60, torch)
         k3 = time_kernel(lambda i: hp.gather(pool=i), 40, torch)
         k2a = time_kernel(lambda i: hp.sample(), 40, torch)
         k2b = time_kernel(lambda i: hp.update(), 40, torch)
         out["workloads"][name] = {"transitions_per_s": round(hp.total * 50 / secs, 1), "ms_per_step": round(secs / 50 * 1e3, 4),
+                                  "transitions_per_s_one_k4_launch_for_all_batches": round(hp.total * 50 / secs_fused, 1),
                                   "k4_us_per_batch": round(k4 * 1e6, 2), "k3_us": round(k3 * 1e6, 2),
                                   "k3_GBps": round(bytes_per_transition(wl["n"]) * hp.total / k3 / 1e9, 1),
                                   "k2a_us": round(k2a * 1e6, 2), "k2b_us": round(k2b * 1e6, 2), "desc": wl["desc"]}

@@ -51,10 +51,14 @@ typedef void* a0_stream_t;               /* cudaStream_t */
 
 int a0_version(void);
 const char* a0_last_error(void);
-/* A0_OPT_PDL (default 1; A0_PDL=0 in the environment also clears it): launch every kernel with
- * programmatic stream serialization so that the launch latency of the ~25 short dependent kernels
- * of one Trainer.step overlaps the predecessor's tail.  Stream-order semantics are unchanged.   */
+/* A0_OPT_PDL: mask of kernel classes launched with programmatic stream serialization (1 = K4
+ * target/loss kernels, 2 = K2 sum-tree, 4 = K3 gather, 8 = K1 append; default 1, A0_PDL=<mask> in
+ * the environment overrides).  Every kernel waits for its predecessor with griddepcontrol.wait
+ * first, so stream-order semantics are unchanged; what overlaps is launch latency.             */
 #define A0_OPT_PDL 1
+/* A0_OPT_K2B_LEVELS (3 or 4, default 3; A0_K2B_LEVELS in the environment): tree levels a priority
+ * update climbs per barrier phase (8 or 16 siblings loaded per index).  Same tree either way.   */
+#define A0_OPT_K2B_LEVELS 2
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------
