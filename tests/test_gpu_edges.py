@@ -1,0 +1,212 @@
+"""Edge cases of the C ABI on the GPU: limits (n_step 16, 32 actions, 128 atoms, 256 quantiles),
+other frame sizes, static screens (0 new frames per step), ragged and empty calls, argument
+errors, stale priority updates after eviction, and the library options."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from agent0_b200 import _lib
+from agent0_b200.config import make_config
+from oracle import losses as OL
+from oracle import reference_replay as OR
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _replay(size, n, E, obs_hw=(84, 84), **kw):
+    from agent0_b200.replay import ReplayDataset
+    cfg = make_config("dqn", per=True, n_step=n, batch_size=8, replay_size=size, num_envs=E)
+    cfg.obs_shape = (4,) + tuple(obs_hw)
+    return ReplayDataset(cfg, native_nstep=True, **kw)
+
+
+def _stream(E, T, hw, seed, p_new4=0.1, p_static=0.0):
+    """obs[k] u8[E,4,h,w]; ordinary step shifts by one new frame, p_new4: whole new stack,
+    p_static: nothing changes (n_new = 0, a paused screen)."""
+    rng = np.random.RandomState(seed)
+    h, w = hw
+    obs = [rng.randint(0, 256, (E, 4, h, w)).astype(np.uint8)]
+    n_new = []
+    for k in range(T):
+        cur = obs[-1].copy()
+        kk = np.ones(E, dtype=np.int64)
+        r = rng.rand(E)
+        kk[r < p_new4] = 4
+        kk[(r >= p_new4) & (r < p_new4 + p_static)] = 0
+        for e in range(E):
+            if kk[e] == 4:
+                cur[e] = rng.randint(0, 256, (4, h, w))
+            elif kk[e] == 1:
+                cur[e, :3] = obs[-1][e, 1:]
+                cur[e, 3] = rng.randint(0, 256, (h, w))
+        obs.append(cur)
+        n_new.append(kk)
+    act = rng.randint(0, 18, (T, E)).astype(np.int64)
+    rew = rng.randn(T, E)
+    done = rng.rand(T, E) < 0.15
+    return np.stack(obs), np.stack(n_new), act, rew, done
+
+
+@pytest.mark.parametrize("n,hw,p_static", [(16, (84, 84), 0.0), (5, (96, 96), 0.3), (2, (16, 16), 0.5), (1, (84, 84), 0.2)])
+def test_nstep_limits_frame_sizes_and_static_screens(n, hw, p_static):
+    """K1/K3 against the oracle's actor packer for n up to A0_MAX_NSTEP, frames of 96x96 and 16x16
+    bytes, and streams whose screen does not change (0 new frames: stacks share all four slots)."""
+    E, T = 3, 60
+    obs, n_new, act, rew, done = _stream(E, T, hw, seed=n, p_static=p_static)
+    fr_ref, a_ref, r_ref, d_ref = OR.pack_nstep(obs, act, rew, done, n, 0.97)
+    rp = _replay(512, n, E, hw)
+    rp.gamma = 0.97
+    rp.reset_streams(np.arange(E), obs[0])
+    for k in range(T):
+        new = [obs[k + 1][e, 4 - n_new[k][e]:] for e in range(E) if n_new[k][e]]
+        new = np.concatenate(new) if new else np.zeros((0,) + hw, np.uint8)
+        rp.append_steps(np.arange(E), n_new[k], new, act[k], rew[k], done[k])
+    assert rp.top == (T - n + 1) * E
+    ks, es = np.meshgrid(np.arange(n - 1, T), np.arange(E), indexing="ij")
+    pos = ((ks - n + 1) * E + es).reshape(-1)
+    ref_i = (ks * E + es).reshape(-1)
+    for variant in (0, 1, 2):
+        rp.gather_variant = variant
+        b = rp.gather(torch.as_tensor(pos, device="cuda"))
+        assert np.array_equal(_np(b.frames), fr_ref[ref_i])
+        assert np.array_equal(_np(b.rewards).view(np.int64), r_ref[ref_i].view(np.int64))
+        assert np.array_equal(_np(b.terminals), d_ref[ref_i]) and np.array_equal(_np(b.actions), a_ref[ref_i])
+    assert rp.index.head_fs == 4 * E + int(n_new.sum())    # one stored frame per NEW frame: static steps store none
+
+
+def test_ragged_and_empty_calls():
+    rp = _replay(128, 3, 4)
+    obs, n_new, act, rew, done = _stream(4, 30, (84, 84), seed=2)
+    rp.reset_streams(np.arange(4), obs[0])
+    # ragged: streams advance at different rates, in arbitrary interleaving, several steps per call
+    order = [(0, 0), (0, 1), (0, 2), (2, 0), (1, 0), (0, 3), (2, 1), (3, 0), (1, 1), (2, 2), (2, 3), (2, 4)]
+    rp.append_steps([], [], np.zeros((0, 84, 84), np.uint8), [], [], [])             # empty append is a no-op
+    streams = np.array([e for e, _ in order])
+    kk = np.array([n_new[k][e] for e, k in order])
+    new = np.concatenate([obs[k + 1][e, 4 - n_new[k][e]:] for e, k in order])
+    rp.append_steps(streams, kk, new, [act[k][e] for e, k in order], [rew[k][e] for e, k in order],
+                    [done[k][e] for e, k in order])
+    # stream 0 has 4 steps -> 2 sampleable, stream 2 has 5 -> 3, streams 1 and 3 too short
+    assert rp.top == 2 + 3
+    live = np.flatnonzero(_np(rp.priority.leaves()) > 0)
+    b = rp.gather(torch.as_tensor(live, device="cuda"))
+    fr_ref, a_ref, r_ref, d_ref = OR.pack_nstep(obs, act, rew, done, 3, 0.99)
+    for i, p in enumerate(live):
+        e, k0 = order[p]
+        ref = (k0 + 2) * 4 + e
+        assert np.array_equal(_np(b.frames[i]), fr_ref[ref]) and _np(b.rewards[i]).view(np.int64) == r_ref[ref].view(np.int64)
+    # gather of a record whose window is incomplete is flagged, not a crash
+    bad = rp.gather(torch.as_tensor([len(order) - 1], device="cuda"))
+    assert int(bad.actions[0]) == -1 and int(bad.boot_indices[0]) == -1
+    lib = rp.lib
+    assert lib.a0_pt_update(rp.h, None, None, 0, 0.5, 0.01, None) == 0
+    assert lib.a0_pt_sample(rp.h, None, 0, 8, 1.0, 0.4, 0.0, 0, None, None, None, None) == 0
+
+
+def test_argument_errors_carry_messages():
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.a0_rb_create(C.byref(h), (1 << 24) + 1, 1 << 20, 7056, 0) == -1 and b"2^24" in lib.a0_last_error()
+    assert lib.a0_rb_create(C.byref(h), 1024, 4096, 7057, 0) == -1 and b"multiple of 16" in lib.a0_last_error()
+    rp = _replay(64, 1, 2)
+    idx = torch.zeros(4, dtype=torch.int64, device="cuda")
+    out = torch.empty(4 * 8 * 7056, dtype=torch.uint8, device="cuda")
+    assert lib.a0_rb_gather(rp.h, idx.data_ptr(), 4, 17, 0.99, out.data_ptr(), None, None, None, None, None, None, 0, None) == -1
+    assert b"n_step" in lib.a0_last_error()
+    assert lib.a0_rb_gather(rp.h, idx.data_ptr(), 4, 1, 0.99, out.data_ptr(), None, None, None, None, None, None, 3, None) == -1
+    assert lib.a0_pt_sample(rp.h, idx.data_ptr(), 10, 4, 1.0, 0.4, 0.0, 0, idx.data_ptr(), idx.data_ptr(), None, None) == -1
+    assert b"multiple of batch" in lib.a0_last_error()
+    c = _lib.LossCommon(B=4, A=33)
+    assert lib.a0_loss_dqn(C.byref(c), None, None, None, None, None) == -1 and b"action_dim" in lib.a0_last_error()
+    assert lib.a0_set_option(99, 1) == -1
+    assert lib.a0_set_option(2, 5) == -1 and lib.a0_set_option(2, 3) == 0
+    # out-of-range sampled positions are flagged by K3 (action -1), never dereferenced
+    b = rp.gather(torch.as_tensor([-5, 64, 1 << 40], device="cuda"))
+    assert (_np(b.actions) == -1).all()
+
+
+def test_stale_priority_updates_after_eviction_are_dropped():
+    """update_priority for a record that was evicted between sample and update must not resurrect
+    its leaf (K2b skips leaves that are 0)."""
+    rp = _replay(256, 1, 2, frame_capacity=120, age_limit=16)      # the frame ring, not the record ring, evicts
+    obs, n_new, act, rew, done = _stream(2, 80, (84, 84), seed=3, p_new4=0.0)
+    rp.reset_streams(np.arange(2), obs[0])
+    step = lambda k: rp.append_steps(np.arange(2), n_new[k], np.concatenate([obs[k + 1][e, 3:] for e in range(2)]),
+                                     act[k], rew[k], done[k])
+    for k in range(10):
+        step(k)
+    old = np.arange(20, dtype=np.int64)                            # "sampled" now: all 20 records are live
+    assert (_np(rp.priority.leaves())[old] > 0).all()
+    for k in range(10, 60):
+        step(k)
+    before = _np(rp.tree).copy()
+    evicted = old[~rp.index.sampleable[old]]
+    assert len(evicted) > 0 and (before[rp.P + evicted] == 0).all()
+    rp.update_priority(torch.as_tensor(old), torch.full((len(old),), 7.0))
+    after = _np(rp.tree)
+    assert (after[rp.P + evicted] == 0).all()                      # not resurrected
+    alive = old[rp.index.sampleable[old]]
+    np.testing.assert_allclose(after[rp.P + alive], np.sqrt(np.float32(7.01)), rtol=1e-6)
+    P = rp.P
+    assert np.array_equal(after[1:P], after[2:2 * P:2] + after[3:2 * P:2])
+    assert rp.max_p == pytest.approx(7.0)
+
+
+@pytest.mark.parametrize("A,M", [(32, 128), (1, 2), (18, 51)])
+def test_c51_limits(A, M):
+    from agent0_b200 import losses as L
+    rng = np.random.RandomState(A * M)
+    B = 37
+    a = rng.randint(0, A, B).astype(np.int64)
+    r = rng.choice([-1.0, 0.0, 1.0, 9.99], B).astype(np.float32)
+    d = (rng.rand(B) < 0.3).astype(np.float32)
+    w = (rng.rand(B) + 0.05).astype(np.float32)
+    lg, tg = [(rng.randn(B, A, M) * 2).astype(np.float32) for _ in range(2)]
+    atoms = np.linspace(-10, 10, M).astype(np.float32)
+    dv = lambda x: torch.as_tensor(x).cuda()
+    out = L.c51_loss(dv(lg), dv(tg), dv(atoms), dv(a), dv(r), dv(d), dv(w), float(np.float32(0.99)), -10.0, 10.0,
+                     want_target_prob=True)
+    loss, grad, m = OL.c51(lg, tg, None, a, r, d, w, 0.99, 1, atoms, -10.0, 10.0)
+    np.testing.assert_allclose(_np(out.target_prob), m, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_np(out.loss), loss, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(_np(out.grad), grad, rtol=1e-5, atol=1e-5)
+
+
+def test_quantile_limits_256_and_1():
+    from agent0_b200 import losses as L
+    rng = np.random.RandomState(5)
+    dv = lambda x: torch.as_tensor(x).cuda()
+    for B, A, N in ((9, 32, 256), (4, 1, 1), (6, 3, 33)):
+        a = rng.randint(0, A, B).astype(np.int64)
+        r = rng.randn(B).astype(np.float32); d = (rng.rand(B) < 0.3).astype(np.float32); w = (rng.rand(B) + 0.1).astype(np.float32)
+        q, tn = [(rng.randn(B, A, N) * 3).astype(np.float32) for _ in range(2)]
+        out = L.qr_loss(dv(q), dv(tn), dv(a), dv(r), dv(d), dv(w), float(np.float32(0.99 ** 3)))
+        loss, grad = OL.qr(q, tn, None, a, r, d, w, 0.99, 3)
+        np.testing.assert_allclose(_np(out.loss), loss, rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(_np(out.grad), grad, rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError, match="outside"):
+        L.qr_loss(torch.zeros(2, 2, 257).cuda(), torch.zeros(2, 2, 257).cuda(), torch.zeros(2).long().cuda(), torch.zeros(2).cuda(),
+                  torch.zeros(2).cuda(), torch.ones(2).cuda(), 0.99)
+
+
+def test_pdl_option_does_not_change_results():
+    from agent0_b200 import losses as L
+    lib = _lib.load()
+    rng = np.random.RandomState(1)
+    B, A, M = 64, 4, 51
+    dv = lambda x: torch.as_tensor(x).cuda()
+    args = (dv((rng.randn(B, A, M) * 3).astype(np.float32)), dv((rng.randn(B, A, M) * 3).astype(np.float32)),
+            dv(np.linspace(-10, 10, M).astype(np.float32)), dv(rng.randint(0, A, B)), dv(rng.randn(B).astype(np.float32)),
+            dv(np.zeros(B, np.float32)), dv(np.ones(B, np.float32)), 0.97, -10.0, 10.0)
+    outs = []
+    for mask in (0, 15, 1):
+        assert lib.a0_set_option(1, mask) == 0
+        outs.append([L.c51_loss(*args) for _ in range(5)][-1])
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].loss, outs[1].loss) and torch.equal(outs[0].grad, outs[2].grad)
