@@ -36,6 +36,7 @@ struct a0_replay {
   A0RecInfo* rec_info;   // [N]
   float* tree;           // [2P], node 1 = root, leaf j at P + j
   float* max_p;          // device scalar
+  float* dyn;            // device {top, beta, sum_offset}: a0_rb_set_dynamic / a0_pt_sample(top < 0)
   int32_t* winner;       // [N] scratch for last-writer-wins, kept at -1 between calls
   int32_t* dirty;        // [P >> 12] chunk needs its sub-tree recomputed
   unsigned int* counter; // [A0_MAX_BATCHES] per-batch tickets of the sampler epilogue, [16] rebuild ticket,

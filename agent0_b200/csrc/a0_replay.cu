@@ -57,7 +57,10 @@ __global__ void a0_fill_i32(int32_t* p, int64_t n, int32_t v) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = v;
 }
-__global__ void a0_init_scalars(float* max_p) { *max_p = 1.0f; }
+__global__ void a0_init_scalars(float* max_p) {
+  *max_p = 1.0f;
+  max_p[16] = 0.0f; max_p[17] = 1.0f; max_p[18] = 0.0f;     // dyn = {top, beta, sum_offset}
+}
 
 extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t frame_capacity,
                             int32_t frame_bytes, int32_t device) {
@@ -88,6 +91,7 @@ extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t fra
   alloc((void**)&h->rec_info, (size_t)h->N * sizeof(A0RecInfo));
   alloc((void**)&h->tree, (size_t)2 * h->P * sizeof(float));
   alloc((void**)&h->max_p, 256);
+  h->dyn = nullptr;
   alloc((void**)&h->winner, (size_t)h->N * sizeof(int32_t));
   alloc((void**)&h->dirty, (size_t)((h->P >> 12) + 1) * sizeof(int32_t));
   alloc((void**)&h->counter, (size_t)(2 * A0_MAX_BATCHES + 64) * sizeof(unsigned int));
@@ -96,6 +100,7 @@ extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t fra
     a0_rb_destroy(h);
     return e == cudaErrorMemoryAllocation ? A0_ENOMEM : (int)e;
   }
+  h->dyn = h->max_p + 16;     // same 256-byte allocation
   int rc = a0_rb_reset(h, nullptr);
   if (rc != 0) { a0_rb_destroy(h); return rc; }
   A0_CUDA(cudaStreamSynchronize(nullptr));
@@ -407,6 +412,98 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// Variant 3: the same data movement split over TWO CTAs per transition (even / odd distinct
+// frames), each with a two-buffer ring (14 KB): 2x finer work units even out the SM load of a
+// single-wave launch (640 transitions on 148 SMs is 4 or 5 CTAs per SM, 1280 half-transitions is
+// 8 or 9) at the price of walking the record chain twice.  Scalar outputs come from the even CTA.
+constexpr int K3S_RING = 2;
+__global__ void __launch_bounds__(32) a0_k3_gather_tma_split(const A0GatherArgs g_in) {
+  extern __shared__ __align__(128) uint8_t a0_smem[];
+  __shared__ __align__(8) uint64_t bars[K3S_RING];
+  if (threadIdx.x != 0) return;
+  A0_PDL_PROLOGUE();
+  const int b = blockIdx.x >> 1;
+  const int half = blockIdx.x & 1;
+  A0GatherArgs g = g_in;
+  if (half) {
+    g.action_out = nullptr; g.reward64_out = nullptr; g.reward32_out = nullptr; g.done8_out = nullptr;
+    g.done32_out = nullptr; g.boot_out = nullptr;
+  }
+  const uint32_t F = (uint32_t)g.F;
+  const uint32_t bar0 = a0_smem_u32(&bars[0]);
+  const uint32_t buf0 = a0_smem_u32(a0_smem);
+  int64_t p0 = g.idx[b];
+  bool ok = p0 >= 0 && p0 < g.N;
+  if (!ok) p0 = 0;
+  const int4 sa = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
+  const A0RecInfo info0 = g.rec_info[p0];
+#pragma unroll
+  for (int r = 0; r < K3S_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
+  a0_fence_barrier_init();
+  int32_t uslot[A0_SLOTS];
+  uint32_t dmask[A0_SLOTS];
+  int U = 0;
+  {
+    int32_t s4[A0_STACK] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+    for (int j = 0; j < A0_STACK; ++j) {
+      if (s4[j] < 0 || s4[j] >= g.NF) { s4[j] = 0; ok = false; }
+      a0_unique_add(s4[j], j, uslot, dmask, U);
+    }
+  }
+  const int U0 = U;
+  // this CTA's frames are u = half, half + 2, ...; its i-th frame uses ring buffer i % 2
+#pragma unroll
+  for (int i = 0; i < K3S_RING; ++i) {
+    const int u = half + 2 * i;
+    if (u < U0) a0_bulk_load(buf0 + i * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * i);
+  }
+  const int64_t pl = a0_walk_window(g, b, p0, info0, ok);
+  const int4 sc = reinterpret_cast<const int4*>(g.rec_slots + (size_t)pl * A0_SLOTS)[1];
+  {
+    int32_t s4[A0_STACK] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+    for (int j = 0; j < A0_STACK; ++j) {
+      if (s4[j] < 0 || s4[j] >= g.NF) { s4[j] = 0; ok = false; }
+      a0_unique_add(s4[j], A0_STACK + j, uslot, dmask, U);
+    }
+  }
+  if (!ok && g.action_out) g.action_out[b] = -1;
+#pragma unroll
+  for (int i = 0; i < K3S_RING; ++i) {
+    const int u = half + 2 * i;
+    if (u >= U0 && u < U) a0_bulk_load(buf0 + i * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * i);
+  }
+  uint8_t* out = g.frames_out + (size_t)b * A0_SLOTS * F;
+#pragma unroll
+  for (int i = 0; i < A0_SLOTS / 2; ++i) {
+    const int u = half + 2 * i;
+    if (u < U) {
+      const int r = i % K3S_RING;
+      a0_mbar_wait(bar0 + 8 * r, (i / K3S_RING) & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      uint32_t dm = 0;
+#pragma unroll
+      for (int q = 0; q < A0_SLOTS; ++q)
+        if (q == u) dm = dmask[q];
+#pragma unroll
+      for (int j = 0; j < A0_SLOTS; ++j)
+        if (dm & (1u << j)) a0_bulk_store(out + (size_t)j * F, buf0 + r * F, F);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      const int un = u + 2 * K3S_RING;
+      if (un < U) {
+        int32_t sl = 0;
+#pragma unroll
+        for (int q = 0; q < A0_SLOTS; ++q)
+          if (q == un) sl = uslot[q];
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        a0_bulk_load(buf0 + r * F, g.frames + (size_t)sl * F, F, bar0 + 8 * r);
+      }
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // Variant 2: all (up to 8) distinct frames staged at once behind one mbarrier (56 KB of shared
 // memory, 4 CTAs per SM).  Kept as the measured alternative to the ring.
 __global__ void __launch_bounds__(32) a0_k3_gather_tma_full(const A0GatherArgs g) {
@@ -488,7 +585,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   A0_REQUIRE(idx && frames_out, "a0_rb_gather: idx and frames_out are required");
   A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_gather: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
   A0_REQUIRE(((uintptr_t)frames_out & 15) == 0, "a0_rb_gather: frames_out must be 16-byte aligned");
-  A0_REQUIRE(variant >= 0 && variant <= 2, "a0_rb_gather: unknown variant %d", variant);
+  A0_REQUIRE(variant >= 0 && variant <= 3, "a0_rb_gather: unknown variant %d", variant);
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   A0GatherArgs g;
@@ -496,7 +593,15 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
   g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
-  if (variant == 0 || variant == 2) {
+  if (variant == 3) {
+    const size_t smem = (size_t)K3S_RING * h->F;
+    static thread_local size_t configured3[64] = {0};
+    if (h->device < 64 && configured3[h->device] < smem) {
+      A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured3[h->device] = smem;
+    }
+    A0_LAUNCH(a0_k3_gather_tma_split, (unsigned)count * 2, 32, smem, stream, 1, A0_PDL_K3, g);
+  } else if (variant == 0 || variant == 2) {
     const size_t smem = (size_t)(variant == 0 ? K3_RING : A0_SLOTS) * h->F;
     static thread_local size_t configured[2][64] = {{0}, {0}};
     const int vi = variant == 0 ? 0 : 1;

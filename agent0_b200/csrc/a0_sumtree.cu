@@ -24,8 +24,13 @@ __global__ void __launch_bounds__(K2A_WARPS * 32)
 a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
               int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
               int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
-              unsigned int* counter, float* bmax) {
+              unsigned int* counter, float* bmax, const float* __restrict__ dyn) {
   A0_PDL_PROLOGUE();
+  if (dyn) {            // top / beta / sum_offset live on the device (a0_rb_set_dynamic): graph-replay safe
+    top = __ldcg(dyn);
+    beta = __ldcg(dyn + 1);
+    sum_offset = __ldcg(dyn + 2);
+  }
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = blockIdx.x * K2A_WARPS + warp;
@@ -139,6 +144,19 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
   if (lane == 0) { counter[k] = 0u; bmax[k] = 0.0f; }
 }
 
+__global__ void a0_set_dyn(float* dyn, float top, float beta, float sum_offset) {
+  dyn[0] = top; dyn[1] = beta; dyn[2] = sum_offset;
+}
+
+extern "C" int a0_rb_set_dynamic(a0_replay_t* h, float top, float beta, float sum_offset, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_set_dynamic: handle is NULL");
+  A0_REQUIRE(top >= 0.0f, "a0_rb_set_dynamic: top must be non-negative");
+  A0DeviceGuard guard(h->device);
+  a0_set_dyn<<<1, 1, 0, (cudaStream_t)stream_>>>(h->dyn, top, beta, sum_offset);
+  A0_LAUNCH_CHECK();
+  return A0_OK;
+}
+
 extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32_t batch, float top, float beta,
                             float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
                             float* weight_out, a0_stream_t stream_) {
@@ -151,7 +169,7 @@ extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32
   const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
   A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, A0_PDL_K2, h->tree, h->P, h->D, u, total, batch,
             top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter,
-            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16));
+            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr));
   return A0_OK;
 }
 

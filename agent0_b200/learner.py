@@ -37,8 +37,13 @@ def _algo_name(cfg):
 
 
 class BaseLearner:
-    def __init__(self, cfg, process_group=None, device=None, max_p=None):
+    def __init__(self, cfg, process_group=None, device=None, max_p=None, capturable=False):
+        """capturable=True makes ``update`` CUDA-graph safe (trainer.GraphedUpdates): device-side
+        optimizer step counters, IQN/FQF taus from the device generator instead of the CPU one
+        (SURVEY Q13 is then not reproduced draw for draw) and no NaN guard (its host sync cannot be
+        captured)."""
         self.cfg = cfg
+        self.capturable = bool(capturable)
         dv = device if device is not None else getattr(cfg.device, "value", cfg.device)
         self.device = torch.device(dv)
         if self.device.type != "cuda":
@@ -49,12 +54,16 @@ class BaseLearner:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.optimizer = torch.optim.Adam(list(self.model.params()), cfg.learner.learning_rate,
-                                          eps=adam_eps(cfg.learner.batch_size, self.world))
+                                          eps=adam_eps(cfg.learner.batch_size, self.world), capturable=self.capturable)
+        if self.capturable:
+            for net in (self.model, self.model_target):
+                if hasattr(net.head, "device_taus"):
+                    net.head.device_taus = True
         self.update_steps = 0
         self.gamma_n = float(np.float32(cfg.learner.discount ** cfg.learner.n_step_q))
         self.alpha, self.eps = float(cfg.replay.alpha), float(cfg.replay.eps)
         self.max_p = max_p                      # device scalar shared with the replay shard (optional)
-        self.nan_guard = True                   # agent.py:152-158 (costs one device->host sync per update)
+        self.nan_guard = not self.capturable    # agent.py:152-158 (costs one device->host sync per update)
         # one flat gradient bucket: zeroed with one memset, all-reduced with one NCCL call
         self.bucket = FlatGradBucket(list(self.model.params()), process_group)
 
@@ -73,6 +82,18 @@ class BaseLearner:
         raise NotImplementedError
 
     def train(self, data):
+        """agent.py:124-169: one update, then the periodic target sync."""
+        result = self.update(data)
+        self.sync_target()
+        return result
+
+    def sync_target(self, force=False):
+        if force or self.update_steps % self.cfg.learner.target_update_freq == 0:
+            self.model_target.load_state_dict(self.model.state_dict())   # deepcopy(model), agent.py:160-161
+
+    def update(self, data):
+        """The update without the target sync (everything here runs on the device; with
+        capturable=True it can be captured into a CUDA graph)."""
         if self.cfg.learner.noisy_net:
             self.model.reset_noise()
             self.model_target.reset_noise()
@@ -95,8 +116,6 @@ class BaseLearner:
             self.update_steps += 1
         else:
             q_loss = None
-        if self.update_steps % self.cfg.learner.target_update_freq == 0:
-            self.model_target.load_state_dict(self.model.state_dict())   # deepcopy(model), agent.py:160-161
         return {"q_loss": q_loss, "fraction_loss": fraction_loss,
                 "indices": indices.to(dev, non_blocking=True).long()}
 
@@ -173,7 +192,8 @@ class FQFLearner(BaseLearner):
     def __init__(self, cfg, **kw):
         super().__init__(cfg, **kw)
         fp = list(self.model.head.fraction_net.parameters())
-        self.fqf_optimizer = torch.optim.RMSprop(fp, lr=cfg.learner.learning_rate / 2e4, alpha=0.95, eps=0.00001)
+        self.fqf_optimizer = torch.optim.RMSprop(fp, lr=cfg.learner.learning_rate / 2e4, alpha=0.95, eps=0.00001,
+                                                 capturable=self.capturable)
         self.frac_bucket = FlatGradBucket(fp, self.pg)
 
     def train_step(self, obs, actions, rewards, terminals, next_obs, weights):

@@ -151,14 +151,22 @@ class IQNHead(nn.Module):
         self.q_head = _dense(noisy, 512, act_dim, 0.01)
         self.value_head = _dense(noisy, 512, 1, 1.0) if dueling else None
         self.cosine_emb = nn.Sequential(_ortho(nn.Linear(cfg.num_cosines, feat_dim), RELU_GAIN), nn.ReLU())
+        # pi * (1..num_cosines) as a non-persistent buffer (not in the state_dict, so checkpoints stay
+        # interchangeable with the reference): the reference rebuilds it on the CPU and copies it to the
+        # device in every forward (model.py:240), which cannot be captured in a CUDA graph
+        self.register_buffer("ipi", (math.pi * torch.arange(1, cfg.num_cosines + 1)).float(), persistent=False)
+        self.device_taus = False       # True: draw taus with the device generator (graph-capturable)
 
     def feature_emb(self, x, n, taus):
         B = x.size(0)
         if taus is None:
-            taus = torch.rand(B, n, 1).to(x)       # CPU default generator, then moved
+            if self.device_taus:
+                taus = torch.rand(B, n, 1, device=x.device, dtype=x.dtype)
+            else:
+                taus = torch.rand(B, n, 1).to(x)   # CPU default generator, then moved
         else:
             n = taus.size(1)
-        ipi = math.pi * torch.arange(1, self.cfg.num_cosines + 1).to(x)
+        ipi = self.ipi.to(x)
         cosine = (ipi.view(1, 1, -1) * taus).cos().view(B * n, -1)
         tau_embed = self.cosine_emb(cosine).view(B, n, -1)
         return (tau_embed * x.unsqueeze(1)).view(B * n, -1), taus, n
@@ -187,7 +195,7 @@ class FQFHead(IQNHead):
     def prop_taus(self, x):
         log_probs = self.fraction_net(x).log_softmax(dim=-1)
         probs = log_probs.exp()
-        taus = torch.cat((torch.zeros(x.size(0), 1).to(x), torch.cumsum(probs, dim=-1)), dim=-1)
+        taus = torch.cat((x.new_zeros(x.size(0), 1), torch.cumsum(probs, dim=-1)), dim=-1)
         taus_hat = (taus[:, :-1] + taus[:, 1:]).detach() / 2.0
         entropies = probs.mul(log_probs).neg().sum(dim=-1, keepdim=True)
         return taus.unsqueeze(-1), taus_hat.unsqueeze(-1), entropies

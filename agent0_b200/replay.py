@@ -275,10 +275,28 @@ class ReplayDataset:
         self.append_steps(streams, k, new, action, reward, done)
 
     # ------------------------------------------------------------------ sample / gather
-    def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None):
+    def alloc_batch(self, total):
+        """Preallocated device buffers for ``total`` sampled transitions (``sample(..., out=)``):
+        static addresses, as CUDA-graph capture of the consumer needs."""
+        dev = self.device
+        e = lambda dt, *s: torch.empty(s or (total,), dtype=dt, device=dev)
+        return Batch(e(torch.uint8, total, 8 * self.F), e(torch.int64), e(torch.float64), e(torch.bool), e(torch.float32),
+                     e(torch.int64), e(torch.float32), e(torch.float32), e(torch.float32), e(torch.int64))
+
+    def push_dynamic(self):
+        """Publish top / beta / sum_offset to the device (stream-ordered) for ``sample(dynamic=True)``:
+        a draw captured in a CUDA graph then follows the shard as it grows and beta anneals."""
+        sum_offset = float(self.size - self.index.top) if self.compat_sum else 0.0
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.a0_rb_set_dynamic(self.h, float(self.index.top), float(self.beta), sum_offset,
+                                                  _lib.stream_ptr(self.device)), "a0_rb_set_dynamic")
+
+    def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None, out=None, dynamic=False):
         """Draw ``k_batches`` stratified batches (K2a) and gather them (K3).  ``u`` (f32 device
         tensor of k*B uniforms) or ``indices`` (i64, explicit record positions) make the draw
-        reproducible for parity tests; otherwise uniforms come from torch's CUDA generator."""
+        reproducible for parity tests; otherwise uniforms come from torch's CUDA generator.
+        ``out`` (from ``alloc_batch``) receives the result in place; ``dynamic=True`` reads top/beta
+        from the device values last published by ``push_dynamic`` (for CUDA-graph capture)."""
         B = int(batch_size or self.cfg.learner.batch_size)
         total = B * int(k_batches)
         dev = self.device
@@ -286,35 +304,43 @@ class ReplayDataset:
             raise RuntimeError("sample() on an empty replay shard")
         with torch.cuda.device(dev):
             stream = _lib.stream_ptr(dev)
-            weights = torch.empty(total, dtype=torch.float32, device=dev)
-            prio = torch.empty(total, dtype=torch.float32, device=dev)
+            weights = out.weights if out is not None else torch.empty(total, dtype=torch.float32, device=dev)
+            prio = out.priorities if out is not None else torch.empty(total, dtype=torch.float32, device=dev)
             if indices is None:
                 if u is None:
                     u = torch.rand(total, dtype=torch.float32, device=dev, generator=generator)
-                idx = torch.empty(total, dtype=torch.int64, device=dev)
+                idx = out.indices if out is not None else torch.empty(total, dtype=torch.int64, device=dev)
                 sum_offset = float(self.size - self.index.top) if self.compat_sum else 0.0
                 _lib.check(self.lib.a0_pt_sample(
-                    self.h, _lib.ptr(u, torch.float32), total, B, float(self.index.top), float(self.beta),
-                    sum_offset, 0 if self.prioritize else 1, _lib.ptr(idx), _lib.ptr(prio), _lib.ptr(weights),
-                    stream), "a0_pt_sample")
+                    self.h, _lib.ptr(u, torch.float32), total, B, -1.0 if dynamic else float(self.index.top),
+                    float(self.beta), sum_offset, 0 if self.prioritize else 1, _lib.ptr(idx), _lib.ptr(prio),
+                    _lib.ptr(weights), stream), "a0_pt_sample")
             else:
                 idx = indices.to(device=dev, dtype=torch.int64).contiguous()
                 total = idx.numel()
                 prio = self.tree[self.P + idx]
                 weights = self.is_weights(prio, B) if self.prioritize else torch.ones_like(prio)
-            return self.gather(idx, prio, weights)
+                if out is not None:
+                    out.indices.copy_(idx); out.priorities.copy_(prio); out.weights.copy_(weights)
+                    idx, prio, weights = out.indices, out.priorities, out.weights
+            return self.gather(idx, prio, weights, out=out)
 
-    def gather(self, idx, prio=None, weights=None):
+    def gather(self, idx, prio=None, weights=None, out=None):
         dev = self.device
         total = idx.numel()
         with torch.cuda.device(dev):
-            frames = torch.empty((total, 8 * self.F), dtype=torch.uint8, device=dev)
-            act = torch.empty(total, dtype=torch.int64, device=dev)
-            r64 = torch.empty(total, dtype=torch.float64, device=dev)
-            r32 = torch.empty(total, dtype=torch.float32, device=dev)
-            d8 = torch.empty(total, dtype=torch.bool, device=dev)
-            d32 = torch.empty(total, dtype=torch.float32, device=dev)
-            boot = torch.empty(total, dtype=torch.int64, device=dev)
+            if out is not None:
+                assert out.frames.shape[0] == total, "out= was allocated for a different number of transitions"
+                frames, act, r64, d8, r32, d32, boot = (out.frames, out.actions, out.rewards, out.terminals, out.rewards_f32,
+                                                        out.terminals_f32, out.boot_indices)
+            else:
+                frames = torch.empty((total, 8 * self.F), dtype=torch.uint8, device=dev)
+                act = torch.empty(total, dtype=torch.int64, device=dev)
+                r64 = torch.empty(total, dtype=torch.float64, device=dev)
+                r32 = torch.empty(total, dtype=torch.float32, device=dev)
+                d8 = torch.empty(total, dtype=torch.bool, device=dev)
+                d32 = torch.empty(total, dtype=torch.float32, device=dev)
+                boot = torch.empty(total, dtype=torch.int64, device=dev)
             _lib.check(self.lib.a0_rb_gather(
                 self.h, _lib.ptr(idx, torch.int64), total, self.n_gather, self.gamma, frames.data_ptr(),
                 act.data_ptr(), r64.data_ptr(), r32.data_ptr(), d8.data_ptr(), d32.data_ptr(), boot.data_ptr(),

@@ -14,12 +14,62 @@ from .learner import make_learner
 from .replay import ReplayDataset, split_batches
 
 
+class GraphedUpdates:
+    """The L learner updates of one Trainer.step -- CNN forward (online + target), K4, backward from
+    the kernel's gradient, Adam, K2b priority write-back, L times -- as ONE CUDA graph replay over
+    static batch buffers.  The draw (uniforms, K2a, K3) is part of the graph:
+    ``top`` and ``beta`` are read from device memory that ``push_dynamic`` refreshes before every
+    replay.  The first call runs eagerly (it is also the warm-up) and captures; later calls replay.
+    At batch 32 the eager loop is bound by ~150 kernel launches per update; the replay is not."""
+
+    def __init__(self, learner, replay, batch_size, learner_steps):
+        import torch
+        assert learner.capturable, "construct the learner with capturable=True"
+        freq = learner.cfg.learner.target_update_freq
+        assert freq % learner_steps == 0, "target_update_freq must be a multiple of learner_steps for graphed updates"
+        self.torch, self.learner, self.replay = torch, learner, replay
+        self.B, self.L = int(batch_size), int(learner_steps)
+        self.static = replay.alloc_batch(self.B * self.L)
+        self.graph, self.outs = None, None
+
+    def _updates(self):
+        self.replay.sample(self.B, k_batches=self.L, out=self.static, dynamic=True)
+        outs = []
+        for b in split_batches(self.static, self.B):
+            data = (b.frames, b.actions, b.rewards_f32, b.terminals_f32, b.weights, b.indices)
+            result = self.learner.update(data)
+            self.replay.update_priority(result["indices"], result["q_loss"])
+            outs.append((result["q_loss"], result["fraction_loss"]))
+        return outs
+
+    def run(self):
+        torch = self.torch
+        self.replay.push_dynamic()
+        if self.graph is None:
+            outs = self._updates()                       # eager: real updates + warm-up
+            steps = self.learner.update_steps
+            torch.cuda.synchronize(self.replay.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):           # capture only records, nothing executes
+                self.outs = self._updates()
+            self.learner.update_steps = steps
+        else:
+            self.graph.replay()
+            self.learner.update_steps += self.L
+            outs = self.outs
+        self.learner.sync_target()
+        return outs
+
+
 class Trainer:
-    def __init__(self, cfg, process_group=None, native_nstep=False, **replay_kw):
+    def __init__(self, cfg, process_group=None, native_nstep=False, graph=False, **replay_kw):
+        """graph=True: the learner updates of a step run as one CUDA-graph replay (GraphedUpdates)."""
         self.cfg = cfg
         self.replay = ReplayDataset(cfg, native_nstep=native_nstep, **replay_kw)
+        self.graph = bool(graph)
         self.learner = make_learner(cfg, process_group=process_group, device=self.replay.device,
-                                    max_p=None)
+                                    max_p=None, capturable=self.graph)
+        self._graphed = None
         self.num_transitions = cfg.actor.sample_steps * cfg.actor.num_envs
         self.frame_count = 0
         self.Ls, self.FLs, self.Rs, self.Qs = [], [], [], []
@@ -30,6 +80,10 @@ class Trainer:
         cfg = self.cfg
         L = int(learner_steps or cfg.learner.learner_steps)
         B = cfg.learner.batch_size
+        if self.graph:
+            if self._graphed is None or self._graphed.L != L:
+                self._graphed = GraphedUpdates(self.learner, self.replay, B, L)
+            return self._graphed.run()
         out = []
         for b in split_batches(self.replay.sample(B, k_batches=L), B):
             data = (b.frames, b.actions, b.rewards_f32, b.terminals_f32, b.weights, b.indices)

@@ -58,7 +58,7 @@ def parse():
     p.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and sweeps")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
-    p.add_argument("--variant", type=int, default=0, help="K3 variant: 0 TMA ring, 1 LDG/STG, 2 TMA full staging")
+    p.add_argument("--variant", type=int, default=0, help="K3 variant: 0 TMA ring, 1 LDG/STG, 2 TMA full staging, 3 TMA two CTAs per transition")
     p.add_argument("--cpu-entries", type=int, default=16384, help="deque entries for the CPU baseline sample")
     p.add_argument("--cpu-workers", type=int, default=-1, help="--impl reference DataLoader workers (-1: all cores)")
     return p.parse_args()
@@ -182,7 +182,9 @@ class HotPath:
     def sample(self, st=None):
         rp = self.rp
         st = self._st()
-        self._lib.check(self.lib.a0_pt_sample(rp.h, self.u.data_ptr(), self.total, self.B, float(rp.top), float(rp.beta), 0.0,
+        # top < 0: the kernel reads top/beta from device memory (ReplayDataset.push_dynamic), so a captured
+        # graph keeps following the shard while it grows
+        self._lib.check(self.lib.a0_pt_sample(rp.h, self.u.data_ptr(), self.total, self.B, -1.0, float(rp.beta), 0.0,
                                               0 if self.wl["per"] else 1, self.idx.data_ptr(), self.prio.data_ptr(),
                                               self.w.data_ptr(), st), "a0_pt_sample")
 
@@ -298,6 +300,7 @@ class HotPath:
 
 def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
     step_fn = step_fn or hp.step
+    hp.rp.push_dynamic()
     for _ in range(3):
         step_fn()
     torch.cuda.synchronize()
@@ -324,6 +327,17 @@ def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
 INNER = 20
 
 
+def capture_step(hp, torch):
+    hp.rp.push_dynamic()
+    for _ in range(3):
+        hp.step()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        hp.step()
+    return g
+
+
 def time_kernel(fn, reps, torch):
     """Average device duration of one launch: INNER back-to-back launches ``fn(i)`` (i selects
     distinct pre-drawn inputs where that matters) captured into one CUDA graph so the host launch
@@ -346,13 +360,15 @@ def time_kernel(fn, reps, torch):
     return e0.elapsed_time(e1) / 1e3 / (rounds * INNER)
 
 
-def e2e_cabi(hp, steps, warmup, torch):
+def e2e_cabi(hp, steps, warmup, torch, graph=True):
     """The headline end-to-end number: one Trainer.step-shaped pass driven through the C ABI with
     HOST buffers.  Per step: new transitions (replay ratio 8 samples per insert) are ingested from
-    page-locked host memory (a0_rb_ingest_steps: index update, H2D DMA, K2b marks, K1), the L
-    batches are drawn, gathered, run through K4 and written back to the tree with eager C-ABI
-    launches (no CUDA graph), and the per-sample losses and indices are copied back to pinned host
-    memory; the host waits for them before the next step.  Wall clock around the whole loop."""
+    page-locked host memory (a0_rb_ingest_steps: index update, H2D DMA, K2b marks, K1) and the
+    shard's top/beta are published to the device (a0_rb_set_dynamic); the L batches are drawn,
+    gathered, run through K4 and written back to the tree by replaying ONE CUDA graph of the
+    C-ABI launches (``graph=False``: the same launches issued eagerly); the per-sample losses and
+    indices are copied back to pinned host memory and the host waits for them before the next
+    step.  Wall clock around the whole loop."""
     rp, L, B = hp.rp, hp.L, hp.B
     total = hp.total
     new_per_step = max(16, total // 8)
@@ -369,14 +385,15 @@ def e2e_cabi(hp, steps, warmup, torch):
     h2d = new_per_step * (F_BYTES + 14 * 4 + 4 + 4)
     d2h = total * (4 + 8)
 
+    g = capture_step(hp, torch) if graph else None
+
     def one():
         rp.append_steps(streams, ones_new, host_frames, actions, zr, zd, pinned_stable=True)
-        hp.u.uniform_()
-        hp.sample()
-        hp.gather()
-        for k in range(L):
-            hp.loss_k(k)
-        hp.update()
+        rp.push_dynamic()
+        if g is not None:
+            g.replay()
+        else:
+            hp.step()
         loss_host.copy_(hp.loss, non_blocking=True)
         idx_host.copy_(hp.idx, non_blocking=True)
         stream.synchronize()
@@ -503,7 +520,7 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json"))).get(f"{total}")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": ["a0_k3_gather_tma", "a0_k3_gather_ldg", "a0_k3_gather_tma_full"][args.variant],
+    roofline = {"bound": "hbm", "kernel": ["a0_k3_gather_tma", "a0_k3_gather_ldg", "a0_k3_gather_tma_full", "a0_k3_gather_tma_split"][args.variant],
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                 "bytes_per_launch": bpt * total, "launch_us": round(k3 * 1e6, 2), "transitions_per_launch": total}
@@ -511,13 +528,15 @@ def run_ours(args):
     # ---- e2e through the public API -----------------------------------------------------------------
     barrier()
     e2e_steps = max(20, args.steps // 2)
-    e2e_v, h2d, d2h = e2e_cabi(hp, e2e_steps, 5, torch)
+    e2e_v, h2d, d2h = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph)
+    barrier()
+    e2e_eager, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=False)
     barrier()
     e2e_py, _, _ = e2e_loop(rp, wl, L, A, max(10, args.steps // 4), 3, torch)
-    t = torch.tensor([e2e_v, e2e_py], device="cuda", dtype=torch.float64)
+    t = torch.tensor([e2e_v, e2e_py, e2e_eager], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    e2e_v, e2e_py = float(t[0].item()), float(t[1].item())
+    e2e_v, e2e_py, e2e_eager = float(t[0].item()), float(t[1].item()), float(t[2].item())
 
     extra = {}
     if world > 1:
@@ -558,7 +577,9 @@ def run_ours(args):
                        "fill_seconds": round(t_fill, 1)},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "C ABI (ctypes) with pinned host buffers, eager launches, host waits for the losses every step",
+                    "path": "C ABI (ctypes): ingest from pinned host buffers + one CUDA-graph replay of the C-ABI launches "
+                            "per step, losses and indices copied back to pinned host memory and waited for every step",
+                    "cabi_eager_value": round(e2e_eager, 1),
                     "python_api_value": round(e2e_py, 1),
                     "python_api_path": "ReplayDataset.append_steps/sample/update_priority + agent0_b200.losses wrappers"},
             "gpu_launches": hp.launches_per_step * args.steps,
@@ -598,10 +619,10 @@ def extras(rp, args, torch, peak):
     hp = HotPath(rp, wl, 128, A, torch)           # buffers for up to 65536 transitions
     hp.draw_pool()
     for count in (32, 512, 640, 4096, 10240, 65536):
-        for variant in (0, 2, 1):
+        for variant in (0, 3, 2, 1):
             dt = time_kernel(lambda i: hp.gather(count=count, variant=variant, pool=i), 40, torch)
             gb = bytes_per_transition(3) * count / dt / 1e9
-            out["k3_sweep"].append({"transitions": count, "variant": ["tma_ring4", "ldg", "tma_full8"][variant], "us": round(dt * 1e6, 2),
+            out["k3_sweep"].append({"transitions": count, "variant": ["tma_ring4", "ldg", "tma_full8", "tma_split2"][variant], "us": round(dt * 1e6, 2),
                                     "GBps": round(gb, 1), "frac_of_measured_peak": round(gb / peak, 4)})
     return out
 

@@ -170,7 +170,11 @@ int a0_pt_set(a0_replay_t* h, const int64_t* idx /* dev */, const float* value /
  *   w = (top * p / (root + sum_offset))^(-beta);  w /= max_over_the_batch(w) + 1e-8
  * uniform != 0 writes w = 1 (ReplayEnum.uniform: weights = priorities = 1, trainer.py:95-96).
  * sum_offset reproduces the reference's denominator over never-written slots when the
- * caller asks for compat mode; 0 otherwise.                                                     */
+ * caller asks for compat mode; 0 otherwise.
+ * top < 0: take top, beta and sum_offset from the device-resident values last written by
+ * a0_rb_set_dynamic (stream-ordered), so that a captured CUDA graph of the draw stays correct
+ * while the shard grows and beta anneals.                                                       */
+int a0_rb_set_dynamic(a0_replay_t* h, float top, float beta, float sum_offset, a0_stream_t stream);
 int a0_pt_sample(a0_replay_t* h, const float* u /* dev [total] */, int32_t total, int32_t batch,
                  float top, float beta, float sum_offset, int32_t uniform,
                  int64_t* idx_out /* dev [total] */, float* prio_out /* dev [total] */,
@@ -185,7 +189,8 @@ int a0_pt_sample(a0_replay_t* h, const float* u /* dev [total] */, int32_t total
  * frames_out [count][8][frame_bytes]: the reference's `frames` layout, concat(st, st_next)
  * (agent.py:80); action i64; reward f64 and f32; done u8 and f32; boot i64.  Any output but
  * frames_out may be NULL.  variant: 0 = TMA bulk copies through a 4-buffer shared-memory ring
- * (default), 1 = LDG/STG through registers, 2 = TMA with all distinct frames staged at once.     */
+ * (default), 1 = LDG/STG through registers, 2 = TMA with all distinct frames staged at once,
+ * 3 = TMA, transition split over two CTAs (even/odd distinct frames).                            */
 int a0_rb_gather(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count, int32_t n_step,
                  double gamma, uint8_t* frames_out, int64_t* action_out, double* reward64_out,
                  float* reward32_out, uint8_t* done8_out, float* done32_out, int64_t* boot_out,

@@ -71,7 +71,7 @@ def test_nstep_limits_frame_sizes_and_static_screens(n, hw, p_static):
     ks, es = np.meshgrid(np.arange(n - 1, T), np.arange(E), indexing="ij")
     pos = ((ks - n + 1) * E + es).reshape(-1)
     ref_i = (ks * E + es).reshape(-1)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         rp.gather_variant = variant
         b = rp.gather(torch.as_tensor(pos, device="cuda"))
         assert np.array_equal(_np(b.frames), fr_ref[ref_i])
@@ -119,7 +119,7 @@ def test_argument_errors_carry_messages():
     out = torch.empty(4 * 8 * 7056, dtype=torch.uint8, device="cuda")
     assert lib.a0_rb_gather(rp.h, idx.data_ptr(), 4, 17, 0.99, out.data_ptr(), None, None, None, None, None, None, 0, None) == -1
     assert b"n_step" in lib.a0_last_error()
-    assert lib.a0_rb_gather(rp.h, idx.data_ptr(), 4, 1, 0.99, out.data_ptr(), None, None, None, None, None, None, 3, None) == -1
+    assert lib.a0_rb_gather(rp.h, idx.data_ptr(), 4, 1, 0.99, out.data_ptr(), None, None, None, None, None, None, 4, None) == -1
     assert lib.a0_pt_sample(rp.h, idx.data_ptr(), 10, 4, 1.0, 0.4, 0.0, 0, idx.data_ptr(), idx.data_ptr(), None, None) == -1
     assert b"multiple of batch" in lib.a0_last_error()
     c = _lib.LossCommon(B=4, A=33)

@@ -74,3 +74,48 @@ def test_trainer_step_end_to_end(golden):
     for node in (1, 2, 3, P // 2, P - 1):
         assert tree[node] == np.float32(tree[2 * node] + tree[2 * node + 1])
     assert tr.replay.max_p >= 1.0
+
+
+@pytest.mark.parametrize("algo", ["c51", "dqn", "qr", "iqn"])
+def test_graphed_updates_match_the_eager_loop(golden, algo):
+    """Trainer(graph=True): the L updates of a step replayed as one CUDA graph must follow the eager
+    loop (same draws, same batches): first step eager+capture, later steps replayed."""
+    from agent0_b200.config import make_config
+    from agent0_b200.trainer import Trainer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden("replay_n3")
+    M = len(g["entry_action"])
+    tup = [(g["entry_frames"][i].tobytes(), g["entry_action"][i], g["entry_reward"][i], g["entry_done"][i]) for i in range(M)]
+    runs = {}
+    for graph in (False, True):
+        cfg = make_config(algo, per=True, n_step=3, batch_size=8, double_q=True, dueling=True, replay_size=256, num_envs=3)
+        cfg.trainer.training_start_steps = 10
+        cfg.learner.learner_steps = 4
+        cfg.learner.target_update_freq = 8
+        torch.manual_seed(11)
+        tr = Trainer(cfg, graph=graph)
+        if algo == "iqn":                                   # same tau source on both arms
+            tr.learner.model.head.device_taus = tr.learner.model_target.head.device_taus = True
+        tr.replay.extend(tup)
+        torch.cuda.manual_seed(5)
+        losses = []
+        for step in range(4):
+            out = tr.learn()
+            losses.append(torch.stack([q for q, _ in out]).clone())
+        runs[graph] = (torch.stack(losses).cpu().numpy(), [p.detach().clone() for p in tr.learner.model.parameters()],
+                       [p.detach().clone() for p in tr.learner.model_target.parameters()], tr.learner.update_steps,
+                       tr.replay.tree.clone())
+    assert runs[False][3] == runs[True][3] == 16
+    tol = dict(rtol=5e-3, atol=1e-5) if algo != "iqn" else dict(rtol=5e-2, atol=1e-4)
+    np.testing.assert_allclose(runs[True][0], runs[False][0], **tol)
+    # Adam normalises every coordinate's step to ~lr, so a last-bit difference between the two
+    # optimizer implementations (python-float vs device step counters) on a near-zero gradient can
+    # move a weight by up to lr per update: bound the drift by updates*lr and require it to be rare
+    lr, updates = cfg.learner.learning_rate, 16
+    for arm in (1, 2):                                      # online net, target net (synced at 8 and 16)
+        for a, b in zip(runs[True][arm], runs[False][arm]):
+            diff = (a - b).abs()
+            assert float(diff.max()) <= updates * lr * 1.01
+            assert float((diff > 2e-5).float().mean()) < 1e-3
+    torch.testing.assert_close(runs[True][4], runs[False][4], rtol=5e-3, atol=1e-5)

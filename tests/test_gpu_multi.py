@@ -1,0 +1,85 @@
+"""Two-GPU data-parallel learner over NCCL (skipped with fewer than two GPUs): two ranks at batch B,
+gradients SUM-all-reduced in one flat bucket and Adam eps = 1e-2/(2B), must take the steps one
+learner takes at batch 2B (the reference's loss is SUM-reduced, agent0/deepq/agent.py:102-106,154);
+each rank samples its own shard with no data-path collective."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _data(seed, B, dev):
+    g = torch.Generator().manual_seed(seed)
+    frames = torch.randint(0, 256, (B, 8 * 84 * 84), dtype=torch.uint8, generator=g)
+    a = torch.randint(0, 4, (B,), generator=g)
+    r = torch.randn(B, generator=g).double()
+    d = torch.rand(B, generator=g) < 0.1
+    w = torch.rand(B, generator=g) + 0.1
+    idx = torch.arange(B)
+    return tuple(t.to(dev) for t in (frames, a, r, d, w, idx))
+
+
+def _cfg(algo, B):
+    from agent0_b200.config import make_config
+    cfg = make_config(algo, per=True, n_step=3, batch_size=B, double_q=True, dueling=True, replay_size=256)
+    cfg.learner.target_update_freq = 1000
+    return cfg
+
+
+def _worker(rank, port, algo, B, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=torch.device("cuda", rank))
+    try:
+        from agent0_b200.learner import make_learner
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.manual_seed(3)
+        learner = make_learner(_cfg(algo, B), process_group=dist.group.WORLD, device=torch.device("cuda", rank))
+        assert learner.world == 2 and learner.optimizer.defaults["eps"] == pytest.approx(1e-2 / (2 * B))
+        losses = []
+        for it in range(3):
+            res = learner.train(_data(10 * it + rank, B, learner.device))
+            losses.append(res["q_loss"].cpu().numpy())
+        out[rank] = dict(params=torch.cat([p.detach().reshape(-1) for p in learner.model.parameters()]).cpu().numpy(),
+                         losses=np.stack(losses))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("algo", ["c51", "qr"])
+def test_two_gpu_learner_equals_one_learner_at_double_batch(algo):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from agent0_b200.learner import make_learner
+    B = 16
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(_free_port(), algo, B, out), nprocs=2, join=True)
+    out = dict(out)
+    assert np.array_equal(out[0]["params"], out[1]["params"])                 # replicas stay identical
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    ref = make_learner(_cfg(algo, 2 * B), device=torch.device("cuda", 0))
+    for it in range(3):
+        parts = [_data(10 * it + r, B, ref.device) for r in range(2)]
+        res = ref.train(tuple(torch.cat(c) for c in zip(*parts)))
+        got = np.concatenate([out[0]["losses"][it], out[1]["losses"][it]])
+        np.testing.assert_allclose(got, res["q_loss"].cpu().numpy(), rtol=2e-3, atol=1e-5)
+    want = torch.cat([p.detach().reshape(-1) for p in ref.model.parameters()]).cpu().numpy()
+    np.testing.assert_allclose(out[0]["params"], want, rtol=2e-3, atol=2e-5)

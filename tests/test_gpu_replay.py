@@ -32,7 +32,7 @@ def _tuples(g, lo, hi):
 
 
 @pytest.mark.parametrize("n", [1, 3])
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_extend_then_gather_equals_reference_getitem(golden, n, variant):
     """ReplayDataset.extend(reference tuples) -> gather(i) == reference replay[i] (replay.py:32-37)."""
     g = golden(f"replay_n{n}")
@@ -60,7 +60,7 @@ def test_native_nstep_gather_equals_reference_actor_entries(golden, n):
     E, T = int(g["num_envs"]), int(g["steps"])
     obs = g["stream_obs"]
     done = OR.done_rule(g["stream_terminal"], g["stream_life_loss"], g["stream_truncated"])
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         rp = _replay(256, n=n, native=True, E=E, gather_variant=variant)
         for k in range(T):
             rp.append_vector_step(obs[k], g["stream_action"][k], g["stream_reward"][k], done[k], obs[k + 1])
@@ -98,7 +98,7 @@ def test_device_resident_native_ingest_and_wraparound():
     q = ix.head_q - 1 - ((ix.head_q - 1 - live) % rp.size)
     k0, e = np.divmod(q, E)
     ref_i = (k0 + n - 1) * E + e
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         rp.gather_variant = variant
         b = rp.gather(torch.as_tensor(live, device="cuda"))
         assert np.array_equal(_np(b.frames), fr_ref[ref_i])

@@ -21,7 +21,7 @@ bench.fill_shard(rp, 1_000_000, 16, 1234, torch)
 out = []
 for name in ("c51_b32", "c51_b512"):
     wl = bench.WORKLOADS[name]
-    for pdl in (15, 0, 1, 3, 11, 7):
+    for pdl in (1,):
         for levels in (3,):
             lib.a0_set_option(1, pdl)
             lib.a0_set_option(2, levels)
@@ -31,6 +31,8 @@ for name in ("c51_b32", "c51_b512"):
             row = {"workload": name, "pdl": pdl, "k2b_levels": levels, "step_us": round(secs / 100 * 1e6, 2),
                    "k4_us": round(bench.time_kernel(lambda i: hp.loss_k(i % 20), 100, torch) * 1e6, 2),
                    "k3_us": round(bench.time_kernel(lambda i: hp.gather(pool=i), 60, torch) * 1e6, 2),
+                   "k3_split_us": round(bench.time_kernel(lambda i: hp.gather(pool=i, variant=3), 60, torch) * 1e6, 2),
+                   "k3_full_us": round(bench.time_kernel(lambda i: hp.gather(pool=i, variant=2), 60, torch) * 1e6, 2),
                    "k2a_us": round(bench.time_kernel(lambda i: hp.sample(), 60, torch) * 1e6, 2),
                    "k2b_us": round(bench.time_kernel(lambda i: hp.update(), 60, torch) * 1e6, 2)}
             print(json.dumps(row), flush=True)
