@@ -117,5 +117,5 @@ def test_graphed_updates_match_the_eager_loop(golden, algo):
         for a, b in zip(runs[True][arm], runs[False][arm]):
             diff = (a - b).abs()
             assert float(diff.max()) <= updates * lr * 1.01
-            assert float((diff > 2e-5).float().mean()) < 1e-3
+            assert float(diff.mean()) < 0.05 * lr and float((diff > lr).float().mean()) < 1e-3
     torch.testing.assert_close(runs[True][4], runs[False][4], rtol=5e-3, atol=1e-5)
