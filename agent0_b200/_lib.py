@@ -35,7 +35,7 @@ class Plan(C.Structure):
 
 IX_HEAD_Q, IX_TAIL_Q, IX_HEAD_FS, IX_TOP, IX_REC_CAPACITY, IX_FRAME_CAPACITY, IX_NSTEP, IX_AGE_LIMIT, \
     IX_MAX_CHUNK, IX_STATE_WORDS = range(10)
-INGEST_FRAMES_ON_DEVICE, INGEST_FRAMES_PINNED = 1, 2
+INGEST_FRAMES_ON_DEVICE, INGEST_FRAMES_PINNED, INGEST_COPY_STREAM = 1, 2, 4
 
 # name -> (restype, argtypes): every symbol include/agent0_b200.h declares
 SIGNATURES = {

@@ -22,6 +22,7 @@ struct A0Staging {        // one half of the double-buffered ingest staging area
   uint8_t* dev;
   size_t capacity;
   cudaEvent_t event;      // recorded after the kernels that consume `dev`
+  cudaEvent_t copied;     // recorded on the copy stream after the H2D copies (A0_INGEST_COPY_STREAM)
 };
 
 struct a0_replay {
@@ -43,6 +44,7 @@ struct a0_replay {
                          // [A0_MAX_BATCHES] per-batch max weight (float bits); all zero between launches
   A0Staging staging[2];
   int staging_turn;
+  cudaStream_t copy_stream;   // lazily created; carries the ingest DMA under A0_INGEST_COPY_STREAM
 };
 
 void a0_set_error(const char* fmt, ...);

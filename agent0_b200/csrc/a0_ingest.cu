@@ -255,6 +255,7 @@ static int a0_stage_reserve(a0_replay* h, int turn, size_t bytes) {
   A0_CUDA(cudaMallocHost((void**)&s.host, cap));
   A0_CUDA(cudaMalloc((void**)&s.dev, cap));
   if (!s.event) A0_CUDA(cudaEventCreateWithFlags(&s.event, cudaEventDisableTiming));
+  if (!s.copied) A0_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
   s.capacity = cap;
   return A0_OK;
 }
@@ -293,11 +294,23 @@ extern "C" int a0_rb_ingest_plan(a0_replay_t* h, const a0_plan_t* plan, const ui
   if (n_new) memcpy(s.host + sec[1], plan->new_frame_pos, (size_t)n_new * 4);
   if (m) memcpy(s.host + sec[2], plan->rec_meta, (size_t)m * A0_REC_META_I32 * 4);
   if (k) memcpy(s.host + sec[3], plan->marks, (size_t)k * 4);
+  // The H2D copies may run on the shard's own copy stream, so that they overlap whatever `stream`
+  // is still executing (the previous step's kernels); `stream` then waits for them.  The staging
+  // buffer they fill was released by a0_stage_reserve (its last consumer has finished).
+  cudaStream_t cs = stream;
+  if (flags & A0_INGEST_COPY_STREAM) {
+    if (!h->copy_stream) A0_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    cs = h->copy_stream;
+  }
   if (stage_frames) {
-    A0_CUDA(cudaMemcpyAsync(s.dev, s.host, sec[4], cudaMemcpyHostToDevice, stream));
+    A0_CUDA(cudaMemcpyAsync(s.dev, s.host, sec[4], cudaMemcpyHostToDevice, cs));
   } else {
-    if (pinned && n_new) A0_CUDA(cudaMemcpyAsync(s.dev + sec[0], frames, (size_t)n_new * F, cudaMemcpyHostToDevice, stream));
-    A0_CUDA(cudaMemcpyAsync(s.dev + sec[1], s.host + sec[1], sec[4] - sec[1], cudaMemcpyHostToDevice, stream));
+    if (pinned && n_new) A0_CUDA(cudaMemcpyAsync(s.dev + sec[0], frames, (size_t)n_new * F, cudaMemcpyHostToDevice, cs));
+    A0_CUDA(cudaMemcpyAsync(s.dev + sec[1], s.host + sec[1], sec[4] - sec[1], cudaMemcpyHostToDevice, cs));
+  }
+  if (cs != stream) {
+    A0_CUDA(cudaEventRecord(s.copied, cs));
+    A0_CUDA(cudaStreamWaitEvent(stream, s.copied, 0));
   }
   const uint8_t* dev_frames = on_device ? frames : s.dev + sec[0];
   if (k) {

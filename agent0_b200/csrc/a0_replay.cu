@@ -115,9 +115,11 @@ extern "C" int a0_rb_destroy(a0_replay_t* h) {
   cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->dirty); cudaFree(h->counter);
   for (int t = 0; t < 2; ++t) {
     if (h->staging[t].event) { cudaEventSynchronize(h->staging[t].event); cudaEventDestroy(h->staging[t].event); }
+    if (h->staging[t].copied) cudaEventDestroy(h->staging[t].copied);
     if (h->staging[t].host) cudaFreeHost(h->staging[t].host);
     if (h->staging[t].dev) cudaFree(h->staging[t].dev);
   }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   delete h;
   return A0_OK;
 }

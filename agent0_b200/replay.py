@@ -240,14 +240,16 @@ class ReplayDataset:
         keep, ptr, flags = self._frames_arg(stacks, 4 * k)
         self._ingest_plan(plan, ptr, None, flags)
 
-    def append_steps(self, streams, n_new, new_frames, action, reward, done, pinned_stable=False):
+    def append_steps(self, streams, n_new, new_frames, action, reward, done, pinned_stable=False, copy_stream=False):
         """Native ingest.  For each transition (in order) the observation is the stream's current
         stack and the next observation is that stack shifted by ``n_new`` (0..4) new frames taken,
         in order, from ``new_frames`` (u8 [sum(n_new), H, W]: host array, CPU tensor or CUDA
         tensor).  ``done`` follows the reference's rule (terminal | life_loss) & ~truncated
         (agent.py:57-62).  One C call: index update, staging, H2D copy, K2b marks and K1 append.
         ``pinned_stable=True`` lets a page-locked CPU tensor be copied by DMA straight from the
-        caller's buffer, which must then stay untouched until the current stream has passed."""
+        caller's buffer, which must then stay untouched until the current stream has passed.
+        ``copy_stream=True`` issues the H2D DMA on the shard's own copy stream (the current stream
+        waits for it), so it overlaps the kernels the current stream is still running."""
         streams = np.ascontiguousarray(streams, dtype=np.int64)
         n_new = np.ascontiguousarray(n_new, dtype=np.int64)
         action = np.ascontiguousarray(action, dtype=np.int64)
@@ -255,6 +257,8 @@ class ReplayDataset:
         done = np.ascontiguousarray(done, dtype=np.bool_)
         m = len(streams)
         keep, ptr, flags = self._frames_arg(new_frames, int(n_new.sum()), pinned_stable)
+        if copy_stream and not (flags & _lib.INGEST_FRAMES_ON_DEVICE):
+            flags |= _lib.INGEST_COPY_STREAM
         with torch.cuda.device(self.device):
             _lib.check(self.lib.a0_rb_ingest_steps(
                 self.h, self.index.h, streams.ctypes.data, n_new.ctypes.data, ptr, flags, action.ctypes.data,

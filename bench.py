@@ -360,53 +360,71 @@ def time_kernel(fn, reps, torch):
     return e0.elapsed_time(e1) / 1e3 / (rounds * INNER)
 
 
-def e2e_cabi(hp, steps, warmup, torch, graph=True):
+def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True):
     """The headline end-to-end number: one Trainer.step-shaped pass driven through the C ABI with
     HOST buffers.  Per step: new transitions (replay ratio 8 samples per insert) are ingested from
     page-locked host memory (a0_rb_ingest_steps: index update, H2D DMA, K2b marks, K1) and the
     shard's top/beta are published to the device (a0_rb_set_dynamic); the L batches are drawn,
     gathered, run through K4 and written back to the tree by replaying ONE CUDA graph of the
     C-ABI launches (``graph=False``: the same launches issued eagerly); the per-sample losses and
-    indices are copied back to pinned host memory and the host waits for them before the next
-    step.  Wall clock around the whole loop."""
+    indices are copied back to pinned host memory and read by the host.
+
+    depth=1: the host waits for the step's losses before it starts the next step.  depth=2: the
+    result buffers are double-buffered -- the host reads step s-1's losses while the device runs
+    step s (the reference's own pump is asynchronous too: 2 worker processes and a 3-deep
+    prefetch queue, utils.py:59-61).  Every step's H2D input copy and D2H result read, and the
+    final drain, are inside the timed region either way.  ``copy_stream``: the ingest's H2D DMA
+    runs on the shard's copy stream so it overlaps the previous step's kernels.
+    Wall clock around the whole loop."""
     rp, L, B = hp.rp, hp.L, hp.B
     total = hp.total
     new_per_step = max(16, total // 8)
     E = 16
     rng = np.random.RandomState(3)
-    host_frames = torch.randint(0, 256, (new_per_step, F_BYTES), dtype=torch.uint8).pin_memory()
+    host_frames = [torch.randint(0, 256, (new_per_step, F_BYTES), dtype=torch.uint8).pin_memory() for _ in range(depth + 1)]
     streams = np.arange(new_per_step, dtype=np.int64) % E
     ones_new = np.ones(new_per_step, dtype=np.int64)
     actions = rng.randint(0, 4, new_per_step).astype(np.int64)
     zr, zd = np.zeros(new_per_step), np.zeros(new_per_step, dtype=bool)
-    loss_host = torch.empty(total, dtype=torch.float32).pin_memory()
-    idx_host = torch.empty(total, dtype=torch.int64).pin_memory()
-    stream = torch.cuda.current_stream()
+    loss_host = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(depth)]
+    idx_host = [torch.empty(total, dtype=torch.int64).pin_memory() for _ in range(depth)]
+    done_ev = [torch.cuda.Event() for _ in range(depth)]
     h2d = new_per_step * (F_BYTES + 14 * 4 + 4 + 4)
     d2h = total * (4 + 8)
 
     g = capture_step(hp, torch) if graph else None
+    acc = [0.0, 0]
 
-    def one():
-        rp.append_steps(streams, ones_new, host_frames, actions, zr, zd, pinned_stable=True)
-        rp.push_dynamic()
-        if g is not None:
-            g.replay()
-        else:
-            hp.step()
-        loss_host.copy_(hp.loss, non_blocking=True)
-        idx_host.copy_(hp.idx, non_blocking=True)
-        stream.synchronize()
+    def consume(slot):
+        done_ev[slot].synchronize()
+        acc[0] += float(loss_host[slot][0]) + float(loss_host[slot][-1])     # the host reads the result
+        acc[1] = max(acc[1], int(idx_host[slot][0]))
 
-    for _ in range(warmup):
-        one()
+    def run(n):
+        for s in range(n):
+            slot = s % depth
+            if s >= depth:
+                consume(slot)                       # step s-depth: its buffers are reused below
+            rp.append_steps(streams, ones_new, host_frames[s % (depth + 1)], actions, zr, zd, pinned_stable=True,
+                            copy_stream=copy_stream)
+            rp.push_dynamic()
+            if g is not None:
+                g.replay()
+            else:
+                hp.step()
+            loss_host[slot].copy_(hp.loss, non_blocking=True)
+            idx_host[slot].copy_(hp.idx, non_blocking=True)
+            done_ev[slot].record()
+        for s in range(max(0, n - depth), n):
+            consume(s % depth)
+
+    run(warmup)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
+    run(steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    assert torch.isfinite(loss_host).all() and int(idx_host.max()) < rp.size
+    assert all(torch.isfinite(x).all() for x in loss_host) and acc[1] < rp.size and np.isfinite(acc[0])
     return total * steps / dt, h2d, d2h
 
 
@@ -528,15 +546,17 @@ def run_ours(args):
     # ---- e2e through the public API -----------------------------------------------------------------
     barrier()
     e2e_steps = max(20, args.steps // 2)
-    e2e_v, h2d, d2h = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph)
+    e2e_v, h2d, d2h = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph, depth=2, copy_stream=True)
     barrier()
-    e2e_eager, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=False)
+    e2e_sync, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph, depth=1, copy_stream=False)
+    barrier()
+    e2e_eager, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=False, depth=2, copy_stream=True)
     barrier()
     e2e_py, _, _ = e2e_loop(rp, wl, L, A, max(10, args.steps // 4), 3, torch)
-    t = torch.tensor([e2e_v, e2e_py, e2e_eager], device="cuda", dtype=torch.float64)
+    t = torch.tensor([e2e_v, e2e_py, e2e_eager, e2e_sync], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    e2e_v, e2e_py, e2e_eager = float(t[0].item()), float(t[1].item()), float(t[2].item())
+    e2e_v, e2e_py, e2e_eager, e2e_sync = (float(x) for x in t.tolist())
 
     extra = {}
     if world > 1:
@@ -577,8 +597,11 @@ def run_ours(args):
                        "fill_seconds": round(t_fill, 1)},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "C ABI (ctypes): ingest from pinned host buffers + one CUDA-graph replay of the C-ABI launches "
-                            "per step, losses and indices copied back to pinned host memory and waited for every step",
+                    "path": "C ABI (ctypes): ingest from pinned host buffers (H2D DMA on the shard's copy stream) + one CUDA-graph "
+                            "replay of the C-ABI launches per step; losses and indices copied back to double-buffered pinned host "
+                            "memory, the host reads step s-1's result while step s runs (final drain inside the timed region)",
+                    "sync_every_step_value": round(e2e_sync, 1),
+                    "sync_every_step_path": "same, but the host waits for each step's losses before starting the next (depth 1)",
                     "cabi_eager_value": round(e2e_eager, 1),
                     "python_api_value": round(e2e_py, 1),
                     "python_api_path": "ReplayDataset.append_steps/sample/update_priority + agent0_b200.losses wrappers"},

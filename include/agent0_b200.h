@@ -137,9 +137,12 @@ int a0_ix_plan(a0_index_t* ix, const int64_t* stream, const int64_t* fs8, int32_
  * allocation order, out of it (NULL: the first n_new).  Flags: FRAMES_ON_DEVICE = frames is a
  * device pointer already in allocation order; FRAMES_PINNED = frames is page-locked host memory
  * in allocation order that stays untouched until `stream` has passed this call (it is copied by
- * DMA straight from there, no staging memcpy).                                                   */
+ * DMA straight from there, no staging memcpy); COPY_STREAM = the H2D copies are issued on a
+ * copy stream owned by the handle and `stream` waits for them, so the DMA overlaps the kernels
+ * `stream` is still running (not usable while `stream` is being captured into a CUDA graph).      */
 #define A0_INGEST_FRAMES_ON_DEVICE 1
 #define A0_INGEST_FRAMES_PINNED 2
+#define A0_INGEST_COPY_STREAM 4
 int a0_rb_ingest_plan(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames,
                       const int64_t* new_frame_src, int32_t flags, float alpha, a0_stream_t stream);
 /* a0_ix_resolve_shift + a0_ix_plan + a0_rb_ingest_plan for m 1-step transitions (any m: split

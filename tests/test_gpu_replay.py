@@ -106,6 +106,41 @@ def test_device_resident_native_ingest_and_wraparound():
         assert np.array_equal(_np(b.terminals), d_ref[ref_i]) and np.array_equal(_np(b.actions), a_ref[ref_i])
 
 
+@pytest.mark.parametrize("mode", ["pageable", "pinned", "pinned_copy_stream", "pageable_copy_stream"])
+def test_host_fed_ingest_modes_and_wraparound(mode):
+    """New frames arriving from HOST memory (pageable staging, pinned DMA, and either of them on the
+    shard's copy stream while the main stream is busy): same ring contents as the brute-force history."""
+    E, T, n = 4, 90, 3
+    s = record_stream(E, T, seed=78, p_terminal=0.05, p_life_loss=0.05, p_truncated=0.03)
+    fr_ref, a_ref, r_ref, d_ref = OR.pack_nstep(s["obs"], s["action"], s["reward"], s["done"], n, 0.99)
+    from agent0_b200.ring_index import stack_delta
+    rp = _replay(96, n=n, native=True, E=E, frame_capacity=400, age_limit=32)
+    rp.reset_streams(np.arange(E), s["obs"][0])
+    busy = torch.empty(1 << 24, device="cuda")
+    keep = []
+    for k in range(T):
+        kk = stack_delta(s["obs"][k], s["obs"][k + 1])
+        new = torch.as_tensor(np.concatenate([s["obs"][k + 1][e, 4 - kk[e]:] for e in range(E)]))
+        pinned = mode.startswith("pinned")
+        if pinned:
+            new = new.pin_memory()
+            keep.append(new)
+        busy.normal_()                      # keeps the main stream busy so the side-stream DMA really overlaps
+        rp.append_steps(np.arange(E), kk, new, s["action"][k], s["reward"][k], s["done"][k], pinned_stable=pinned,
+                        copy_stream=mode.endswith("copy_stream"))
+    ix = rp.index
+    assert ix.tail_q > 0
+    live = np.flatnonzero(_np(rp.priority.leaves()) > 0)
+    assert len(live) == rp.top and np.array_equal(live, np.flatnonzero(ix.sampleable))
+    q = ix.head_q - 1 - ((ix.head_q - 1 - live) % rp.size)
+    k0, e = np.divmod(q, E)
+    ref_i = (k0 + n - 1) * E + e
+    b = rp.gather(torch.as_tensor(live, device="cuda"))
+    assert np.array_equal(_np(b.frames), fr_ref[ref_i])
+    assert np.array_equal(_np(b.rewards).view(np.int64), r_ref[ref_i].view(np.int64))
+    assert np.array_equal(_np(b.terminals), d_ref[ref_i]) and np.array_equal(_np(b.actions), a_ref[ref_i])
+
+
 def test_sumtree_sample_update_bit_exact():
     """K2a/K2b against oracle/sumtree.py: same leaves, same uniforms -> identical indices and an
     identical tree, node for node."""
