@@ -577,6 +577,144 @@ __global__ void __launch_bounds__(K3_LDG_THREADS) a0_k3_gather_ldg(const A0Gathe
   }
 }
 
+// K3 with the learner's input conversion fused in (agent.py:129-135: frames.reshape(-1, 8, 84, 84)
+// .float().div(255) and the split into obs / next_obs; trainer.py:88-90 is the .float()): every distinct
+// frame is fetched ONCE with cp.async.bulk into the same 4-buffer shared-memory ring as variant 0, and
+// the CTA's four warps turn it into normalised fp32 and write it to every stack position it occupies
+// in the two contiguous outputs obs[B][4][F] and next_obs[B][4][F] with fully coalesced 16-byte
+// stores.  (S+n)F bytes read + 8F*4 written per transition (39F at n = 3) instead of the 119F of
+// gather-to-u8 + .float() + .div() as three passes.
+//   norm_mode 0: x / 255 correctly rounded -- what torch computes on the CPU (the oracle);
+//                q = x*r, e = fma(-q, 255, x), q' = fma(e, r, q) is exact for x in 0..255
+//   norm_mode 1: x * fl(1/255)             -- what torch's CUDA div-by-scalar kernel computes
+//   norm_mode 2: (float)x                  -- .float() only
+constexpr int K3F_THREADS = 128;
+__device__ __forceinline__ float a0_norm255(float x, int mode) {
+  const float r = 1.0f / 255.0f;
+  if (mode == 2) return x;
+  const float q = __fmul_rn(x, r);
+  if (mode == 1) return q;
+  const float e = __fmaf_rn(-q, 255.0f, x);
+  return __fmaf_rn(e, r, q);
+}
+__global__ void __launch_bounds__(K3F_THREADS)
+a0_k3_gather_f32(const A0GatherArgs g, float* __restrict__ obs_out, float* __restrict__ next_out, int norm_mode) {
+  extern __shared__ __align__(128) uint8_t a0_smem[];
+  __shared__ __align__(8) uint64_t bars[K3_RING];
+  __shared__ int32_t s_uslot[A0_SLOTS];
+  __shared__ uint32_t s_dmask[A0_SLOTS];
+  __shared__ int s_U;
+  A0_PDL_PROLOGUE();
+  const int b = blockIdx.x;
+  const uint32_t F = (uint32_t)g.F;
+  const uint32_t bar0 = a0_smem_u32(&bars[0]);
+  const uint32_t buf0 = a0_smem_u32(a0_smem);
+  if (threadIdx.x == 0) {
+    int64_t p0 = g.idx[b];
+    bool ok = p0 >= 0 && p0 < g.N;
+    if (!ok) p0 = 0;
+    const int4 sa = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
+    const A0RecInfo info0 = g.rec_info[p0];
+#pragma unroll
+    for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
+    a0_fence_barrier_init();
+    int32_t uslot[A0_SLOTS];
+    uint32_t dmask[A0_SLOTS];
+    int U = 0;
+    {
+      int32_t s4[A0_STACK] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+      for (int j = 0; j < A0_STACK; ++j) {
+        if (s4[j] < 0 || s4[j] >= g.NF) { s4[j] = 0; ok = false; }
+        a0_unique_add(s4[j], j, uslot, dmask, U);
+      }
+    }
+    const int U0 = U;
+#pragma unroll
+    for (int u = 0; u < K3_RING; ++u)
+      if (u < U0) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
+    const int64_t pl = a0_walk_window(g, b, p0, info0, ok);
+    const int4 sc = reinterpret_cast<const int4*>(g.rec_slots + (size_t)pl * A0_SLOTS)[1];
+    {
+      int32_t s4[A0_STACK] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+      for (int j = 0; j < A0_STACK; ++j) {
+        if (s4[j] < 0 || s4[j] >= g.NF) { s4[j] = 0; ok = false; }
+        a0_unique_add(s4[j], A0_STACK + j, uslot, dmask, U);
+      }
+    }
+    if (!ok && g.action_out) g.action_out[b] = -1;
+#pragma unroll
+    for (int u = 0; u < K3_RING; ++u)
+      if (u >= U0 && u < U) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
+#pragma unroll
+    for (int u = 0; u < A0_SLOTS; ++u) { s_uslot[u] = uslot[u]; s_dmask[u] = u < U ? dmask[u] : 0u; }
+    s_U = U;
+  }
+  __syncthreads();
+  const int U = s_U;
+  const int groups = (int)(F >> 2);                       // 4 pixels -> one float4
+  const size_t stack_elems = (size_t)A0_STACK * F;
+  float* obs_b = obs_out + (size_t)b * stack_elems;
+  float* next_b = next_out + (size_t)b * stack_elems;
+  for (int u = 0; u < U; ++u) {
+    const int r = u % K3_RING;
+    a0_mbar_wait(bar0 + 8 * r, (u / K3_RING) & 1);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a0_smem + (size_t)r * F);
+    const uint32_t dm = s_dmask[u];
+    for (int i = threadIdx.x; i < groups; i += K3F_THREADS) {
+      const uint32_t px = src[i];
+      float4 v;
+      // byte -> float without the conversion pipe: 0x4B000000 | byte is 2^23 + byte exactly
+      v.x = a0_norm255(__uint_as_float(0x4B000000u | (px & 0xffu)) - 8388608.0f, norm_mode);
+      v.y = a0_norm255(__uint_as_float(0x4B000000u | ((px >> 8) & 0xffu)) - 8388608.0f, norm_mode);
+      v.z = a0_norm255(__uint_as_float(0x4B000000u | ((px >> 16) & 0xffu)) - 8388608.0f, norm_mode);
+      v.w = a0_norm255(__uint_as_float(0x4B000000u | (px >> 24)) - 8388608.0f, norm_mode);
+#pragma unroll
+      for (int j = 0; j < A0_SLOTS; ++j)
+        if (dm & (1u << j)) {
+          float* dst = (j < A0_STACK ? obs_b + (size_t)j * F : next_b + (size_t)(j - A0_STACK) * F);
+          reinterpret_cast<float4*>(dst)[i] = v;
+        }
+    }
+    if (u + K3_RING < U) {
+      __syncthreads();                                     // every thread has read buffer r
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        a0_bulk_load(buf0 + r * F, g.frames + (size_t)s_uslot[u + K3_RING] * F, F, bar0 + 8 * r);
+      }
+    }
+  }
+}
+
+extern "C" int a0_rb_gather_f32(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
+                                float* obs_out, float* next_out, int32_t norm_mode, int64_t* action_out,
+                                double* reward64_out, float* reward32_out, uint8_t* done8_out, float* done32_out,
+                                int64_t* boot_out, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_gather_f32: handle is NULL");
+  A0_REQUIRE(count >= 0, "a0_rb_gather_f32: negative count");
+  if (count == 0) return A0_OK;
+  A0_REQUIRE(idx && obs_out && next_out, "a0_rb_gather_f32: idx, obs_out and next_out are required");
+  A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_gather_f32: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
+  A0_REQUIRE((((uintptr_t)obs_out | (uintptr_t)next_out) & 15) == 0, "a0_rb_gather_f32: outputs must be 16-byte aligned");
+  A0_REQUIRE(norm_mode >= 0 && norm_mode <= 2, "a0_rb_gather_f32: norm_mode %d outside [0,2]", norm_mode);
+  A0DeviceGuard guard(h->device);
+  A0GatherArgs g;
+  g.frames = h->frames; g.rec_slots = h->rec_slots; g.rec_info = h->rec_info; g.idx = idx;
+  g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
+  g.frames_out = nullptr; g.action_out = action_out; g.reward64_out = reward64_out;
+  g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
+  const size_t smem = (size_t)K3_RING * h->F;
+  static thread_local size_t configured[64] = {0};
+  if (h->device < 64 && configured[h->device] < smem) {
+    A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[h->device] = smem;
+  }
+  A0_LAUNCH(a0_k3_gather_f32, (unsigned)count, K3F_THREADS, smem, (cudaStream_t)stream_, 1, A0_PDL_K3, g, obs_out, next_out,
+            (int)norm_mode);
+  return A0_OK;
+}
+
 extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
                             uint8_t* frames_out, int64_t* action_out, double* reward64_out,
                             float* reward32_out, uint8_t* done8_out, float* done32_out,

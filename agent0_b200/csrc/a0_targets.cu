@@ -474,3 +474,94 @@ extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const
             qsel, Ni, Nj, grad, q_bar, taus_full, fraction_loss, grad_taus);
   return A0_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// K5: batched epsilon-greedy action selection for the actors that feed the shard.
+// Replaces Actor.act's tail (agent0/deepq/agent.py:30-39): qt.max(dim=-1), .cpu() of the arg-max,
+// np.where(rand > epsilon, greedy, random) and qt_max.mean().item() -- two host syncs per env step --
+// with one launch whose results (E actions + the mean of the per-env max) are read back in one copy.
+// The random draws stay the caller's (the reference takes them from numpy's global generator in
+// the order randint, rand), so a seeded run picks the same actions.  One warp per env, lane = action.
+// ------------------------------------------------------------------------------------------------
+constexpr int K5_WARPS = 4;
+__global__ void __launch_bounds__(K5_WARPS * 32)
+a0_k5_act(const float* __restrict__ q, int32_t E, int32_t A, double epsilon, const double* __restrict__ u,
+          const int64_t* __restrict__ action_random, int64_t* __restrict__ action_out, float* __restrict__ qmax_out,
+          float* __restrict__ qmax_sum, unsigned int* __restrict__ ticket, float* __restrict__ qmax_mean) {
+  __shared__ bool is_last;
+  A0_PDL_PROLOGUE();
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * K5_WARPS + (threadIdx.x >> 5);
+  if (e < E) {
+    const float v = lane < A ? q[(size_t)e * A + lane] : -INFINITY;
+    const int arg = a0_warp_argmax(v, lane);
+    const float mx = __shfl_sync(0xffffffffu, v, arg);
+    if (lane == 0) {
+      action_out[e] = (u[e] > epsilon) ? (int64_t)arg : action_random[e];
+      if (qmax_out) qmax_out[e] = mx;
+      atomicAdd(qmax_sum, mx);
+    }
+  }
+  // the last CTA turns the sum into the mean and re-arms the scratch for the next launch
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    *qmax_mean = __fdiv_rn(atomicExch(qmax_sum, 0.0f), (float)E);
+    *ticket = 0u;
+  }
+}
+
+extern "C" int a0_act_epsilon_greedy(const float* q, int32_t E, int32_t A, double epsilon, const double* u,
+                                     const int64_t* action_random, int64_t* action_out, float* qmax_out,
+                                     float* scratch, float* qmax_mean, a0_stream_t stream) {
+  A0_REQUIRE(E >= 0, "a0_act_epsilon_greedy: negative env count");
+  A0_REQUIRE(A >= 1 && A <= A0_MAX_ACTIONS, "a0_act_epsilon_greedy: action_dim %d outside [1,%d]", A, A0_MAX_ACTIONS);
+  if (E == 0) return A0_OK;
+  A0_REQUIRE(q && u && action_random && action_out && scratch && qmax_mean, "a0_act_epsilon_greedy: NULL argument");
+  A0_LAUNCH(a0_k5_act, (unsigned)((E + K5_WARPS - 1) / K5_WARPS), K5_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4, q, E, A, epsilon,
+            u, action_random, action_out, qmax_out, scratch, reinterpret_cast<unsigned int*>(scratch) + 1, qmax_mean);
+  return A0_OK;
+}
+
+// u8 -> f32 of the actors' observations with the same three normalisations as a0_rb_gather_f32
+// (agent.py:27: torch.from_numpy(obs).to(device).float().div(255.0)); 16 pixels per thread.
+__global__ void __launch_bounds__(256) a0_k5_u8_to_f32(const uint4* __restrict__ in, float4* __restrict__ out, int64_t nvec,
+                                                       int norm_mode) {
+  A0_PDL_PROLOGUE();
+  const float r = 1.0f / 255.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 px = __ldg(in + i);
+    const uint32_t w[4] = {px.x, px.y, px.z, px.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = __uint_as_float(0x4B000000u | ((w[k] >> (8 * j)) & 0xffu)) - 8388608.0f;
+        float y = x;
+        if (norm_mode != 2) {
+          const float qv = __fmul_rn(x, r);
+          y = norm_mode == 1 ? qv : __fmaf_rn(__fmaf_rn(-qv, 255.0f, x), r, qv);
+        }
+        f[j] = y;
+      }
+      out[i * 4 + k] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+}
+
+extern "C" int a0_u8_to_f32(const uint8_t* in, float* out, int64_t count, int32_t norm_mode, a0_stream_t stream) {
+  A0_REQUIRE(count >= 0 && count % 16 == 0, "a0_u8_to_f32: count %lld must be a non-negative multiple of 16", (long long)count);
+  if (count == 0) return A0_OK;
+  A0_REQUIRE(in && out, "a0_u8_to_f32: NULL argument");
+  A0_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "a0_u8_to_f32: pointers must be 16-byte aligned");
+  A0_REQUIRE(norm_mode >= 0 && norm_mode <= 2, "a0_u8_to_f32: norm_mode %d outside [0,2]", norm_mode);
+  const int64_t nvec = count / 16;
+  const unsigned blocks = (unsigned)((nvec + 255) / 256 < 148 * 8 ? (nvec + 255) / 256 : 148 * 8);
+  A0_LAUNCH(a0_k5_u8_to_f32, blocks, 256, 0, (cudaStream_t)stream, 1, A0_PDL_K4, reinterpret_cast<const uint4*>(in),
+            reinterpret_cast<float4*>(out), nvec, (int)norm_mode);
+  return A0_OK;
+}

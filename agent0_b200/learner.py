@@ -99,7 +99,10 @@ class BaseLearner:
             self.model_target.reset_noise()
         frames, actions, rewards, terminals, weights, indices = data
         dev = self.device
-        obs, next_obs = self.split_frames(frames.to(dev, non_blocking=True))
+        if isinstance(frames, (tuple, list)):
+            obs, next_obs = frames          # f32 [B,4,H,W] pair from the fused gather (ReplayDataset.sample(normalized=))
+        else:
+            obs, next_obs = self.split_frames(frames.to(dev, non_blocking=True))
         actions = actions.to(dev, non_blocking=True).long()
         rewards = rewards.to(dev, non_blocking=True).float()
         terminals = terminals.to(dev, non_blocking=True).float()

@@ -24,10 +24,14 @@ from . import _lib
 from .ring_index import ContentDeduper, NativeRingIndex, stack_delta
 
 Batch = namedtuple("Batch", ["frames", "actions", "rewards", "terminals", "priorities", "indices",
-                             "weights", "rewards_f32", "terminals_f32", "boot_indices"])
+                             "weights", "rewards_f32", "terminals_f32", "boot_indices", "obs", "next_obs"],
+                   defaults=(None, None))
 Batch.__doc__ = """One or more sampled batches, device resident.  Fields 0..5 are the reference's
 collated 6-tuple (frames u8[B,8*F], a i64, r f64, d bool, priority f32, idx i64; SURVEY 8b);
-``weights`` are the IS weights of trainer.py:91-96, ``*_f32`` the .float() casts of trainer.py:88-90."""
+``weights`` are the IS weights of trainer.py:91-96, ``*_f32`` the .float() casts of trainer.py:88-90.
+With ``normalized=`` sampling, ``frames`` is None and ``obs`` / ``next_obs`` are the learner's
+f32 [B,4,H,W] inputs (agent.py:129-135: /255 and split, fused into the gather)."""
+NORM_DIV, NORM_RECIP, NORM_NONE = 0, 1, 2      # a0_rb_gather_f32 norm_mode
 
 
 
@@ -35,7 +39,7 @@ def split_batches(batch, batch_size):
     """Per-update views of a multi-batch draw: a list of ``Batch`` tuples, one per learner update
     (torch.split makes all views of a field in one call)."""
     cols = [f.split(batch_size) if f is not None else None for f in batch]
-    k = len(cols[0])
+    k = len(next(c for c in cols if c is not None))
     return [Batch(*[(c[i] if c is not None else None) for c in cols]) for i in range(k)]
 
 
@@ -279,13 +283,18 @@ class ReplayDataset:
         self.append_steps(streams, k, new, action, reward, done)
 
     # ------------------------------------------------------------------ sample / gather
-    def alloc_batch(self, total):
+    def alloc_batch(self, total, normalized=None):
         """Preallocated device buffers for ``total`` sampled transitions (``sample(..., out=)``):
-        static addresses, as CUDA-graph capture of the consumer needs."""
+        static addresses, as CUDA-graph capture of the consumer needs.  ``normalized`` (a NORM_*
+        mode): f32 obs / next_obs buffers instead of the u8 frames."""
         dev = self.device
         e = lambda dt, *s: torch.empty(s or (total,), dtype=dt, device=dev)
-        return Batch(e(torch.uint8, total, 8 * self.F), e(torch.int64), e(torch.float64), e(torch.bool), e(torch.float32),
-                     e(torch.int64), e(torch.float32), e(torch.float32), e(torch.float32), e(torch.int64))
+        shape = (total, self.stack) + tuple(self.frame_shape)
+        frames = e(torch.uint8, total, 8 * self.F) if normalized is None else None
+        obs = e(torch.float32, *shape) if normalized is not None else None
+        nxt = e(torch.float32, *shape) if normalized is not None else None
+        return Batch(frames, e(torch.int64), e(torch.float64), e(torch.bool), e(torch.float32),
+                     e(torch.int64), e(torch.float32), e(torch.float32), e(torch.float32), e(torch.int64), obs, nxt)
 
     def push_dynamic(self):
         """Publish top / beta / sum_offset to the device (stream-ordered) for ``sample(dynamic=True)``:
@@ -295,12 +304,15 @@ class ReplayDataset:
             _lib.check(self.lib.a0_rb_set_dynamic(self.h, float(self.index.top), float(self.beta), sum_offset,
                                                   _lib.stream_ptr(self.device)), "a0_rb_set_dynamic")
 
-    def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None, out=None, dynamic=False):
+    def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None, out=None, dynamic=False,
+               normalized=None):
         """Draw ``k_batches`` stratified batches (K2a) and gather them (K3).  ``u`` (f32 device
         tensor of k*B uniforms) or ``indices`` (i64, explicit record positions) make the draw
         reproducible for parity tests; otherwise uniforms come from torch's CUDA generator.
         ``out`` (from ``alloc_batch``) receives the result in place; ``dynamic=True`` reads top/beta
-        from the device values last published by ``push_dynamic`` (for CUDA-graph capture)."""
+        from the device values last published by ``push_dynamic`` (for CUDA-graph capture).
+        ``normalized`` (NORM_DIV / NORM_RECIP / NORM_NONE): gather straight into the learner's f32
+        obs / next_obs inputs (K3 with the /255 + split of agent.py:129-135 fused in)."""
         B = int(batch_size or self.cfg.learner.batch_size)
         total = B * int(k_batches)
         dev = self.device
@@ -327,12 +339,16 @@ class ReplayDataset:
                 if out is not None:
                     out.indices.copy_(idx); out.priorities.copy_(prio); out.weights.copy_(weights)
                     idx, prio, weights = out.indices, out.priorities, out.weights
-            return self.gather(idx, prio, weights, out=out)
+            return self.gather(idx, prio, weights, out=out, normalized=normalized)
 
-    def gather(self, idx, prio=None, weights=None, out=None):
+    def gather(self, idx, prio=None, weights=None, out=None, normalized=None):
         dev = self.device
         total = idx.numel()
+        if out is not None and out.obs is not None and normalized is None:
+            normalized = NORM_DIV
         with torch.cuda.device(dev):
+            if normalized is not None:
+                return self._gather_f32(idx, prio, weights, out, int(normalized))
             if out is not None:
                 assert out.frames.shape[0] == total, "out= was allocated for a different number of transitions"
                 frames, act, r64, d8, r32, d32, boot = (out.frames, out.actions, out.rewards, out.terminals, out.rewards_f32,
@@ -350,6 +366,24 @@ class ReplayDataset:
                 act.data_ptr(), r64.data_ptr(), r32.data_ptr(), d8.data_ptr(), d32.data_ptr(), boot.data_ptr(),
                 self.gather_variant, _lib.stream_ptr(dev)), "a0_rb_gather")
         return Batch(frames, act, r64, d8, prio, idx, weights, r32, d32, boot)
+
+    def _gather_f32(self, idx, prio, weights, out, mode):
+        dev, total = self.device, idx.numel()
+        shape = (total, self.stack) + tuple(self.frame_shape)
+        if out is not None:
+            assert out.obs is not None and out.obs.shape[0] == total, "out= was not allocated with normalized= for this size"
+            obs, nxt, act, r64, d8, r32, d32, boot = (out.obs, out.next_obs, out.actions, out.rewards, out.terminals,
+                                                      out.rewards_f32, out.terminals_f32, out.boot_indices)
+        else:
+            e = lambda dt, *s: torch.empty(s or (total,), dtype=dt, device=dev)
+            obs, nxt = e(torch.float32, *shape), e(torch.float32, *shape)
+            act, r64, d8, r32 = e(torch.int64), e(torch.float64), e(torch.bool), e(torch.float32)
+            d32, boot = e(torch.float32), e(torch.int64)
+        _lib.check(self.lib.a0_rb_gather_f32(
+            self.h, _lib.ptr(idx, torch.int64), total, self.n_gather, self.gamma, obs.data_ptr(), nxt.data_ptr(), mode,
+            act.data_ptr(), r64.data_ptr(), r32.data_ptr(), d8.data_ptr(), d32.data_ptr(), boot.data_ptr(),
+            _lib.stream_ptr(dev)), "a0_rb_gather_f32")
+        return Batch(None, act, r64, d8, prio, idx, weights, r32, d32, boot, obs, nxt)
 
     def is_weights(self, prio, batch):
         """trainer.py:91-94 with torch ops (used only when indices are given explicitly; the

@@ -11,7 +11,14 @@ sample several batches ahead with a fork-time snapshot of the priorities (SURVEY
 from __future__ import annotations
 
 from .learner import make_learner
-from .replay import ReplayDataset, split_batches
+from .replay import NORM_RECIP, ReplayDataset, split_batches
+
+
+def _learner_data(b):
+    """The reference's ``data`` tuple of BaseLearner.train (agent.py:126-131); with the fused gather the
+    first field is the (obs, next_obs) f32 pair instead of the u8 frames."""
+    frames = (b.obs, b.next_obs) if b.frames is None else b.frames
+    return (frames, b.actions, b.rewards_f32, b.terminals_f32, b.weights, b.indices)
 
 
 class GraphedUpdates:
@@ -22,22 +29,22 @@ class GraphedUpdates:
     replay.  The first call runs eagerly (it is also the warm-up) and captures; later calls replay.
     At batch 32 the eager loop is bound by ~150 kernel launches per update; the replay is not."""
 
-    def __init__(self, learner, replay, batch_size, learner_steps):
+    def __init__(self, learner, replay, batch_size, learner_steps, normalized=None):
         import torch
         assert learner.capturable, "construct the learner with capturable=True"
         freq = learner.cfg.learner.target_update_freq
         assert freq % learner_steps == 0, "target_update_freq must be a multiple of learner_steps for graphed updates"
         self.torch, self.learner, self.replay = torch, learner, replay
         self.B, self.L = int(batch_size), int(learner_steps)
-        self.static = replay.alloc_batch(self.B * self.L)
+        self.normalized = normalized
+        self.static = replay.alloc_batch(self.B * self.L, normalized=normalized)
         self.graph, self.outs = None, None
 
     def _updates(self):
-        self.replay.sample(self.B, k_batches=self.L, out=self.static, dynamic=True)
+        self.replay.sample(self.B, k_batches=self.L, out=self.static, dynamic=True, normalized=self.normalized)
         outs = []
         for b in split_batches(self.static, self.B):
-            data = (b.frames, b.actions, b.rewards_f32, b.terminals_f32, b.weights, b.indices)
-            result = self.learner.update(data)
+            result = self.learner.update(_learner_data(b))
             self.replay.update_priority(result["indices"], result["q_loss"])
             outs.append((result["q_loss"], result["fraction_loss"]))
         return outs
@@ -62,9 +69,13 @@ class GraphedUpdates:
 
 
 class Trainer:
-    def __init__(self, cfg, process_group=None, native_nstep=False, graph=False, **replay_kw):
-        """graph=True: the learner updates of a step run as one CUDA-graph replay (GraphedUpdates)."""
+    def __init__(self, cfg, process_group=None, native_nstep=False, graph=False, fused_input=False, **replay_kw):
+        """graph=True: the learner updates of a step run as one CUDA-graph replay (GraphedUpdates).
+        fused_input=True: K3 writes the learner's normalised f32 obs / next_obs directly
+        (a0_rb_gather_f32) instead of u8 frames that torch then casts, divides and splits
+        (agent.py:129-135); ``x * fl(1/255)``, i.e. bit-identical to torch's CUDA ``.div(255)``."""
         self.cfg = cfg
+        self.normalized = NORM_RECIP if fused_input else None
         self.replay = ReplayDataset(cfg, native_nstep=native_nstep, **replay_kw)
         self.graph = bool(graph)
         self.learner = make_learner(cfg, process_group=process_group, device=self.replay.device,
@@ -82,12 +93,11 @@ class Trainer:
         B = cfg.learner.batch_size
         if self.graph:
             if self._graphed is None or self._graphed.L != L:
-                self._graphed = GraphedUpdates(self.learner, self.replay, B, L)
+                self._graphed = GraphedUpdates(self.learner, self.replay, B, L, normalized=self.normalized)
             return self._graphed.run()
         out = []
-        for b in split_batches(self.replay.sample(B, k_batches=L), B):
-            data = (b.frames, b.actions, b.rewards_f32, b.terminals_f32, b.weights, b.indices)
-            result = self.learner.train(data)
+        for b in split_batches(self.replay.sample(B, k_batches=L, normalized=self.normalized), B):
+            result = self.learner.train(_learner_data(b))
             self.replay.update_priority(result["indices"], result["q_loss"])
             out.append((result["q_loss"], result["fraction_loss"]))
         return out

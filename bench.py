@@ -638,6 +638,36 @@ def extras(rp, args, torch, peak):
                                   "k3_GBps": round(bytes_per_transition(wl["n"]) * hp.total / k3 / 1e9, 1),
                                   "k2a_us": round(k2a * 1e6, 2), "k2b_us": round(k2b * 1e6, 2), "desc": wl["desc"]}
         del hp
+    # K3 with the learner's input conversion fused in (a0_rb_gather_f32) against the three-pass
+    # alternative it replaces: K3 to u8, then torch's .float() and .div(255) (agent.py:129-135)
+    out["k3_f32"] = []
+    from agent0_b200 import _lib as LB
+    lib = LB.load()
+    for name, count in (("c51_b32", 640), ("c51_b512", 10240)):
+        wl = WORKLOADS[name]
+        hp = HotPath(rp, wl, L, A, torch, variant=args.variant)
+        hp.draw_pool()
+        nbuf = 4 if count <= 1024 else 1
+        obs = torch.empty(nbuf, count, 4 * F_BYTES, dtype=torch.float32, device=hp.dev)
+        nxt = torch.empty_like(obs)
+
+        def fused(i):
+            LB.check(lib.a0_rb_gather_f32(rp.h, hp.idx_pool[i % INNER].data_ptr(), count, hp.n, 0.99, obs[i % nbuf].data_ptr(),
+                                          nxt[i % nbuf].data_ptr(), 1, hp.act.data_ptr(), hp.r64.data_ptr(), hp.r32.data_ptr(),
+                                          hp.d8.data_ptr(), hp.d32.data_ptr(), hp.boot.data_ptr(), hp._st()), "a0_rb_gather_f32")
+
+        def three_pass(i):
+            hp.gather(pool=i)
+            x = hp.frames_pool[i % hp.n_out].view(count, 8, 84, 84).float().div(255.0)
+            return x
+
+        t_f = time_kernel(fused, 40, torch)
+        t_3 = time_kernel(three_pass, 40, torch)
+        by = (4 + min(wl["n"], 4)) * F_BYTES + 8 * F_BYTES * 4
+        out["k3_f32"].append({"transitions": count, "fused_us": round(t_f * 1e6, 2), "three_pass_us": round(t_3 * 1e6, 2),
+                              "fused_GBps": round(by * count / t_f / 1e9, 1), "frac_of_measured_peak": round(by * count / t_f / 1e9 / peak, 4),
+                              "bytes_per_transition": by})
+        del hp, obs, nxt
     wl = dict(WORKLOADS["c51_b512"])
     hp = HotPath(rp, wl, 128, A, torch)           # buffers for up to 65536 transitions
     hp.draw_pool()

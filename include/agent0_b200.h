@@ -17,6 +17,7 @@
  *   agent0/deepq/replay.py:39-43   ReplayDataset.__iter__ (draw)   -> a0_pt_sample
  *   agent0/deepq/replay.py:32-37   ReplayDataset.__getitem__ + default_collate, and
  *   agent0/deepq/agent.py:64-73    Actor.sample's n-step tracker   -> a0_rb_gather
+ *   agent0/deepq/agent.py:129-135  BaseLearner.train: /255 + split -> a0_rb_gather_f32
  *   agent0/deepq/trainer.py:91-94  IS weights in Trainer.step      -> a0_pt_sample (epilogue)
  *   agent0/deepq/replay.py:55-59   ReplayDataset.update_priority   -> a0_pt_update
  *   agent0/deepq/agent.py:173-190  DQNLearner.train_step           -> a0_loss_dqn
@@ -24,6 +25,7 @@
  *   agent0/deepq/agent.py:219-269  C51Learner.train_step           -> a0_loss_c51
  *   agent0/deepq/agent.py:110-114,273-327 huber_qr_loss, QR/IQN    -> a0_loss_quantile
  *   agent0/deepq/agent.py:340-388  FQFLearner.train_step           -> a0_loss_quantile (+fraction)
+ *   agent0/deepq/agent.py:25-39    Actor.act (actor side, "next")  -> a0_u8_to_f32 + a0_act_epsilon_greedy
  */
 #ifndef AGENT0_B200_H
 #define AGENT0_B200_H
@@ -199,6 +201,15 @@ int a0_rb_gather(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count, in
                  float* reward32_out, uint8_t* done8_out, float* done32_out, int64_t* boot_out,
                  int32_t variant, a0_stream_t stream);
 
+/* K3 with the learner's input conversion fused in (agent.py:129-135: reshape, .float(), .div(255),
+ * split into obs / next_obs).  obs_out, next_out: f32 [count][4][frame_bytes], contiguous, ready
+ * for the CNN.  norm_mode 0: x/255 correctly rounded (torch on the CPU); 1: x * fl(1/255) (torch's
+ * CUDA div-by-scalar); 2: (float)x.  Scalar outputs as a0_rb_gather.                               */
+int a0_rb_gather_f32(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count, int32_t n_step,
+                     double gamma, float* obs_out, float* next_out, int32_t norm_mode,
+                     int64_t* action_out, double* reward64_out, float* reward32_out,
+                     uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream);
+
 /* ---- K4: fused target + loss + IS weighting + new priority -----------------------------------------------
  * Common arguments: B samples; A actions; action i64[B]; reward f32[B] (n-step return); done f32[B]
  * in {0,1}; weight f32[B]; gamma_n = float(discount**n_step).  Outputs: loss f32[B] (unweighted,
@@ -238,6 +249,22 @@ int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const float* q, 
                      const float* taus, const float* qsel, int32_t Ni, int32_t Nj, float* grad,
                      const float* q_bar, const float* taus_full, float* fraction_loss,
                      float* grad_taus, a0_stream_t stream);
+
+/* ---- K5: actor-side helpers (actor inference batching) ----------------------------------
+ * a0_act_epsilon_greedy replaces the tail of Actor.act (agent.py:30-39): per env e,
+ *   action[e] = u[e] > epsilon ? argmax_a q[e,a] : action_random[e]   (np.where(rand > eps, greedy, random))
+ *   qmax_out[e] = max_a q[e,a] (optional), *qmax_mean = mean_e qmax (qt_max.mean()).
+ * q f32[E,A] = model.qval(obs); u f64[E] and action_random i64[E] are the caller's draws (numpy's
+ * generator in the reference: randint first, then rand).  scratch: 8 bytes of device memory, zero
+ * before the first call (the kernel re-arms it).
+ * a0_u8_to_f32 is Actor.act's input conversion (agent.py:27), count a multiple of 16 bytes,
+ * norm_mode as a0_rb_gather_f32.                                                                  */
+int a0_act_epsilon_greedy(const float* q /* dev */, int32_t E, int32_t A, double epsilon,
+                          const double* u /* dev */, const int64_t* action_random /* dev */,
+                          int64_t* action_out, float* qmax_out, float* scratch, float* qmax_mean,
+                          a0_stream_t stream);
+int a0_u8_to_f32(const uint8_t* in /* dev */, float* out /* dev */, int64_t count, int32_t norm_mode,
+                 a0_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,8 @@ Follows, line by line:
   * ReplayDataset                                  agent0/deepq/replay.py:14-59
   * LinearSchedule                                 agent0/common/utils.py:12-28
   * the .float() + IS-weight block of Trainer.step agent0/deepq/trainer.py:88-96
-Pinned against tests/golden/{replay_n1,replay_n3,per_state,trainer_step}.npz, which are
+  * Actor.act's epsilon-greedy selection            agent0/deepq/agent.py:25-39
+Pinned against tests/golden/{replay_n1,replay_n3,per_state,trainer_step,act}.npz, which are
 outputs of the unmodified reference.
 """
 from collections import deque
@@ -113,3 +114,20 @@ def is_weights(batch_priority, priority_sum_all, top, beta):
     probs = p / np.float32(priority_sum_all)
     w = np.power(np.float32(top) * probs, np.float32(-beta)).astype(np.float32)
     return (w / (w.max() + np.float32(1e-8))).astype(np.float32)
+
+
+def act_rule(q, epsilon, num_actions, rng=np.random):
+    """Actor.act (agent.py:29-39) after the network: draws randint first, then rand (float64), from
+    numpy's generator; action = where(rand > epsilon, argmax_a q, random); returns the mean of the
+    per-env maximum in float32 like ``qt_max.mean().item()``."""
+    q = np.asarray(q, dtype=np.float32)
+    E = q.shape[0]
+    action_random = rng.randint(0, num_actions, E)
+    greedy = q.argmax(axis=-1)
+    action = np.where(rng.rand(E) > epsilon, greedy, action_random)
+    return action.astype(np.int64), float(q.max(axis=-1).mean(dtype=np.float32))
+
+
+def obs_to_float(obs):
+    """agent.py:27 / agent.py:129-131 on the CPU: uint8 -> float32, true division by 255."""
+    return np.asarray(obs, dtype=np.uint8).astype(np.float32) / np.float32(255.0)

@@ -16,6 +16,7 @@ Fixtures:
   trainer_step.npz    the real Trainer.step inner loop (IS weights, priorities)
   loss_<algo>_<dq>.npz  train_step inputs/outputs/autograd grads, six algos
   static_fns.npz      huber_qr_loss / log_softmax_stable known answers
+  act.npz             Actor.act epsilon-greedy selection (python tests/golden/make_golden.py --only act)
 """
 import os
 import sys
@@ -433,9 +434,41 @@ def gen_static_fns():
     print("static_fns ok")
 
 
+def gen_act():
+    """The unmodified Actor.act (agent.py:25-39) with the real DeepQNet on CPU: per call the q-values it
+    computed (captured from model.qval), numpy's seed, the chosen actions and the returned mean."""
+    E, T = 16, 6
+    out = {}
+    for algo in ("dqn", "c51"):
+        torch.manual_seed(7)
+        stream = record_stream(E, T, seed=321, p_terminal=0.05, p_life_loss=0.05, p_truncated=0.02)
+        cfg = base_cfg(E=E, n=1, algo=algo, steps=T, dueling=(algo == "c51"))
+        _CURRENT_ENV["stream"] = stream
+        actor = agents.Actor(cfg)
+        seen = []
+        inner = actor.model.qval
+        actor.model.qval = lambda st: (seen.append((st.clone(), inner(st))), seen[-1][1])[1]   # instance attribute
+        qs, sts, acts, means, epss, seeds = [], [], [], [], [], []
+        for k, eps in enumerate((0.0, 0.05, 0.3, 0.7, 1.0, 0.5)):
+            actor.obs = stream["obs"][k]
+            np.random.seed(1000 + k)
+            a, m = actor.act(eps)
+            st, q = seen[-1]
+            qs.append(q.numpy().copy()); sts.append(st.numpy().copy()); acts.append(np.asarray(a, dtype=np.int64))
+            means.append(m); epss.append(eps); seeds.append(1000 + k)
+        out.update({f"{algo}_q": np.stack(qs), f"{algo}_action": np.stack(acts), f"{algo}_qmax_mean": np.array(means, dtype=np.float64),
+                    f"{algo}_st_first": sts[0], f"{algo}_obs_first": stream["obs"][0]})
+        out["epsilon"], out["np_seed"] = np.array(epss), np.array(seeds)
+    np.savez_compressed(os.path.join(HERE, "act.npz"), **out)
+    print("act ok:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     np.random.seed(0)
     torch.manual_seed(0)
+    if "--only" in sys.argv:
+        globals()["gen_" + sys.argv[sys.argv.index("--only") + 1]]()
+        sys.exit(0)
     gen_replay(1)
     gen_replay(3)
     gen_per_state()

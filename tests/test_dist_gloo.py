@@ -81,7 +81,19 @@ def _worker(rank, port, out):
         tops = torch.tensor([float(ix.top)])
         dist.all_reduce(tops)
         s_g, top_g = global_priority_stats(torch.tensor(1.5 + rank), ix.top, dist.group.WORLD)
-        out[rank] = dict(params=flat.numpy(), top_sum=float(tops.item()), local_top=ix.top,
+        # weight hand-off to actor ranks (launch.py:33-36): one flat broadcast instead of a pickled state_dict
+        from agent0_b200.actor import broadcast_model, flat_state
+        from agent0_b200.config import make_config
+        from agent0_b200.model import DeepQNet
+        cfg = make_config("c51", dueling=True, action_dim=4)
+        torch.manual_seed(50 + rank)                      # every rank starts from different weights
+        model = DeepQNet(cfg)
+        model.register_buffer("steps_seen", torch.tensor([3 + rank]))     # an integer buffer rides along
+        before = torch.cat([t.reshape(-1).float() for t in flat_state(model)]).clone()
+        sent = broadcast_model(model, src=0, process_group=dist.group.WORLD)
+        after = torch.cat([t.reshape(-1).float() for t in flat_state(model)])
+        out[rank] = dict(model_before=before.numpy(), model_after=after.numpy(), model_bytes=sent,
+                         params=flat.numpy(), top_sum=float(tops.item()), local_top=ix.top,
                          stats=(float(s_g), float(top_g)), streams=mine)
     finally:
         dist.destroy_process_group()
@@ -121,3 +133,11 @@ def test_global_priority_stats(gloo_run):
     s_g, top_g = gloo_run[0]["stats"]
     assert s_g == pytest.approx(1.5 + 2.5) and top_g == gloo_run[0]["top_sum"]
     assert gloo_run[1]["stats"] == gloo_run[0]["stats"]
+
+
+def test_broadcast_model_replaces_state_dict_shipping(gloo_run):
+    r0, r1 = gloo_run[0], gloo_run[1]
+    assert not np.array_equal(r0["model_before"], r1["model_before"])
+    assert np.array_equal(r0["model_after"], r0["model_before"])               # the source is unchanged
+    assert np.array_equal(r1["model_after"], r0["model_before"])               # the actor rank now holds the learner's net
+    assert r0["model_bytes"] == r1["model_bytes"] == (len(r0["model_before"]) - 1) * 4 + 8

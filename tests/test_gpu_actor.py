@@ -1,0 +1,96 @@
+"""K5 on the GPU through the C ABI: Actor.act's epsilon-greedy selection (agent0/deepq/agent.py:25-39)
+against outputs of the unmodified reference (tests/golden/act.npz) and the oracle restatement.
+Bit-exact: actions, normalised observations; <=1e-6 relative: the mean of the per-env max."""
+import numpy as np
+import pytest
+import torch
+
+from agent0_b200.config import make_config
+from oracle import reference_replay as OR
+
+pytestmark = pytest.mark.gpu
+
+
+class _TableNet(torch.nn.Module):
+    """Stands in for DeepQNet where the kernel's input must be exactly the reference's q-values."""
+
+    def __init__(self, q):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+        self.q = torch.as_tensor(q, device="cuda")
+        self.seen = None
+
+    def qval(self, st):
+        self.seen = st.clone()
+        return self.q
+
+
+@pytest.mark.parametrize("algo", ["dqn", "c51"])
+def test_actor_policy_matches_reference_act(golden, algo):
+    from agent0_b200.actor import ActorPolicy
+    from agent0_b200.replay import NORM_DIV
+    g = golden("act")
+    cfg = make_config(algo, action_dim=4, num_envs=16)
+    obs = g[f"{algo}_obs_first"]
+    for k, (eps, seed) in enumerate(zip(g["epsilon"], g["np_seed"])):
+        net = _TableNet(g[f"{algo}_q"][k])
+        pol = ActorPolicy(cfg, net, norm_mode=NORM_DIV)
+        np.random.seed(int(seed))                       # numpy's global generator, as the reference
+        a, m = pol.act(obs, float(eps))
+        assert a.dtype == np.int64 and np.array_equal(a, g[f"{algo}_action"][k])
+        assert abs(m - g[f"{algo}_qmax_mean"][k]) <= 1e-6 * max(1.0, abs(g[f"{algo}_qmax_mean"][k]))
+        # the network saw exactly the reference's input (agent.py:27 on the CPU: true division)
+        assert np.array_equal(net.seen.cpu().numpy().view(np.int32), g[f"{algo}_st_first"].view(np.int32))
+        # the same generator state is consumed: the next draw agrees with the reference's stream
+        np.random.seed(int(seed))
+        OR.act_rule(g[f"{algo}_q"][k], float(eps), 4)
+        nxt = np.random.rand()
+        np.random.seed(int(seed))
+        pol.act(obs, float(eps))
+        assert np.random.rand() == nxt
+
+
+def test_actor_policy_with_the_real_network_and_private_rng():
+    """Real DeepQNet, many envs, a private RandomState: equals the oracle rule applied to the q-values
+    torch computes from torch's own cast/divide of the same observations on this device."""
+    from agent0_b200.actor import ActorPolicy
+    from agent0_b200.model import DeepQNet
+    cfg = make_config("qr", action_dim=18, num_envs=70)
+    torch.manual_seed(3)
+    net = DeepQNet(cfg).cuda()
+    rs = np.random.RandomState(9)
+    obs = rs.randint(0, 256, (70, 4, 84, 84)).astype(np.uint8)
+    pol = ActorPolicy(cfg, net, rng=np.random.RandomState(42))
+    for eps in (0.0, 0.5, 1.0):
+        a, m = pol.act(obs, eps)
+        with torch.no_grad():
+            q = net.qval(torch.from_numpy(obs).cuda().float().div(255.0)).cpu().numpy()
+        if eps == 0.0:
+            assert np.array_equal(a, q.argmax(-1))
+        assert a.min() >= 0 and a.max() < 18
+        assert abs(m - float(q.max(-1).mean())) <= 1e-5 * abs(float(q.max(-1).mean())) + 1e-6
+    ref_rng = np.random.RandomState(42)
+    pol2 = ActorPolicy(cfg, net, rng=np.random.RandomState(42))
+    for eps in (0.0, 0.5, 1.0):
+        with torch.no_grad():
+            q = net.qval(torch.from_numpy(obs).cuda().float().div(255.0)).cpu().numpy()
+        want, _ = OR.act_rule(q, eps, 18, rng=ref_rng)
+        got, _ = pol2.act(obs, eps)
+        assert np.array_equal(got, want)
+
+
+def test_u8_to_f32_all_modes_and_errors():
+    from agent0_b200 import _lib
+    lib = _lib.load()
+    x = torch.arange(256 * 16, dtype=torch.int64).remainder(256).to(torch.uint8).cuda()
+    out = torch.empty(x.numel(), dtype=torch.float32, device="cuda")
+    xf = x.cpu().numpy().astype(np.float32)
+    want = {0: xf / np.float32(255.0), 1: xf * (np.float32(1.0) / np.float32(255.0)), 2: xf}
+    for mode in (0, 1, 2):
+        _lib.check(lib.a0_u8_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), mode, _lib.stream_ptr()), "a0_u8_to_f32")
+        assert np.array_equal(out.cpu().numpy().view(np.int32), want[mode].view(np.int32))
+    assert torch.equal(out.new_tensor(want[1]), x.float().div(255.0))          # mode 1 is torch's CUDA .div(255)
+    assert lib.a0_u8_to_f32(x.data_ptr(), out.data_ptr(), 17, 0, _lib.stream_ptr()) == -1
+    assert lib.a0_u8_to_f32(x.data_ptr(), out.data_ptr(), 16, 5, _lib.stream_ptr()) == -1
+    assert lib.a0_act_epsilon_greedy(out.data_ptr(), 4, 64, 0.1, None, None, None, None, None, None, _lib.stream_ptr()) == -1
+    assert lib.a0_u8_to_f32(None, None, 0, 0, _lib.stream_ptr()) == 0

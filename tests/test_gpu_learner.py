@@ -119,3 +119,34 @@ def test_graphed_updates_match_the_eager_loop(golden, algo):
             assert float(diff.max()) <= updates * lr * 1.01
             assert float(diff.mean()) < 0.05 * lr and float((diff > lr).float().mean()) < 1e-3
     torch.testing.assert_close(runs[True][4], runs[False][4], rtol=5e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_input_trainer_equals_unfused(golden, graph):
+    """Trainer(fused_input=True): K3 writes the CNN's normalised f32 inputs directly (a0_rb_gather_f32,
+    x * fl(1/255) like torch's CUDA .div(255)); losses, weights and tree must equal the u8-gather +
+    torch cast/divide/split path bit for bit."""
+    from agent0_b200.config import make_config
+    from agent0_b200.trainer import Trainer
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = golden("replay_n3")
+    M = len(g["entry_action"])
+    tup = [(g["entry_frames"][i].tobytes(), g["entry_action"][i], g["entry_reward"][i], g["entry_done"][i]) for i in range(M)]
+    runs = {}
+    for fused in (False, True):
+        cfg = make_config("c51", per=True, n_step=3, batch_size=8, double_q=True, dueling=True, replay_size=256, num_envs=3)
+        cfg.trainer.training_start_steps = 10
+        cfg.learner.learner_steps = 4
+        cfg.learner.target_update_freq = 8
+        torch.manual_seed(11)
+        tr = Trainer(cfg, graph=graph, fused_input=fused)
+        tr.replay.extend(tup)
+        torch.cuda.manual_seed(5)
+        losses = [torch.stack([q for q, _ in tr.learn()]).clone() for _ in range(3)]
+        runs[fused] = (torch.stack(losses), [p.detach().clone() for p in tr.learner.model.parameters()], tr.replay.tree.clone())
+    # non-contiguous split views vs contiguous inputs can pick different cuDNN kernels: allow fp32 noise
+    torch.testing.assert_close(runs[True][0], runs[False][0], rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(runs[True][2], runs[False][2], rtol=2e-4, atol=1e-6)
+    for a, b in zip(runs[True][1], runs[False][1]):
+        assert float((a - b).abs().max()) <= 12 * cfg.learner.learning_rate * 1.01

@@ -141,6 +141,69 @@ def test_host_fed_ingest_modes_and_wraparound(mode):
     assert np.array_equal(_np(b.terminals), d_ref[ref_i]) and np.array_equal(_np(b.actions), a_ref[ref_i])
 
 
+def _norm_ref(u8, mode):
+    """agent.py:129-135 / trainer.py:88-90 on the host: mode 0 = torch-CPU true division, 1 = torch-CUDA
+    reciprocal multiply, 2 = .float() only; all float32."""
+    x = u8.astype(np.float32)
+    if mode == 0:
+        return x / np.float32(255.0)
+    if mode == 1:
+        return x * (np.float32(1.0) / np.float32(255.0))
+    return x
+
+
+@pytest.mark.parametrize("n", [1, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fused_f32_gather_equals_reference_float_div_split(golden, n, mode):
+    """a0_rb_gather_f32 = K3 + BaseLearner.train's reshape/.float()/.div(255)/split (agent.py:129-135):
+    bit-exact f32 against the reference actor's entries converted on the host, scalars as K3."""
+    g = golden(f"replay_n{n}")
+    E, T = int(g["num_envs"]), int(g["steps"])
+    obs = g["stream_obs"]
+    done = OR.done_rule(g["stream_terminal"], g["stream_life_loss"], g["stream_truncated"])
+    rp = _replay(256, n=n, native=True, E=E)
+    for k in range(T):
+        rp.append_vector_step(obs[k], g["stream_action"][k], g["stream_reward"][k], done[k], obs[k + 1])
+    ks, es = np.meshgrid(np.arange(n - 1, T), np.arange(E), indexing="ij")
+    ref_i = (ks * E + es).reshape(-1)
+    pos = torch.as_tensor(((ks - n + 1) * E + es).reshape(-1), device="cuda")
+    b = rp.gather(pos, normalized=mode)
+    assert b.frames is None and b.obs.dtype == torch.float32 and b.obs.shape == (len(ref_i), 4, 84, 84)
+    ref = _norm_ref(g["entry_frames"][ref_i].reshape(-1, 8, 84, 84), mode)
+    assert np.array_equal(_np(b.obs).view(np.int32), ref[:, :4].view(np.int32))
+    assert np.array_equal(_np(b.next_obs).view(np.int32), ref[:, 4:].view(np.int32))
+    assert np.array_equal(_np(b.actions), g["entry_action"][ref_i])
+    assert np.array_equal(_np(b.rewards).view(np.int64), g["entry_reward"][ref_i].view(np.int64))
+    assert np.array_equal(_np(b.terminals), g["entry_done"][ref_i])
+    # the u8 gather + torch's own cast/divide on this device gives the same bits as mode 1
+    if mode == 1:
+        u = rp.gather(pos).frames.reshape(-1, 8, 84, 84).float().div(255.0)
+        assert torch.equal(u[:, :4], b.obs) and torch.equal(u[:, 4:], b.next_obs)
+
+
+def test_fused_f32_gather_every_byte_value_and_out_buffers():
+    """All 256 byte values through the three normalisations; preallocated out= buffers; error paths."""
+    from agent0_b200.replay import NORM_DIV
+    E = 2
+    rp = _replay(64, n=1, native=True, E=E)
+    ramp = (np.arange(4 * 84 * 84, dtype=np.int64) % 256).astype(np.uint8).reshape(4, 84, 84)
+    obs0 = np.stack([ramp, ramp[::-1].copy()])
+    rp.reset_streams(np.arange(E), obs0)
+    new = np.stack([np.full((84, 84), 255, np.uint8), np.zeros((84, 84), np.uint8)])
+    rp.append_steps(np.arange(E), np.ones(E, dtype=np.int64), new, np.array([1, 2]), np.array([0.5, -1.0]), np.array([False, True]))
+    pos = torch.arange(E, device="cuda")
+    u8 = _np(rp.gather(pos).frames).reshape(E, 8, 84, 84)
+    for mode in (0, 1, 2):
+        b = rp.gather(pos, normalized=mode)
+        ref = _norm_ref(u8, mode)
+        assert np.array_equal(_np(b.obs), ref[:, :4]) and np.array_equal(_np(b.next_obs), ref[:, 4:])
+    out = rp.alloc_batch(E, normalized=NORM_DIV)
+    b = rp.sample(E, indices=pos, out=out)
+    assert b.obs.data_ptr() == out.obs.data_ptr() and np.array_equal(_np(out.obs), _norm_ref(u8, 0)[:, :4])
+    with pytest.raises(RuntimeError, match="norm_mode"):
+        rp.gather(pos, normalized=7)
+
+
 def test_sumtree_sample_update_bit_exact():
     """K2a/K2b against oracle/sumtree.py: same leaves, same uniforms -> identical indices and an
     identical tree, node for node."""

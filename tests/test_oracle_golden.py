@@ -169,3 +169,15 @@ def test_sumtree_invariants_and_law():
     emp = counts / counts.sum()
     assert np.abs(emp - law).max() < 4e-3
     assert abs(np.corrcoef(emp, law)[0, 1]) > 0.97
+
+
+# ------------------------------------------------------------------ Actor.act
+@pytest.mark.parametrize("algo", ["dqn", "c51"])
+def test_act_rule_matches_reference_actor(golden, algo):
+    g = golden("act")
+    for k, (eps, seed) in enumerate(zip(g["epsilon"], g["np_seed"])):
+        np.random.seed(int(seed))
+        a, m = OR.act_rule(g[f"{algo}_q"][k], float(eps), 4)
+        assert np.array_equal(a, g[f"{algo}_action"][k])
+        close(m, g[f"{algo}_qmax_mean"][k], rtol=1e-6)
+    assert np.array_equal(OR.obs_to_float(g[f"{algo}_obs_first"]).view(np.int32), g[f"{algo}_st_first"].view(np.int32))
