@@ -91,6 +91,10 @@ constexpr int A0_PDL_DEFAULT = A0_PDL_K4;   // measured: K4-only is best at B=32
 bool a0_pdl_enabled(int kernel_class);
 int a0_option_k2b_levels();
 
+// (Measured alternative: launch_dependents BEFORE the wait lets a whole chain of dependent kernels
+// become resident launches ahead.  It does not lower the ~2.85 us per-link cost of the batch-32 K4
+// chain -- that cost is the completion hand-over, not launch latency -- and the pre-launched CTAs
+// take SM resources from a heavy predecessor: QR-200 K4 10.6 -> 16.7 us.  Not used.)
 #define A0_PDL_PROLOGUE()                                   \
   do {                                                      \
     asm volatile("griddepcontrol.wait;" ::: "memory");      \

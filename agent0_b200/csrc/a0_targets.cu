@@ -141,17 +141,32 @@ constexpr int C51_MAXR = 4;     // atoms per lane: M <= 128
 constexpr int C51_SPEC_A = 6;   // speculative all-action row fetch up to this many actions
 
 // Adds v (keyed by destination bin) into bins[]: runs of equal adjacent keys are reduced with
-// shuffles first.  key < 0 marks a lane without a term.
-__device__ __forceinline__ void a0_c51_scatter(float* bins, int key, float v, int lane) {
+// shuffles first.  key < 0 marks a lane without a term.  NP independent (key, value) streams are
+// scanned together -- their shuffles are issued back to back, so the five dependent steps cost one
+// shuffle latency each instead of NP -- and then added stream by stream in a fixed order.
+template <int NP>
+__device__ __forceinline__ void a0_c51_scatter(float* bins, const int (&key)[NP], float (&v)[NP], int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const float vu = __shfl_up_sync(0xffffffffu, v, d);
-    const int ku = __shfl_up_sync(0xffffffffu, key, d);
-    if (lane >= d && ku == key) v = __fadd_rn(v, vu);
+    float vu[NP];
+    int ku[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      vu[p] = __shfl_up_sync(0xffffffffu, v[p], d);
+      ku[p] = __shfl_up_sync(0xffffffffu, key[p], d);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (lane >= d && ku[p] == key[p]) v[p] = __fadd_rn(v[p], vu[p]);
   }
-  const int kn = __shfl_down_sync(0xffffffffu, key, 1);
-  if (key >= 0 && (lane == 31 || kn != key)) atomicAdd(bins + key, v);   // one writer per bin when keys are sorted
-  __syncwarp();
+  int kn[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) kn[p] = __shfl_down_sync(0xffffffffu, key[p], 1);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    if (key[p] >= 0 && (lane == 31 || kn[p] != key[p])) atomicAdd(bins + key[p], v[p]);   // one writer per bin when keys are sorted
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(C51_WARPS * 32)
@@ -202,11 +217,29 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
       if (a2 == a) { l[0] = lo_all[a2][0]; l[1] = lo_all[a2][1]; }
   }
 
-  // ---- action selection ------------------------------------------------------------------------
+  // ---- action selection + the reductions of both softmaxes ---------------------------------------
+  // This kernel is one warp per sample and latency-bound: every warp reduction is five dependent
+  // shuffle steps.  Independent reductions are therefore advanced together, one shuffle latency
+  // per step for the pair: (arg-max of qsel | max of the online row), then (max of the selected
+  // target row | sum-exp of the online row).
+  float omx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) omx = fmaxf(omx, l[k]);
   int a_star;
   if (qsel) {
-    a_star = a0_warp_argmax(qs, lane);
+    float v = qs;
+    int vi = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+      const float om = __shfl_xor_sync(0xffffffffu, omx, o);
+      if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
+      omx = fmaxf(omx, om);
+    }
+    a_star = vi;
   } else {
+    omx = a0_warp_max(omx);
     // argmax_a sum_j softmax(tgt[b,a,:])_j * z_j (agent.py:226)
     float best = -INFINITY;
     a_star = 0;
@@ -231,7 +264,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
     }
   }
 
-  // ---- softmax of the selected target row --------------------------------------------------------
+  // ---- softmax of the selected target row | sum-exp of the online row -----------------------------
   const float* trow = tgt_logits + ((size_t)b * A + a_star) * M;
   float p[C51_MAXR], mx = -INFINITY;
 #pragma unroll
@@ -247,7 +280,16 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   }
 #pragma unroll
   for (int k = 0; k < C51_MAXR; ++k) mx = fmaxf(mx, p[k]);
-  mx = a0_warp_max(mx);
+  float ose = 0.0f;
+#pragma unroll
+  for (int k = 0; k < C51_MAXR; ++k) ose += (k < R && lane + 32 * k < M) ? expf(l[k] - omx) : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const float os = __shfl_xor_sync(0xffffffffu, ose, o);
+    mx = fmaxf(mx, om);
+    ose += os;
+  }
   float se = 0.0f;
 #pragma unroll
   for (int k = 0; k < C51_MAXR; ++k) { p[k] = (k < R && lane + 32 * k < M) ? expf(p[k] - mx) : 0.0f; se += p[k]; }
@@ -276,25 +318,20 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
     }
   }
   __syncwarp();
-#pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k)
-    if (k < R) a0_c51_scatter(s_m[wid], lo[k], wlo[k], lane);
-#pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k)
-    if (k < R) a0_c51_scatter(s_m[wid], up[k], wup[k], lane);
+  if (R <= 2) {
+    // M <= 64 (the 51-atom case): lower and upper terms of both atom chunks in one scan
+    const int key4[4] = {lo[0], lo[1], up[0], up[1]};
+    float val4[4] = {wlo[0], wlo[1], wup[0], wup[1]};
+    a0_c51_scatter<4>(s_m[wid], key4, val4, lane);
+  } else {
+    a0_c51_scatter<C51_MAXR>(s_m[wid], lo, wlo, lane);
+    a0_c51_scatter<C51_MAXR>(s_m[wid], up, wup, lane);
+  }
   float m[C51_MAXR];
 #pragma unroll
   for (int k = 0; k < C51_MAXR; ++k) m[k] = s_m[wid][lane + 32 * k];
 
   // ---- cross-entropy with the online row, gradient through log_softmax (agent.py:266-268) ------
-  float omx = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k) omx = fmaxf(omx, l[k]);
-  omx = a0_warp_max(omx);
-  float ose = 0.0f;
-#pragma unroll
-  for (int k = 0; k < C51_MAXR; ++k) ose += (k < R && lane + 32 * k < M) ? expf(l[k] - omx) : 0.0f;
-  ose = a0_warp_sum(ose);
   const float lse = logf(ose);
   float ce = 0.0f, msum = 0.0f;
 #pragma unroll
