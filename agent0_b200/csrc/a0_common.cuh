@@ -45,6 +45,8 @@ struct a0_replay {
   A0Staging staging[2];
   int staging_turn;
   cudaStream_t copy_stream;   // lazily created; carries the ingest DMA under A0_INGEST_COPY_STREAM
+  int64_t stride_hint;        // distance record -> successor of the same stream seen by the last appends
+                              // (0: not uniform); lets K3 fetch an n-step window without chasing links
 };
 
 void a0_set_error(const char* fmt, ...);

@@ -273,6 +273,19 @@ extern "C" int a0_rb_ingest_plan(a0_replay_t* h, const a0_plan_t* plan, const ui
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t F = (size_t)h->F;
+  // successor stride of this append (rec_meta: {pos, link_from, ...}): the same for every record when
+  // the actors step in lockstep; K3 uses it as a (verified) guess, see a0_spec_fetch
+  if (m > 0) {
+    int64_t stride = -1;
+    for (int32_t i = 0; i < m && stride != 0; ++i) {
+      const int32_t* mt = plan->rec_meta + (size_t)i * A0_REC_META_I32;
+      if (mt[1] < 0) continue;                         // first record of its stream
+      int64_t dlt = (int64_t)mt[0] - mt[1];
+      if (dlt <= 0) dlt += h->N;
+      stride = (stride < 0 || stride == dlt) ? dlt : 0;
+    }
+    if (stride >= 0) h->stride_hint = stride;
+  }
   const bool stage_frames = n_new > 0 && !on_device && !pinned;
   size_t sec[5];
   sec[0] = 0;

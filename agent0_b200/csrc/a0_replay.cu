@@ -217,6 +217,7 @@ struct A0GatherArgs {
   const int64_t* idx;
   int64_t N, NF;
   int32_t F, count, n_step;
+  int32_t stride_hint;   // expected distance between a record and its successor in the same stream (0: unknown)
   double gamma;
   uint8_t* frames_out;
   int64_t* action_out;
@@ -264,6 +265,83 @@ __device__ __forceinline__ int64_t a0_walk_window(const A0GatherArgs& g, int b, 
   if (g.done8_out) g.done8_out[b] = (uint8_t)d_any;
   if (g.done32_out) g.done32_out[b] = (float)d_any;
   if (g.boot_out) g.boot_out[b] = ok ? (int64_t)link : -1;
+  return p;
+}
+
+// The same walk with the dependent chain speculated away.  Vector actors append one record per
+// stream per step, so the successor of record p is almost always (p + stride) mod N, stride = the
+// number of streams (the ingest path measures it: a0_replay::stride_hint).  The records and the
+// next-stack slots of the guessed window are fetched together with the first record -- ONE
+// memory round trip instead of n_step + 1 dependent ones -- and used only where the stored link
+// confirms the guess; anything else falls back to the dependent load.  Results are identical.
+constexpr int K3_SPEC_MAX = 4;         // speculate windows of up to this many records
+struct A0Spec {
+  int64_t pos[K3_SPEC_MAX];            // guessed record positions (pos[0] = p0)
+  A0RecInfo info[K3_SPEC_MAX];
+  int4 next_slots;                     // rec_slots[pos[n-1]][4..7]
+  bool on;
+};
+__device__ __forceinline__ void a0_spec_fetch(const A0GatherArgs& g, int64_t p0, A0Spec& sp) {
+  sp.on = g.n_step <= K3_SPEC_MAX && (g.n_step == 1 || g.stride_hint > 0);
+  if (!sp.on) return;
+  int64_t p = p0;
+#pragma unroll
+  for (int i = 0; i < K3_SPEC_MAX; ++i) {
+    sp.pos[i] = p;
+    if (i > 0 && i < g.n_step) sp.info[i] = g.rec_info[p];
+    if (i == g.n_step - 1) sp.next_slots = reinterpret_cast<const int4*>(g.rec_slots + (size_t)p * A0_SLOTS)[1];
+    p += g.stride_hint;
+    if (p >= g.N) p -= g.N;
+  }
+}
+__device__ __forceinline__ int64_t a0_walk_window_spec(const A0GatherArgs& g, int b, int64_t p0, A0RecInfo info,
+                                                       const A0Spec& sp, bool& ok, int4& next_slots) {
+  if (!sp.on) {
+    const int64_t pl = a0_walk_window(g, b, p0, info, ok);
+    next_slots = reinterpret_cast<const int4*>(g.rec_slots + (size_t)pl * A0_SLOTS)[1];
+    return pl;
+  }
+  double rew[K3_SPEC_MAX];
+  int dn[K3_SPEC_MAX];
+  int64_t p = p0;
+  const int32_t action = info.action_done & 0x7fffffff;
+  int32_t link = -1;
+  int steps = 0;
+  bool guessed = true;                 // every record so far sits where the guess put it
+#pragma unroll
+  for (int i = 0; i < K3_SPEC_MAX; ++i) {
+    if (i < g.n_step && steps == i) {
+      if (i > 0) info = guessed ? sp.info[i] : g.rec_info[p];
+      rew[i] = info.reward;
+      dn[i] = (info.action_done >> 31) & 1;
+      link = info.link;
+      steps = i + 1;
+      if (i + 1 < g.n_step) {
+        if (link < 0 || link >= g.N) { ok = false; steps = -steps; }     // window not complete: stop here
+        else {
+          p = link;
+          guessed = guessed && (i + 1 < K3_SPEC_MAX) && p == sp.pos[i + 1 < K3_SPEC_MAX ? i + 1 : 0];
+        }
+      }
+    }
+  }
+  if (steps < 0) steps = -steps;
+  double r = 0.0;
+  int d_any = 0;
+#pragma unroll
+  for (int i = K3_SPEC_MAX - 1; i >= 0; --i) {
+    if (i < steps) {
+      d_any |= dn[i];
+      r = __dadd_rn(__dmul_rn(__dmul_rn(r, g.gamma), (double)(1 - dn[i])), rew[i]);
+    }
+  }
+  if (g.action_out) g.action_out[b] = ok ? (int64_t)action : -1;
+  if (g.reward64_out) g.reward64_out[b] = r;
+  if (g.reward32_out) g.reward32_out[b] = (float)r;          // .float() in Trainer.step (trainer.py:88-90)
+  if (g.done8_out) g.done8_out[b] = (uint8_t)d_any;
+  if (g.done32_out) g.done32_out[b] = (float)d_any;
+  if (g.boot_out) g.boot_out[b] = ok ? (int64_t)link : -1;
+  next_slots = (guessed && ok) ? sp.next_slots : reinterpret_cast<const int4*>(g.rec_slots + (size_t)p * A0_SLOTS)[1];
   return p;
 }
 
@@ -361,6 +439,8 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   if (!ok) p0 = 0;
   const int4 sa = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
   const A0RecInfo info0 = g.rec_info[p0];
+  A0Spec sp;
+  a0_spec_fetch(g, p0, sp);              // the guessed rest of the window, same round trip as the first record
 #pragma unroll
   for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
   a0_fence_barrier_init();
@@ -380,8 +460,8 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   for (int u = 0; u < K3_RING; ++u)
     if (u < U0) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
   // the n-step walk and the next stack, while those loads are in flight
-  const int64_t pl = a0_walk_window(g, b, p0, info0, ok);
-  const int4 sc = reinterpret_cast<const int4*>(g.rec_slots + (size_t)pl * A0_SLOTS)[1];
+  int4 sc;
+  a0_walk_window_spec(g, b, p0, info0, sp, ok, sc);
   {
     int32_t s4[A0_STACK] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
@@ -615,6 +695,8 @@ a0_k3_gather_f32(const A0GatherArgs g, float* __restrict__ obs_out, float* __res
     if (!ok) p0 = 0;
     const int4 sa = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
     const A0RecInfo info0 = g.rec_info[p0];
+    A0Spec sp;
+    a0_spec_fetch(g, p0, sp);
 #pragma unroll
     for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
     a0_fence_barrier_init();
@@ -633,8 +715,8 @@ a0_k3_gather_f32(const A0GatherArgs g, float* __restrict__ obs_out, float* __res
 #pragma unroll
     for (int u = 0; u < K3_RING; ++u)
       if (u < U0) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
-    const int64_t pl = a0_walk_window(g, b, p0, info0, ok);
-    const int4 sc = reinterpret_cast<const int4*>(g.rec_slots + (size_t)pl * A0_SLOTS)[1];
+    int4 sc;
+    a0_walk_window_spec(g, b, p0, info0, sp, ok, sc);
     {
       int32_t s4[A0_STACK] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
@@ -702,6 +784,7 @@ extern "C" int a0_rb_gather_f32(a0_replay_t* h, const int64_t* idx, int32_t coun
   A0GatherArgs g;
   g.frames = h->frames; g.rec_slots = h->rec_slots; g.rec_info = h->rec_info; g.idx = idx;
   g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
+  g.stride_hint = (h->stride_hint > 0 && h->stride_hint < h->N) ? (int32_t)h->stride_hint : 0;
   g.frames_out = nullptr; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
   const size_t smem = (size_t)K3_RING * h->F;
@@ -731,6 +814,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   A0GatherArgs g;
   g.frames = h->frames; g.rec_slots = h->rec_slots; g.rec_info = h->rec_info; g.idx = idx;
   g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
+  g.stride_hint = (h->stride_hint > 0 && h->stride_hint < h->N) ? (int32_t)h->stride_hint : 0;
   g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
   if (variant == 3) {
