@@ -109,6 +109,57 @@ def test_ragged_and_empty_calls():
     assert lib.a0_pt_sample(rp.h, None, 0, 8, 1.0, 0.4, 0.0, 0, None, None, None, None) == 0
 
 
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_speculative_window_fetch_with_wrong_and_right_stride_guesses(n):
+    """K3 guesses the successor of record p as p + stride (stride measured at ingest) and fetches the
+    whole n-step window in one round trip; the stored links decide.  Lockstep steps (guess right),
+    steps where random streams sit out (guess wrong for their neighbours), wrap-around of the record
+    ring, then lockstep again so the hint is armed when the gather runs: every sampleable record must
+    still return its own stream's window."""
+    E, T = 5, 70
+    obs, n_new, act, rew, done = _stream(E, T, (84, 84), seed=40 + n)
+    rng = np.random.RandomState(n)
+    rp = _replay(160, n, E, frame_capacity=900, age_limit=64)
+    rp.reset_streams(np.arange(E), obs[0])
+    hist = {e: [] for e in range(E)}          # per stream: ring positions of its records, in step order
+    owner = {}                                # ring position -> (stream, index into hist[stream]) of its newest record
+    step_of = np.zeros(E, dtype=np.int64)
+    q = 0
+    for rnd in range(T + 40):
+        lockstep = rnd < 10 or rnd % 3 == 0 or step_of.min() >= T - 12
+        es = np.arange(E) if lockstep else np.flatnonzero(rng.rand(E) < 0.6)
+        es = es[step_of[es] < T]
+        if len(es) == 0:
+            continue
+        ks = step_of[es]
+        new = [obs[k + 1][e, 4 - n_new[k][e]:] for e, k in zip(es, ks) if n_new[k][e]]
+        new = np.concatenate(new) if new else np.zeros((0, 84, 84), np.uint8)
+        rp.append_steps(es, [n_new[k][e] for e, k in zip(es, ks)], new, [act[k][e] for e, k in zip(es, ks)],
+                        [rew[k][e] for e, k in zip(es, ks)], [done[k][e] for e, k in zip(es, ks)])
+        for e in es:
+            owner[q % rp.size] = (e, len(hist[e]))
+            hist[e].append(q % rp.size)        # record j of stream e is its step j
+            q += 1
+        step_of[es] += 1
+    assert q == E * T > rp.size                                  # everything appended; the record ring wrapped
+    live = np.flatnonzero(_np(rp.priority.leaves()) > 0)
+    assert len(live) == rp.top and rp.top > 40
+    fr_ref, a_ref, r_ref, d_ref = OR.pack_nstep(obs, act, rew, done, n, 0.99)
+    for variant in (0, 1):
+        rp.gather_variant = variant
+        b = rp.gather(torch.as_tensor(live, device="cuda"))
+        fr, rw, dn, ac, boot = _np(b.frames), _np(b.rewards), _np(b.terminals), _np(b.actions), _np(b.boot_indices)
+        for i, p in enumerate(live):
+            e, k0 = owner[int(p)]
+            ref = (k0 + n - 1) * E + e
+            assert np.array_equal(fr[i], fr_ref[ref]) and rw[i].view(np.int64) == r_ref[ref].view(np.int64)
+            assert dn[i] == d_ref[ref] and ac[i] == a_ref[ref]
+            assert boot[i] == (hist[e][k0 + n] if k0 + n < len(hist[e]) else -1)
+    bf = rp.gather(torch.as_tensor(live, device="cuda"), normalized=2)
+    assert np.array_equal(_np(bf.obs).astype(np.uint8).reshape(len(live), -1), fr[:, :4 * 84 * 84])
+    assert np.array_equal(_np(bf.rewards).view(np.int64), rw.view(np.int64))
+
+
 def test_argument_errors_carry_messages():
     lib = _lib.load()
     h = C.c_void_p()
