@@ -87,6 +87,50 @@ class ActorPolicy:
         return r[:E].copy(), float(r[E:].view(np.float32)[0])
 
 
+class ShardActor:
+    """``Actor.sample`` (agent0/deepq/agent.py:44-90) with the shard as the sink: the env loop, the done
+    rule ``(terminal | life_loss) & ~truncated`` (agent.py:57-62) and the statistics are the
+    reference's; what changes is where a transition goes.  The reference keeps an n-step tracker,
+    concatenates the two 4-frame stacks and lz4-compresses 56 448 bytes per transition (agent.py:64-81);
+    here each 1-step transition is appended to the HBM ring as it happens (only its new frames cross
+    PCIe) and K3 folds the n steps at gather time.  ``envs`` is the vector env of
+    ``make_atari`` (reset() -> (obs, info); step(a) -> (obs, reward, terminal, truncated, info))."""
+
+    def __init__(self, cfg, envs, policy, replay):
+        assert replay.n_gather == int(cfg.learner.n_step_q), "construct the ReplayDataset with native_nstep=True"
+        self.cfg, self.envs, self.policy, self.replay = cfg, envs, policy, replay
+        self.obs, _ = envs.reset()
+        self.steps = 0
+
+    def reset(self):
+        self.obs, _ = self.envs.reset()
+
+    def sample(self, epsilon):
+        """Runs ``cfg.actor.sample_steps`` vector steps.  Returns (transitions appended, episode returns,
+        per-step mean max-q), i.e. the reference's (data, rs, qs) with the data already in the shard."""
+        cfg = self.cfg
+        rs, qs, count = [], [], 0
+        for _ in range(cfg.actor.sample_steps):
+            if cfg.learner.noisy_net and self.steps % cfg.learner.reset_noise_freq == 0:
+                self.policy.model.reset_noise()
+            action, qt_max = self.policy.act(self.obs, epsilon)
+            obs_next, reward, terminal, truncated, info = self.envs.step(action)
+            self.steps += 1
+            done = np.logical_or(terminal, info["life_loss"]) if "life_loss" in info else terminal
+            done = np.logical_and(done, np.logical_not(truncated))
+            self.replay.append_vector_step(np.asarray(self.obs), action, reward, done, np.asarray(obs_next))
+            count += len(action)
+            self.obs = obs_next
+            qs.append(qt_max)
+            if "final_info" in info:
+                for stat in info["final_info"][info["_final_info"]]:
+                    rs.append(stat["episode"]["r"][0])
+        return count, rs, qs
+
+    def close(self):
+        self.envs.close()
+
+
 def flat_state(model):
     """Parameters and buffers of ``model`` in state_dict order (what launch.py ships to the actors)."""
     return [t for t in model.state_dict().values() if torch.is_tensor(t)]

@@ -529,29 +529,40 @@ constexpr int K5_WARPS = 4;
 __global__ void __launch_bounds__(K5_WARPS * 32)
 a0_k5_act(const float* __restrict__ q, int32_t E, int32_t A, double epsilon, const double* __restrict__ u,
           const int64_t* __restrict__ action_random, int64_t* __restrict__ action_out, float* __restrict__ qmax_out,
-          float* __restrict__ qmax_sum, unsigned int* __restrict__ ticket, float* __restrict__ qmax_mean) {
+          unsigned int* __restrict__ ticket, float* __restrict__ qmax_mean) {
   __shared__ bool is_last;
+  __shared__ float red[K5_WARPS];
   A0_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int e = blockIdx.x * K5_WARPS + (threadIdx.x >> 5);
   if (e < E) {
     const float v = lane < A ? q[(size_t)e * A + lane] : -INFINITY;
     const int arg = a0_warp_argmax(v, lane);
-    const float mx = __shfl_sync(0xffffffffu, v, arg);
     if (lane == 0) {
       action_out[e] = (u[e] > epsilon) ? (int64_t)arg : action_random[e];
-      if (qmax_out) qmax_out[e] = mx;
-      atomicAdd(qmax_sum, mx);
+      if (qmax_out) qmax_out[e] = q[(size_t)e * A + arg];
     }
   }
-  // the last CTA turns the sum into the mean and re-arms the scratch for the next launch
-  __threadfence();
+  // The last CTA to finish computes mean_e max_a q[e,a] in a fixed order (thread-strided partial sums,
+  // shuffle tree, warps in order), so the result does not depend on scheduling; it then re-arms the ticket.
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
-    *qmax_mean = __fdiv_rn(atomicExch(qmax_sum, 0.0f), (float)E);
+  if (!is_last) return;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < E; i += K5_WARPS * 32) {
+    float m = -INFINITY;
+    for (int a2 = 0; a2 < A; ++a2) m = fmaxf(m, q[(size_t)i * A + a2]);
+    s += m;
+  }
+  s = a0_warp_sum(s);
+  if (lane == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < K5_WARPS; ++w) t += red[w];
+    *qmax_mean = __fdiv_rn(t, (float)E);
     *ticket = 0u;
   }
 }
@@ -564,7 +575,7 @@ extern "C" int a0_act_epsilon_greedy(const float* q, int32_t E, int32_t A, doubl
   if (E == 0) return A0_OK;
   A0_REQUIRE(q && u && action_random && action_out && scratch && qmax_mean, "a0_act_epsilon_greedy: NULL argument");
   A0_LAUNCH(a0_k5_act, (unsigned)((E + K5_WARPS - 1) / K5_WARPS), K5_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4, q, E, A, epsilon,
-            u, action_random, action_out, qmax_out, scratch, reinterpret_cast<unsigned int*>(scratch) + 1, qmax_mean);
+            u, action_random, action_out, qmax_out, reinterpret_cast<unsigned int*>(scratch), qmax_mean);
   return A0_OK;
 }
 

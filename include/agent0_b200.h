@@ -256,7 +256,8 @@ int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const float* q, 
  *   qmax_out[e] = max_a q[e,a] (optional), *qmax_mean = mean_e qmax (qt_max.mean()).
  * q f32[E,A] = model.qval(obs); u f64[E] and action_random i64[E] are the caller's draws (numpy's
  * generator in the reference: randint first, then rand).  scratch: 8 bytes of device memory, zero
- * before the first call (the kernel re-arms it).
+ * before the first call (the kernel re-arms it).  The mean is summed in a fixed order: the same
+ * inputs give the same bits on every launch and every GPU.
  * a0_u8_to_f32 is Actor.act's input conversion (agent.py:27), count a multiple of 16 bytes,
  * norm_mode as a0_rb_gather_f32.                                                                  */
 int a0_act_epsilon_greedy(const float* q /* dev */, int32_t E, int32_t A, double epsilon,

@@ -94,3 +94,60 @@ def test_u8_to_f32_all_modes_and_errors():
     assert lib.a0_u8_to_f32(x.data_ptr(), out.data_ptr(), 16, 5, _lib.stream_ptr()) == -1
     assert lib.a0_act_epsilon_greedy(out.data_ptr(), 4, 64, 0.1, None, None, None, None, None, None, _lib.stream_ptr()) == -1
     assert lib.a0_u8_to_f32(None, None, 0, 0, _lib.stream_ptr()) == 0
+
+
+class _ScriptedVecEnv:
+    """The recorded stream of tests/golden/replay_n*.npz behind the vector-env contract (the same stand-in
+    tests/golden/make_golden.py puts behind make_atari for the reference Actor)."""
+
+    def __init__(self, g):
+        self.g, self.k = g, 0
+
+    def reset(self):
+        return self.g["stream_obs"][0].copy(), {}
+
+    def step(self, action):
+        k = self.k
+        assert np.array_equal(action, self.g["stream_action"][k])
+        self.k += 1
+        info = {"life_loss": self.g["stream_life_loss"][k]}
+        return (self.g["stream_obs"][k + 1].copy(), self.g["stream_reward"][k].copy(), self.g["stream_terminal"][k].copy(),
+                self.g["stream_truncated"][k].copy(), info)
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_shard_actor_fills_the_ring_like_the_reference_actor_fills_its_deque(golden, n):
+    """ShardActor.sample over the recorded env stream (scripted actions, as the fixture's reference run):
+    gathering the shard must give the reference Actor.sample's n-step entries bit for bit."""
+    from agent0_b200.actor import ShardActor
+    from agent0_b200.replay import ReplayDataset
+    g = golden(f"replay_n{n}")
+    E, T = int(g["num_envs"]), int(g["steps"])
+    cfg = make_config("dqn", per=True, n_step=n, batch_size=8, replay_size=256, num_envs=E)
+    cfg.actor.sample_steps = T
+    rp = ReplayDataset(cfg, native_nstep=True)
+
+    class _Script:
+        model = None
+
+        def __init__(self):
+            self.it = iter(g["stream_action"])
+
+        def act(self, obs, eps):
+            return next(self.it), 0.5
+
+    actor = ShardActor(cfg, _ScriptedVecEnv(g), _Script(), rp)
+    count, rs, qs = actor.sample(1.0)
+    assert count == T * E and len(qs) == T and rs == []
+    assert rp.top == (T - n + 1) * E
+    ks, es = np.meshgrid(np.arange(n - 1, T), np.arange(E), indexing="ij")
+    ref_i = (ks * E + es).reshape(-1)
+    pos = torch.as_tensor(((ks - n + 1) * E + es).reshape(-1), device="cuda")
+    b = rp.gather(pos)
+    assert np.array_equal(b.frames.cpu().numpy(), g["entry_frames"][ref_i])
+    assert np.array_equal(b.actions.cpu().numpy(), g["entry_action"][ref_i])
+    assert np.array_equal(b.rewards.cpu().numpy().view(np.int64), g["entry_reward"][ref_i].view(np.int64))
+    assert np.array_equal(b.terminals.cpu().numpy(), g["entry_done"][ref_i])

@@ -54,8 +54,19 @@ def _worker(rank, port, algo, B, out):
         for it in range(3):
             res = learner.train(_data(10 * it + rank, B, learner.device))
             losses.append(res["q_loss"].cpu().numpy())
-        out[rank] = dict(params=torch.cat([p.detach().reshape(-1) for p in learner.model.parameters()]).cpu().numpy(),
-                         losses=np.stack(losses))
+        params = torch.cat([p.detach().reshape(-1) for p in learner.model.parameters()]).cpu().numpy()
+        # weight hand-off to an actor rank over NCCL (launch.py:33-36 ships a pickled state_dict per call):
+        # rank 1 plays an actor whose copy of the net is stale
+        from agent0_b200.actor import ActorPolicy, broadcast_model
+        if rank == 1:
+            with torch.no_grad():
+                for p in learner.model.parameters():
+                    p.add_(0.25)
+        sent = broadcast_model(learner.model, src=0, process_group=dist.group.WORLD)
+        after = torch.cat([p.detach().reshape(-1) for p in learner.model.parameters()]).cpu().numpy()
+        obs = np.random.RandomState(5).randint(0, 256, (16, 4, 84, 84)).astype(np.uint8)
+        act, qmean = ActorPolicy(learner.cfg, learner.model, rng=np.random.RandomState(1)).act(obs, 0.05)
+        out[rank] = dict(params=params, losses=np.stack(losses), after=after, sent=sent, act=act, qmean=qmean)
     finally:
         dist.destroy_process_group()
 
@@ -72,6 +83,9 @@ def test_two_gpu_learner_equals_one_learner_at_double_batch(algo):
     mp.spawn(_worker, args=(_free_port(), algo, B, out), nprocs=2, join=True)
     out = dict(out)
     assert np.array_equal(out[0]["params"], out[1]["params"])                 # replicas stay identical
+    assert np.array_equal(out[1]["after"], out[0]["params"]) and np.array_equal(out[0]["after"], out[0]["params"])
+    assert out[0]["sent"] == out[1]["sent"] >= out[0]["params"].size * 4      # one flat broadcast carried the whole net
+    assert np.array_equal(out[0]["act"], out[1]["act"]) and out[0]["qmean"] == out[1]["qmean"]
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(3)
