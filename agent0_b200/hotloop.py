@@ -1,0 +1,179 @@
+"""The inner loop of the reference's ``Trainer.step`` (agent0/deepq/trainer.py:82-104) as a pre-bound,
+CUDA-graph-capturable sequence of C-ABI launches, for callers that supply the network outputs
+themselves (a training loop owns the CNN; bench.py pre-generates them because the BASELINE metric
+excludes the CNN).
+
+Per ``step()``: draw L = learner_steps batches of B transitions (K2a, one launch), gather them (K3,
+one launch: stack reconstruction + n-step return), run the fused target/loss kernel once per batch
+(K4, L launches: in training every batch's outputs depend on the previous optimizer step, so they
+stay separate launches), write the new priorities (K2b, one launch).  All buffers are allocated
+once; every launch is a single ctypes call with pre-built argument blocks, so the host cost per
+step is ~25 ctypes calls -- or one ``graph.replay()`` after ``capture()``.  ``sample(dynamic=True)``
+semantics: top/beta are read from the device values published by ``ReplayDataset.push_dynamic``,
+so a captured graph keeps following the shard as it grows and beta anneals.
+
+The general-purpose wrappers (``ReplayDataset.sample``, ``agent0_b200.losses``) allocate their
+outputs and validate their inputs on every call; this class is the same work without that.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ALGOS = ("dqn", "mdqn", "c51", "qr", "iqn", "fqf")
+
+
+class ReplayTargetLoop:
+    def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, n_step=None, double_q=True,
+                 per=None, variant=0, discount=None, alpha=0.5, eps=0.01, c51=(51, -10.0, 10.0), mdqn=(0.03, -1.0),
+                 frames=None):
+        """replay: ReplayDataset (native_nstep=True when n_step > 1).  outputs: dict of STATIC f32 device
+        tensors holding the network outputs of all L*B sampled transitions, batch k in rows
+        [k*B, (k+1)*B): ``online``, ``tgt_next`` (+ ``qsel`` [L*B,A] under double_q / for iqn, fqf;
+        ``tgt_cur`` for mdqn; ``atoms`` [M] for c51; ``taus`` for iqn; ``taus``, ``taus_hat``, ``q_bar`` for
+        fqf), shaped as the learners produce them (agent0_b200.losses).  frames: optional u8
+        [L*B, 8*F] output buffer for the gather (allocated if None)."""
+        assert algo in ALGOS, algo
+        self.lib = _lib.load()
+        self.rp, self.algo, self.B, self.L, self.A = replay, algo, int(batch_size), int(learner_steps), int(action_dim)
+        self.total = T = self.L * self.B
+        self.dev = dev = replay.device
+        self.variant = int(variant)
+        self.n = int(n_step if n_step is not None else replay.n_gather)
+        self.gamma = float(discount if discount is not None else replay.gamma)
+        self.gamma_n = float(np.float32(self.gamma ** self.n))
+        self.per = replay.prioritize if per is None else bool(per)
+        self.double_q = bool(double_q)
+        self.alpha, self.eps = float(alpha), float(eps)
+        self.c51, self.mdqn = c51, mdqn
+        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        self.u = e(T)
+        self.idx = e(T, dt=torch.int64); self.prio = e(T); self.w = e(T)
+        self.frames = frames if frames is not None else e(T, 8 * replay.F, dt=torch.uint8)
+        self.act = e(T, dt=torch.int64); self.r64 = e(T, dt=torch.float64); self.r32 = e(T)
+        self.d8 = e(T, dt=torch.uint8); self.d32 = e(T); self.boot = e(T, dt=torch.int64)
+        self.loss = e(T); self.newp = e(T)
+        self.o = outputs
+        self.grad = torch.empty_like(self.o["online"])
+        self.frac = e(T) if algo == "fqf" else None
+        self.gtau = e(T, self.o["taus"].shape[1]) if algo == "fqf" else None
+        self.launches_per_step = 2 + self.L + (1 if self.per else 0)
+        self._k4 = None
+        self._k4_all = None
+        self.graph = None
+
+    # ------------------------------------------------------------------ single launches
+    def _st(self):
+        return _lib.stream_ptr(self.dev)      # evaluated at call time: the capture stream inside a graph
+
+    def sample(self):
+        """K2a: L stratified batches + IS weights (top/beta from the device: push_dynamic first)."""
+        rp = self.rp
+        _lib.check(self.lib.a0_pt_sample(rp.h, self.u.data_ptr(), self.total, self.B, -1.0, float(rp.beta), 0.0,
+                                         0 if self.per else 1, self.idx.data_ptr(), self.prio.data_ptr(),
+                                         self.w.data_ptr(), self._st()), "a0_pt_sample")
+
+    def gather(self, idx_ptr=None, out_ptr=None, count=None, variant=None):
+        """K3: the sampled transitions' stacks + n-step scalars into the static buffers."""
+        _lib.check(self.lib.a0_rb_gather(self.rp.h, idx_ptr or self.idx.data_ptr(), count or self.total, self.n, self.gamma,
+                                         out_ptr or self.frames.data_ptr(), self.act.data_ptr(), self.r64.data_ptr(),
+                                         self.r32.data_ptr(), self.d8.data_ptr(), self.d32.data_ptr(), self.boot.data_ptr(),
+                                         self.variant if variant is None else variant, self._st()), "a0_rb_gather")
+
+    def _common(self, lo, count):
+        s = slice(lo, lo + count)
+        p = lambda t: t[s].data_ptr()
+        return _lib.LossCommon(B=count, A=self.A, action=p(self.act), reward=p(self.r32), done=p(self.d32), weight=p(self.w),
+                               gamma_n=self.gamma_n, alpha=self.alpha, eps=self.eps, loss=p(self.loss), prio=p(self.newp),
+                               max_p=self.rp.max_p_tensor.data_ptr()), s
+
+    def _bind(self, lo, count):
+        """(function, argument tuple) of the K4 launch over rows [lo, lo+count): the a0_loss_common_t block
+        and the sliced device pointers are built once, so a launch is a single ctypes call."""
+        lib, o, algo = self.lib, self.o, self.algo
+        c, s = self._common(lo, count)
+        p = lambda t: t[s].data_ptr()
+        qsel = p(o["qsel"]) if (self.double_q or algo in ("iqn", "fqf")) and algo != "mdqn" else None
+        if algo == "dqn":
+            a = (lib.a0_loss_dqn, (C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, p(self.grad)))
+        elif algo == "mdqn":
+            a = (lib.a0_loss_mdqn, (C.byref(c), p(o["online"]), p(o["tgt_next"]), p(o["tgt_cur"]), self.mdqn[0], self.mdqn[1],
+                                    p(self.grad)))
+        elif algo == "c51":
+            M, vmin, vmax = self.c51
+            a = (lib.a0_loss_c51, (C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, o["atoms"].data_ptr(), M, vmin, vmax,
+                                   p(self.grad), None))
+        elif algo == "qr":
+            N = o["online"].shape[2]
+            a = (lib.a0_loss_quantile, (C.byref(c), 0, p(o["online"]), p(o["tgt_next"]), None, qsel, o["tgt_next"].shape[2], N,
+                                        p(self.grad), None, None, None, None))
+        elif algo == "iqn":
+            a = (lib.a0_loss_quantile, (C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus"]), qsel,
+                                        o["tgt_next"].shape[1], o["online"].shape[1], p(self.grad), None, None, None, None))
+        else:
+            F_ = o["online"].shape[1]
+            a = (lib.a0_loss_quantile, (C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus_hat"]), qsel, F_, F_,
+                                        p(self.grad), p(o["q_bar"]), p(o["taus"]), p(self.frac), p(self.gtau)))
+        return c, a
+
+    def target_loss(self, k):
+        """K4 for batch k: per-sample loss, gradient w.r.t. the online output, new priorities."""
+        if self._k4 is None:
+            self._k4 = [self._bind(k_ * self.B, self.B) for k_ in range(self.L)]
+        fn, args = self._k4[k][1]
+        rc = fn(*args, self._st())
+        if rc:
+            _lib.check(rc, "a0_loss_" + self.algo)
+
+    def target_loss_all(self):
+        """All L batches in ONE K4 launch.  Valid only when every batch's network outputs exist before
+        the first update, which a training loop cannot offer (evaluation, or measuring how much of a
+        batch-32 step is launch latency)."""
+        if self._k4_all is None:
+            self._k4_all = self._bind(0, self.total)
+        fn, args = self._k4_all[1]
+        rc = fn(*args, self._st())
+        if rc:
+            _lib.check(rc, "a0_loss_" + self.algo)
+
+    def update(self):
+        """K2b: priority[idx] = (loss+eps)^alpha for all L batches, max_p (replay.py:55-59)."""
+        if self.per:
+            _lib.check(self.lib.a0_pt_update(self.rp.h, self.idx.data_ptr(), self.loss.data_ptr(), self.total, self.alpha,
+                                             self.eps, self._st()), "a0_pt_update")
+
+    # ------------------------------------------------------------------ whole steps
+    def step(self, fused_k4=False):
+        self.u.uniform_()
+        self.sample()
+        self.gather()
+        if fused_k4:
+            self.target_loss_all()
+        else:
+            for k in range(self.L):
+                self.target_loss(k)
+        self.update()
+
+    def capture(self, warm=3, fused_k4=False):
+        """Warm up, then capture one step into a CUDA graph (returned; also kept as ``self.graph``)."""
+        self.rp.push_dynamic()
+        for _ in range(warm):
+            self.step(fused_k4)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(fused_k4)
+        self.graph = g
+        return g
+
+    def run(self):
+        """One step: publishes top/beta, then replays the captured graph (or issues the launches)."""
+        self.rp.push_dynamic()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.step()

@@ -141,161 +141,47 @@ def bytes_per_transition(n):
     return (4 + min(n, 4) + 8) * F_BYTES
 
 
-class HotPath:
-    """Pre-allocated buffers + direct C-ABI launches of one Trainer.step-shaped pass."""
+def make_hotpath(rp, wl, L, A, torch, variant=0):
+    from agent0_b200.hotloop import ReplayTargetLoop
 
-    def __init__(self, rp, wl, L, A, torch, variant=0):
-        from agent0_b200 import _lib
-        self.torch, self._lib, self.lib = torch, _lib, _lib.load()
-        self.rp, self.wl, self.L, self.B, self.A = rp, wl, L, wl["B"], A
-        self.total = T = L * wl["B"]
-        dev = rp.device
-        self.dev = dev
-        self.variant = variant
-        self.n = wl["n"]
-        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
-        self.u = e(T)
-        self.idx = e(T, dt=torch.int64); self.prio = e(T); self.w = e(T)
-        # timed gathers rotate over enough output buffers (>= ~1 GB) that stores are not absorbed by L2
-        self.n_out = min(INNER, max(1, int(1e9 // (T * 8 * F_BYTES))))
-        self.frames_pool = e(self.n_out, T, 8 * F_BYTES, dt=torch.uint8)
-        self.frames = self.frames_pool[0]
-        self.act = e(T, dt=torch.int64); self.r64 = e(T, dt=torch.float64); self.r32 = e(T)
-        self.d8 = e(T, dt=torch.uint8); self.d32 = e(T); self.boot = e(T, dt=torch.int64)
-        self.loss = e(T); self.newp = e(T)
-        self.o = net_outputs(wl["algo"], T, A, torch, dev)
-        self.grad = torch.empty_like(self.o["online"])
-        self.frac = e(T); self.gtau = e(T, 33)
-        self.idx_pool = None
-        self.gamma_n = float(np.float32(0.99 ** self.n))
-        self.launches_per_step = 3 + L
-        self._k4 = None
+    class HotPath(ReplayTargetLoop):
+        """agent0_b200.hotloop.ReplayTargetLoop (the package's pre-bound form of the Trainer.step inner
+        loop) plus what only the benchmark needs: synthetic network outputs, and pools of pre-drawn
+        index sets and rotating output buffers so that back-to-back timed gathers neither re-read
+        frames nor have their stores absorbed by L2."""
 
-    def _common(self, k):
-        B, A = self.B, self.A
-        s = slice(k * B, (k + 1) * B)
-        p = lambda t: t[s].data_ptr()
-        return self._lib.LossCommon(B=B, A=A, action=p(self.act), reward=p(self.r32), done=p(self.d32), weight=p(self.w),
-                                    gamma_n=self.gamma_n, alpha=0.5, eps=0.01, loss=p(self.loss), prio=p(self.newp),
-                                    max_p=self.rp.max_p_tensor.data_ptr()), s
+        def __init__(self):
+            T = L * wl["B"]
+            # timed gathers rotate over enough output buffers (>= ~1 GB) that stores are not absorbed by L2
+            self.n_out = min(INNER, max(1, int(1e9 // (T * 8 * F_BYTES))))
+            self.frames_pool = torch.empty(self.n_out, T, 8 * F_BYTES, dtype=torch.uint8, device=rp.device)
+            super().__init__(rp, wl["algo"], wl["B"], L, A, net_outputs(wl["algo"], T, A, torch, rp.device), n_step=wl["n"],
+                             double_q=wl["double"], per=wl["per"], variant=variant, discount=0.99, frames=self.frames_pool[0])
+            self.wl, self.idx_pool = wl, None
 
-    def sample(self, st=None):
-        rp = self.rp
-        st = self._st()
-        # top < 0: the kernel reads top/beta from device memory (ReplayDataset.push_dynamic), so a captured
-        # graph keeps following the shard while it grows
-        self._lib.check(self.lib.a0_pt_sample(rp.h, self.u.data_ptr(), self.total, self.B, -1.0, float(rp.beta), 0.0,
-                                              0 if self.wl["per"] else 1, self.idx.data_ptr(), self.prio.data_ptr(),
-                                              self.w.data_ptr(), st), "a0_pt_sample")
+        def draw_pool(self):
+            """INNER independent index sets, so that back-to-back timed gathers never re-read frames."""
+            self.idx_pool = torch.empty(INNER, self.total, dtype=torch.int64, device=self.dev)
+            for i in range(INNER):
+                self.u.uniform_(); self.sample()
+                self.idx_pool[i].copy_(self.idx)
 
-    def _st(self):
-        return self._lib.stream_ptr(self.dev)      # evaluated at call time: the capture stream inside a graph
+        def gather(self, count=None, variant=None, pool=None):
+            if pool is None:
+                return super().gather(count=count, variant=variant)
+            return super().gather(self.idx_pool[pool % INNER].data_ptr(), self.frames_pool[pool % self.n_out].data_ptr(),
+                                  count, variant)
 
-    def draw_pool(self, st=None):
-        """INNER independent index sets, so that back-to-back timed gathers never re-read frames."""
-        torch = self.torch
-        self.idx_pool = torch.empty(INNER, self.total, dtype=torch.int64, device=self.dev)
-        for i in range(INNER):
-            self.u.uniform_(); self.sample(st)
-            self.idx_pool[i].copy_(self.idx)
+        loss_k = ReplayTargetLoop.target_loss
 
-    def gather(self, st=None, count=None, variant=None, pool=None):
-        rp = self.rp
-        st = self._st()
-        idx_ptr = self.idx.data_ptr() if pool is None else self.idx_pool[pool % INNER].data_ptr()
-        out_ptr = self.frames.data_ptr() if pool is None else self.frames_pool[pool % self.n_out].data_ptr()
-        self._lib.check(self.lib.a0_rb_gather(rp.h, idx_ptr, count or self.total, self.n, 0.99, out_ptr,
-                                              self.act.data_ptr(), self.r64.data_ptr(), self.r32.data_ptr(), self.d8.data_ptr(),
-                                              self.d32.data_ptr(), self.boot.data_ptr(),
-                                              self.variant if variant is None else variant, st), "a0_rb_gather")
+        def step_fused_k4(self):
+            self.step(fused_k4=True)
 
-    def _bind_k4(self):
-        """One pre-bound C-ABI call per batch: the a0_loss_common_t blocks and the sliced device
-        pointers are built once, so a timed launch is a single ctypes call."""
-        lib, o, algo = self.lib, self.o, self.wl["algo"]
-        calls, self._k4_keep = [], []
-        for k in range(self.L):
-            c, s = self._common(k)
-            self._k4_keep.append(c)
-            p = lambda t: t[s].data_ptr()
-            qsel = p(o["qsel"]) if self.wl["double"] or algo in ("iqn", "fqf") else None
-            if algo == "dqn":
-                a = (lib.a0_loss_dqn, (C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, p(self.grad)))
-            elif algo == "mdqn":
-                a = (lib.a0_loss_mdqn, (C.byref(c), p(o["online"]), p(o["tgt_next"]), p(o["tgt_cur"]), 0.03, -1.0, p(self.grad)))
-            elif algo == "c51":
-                a = (lib.a0_loss_c51, (C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, o["atoms"].data_ptr(), 51, -10.0, 10.0,
-                                       p(self.grad), None))
-            elif algo == "qr":
-                a = (lib.a0_loss_quantile, (C.byref(c), 0, p(o["online"]), p(o["tgt_next"]), None, qsel, 200, 200, p(self.grad),
-                                            None, None, None, None))
-            elif algo == "iqn":
-                a = (lib.a0_loss_quantile, (C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus"]), qsel, 64, 64,
-                                            p(self.grad), None, None, None, None))
-            else:
-                a = (lib.a0_loss_quantile, (C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus_hat"]), qsel, 32, 32,
-                                            p(self.grad), p(o["q_bar"]), p(o["taus"]), p(self.frac), p(self.gtau)))
-            calls.append(a)
-        self._k4 = calls
+    return HotPath()
 
-    def loss_k(self, k, st=None):
-        if self._k4 is None:
-            self._bind_k4()
-        fn, args = self._k4[k]
-        rc = fn(*args, self._st())
-        if rc:
-            self._lib.check(rc, "a0_loss_" + self.wl["algo"])
 
-    def loss_all(self):
-        """All L batches in ONE K4 launch (B = L*batch).  Valid only when every batch's network
-        outputs exist before the first update, which a training loop cannot offer; reported as an
-        extra to show how much of the batch-32 step is launch latency."""
-        lib, o, algo, T = self.lib, self.o, self.wl["algo"], self.total
-        if getattr(self, "_k4_all", None) is None:
-            c = self._lib.LossCommon(B=T, A=self.A, action=self.act.data_ptr(), reward=self.r32.data_ptr(),
-                                     done=self.d32.data_ptr(), weight=self.w.data_ptr(), gamma_n=self.gamma_n, alpha=0.5,
-                                     eps=0.01, loss=self.loss.data_ptr(), prio=self.newp.data_ptr(),
-                                     max_p=self.rp.max_p_tensor.data_ptr())
-            self._k4_all = c
-        c = self._k4_all
-        p = lambda t: t.data_ptr()
-        qsel = p(o["qsel"]) if self.wl["double"] or algo in ("iqn", "fqf") else None
-        st = self._st()
-        if algo == "dqn":
-            rc = lib.a0_loss_dqn(C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, p(self.grad), st)
-        elif algo == "mdqn":
-            rc = lib.a0_loss_mdqn(C.byref(c), p(o["online"]), p(o["tgt_next"]), p(o["tgt_cur"]), 0.03, -1.0, p(self.grad), st)
-        elif algo == "c51":
-            rc = lib.a0_loss_c51(C.byref(c), p(o["online"]), p(o["tgt_next"]), qsel, p(o["atoms"]), 51, -10.0, 10.0, p(self.grad), None, st)
-        elif algo == "qr":
-            rc = lib.a0_loss_quantile(C.byref(c), 0, p(o["online"]), p(o["tgt_next"]), None, qsel, 200, 200, p(self.grad), None, None, None, None, st)
-        elif algo == "iqn":
-            rc = lib.a0_loss_quantile(C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus"]), qsel, 64, 64, p(self.grad), None, None, None, None, st)
-        else:
-            rc = lib.a0_loss_quantile(C.byref(c), 1, p(o["online"]), p(o["tgt_next"]), p(o["taus_hat"]), qsel, 32, 32, p(self.grad),
-                                      p(o["q_bar"]), p(o["taus"]), p(self.frac), p(self.gtau), st)
-        self._lib.check(rc, "a0_loss_" + algo)
-
-    def step_fused_k4(self):
-        self.u.uniform_()
-        self.sample()
-        self.gather()
-        self.loss_all()
-        self.update()
-
-    def update(self, st=None):
-        st = self._st()
-        if self.wl["per"]:
-            self._lib.check(self.lib.a0_pt_update(self.rp.h, self.idx.data_ptr(), self.loss.data_ptr(), self.total, 0.5, 0.01, st),
-                            "a0_pt_update")
-
-    def step(self):
-        self.u.uniform_()
-        self.sample()
-        self.gather()
-        for k in range(self.L):
-            self.loss_k(k)
-        self.update()
+def HotPath(rp, wl, L, A, torch, variant=0):
+    return make_hotpath(rp, wl, L, A, torch, variant)
 
 
 def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
@@ -597,7 +483,7 @@ def run_ours(args):
                        "fill_seconds": round(t_fill, 1)},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "C ABI (ctypes): ingest from pinned host buffers (H2D DMA on the shard's copy stream) + one CUDA-graph "
+                    "path": "agent0_b200 public API over the C ABI (ReplayDataset.append_steps + hotloop.ReplayTargetLoop): ingest from pinned host buffers (H2D DMA on the shard's copy stream) + one CUDA-graph "
                             "replay of the C-ABI launches per step; losses and indices copied back to double-buffered pinned host "
                             "memory, the host reads step s-1's result while step s runs (final drain inside the timed region)",
                     "sync_every_step_value": round(e2e_sync, 1),

@@ -1,0 +1,144 @@
+"""agent0_b200.hotloop.ReplayTargetLoop (the pre-bound, graph-capturable inner loop of Trainer.step,
+agent0/deepq/trainer.py:82-104) against the general-purpose API on the same draws: sampled indices,
+IS weights, gathered stacks, losses, gradients and the sum-tree after the priority write-back must be
+identical; the captured CUDA graph must replay to the same results as the eager launches."""
+import numpy as np
+import pytest
+import torch
+
+from agent0_b200.config import make_config
+from agent0_b200.synth import fill_shard_synthetic
+
+pytestmark = pytest.mark.gpu
+B, L, A = 16, 3, 4
+
+
+def _outputs(algo, T, seed=7):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g) * 3.0
+    o = {"qsel": rn(T, A)}
+    if algo in ("dqn", "mdqn"):
+        o.update(online=rn(T, A), tgt_next=rn(T, A), tgt_cur=rn(T, A))
+    elif algo == "c51":
+        o.update(online=rn(T, A, 51), tgt_next=rn(T, A, 51), atoms=torch.linspace(-10, 10, 51, device="cuda"))
+    elif algo == "qr":
+        o.update(online=rn(T, A, 200), tgt_next=rn(T, A, 200))
+    elif algo == "iqn":
+        o.update(online=rn(T, 64, A), tgt_next=rn(T, 64, A), taus=torch.rand(T, 64, device="cuda", generator=g))
+    else:
+        p = torch.softmax(torch.randn(T, 32, device="cuda", generator=g), -1)
+        taus = torch.cat((torch.zeros(T, 1, device="cuda"), torch.cumsum(p, -1)), -1).contiguous()
+        o.update(online=rn(T, 32, A), tgt_next=rn(T, 32, A), q_bar=rn(T, 31, A), taus=taus,
+                 taus_hat=((taus[:, :-1] + taus[:, 1:]) / 2).contiguous())
+    return o
+
+
+def _shard(algo, seed=3):
+    from agent0_b200.replay import ReplayDataset
+    cfg = make_config(algo, per=True, n_step=3, batch_size=B, replay_size=4096, double_q=True, dueling=True, num_envs=8,
+                      action_dim=A)
+    rp = ReplayDataset(cfg, native_nstep=True)
+    fill_shard_synthetic(rp, 4096, 8, seed)
+    # uneven priorities so that the draw is not uniform
+    ids = torch.arange(0, 4000, 7, device="cuda")
+    rp.update_priority(ids, torch.rand(len(ids), device="cuda", generator=torch.Generator("cuda").manual_seed(seed)) * 4)
+    return rp
+
+
+def _general_api(rp, algo, o, u):
+    from agent0_b200 import losses as LS
+    from agent0_b200.replay import split_batches
+    b = rp.sample(B, k_batches=L, u=u)
+    gam = float(np.float32(0.99 ** 3))
+    outs, grads = [], []
+    for k, bk in enumerate(split_batches(b, B)):
+        s = slice(k * B, (k + 1) * B)
+        cm = (bk.actions, bk.rewards_f32, bk.terminals_f32, bk.weights, gam)
+        kw = dict(max_p=rp.max_p_tensor)
+        if algo == "dqn":
+            r = LS.dqn_loss(o["online"][s], o["tgt_next"][s], *cm, qsel=o["qsel"][s], **kw)
+        elif algo == "mdqn":
+            r = LS.mdqn_loss(o["online"][s], o["tgt_next"][s], o["tgt_cur"][s], *cm, **kw)
+        elif algo == "c51":
+            r = LS.c51_loss(o["online"][s], o["tgt_next"][s], o["atoms"], *cm, -10.0, 10.0, qsel=o["qsel"][s], **kw)
+        elif algo == "qr":
+            r = LS.qr_loss(o["online"][s], o["tgt_next"][s], *cm, qsel=o["qsel"][s], **kw)
+        elif algo == "iqn":
+            r = LS.iqn_loss(o["online"][s], o["taus"][s], o["tgt_next"][s], o["qsel"][s], *cm, **kw)
+        else:
+            r = LS.fqf_loss(o["online"][s], o["taus"][s], o["taus_hat"][s], o["tgt_next"][s], o["q_bar"][s], o["qsel"][s], *cm, **kw)
+        outs.append(r.loss); grads.append(r.grad)
+    loss = torch.cat(outs)
+    rp.update_priority(b.indices, loss)
+    return b, loss, torch.cat(grads)
+
+
+@pytest.mark.parametrize("algo", ["dqn", "mdqn", "c51", "qr", "iqn", "fqf"])
+def test_prebound_loop_equals_general_api_and_graph_replays_identically(algo):
+    from agent0_b200.hotloop import ReplayTargetLoop
+    T = B * L
+    o = _outputs(algo, T)
+    u = torch.rand(T, device="cuda", generator=torch.Generator("cuda").manual_seed(11))
+    rp_a, rp_b, rp_c = _shard(algo), _shard(algo), _shard(algo)
+    assert torch.equal(rp_a.tree, rp_b.tree)
+    batch, loss_ref, grad_ref = _general_api(rp_a, algo, o, u)
+
+    def run(rp, graph):
+        loop = ReplayTargetLoop(rp, algo, B, L, A, o, n_step=3, double_q=(algo != "mdqn"))
+        rp.push_dynamic()
+        if graph:
+            loop.idx.zero_()
+            loop.gather()                       # first-use function attributes are set outside the capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            loop.u.copy_(u)
+            # warm-up launches must not touch the tree: capture only records
+            with torch.cuda.graph(g):
+                loop.sample(); loop.gather()
+                for k in range(L):
+                    loop.target_loss(k)
+                loop.update()
+            loop.u.copy_(u)
+            g.replay()
+        else:
+            loop.u.copy_(u)
+            loop.sample(); loop.gather()
+            for k in range(L):
+                loop.target_loss(k)
+            loop.update()
+        torch.cuda.synchronize()
+        return loop
+
+    for rp, graph in ((rp_b, False), (rp_c, True)):
+        loop = run(rp, graph)
+        assert torch.equal(loop.idx, batch.indices) and torch.equal(loop.w, batch.weights)
+        assert torch.equal(loop.frames, batch.frames) and torch.equal(loop.r64, batch.rewards)
+        assert torch.equal(loop.act, batch.actions) and torch.equal(loop.d8.bool(), batch.terminals)
+        assert torch.equal(loop.loss, loss_ref) and torch.equal(loop.grad, grad_ref)
+        assert torch.equal(rp.tree, rp_a.tree) and float(rp.max_p_tensor) == float(rp_a.max_p_tensor)
+        assert loop.launches_per_step == L + 3
+
+
+def test_prebound_loop_step_capture_and_single_launch_k4():
+    """step()/capture()/run() on a growing shard, and the one-launch-for-all-batches K4 variant."""
+    from agent0_b200.hotloop import ReplayTargetLoop
+    T = B * L
+    o = _outputs("c51", T)
+    rp = _shard("c51")
+    loop = ReplayTargetLoop(rp, "c51", B, L, A, o, n_step=3)
+    loop.capture()
+    root0 = float(rp.tree[1])
+    for _ in range(3):
+        loop.run()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loop.loss).all() and int(loop.idx.max()) < rp.size and float(rp.tree[1]) != root0
+    tree = rp.tree.cpu().numpy()
+    for node in (1, 2, 3, rp.P // 2, rp.P - 1):
+        assert tree[node] == np.float32(tree[2 * node] + tree[2 * node + 1])
+    # all batches in one K4 launch == one launch per batch
+    loop.u.uniform_(); loop.sample(); loop.gather()
+    for k in range(L):
+        loop.target_loss(k)
+    per_batch = (loop.loss.clone(), loop.grad.clone())
+    loop.target_loss_all()
+    assert torch.equal(loop.loss, per_batch[0]) and torch.equal(loop.grad, per_batch[1])
