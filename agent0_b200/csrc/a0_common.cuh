@@ -41,7 +41,8 @@ struct a0_replay {
   int32_t* winner;       // [N] scratch for last-writer-wins, kept at -1 between calls
   int32_t* dirty;        // [P >> 12] chunk needs its sub-tree recomputed
   unsigned int* counter; // [A0_MAX_BATCHES] per-batch tickets of the sampler epilogue, [16] rebuild ticket,
-                         // [A0_MAX_BATCHES] per-batch max weight (float bits); all zero between launches
+                         // [A0_MAX_BATCHES] per-batch max weight (float bits); all zero between launches;
+                         // then the sampler's RNG words: CTA ticket and the 64-bit call counter
   A0Staging staging[2];
   int staging_turn;
   cudaStream_t copy_stream;   // lazily created; carries the ingest DMA under A0_INGEST_COPY_STREAM

@@ -20,17 +20,59 @@
 // ------------------------------------------------------------------------------------------------
 constexpr int K2A_WARPS = 8;
 
+// Philox4x32-10 (Salmon et al., SC'11; the generator behind curand and torch's CUDA RNG), first
+// output word.  The sampler's own uniforms: draw g of call c under seed s is
+// u = (philox(counter = {g, 0, c_lo, c_hi}, key = {s_lo, s_hi}).x >> 8) * 2^-24  in [0, 1)
+// (oracle/sumtree.py: philox_uniform), so a host without torch -- or a captured CUDA graph, which
+// cannot take fresh host randoms per replay -- draws reproducible batches with no extra launch.
+__device__ __forceinline__ uint32_t a0_philox_x0(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+struct A0Rng {
+  unsigned long long seed;
+  long long call;                  // >= 0: this call number; < 0: the device-resident counter, advanced by the launch
+  unsigned long long* call_dev;    // device call counter (8-byte aligned)
+  unsigned int* ticket;            // CTA arrivals of this launch (zero between launches)
+  float* u_out;                    // optional copy of the uniforms (tests)
+};
+
+// One arrival per finished unit (`units` in the launch: batches on the prioritized path, whose
+// last CTA reports for the whole batch -- 20 arrivals instead of 1280 same-address atomics at
+// 20 x 512 draws; CTAs otherwise).  The last arrival advances the call counter and re-arms the ticket.
+__device__ __forceinline__ void a0_rng_done(const A0Rng& rng, unsigned long long call, unsigned int units) {
+  __threadfence();
+  if (atomicAdd(rng.ticket, 1u) == units - 1u) {
+    *rng.call_dev = call + 1ull;
+    *rng.ticket = 0u;
+  }
+}
+
 __global__ void __launch_bounds__(K2A_WARPS * 32)
 a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
               int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
               int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
-              unsigned int* counter, float* bmax, const float* __restrict__ dyn) {
+              unsigned int* counter, float* bmax, const float* __restrict__ dyn, const A0Rng rng) {
   A0_PDL_PROLOGUE();
   if (dyn) {            // top / beta / sum_offset live on the device (a0_rb_set_dynamic): graph-replay safe
     top = __ldcg(dyn);
     beta = __ldcg(dyn + 1);
     sum_offset = __ldcg(dyn + 2);
   }
+  // Device-resident call counter (rng.call < 0): every warp reads it before anything else; it is
+  // advanced for the next launch / graph replay only after every CTA has reported in below
+  // (a0_rng_done), i.e. after every warp of the launch has read it.
+  const bool rng_dev = u == nullptr && rng.call < 0;
+  const unsigned long long call = rng_dev ? __ldcg(rng.call_dev) : (unsigned long long)rng.call;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = blockIdx.x * K2A_WARPS + warp;
@@ -38,7 +80,16 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
   float leaf_w = 0.0f;
   if (g < total) {
     const int b = g % batch;
-    float t = __fmul_rn(__fdiv_rn(__fadd_rn((float)b, u[g]), (float)batch), root);
+    float ug;
+    if (u) {
+      ug = u[g];
+    } else {
+      const uint32_t x = a0_philox_x0((uint32_t)g, 0u, (uint32_t)call, (uint32_t)(call >> 32), (uint32_t)rng.seed,
+                                      (uint32_t)(rng.seed >> 32));
+      ug = __uint2float_rn(x >> 8) * 5.9604644775390625e-08f;      // exact: 24 bits * 2^-24
+      if (rng.u_out && lane == 0) rng.u_out[g] = ug;
+    }
+    float t = __fmul_rn(__fdiv_rn(__fadd_rn((float)b, ug), (float)batch), root);
     int64_t v = 1;          // current node, warp-uniform
     float leaf = root;
     int left = D;
@@ -73,7 +124,14 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
     }
     leaf_w = leaf;
   }
-  if (weight_out == nullptr) return;
+  if (weight_out == nullptr || uniform) {
+    if (uniform && weight_out && g < total && lane == 0) weight_out[g] = 1.0f;   // ReplayEnum.uniform: weights = 1 (trainer.py:95-96)
+    if (rng_dev) {
+      __syncthreads();                                  // every warp of this CTA has read the counter
+      if (threadIdx.x == 0) a0_rng_done(rng, call, gridDim.x);
+    }
+    return;
+  }
   // ---- epilogue (trainer.py:91-94): every warp turns its own priority into the un-normalised
   //      weight; the batch maximum is folded with atomicMax on the bit pattern (w > 0) and the last
   //      arrival of each batch (ticket counter) divides the batch by (max + 1e-8).  All batches of
@@ -81,10 +139,7 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
   //      warps per CTA, a CTA lies inside one batch and aggregates in shared memory first (one
   //      atomic pair per CTA instead of per warp: 512 same-address atomics per batch become 64) and
   //      the last CTA normalises with all of its threads.
-  if (uniform) {                        // ReplayEnum.uniform: weights = priorities = 1 (trainer.py:95-96)
-    if (g < total && lane == 0) weight_out[g] = 1.0f;
-    return;
-  }
+  const unsigned int nbatches = (unsigned int)(total / batch);
   const float denom = __fadd_rn(root, sum_offset);
   if (batch % K2A_WARPS == 0) {         // total % batch == 0, so every warp of the CTA has a draw
     __shared__ float s_w[K2A_WARPS];
@@ -110,7 +165,10 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
     __threadfence();
     const float inv = __fadd_rn(__ldcg(bmax + k), 1e-8f);
     for (int j = threadIdx.x; j < batch; j += K2A_WARPS * 32) w[j] = __fdiv_rn(__ldcg(w + j), inv);
-    if (threadIdx.x == 0) { counter[k] = 0u; bmax[k] = 0.0f; }
+    if (threadIdx.x == 0) {
+      counter[k] = 0u; bmax[k] = 0.0f;
+      if (rng_dev) a0_rng_done(rng, call, nbatches);    // this batch's CTAs have all arrived, hence all read the counter
+    }
     return;
   }
   if (g >= total) return;
@@ -141,7 +199,10 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
       if (j < batch) w[j] = __fdiv_rn(v[q], inv);
     }
   }
-  if (lane == 0) { counter[k] = 0u; bmax[k] = 0.0f; }
+  if (lane == 0) {
+    counter[k] = 0u; bmax[k] = 0.0f;
+    if (rng_dev) a0_rng_done(rng, call, nbatches);
+  }
 }
 
 __global__ void a0_set_dyn(float* dyn, float top, float beta, float sum_offset) {
@@ -157,19 +218,57 @@ extern "C" int a0_rb_set_dynamic(a0_replay_t* h, float top, float beta, float su
   return A0_OK;
 }
 
-extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32_t batch, float top, float beta,
-                            float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
-                            float* weight_out, a0_stream_t stream_) {
-  A0_REQUIRE(h != nullptr, "a0_pt_sample: handle is NULL");
-  A0_REQUIRE(total >= 0 && batch > 0 && total % batch == 0, "a0_pt_sample: total %d must be a multiple of batch %d", total, batch);
+static int a0_sample_launch(a0_replay_t* h, const float* u, const A0Rng& rng, int32_t total, int32_t batch, float top,
+                            float beta, float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
+                            float* weight_out, a0_stream_t stream_, const char* who) {
+  A0_REQUIRE(h != nullptr, "%s: handle is NULL", who);
+  A0_REQUIRE(total >= 0 && batch > 0 && total % batch == 0, "%s: total %d must be a multiple of batch %d", who, total, batch);
   if (total == 0) return A0_OK;
-  A0_REQUIRE(u && idx_out && prio_out, "a0_pt_sample: NULL argument");
-  A0_REQUIRE(total / batch <= A0_MAX_BATCHES, "a0_pt_sample: at most %d batches per call", A0_MAX_BATCHES);
+  A0_REQUIRE(idx_out && prio_out, "%s: NULL argument", who);
+  A0_REQUIRE(total / batch <= A0_MAX_BATCHES, "%s: at most %d batches per call", who, A0_MAX_BATCHES);
   A0DeviceGuard guard(h->device);
   const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
   A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, A0_PDL_K2, h->tree, h->P, h->D, u, total, batch,
             top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter,
-            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr));
+            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr), rng);
+  return A0_OK;
+}
+
+extern "C" int a0_pt_sample(a0_replay_t* h, const float* u, int32_t total, int32_t batch, float top, float beta,
+                            float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
+                            float* weight_out, a0_stream_t stream_) {
+  A0_REQUIRE(total == 0 || u != nullptr, "a0_pt_sample: u is NULL (a0_pt_sample_rng draws its own uniforms)");
+  A0Rng rng = {0ull, 0ll, nullptr, nullptr, nullptr};
+  return a0_sample_launch(h, u, rng, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, stream_,
+                          "a0_pt_sample");
+}
+
+// counter[] words used by the sampler's own generator (the rest of the layout is in a0_common.cuh)
+constexpr int K2A_RNG_TICKET = 2 * A0_MAX_BATCHES + 32;  // past the per-batch maxima at [MAXB+16, 2*MAXB+16)
+constexpr int K2A_RNG_CALL = 2 * A0_MAX_BATCHES + 34;    // two words, 8-byte aligned
+
+extern "C" int a0_pt_sample_rng(a0_replay_t* h, uint64_t seed, int64_t call, int32_t total, int32_t batch, float top,
+                                float beta, float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
+                                float* weight_out, float* u_out, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_pt_sample_rng: handle is NULL");
+  A0Rng rng;
+  rng.seed = seed;
+  rng.call = call;
+  rng.call_dev = reinterpret_cast<unsigned long long*>(h->counter + K2A_RNG_CALL);
+  rng.ticket = h->counter + K2A_RNG_TICKET;
+  rng.u_out = u_out;
+  return a0_sample_launch(h, nullptr, rng, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out,
+                          stream_, "a0_pt_sample_rng");
+}
+
+__global__ void a0_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+
+extern "C" int a0_pt_rng_seek(a0_replay_t* h, uint64_t call, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_pt_rng_seek: handle is NULL");
+  A0DeviceGuard guard(h->device);
+  a0_set_u64<<<1, 1, 0, (cudaStream_t)stream_>>>(reinterpret_cast<unsigned long long*>(h->counter + K2A_RNG_CALL),
+                                                 (unsigned long long)call);
+  A0_LAUNCH_CHECK();
   return A0_OK;
 }
 

@@ -30,19 +30,22 @@ ALGOS = ("dqn", "mdqn", "c51", "qr", "iqn", "fqf")
 class ReplayTargetLoop:
     def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, n_step=None, double_q=True,
                  per=None, variant=0, discount=None, alpha=0.5, eps=0.01, c51=(51, -10.0, 10.0), mdqn=(0.03, -1.0),
-                 frames=None):
+                 frames=None, rng_seed=None):
         """replay: ReplayDataset (native_nstep=True when n_step > 1).  outputs: dict of STATIC f32 device
         tensors holding the network outputs of all L*B sampled transitions, batch k in rows
         [k*B, (k+1)*B): ``online``, ``tgt_next`` (+ ``qsel`` [L*B,A] under double_q / for iqn, fqf;
         ``tgt_cur`` for mdqn; ``atoms`` [M] for c51; ``taus`` for iqn; ``taus``, ``taus_hat``, ``q_bar`` for
         fqf), shaped as the learners produce them (agent0_b200.losses).  frames: optional u8
-        [L*B, 8*F] output buffer for the gather (allocated if None)."""
+        [L*B, 8*F] output buffer for the gather (allocated if None).  rng_seed: the sampler draws its own
+        uniforms (Philox inside K2a, device-resident call counter advanced by every launch/replay)
+        instead of reading ``self.u``, which ``step()`` otherwise refills with ``uniform_()``."""
         assert algo in ALGOS, algo
         self.lib = _lib.load()
         self.rp, self.algo, self.B, self.L, self.A = replay, algo, int(batch_size), int(learner_steps), int(action_dim)
         self.total = T = self.L * self.B
         self.dev = dev = replay.device
         self.variant = int(variant)
+        self.rng_seed = None if rng_seed is None else int(rng_seed) & 0xFFFFFFFFFFFFFFFF
         self.n = int(n_step if n_step is not None else replay.n_gather)
         self.gamma = float(discount if discount is not None else replay.gamma)
         self.gamma_n = float(np.float32(self.gamma ** self.n))
@@ -61,7 +64,7 @@ class ReplayTargetLoop:
         self.grad = torch.empty_like(self.o["online"])
         self.frac = e(T) if algo == "fqf" else None
         self.gtau = e(T, self.o["taus"].shape[1]) if algo == "fqf" else None
-        self.launches_per_step = 2 + self.L + (1 if self.per else 0)
+        self.launches_per_step = 2 + self.L + (1 if self.per else 0)     # our kernels (uniform_ is torch's)
         self._k4 = None
         self._k4_all = None
         self.graph = None
@@ -73,6 +76,11 @@ class ReplayTargetLoop:
     def sample(self):
         """K2a: L stratified batches + IS weights (top/beta from the device: push_dynamic first)."""
         rp = self.rp
+        if self.rng_seed is not None:
+            _lib.check(self.lib.a0_pt_sample_rng(rp.h, self.rng_seed, -1, self.total, self.B, -1.0, float(rp.beta), 0.0,
+                                                 0 if self.per else 1, self.idx.data_ptr(), self.prio.data_ptr(),
+                                                 self.w.data_ptr(), None, self._st()), "a0_pt_sample_rng")
+            return
         _lib.check(self.lib.a0_pt_sample(rp.h, self.u.data_ptr(), self.total, self.B, -1.0, float(rp.beta), 0.0,
                                          0 if self.per else 1, self.idx.data_ptr(), self.prio.data_ptr(),
                                          self.w.data_ptr(), self._st()), "a0_pt_sample")
@@ -148,7 +156,8 @@ class ReplayTargetLoop:
 
     # ------------------------------------------------------------------ whole steps
     def step(self, fused_k4=False):
-        self.u.uniform_()
+        if self.rng_seed is None:
+            self.u.uniform_()
         self.sample()
         self.gather()
         if fused_k4:

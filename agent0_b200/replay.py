@@ -305,14 +305,17 @@ class ReplayDataset:
                                                   _lib.stream_ptr(self.device)), "a0_rb_set_dynamic")
 
     def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None, out=None, dynamic=False,
-               normalized=None):
+               normalized=None, seed=None, call=-1, u_out=None):
         """Draw ``k_batches`` stratified batches (K2a) and gather them (K3).  ``u`` (f32 device
         tensor of k*B uniforms) or ``indices`` (i64, explicit record positions) make the draw
         reproducible for parity tests; otherwise uniforms come from torch's CUDA generator.
         ``out`` (from ``alloc_batch``) receives the result in place; ``dynamic=True`` reads top/beta
         from the device values last published by ``push_dynamic`` (for CUDA-graph capture).
         ``normalized`` (NORM_DIV / NORM_RECIP / NORM_NONE): gather straight into the learner's f32
-        obs / next_obs inputs (K3 with the /255 + split of agent.py:129-135 fused in)."""
+        obs / next_obs inputs (K3 with the /255 + split of agent.py:129-135 fused in).
+        ``seed`` (int): the sampler draws its own uniforms (Philox4x32-10 inside K2a, no separate RNG
+        launch); ``call`` >= 0 names the call number, < 0 uses the shard's device-resident counter,
+        which every launch -- or graph replay -- advances; ``u_out`` receives the uniforms."""
         B = int(batch_size or self.cfg.learner.batch_size)
         total = B * int(k_batches)
         dev = self.device
@@ -323,14 +326,21 @@ class ReplayDataset:
             weights = out.weights if out is not None else torch.empty(total, dtype=torch.float32, device=dev)
             prio = out.priorities if out is not None else torch.empty(total, dtype=torch.float32, device=dev)
             if indices is None:
-                if u is None:
-                    u = torch.rand(total, dtype=torch.float32, device=dev, generator=generator)
                 idx = out.indices if out is not None else torch.empty(total, dtype=torch.int64, device=dev)
                 sum_offset = float(self.size - self.index.top) if self.compat_sum else 0.0
-                _lib.check(self.lib.a0_pt_sample(
-                    self.h, _lib.ptr(u, torch.float32), total, B, -1.0 if dynamic else float(self.index.top),
-                    float(self.beta), sum_offset, 0 if self.prioritize else 1, _lib.ptr(idx), _lib.ptr(prio),
-                    _lib.ptr(weights), stream), "a0_pt_sample")
+                top = -1.0 if dynamic else float(self.index.top)
+                if u is None and seed is not None:
+                    _lib.check(self.lib.a0_pt_sample_rng(
+                        self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(call), total, B, top, float(self.beta), sum_offset,
+                        0 if self.prioritize else 1, _lib.ptr(idx), _lib.ptr(prio), _lib.ptr(weights),
+                        _lib.ptr(u_out, torch.float32), stream), "a0_pt_sample_rng")
+                else:
+                    if u is None:
+                        u = torch.rand(total, dtype=torch.float32, device=dev, generator=generator)
+                    _lib.check(self.lib.a0_pt_sample(
+                        self.h, _lib.ptr(u, torch.float32), total, B, top, float(self.beta), sum_offset,
+                        0 if self.prioritize else 1, _lib.ptr(idx), _lib.ptr(prio), _lib.ptr(weights), stream),
+                        "a0_pt_sample")
             else:
                 idx = indices.to(device=dev, dtype=torch.int64).contiguous()
                 total = idx.numel()
@@ -403,6 +413,11 @@ class ReplayDataset:
         with torch.cuda.device(dev):
             _lib.check(self.lib.a0_pt_update(self.h, ids.data_ptr(), loss.data_ptr(), ids.numel(), self.alpha,
                                              self.eps, _lib.stream_ptr(dev)), "a0_pt_update")
+
+    def rng_seek(self, call):
+        """Set the device-resident call counter of the sampler's own generator (stream-ordered)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.a0_pt_rng_seek(self.h, int(call), _lib.stream_ptr(self.device)), "a0_pt_rng_seek")
 
     def set_priorities(self, ids, values):
         dev = self.device

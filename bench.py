@@ -58,6 +58,7 @@ def parse():
     p.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and sweeps")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--torch-rng", action="store_true", help="uniforms from torch.Tensor.uniform_ (one more launch per step) instead of the sampler's own Philox")
     p.add_argument("--variant", type=int, default=0, help="K3 variant: 0 TMA ring, 1 LDG/STG, 2 TMA full staging, 3 TMA two CTAs per transition")
     p.add_argument("--cpu-entries", type=int, default=16384, help="deque entries for the CPU baseline sample")
     p.add_argument("--cpu-workers", type=int, default=-1, help="--impl reference DataLoader workers (-1: all cores)")
@@ -156,7 +157,8 @@ def make_hotpath(rp, wl, L, A, torch, variant=0):
             self.n_out = min(INNER, max(1, int(1e9 // (T * 8 * F_BYTES))))
             self.frames_pool = torch.empty(self.n_out, T, 8 * F_BYTES, dtype=torch.uint8, device=rp.device)
             super().__init__(rp, wl["algo"], wl["B"], L, A, net_outputs(wl["algo"], T, A, torch, rp.device), n_step=wl["n"],
-                             double_q=wl["double"], per=wl["per"], variant=variant, discount=0.99, frames=self.frames_pool[0])
+                             double_q=wl["double"], per=wl["per"], variant=variant, discount=0.99, frames=self.frames_pool[0],
+                             rng_seed=RNG_SEED)
             self.wl, self.idx_pool = wl, None
 
         def draw_pool(self):
@@ -211,6 +213,7 @@ def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
 
 
 INNER = 20
+RNG_SEED = 20261017      # the sampler draws its own uniforms (Philox inside K2a); None: torch's uniform_ + a0_pt_sample
 
 
 def capture_step(hp, torch):
@@ -390,6 +393,11 @@ def run_ours(args):
     from agent0_b200.replay import ReplayDataset
     wl = WORKLOADS[args.workload]
     L, A = args.learner_steps, args.actions
+    global RNG_SEED
+    if args.torch_rng:
+        RNG_SEED = None
+    elif RNG_SEED is not None:
+        RNG_SEED += rank
     ring = args.total_ring // world if args.total_ring else args.ring
     cfg = make_config(wl["algo"], per=wl["per"], n_step=wl["n"], batch_size=wl["B"], replay_size=ring,
                       double_q=wl["double"], dueling=True, num_envs=16, action_dim=A)
@@ -478,7 +486,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": wl["desc"], "learner_steps_per_step": L, "transitions_per_step_per_gpu": total,
                        "ring_transitions_per_gpu": ring, "frame_ring_GB_per_gpu": round(rp.index.NF * F_BYTES / 1e9, 2),
-                       "actions": A, "cuda_graph": not args.no_graph, "sharding": f"{world} independent shards, no data-path collective",
+                       "actions": A, "cuda_graph": not args.no_graph,
+                       "uniforms": "torch uniform_ launch" if RNG_SEED is None else "Philox4x32-10 inside K2a (a0_pt_sample_rng)", "sharding": f"{world} independent shards, no data-path collective",
                        "l2_note": "inputs larger than L2: gathers are random reads over the multi-GB frame ring",
                        "fill_seconds": round(t_fill, 1)},
             "clocks": clk.summary(),

@@ -185,6 +185,17 @@ int a0_pt_sample(a0_replay_t* h, const float* u /* dev [total] */, int32_t total
                  int64_t* idx_out /* dev [total] */, float* prio_out /* dev [total] */,
                  float* weight_out /* dev [total] */, a0_stream_t stream);
 
+/* The same draw with the sampler's own uniforms (no torch / host RNG, no extra launch): draw g of
+ * call c under `seed` uses u = (Philox4x32-10(counter {g, 0, c_lo, c_hi}, key {seed_lo, seed_hi}).x >> 8)
+ * * 2^-24.  call >= 0 gives the call number explicitly; call < 0 uses a device-resident counter
+ * that the launch itself advances, so every replay of a captured CUDA graph draws fresh batches
+ * (a0_rb_reset zeroes it, a0_pt_rng_seek sets it).  u_out (optional, dev [total]) receives the
+ * uniforms.                                                                                      */
+int a0_pt_sample_rng(a0_replay_t* h, uint64_t seed, int64_t call, int32_t total, int32_t batch,
+                     float top, float beta, float sum_offset, int32_t uniform, int64_t* idx_out,
+                     float* prio_out, float* weight_out, float* u_out, a0_stream_t stream);
+int a0_pt_rng_seek(a0_replay_t* h, uint64_t call, a0_stream_t stream);
+
 /* ---- K3: fused gather ---------------------------------------------------------------------------------
  * For each sampled record position: walk n_step-1 successor links, rebuild the two 4-frame stacks
  * (each distinct frame is read from HBM once and written to every place it appears), and compute

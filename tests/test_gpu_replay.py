@@ -253,6 +253,48 @@ def test_sumtree_sample_update_bit_exact():
     assert np.corrcoef(counts / counts.sum(), law)[0, 1] > 0.95
 
 
+def test_sampler_own_generator_matches_oracle_philox_and_advances_per_launch():
+    """a0_pt_sample_rng: uniforms bit-equal to oracle.sumtree.philox_uniform(seed, call, n), indices
+    equal to the oracle sum-tree fed those uniforms; the device-resident call counter advances with
+    every launch and every replay of a captured graph; rng_seek repositions it."""
+    from oracle.sumtree import philox_uniform
+    N, Bn, k = 4096, 32, 5
+    rp = _replay(N, per=True, native=True, E=4)
+    from agent0_b200.synth import fill_shard_synthetic
+    fill_shard_synthetic(rp, N, 4, 1)
+    ids = torch.arange(0, rp.top, 3, device="cuda")
+    rp.update_priority(ids, torch.rand(len(ids), device="cuda", generator=torch.Generator("cuda").manual_seed(2)) * 5)
+    tree = SumTree(N)
+    tree.set(np.arange(N), _np(rp.priority.leaves()))
+    total = Bn * k
+    u_out = torch.empty(total, device="cuda")
+    seed = 0x1234_5678_9ABC_DEF0
+
+    def check(call, batch):
+        want_u = philox_uniform(seed, call, total)
+        assert np.array_equal(_np(u_out), want_u)
+        want_idx = np.concatenate([tree.sample_stratified(want_u[j * Bn:(j + 1) * Bn])[0] for j in range(k)])
+        assert np.array_equal(_np(batch.indices), want_idx)
+
+    check(7, rp.sample(Bn, k_batches=k, seed=seed, call=7, u_out=u_out))           # explicit call number
+    for call in (0, 1, 2):                                                             # device counter: 0, 1, 2, ...
+        check(call, rp.sample(Bn, k_batches=k, seed=seed, u_out=u_out))
+    rp.rng_seek(2 ** 33 + 5)                                                           # 64-bit call numbers
+    check(2 ** 33 + 5, rp.sample(Bn, k_batches=k, seed=seed, u_out=u_out))
+    # captured graph: every replay draws the next call
+    out = rp.alloc_batch(total)
+    rp.push_dynamic()
+    rp.rng_seek(100)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        rp.sample(Bn, k_batches=k, seed=seed, u_out=u_out, out=out, dynamic=True)
+    for call in (100, 101, 102):
+        g.replay()
+        torch.cuda.synchronize()
+        check(call, out)
+
+
 @pytest.mark.parametrize("N", [2048, 4096, 70000])
 def test_sumtree_update_paths_all_depths_and_sizes(N):
     """K2b at tree depths with D % 3 = 2, 0, 2... and at every launch shape: one CTA, a cluster of

@@ -181,3 +181,20 @@ def test_act_rule_matches_reference_actor(golden, algo):
         assert np.array_equal(a, g[f"{algo}_action"][k])
         close(m, g[f"{algo}_qmax_mean"][k], rtol=1e-6)
     assert np.array_equal(OR.obs_to_float(g[f"{algo}_obs_first"]).view(np.int32), g[f"{algo}_st_first"].view(np.int32))
+
+
+# ------------------------------------------------------------------ the sampler's own generator
+def test_philox4x32_10_known_answers():
+    """Random123's published known-answer vectors for Philox4x32-10 (kat_vectors): the oracle of
+    a0_pt_sample_rng's uniforms is pinned to the published algorithm."""
+    from oracle.sumtree import philox4x32_10, philox_uniform
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kat:
+        got = philox4x32_10(np.array([c], dtype=np.uint32), np.array([k], dtype=np.uint32))[0]
+        assert tuple(int(x) for x in got) == want
+    u = philox_uniform(1234, 5, 100000)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
+    assert not np.array_equal(u[:100], philox_uniform(1234, 6, 100)) and np.array_equal(u[:100], philox_uniform(1234, 5, 100))
