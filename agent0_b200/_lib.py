@@ -55,6 +55,9 @@ SIGNATURES = {
     "a0_ix_get_stack": (_i32, [_vp, _i64, _vp]),
     "a0_ix_resolve_shift": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "a0_ix_plan": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, C.POINTER(Plan)]),
+    "a0_dd_create": (_i32, [C.POINTER(_vp), _i32]),
+    "a0_dd_destroy": (_i32, [_vp]),
+    "a0_dd_resolve": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, C.POINTER(_i32)]),
     "a0_rb_ingest_plan": (_i32, [_vp, C.POINTER(Plan), _vp, _vp, _i32, _f32, _vp]),
     "a0_rb_ingest_steps": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp]),
     "a0_rb_append": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp]),

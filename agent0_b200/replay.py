@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ring_index import ContentDeduper, NativeRingIndex, stack_delta
+from .ring_index import NativeContentDeduper, NativeRingIndex, stack_delta
 
 Batch = namedtuple("Batch", ["frames", "actions", "rewards", "terminals", "priorities", "indices",
                              "weights", "rewards_f32", "terminals_f32", "boot_indices", "obs", "next_obs"],
@@ -132,8 +132,9 @@ class ReplayDataset:
         self.tree = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_TREE), (2 * self.P,), "<f4", dev)
         self.max_p_tensor = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_MAX_P), (1,), "<f4", dev)
         self.priority = _PrioritySum(self)
-        self._dedupe = ContentDeduper(self.index, self.F)   # reference-tuple ingest
+        self._dedupe = NativeContentDeduper(self.index, self.F)   # reference-tuple ingest
         self._lz4 = None
+        self._scratch = None
 
     # ------------------------------------------------------------------ reference surface
     def __len__(self):
@@ -163,36 +164,43 @@ class ReplayDataset:
             pass
 
     # ------------------------------------------------------------------ ingest: reference tuples
-    def _decompress(self, blob):
-        want = 2 * self.stack * self.F
+    def _decompress_into(self, blob, row):
+        """One reference entry (raw bytes / ndarray / python-lz4 block, agent.py:80) into row u8[8*F]."""
+        want = row.size
         if isinstance(blob, np.ndarray):
-            return blob.reshape(-1)
-        if len(blob) == want:
-            return np.frombuffer(blob, dtype=np.uint8)
-        if self._lz4 is None:
-            try:
-                from lz4.block import decompress as _d
-                self._lz4 = _d
-            except Exception:
-                self._lz4 = _liblz4_block_decompress
-        return np.frombuffer(self._lz4(blob), dtype=np.uint8)
+            row[:] = blob.reshape(-1)
+        elif len(blob) == want:
+            row[:] = np.frombuffer(blob, dtype=np.uint8)
+        else:
+            if self._lz4 is None:
+                try:
+                    from lz4.block import decompress as _d
+                    self._lz4 = lambda b, r: r.__setitem__(slice(None), np.frombuffer(_d(b), dtype=np.uint8))
+                except Exception:
+                    self._lz4 = _liblz4_block_decompress_into
+            self._lz4(blob, row)
 
     def extend(self, transitions, streams=None):
         """Reference-compatible ingest (replay.py:45-53): a list of (frames, action, reward, done)
         with frames = the 8-frame blob concat(st, st_next) (raw bytes/ndarray or lz4 block,
         agent.py:78-81).  Entries arrive step-major, env-minor, so entry i belongs to stream
         i % num_envs unless ``streams`` says otherwise.  Frames already held for the stream's
-        previous entry are not stored again."""
+        previous entry are not stored again (native content de-duplication, a0_dd_resolve)."""
         m = len(transitions)
         if m == 0:
             return
         if streams is None:
             streams = np.arange(m, dtype=np.int64) % self.num_envs
         streams = np.asarray(streams, dtype=np.int64)
-        frames = np.stack([self._decompress(t[0]) for t in transitions]).reshape(m, 8, self.F)
-        action = np.array([int(t[1]) for t in transitions], dtype=np.int64)
-        reward = np.array([float(t[2]) for t in transitions], dtype=np.float64)
-        done = np.array([bool(t[3]) for t in transitions], dtype=np.bool_)
+        if self._scratch is None or self._scratch.shape[0] < m:      # reused: no page faults after the first call
+            self._scratch = np.empty((m, 8 * self.F), dtype=np.uint8)
+        frames = self._scratch[:m]
+        for i, t in enumerate(transitions):
+            self._decompress_into(t[0], frames[i])
+        frames = frames.reshape(m, 8, self.F)
+        action = np.fromiter((int(t[1]) for t in transitions), dtype=np.int64, count=m)
+        reward = np.fromiter((float(t[2]) for t in transitions), dtype=np.float64, count=m)
+        done = np.fromiter((bool(t[3]) for t in transitions), dtype=np.bool_, count=m)
         step = self.index.max_chunk
         for lo in range(0, m, step):
             hi = min(m, lo + step)
@@ -428,21 +436,22 @@ class ReplayDataset:
                                           _lib.stream_ptr(dev)), "a0_pt_set")
 
 
-def _liblz4_block_decompress(blob):
+def _liblz4_block_decompress_into(blob, row):
     """python-lz4 block format (4-byte little-endian size prefix + raw LZ4 block) via the system
-    liblz4, for blobs produced by the reference actor's lz4.block.compress (agent.py:80) when the
-    python package is absent."""
-    lib = _liblz4_block_decompress.lib
+    liblz4, straight into ``row`` (u8, contiguous), for blobs produced by the reference actor's
+    lz4.block.compress (agent.py:80) when the python package is absent."""
+    lib = _liblz4_block_decompress_into.lib
     if lib is None:
-        lib = _liblz4_block_decompress.lib = C.CDLL("liblz4.so.1")
+        lib = _liblz4_block_decompress_into.lib = C.CDLL("liblz4.so.1")
         lib.LZ4_decompress_safe.restype = C.c_int
-        lib.LZ4_decompress_safe.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+        lib.LZ4_decompress_safe.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+    blob = bytes(blob)
     size = int.from_bytes(blob[:4], "little")
-    out = C.create_string_buffer(size)
-    n = lib.LZ4_decompress_safe(bytes(blob[4:]), out, len(blob) - 4, size)
+    if size != row.size:
+        raise RuntimeError(f"lz4 block holds {size} bytes, expected {row.size}")
+    n = lib.LZ4_decompress_safe(blob[4:], row.ctypes.data, len(blob) - 4, size)
     if n != size:
         raise RuntimeError("lz4 block decompression failed")
-    return out.raw
 
 
-_liblz4_block_decompress.lib = None
+_liblz4_block_decompress_into.lib = None

@@ -242,6 +242,47 @@ class ContentDeduper:
             self.tail[sid] = (f.copy(), s_, h_.copy())
 
 
+class NativeContentDeduper:
+    """ContentDeduper's rule in C++ (csrc/a0_ingest.cu: a0_dd_resolve) -- the one ``ReplayDataset.extend``
+    uses: 1280 reference entries (72 MB) resolve in ~20 ms instead of ~260 ms of numpy.  The Python class
+    above stays as the executable specification (tests/test_ring_index.py requires identical output)."""
+
+    def __init__(self, index, frame_bytes):
+        import ctypes as C
+
+        from . import _lib
+        assert isinstance(index, NativeRingIndex), "the native deduper reads the native index"
+        self._C, self._L, self.ix, self.F = C, _lib, index, int(frame_bytes)
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.a0_dd_create(C.byref(h), self.F), "a0_dd_create")
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.lib.a0_dd_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def resolve(self, streams, frames):
+        """frames u8[m,8,F] (C-contiguous).  Returns fs8 i64[m,8] and new_src i64[n_new]."""
+        streams = np.ascontiguousarray(streams, dtype=np.int64)
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        m = len(streams)
+        assert frames.size == m * SLOTS * self.F
+        fs8 = np.empty((m, SLOTS), dtype=np.int64)
+        new_src = np.empty(m * SLOTS, dtype=np.int64)
+        n_new = self._C.c_int32(0)
+        self._L.check(self.lib.a0_dd_resolve(self.h, self.ix.h, streams.ctypes.data, frames.ctypes.data, m, fs8.ctypes.data,
+                                             new_src.ctypes.data, self._C.byref(n_new)), "a0_dd_resolve")
+        return fs8, new_src[:n_new.value].copy()
+
+    def detach(self, streams):
+        """No-op: a0_dd_resolve already took private copies of the stream tails."""
+
+
 def stack_delta(prev_stack, next_stack):
     """Smallest k in 0..4 such that next_stack[:4-k] == prev_stack[k:] (how many new frames a
     vector-env step brought).  Stacks are uint8 [E,4,...]; returns int64 [E]."""

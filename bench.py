@@ -563,6 +563,28 @@ def extras(rp, args, torch, peak):
                               "fused_GBps": round(by * count / t_f / 1e9, 1), "frac_of_measured_peak": round(by * count / t_f / 1e9 / peak, 4),
                               "bytes_per_transition": by})
         del hp, obs, nxt
+    # the drop-in ingest: ReplayDataset.extend with what the reference actor ships per Trainer.step --
+    # 80 steps x 16 envs = 1280 lz4 blocks of concat(st, st_next) (agent.py:78-81, config.py:111-112)
+    try:
+        from agent0_b200.config import make_config
+        from agent0_b200.replay import ReplayDataset
+        from agent0_b200.synth import record_stream
+        from oracle import cpu_path as CP, reference_replay as OR_
+        s_ = record_stream(16, 2 * 80 + 2, seed=77)
+        fr_, a_, r_, d_ = OR_.pack_nstep(s_["obs"], s_["action"], s_["reward"], s_["done"], 3, 0.99)
+        z = CP.lz4()
+        tup = [(z.compress(fr_[i].tobytes()), a_[i], r_[i], d_[i]) for i in range(2 * 1280)]
+        rq = ReplayDataset(make_config("c51", per=True, n_step=3, batch_size=32, replay_size=100_000, num_envs=16))
+        rq.extend(tup[:1280])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rq.extend(tup[1280:])
+        torch.cuda.synchronize()
+        out["compat_extend"] = {"transitions": 1280, "ms": round((time.perf_counter() - t0) * 1e3, 2),
+                                "note": "lz4 decode + native content de-duplication + staged H2D + K2b marks + K1, one call"}
+        del rq
+    except Exception as e:          # measurement only
+        out["compat_extend"] = {"error": repr(e)}
     wl = dict(WORKLOADS["c51_b512"])
     hp = HotPath(rp, wl, 128, A, torch)           # buffers for up to 65536 transitions
     hp.draw_pool()

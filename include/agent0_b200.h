@@ -132,6 +132,20 @@ typedef struct {
 int a0_ix_plan(a0_index_t* ix, const int64_t* stream, const int64_t* fs8, int32_t m, int32_t n_new,
                const int64_t* action, const double* reward, const uint8_t* done, a0_plan_t* out);
 
+/* ---- content de-duplication for the reference-compatible ingest (host code) ------------------------
+ * ReplayDataset.extend receives self-contained 8-frame entries concat(st, st_next) (agent.py:78-81).
+ * a0_dd_resolve decides which of their frames are new: a frame is matched -- 64-bit hash, then full
+ * byte comparison, so a match is always bit-exact -- against the 8 frames of the stream's previous
+ * entry (if still resident and younger than the index's age limit) and the earlier frames of its
+ * own entry.  frames: host u8[m][8][frame_bytes]; fs8_out i64[m][8] frame sequence numbers (new
+ * ones numbered upwards from the index's head_fs) for a0_ix_plan; new_src_out i64[<= 8m] flat
+ * indices t*8+j of the new frames in allocation order (a0_rb_ingest_plan's new_frame_src).       */
+typedef struct a0_dedupe a0_dedupe_t;
+int a0_dd_create(a0_dedupe_t** out, int32_t frame_bytes);
+int a0_dd_destroy(a0_dedupe_t* dd);
+int a0_dd_resolve(a0_dedupe_t* dd, a0_index_t* ix, const int64_t* stream, const uint8_t* frames,
+                  int32_t m, int64_t* fs8_out, int64_t* new_src_out, int32_t* n_new_out);
+
 /* ---- staged ingest: execute a plan on the device ------------------------------------------------
  * One pinned H2D copy of {frames, positions, record metadata, marks} from a double-buffered
  * staging area owned by the handle, then a0_pt_mark and a0_rb_append on `stream`.  frames:

@@ -52,6 +52,30 @@ def test_extend_then_gather_equals_reference_getitem(golden, n, variant):
     assert b.rewards.dtype == torch.float64 and b.terminals.dtype == torch.bool
 
 
+def test_extend_accepts_lz4_blocks_ndarrays_and_bytes(golden):
+    """The reference actor ships lz4.block.compress(concat(st, st_next)) (agent.py:78-81): python-lz4
+    block framing (4-byte size prefix) decoded through the system liblz4 straight into the ingest
+    buffer; raw bytes and ndarrays are accepted too.  Several extend() calls, mixed formats."""
+    from oracle import cpu_path as CP
+    g = golden("replay_n3")
+    z = CP.lz4()
+    M = len(g["entry_action"])
+    rp = _replay(256, n=1, E=int(g["num_envs"]))
+    tup = []
+    for i in range(M):
+        raw = g["entry_frames"][i].tobytes()
+        blob = (z.compress(raw), raw, g["entry_frames"][i])[i % 3]
+        tup.append((blob, g["entry_action"][i], g["entry_reward"][i], g["entry_done"][i]))
+    assert len(tup[0][0]) < 56448 // 4                          # really compressed
+    for lo in range(0, M, 37):
+        rp.extend(tup[lo:lo + 37], streams=np.arange(lo, min(M, lo + 37)) % int(g["num_envs"]))
+    assert rp.top == M and rp.index.head_fs < 3 * M             # de-duplicated: ~1-2 stored frames per entry, not 8
+    b = rp.gather(torch.arange(M, device="cuda"))
+    assert np.array_equal(_np(b.frames), g["entry_frames"])
+    assert np.array_equal(_np(b.actions), g["entry_action"]) and np.array_equal(_np(b.terminals), g["entry_done"])
+    assert np.array_equal(_np(b.rewards).view(np.int64), g["entry_reward"].view(np.int64))
+
+
 @pytest.mark.parametrize("n", [1, 3])
 def test_native_nstep_gather_equals_reference_actor_entries(golden, n):
     """Raw 1-step transitions in; K3 folds n steps: must equal Actor.sample's entries

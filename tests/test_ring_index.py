@@ -3,7 +3,7 @@ the reference's actor packing + deque (golden-pinned in test_oracle_golden.py)."
 import numpy as np
 import pytest
 
-from agent0_b200.ring_index import ContentDeduper, NativeRingIndex, RingIndex, stack_delta
+from agent0_b200.ring_index import ContentDeduper, NativeContentDeduper, NativeRingIndex, RingIndex, stack_delta
 from agent0_b200.synth import record_stream
 from oracle import reference_replay as OR
 from tests.ring_sim import SimDevice
@@ -161,6 +161,47 @@ def test_compat_wraparound_small_ring(Index):
             got, a, r, d, _ = dev.gather(int(pos), 1, 0.99)
             assert np.array_equal(got, frames_ref[q]) and a == a_ref[q] and d == d_ref[q]
     assert ix.tail_q > 0 and 0 < ix.top <= N
+
+
+@pytest.mark.parametrize("n,N,NF,age,chunk", [(3, 48, 150, 12, 7), (1, 256, 2048, None, 30), (3, 64, 400, 20, 1000), (2, 32, 200, 5, 3)])
+def test_native_deduper_equals_the_specification(n, N, NF, age, chunk):
+    """a0_dd_resolve (C++) against ContentDeduper (numpy specification) on the same reference entries:
+    identical frame sequence numbers and identical new-frame lists, call after call -- ring wrap, frames
+    that age out and are stored again, static screens (all eight frames equal), repeated frames inside
+    one entry, several entries of a stream per call, and a caller that overwrites its buffer between calls."""
+    E, T = 3, 90
+    s = _stream(E, T, seed=10 + n)
+    frames_ref, a_ref, r_ref, d_ref = _entries(s, n)
+    frames_ref = frames_ref.copy()
+    M = len(a_ref)
+    # static screen: a run of entries of stream 1 whose eight frames are all the same picture; and an
+    # entry whose next stack repeats its own first frame
+    for i in range(1 + 5 * E, M, E)[:6]:
+        frames_ref[i] = np.tile(frames_ref[1, :F], 8)
+    frames_ref[2 + 9 * E].reshape(8, F)[5] = frames_ref[2 + 9 * E].reshape(8, F)[0]
+    ix_py, ix_cc = NativeRingIndex(N, NF, 1, age), NativeRingIndex(N, NF, 1, age)
+    dd_py, dd_cc = ContentDeduper(ix_py, F), NativeContentDeduper(ix_cc, F)
+    step = min(chunk, ix_py.max_chunk)
+    total_new = 0
+    for lo in range(0, M, step):
+        hi = min(M, lo + step)
+        st = np.arange(lo, hi, dtype=np.int64) % E
+        fr_py = np.ascontiguousarray(frames_ref[lo:hi].reshape(hi - lo, 8, F))
+        fr_cc = fr_py.copy()
+        fs_py, new_py = dd_py.resolve(st, fr_py)
+        fs_cc, new_cc = dd_cc.resolve(st, fr_cc)
+        assert np.array_equal(fs_py, fs_cc) and np.array_equal(new_py, new_cc)
+        for ix, fs8, new in ((ix_py, fs_py, new_py), (ix_cc, fs_cc, new_cc)):
+            ix.plan(st, fs8, new, a_ref[lo:hi], r_ref[lo:hi], d_ref[lo:hi])
+        dd_py.detach(st)
+        dd_cc.detach(st)
+        fr_cc[:] = 0                      # the native deduper must not keep pointers into the caller's buffer
+        total_new += len(new_cc)
+    assert ix_py.head_fs == ix_cc.head_fs == total_new
+    if age is None:
+        assert total_new < 4 * M          # de-duplication works: far fewer than eight stored frames per entry
+    if N < M:
+        assert ix_cc.tail_q > 0
 
 
 @pytest.mark.parametrize("n,N,NF,age", [(1, 64, 300, 16), (3, 48, 220, 12), (4, 200, 5000, 64), (2, 16, 120, 8)])
