@@ -29,7 +29,7 @@ class GraphedUpdates:
     replay.  The first call runs eagerly (it is also the warm-up) and captures; later calls replay.
     At batch 32 the eager loop is bound by ~150 kernel launches per update; the replay is not."""
 
-    def __init__(self, learner, replay, batch_size, learner_steps, normalized=None):
+    def __init__(self, learner, replay, batch_size, learner_steps, normalized=None, sampler_seed=None):
         import torch
         assert learner.capturable, "construct the learner with capturable=True"
         freq = learner.cfg.learner.target_update_freq
@@ -37,11 +37,13 @@ class GraphedUpdates:
         self.torch, self.learner, self.replay = torch, learner, replay
         self.B, self.L = int(batch_size), int(learner_steps)
         self.normalized = normalized
+        self.sampler_seed = sampler_seed
         self.static = replay.alloc_batch(self.B * self.L, normalized=normalized)
         self.graph, self.outs = None, None
 
     def _updates(self):
-        self.replay.sample(self.B, k_batches=self.L, out=self.static, dynamic=True, normalized=self.normalized)
+        self.replay.sample(self.B, k_batches=self.L, out=self.static, dynamic=True, normalized=self.normalized,
+                           seed=self.sampler_seed)
         outs = []
         for b in split_batches(self.static, self.B):
             result = self.learner.update(_learner_data(b))
@@ -69,12 +71,16 @@ class GraphedUpdates:
 
 
 class Trainer:
-    def __init__(self, cfg, process_group=None, native_nstep=False, graph=False, fused_input=False, **replay_kw):
+    def __init__(self, cfg, process_group=None, native_nstep=False, graph=False, fused_input=False, sampler_seed=None,
+                 **replay_kw):
         """graph=True: the learner updates of a step run as one CUDA-graph replay (GraphedUpdates).
         fused_input=True: K3 writes the learner's normalised f32 obs / next_obs directly
         (a0_rb_gather_f32) instead of u8 frames that torch then casts, divides and splits
-        (agent.py:129-135); ``x * fl(1/255)``, i.e. bit-identical to torch's CUDA ``.div(255)``."""
+        (agent.py:129-135); ``x * fl(1/255)``, i.e. bit-identical to torch's CUDA ``.div(255)``.
+        sampler_seed: the prioritized draw takes its uniforms from the sampler's own Philox generator
+        (a0_pt_sample_rng) instead of torch's CUDA generator."""
         self.cfg = cfg
+        self.sampler_seed = sampler_seed
         self.normalized = NORM_RECIP if fused_input else None
         self.replay = ReplayDataset(cfg, native_nstep=native_nstep, **replay_kw)
         self.graph = bool(graph)
@@ -93,10 +99,11 @@ class Trainer:
         B = cfg.learner.batch_size
         if self.graph:
             if self._graphed is None or self._graphed.L != L:
-                self._graphed = GraphedUpdates(self.learner, self.replay, B, L, normalized=self.normalized)
+                self._graphed = GraphedUpdates(self.learner, self.replay, B, L, normalized=self.normalized,
+                                               sampler_seed=self.sampler_seed)
             return self._graphed.run()
         out = []
-        for b in split_batches(self.replay.sample(B, k_batches=L, normalized=self.normalized), B):
+        for b in split_batches(self.replay.sample(B, k_batches=L, normalized=self.normalized, seed=self.sampler_seed), B):
             result = self.learner.train(_learner_data(b))
             self.replay.update_priority(result["indices"], result["q_loss"])
             out.append((result["q_loss"], result["fraction_loss"]))

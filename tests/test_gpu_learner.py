@@ -150,3 +150,31 @@ def test_fused_input_trainer_equals_unfused(golden, graph):
     torch.testing.assert_close(runs[True][2], runs[False][2], rtol=2e-4, atol=1e-6)
     for a, b in zip(runs[True][1], runs[False][1]):
         assert float((a - b).abs().max()) <= 12 * cfg.learner.learning_rate * 1.01
+
+
+def test_trainer_with_the_samplers_own_generator_draws_fresh_batches_per_replay(golden):
+    """Trainer(graph=True, sampler_seed=...): uniforms come from the sampler's Philox stream, whose call
+    counter lives on the device, so every replay of the captured updates draws new batches."""
+    from agent0_b200.config import make_config
+    from agent0_b200.trainer import Trainer
+    g = golden("replay_n3")
+    M = len(g["entry_action"])
+    tup = [(g["entry_frames"][i].tobytes(), g["entry_action"][i], g["entry_reward"][i], g["entry_done"][i]) for i in range(M)]
+    cfg = make_config("c51", per=True, n_step=3, batch_size=8, double_q=True, dueling=True, replay_size=256, num_envs=3)
+    cfg.trainer.training_start_steps = 10
+    cfg.learner.learner_steps = 4
+    cfg.learner.target_update_freq = 8
+    tr = Trainer(cfg, graph=True, fused_input=True, sampler_seed=99)
+    tr.replay.extend(tup)
+    seen = []
+    for _ in range(4):
+        out = tr.learn()
+        torch.cuda.synchronize()
+        assert all(torch.isfinite(q).all() for q, _ in out)
+        seen.append(tr._graphed.static.indices.clone())
+    assert tr.learner.update_steps == 16
+    assert not torch.equal(seen[1], seen[2]) and not torch.equal(seen[2], seen[3])     # replays 2 and 3 drew different batches
+    tree = tr.replay.tree.cpu().numpy()
+    P = tr.replay.P
+    for node in (1, 2, 3, P // 2, P - 1):
+        assert tree[node] == np.float32(tree[2 * node] + tree[2 * node + 1])
