@@ -319,6 +319,33 @@ def test_sampler_own_generator_matches_oracle_philox_and_advances_per_launch():
         check(call, out)
 
 
+@pytest.mark.parametrize("per,Bn", [(True, 12), (False, 32), (False, 5)])
+def test_sampler_own_generator_other_launch_shapes(per, Bn):
+    """The device call counter must advance exactly once per launch on every epilogue path: batch sizes
+    that are not a multiple of the warps per CTA (per-warp tickets) and the uniform policy (no weights
+    epilogue, per-CTA arrivals)."""
+    from oracle.sumtree import philox_uniform
+    N, k = 1024, 3
+    rp = _replay(N, per=per, native=True, E=4)
+    from agent0_b200.synth import fill_shard_synthetic
+    fill_shard_synthetic(rp, N, 4, 1)
+    tree = SumTree(N)
+    tree.set(np.arange(N), _np(rp.priority.leaves()))
+    total = Bn * k
+    u_out = torch.empty(total, device="cuda")
+    for call in range(4):
+        b = rp.sample(Bn, k_batches=k, seed=5, u_out=u_out)
+        want_u = philox_uniform(5, call, total)
+        assert np.array_equal(_np(u_out), want_u)
+        want_idx = np.concatenate([tree.sample_stratified(want_u[j * Bn:(j + 1) * Bn])[0] for j in range(k)])
+        assert np.array_equal(_np(b.indices), want_idx)
+        if not per:
+            assert bool((b.weights == 1).all())
+        else:
+            w = _np(b.weights).reshape(k, Bn)
+            assert np.allclose(w.max(axis=1), 1.0, atol=1e-6)
+
+
 @pytest.mark.parametrize("N", [2048, 4096, 70000])
 def test_sumtree_update_paths_all_depths_and_sizes(N):
     """K2b at tree depths with D % 3 = 2, 0, 2... and at every launch shape: one CTA, a cluster of
