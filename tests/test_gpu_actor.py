@@ -151,3 +151,35 @@ def test_shard_actor_fills_the_ring_like_the_reference_actor_fills_its_deque(gol
     assert np.array_equal(b.actions.cpu().numpy(), g["entry_action"][ref_i])
     assert np.array_equal(b.rewards.cpu().numpy().view(np.int64), g["entry_reward"][ref_i].view(np.int64))
     assert np.array_equal(b.terminals.cpu().numpy(), g["entry_done"][ref_i])
+
+
+def test_actor_and_trainer_run_the_whole_loop_together():
+    """Trainer.run's loop (trainer.py:171-184) with every piece on the new path: ActorPolicy + ShardActor
+    feed the shard one step at a time, Trainer(graph, fused input, the sampler's own generator) learns
+    from it; counts, priorities and the tree stay consistent."""
+    from agent0_b200.actor import ActorPolicy, ShardActor
+    from agent0_b200.synth import SyntheticStreams
+    from agent0_b200.trainer import Trainer
+    E = 4
+    cfg = make_config("c51", per=True, n_step=3, batch_size=8, double_q=True, dueling=True, replay_size=512, num_envs=E)
+    cfg.actor.sample_steps = 20
+    cfg.learner.learner_steps = 4
+    cfg.learner.target_update_freq = 8
+    tr = Trainer(cfg, native_nstep=True, graph=True, fused_input=True, sampler_seed=3)
+    actor = ShardActor(cfg, SyntheticStreams(E, seed=5, noise=True), ActorPolicy(cfg, tr.learner.model, rng=np.random.RandomState(0)),
+                       tr.replay)
+    losses = []
+    for it in range(8):                    # 8 x 20 x 4 = 640 transitions through a 512-record ring: it wraps
+        n, rs, qs = actor.sample(0.5)
+        assert n == 20 * E and len(qs) == 20 and all(np.isfinite(q) for q in qs)
+        out = tr.learn()
+        torch.cuda.synchronize()
+        losses.append(float(torch.stack([q.mean() for q, _ in out]).mean()))
+    assert all(np.isfinite(l) for l in losses) and tr.learner.update_steps == 32
+    rp = tr.replay
+    assert 0 < rp.top <= 512 and rp.index.tail_q > 0
+    leaves = rp.priority.leaves().cpu().numpy()
+    assert (leaves > 0).sum() == rp.top and (leaves != 1.0).sum() > 20       # priorities were rewritten
+    tree = rp.tree.cpu().numpy()
+    for node in (1, 2, 3, rp.P // 2, rp.P - 1):
+        assert tree[node] == np.float32(tree[2 * node] + tree[2 * node + 1])
