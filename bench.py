@@ -212,6 +212,7 @@ def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
     return e0.elapsed_time(e1) / 1e3
 
 
+EMIT = print
 INNER = 20
 RNG_SEED = 20261017      # the sampler draws its own uniforms (Philox inside K2a); None: torch's uniform_ + a0_pt_sample
 
@@ -505,7 +506,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "extra": extra,
         }
-        print(json.dumps(line))
+        EMIT(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -685,7 +686,7 @@ def run_reference(args):
               f"({'in-process, num_workers=0' if workers == 0 else str(workers) + ' worker processes'}) on a {n_entries}-entry "
               f"lz4 deque + torch CPU loss ({threads} intra-op threads); fastest of {tried}")
     cores_used = used
-    print(json.dumps({
+    EMIT(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8 frames / f32 targets / f64 n-step returns", "data": "synthetic",
@@ -697,8 +698,24 @@ def run_reference(args):
     del loader
 
 
+def _json_only_stdout():
+    """Everything any library prints to stdout while the benchmark runs (NCCL's version banner, for
+    one) goes to stderr; the process's real stdout receives exactly the one JSON line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    sys.stdout = sys.stderr
+
+    def emit(line):
+        out.write(line + "\n")
+        out.flush()
+    return emit
+
+
 if __name__ == "__main__":
     a = parse()
+    EMIT = _json_only_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
