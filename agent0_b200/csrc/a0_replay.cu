@@ -38,11 +38,25 @@ int a0_option_k2b_levels() {
   }
   return g_k2b_levels;
 }
+static int g_k2b_bulk_min = 0;
+int a0_option_k2b_bulk_min() {
+  if (g_k2b_bulk_min == 0) {
+    const char* e = getenv("A0_K2B_BULK_MIN");
+    g_k2b_bulk_min = e ? atoi(e) : A0_K2B_BULK_MIN_DEFAULT;
+    if (g_k2b_bulk_min < 1) g_k2b_bulk_min = 1;
+  }
+  return g_k2b_bulk_min;
+}
 extern "C" int a0_set_option(int32_t option, int64_t value) {
   if (option == A0_OPT_PDL) { g_pdl = (int)value & 15; return A0_OK; }
   if (option == A0_OPT_K2B_LEVELS) {
     A0_REQUIRE(value == 3 || value == 4, "a0_set_option: A0_OPT_K2B_LEVELS must be 3 or 4");
     g_k2b_levels = (int)value;
+    return A0_OK;
+  }
+  if (option == A0_OPT_K2B_BULK_MIN) {
+    A0_REQUIRE(value >= 1, "a0_set_option: A0_OPT_K2B_BULK_MIN must be positive");
+    g_k2b_bulk_min = (int)(value > (1 << 30) ? (1 << 30) : value);
     return A0_OK;
   }
   a0_set_error("a0_set_option: unknown option %d", option);

@@ -468,7 +468,8 @@ template <int K2P_LEVELS>
 __global__ void __launch_bounds__(K2P_THREADS)
 a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
-             float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner) {
+             float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
+             int32_t* __restrict__ dirty, int32_t chunk_log) {
   A0_PDL_PROLOGUE();
   const bool single = gridDim.x == 1;
   const int gtid = blockIdx.x * K2P_THREADS + threadIdx.x;
@@ -521,11 +522,13 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
       v = val[s];
     }
     __stcg(tree + P + pos[s], v);
+    if (dirty) dirty[pos[s] >> chunk_log] = 1;               // hybrid: a0_k2b_rebuild recomputes the touched chunks
   }
   a0_cluster_sync(single);
 #pragma unroll
   for (int s = 0; s < K2P_PER_THREAD; ++s)                   // release
     if (pos[s] >= 0) winner[pos[s]] = -1;
+  if (dirty) return;
   // ---- propagate, sparse part: climb from the leaves (level D) to level `top` ---------------------
   // Near the root every index shares its ancestors with every other one (10 240 stores to the
   // root per phase serialise in L2), so the per-index climb stops at level `top` <= K2P_TOP and the
@@ -570,7 +573,8 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
 }
 
 static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
-                           int32_t count, int32_t mode, float alpha, float eps, cudaStream_t stream) {
+                           int32_t count, int32_t mode, float alpha, float eps, cudaStream_t stream,
+                           int32_t* dirty = nullptr, int32_t chunk_log = 0) {
   int ctas = (count + K2P_THREADS - 1) / K2P_THREADS;
   ctas = ctas < 1 ? 1 : (ctas > K2P_CLUSTER ? K2P_CLUSTER : ctas);
   if (ctas > 1 && (ctas & (ctas - 1))) {            // cluster sizes: powers of two
@@ -580,10 +584,10 @@ static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* 
   }
   if (a0_option_k2b_levels() == 4)
     A0_LAUNCH(a0_k2b_paths<4>, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32,
-              vals, count, mode, alpha, eps, h->max_p, h->winner);
+              vals, count, mode, alpha, eps, h->max_p, h->winner, dirty, chunk_log);
   else
     A0_LAUNCH(a0_k2b_paths<3>, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32,
-              vals, count, mode, alpha, eps, h->max_p, h->winner);
+              vals, count, mode, alpha, eps, h->max_p, h->winner, dirty, chunk_log);
   return A0_OK;
 }
 
@@ -592,11 +596,22 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
   if (count == 0) return A0_OK;
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (count <= K2P_MAX) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream);
   const int chunk_log = h->D < K2R_MAXLOG ? h->D : K2R_MAXLOG;
-  A0_LAUNCH(a0_k2b_write, 1, K2B_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
-            eps, h->max_p, h->winner, h->dirty);
-  A0_LAUNCH(a0_k2b_rebuild, (unsigned)(h->P >> chunk_log), K2R_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->D, chunk_log, h->dirty,
+  const int64_t chunks = h->P >> chunk_log;
+  // Three schedules, same tree.  Few indices: one cluster climbs the paths.  Many indices relative to
+  // the tree (10 240 updates on a 1 M-leaf tree touch nearly every 4096-leaf chunk): the cluster only
+  // writes the leaves (claim / write / release, two cluster barriers) and the chunk rebuild runs on
+  // all SMs -- measured 29 -> see DESIGN.md.  More than one cluster can hold: one CTA writes.
+  const bool hybrid = count >= a0_option_k2b_bulk_min() && (int64_t)count >= 4 * chunks;
+  if (count <= K2P_MAX && !hybrid) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream);
+  if (count <= K2P_MAX) {
+    int rc = a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream, h->dirty, chunk_log);
+    if (rc) return rc;
+  } else {
+    A0_LAUNCH(a0_k2b_write, 1, K2B_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
+              eps, h->max_p, h->winner, h->dirty);
+  }
+  A0_LAUNCH(a0_k2b_rebuild, (unsigned)chunks, K2R_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->D, chunk_log, h->dirty,
             h->counter + A0_MAX_BATCHES);
   return A0_OK;
 }

@@ -61,6 +61,11 @@ const char* a0_last_error(void);
 /* A0_OPT_K2B_LEVELS (3 or 4, default 3; A0_K2B_LEVELS in the environment): tree levels a priority
  * update climbs per barrier phase (8 or 16 siblings loaded per index).  Same tree either way.   */
 #define A0_OPT_K2B_LEVELS 2
+/* A0_OPT_K2B_BULK_MIN (default 2048; A0_K2B_BULK_MIN in the environment): sum-tree writes of at
+ * least this many indices -- and at least 4 per 4096-leaf chunk of the tree -- write the leaves in
+ * one cluster launch and rebuild the touched chunks on all SMs in a second one, instead of the
+ * single-cluster path climb.  Same tree either way.                                              */
+#define A0_OPT_K2B_BULK_MIN 3
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------

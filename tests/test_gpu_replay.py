@@ -349,7 +349,8 @@ def test_sampler_own_generator_other_launch_shapes(per, Bn):
 @pytest.mark.parametrize("N", [2048, 4096, 70000])
 def test_sumtree_update_paths_all_depths_and_sizes(N):
     """K2b at tree depths with D % 3 = 2, 0, 2... and at every launch shape: one CTA, a cluster of
-    up to 8 CTAs, and the chunk-rebuild fallback above 16384 indices -- always the oracle's tree."""
+    up to 8 CTAs climbing the paths, the cluster leaf write + chunk rebuild on all SMs (from 2048 indices
+    with >= 4 per chunk), and the one-CTA write + rebuild above 16384 indices -- always the oracle's tree."""
     rp = _replay(N, per=True)
     rng = np.random.RandomState(N)
     ref = SumTree(N)
