@@ -60,9 +60,12 @@ SIGNATURES = {
     "a0_dd_resolve": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, C.POINTER(_i32)]),
     "a0_rb_ingest_plan": (_i32, [_vp, C.POINTER(Plan), _vp, _vp, _i32, _f32, _vp]),
     "a0_rb_ingest_steps": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp]),
+    "a0_rb_ingest_steps_dyn": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _vp]),
     "a0_rb_append": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "a0_pt_mark": (_i32, [_vp, _vp, _i32, _f32, _vp]),
     "a0_pt_update": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _vp]),
+    "a0_pt_update_report": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp]),
+    "a0_host_map": (_i32, [_vp, C.POINTER(_vp)]),
     "a0_pt_set": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "a0_rb_set_dynamic": (_i32, [_vp, _f32, _f32, _f32, _vp]),
     "a0_pt_sample": (_i32, [_vp, _vp, _i32, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
@@ -132,6 +135,16 @@ def ptr(t, dtype=None):
     if not t.is_contiguous():
         raise ValueError("tensor must be contiguous")
     return t.data_ptr()
+
+
+def host_map(t):
+    """Device-visible address of a pinned CPU tensor (a0_host_map), for kernels that write results
+    straight into host memory."""
+    if t.is_cuda or not t.is_pinned():
+        raise ValueError("host_map needs a pinned CPU tensor")
+    out = _vp()
+    check(load().a0_host_map(t.data_ptr(), C.byref(out)), "a0_host_map")
+    return out.value
 
 
 class _DevView:

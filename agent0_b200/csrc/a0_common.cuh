@@ -95,6 +95,7 @@ bool a0_pdl_enabled(int kernel_class);
 int a0_option_k2b_levels();
 constexpr int A0_K2B_BULK_MIN_DEFAULT = 2048;    // from this many indices (and >= 4 per 4096-leaf chunk): leaf writes + chunk rebuild on all SMs
 int a0_option_k2b_bulk_min();
+bool a0_option_fused_ingest();
 
 // (Measured alternative: launch_dependents BEFORE the wait lets a whole chain of dependent kernels
 // become resident launches ahead.  It does not lower the ~2.85 us per-link cost of the batch-32 K4
@@ -148,6 +149,51 @@ struct A0DeviceGuard {
   explicit A0DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); else prev = -1; }
   ~A0DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+// ---- K1 building blocks (used by a0_k1_append and by the fused append + mark launch) -----------------
+// One staged frame into its ring slot with 16-byte vector loads/stores (7056 B = 441 uint4).
+__device__ __forceinline__ void a0_k1_copy_frame(uint8_t* __restrict__ frames, int32_t F, int64_t NF,
+                                                 const uint8_t* __restrict__ staged, const int32_t* __restrict__ new_pos,
+                                                 int f, int tid, int nthreads) {
+  const int32_t pos = new_pos[f];
+  if (pos < 0 || pos >= NF) return;
+  const uint4* src = reinterpret_cast<const uint4*>(staged + (size_t)f * F);
+  uint4* dst = reinterpret_cast<uint4*>(frames + (size_t)pos * F);
+  const int nvec = F >> 4;
+  for (int i = tid; i < nvec; i += nthreads) dst[i] = __ldg(src + i);
+}
+// Record r of the append: slots, {reward, action|done, link}, and the predecessor's successor link.
+__device__ __forceinline__ void a0_k1_write_record(int32_t* __restrict__ rec_slots, A0RecInfo* __restrict__ rec_info,
+                                                   int64_t N, const int32_t* __restrict__ meta, int r) {
+  const int32_t* mt = meta + (size_t)r * A0_REC_META_I32;
+  const int32_t pos = mt[0], link_from = mt[1], link_to = mt[2], action_done = mt[3];
+  if (pos < 0 || pos >= N) return;
+  int4* s = reinterpret_cast<int4*>(rec_slots + (size_t)pos * A0_SLOTS);
+  s[0] = make_int4(mt[4], mt[5], mt[6], mt[7]);
+  s[1] = make_int4(mt[8], mt[9], mt[10], mt[11]);
+  A0RecInfo info;
+  info.reward = __hiloint2double(mt[13], mt[12]);
+  info.action_done = action_done;
+  info.link = link_to;
+  rec_info[pos] = info;
+  // predecessor written by an earlier append: only its link word is touched
+  if (link_from >= 0 && link_from < N) rec_info[link_from].link = pos;
+}
+// {top, beta, sum_offset} for a0_pt_sample(top < 0); dyn == NULL: nothing to publish
+struct A0Dyn {
+  float* dyn;
+  float top, beta, sum_offset;
+};
+
+// a0_sumtree.cu: marks (a0_pt_mark) and the append (a0_rb_append) of one small ingest in ONE launch.
+// Returns A0_NOFIT when the sizes do not fit the fused kernel (the caller then launches the two separately).
+constexpr int A0_NOFIT = -100;
+int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, float alpha, const uint8_t* new_frames,
+                          const int32_t* new_frame_pos, int32_t n_new, const int32_t* rec_meta, int32_t m,
+                          const A0Dyn& dyn, cudaStream_t stream);
+// a0_replay.cu: a0_rb_append that also publishes the sampler's dynamic scalars
+int a0_append_launch(a0_replay* h, const uint8_t* new_frames, const int32_t* new_frame_pos, int32_t n_new,
+                     const int32_t* rec_meta, int32_t m, const A0Dyn& dyn, cudaStream_t stream);
 
 // ---- small device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float a0_warp_max(float v) {

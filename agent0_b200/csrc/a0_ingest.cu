@@ -369,11 +369,18 @@ static int a0_stage_reserve(a0_replay* h, int turn, size_t bytes) {
   return A0_OK;
 }
 
-extern "C" int a0_rb_ingest_plan(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames,
-                                 const int64_t* new_frame_src, int32_t flags, float alpha, a0_stream_t stream_) {
+// dyn.dyn != NULL: the launch that appends also publishes {top, beta, sum_offset} for the sampler
+// (what a0_rb_set_dynamic would otherwise launch a kernel for).
+static int a0_ingest_plan_impl(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames,
+                               const int64_t* new_frame_src, int32_t flags, float alpha, a0_stream_t stream_,
+                               const A0Dyn& dyn) {
   A0_REQUIRE(h && plan, "a0_rb_ingest_plan: NULL argument");
   const int32_t n_new = plan->n_new, m = plan->m, k = plan->n_marks;
-  if (n_new == 0 && m == 0 && k == 0) return A0_OK;
+  if (n_new == 0 && m == 0 && k == 0) {
+    if (!dyn.dyn) return A0_OK;
+    A0DeviceGuard guard(h->device);
+    return a0_append_launch(h, nullptr, nullptr, 0, nullptr, 0, dyn, (cudaStream_t)stream_);
+  }
   A0_REQUIRE(n_new == 0 || frames, "a0_rb_ingest_plan: frames is NULL");
   const bool on_device = flags & A0_INGEST_FRAMES_ON_DEVICE;
   const bool pinned = flags & A0_INGEST_FRAMES_PINNED;
@@ -434,30 +441,48 @@ extern "C" int a0_rb_ingest_plan(a0_replay_t* h, const a0_plan_t* plan, const ui
     A0_CUDA(cudaEventRecord(s.copied, cs));
     A0_CUDA(cudaStreamWaitEvent(stream, s.copied, 0));
   }
-  const uint8_t* dev_frames = on_device ? frames : s.dev + sec[0];
-  if (k) {
-    rc = a0_pt_mark(h, (const int32_t*)(s.dev + sec[3]), k, alpha, stream_);
-    if (rc) return rc;
+  const uint8_t* dev_frames = n_new ? (on_device ? frames : s.dev + sec[0]) : nullptr;
+  const int32_t* dev_pos = n_new ? (const int32_t*)(s.dev + sec[1]) : nullptr;
+  const int32_t* dev_meta = m ? (const int32_t*)(s.dev + sec[2]) : nullptr;
+  A0_REQUIRE(((uintptr_t)dev_frames & 15) == 0, "a0_rb_ingest_plan: device frames must be 16-byte aligned");
+  // A step-sized append (a few hundred marks, tens of frames) goes out as ONE launch: marks and
+  // append touch disjoint state.  Bulk fills keep the two launches (cluster marks, 128-thread K1 CTAs).
+  rc = (k && a0_option_fused_ingest()) ? a0_launch_mark_append(h, (const int32_t*)(s.dev + sec[3]), k, alpha, dev_frames, dev_pos, n_new, dev_meta, m,
+                                                               dyn, stream)
+                                       : A0_NOFIT;
+  if (rc == A0_NOFIT) {
+    if (k) {
+      rc = a0_pt_mark(h, (const int32_t*)(s.dev + sec[3]), k, alpha, stream_);
+      if (rc) return rc;
+    }
+    rc = a0_append_launch(h, dev_frames, dev_pos, n_new, dev_meta, m, dyn, stream);
   }
-  rc = a0_rb_append(h, n_new ? dev_frames : nullptr, n_new ? (const int32_t*)(s.dev + sec[1]) : nullptr, n_new,
-                    m ? (const int32_t*)(s.dev + sec[2]) : nullptr, m, stream_);
   if (rc) return rc;
   A0_CUDA(cudaEventRecord(s.event, stream));
   return A0_OK;
 }
 
-extern "C" int a0_rb_ingest_steps(a0_replay_t* h, a0_index_t* ix, const int64_t* stream, const int64_t* n_new,
-                                  const uint8_t* new_frames, int32_t flags, const int64_t* action,
-                                  const double* reward, const uint8_t* done, int32_t m, float alpha,
-                                  a0_stream_t cuda_stream) {
-  A0_REQUIRE(h && ix, "a0_rb_ingest_steps: NULL handle");
-  A0_REQUIRE(m >= 0, "a0_rb_ingest_steps: negative count");
-  A0_REQUIRE(ix->N == h->N && ix->NF == h->NF, "a0_rb_ingest_steps: index and shard capacities differ");
+extern "C" int a0_rb_ingest_plan(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames,
+                                 const int64_t* new_frame_src, int32_t flags, float alpha, a0_stream_t stream) {
+  const A0Dyn none = {nullptr, 0.0f, 0.0f, 0.0f};
+  return a0_ingest_plan_impl(h, plan, frames, new_frame_src, flags, alpha, stream, none);
+}
+
+// beta == NULL: nothing is published.  Otherwise the LAST chunk's append publishes
+// {ix->top after the append, *beta, compat_sum ? N - top : 0}.
+static int a0_ingest_steps_impl(a0_replay_t* h, a0_index_t* ix, const int64_t* stream, const int64_t* n_new,
+                                const uint8_t* new_frames, int32_t flags, const int64_t* action, const double* reward,
+                                const uint8_t* done, int32_t m, float alpha, const float* beta, int32_t compat_sum,
+                                a0_stream_t cuda_stream, const char* who) {
+  A0_REQUIRE(h && ix, "%s: NULL handle", who);
+  A0_REQUIRE(m >= 0, "%s: negative count", who);
+  A0_REQUIRE(ix->N == h->N && ix->NF == h->NF, "%s: index and shard capacities differ", who);
   const size_t F = (size_t)h->F;
   const int64_t step = ix->max_chunk();
   size_t frame_off = 0;
-  for (int64_t lo = 0; lo < m; lo += step) {
-    const int32_t cnt = (int32_t)std::min<int64_t>(step, m - lo);
+  A0Dyn dyn = {nullptr, 0.0f, 0.0f, 0.0f};
+  for (int64_t lo = 0; lo < m || (lo == 0 && beta); lo += step) {
+    const int32_t cnt = (int32_t)std::max<int64_t>(0, std::min<int64_t>(step, m - lo));
     ix->fs8.resize((size_t)cnt * A0_SLOTS);
     int rc = a0_ix_resolve_shift(ix, stream + lo, n_new + lo, cnt, ix->fs8.data());
     if (rc) return rc;
@@ -466,9 +491,33 @@ extern "C" int a0_rb_ingest_steps(a0_replay_t* h, a0_index_t* ix, const int64_t*
     a0_plan_t plan;
     rc = a0_ix_plan(ix, stream + lo, ix->fs8.data(), cnt, (int32_t)total_new, action + lo, reward + lo, done + lo, &plan);
     if (rc) return rc;
-    rc = a0_rb_ingest_plan(h, &plan, new_frames ? new_frames + frame_off * F : nullptr, nullptr, flags, alpha, cuda_stream);
+    if (beta && lo + step >= m) {
+      dyn.dyn = h->dyn;
+      dyn.top = (float)ix->top;
+      dyn.beta = *beta;
+      dyn.sum_offset = compat_sum ? (float)(ix->N - ix->top) : 0.0f;
+    }
+    rc = a0_ingest_plan_impl(h, &plan, new_frames ? new_frames + frame_off * F : nullptr, nullptr, flags, alpha, cuda_stream,
+                             dyn);
     if (rc) return rc;
     frame_off += (size_t)total_new;
+    if (m == 0) break;
   }
   return A0_OK;
+}
+
+extern "C" int a0_rb_ingest_steps(a0_replay_t* h, a0_index_t* ix, const int64_t* stream, const int64_t* n_new,
+                                  const uint8_t* new_frames, int32_t flags, const int64_t* action,
+                                  const double* reward, const uint8_t* done, int32_t m, float alpha,
+                                  a0_stream_t cuda_stream) {
+  return a0_ingest_steps_impl(h, ix, stream, n_new, new_frames, flags, action, reward, done, m, alpha, nullptr, 0,
+                              cuda_stream, "a0_rb_ingest_steps");
+}
+
+extern "C" int a0_rb_ingest_steps_dyn(a0_replay_t* h, a0_index_t* ix, const int64_t* stream, const int64_t* n_new,
+                                      const uint8_t* new_frames, int32_t flags, const int64_t* action,
+                                      const double* reward, const uint8_t* done, int32_t m, float alpha, float beta,
+                                      int32_t compat_sum, a0_stream_t cuda_stream) {
+  return a0_ingest_steps_impl(h, ix, stream, n_new, new_frames, flags, action, reward, done, m, alpha, &beta, compat_sum,
+                              cuda_stream, "a0_rb_ingest_steps_dyn");
 }

@@ -47,7 +47,16 @@ int a0_option_k2b_bulk_min() {
   }
   return g_k2b_bulk_min;
 }
+static int g_fused_ingest = -1;
+bool a0_option_fused_ingest() {
+  if (g_fused_ingest < 0) {
+    const char* e = getenv("A0_FUSED_INGEST");
+    g_fused_ingest = e ? (atoi(e) != 0) : 1;
+  }
+  return g_fused_ingest != 0;
+}
 extern "C" int a0_set_option(int32_t option, int64_t value) {
+  if (option == A0_OPT_FUSED_INGEST) { g_fused_ingest = value != 0; return A0_OK; }
   if (option == A0_OPT_PDL) { g_pdl = (int)value & 15; return A0_OK; }
   if (option == A0_OPT_K2B_LEVELS) {
     A0_REQUIRE(value == 3 || value == 4, "a0_set_option: A0_OPT_K2B_LEVELS must be 3 or 4");
@@ -177,33 +186,29 @@ constexpr int K1_THREADS = 128;
 __global__ void __launch_bounds__(K1_THREADS)
 a0_k1_append(uint8_t* __restrict__ frames, int32_t F, int64_t NF, const uint8_t* __restrict__ staged,
              const int32_t* __restrict__ new_pos, int32_t n_new, int32_t* __restrict__ rec_slots,
-             A0RecInfo* __restrict__ rec_info, int64_t N, const int32_t* __restrict__ meta, int32_t m) {
+             A0RecInfo* __restrict__ rec_info, int64_t N, const int32_t* __restrict__ meta, int32_t m, const A0Dyn dyn) {
   A0_PDL_PROLOGUE();
+  if (dyn.dyn && blockIdx.x == 0 && threadIdx.x == 0) {   // what a0_rb_set_dynamic would launch a kernel for
+    dyn.dyn[0] = dyn.top; dyn.dyn[1] = dyn.beta; dyn.dyn[2] = dyn.sum_offset;
+  }
   if ((int)blockIdx.x < n_new) {
-    const int f = blockIdx.x;
-    const int32_t pos = new_pos[f];
-    if (pos < 0 || pos >= NF) return;
-    const uint4* src = reinterpret_cast<const uint4*>(staged + (size_t)f * F);
-    uint4* dst = reinterpret_cast<uint4*>(frames + (size_t)pos * F);
-    const int nvec = F >> 4;
-    for (int i = threadIdx.x; i < nvec; i += K1_THREADS) dst[i] = __ldg(src + i);
+    a0_k1_copy_frame(frames, F, NF, staged, new_pos, blockIdx.x, threadIdx.x, K1_THREADS);
     return;
   }
   const int r = ((int)blockIdx.x - n_new) * K1_THREADS + threadIdx.x;
-  if (r >= m) return;
-  const int32_t* mt = meta + (size_t)r * A0_REC_META_I32;
-  const int32_t pos = mt[0], link_from = mt[1], link_to = mt[2], action_done = mt[3];
-  if (pos < 0 || pos >= N) return;
-  int4* s = reinterpret_cast<int4*>(rec_slots + (size_t)pos * A0_SLOTS);
-  s[0] = make_int4(mt[4], mt[5], mt[6], mt[7]);
-  s[1] = make_int4(mt[8], mt[9], mt[10], mt[11]);
-  A0RecInfo info;
-  info.reward = __hiloint2double(mt[13], mt[12]);
-  info.action_done = action_done;
-  info.link = link_to;
-  rec_info[pos] = info;
-  // predecessor written by an earlier append: only its link word is touched
-  if (link_from >= 0 && link_from < N) rec_info[link_from].link = pos;
+  if (r < m) a0_k1_write_record(rec_slots, rec_info, N, meta, r);
+}
+
+int a0_append_launch(a0_replay* h, const uint8_t* new_frames, const int32_t* new_frame_pos, int32_t n_new,
+                     const int32_t* rec_meta, int32_t m, const A0Dyn& dyn, cudaStream_t stream) {
+  int blocks = n_new + (m + K1_THREADS - 1) / K1_THREADS;
+  if (blocks == 0) {
+    if (!dyn.dyn) return A0_OK;
+    blocks = 1;                                   // nothing to append: the launch only publishes the scalars
+  }
+  A0_LAUNCH(a0_k1_append, (unsigned)blocks, K1_THREADS, 0, stream, 1, A0_PDL_K1, h->frames, h->F, h->NF, new_frames,
+            new_frame_pos, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m, dyn);
+  return A0_OK;
 }
 
 extern "C" int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames, const int32_t* new_frame_pos,
@@ -215,10 +220,8 @@ extern "C" int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames, const int
   A0_REQUIRE(m == 0 || rec_meta, "a0_rb_append: NULL rec_meta");
   A0_REQUIRE(((uintptr_t)new_frames & 15) == 0, "a0_rb_append: new_frames must be 16-byte aligned");
   A0DeviceGuard guard(h->device);
-  const int blocks = n_new + (m + K1_THREADS - 1) / K1_THREADS;
-  A0_LAUNCH(a0_k1_append, (unsigned)blocks, K1_THREADS, 0, (cudaStream_t)stream_, 1, A0_PDL_K1, h->frames, h->F, h->NF, new_frames,
-            new_frame_pos, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m);
-  return A0_OK;
+  const A0Dyn none = {nullptr, 0.0f, 0.0f, 0.0f};
+  return a0_append_launch(h, new_frames, new_frame_pos, n_new, rec_meta, m, none, (cudaStream_t)stream_);
 }
 
 // ------------------------------------------------------------------------------------------------

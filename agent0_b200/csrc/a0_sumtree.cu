@@ -295,11 +295,21 @@ extern "C" int a0_pt_rng_seek(a0_replay_t* h, uint64_t call, a0_stream_t stream_
 // ------------------------------------------------------------------------------------------------
 constexpr int K2B_THREADS = 1024;
 
+// Optional copy of the update's inputs for the host (a0_pt_update_report): the per-sample losses and
+// indices are what BaseLearner.train hands back on the CPU (agent.py:163-169); writing them from the
+// kernel that reads them anyway -- plain stores into mapped page-locked host memory -- replaces two
+// device-to-host copies on the stream.
+struct A0Report {
+  int64_t* idx;
+  float* loss;
+};
+
+
 __global__ void __launch_bounds__(K2B_THREADS)
 a0_k2b_write(float* __restrict__ tree, int64_t P, int32_t chunk_log, int64_t N, const int64_t* __restrict__ idx64,
              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
              float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
-             int32_t* __restrict__ dirty) {
+             int32_t* __restrict__ dirty, const A0Report rep) {
   __shared__ float red[K2B_THREADS / 32];
   A0_PDL_PROLOGUE();
   const int tid = threadIdx.x;
@@ -311,6 +321,7 @@ a0_k2b_write(float* __restrict__ tree, int64_t P, int32_t chunk_log, int64_t N, 
   float local_max = 0.0f;
   for (int k = tid; k < count; k += K2B_THREADS) {          // claim
     const int64_t pos = position(k);
+    if (rep.idx) { rep.idx[k] = pos; rep.loss[k] = vals[k]; }
     if (pos < 0 || pos >= N) continue;
     atomicMax(winner + pos, k);
     if (mode == 0) local_max = fmaxf(local_max, vals[k]);
@@ -464,16 +475,16 @@ __device__ __forceinline__ void a0_climb_all(float* __restrict__ tree, int64_t P
   }
 }
 
+// `cta` of `nctas` CTAs (one cluster when nctas > 1) run this body; the caller has executed the PDL prologue.
 template <int K2P_LEVELS>
-__global__ void __launch_bounds__(K2P_THREADS)
-a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
-             const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
-             float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
-             int32_t* __restrict__ dirty, int32_t chunk_log) {
-  A0_PDL_PROLOGUE();
-  const bool single = gridDim.x == 1;
-  const int gtid = blockIdx.x * K2P_THREADS + threadIdx.x;
-  const int gstride = gridDim.x * K2P_THREADS;
+__device__ __forceinline__ void
+a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
+              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+              float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
+              int32_t* __restrict__ dirty, int32_t chunk_log, const int cta, const int nctas, const A0Report rep) {
+  const bool single = nctas == 1;
+  const int gtid = cta * K2P_THREADS + threadIdx.x;
+  const int gstride = nctas * K2P_THREADS;
   const float maxp_in = __ldcg(max_p);
   // this thread's (at most K2P_PER_THREAD) indices, kept in registers for all phases
   int64_t pos[K2P_PER_THREAD];
@@ -490,6 +501,7 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
       bool set = true;
       if (mode == 1) { const int32_t q = idx32[k]; set = q >= 0; p = set ? q : ~q; }
       else p = idx64[k];
+      if (rep.idx) { rep.idx[k] = p; rep.loss[k] = vals[k]; }
       if (p >= 0 && p < N) {
         pos[s] = p;
         if (mode == 0) val[s] = vals[k];
@@ -554,7 +566,7 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
     a0_cluster_sync(single);
   }
   // ---- dense part: CTA 0 rebuilds levels top-1 .. 0 from the 2^top nodes of level `top` -----------
-  if (blockIdx.x != 0 || top == 0) return;
+  if (cta != 0 || top == 0) return;
   __shared__ float buf[2][1 << K2P_TOP];
   const int n = 1 << top;
   for (int i = threadIdx.x; i < n; i += K2P_THREADS) buf[0][i] = __ldcg(tree + n + i);
@@ -572,9 +584,61 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
   }
 }
 
+template <int K2P_LEVELS>
+__global__ void __launch_bounds__(K2P_THREADS)
+a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
+             const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+             float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
+             int32_t* __restrict__ dirty, int32_t chunk_log, const A0Report rep) {
+  A0_PDL_PROLOGUE();
+  a0_paths_body<K2P_LEVELS>(tree, P, D, N, idx64, idx32, vals, count, mode, alpha, eps, max_p, winner, dirty, chunk_log,
+                            (int)blockIdx.x, (int)gridDim.x, rep);
+}
+
+// A small ingest in ONE launch: CTA 0 applies the marks to the tree (the single-CTA path climb above),
+// CTAs 1..n_new copy one new frame each, the rest scatter the record metadata (K1).  The two halves
+// touch disjoint state (tree / winner / max_p vs frames / records), so they need no ordering inside
+// the launch; everything that samples runs after it in stream order.  Thread 0 also publishes the
+// sampler's dynamic scalars when asked to.
+constexpr int K1M_MAX_MARKS = K2P_THREADS * K2P_PER_THREAD;     // what one CTA holds in registers
+constexpr int K1M_MAX_FRAMES = 2048;                            // larger appends: K1's own 128-thread CTAs
+__global__ void __launch_bounds__(K2P_THREADS)
+a0_k1_append_mark(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int32_t* __restrict__ marks,
+                  int32_t n_marks, float alpha, float* __restrict__ max_p, int32_t* __restrict__ winner,
+                  uint8_t* __restrict__ frames, int32_t F, int64_t NF, const uint8_t* __restrict__ staged,
+                  const int32_t* __restrict__ new_pos, int32_t n_new, int32_t* __restrict__ rec_slots,
+                  A0RecInfo* __restrict__ rec_info, const int32_t* __restrict__ meta, int32_t m, const A0Dyn dyn) {
+  A0_PDL_PROLOGUE();
+  if (blockIdx.x == 0) {
+    if (dyn.dyn && threadIdx.x == 0) { dyn.dyn[0] = dyn.top; dyn.dyn[1] = dyn.beta; dyn.dyn[2] = dyn.sum_offset; }
+    const A0Report none = {nullptr, nullptr};
+    a0_paths_body<K2P_LEVELS_DEFAULT>(tree, P, D, N, nullptr, marks, nullptr, n_marks, 1, alpha, 0.0f, max_p, winner,
+                                      nullptr, 0, 0, 1, none);
+    return;
+  }
+  const int blk = (int)blockIdx.x - 1;
+  if (blk < n_new) {
+    a0_k1_copy_frame(frames, F, NF, staged, new_pos, blk, threadIdx.x, K2P_THREADS);
+    return;
+  }
+  const int r = (blk - n_new) * K2P_THREADS + threadIdx.x;
+  if (r < m) a0_k1_write_record(rec_slots, rec_info, N, meta, r);
+}
+
+int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, float alpha, const uint8_t* new_frames,
+                          const int32_t* new_frame_pos, int32_t n_new, const int32_t* rec_meta, int32_t m,
+                          const A0Dyn& dyn, cudaStream_t stream) {
+  if (n_marks <= 0 || n_marks > K1M_MAX_MARKS || n_new > K1M_MAX_FRAMES) return A0_NOFIT;
+  const int blocks = 1 + n_new + (m + K2P_THREADS - 1) / K2P_THREADS;
+  A0_LAUNCH(a0_k1_append_mark, (unsigned)blocks, K2P_THREADS, 0, stream, 1, A0_PDL_K1, h->tree, h->P, h->D, h->N, marks, n_marks,
+            alpha, h->max_p, h->winner, h->frames, h->F, h->NF, new_frames, new_frame_pos, n_new, h->rec_slots, h->rec_info,
+            rec_meta, m, dyn);
+  return A0_OK;
+}
+
 static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
                            int32_t count, int32_t mode, float alpha, float eps, cudaStream_t stream,
-                           int32_t* dirty = nullptr, int32_t chunk_log = 0) {
+                           const A0Report& rep, int32_t* dirty = nullptr, int32_t chunk_log = 0) {
   int ctas = (count + K2P_THREADS - 1) / K2P_THREADS;
   ctas = ctas < 1 ? 1 : (ctas > K2P_CLUSTER ? K2P_CLUSTER : ctas);
   if (ctas > 1 && (ctas & (ctas - 1))) {            // cluster sizes: powers of two
@@ -584,15 +648,16 @@ static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* 
   }
   if (a0_option_k2b_levels() == 4)
     A0_LAUNCH(a0_k2b_paths<4>, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32,
-              vals, count, mode, alpha, eps, h->max_p, h->winner, dirty, chunk_log);
+              vals, count, mode, alpha, eps, h->max_p, h->winner, dirty, chunk_log, rep);
   else
     A0_LAUNCH(a0_k2b_paths<3>, (unsigned)ctas, K2P_THREADS, 0, stream, (unsigned)ctas, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32,
-              vals, count, mode, alpha, eps, h->max_p, h->winner, dirty, chunk_log);
+              vals, count, mode, alpha, eps, h->max_p, h->winner, dirty, chunk_log, rep);
   return A0_OK;
 }
 
 static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
-                            int32_t count, int32_t mode, float alpha, float eps, a0_stream_t stream_) {
+                            int32_t count, int32_t mode, float alpha, float eps, a0_stream_t stream_,
+                            const A0Report rep = {nullptr, nullptr}) {
   if (count == 0) return A0_OK;
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -603,13 +668,13 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
   // writes the leaves (claim / write / release, two cluster barriers) and the chunk rebuild runs on
   // all SMs -- measured 29 -> see DESIGN.md.  More than one cluster can hold: one CTA writes.
   const bool hybrid = count >= a0_option_k2b_bulk_min() && (int64_t)count >= 4 * chunks;
-  if (count <= K2P_MAX && !hybrid) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream);
+  if (count <= K2P_MAX && !hybrid) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream, rep);
   if (count <= K2P_MAX) {
-    int rc = a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream, h->dirty, chunk_log);
+    int rc = a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream, rep, h->dirty, chunk_log);
     if (rc) return rc;
   } else {
     A0_LAUNCH(a0_k2b_write, 1, K2B_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->P, chunk_log, h->N, idx64, idx32, vals, count, mode, alpha,
-              eps, h->max_p, h->winner, h->dirty);
+              eps, h->max_p, h->winner, h->dirty, rep);
   }
   A0_LAUNCH(a0_k2b_rebuild, (unsigned)chunks, K2R_THREADS, 0, stream, 1, A0_PDL_K2, h->tree, h->D, chunk_log, h->dirty,
             h->counter + A0_MAX_BATCHES);
@@ -621,6 +686,27 @@ extern "C" int a0_pt_update(a0_replay_t* h, const int64_t* idx, const float* los
   A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_update: bad handle or count");
   A0_REQUIRE(count == 0 || (idx && loss), "a0_pt_update: NULL argument");
   return a0_launch_update(h, idx, nullptr, loss, count, 0, alpha, eps, stream);
+}
+// Device-visible alias of page-locked host memory (mapped under unified addressing: what cudaHostAlloc
+// and torch's pin_memory give), for the report buffers of a0_pt_update_report.  Not a stream
+// operation; call it once per buffer, outside any graph capture.
+extern "C" int a0_host_map(const void* host_ptr, void** dev_ptr_out) {
+  A0_REQUIRE(host_ptr && dev_ptr_out, "a0_host_map: NULL argument");
+  cudaPointerAttributes at;
+  A0_CUDA(cudaPointerGetAttributes(&at, host_ptr));
+  A0_REQUIRE(at.type != cudaMemoryTypeUnregistered && at.devicePointer != nullptr,
+             "a0_host_map: pageable host memory; the buffer must be page-locked (cudaHostAlloc / pin_memory)");
+  *dev_ptr_out = at.devicePointer;
+  return A0_OK;
+}
+
+extern "C" int a0_pt_update_report(a0_replay_t* h, const int64_t* idx, const float* loss, int32_t count, float alpha,
+                                   float eps, int64_t* idx_report, float* loss_report, a0_stream_t stream) {
+  A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_update_report: bad handle or count");
+  A0_REQUIRE(count == 0 || (idx && loss), "a0_pt_update_report: NULL argument");
+  A0_REQUIRE(idx_report && loss_report, "a0_pt_update_report: NULL report buffer (a0_pt_update reports nothing)");
+  const A0Report rep = {idx_report, loss_report};
+  return a0_launch_update(h, idx, nullptr, loss, count, 0, alpha, eps, stream, rep);
 }
 extern "C" int a0_pt_mark(a0_replay_t* h, const int32_t* pos, int32_t count, float alpha, a0_stream_t stream) {
   A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_mark: bad handle or count");

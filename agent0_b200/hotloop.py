@@ -68,6 +68,9 @@ class ReplayTargetLoop:
         self._k4 = None
         self._k4_all = None
         self.graph = None
+        self.report = []          # pinned host (indices, losses) pairs filled by K2b: bind_report()
+        self._report_dev = []
+        self.graphs = []          # one captured step per report slot
 
     # ------------------------------------------------------------------ single launches
     def _st(self):
@@ -148,14 +151,34 @@ class ReplayTargetLoop:
         if rc:
             _lib.check(rc, "a0_loss_" + self.algo)
 
-    def update(self):
-        """K2b: priority[idx] = (loss+eps)^alpha for all L batches, max_p (replay.py:55-59)."""
+    def bind_report(self, slots=2):
+        """Page-locked host buffers for the step's result -- what ``BaseLearner.train`` returns on the
+        CPU (agent.py:163-169: per-sample losses and indices).  With a report slot, K2b stores them
+        straight into host memory (a0_pt_update_report) instead of two device-to-host copies being
+        queued behind the step; ``slots`` buffers let the host read step s-1 while step s runs.
+        Returns the list of (indices i64[L*B], losses f32[L*B]) pinned CPU tensor pairs."""
+        self.report = [(torch.empty(self.total, dtype=torch.int64).pin_memory(),
+                        torch.empty(self.total, dtype=torch.float32).pin_memory()) for _ in range(int(slots))]
+        self._report_dev = [(_lib.host_map(i), _lib.host_map(l)) for i, l in self.report]
+        return self.report
+
+    def update(self, slot=None):
+        """K2b: priority[idx] = (loss+eps)^alpha for all L batches, max_p (replay.py:55-59).  ``slot``:
+        also hand indices and losses to the host through report buffer ``slot`` (bind_report)."""
+        if self.per and slot is not None:
+            ri, rl = self._report_dev[slot]
+            _lib.check(self.lib.a0_pt_update_report(self.rp.h, self.idx.data_ptr(), self.loss.data_ptr(), self.total, self.alpha,
+                                                    self.eps, ri, rl, self._st()), "a0_pt_update_report")
+            return
         if self.per:
             _lib.check(self.lib.a0_pt_update(self.rp.h, self.idx.data_ptr(), self.loss.data_ptr(), self.total, self.alpha,
                                              self.eps, self._st()), "a0_pt_update")
+        if slot is not None:          # uniform replay has no K2b launch to carry the report
+            self.report[slot][0].copy_(self.idx, non_blocking=True)
+            self.report[slot][1].copy_(self.loss, non_blocking=True)
 
     # ------------------------------------------------------------------ whole steps
-    def step(self, fused_k4=False):
+    def step(self, fused_k4=False, slot=None):
         if self.rng_seed is None:
             self.u.uniform_()
         self.sample()
@@ -165,7 +188,7 @@ class ReplayTargetLoop:
         else:
             for k in range(self.L):
                 self.target_loss(k)
-        self.update()
+        self.update(slot)
 
     def capture(self, warm=3, fused_k4=False):
         """Warm up, then capture one step into a CUDA graph (returned; also kept as ``self.graph``)."""
@@ -179,10 +202,31 @@ class ReplayTargetLoop:
         self.graph = g
         return g
 
-    def run(self):
-        """One step: publishes top/beta, then replays the captured graph (or issues the launches)."""
+    def capture_reporting(self, warm=3):
+        """One captured step per report slot (bind_report first): ``run(slot=s)`` replays the graph whose
+        K2b writes the result into host buffer ``s``."""
+        assert self.report, "bind_report() first"
         self.rp.push_dynamic()
-        if self.graph is not None:
+        for _ in range(warm):
+            self.step(slot=0)
+        torch.cuda.synchronize(self.dev)
+        self.graphs = []
+        for s in range(len(self.report)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step(slot=s)
+            self.graphs.append(g)
+        return self.graphs
+
+    def run(self, slot=None, publish=True):
+        """One step: publishes top/beta (``publish=False`` when the ingest already did:
+        ``append_steps(publish_dynamic=True)``), then replays the captured graph (or issues the
+        launches).  ``slot``: the report buffer this step's result goes to."""
+        if publish:
+            self.rp.push_dynamic()
+        if slot is not None and self.graphs:
+            self.graphs[slot].replay()
+        elif slot is None and self.graph is not None:
             self.graph.replay()
         else:
-            self.step()
+            self.step(slot=slot)

@@ -252,16 +252,20 @@ class ReplayDataset:
         keep, ptr, flags = self._frames_arg(stacks, 4 * k)
         self._ingest_plan(plan, ptr, None, flags)
 
-    def append_steps(self, streams, n_new, new_frames, action, reward, done, pinned_stable=False, copy_stream=False):
+    def append_steps(self, streams, n_new, new_frames, action, reward, done, pinned_stable=False, copy_stream=False,
+                     publish_dynamic=False):
         """Native ingest.  For each transition (in order) the observation is the stream's current
         stack and the next observation is that stack shifted by ``n_new`` (0..4) new frames taken,
         in order, from ``new_frames`` (u8 [sum(n_new), H, W]: host array, CPU tensor or CUDA
         tensor).  ``done`` follows the reference's rule (terminal | life_loss) & ~truncated
-        (agent.py:57-62).  One C call: index update, staging, H2D copy, K2b marks and K1 append.
+        (agent.py:57-62).  One C call: index update, staging, H2D copy, K2b marks and K1 append
+        (one launch for a step-sized append).
         ``pinned_stable=True`` lets a page-locked CPU tensor be copied by DMA straight from the
         caller's buffer, which must then stay untouched until the current stream has passed.
         ``copy_stream=True`` issues the H2D DMA on the shard's own copy stream (the current stream
-        waits for it), so it overlaps the kernels the current stream is still running."""
+        waits for it), so it overlaps the kernels the current stream is still running.
+        ``publish_dynamic=True``: the append launch also publishes top / beta / sum_offset for
+        ``sample(dynamic=True)`` -- what a separate ``push_dynamic()`` launch would do."""
         streams = np.ascontiguousarray(streams, dtype=np.int64)
         n_new = np.ascontiguousarray(n_new, dtype=np.int64)
         action = np.ascontiguousarray(action, dtype=np.int64)
@@ -271,12 +275,18 @@ class ReplayDataset:
         keep, ptr, flags = self._frames_arg(new_frames, int(n_new.sum()), pinned_stable)
         if copy_stream and not (flags & _lib.INGEST_FRAMES_ON_DEVICE):
             flags |= _lib.INGEST_COPY_STREAM
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.a0_rb_ingest_steps(
-                self.h, self.index.h, streams.ctypes.data, n_new.ctypes.data, ptr, flags, action.ctypes.data,
-                reward.ctypes.data, done.ctypes.data, m, self.alpha, _lib.stream_ptr(self.device)), "a0_rb_ingest_steps")
         if self.prioritize:
-            self.beta = self.beta_schedule(m)
+            self.beta = self.beta_schedule(m)         # replay.py:53; the C call below does not read it
+        with torch.cuda.device(self.device):
+            if publish_dynamic:
+                _lib.check(self.lib.a0_rb_ingest_steps_dyn(
+                    self.h, self.index.h, streams.ctypes.data, n_new.ctypes.data, ptr, flags, action.ctypes.data,
+                    reward.ctypes.data, done.ctypes.data, m, self.alpha, float(self.beta), 1 if self.compat_sum else 0,
+                    _lib.stream_ptr(self.device)), "a0_rb_ingest_steps_dyn")
+            else:
+                _lib.check(self.lib.a0_rb_ingest_steps(
+                    self.h, self.index.h, streams.ctypes.data, n_new.ctypes.data, ptr, flags, action.ctypes.data,
+                    reward.ctypes.data, done.ctypes.data, m, self.alpha, _lib.stream_ptr(self.device)), "a0_rb_ingest_steps")
 
     def append_vector_step(self, obs, action, reward, done, obs_next, streams=None):
         """Convenience for a gymnasium-style vector step: derives ``n_new`` by comparing stacks."""

@@ -250,14 +250,18 @@ def time_kernel(fn, reps, torch):
     return e0.elapsed_time(e1) / 1e3 / (rounds * INNER)
 
 
-def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True):
+def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True, fused=True):
     """The headline end-to-end number: one Trainer.step-shaped pass driven through the C ABI with
     HOST buffers.  Per step: new transitions (replay ratio 8 samples per insert) are ingested from
-    page-locked host memory (a0_rb_ingest_steps: index update, H2D DMA, K2b marks, K1) and the
-    shard's top/beta are published to the device (a0_rb_set_dynamic); the L batches are drawn,
+    page-locked host memory (a0_rb_ingest_steps_dyn: index update, H2D DMA, K2b marks + K1 in one
+    launch, which also publishes the shard's top/beta to the device); the L batches are drawn,
     gathered, run through K4 and written back to the tree by replaying ONE CUDA graph of the
     C-ABI launches (``graph=False``: the same launches issued eagerly); the per-sample losses and
-    indices are copied back to pinned host memory and read by the host.
+    indices reach page-locked host memory -- stored there by the K2b launch that reads them
+    (a0_pt_update_report) -- and are read by the host.
+
+    ``fused=False`` is the same loop with the separate pieces: a0_rb_ingest_steps, an
+    a0_rb_set_dynamic launch, and two device-to-host copies queued behind the graph.
 
     depth=1: the host waits for the step's losses before it starts the next step.  depth=2: the
     result buffers are double-buffered -- the host reads step s-1's losses while the device runs
@@ -276,13 +280,23 @@ def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True):
     ones_new = np.ones(new_per_step, dtype=np.int64)
     actions = rng.randint(0, 4, new_per_step).astype(np.int64)
     zr, zd = np.zeros(new_per_step), np.zeros(new_per_step, dtype=bool)
-    loss_host = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(depth)]
-    idx_host = [torch.empty(total, dtype=torch.int64).pin_memory() for _ in range(depth)]
+    if fused:
+        rep = hp.bind_report(depth)
+        idx_host, loss_host = [r[0] for r in rep], [r[1] for r in rep]
+    else:
+        loss_host = [torch.empty(total, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        idx_host = [torch.empty(total, dtype=torch.int64).pin_memory() for _ in range(depth)]
     done_ev = [torch.cuda.Event() for _ in range(depth)]
     h2d = new_per_step * (F_BYTES + 14 * 4 + 4 + 4)
     d2h = total * (4 + 8)
 
-    g = capture_step(hp, torch) if graph else None
+    g = None
+    if graph and fused:
+        hp.capture_reporting()
+    elif graph:
+        g = capture_step(hp, torch)
+    else:
+        hp.graphs, hp.graph = [], None
     acc = [0.0, 0]
 
     def consume(slot):
@@ -296,14 +310,17 @@ def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True):
             if s >= depth:
                 consume(slot)                       # step s-depth: its buffers are reused below
             rp.append_steps(streams, ones_new, host_frames[s % (depth + 1)], actions, zr, zd, pinned_stable=True,
-                            copy_stream=copy_stream)
-            rp.push_dynamic()
-            if g is not None:
-                g.replay()
+                            copy_stream=copy_stream, publish_dynamic=fused)
+            if fused:
+                hp.run(slot=slot, publish=False)
             else:
-                hp.step()
-            loss_host[slot].copy_(hp.loss, non_blocking=True)
-            idx_host[slot].copy_(hp.idx, non_blocking=True)
+                rp.push_dynamic()
+                if g is not None:
+                    g.replay()
+                else:
+                    hp.step()
+                loss_host[slot].copy_(hp.loss, non_blocking=True)
+                idx_host[slot].copy_(hp.idx, non_blocking=True)
             done_ev[slot].record()
         for s in range(max(0, n - depth), n):
             consume(s % depth)
@@ -315,6 +332,9 @@ def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     assert all(torch.isfinite(x).all() for x in loss_host) and acc[1] < rp.size and np.isfinite(acc[0])
+    if fused:       # what reached the host is what the device holds
+        last = (steps - 1) % depth
+        assert torch.equal(loss_host[last], hp.loss.cpu()) and torch.equal(idx_host[last], hp.idx.cpu())
     return total * steps / dt, h2d, d2h
 
 
@@ -447,11 +467,13 @@ def run_ours(args):
     barrier()
     e2e_eager, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=False, depth=2, copy_stream=True)
     barrier()
+    e2e_sep, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph, depth=2, copy_stream=True, fused=False)
+    barrier()
     e2e_py, _, _ = e2e_loop(rp, wl, L, A, max(10, args.steps // 4), 3, torch)
-    t = torch.tensor([e2e_v, e2e_py, e2e_eager, e2e_sync], device="cuda", dtype=torch.float64)
+    t = torch.tensor([e2e_v, e2e_py, e2e_eager, e2e_sync, e2e_sep], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    e2e_v, e2e_py, e2e_eager, e2e_sync = (float(x) for x in t.tolist())
+    e2e_v, e2e_py, e2e_eager, e2e_sync, e2e_sep = (float(x) for x in t.tolist())
 
     extra = {}
     if world > 1:
@@ -493,9 +515,13 @@ def run_ours(args):
                        "fill_seconds": round(t_fill, 1)},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "agent0_b200 public API over the C ABI (ReplayDataset.append_steps + hotloop.ReplayTargetLoop): ingest from pinned host buffers (H2D DMA on the shard's copy stream) + one CUDA-graph "
-                            "replay of the C-ABI launches per step; losses and indices copied back to double-buffered pinned host "
-                            "memory, the host reads step s-1's result while step s runs (final drain inside the timed region)",
+                    "path": "agent0_b200 public API over the C ABI (ReplayDataset.append_steps + hotloop.ReplayTargetLoop): ingest from pinned host buffers "
+                            "(H2D DMA on the shard's copy stream; marks + append + top/beta publication in one launch) + one CUDA-graph "
+                            "replay of the C-ABI launches per step; losses and indices stored by the K2b launch into double-buffered "
+                            "mapped pinned host memory (a0_pt_update_report), the host reads step s-1's result while step s runs "
+                            "(final drain inside the timed region)",
+                    "separate_launches_value": round(e2e_sep, 1),
+                    "separate_launches_path": "same loop with a0_rb_set_dynamic as its own launch and two device-to-host copies queued behind the graph",
                     "sync_every_step_value": round(e2e_sync, 1),
                     "sync_every_step_path": "same, but the host waits for each step's losses before starting the next (depth 1)",
                     "cabi_eager_value": round(e2e_eager, 1),

@@ -20,6 +20,7 @@
  *   agent0/deepq/agent.py:129-135  BaseLearner.train: /255 + split -> a0_rb_gather_f32
  *   agent0/deepq/trainer.py:91-94  IS weights in Trainer.step      -> a0_pt_sample (epilogue)
  *   agent0/deepq/replay.py:55-59   ReplayDataset.update_priority   -> a0_pt_update
+ *   agent0/deepq/agent.py:163-169  BaseLearner.train: loss/indices .cpu() -> a0_pt_update_report
  *   agent0/deepq/agent.py:173-190  DQNLearner.train_step           -> a0_loss_dqn
  *   agent0/deepq/agent.py:194-215  MDQNLearner.train_step          -> a0_loss_mdqn
  *   agent0/deepq/agent.py:219-269  C51Learner.train_step           -> a0_loss_c51
@@ -66,6 +67,10 @@ const char* a0_last_error(void);
  * one cluster launch and rebuild the touched chunks on all SMs in a second one, instead of the
  * single-cluster path climb.  Same tree either way.                                              */
 #define A0_OPT_K2B_BULK_MIN 3
+/* A0_OPT_FUSED_INGEST (default 1; A0_FUSED_INGEST in the environment): a step-sized ingest (at most
+ * 2048 marks and 2048 new frames) applies its marks and its append in ONE launch instead of
+ * a0_pt_mark followed by a0_rb_append.  Same shard state either way.                              */
+#define A0_OPT_FUSED_INGEST 4
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------
@@ -172,6 +177,15 @@ int a0_rb_ingest_steps(a0_replay_t* h, a0_index_t* ix, const int64_t* stream, co
                        const uint8_t* new_frames, int32_t flags, const int64_t* action,
                        const double* reward, const uint8_t* done, int32_t m, float alpha,
                        a0_stream_t cuda_stream);
+/* The same ingest, which also publishes the sampler's device-resident scalars (a0_rb_set_dynamic:
+ * top = sampleable records after this append, beta, sum_offset = compat_sum ? capacity - top : 0)
+ * from inside its append launch: no separate launch per Trainer.step for a graph-captured draw.
+ * beta is the value ReplayDataset.extend leaves in self.beta (replay.py:53).  m == 0 only publishes. */
+int a0_rb_ingest_steps_dyn(a0_replay_t* h, a0_index_t* ix, const int64_t* stream,
+                           const int64_t* n_new, const uint8_t* new_frames, int32_t flags,
+                           const int64_t* action, const double* reward, const uint8_t* done,
+                           int32_t m, float alpha, float beta, int32_t compat_sum,
+                           a0_stream_t cuda_stream);
 
 /* ---- K2b: sum-tree leaf writes ---------------------------------------------------------------------
  * a0_pt_mark: pos[k] >= 0 -> leaf = max_p^alpha (a newly sampleable record, replay.py:52);
@@ -187,6 +201,19 @@ int a0_pt_update(a0_replay_t* h, const int64_t* idx /* dev */, const float* loss
                  int32_t count, float alpha, float eps, a0_stream_t stream);
 int a0_pt_set(a0_replay_t* h, const int64_t* idx /* dev */, const float* value /* dev */,
               int32_t count, a0_stream_t stream);
+/* a0_pt_update that also hands the step's result to the host: idx[k] and loss[k] are stored to
+ * idx_report / loss_report by the kernel that reads them anyway.  With report buffers in mapped
+ * page-locked host memory (device-visible aliases from a0_host_map) this is the `.cpu()` of
+ * BaseLearner.train's return value (agent.py:163-169: q_loss and indices on the CPU) without two
+ * device-to-host copies on the stream; the data is valid on the host once an event recorded after
+ * the call has completed.  Device memory works too.                                             */
+int a0_pt_update_report(a0_replay_t* h, const int64_t* idx /* dev */, const float* loss /* dev */,
+                        int32_t count, float alpha, float eps, int64_t* idx_report /* dev-visible */,
+                        float* loss_report /* dev-visible */, a0_stream_t stream);
+/* Device-visible alias of page-locked host memory (cudaHostAlloc / cudaHostRegister with mapping,
+ * torch's pin_memory); fails for pageable memory.  Not a stream operation: call it once per
+ * buffer, outside CUDA-graph capture.                                                          */
+int a0_host_map(const void* host_ptr, void** dev_ptr_out);
 
 /* ---- K2a: batched stratified prioritized draws + IS weights ------------------------------------------
  * total = k_batches * batch draws; draw j of a batch uses t = ((j + u)/batch) * root and descends

@@ -290,3 +290,57 @@ def test_k2b_schedules_build_the_same_tree():
         lib.a0_set_option(3, 2048)
     assert torch.equal(trees[0], trees[1]) and torch.equal(trees[0], trees[2])
     assert lib.a0_set_option(3, 0) == -1
+
+
+def _shard_state(rp):
+    """Every piece of device state an ingest touches, as host arrays."""
+    lib = _lib.load()
+    dev = rp.device
+    slots = _lib.device_view(lib.a0_rb_ptr(rp.h, _lib.PTR_REC_SLOTS), (rp.size, 8), "<i4", dev)
+    info = _lib.device_view(lib.a0_rb_ptr(rp.h, _lib.PTR_REC_INFO), (rp.size, 4), "<i4", dev)
+    scal = _lib.device_view(lib.a0_rb_ptr(rp.h, _lib.PTR_MAX_P), (19,), "<f4", dev)      # max_p, ..., dyn at [16..18]
+    torch.cuda.synchronize()
+    return [_np(rp.frames), _np(slots), _np(info), _np(rp.tree), _np(scal)]
+
+
+@pytest.mark.parametrize("compat", [False, True])
+def test_fused_ingest_launch_and_dynamic_publication_equal_the_separate_launches(compat):
+    """A step-sized ingest applies marks + append (+ top/beta/sum_offset publication) in ONE launch
+    (a0_k1_append_mark); with A0_OPT_FUSED_INGEST off and push_dynamic() as its own launch the shard
+    must end up bit-identical: frames, records, links, the whole tree, max_p and the dyn scalars --
+    on a ring smaller than the stream (evictions every step) and with n_new in {0, 1, 4}."""
+    lib = _lib.load()
+    E, T, n = 4, 70, 3
+    obs, n_new, act, rew, done = _stream(E, T, (84, 84), seed=31, p_new4=0.1, p_static=0.1)
+    states = []
+    try:
+        for fused in (1, 0):
+            assert lib.a0_set_option(4, fused) == 0
+            rp = _replay(96, n, E, frame_capacity=400, age_limit=32, compat_sum=compat)
+            rp.frames.zero_()                           # cudaMalloc'd, never-written slots would differ
+            rp.reset_streams(np.arange(E), obs[0])
+            for k in range(T):
+                new = np.concatenate([obs[k + 1][e, 4 - n_new[k][e]:] for e in range(E)]) if n_new[k].sum() else \
+                    np.zeros((0, 84, 84), dtype=np.uint8)
+                if k % 9 == 0:                          # some losses, so that max_p moves between appends
+                    live = torch.nonzero(rp.priority.leaves() > 0).view(-1)[:5]
+                    rp.update_priority(live, torch.full((len(live),), 1.5 + k, device="cuda"))
+                rp.append_steps(np.arange(E), n_new[k], new, act[k], rew[k], done[k], publish_dynamic=bool(fused))
+                if not fused:
+                    rp.push_dynamic()
+            # an empty append still publishes
+            z = np.zeros(0, dtype=np.int64)
+            rp.beta = 0.77
+            rp.beta_schedule = lambda m: 0.77
+            rp.append_steps(z, z, np.zeros((0, 84, 84), dtype=np.uint8), z, z.astype(np.float64), z.astype(bool),
+                            publish_dynamic=bool(fused))
+            if not fused:
+                rp.push_dynamic()
+            assert rp.index.tail_q > 0
+            states.append(_shard_state(rp))
+            assert states[-1][4][16] == float(rp.index.top) and states[-1][4][17] == np.float32(0.77)
+            assert states[-1][4][18] == (float(rp.size - rp.index.top) if compat else 0.0)
+    finally:
+        lib.a0_set_option(4, 1)
+    for a, b in zip(*states):
+        assert np.array_equal(a, b)

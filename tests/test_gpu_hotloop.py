@@ -142,3 +142,85 @@ def test_prebound_loop_step_capture_and_single_launch_k4():
     per_batch = (loop.loss.clone(), loop.grad.clone())
     loop.target_loss_all()
     assert torch.equal(loop.loss, per_batch[0]) and torch.equal(loop.grad, per_batch[1])
+
+
+@pytest.mark.parametrize("count,bulk_min", [(48, 2048), (640, 2048), (5000, 1), (5000, 1 << 30), (20000, 2048)])
+def test_update_report_hands_the_result_to_mapped_host_memory(count, bulk_min):
+    """a0_pt_update_report = a0_pt_update + the step's (indices, losses) stored by the same kernel into
+    page-locked host memory: same tree and max_p as the plain update under every K2b schedule
+    (one CTA, cluster climb, cluster write + rebuild, one-CTA bulk write), host buffers equal to the
+    device inputs once the stream has passed -- duplicates and out-of-range indices included."""
+    from agent0_b200 import _lib
+    from agent0_b200.replay import ReplayDataset
+    lib = _lib.load()
+    N = 30000
+    cfg = make_config("dqn", per=True, n_step=1, batch_size=8, replay_size=N, num_envs=4)
+    rng = np.random.RandomState(count)
+    ids = rng.randint(0, N, count).astype(np.int64)
+    ids[-3:] = ids[0]
+    ids[1] = N + 5                                   # skipped by the update, still reported as given
+    loss = np.abs(rng.randn(count)).astype(np.float32) * 3
+    trees = []
+    try:
+        assert lib.a0_set_option(3, bulk_min) == 0
+        for report in (False, True):
+            rp = ReplayDataset(cfg, native_nstep=True)
+            rp.set_priorities(torch.arange(N), torch.as_tensor((np.arange(N) % 13 + 1).astype(np.float32)))
+            d_ids, d_loss = torch.as_tensor(ids).cuda(), torch.as_tensor(loss).cuda()
+            if report:
+                h_ids = torch.full((count,), -7, dtype=torch.int64).pin_memory()
+                h_loss = torch.full((count,), -7.0, dtype=torch.float32).pin_memory()
+                _lib.check(lib.a0_pt_update_report(rp.h, d_ids.data_ptr(), d_loss.data_ptr(), count, rp.alpha, rp.eps,
+                                                   _lib.host_map(h_ids), _lib.host_map(h_loss), _lib.stream_ptr(rp.device)),
+                           "a0_pt_update_report")
+                ev = torch.cuda.Event()
+                ev.record()
+                ev.synchronize()
+                assert np.array_equal(h_ids.numpy(), ids) and np.array_equal(h_loss.numpy(), loss)
+            else:
+                rp.update_priority(d_ids, d_loss)
+            torch.cuda.synchronize()
+            trees.append((rp.tree.clone(), float(rp.max_p_tensor)))
+    finally:
+        lib.a0_set_option(3, 2048)
+    assert torch.equal(trees[0][0], trees[1][0]) and trees[0][1] == trees[1][1]
+    with pytest.raises(ValueError):
+        _lib.host_map(torch.empty(4))                # a pageable tensor
+    import ctypes as C
+    pageable, out = np.zeros(16, dtype=np.float32), C.c_void_p()
+    assert lib.a0_host_map(pageable.ctypes.data, C.byref(out)) != 0 and b"page" in lib.a0_last_error()
+
+
+def test_reporting_graphs_with_ingest_published_scalars_equal_the_plain_loop():
+    """The end-to-end form of the loop (bench.py's `e2e`): the ingest publishes top/beta from its own
+    launch, one captured graph per report slot stores losses + indices straight into pinned host
+    memory.  Against the plain loop (push_dynamic launch, results read from the device) on a twin
+    shard with the same sampler seed: same draws, losses, trees, step after step, and the host
+    buffers hold exactly what the device computed."""
+    from agent0_b200.hotloop import ReplayTargetLoop
+    T = B * L
+    o = _outputs("c51", T)
+    rp_a, rp_b = _shard("c51"), _shard("c51")
+    la = ReplayTargetLoop(rp_a, "c51", B, L, A, o, n_step=3, rng_seed=5)
+    lb = ReplayTargetLoop(rp_b, "c51", B, L, A, o, n_step=3, rng_seed=5)
+    la.capture()
+    rep = lb.bind_report(2)
+    lb.capture_reporting()
+    rp_a.rng_seek(0); rp_b.rng_seek(0)
+    E = 8
+    g = torch.Generator().manual_seed(2)
+    for s in range(5):
+        new = torch.randint(0, 256, (E, 84 * 84), dtype=torch.uint8, generator=g).pin_memory()
+        args = (np.arange(E), np.ones(E, dtype=np.int64), new, np.arange(E) % A, np.ones(E) * s, np.zeros(E, dtype=bool))
+        rp_a.append_steps(*args)
+        la.run()
+        rp_b.append_steps(*args, pinned_stable=True, copy_stream=True, publish_dynamic=True)
+        lb.run(slot=s % 2, publish=False)
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()
+        assert torch.equal(rep[s % 2][0], lb.idx.cpu()) and torch.equal(rep[s % 2][1], lb.loss.cpu())
+        torch.cuda.synchronize()
+        assert torch.equal(la.idx, lb.idx) and torch.equal(la.loss, lb.loss) and torch.equal(la.w, lb.w)
+        assert torch.equal(rp_a.tree, rp_b.tree)
+    assert len({int(rep[0][0][0]), int(rep[1][0][0])}) == 2 or not torch.equal(rep[0][0], rep[1][0])
