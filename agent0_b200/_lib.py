@@ -73,6 +73,7 @@ SIGNATURES = {
     "a0_pt_rng_seek": (_i32, [_vp, C.c_uint64, _vp]),
     "a0_rb_gather": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "a0_rb_gather_f32": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "a0_rb_gather_bf16": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "a0_loss_dqn": (_i32, [C.POINTER(LossCommon), _vp, _vp, _vp, _vp, _vp]),
     "a0_loss_mdqn": (_i32, [C.POINTER(LossCommon), _vp, _vp, _vp, _f32, _f32, _vp, _vp]),
     "a0_loss_c51": (_i32, [C.POINTER(LossCommon), _vp, _vp, _vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp]),

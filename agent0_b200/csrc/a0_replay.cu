@@ -694,8 +694,64 @@ __device__ __forceinline__ float a0_norm255(float x, int mode) {
   const float e = __fmaf_rn(-q, 255.0f, x);
   return __fmaf_rn(e, r, q);
 }
+// byte -> float without the conversion pipe: 0x4B000000 | byte is 2^23 + byte exactly
+__device__ __forceinline__ float a0_byte_norm(uint32_t byte, int mode) {
+  return a0_norm255(__uint_as_float(0x4B000000u | byte) - 8388608.0f, mode);
+}
+// bf16(fl32(norm(x))), round to nearest even: what .float().div(255).to(torch.bfloat16) gives.  Two
+// values per 32-bit word, low half first (little endian: element 2i in the low half).
+__device__ __forceinline__ uint32_t a0_bf16_pair(float lo, float hi) {
+  auto rne = [](float v) -> uint32_t {
+    const uint32_t u = __float_as_uint(v);               // finite, non-negative here (0..255 or 0..1)
+    return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+  };
+  return rne(lo) | (rne(hi) << 16);
+}
+
+// One group of pixels of staged frame `src` into every stack position it fills.
+//   OutT = float:    4 pixels  (one 32-bit shared-memory word)  -> one float4 (16 B) store per position
+//   OutT = uint16_t: 8 pixels  (one 64-bit shared-memory word)  -> 8 bf16 = one uint4 (16 B) store
+template <typename OutT> struct A0Conv;
+template <> struct A0Conv<float> {
+  static constexpr int PIX = 4;
+  __device__ static __forceinline__ void run(const uint8_t* src, int i, uint32_t dm, float* obs_b, float* next_b, uint32_t F,
+                                             int mode) {
+    const uint32_t px = reinterpret_cast<const uint32_t*>(src)[i];
+    float4 v;
+    v.x = a0_byte_norm(px & 0xffu, mode);
+    v.y = a0_byte_norm((px >> 8) & 0xffu, mode);
+    v.z = a0_byte_norm((px >> 16) & 0xffu, mode);
+    v.w = a0_byte_norm(px >> 24, mode);
+#pragma unroll
+    for (int j = 0; j < A0_SLOTS; ++j)
+      if (dm & (1u << j)) {
+        float* dst = (j < A0_STACK ? obs_b + (size_t)j * F : next_b + (size_t)(j - A0_STACK) * F);
+        reinterpret_cast<float4*>(dst)[i] = v;
+      }
+  }
+};
+template <> struct A0Conv<uint16_t> {
+  static constexpr int PIX = 8;
+  __device__ static __forceinline__ void run(const uint8_t* src, int i, uint32_t dm, uint16_t* obs_b, uint16_t* next_b,
+                                             uint32_t F, int mode) {
+    const uint2 px = reinterpret_cast<const uint2*>(src)[i];
+    uint4 v;
+    v.x = a0_bf16_pair(a0_byte_norm(px.x & 0xffu, mode), a0_byte_norm((px.x >> 8) & 0xffu, mode));
+    v.y = a0_bf16_pair(a0_byte_norm((px.x >> 16) & 0xffu, mode), a0_byte_norm(px.x >> 24, mode));
+    v.z = a0_bf16_pair(a0_byte_norm(px.y & 0xffu, mode), a0_byte_norm((px.y >> 8) & 0xffu, mode));
+    v.w = a0_bf16_pair(a0_byte_norm((px.y >> 16) & 0xffu, mode), a0_byte_norm(px.y >> 24, mode));
+#pragma unroll
+    for (int j = 0; j < A0_SLOTS; ++j)
+      if (dm & (1u << j)) {
+        uint16_t* dst = (j < A0_STACK ? obs_b + (size_t)j * F : next_b + (size_t)(j - A0_STACK) * F);
+        reinterpret_cast<uint4*>(dst)[i] = v;
+      }
+  }
+};
+
+template <typename OutT>
 __global__ void __launch_bounds__(K3F_THREADS)
-a0_k3_gather_f32(const A0GatherArgs g, float* __restrict__ obs_out, float* __restrict__ next_out, int norm_mode) {
+a0_k3_gather_cvt(const A0GatherArgs g, OutT* __restrict__ obs_out, OutT* __restrict__ next_out, int norm_mode) {
   extern __shared__ __align__(128) uint8_t a0_smem[];
   __shared__ __align__(8) uint64_t bars[K3_RING];
   __shared__ int32_t s_uslot[A0_SLOTS];
@@ -752,30 +808,16 @@ a0_k3_gather_f32(const A0GatherArgs g, float* __restrict__ obs_out, float* __res
   }
   __syncthreads();
   const int U = s_U;
-  const int groups = (int)(F >> 2);                       // 4 pixels -> one float4
+  const int groups = (int)(F / A0Conv<OutT>::PIX);
   const size_t stack_elems = (size_t)A0_STACK * F;
-  float* obs_b = obs_out + (size_t)b * stack_elems;
-  float* next_b = next_out + (size_t)b * stack_elems;
+  OutT* obs_b = obs_out + (size_t)b * stack_elems;
+  OutT* next_b = next_out + (size_t)b * stack_elems;
   for (int u = 0; u < U; ++u) {
     const int r = u % K3_RING;
     a0_mbar_wait(bar0 + 8 * r, (u / K3_RING) & 1);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a0_smem + (size_t)r * F);
+    const uint8_t* src = a0_smem + (size_t)r * F;
     const uint32_t dm = s_dmask[u];
-    for (int i = threadIdx.x; i < groups; i += K3F_THREADS) {
-      const uint32_t px = src[i];
-      float4 v;
-      // byte -> float without the conversion pipe: 0x4B000000 | byte is 2^23 + byte exactly
-      v.x = a0_norm255(__uint_as_float(0x4B000000u | (px & 0xffu)) - 8388608.0f, norm_mode);
-      v.y = a0_norm255(__uint_as_float(0x4B000000u | ((px >> 8) & 0xffu)) - 8388608.0f, norm_mode);
-      v.z = a0_norm255(__uint_as_float(0x4B000000u | ((px >> 16) & 0xffu)) - 8388608.0f, norm_mode);
-      v.w = a0_norm255(__uint_as_float(0x4B000000u | (px >> 24)) - 8388608.0f, norm_mode);
-#pragma unroll
-      for (int j = 0; j < A0_SLOTS; ++j)
-        if (dm & (1u << j)) {
-          float* dst = (j < A0_STACK ? obs_b + (size_t)j * F : next_b + (size_t)(j - A0_STACK) * F);
-          reinterpret_cast<float4*>(dst)[i] = v;
-        }
-    }
+    for (int i = threadIdx.x; i < groups; i += K3F_THREADS) A0Conv<OutT>::run(src, i, dm, obs_b, next_b, F, norm_mode);
     if (u + K3_RING < U) {
       __syncthreads();                                     // every thread has read buffer r
       if (threadIdx.x == 0) {
@@ -786,17 +828,17 @@ a0_k3_gather_f32(const A0GatherArgs g, float* __restrict__ obs_out, float* __res
   }
 }
 
-extern "C" int a0_rb_gather_f32(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
-                                float* obs_out, float* next_out, int32_t norm_mode, int64_t* action_out,
-                                double* reward64_out, float* reward32_out, uint8_t* done8_out, float* done32_out,
-                                int64_t* boot_out, a0_stream_t stream_) {
-  A0_REQUIRE(h != nullptr, "a0_rb_gather_f32: handle is NULL");
-  A0_REQUIRE(count >= 0, "a0_rb_gather_f32: negative count");
+template <typename OutT>
+static int a0_gather_cvt(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma, OutT* obs_out,
+                         OutT* next_out, int32_t norm_mode, int64_t* action_out, double* reward64_out, float* reward32_out,
+                         uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream_, const char* who) {
+  A0_REQUIRE(h != nullptr, "%s: handle is NULL", who);
+  A0_REQUIRE(count >= 0, "%s: negative count", who);
   if (count == 0) return A0_OK;
-  A0_REQUIRE(idx && obs_out && next_out, "a0_rb_gather_f32: idx, obs_out and next_out are required");
-  A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_gather_f32: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
-  A0_REQUIRE((((uintptr_t)obs_out | (uintptr_t)next_out) & 15) == 0, "a0_rb_gather_f32: outputs must be 16-byte aligned");
-  A0_REQUIRE(norm_mode >= 0 && norm_mode <= 2, "a0_rb_gather_f32: norm_mode %d outside [0,2]", norm_mode);
+  A0_REQUIRE(idx && obs_out && next_out, "%s: idx, obs_out and next_out are required", who);
+  A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "%s: n_step %d outside [1,%d]", who, n_step, A0_MAX_NSTEP);
+  A0_REQUIRE((((uintptr_t)obs_out | (uintptr_t)next_out) & 15) == 0, "%s: outputs must be 16-byte aligned", who);
+  A0_REQUIRE(norm_mode >= 0 && norm_mode <= 2, "%s: norm_mode %d outside [0,2]", who, norm_mode);
   A0DeviceGuard guard(h->device);
   A0GatherArgs g;
   g.frames = h->frames; g.rec_slots = h->rec_slots; g.rec_info = h->rec_info; g.idx = idx;
@@ -805,14 +847,30 @@ extern "C" int a0_rb_gather_f32(a0_replay_t* h, const int64_t* idx, int32_t coun
   g.frames_out = nullptr; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
   const size_t smem = (size_t)K3_RING * h->F;
-  static thread_local size_t configured[64] = {0};
+  static thread_local size_t configured[64] = {0};       // one table per OutT instantiation
   if (h->device < 64 && configured[h->device] < smem) {
-    A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_cvt<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[h->device] = smem;
   }
-  A0_LAUNCH(a0_k3_gather_f32, (unsigned)count, K3F_THREADS, smem, (cudaStream_t)stream_, 1, A0_PDL_K3, g, obs_out, next_out,
+  A0_LAUNCH(a0_k3_gather_cvt<OutT>, (unsigned)count, K3F_THREADS, smem, (cudaStream_t)stream_, 1, A0_PDL_K3, g, obs_out, next_out,
             (int)norm_mode);
   return A0_OK;
+}
+
+extern "C" int a0_rb_gather_f32(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
+                                float* obs_out, float* next_out, int32_t norm_mode, int64_t* action_out,
+                                double* reward64_out, float* reward32_out, uint8_t* done8_out, float* done32_out,
+                                int64_t* boot_out, a0_stream_t stream_) {
+  return a0_gather_cvt<float>(h, idx, count, n_step, gamma, obs_out, next_out, norm_mode, action_out, reward64_out,
+                              reward32_out, done8_out, done32_out, boot_out, stream_, "a0_rb_gather_f32");
+}
+
+extern "C" int a0_rb_gather_bf16(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
+                                 uint16_t* obs_out, uint16_t* next_out, int32_t norm_mode, int64_t* action_out,
+                                 double* reward64_out, float* reward32_out, uint8_t* done8_out, float* done32_out,
+                                 int64_t* boot_out, a0_stream_t stream_) {
+  return a0_gather_cvt<uint16_t>(h, idx, count, n_step, gamma, obs_out, next_out, norm_mode, action_out, reward64_out,
+                                 reward32_out, done8_out, done32_out, boot_out, stream_, "a0_rb_gather_bf16");
 }
 
 extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,

@@ -301,16 +301,17 @@ class ReplayDataset:
         self.append_steps(streams, k, new, action, reward, done)
 
     # ------------------------------------------------------------------ sample / gather
-    def alloc_batch(self, total, normalized=None):
+    def alloc_batch(self, total, normalized=None, obs_dtype=torch.float32):
         """Preallocated device buffers for ``total`` sampled transitions (``sample(..., out=)``):
         static addresses, as CUDA-graph capture of the consumer needs.  ``normalized`` (a NORM_*
-        mode): f32 obs / next_obs buffers instead of the u8 frames."""
+        mode): obs / next_obs buffers of ``obs_dtype`` (float32 or bfloat16) instead of the u8 frames."""
         dev = self.device
         e = lambda dt, *s: torch.empty(s or (total,), dtype=dt, device=dev)
         shape = (total, self.stack) + tuple(self.frame_shape)
+        assert obs_dtype in (torch.float32, torch.bfloat16)
         frames = e(torch.uint8, total, 8 * self.F) if normalized is None else None
-        obs = e(torch.float32, *shape) if normalized is not None else None
-        nxt = e(torch.float32, *shape) if normalized is not None else None
+        obs = e(obs_dtype, *shape) if normalized is not None else None
+        nxt = e(obs_dtype, *shape) if normalized is not None else None
         return Batch(frames, e(torch.int64), e(torch.float64), e(torch.bool), e(torch.float32),
                      e(torch.int64), e(torch.float32), e(torch.float32), e(torch.float32), e(torch.int64), obs, nxt)
 
@@ -323,14 +324,15 @@ class ReplayDataset:
                                                   _lib.stream_ptr(self.device)), "a0_rb_set_dynamic")
 
     def sample(self, batch_size=None, k_batches=1, u=None, indices=None, generator=None, out=None, dynamic=False,
-               normalized=None, seed=None, call=-1, u_out=None):
+               normalized=None, seed=None, call=-1, u_out=None, obs_dtype=None):
         """Draw ``k_batches`` stratified batches (K2a) and gather them (K3).  ``u`` (f32 device
         tensor of k*B uniforms) or ``indices`` (i64, explicit record positions) make the draw
         reproducible for parity tests; otherwise uniforms come from torch's CUDA generator.
         ``out`` (from ``alloc_batch``) receives the result in place; ``dynamic=True`` reads top/beta
         from the device values last published by ``push_dynamic`` (for CUDA-graph capture).
         ``normalized`` (NORM_DIV / NORM_RECIP / NORM_NONE): gather straight into the learner's f32
-        obs / next_obs inputs (K3 with the /255 + split of agent.py:129-135 fused in).
+        obs / next_obs inputs (K3 with the /255 + split of agent.py:129-135 fused in);
+        ``obs_dtype=torch.bfloat16`` writes them as bf16(f32 value) for a mixed-precision CNN.
         ``seed`` (int): the sampler draws its own uniforms (Philox4x32-10 inside K2a, no separate RNG
         launch); ``call`` >= 0 names the call number, < 0 uses the shard's device-resident counter,
         which every launch -- or graph replay -- advances; ``u_out`` receives the uniforms."""
@@ -367,16 +369,18 @@ class ReplayDataset:
                 if out is not None:
                     out.indices.copy_(idx); out.priorities.copy_(prio); out.weights.copy_(weights)
                     idx, prio, weights = out.indices, out.priorities, out.weights
-            return self.gather(idx, prio, weights, out=out, normalized=normalized)
+            return self.gather(idx, prio, weights, out=out, normalized=normalized, obs_dtype=obs_dtype)
 
-    def gather(self, idx, prio=None, weights=None, out=None, normalized=None):
+    def gather(self, idx, prio=None, weights=None, out=None, normalized=None, obs_dtype=None):
         dev = self.device
         total = idx.numel()
         if out is not None and out.obs is not None and normalized is None:
             normalized = NORM_DIV
+        if obs_dtype is not None and normalized is None:
+            normalized = NORM_DIV
         with torch.cuda.device(dev):
             if normalized is not None:
-                return self._gather_f32(idx, prio, weights, out, int(normalized))
+                return self._gather_f32(idx, prio, weights, out, int(normalized), obs_dtype)
             if out is not None:
                 assert out.frames.shape[0] == total, "out= was allocated for a different number of transitions"
                 frames, act, r64, d8, r32, d32, boot = (out.frames, out.actions, out.rewards, out.terminals, out.rewards_f32,
@@ -395,22 +399,27 @@ class ReplayDataset:
                 self.gather_variant, _lib.stream_ptr(dev)), "a0_rb_gather")
         return Batch(frames, act, r64, d8, prio, idx, weights, r32, d32, boot)
 
-    def _gather_f32(self, idx, prio, weights, out, mode):
+    def _gather_f32(self, idx, prio, weights, out, mode, obs_dtype=None):
         dev, total = self.device, idx.numel()
         shape = (total, self.stack) + tuple(self.frame_shape)
         if out is not None:
             assert out.obs is not None and out.obs.shape[0] == total, "out= was not allocated with normalized= for this size"
+            assert obs_dtype is None or obs_dtype == out.obs.dtype, "out= was allocated with another obs_dtype"
             obs, nxt, act, r64, d8, r32, d32, boot = (out.obs, out.next_obs, out.actions, out.rewards, out.terminals,
                                                       out.rewards_f32, out.terminals_f32, out.boot_indices)
         else:
             e = lambda dt, *s: torch.empty(s or (total,), dtype=dt, device=dev)
-            obs, nxt = e(torch.float32, *shape), e(torch.float32, *shape)
+            odt = obs_dtype or torch.float32
+            assert odt in (torch.float32, torch.bfloat16)
+            obs, nxt = e(odt, *shape), e(odt, *shape)
             act, r64, d8, r32 = e(torch.int64), e(torch.float64), e(torch.bool), e(torch.float32)
             d32, boot = e(torch.float32), e(torch.int64)
-        _lib.check(self.lib.a0_rb_gather_f32(
+        bf16 = obs.dtype == torch.bfloat16
+        fn = self.lib.a0_rb_gather_bf16 if bf16 else self.lib.a0_rb_gather_f32
+        _lib.check(fn(
             self.h, _lib.ptr(idx, torch.int64), total, self.n_gather, self.gamma, obs.data_ptr(), nxt.data_ptr(), mode,
             act.data_ptr(), r64.data_ptr(), r32.data_ptr(), d8.data_ptr(), d32.data_ptr(), boot.data_ptr(),
-            _lib.stream_ptr(dev)), "a0_rb_gather_f32")
+            _lib.stream_ptr(dev)), "a0_rb_gather_bf16" if bf16 else "a0_rb_gather_f32")
         return Batch(None, act, r64, d8, prio, idx, weights, r32, d32, boot, obs, nxt)
 
     def is_weights(self, prio, batch):

@@ -266,6 +266,14 @@ int a0_rb_gather_f32(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count
                      double gamma, float* obs_out, float* next_out, int32_t norm_mode,
                      int64_t* action_out, double* reward64_out, float* reward32_out,
                      uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream);
+/* The same with bfloat16 outputs (bit patterns in uint16_t), for a learner that runs its CNN in
+ * mixed precision: each value is bf16(fl32(norm(x))) rounded to nearest even, i.e.
+ * what `.float().div(255).to(torch.bfloat16)` gives for the chosen norm_mode.  obs_out, next_out:
+ * bf16 [count][4][frame_bytes]; 23 frame-sizes of traffic per transition at n = 3 instead of 39. */
+int a0_rb_gather_bf16(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count, int32_t n_step,
+                      double gamma, uint16_t* obs_out, uint16_t* next_out, int32_t norm_mode,
+                      int64_t* action_out, double* reward64_out, float* reward32_out,
+                      uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream);
 
 /* ---- K4: fused target + loss + IS weighting + new priority -----------------------------------------------
  * Common arguments: B samples; A actions; action i64[B]; reward f32[B] (n-step return); done f32[B]

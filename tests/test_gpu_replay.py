@@ -442,3 +442,42 @@ def test_empty_and_error_paths():
     assert lib.a0_rb_gather(rp.h, None, 4, 1, 0.99, None, None, None, None, None, None, None, 0, None) != 0
     assert b"required" in lib.a0_last_error()
     assert lib.a0_rb_gather(rp.h, None, 0, 1, 0.99, None, None, None, None, None, None, None, 0, None) == 0
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_fused_bf16_gather_equals_torch_cast_of_the_f32_gather(golden, n):
+    """a0_rb_gather_bf16 (mixed-precision learner input): every value is
+    bf16(fl32(norm(x))) rounded to nearest even -- bit-identical to casting the f32 gather with torch,
+    for all 256 byte values and the three normalisations, on the golden actor stream (n-step window,
+    episode boundaries) and into preallocated out= buffers; scalars as the f32 gather."""
+    from agent0_b200.replay import NORM_RECIP
+    E = 2
+    rp = _replay(64, n=1, native=True, E=E)
+    ramp = (np.arange(4 * 84 * 84, dtype=np.int64) % 256).astype(np.uint8).reshape(4, 84, 84)
+    rp.reset_streams(np.arange(E), np.stack([ramp, ramp[::-1].copy()]))
+    new = np.stack([np.full((84, 84), 255, np.uint8), np.zeros((84, 84), np.uint8)])
+    rp.append_steps(np.arange(E), np.ones(E, dtype=np.int64), new, np.array([1, 2]), np.array([0.5, -1.0]), np.array([False, True]))
+    pos = torch.arange(E, device="cuda")
+    for mode in (0, 1, 2):
+        f = rp.gather(pos, normalized=mode)
+        h = rp.gather(pos, normalized=mode, obs_dtype=torch.bfloat16)
+        assert h.obs.dtype == torch.bfloat16 and h.obs.shape == f.obs.shape
+        assert torch.equal(h.obs, f.obs.to(torch.bfloat16)) and torch.equal(h.next_obs, f.next_obs.to(torch.bfloat16))
+        assert torch.equal(h.rewards, f.rewards) and torch.equal(h.actions, f.actions)
+    out = rp.alloc_batch(E, normalized=NORM_RECIP, obs_dtype=torch.bfloat16)
+    b = rp.sample(E, indices=pos, out=out, normalized=NORM_RECIP)
+    assert b.obs.data_ptr() == out.obs.data_ptr()
+    assert torch.equal(out.obs, rp.gather(pos, normalized=NORM_RECIP).obs.to(torch.bfloat16))
+    # the golden actor stream through the native n-step path
+    g = golden(f"replay_n{n}")
+    E2, T = int(g["num_envs"]), int(g["steps"])
+    s_obs = g["stream_obs"]
+    done = OR.done_rule(g["stream_terminal"], g["stream_life_loss"], g["stream_truncated"])
+    rp = _replay(256, n=n, native=True, E=E2)
+    for k in range(T):
+        rp.append_vector_step(s_obs[k], g["stream_action"][k], g["stream_reward"][k], done[k], s_obs[k + 1])
+    live = torch.nonzero(rp.priority.leaves() > 0).view(-1)
+    f = rp.gather(live, normalized=0)
+    h = rp.gather(live, obs_dtype=torch.bfloat16)
+    assert torch.equal(h.obs, f.obs.to(torch.bfloat16)) and torch.equal(h.next_obs, f.next_obs.to(torch.bfloat16))
+    assert torch.equal(h.rewards, f.rewards) and torch.equal(h.terminals, f.terminals) and torch.equal(h.boot_indices, f.boot_indices)
