@@ -48,6 +48,8 @@ struct a0_replay {
   cudaStream_t copy_stream;   // lazily created; carries the ingest DMA under A0_INGEST_COPY_STREAM
   int64_t stride_hint;        // distance record -> successor of the same stream seen by the last appends
                               // (0: not uniform); lets K3 fetch an n-step window without chasing links
+  long long* mail;            // [mail_cap] sampler -> gather mailbox of a0_rb_sample_gather: draw g's record
+  int64_t mail_cap;           // position + 1, 0 = empty; every word is consumed (reset) by the gather CTA
 };
 
 void a0_set_error(const char* fmt, ...);
@@ -89,7 +91,7 @@ void a0_set_error(const char* fmt, ...);
 // CUDA graphs.  a0_set_option(A0_OPT_PDL, mask) / A0_PDL=mask in the environment selects the kernel
 // classes that use it (0 = none).
 // kernel classes for the PDL mask (A0_OPT_PDL): which launches carry the attribute
-enum { A0_PDL_K4 = 1, A0_PDL_K2 = 2, A0_PDL_K3 = 4, A0_PDL_K1 = 8 };
+enum { A0_PDL_K4 = 1, A0_PDL_K2 = 2, A0_PDL_K3 = 4, A0_PDL_K1 = 8, A0_PDL_FORCE = 1 << 30 };
 constexpr int A0_PDL_DEFAULT = A0_PDL_K4;   // measured: K4-only is best at B=32 and B=512 (profiles/r01_kernel_options.json)
 bool a0_pdl_enabled(int kernel_class);
 int a0_option_k2b_levels();
@@ -194,6 +196,19 @@ int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, f
 // a0_replay.cu: a0_rb_append that also publishes the sampler's dynamic scalars
 int a0_append_launch(a0_replay* h, const uint8_t* new_frames, const int32_t* new_frame_pos, int32_t n_new,
                      const int32_t* rec_meta, int32_t m, const A0Dyn& dyn, cudaStream_t stream);
+
+// a0_sumtree.cu / a0_replay.cu: the two launches behind a0_rb_sample_gather (see there)
+struct A0GatherOut {
+  uint8_t* frames;
+  int64_t* action;
+  double* reward64;
+  float* reward32;
+  uint8_t* done8;
+  float* done32;
+  int64_t* boot;
+};
+int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int32_t count, int32_t n_step, double gamma,
+                          const A0GatherOut& out, cudaStream_t stream);
 
 // ---- small device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float a0_warp_max(float v) {

@@ -28,7 +28,7 @@ bool a0_pdl_enabled(int kernel_class) {
     const char* e = getenv("A0_PDL");
     g_pdl = e ? atoi(e) : A0_PDL_DEFAULT;
   }
-  return (g_pdl & kernel_class) != 0;
+  return (kernel_class & A0_PDL_FORCE) || (g_pdl & kernel_class) != 0;
 }
 static int g_k2b_levels = 0;
 int a0_option_k2b_levels() {
@@ -135,7 +135,7 @@ extern "C" int a0_rb_destroy(a0_replay_t* h) {
   if (!h) return A0_OK;
   A0DeviceGuard guard(h->device);
   cudaFree(h->frames); cudaFree(h->rec_slots); cudaFree(h->rec_info); cudaFree(h->tree);
-  cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->dirty); cudaFree(h->counter);
+  cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->dirty); cudaFree(h->counter); cudaFree(h->mail);
   for (int t = 0; t < 2; ++t) {
     if (h->staging[t].event) { cudaEventSynchronize(h->staging[t].event); cudaEventDestroy(h->staging[t].event); }
     if (h->staging[t].copied) cudaEventDestroy(h->staging[t].copied);
@@ -243,6 +243,7 @@ struct A0GatherArgs {
   uint8_t* done8_out;
   float* done32_out;
   int64_t* boot_out;
+  long long* mail;       // != NULL: record positions arrive through the sampler's mailbox (a0_rb_sample_gather)
 };
 
 // Walks the n-step window that starts at record p0 (whose info word is already loaded), writes
@@ -446,21 +447,42 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   extern __shared__ __align__(128) uint8_t a0_smem[];
   __shared__ __align__(8) uint64_t bars[K3_RING];
   if (threadIdx.x != 0) return;
-  A0_PDL_PROLOGUE();
   const int b = blockIdx.x;
   const uint32_t F = (uint32_t)g.F;
   const uint32_t bar0 = a0_smem_u32(&bars[0]);
   const uint32_t buf0 = a0_smem_u32(a0_smem);
-  int64_t p0 = g.idx[b];
+  int64_t p0;
+  if (g.mail) {
+    // Launched (programmatically) while the sampler is still running: everything older than the
+    // sampler is complete -- it executed griddepcontrol.wait before it let this grid launch -- so
+    // the shard may be read; the record position comes through the mailbox as soon as the draw's
+    // warp has finished its descent.  The wait at the END of this kernel makes its completion
+    // imply the sampler's (weights, priorities), which is what the successors rely on.
+    asm volatile("griddepcontrol.launch_dependents;");
+#pragma unroll
+    for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
+    a0_fence_barrier_init();
+    long long v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(g.mail + b) : "memory");
+    } while (v == 0);
+    asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(g.mail + b), "l"(0ll) : "memory");
+    p0 = v - 1;
+  } else {
+    A0_PDL_PROLOGUE();
+    p0 = g.idx[b];
+  }
   bool ok = p0 >= 0 && p0 < g.N;
   if (!ok) p0 = 0;
   const int4 sa = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
   const A0RecInfo info0 = g.rec_info[p0];
   A0Spec sp;
   a0_spec_fetch(g, p0, sp);              // the guessed rest of the window, same round trip as the first record
+  if (!g.mail) {
 #pragma unroll
-  for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
-  a0_fence_barrier_init();
+    for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
+    a0_fence_barrier_init();
+  }
   int32_t uslot[A0_SLOTS];
   uint32_t dmask[A0_SLOTS];
   int U = 0;
@@ -509,6 +531,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
     }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (g.mail) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // Variant 3: the same data movement split over TWO CTAs per transition (even / odd distinct
@@ -846,6 +869,7 @@ static int a0_gather_cvt(a0_replay_t* h, const int64_t* idx, int32_t count, int3
   g.stride_hint = (h->stride_hint > 0 && h->stride_hint < h->N) ? (int32_t)h->stride_hint : 0;
   g.frames_out = nullptr; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
+  g.mail = nullptr;
   const size_t smem = (size_t)K3_RING * h->F;
   static thread_local size_t configured[64] = {0};       // one table per OutT instantiation
   if (h->device < 64 && configured[h->device] < smem) {
@@ -873,6 +897,33 @@ extern "C" int a0_rb_gather_bf16(a0_replay_t* h, const int64_t* idx, int32_t cou
                                  reward32_out, done8_out, done32_out, boot_out, stream_, "a0_rb_gather_bf16");
 }
 
+static int a0_k3_smem_attr(a0_replay_t* h, size_t smem) {
+  static thread_local size_t configured[64] = {0};
+  if (h->device < 64 && configured[h->device] < smem) {
+    A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[h->device] = smem;
+  }
+  return A0_OK;
+}
+
+// The gather half of a0_rb_sample_gather: variant 0 taking its record positions from the mailbox, always
+// launched with programmatic stream serialization so that it becomes resident under the sampler.
+int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int32_t count, int32_t n_step, double gamma,
+                          const A0GatherOut& out, cudaStream_t stream) {
+  A0GatherArgs g;
+  g.frames = h->frames; g.rec_slots = h->rec_slots; g.rec_info = h->rec_info; g.idx = idx;
+  g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
+  g.stride_hint = (h->stride_hint > 0 && h->stride_hint < h->N) ? (int32_t)h->stride_hint : 0;
+  g.frames_out = out.frames; g.action_out = out.action; g.reward64_out = out.reward64;
+  g.reward32_out = out.reward32; g.done8_out = out.done8; g.done32_out = out.done32; g.boot_out = out.boot;
+  g.mail = mail;
+  const size_t smem = (size_t)K3_RING * h->F;
+  int rc = a0_k3_smem_attr(h, smem);
+  if (rc) return rc;
+  A0_LAUNCH(a0_k3_gather_tma, (unsigned)count, 32, smem, stream, 1, A0_PDL_FORCE, g);
+  return A0_OK;
+}
+
 extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
                             uint8_t* frames_out, int64_t* action_out, double* reward64_out,
                             float* reward32_out, uint8_t* done8_out, float* done32_out,
@@ -892,6 +943,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   g.stride_hint = (h->stride_hint > 0 && h->stride_hint < h->N) ? (int32_t)h->stride_hint : 0;
   g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
+  g.mail = nullptr;
   if (variant == 3) {
     const size_t smem = (size_t)K3S_RING * h->F;
     static thread_local size_t configured3[64] = {0};
@@ -902,12 +954,13 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
     A0_LAUNCH(a0_k3_gather_tma_split, (unsigned)count * 2, 32, smem, stream, 1, A0_PDL_K3, g);
   } else if (variant == 0 || variant == 2) {
     const size_t smem = (size_t)(variant == 0 ? K3_RING : A0_SLOTS) * h->F;
-    static thread_local size_t configured[2][64] = {{0}, {0}};
-    const int vi = variant == 0 ? 0 : 1;
-    if (h->device < 64 && configured[vi][h->device] < smem) {
-      if (variant == 0) A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      else A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[vi][h->device] = smem;
+    static thread_local size_t configured[64] = {0};
+    if (variant == 0) {
+      int rc = a0_k3_smem_attr(h, smem);
+      if (rc) return rc;
+    } else if (h->device < 64 && configured[h->device] < smem) {
+      A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[h->device] = smem;
     }
     if (variant == 0) A0_LAUNCH(a0_k3_gather_tma, (unsigned)count, 32, smem, stream, 1, A0_PDL_K3, g);
     else A0_LAUNCH(a0_k3_gather_tma_full, (unsigned)count, 32, smem, stream, 1, A0_PDL_K3, g);

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(K2A_WARPS * 32)
 a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
               int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
               int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
-              unsigned int* counter, float* bmax, const float* __restrict__ dyn, const A0Rng rng) {
+              unsigned int* counter, float* bmax, const float* __restrict__ dyn, const A0Rng rng,
+              long long* __restrict__ mail) {
   A0_PDL_PROLOGUE();
   if (dyn) {            // top / beta / sum_offset live on the device (a0_rb_set_dynamic): graph-replay safe
     top = __ldcg(dyn);
@@ -119,6 +120,9 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
       left -= c;
     }
     if (lane == 0) {
+      // the gather CTA of this draw may already be resident and polling (a0_rb_sample_gather): it
+      // needs nothing but the position, so the mailbox word carries it (position + 1, 0 = empty)
+      if (mail) asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(mail + g), "l"((long long)(v - P) + 1ll) : "memory");
       idx_out[g] = v - P;
       prio_out[g] = leaf;
     }
@@ -220,7 +224,7 @@ extern "C" int a0_rb_set_dynamic(a0_replay_t* h, float top, float beta, float su
 
 static int a0_sample_launch(a0_replay_t* h, const float* u, const A0Rng& rng, int32_t total, int32_t batch, float top,
                             float beta, float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
-                            float* weight_out, a0_stream_t stream_, const char* who) {
+                            float* weight_out, a0_stream_t stream_, const char* who, long long* mail = nullptr) {
   A0_REQUIRE(h != nullptr, "%s: handle is NULL", who);
   A0_REQUIRE(total >= 0 && batch > 0 && total % batch == 0, "%s: total %d must be a multiple of batch %d", who, total, batch);
   if (total == 0) return A0_OK;
@@ -230,7 +234,7 @@ static int a0_sample_launch(a0_replay_t* h, const float* u, const A0Rng& rng, in
   const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
   A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, A0_PDL_K2, h->tree, h->P, h->D, u, total, batch,
             top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter,
-            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr), rng);
+            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr), rng, mail);
   return A0_OK;
 }
 
@@ -259,6 +263,53 @@ extern "C" int a0_pt_sample_rng(a0_replay_t* h, uint64_t seed, int64_t call, int
   rng.u_out = u_out;
   return a0_sample_launch(h, nullptr, rng, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out,
                           stream_, "a0_pt_sample_rng");
+}
+
+// Sample + gather as a producer/consumer pair.  Two launches, but the gather (K3, one CTA per draw)
+// is launched with programmatic stream serialization and does NOT wait for the sampler to finish:
+// it becomes resident while the sampler's warps are still descending the tree, and each gather CTA
+// starts fetching frames the moment its own draw's position lands in the mailbox.  What disappears
+// from the critical path of a step is the sampler's epilogue (IS-weight normalisation, tickets),
+// its drain, and the launch hand-over between the two kernels.  The gather ends with
+// griddepcontrol.wait, so "gather complete" still implies "sampler complete" for everything
+// downstream (K4 reads the weights).  Results are those of a0_pt_sample[_rng] + a0_rb_gather.
+extern "C" int a0_rb_sample_gather(a0_replay_t* h, const float* u, uint64_t seed, int64_t call, int32_t total,
+                                   int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
+                                   int64_t* idx_out, float* prio_out, float* weight_out, int32_t n_step, double gamma,
+                                   uint8_t* frames_out, int64_t* action_out, double* reward64_out, float* reward32_out,
+                                   uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_sample_gather: handle is NULL");
+  A0_REQUIRE(total >= 0 && batch > 0 && total % batch == 0, "a0_rb_sample_gather: total %d must be a multiple of batch %d", total, batch);
+  if (total == 0) return A0_OK;
+  A0_REQUIRE(idx_out && prio_out && frames_out, "a0_rb_sample_gather: idx_out, prio_out and frames_out are required");
+  A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_sample_gather: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
+  A0_REQUIRE(((uintptr_t)frames_out & 15) == 0, "a0_rb_sample_gather: frames_out must be 16-byte aligned");
+  A0DeviceGuard guard(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (h->mail_cap < total) {          // first use (or a larger draw): not inside a graph capture
+    int64_t cap = h->mail_cap > 0 ? h->mail_cap : 1024;
+    while (cap < total) cap *= 2;
+    A0_CUDA(cudaStreamSynchronize(stream));
+    if (h->mail) A0_CUDA(cudaFree(h->mail));
+    h->mail = nullptr; h->mail_cap = 0;
+    A0_CUDA(cudaMalloc((void**)&h->mail, (size_t)cap * sizeof(long long)));
+    A0_CUDA(cudaMemset(h->mail, 0, (size_t)cap * sizeof(long long)));
+    h->mail_cap = cap;
+  }
+  A0Rng rng = {0ull, 0ll, nullptr, nullptr, nullptr};
+  if (!u) {
+    rng.seed = seed;
+    rng.call = call;
+    rng.call_dev = reinterpret_cast<unsigned long long*>(h->counter + K2A_RNG_CALL);
+    rng.ticket = h->counter + K2A_RNG_TICKET;
+  }
+  int rc = a0_sample_launch(h, u, rng, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, stream_,
+                            "a0_rb_sample_gather", h->mail);
+  if (rc) return rc;
+  const A0GatherOut out = {frames_out, action_out, reward64_out, reward32_out, done8_out, done32_out, boot_out};
+  rc = a0_gather_launch_mail(h, idx_out, h->mail, total, n_step, gamma, out, stream);
+  if (rc) cudaMemsetAsync(h->mail, 0, (size_t)total * sizeof(long long), stream);   // nobody will consume the posted words
+  return rc;
 }
 
 __global__ void a0_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }

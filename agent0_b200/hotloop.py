@@ -30,7 +30,7 @@ ALGOS = ("dqn", "mdqn", "c51", "qr", "iqn", "fqf")
 class ReplayTargetLoop:
     def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, n_step=None, double_q=True,
                  per=None, variant=0, discount=None, alpha=0.5, eps=0.01, c51=(51, -10.0, 10.0), mdqn=(0.03, -1.0),
-                 frames=None, rng_seed=None):
+                 frames=None, rng_seed=None, overlap_sample_gather=True):
         """replay: ReplayDataset (native_nstep=True when n_step > 1).  outputs: dict of STATIC f32 device
         tensors holding the network outputs of all L*B sampled transitions, batch k in rows
         [k*B, (k+1)*B): ``online``, ``tgt_next`` (+ ``qsel`` [L*B,A] under double_q / for iqn, fqf;
@@ -38,13 +38,16 @@ class ReplayTargetLoop:
         fqf), shaped as the learners produce them (agent0_b200.losses).  frames: optional u8
         [L*B, 8*F] output buffer for the gather (allocated if None).  rng_seed: the sampler draws its own
         uniforms (Philox inside K2a, device-resident call counter advanced by every launch/replay)
-        instead of reading ``self.u``, which ``step()`` otherwise refills with ``uniform_()``."""
+        instead of reading ``self.u``, which ``step()`` otherwise refills with ``uniform_()``.
+        overlap_sample_gather: ``step()`` issues K2a and K3 through a0_rb_sample_gather (the gather runs
+        under the sampler, fed draw by draw through a mailbox) instead of back to back; same results."""
         assert algo in ALGOS, algo
         self.lib = _lib.load()
         self.rp, self.algo, self.B, self.L, self.A = replay, algo, int(batch_size), int(learner_steps), int(action_dim)
         self.total = T = self.L * self.B
         self.dev = dev = replay.device
         self.variant = int(variant)
+        self.overlap_sg = bool(overlap_sample_gather) and int(variant) == 0
         self.rng_seed = None if rng_seed is None else int(rng_seed) & 0xFFFFFFFFFFFFFFFF
         self.n = int(n_step if n_step is not None else replay.n_gather)
         self.gamma = float(discount if discount is not None else replay.gamma)
@@ -94,6 +97,15 @@ class ReplayTargetLoop:
                                          out_ptr or self.frames.data_ptr(), self.act.data_ptr(), self.r64.data_ptr(),
                                          self.r32.data_ptr(), self.d8.data_ptr(), self.d32.data_ptr(), self.boot.data_ptr(),
                                          self.variant if variant is None else variant, self._st()), "a0_rb_gather")
+
+    def sample_gather(self):
+        """K2a + K3 overlapped (a0_rb_sample_gather): same outputs as sample() followed by gather()."""
+        rp = self.rp
+        _lib.check(self.lib.a0_rb_sample_gather(
+            rp.h, None if self.rng_seed is not None else self.u.data_ptr(), self.rng_seed or 0, -1, self.total, self.B, -1.0,
+            float(rp.beta), 0.0, 0 if self.per else 1, self.idx.data_ptr(), self.prio.data_ptr(), self.w.data_ptr(), self.n,
+            self.gamma, self.frames.data_ptr(), self.act.data_ptr(), self.r64.data_ptr(), self.r32.data_ptr(),
+            self.d8.data_ptr(), self.d32.data_ptr(), self.boot.data_ptr(), self._st()), "a0_rb_sample_gather")
 
     def _common(self, lo, count):
         s = slice(lo, lo + count)
@@ -181,8 +193,11 @@ class ReplayTargetLoop:
     def step(self, fused_k4=False, slot=None):
         if self.rng_seed is None:
             self.u.uniform_()
-        self.sample()
-        self.gather()
+        if self.overlap_sg:
+            self.sample_gather()
+        else:
+            self.sample()
+            self.gather()
         if fused_k4:
             self.target_loss_all()
         else:

@@ -258,6 +258,22 @@ int a0_rb_gather(a0_replay_t* h, const int64_t* idx /* dev */, int32_t count, in
                  float* reward32_out, uint8_t* done8_out, float* done32_out, int64_t* boot_out,
                  int32_t variant, a0_stream_t stream);
 
+/* a0_pt_sample[_rng] + a0_rb_gather (variant 0) as an overlapped producer/consumer pair: the gather
+ * is launched with programmatic stream serialization, becomes resident while the sampler is still
+ * descending the tree, and each of its CTAs starts fetching frames as soon as its own draw's record
+ * position arrives through a handle-owned mailbox -- the sampler's IS-weight epilogue, its drain and
+ * the launch hand-over between the two kernels leave the critical path of a step.  The gather ends
+ * with griddepcontrol.wait, so work queued after this call sees both kernels complete.  Same results
+ * as the two separate calls.  u != NULL: caller-supplied uniforms (seed, call ignored); u == NULL:
+ * the sampler's own Philox stream as a0_pt_sample_rng.  The first call (and any call with a larger
+ * total) allocates the mailbox and must not be inside a CUDA-graph capture.                        */
+int a0_rb_sample_gather(a0_replay_t* h, const float* u /* dev [total] or NULL */, uint64_t seed,
+                        int64_t call, int32_t total, int32_t batch, float top, float beta,
+                        float sum_offset, int32_t uniform, int64_t* idx_out, float* prio_out,
+                        float* weight_out, int32_t n_step, double gamma, uint8_t* frames_out,
+                        int64_t* action_out, double* reward64_out, float* reward32_out,
+                        uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream);
+
 /* K3 with the learner's input conversion fused in (agent.py:129-135: reshape, .float(), .div(255),
  * split into obs / next_obs).  obs_out, next_out: f32 [count][4][frame_bytes], contiguous, ready
  * for the CNN.  norm_mode 0: x/255 correctly rounded (torch on the CPU); 1: x * fl(1/255) (torch's

@@ -224,3 +224,56 @@ def test_reporting_graphs_with_ingest_published_scalars_equal_the_plain_loop():
         assert torch.equal(la.idx, lb.idx) and torch.equal(la.loss, lb.loss) and torch.equal(la.w, lb.w)
         assert torch.equal(rp_a.tree, rp_b.tree)
     assert len({int(rep[0][0][0]), int(rep[1][0][0])}) == 2 or not torch.equal(rep[0][0], rep[1][0])
+
+
+@pytest.mark.parametrize("Bn,k,per", [(32, 20, True), (512, 4, True), (12, 3, True), (32, 2, False)])
+def test_overlapped_sample_gather_equals_the_two_separate_launches(Bn, k, per):
+    """a0_rb_sample_gather: the gather runs UNDER the sampler (programmatic launch, record positions
+    through a mailbox, griddepcontrol.wait at its end).  Indices, priorities, IS weights, stacks and
+    n-step scalars must be those of a0_pt_sample[_rng] followed by a0_rb_gather -- with caller-supplied
+    uniforms and with the sampler's own generator, on repeated calls (the mailbox re-arms itself), and
+    when captured into a CUDA graph and replayed."""
+    from agent0_b200 import _lib
+    from agent0_b200.hotloop import ReplayTargetLoop
+    lib = _lib.load()
+    rp = _shard("c51")
+    T = Bn * k
+    o = _outputs("dqn", T)
+    la = ReplayTargetLoop(rp, "dqn", Bn, k, A, o, n_step=3, per=per, overlap_sample_gather=False)
+    lb = ReplayTargetLoop(rp, "dqn", Bn, k, A, o, n_step=3, per=per, overlap_sample_gather=True)
+    rp.push_dynamic()
+    fields = ("idx", "prio", "w", "frames", "act", "r64", "r32", "d8", "d32", "boot")
+
+    def same():
+        torch.cuda.synchronize()
+        for f in fields:
+            assert torch.equal(getattr(la, f), getattr(lb, f)), f
+
+    g = torch.Generator("cuda").manual_seed(5)
+    for rep in range(3):                                   # caller-supplied uniforms
+        la.u.uniform_(generator=g)
+        lb.u.copy_(la.u)
+        la.sample(); la.gather()
+        lb.frames.zero_(); lb.idx.fill_(-1)
+        lb.sample_gather()
+        same()
+    la.rng_seed = lb.rng_seed = 1234                       # the sampler's own Philox stream, device call counter
+    rp.rng_seek(40)
+    la.sample(); la.gather()
+    rp.rng_seek(40)
+    lb.sample_gather()
+    same()
+    # captured: every replay advances the counter and refills the mailbox
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        lb.sample_gather()
+    for call in (50, 51, 52):
+        rp.rng_seek(call)
+        la.sample(); la.gather()
+        rp.rng_seek(call)                                  # la's launch advanced the counter: step back (stream-ordered)
+        gr.replay()
+        same()
+    # work queued behind the pair sees the sampler complete: weights are normalised (max == 1 per batch)
+    if per:
+        w = lb.w.view(k, Bn).max(dim=1)[0]
+        assert torch.allclose(w, torch.ones_like(w), atol=1e-6)
