@@ -8,7 +8,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libagent0_b200.so")
+LIB_PATH = os.environ.get("A0_LIB") or os.path.join(_PKG, "libagent0_b200.so")   # A0_LIB: the -DA0_TRACE build (tools/trace_step.py)
 
 A0_SLOTS = 8
 A0_REC_META_I32 = 14

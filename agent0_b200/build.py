@@ -22,12 +22,17 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+TRACE_LIB = os.path.join(PKG, "libagent0_b200_trace.so")
+
+
+def build(force=False, verbose=False, trace=False):
+    """trace=True: the same sources with -DA0_TRACE (device-side timeline records) into
+    libagent0_b200_trace.so, loaded instead of the product library when A0_LIB points at it."""
+    if not trace and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DA0_TRACE"] if trace else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", TRACE_LIB if trace else LIB]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -35,8 +40,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return TRACE_LIB if trace else LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -82,6 +82,41 @@ void a0_set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
+// ---- optional device-side timeline (build with -DA0_TRACE: tools/trace_step.py) ----------------------
+// Every traced CTA appends {kernel id, block, t_entry, t_mid, t_exit} (%globaltimer, ns) to a log; the
+// production build compiles all of it away.
+#ifdef A0_TRACE
+struct A0TraceRec { unsigned long long t0, t1, t2; int kid, blk; unsigned long long x[8]; };
+static __device__ A0TraceRec* a0_trace_buf;
+static __device__ unsigned int* a0_trace_cur;
+__device__ __forceinline__ unsigned long long a0_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define A0_TRACE_SETTER(name)                                   \
+  int name(void* buf, void* cur) {                              \
+    cudaMemcpyToSymbol(a0_trace_buf, &buf, sizeof(buf));        \
+    cudaMemcpyToSymbol(a0_trace_cur, &cur, sizeof(cur));        \
+    return 0;                                                   \
+  }
+#define A0_T0() const unsigned long long _t0 = a0_now(); unsigned long long _t2 = 0, _tx[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define A0_TX(i) _tx[i] = (unsigned long long)clock64()      /* SM cycles: cheap, for phases inside one CTA */
+#define A0_TMID() _t2 = a0_now()
+#define A0_TEND(kid)                                                                       \
+  do {                                                                                     \
+    if (a0_trace_buf) {                                                                    \
+      const unsigned _i = atomicAdd(a0_trace_cur, 1u);                                     \
+      if (_i < (1u << 16)) a0_trace_buf[_i] = A0TraceRec{_t0, a0_now(), _t2, kid, (int)blockIdx.x, {_tx[0], _tx[1], _tx[2], _tx[3], _tx[4], _tx[5], _tx[6], _tx[7]}}; \
+    }                                                                                      \
+  } while (0)
+#else
+#define A0_T0() do {} while (0)
+#define A0_TMID() do {} while (0)
+#define A0_TX(i) do {} while (0)
+#define A0_TEND(kid) do {} while (0)
+#endif
+
 // ---- launches ---------------------------------------------------------------------------------------
 // Kernels can be launched with programmatic stream serialization (PDL): the kernel may become
 // resident while its predecessor in the stream drains, executes griddepcontrol.wait as its first
@@ -98,6 +133,7 @@ int a0_option_k2b_levels();
 constexpr int A0_K2B_BULK_MIN_DEFAULT = 2048;    // from this many indices (and >= 4 per 4096-leaf chunk): leaf writes + chunk rebuild on all SMs
 int a0_option_k2b_bulk_min();
 bool a0_option_fused_ingest();
+void a0_set_c51_fast(int on);
 
 // (Measured alternative: launch_dependents BEFORE the wait lets a whole chain of dependent kernels
 // become resident launches ahead.  It does not lower the ~2.85 us per-link cost of the batch-32 K4

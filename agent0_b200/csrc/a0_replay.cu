@@ -21,6 +21,15 @@ void a0_set_error(const char* fmt, ...) {
 }
 extern "C" const char* a0_last_error(void) { return g_err; }
 extern "C" int a0_version(void) { return 101; }
+#ifdef A0_TRACE
+A0_TRACE_SETTER(a0_trace_set_replay)
+int a0_trace_set_sumtree(void*, void*);
+int a0_trace_set_targets(void*, void*);
+extern "C" int a0_trace_set(void* buf, void* cur) {
+  a0_trace_set_replay(buf, cur); a0_trace_set_sumtree(buf, cur); a0_trace_set_targets(buf, cur);
+  return (int)cudaDeviceSynchronize();
+}
+#endif
 
 static int g_pdl = -1;     // -1: not decided yet (environment); else a mask of A0_PDL_* classes
 bool a0_pdl_enabled(int kernel_class) {
@@ -57,6 +66,7 @@ bool a0_option_fused_ingest() {
 }
 extern "C" int a0_set_option(int32_t option, int64_t value) {
   if (option == A0_OPT_FUSED_INGEST) { g_fused_ingest = value != 0; return A0_OK; }
+  if (option == A0_OPT_C51_FAST) { a0_set_c51_fast(value != 0); return A0_OK; }
   if (option == A0_OPT_PDL) { g_pdl = (int)value & 15; return A0_OK; }
   if (option == A0_OPT_K2B_LEVELS) {
     A0_REQUIRE(value == 3 || value == 4, "a0_set_option: A0_OPT_K2B_LEVELS must be 3 or 4");
@@ -447,6 +457,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   extern __shared__ __align__(128) uint8_t a0_smem[];
   __shared__ __align__(8) uint64_t bars[K3_RING];
   if (threadIdx.x != 0) return;
+  A0_T0();
   const int b = blockIdx.x;
   const uint32_t F = (uint32_t)g.F;
   const uint32_t bar0 = a0_smem_u32(&bars[0]);
@@ -472,6 +483,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
     A0_PDL_PROLOGUE();
     p0 = g.idx[b];
   }
+  A0_TMID();
   bool ok = p0 >= 0 && p0 < g.N;
   if (!ok) p0 = 0;
   const int4 sa = *reinterpret_cast<const int4*>(g.rec_slots + (size_t)p0 * A0_SLOTS);
@@ -531,6 +543,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
     }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  A0_TEND(3);
   if (g.mail) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 

@@ -12,6 +12,9 @@
 // The tree (2P floats, 8 MB at 1 M leaves, 16.8 MB at 2 M) is L2-resident: these kernels are
 // latency-bound, not HBM-bound.
 #include "a0_common.cuh"
+#ifdef A0_TRACE
+A0_TRACE_SETTER(a0_trace_set_sumtree)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // K2a.  One warp per draw.  Instead of one dependent L2 round trip per level, the warp fetches the
@@ -63,7 +66,9 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
               int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
               unsigned int* counter, float* bmax, const float* __restrict__ dyn, const A0Rng rng,
               long long* __restrict__ mail) {
+  A0_T0();
   A0_PDL_PROLOGUE();
+  A0_TMID();
   if (dyn) {            // top / beta / sum_offset live on the device (a0_rb_set_dynamic): graph-replay safe
     top = __ldcg(dyn);
     beta = __ldcg(dyn + 1);
@@ -125,6 +130,7 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
       if (mail) asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(mail + g), "l"((long long)(v - P) + 1ll) : "memory");
       idx_out[g] = v - P;
       prio_out[g] = leaf;
+      if (warp == 0) A0_TEND(2);
     }
     leaf_w = leaf;
   }
@@ -641,9 +647,12 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
              float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
              int32_t* __restrict__ dirty, int32_t chunk_log, const A0Report rep) {
+  A0_T0();
   A0_PDL_PROLOGUE();
+  A0_TMID();
   a0_paths_body<K2P_LEVELS>(tree, P, D, N, idx64, idx32, vals, count, mode, alpha, eps, max_p, winner, dirty, chunk_log,
                             (int)blockIdx.x, (int)gridDim.x, rep);
+  if (threadIdx.x == 0) A0_TEND(5);
 }
 
 // A small ingest in ONE launch: CTA 0 applies the marks to the tree (the single-CTA path climb above),

@@ -8,7 +8,12 @@
 // and, for the quantile family, materialises [B,N,N] tensors several times (agent.py:110-114);
 // here the pair loop stays in registers.  Inputs are <= 2.4 KB per transition: these kernels are
 // launch/ALU-bound, not HBM-bound.
+#include <stdlib.h>
+
 #include "a0_common.cuh"
+#ifdef A0_TRACE
+A0_TRACE_SETTER(a0_trace_set_targets)
+#endif
 
 struct A0Common {
   int32_t B, A;
@@ -174,7 +179,12 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
           const float* __restrict__ qsel, const float* __restrict__ atoms, int32_t M, float vmin, float vmax,
           float* __restrict__ grad, float* __restrict__ target_prob) {
   __shared__ float s_m[C51_WARPS][C51_MAXR * 32];      // projected distribution of this warp's sample
+  A0_T0();
   A0_PDL_PROLOGUE();
+  A0_TMID();
+#ifdef A0_TRACE
+  const long long _c0 = clock64();
+#endif
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int b = blockIdx.x * C51_WARPS + wid;
@@ -225,6 +235,10 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   float omx = -INFINITY;
 #pragma unroll
   for (int k = 0; k < C51_MAXR; ++k) omx = fmaxf(omx, l[k]);
+#ifdef A0_TRACE
+  if (omx == 12345.678f) printf("x");     // forces the loads to have landed before the timestamp
+#endif
+  A0_TX(0);
   int a_star;
   if (qsel) {
     float v = qs;
@@ -264,6 +278,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
     }
   }
 
+  A0_TX(1);
   // ---- softmax of the selected target row | sum-exp of the online row -----------------------------
   const float* trow = tgt_logits + ((size_t)b * A + a_star) * M;
   float p[C51_MAXR], mx = -INFINITY;
@@ -295,6 +310,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
   for (int k = 0; k < C51_MAXR; ++k) { p[k] = (k < R && lane + 32 * k < M) ? expf(p[k] - mx) : 0.0f; se += p[k]; }
   se = a0_warp_sum(se);
 
+  A0_TX(2);
   // ---- projection (agent.py:230-264) ------------------------------------------------------------
   const float gm = __fmul_rn(c.gamma_n, __fsub_rn(1.0f, d));
   const float delta = (vmax - vmin) / (float)(M - 1);
@@ -318,6 +334,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
     }
   }
   __syncwarp();
+  A0_TX(3);
   if (R <= 2) {
     // M <= 64 (the 51-atom case): lower and upper terms of both atom chunks in one scan
     const int key4[4] = {lo[0], lo[1], up[0], up[1]};
@@ -331,6 +348,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
 #pragma unroll
   for (int k = 0; k < C51_MAXR; ++k) m[k] = s_m[wid][lane + 32 * k];
 
+  A0_TX(4);
   // ---- cross-entropy with the online row, gradient through log_softmax (agent.py:266-268) ------
   const float lse = logf(ose);
   float ce = 0.0f, msum = 0.0f;
@@ -339,6 +357,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
     if (k < R && lane + 32 * k < M) { ce += m[k] * ((l[k] - omx) - lse); msum += m[k]; }
   ce = a0_warp_sum(ce);
   msum = a0_warp_sum(msum);
+  A0_TX(5);
   float* grow = grad + (size_t)b * A * M;
   for (int a2 = 0; a2 < A; ++a2) {
     if (a2 == a) continue;
@@ -353,8 +372,203 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
       if (target_prob) target_prob[(size_t)b * M + j] = m[k];
     }
   }
+  A0_TX(6);
   if (lane == 0) a0_emit(c, b, -ce);
+  A0_TX(7);
+#ifdef A0_TRACE
+  _t2 = _t2 * 0 + (unsigned long long)_c0;      // phases are reported in SM cycles relative to the wait's return
+#endif
+  if (threadIdx.x == 0) A0_TEND(4);
 }
+
+// ------------------------------------------------------------------------------------------------
+// C51, the Atari shape (A <= 6 actions, M <= 64 atoms, double-Q action selection given): the same
+// arithmetic as a0_k4_c51 -- bit for bit -- with the dependent instruction chain cut down.  A batch of
+// 32 is one warp per sample on 8 SMs: the kernel's duration IS the length of one warp's dependent
+// chain (device timeline, tools/trace_step.py: 3.5 us of a 3.9 us launch-to-launch period, 20 of them
+// per Trainer.step), so what counts is instructions on that chain, not throughput:
+//   * arg-max over the A selection values computed by every lane from broadcast loads (no shuffles);
+//   * the two row maxima reduced together, then the two sum-exps together: 10 shuffle steps, not 15;
+//   * u = l + 1 always holds after the reference's two adjustments (agent.py:246-250), so
+//     l = max(ceil(b) - 1, 0) and one key per atom drives the scan of both terms;
+//   * bins are written by read-modify-write in four fixed phases (one writer per bin and phase by
+//     construction) instead of shared-memory atomics (CAS loops);
+//   * cross-entropy and mass reduced together; the gradient block [A, M] of a sample leaves through
+//     shared memory as 16-byte stores when A*M is a multiple of 4 (204 floats at A = 4, M = 51).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(C51_WARPS * 32)
+a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* __restrict__ tgt_logits,
+               const float* __restrict__ qsel, const float* __restrict__ atoms, int32_t M, float vmin, float vmax,
+               float* __restrict__ grad, float* __restrict__ target_prob) {
+  __shared__ float s_m[C51_WARPS][72];       // projected distribution (bin M may be touched when b rounds above M-1:
+                                             // ignored, as in the reference's clamp), then the taken action's gradient row
+  A0_T0();
+  A0_PDL_PROLOGUE();
+  A0_TMID();
+#ifdef A0_TRACE
+  const long long _c0 = clock64();
+#endif
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int b = blockIdx.x * C51_WARPS + wid;
+  if (b >= c.B) return;
+  const int A = c.A;
+  const bool in0 = lane < M, in1 = lane + 32 < M;
+  // ---- every global load of the sample, issued up front ----------------------------------------------
+  float lo_all[C51_SPEC_A][2], tg_all[C51_SPEC_A][2], qs[C51_SPEC_A];
+  const float* lrow = logits + (size_t)b * A * M + lane;
+  const float* trow = tgt_logits + (size_t)b * A * M + lane;
+  const float* qrow = qsel + (size_t)b * A;
+#pragma unroll
+  for (int a2 = 0; a2 < C51_SPEC_A; ++a2) {
+    const bool on = a2 < A;
+    lo_all[a2][0] = (on && in0) ? lrow[a2 * M] : -INFINITY;
+    lo_all[a2][1] = (on && in1) ? lrow[a2 * M + 32] : -INFINITY;
+    tg_all[a2][0] = (on && in0) ? trow[a2 * M] : -INFINITY;
+    tg_all[a2][1] = (on && in1) ? trow[a2 * M + 32] : -INFINITY;
+    qs[a2] = on ? qrow[a2] : -INFINITY;                 // same address in every lane: one broadcast transaction
+  }
+  const int a = (int)c.action[b];
+  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  const float z0 = in0 ? atoms[lane] : 0.0f, z1 = in1 ? atoms[lane + 32] : 0.0f;
+  s_m[wid][lane] = 0.0f;
+  s_m[wid][lane + 32] = 0.0f;
+  // ---- action selection: first maximum, as torch.argmax (agent.py:224) ---------------------------------
+  int a_star = 0;
+  float best = qs[0];
+#pragma unroll
+  for (int a2 = 1; a2 < C51_SPEC_A; ++a2)
+    if (qs[a2] > best) { best = qs[a2]; a_star = a2; }
+  float l0 = -INFINITY, l1 = -INFINITY, p0 = -INFINITY, p1 = -INFINITY;
+#pragma unroll
+  for (int a2 = 0; a2 < C51_SPEC_A; ++a2) {
+    if (a2 == a) { l0 = lo_all[a2][0]; l1 = lo_all[a2][1]; }
+    if (a2 == a_star) { p0 = tg_all[a2][0]; p1 = tg_all[a2][1]; }
+  }
+  A0_TX(0);
+  // ---- both softmaxes: maxima together, then sum-exps together -----------------------------------------
+  float omx = fmaxf(l0, l1), mx = fmaxf(p0, p1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float a_ = __shfl_xor_sync(0xffffffffu, omx, o);
+    const float b_ = __shfl_xor_sync(0xffffffffu, mx, o);
+    omx = fmaxf(omx, a_);
+    mx = fmaxf(mx, b_);
+  }
+  A0_TX(1);
+  const float eo0 = in0 ? expf(l0 - omx) : 0.0f, eo1 = in1 ? expf(l1 - omx) : 0.0f;
+  p0 = in0 ? expf(p0 - mx) : 0.0f;
+  p1 = in1 ? expf(p1 - mx) : 0.0f;
+  float ose = eo0 + eo1, se = p0 + p1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float a_ = __shfl_xor_sync(0xffffffffu, ose, o);
+    const float b_ = __shfl_xor_sync(0xffffffffu, se, o);
+    ose += a_;
+    se += b_;
+  }
+  A0_TX(2);
+  // ---- projection (agent.py:230-264) ---------------------------------------------------------------------
+  const float gm = __fmul_rn(c.gamma_n, __fsub_rn(1.0f, d));
+  const float delta = (vmax - vmin) / (float)(M - 1);
+  int k0 = -1, k1 = -1;                       // lower bin of atoms lane and lane + 32; the upper one is k + 1
+  float wl0 = 0.0f, wu0 = 0.0f, wl1 = 0.0f, wu1 = 0.0f;
+  {
+    const float pj0 = __fdiv_rn(p0, se), pj1 = __fdiv_rn(p1, se);
+    const float tz0 = fminf(fmaxf(__fadd_rn(r, __fmul_rn(gm, z0)), vmin), vmax);
+    const float tz1 = fminf(fmaxf(__fadd_rn(r, __fmul_rn(gm, z1)), vmin), vmax);
+    const float bs0 = __fdiv_rn(__fsub_rn(tz0, vmin), delta), bs1 = __fdiv_rn(__fsub_rn(tz1, vmin), delta);
+    const int c0 = max((int)ceilf(bs0) - 1, 0), c1 = max((int)ceilf(bs1) - 1, 0);
+    if (in0) { k0 = c0; wl0 = __fmul_rn(pj0, __fsub_rn((float)(c0 + 1), bs0)); wu0 = __fmul_rn(pj0, __fsub_rn(bs0, (float)c0)); }
+    if (in1) { k1 = c1; wl1 = __fmul_rn(pj1, __fsub_rn((float)(c1 + 1), bs1)); wu1 = __fmul_rn(pj1, __fsub_rn(bs1, (float)c1)); }
+  }
+  A0_TX(3);
+  // segmented inclusive scan over the lanes, keyed by the lower bin (bins are non-decreasing in the atom
+  // index, so the sources of one bin are adjacent lanes); the same combination order as a0_c51_scatter
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const int q0 = __shfl_up_sync(0xffffffffu, k0, dd), q1 = __shfl_up_sync(0xffffffffu, k1, dd);
+    const float a0_ = __shfl_up_sync(0xffffffffu, wl0, dd), b0_ = __shfl_up_sync(0xffffffffu, wu0, dd);
+    const float a1_ = __shfl_up_sync(0xffffffffu, wl1, dd), b1_ = __shfl_up_sync(0xffffffffu, wu1, dd);
+    if (lane >= dd && q0 == k0) { wl0 = __fadd_rn(wl0, a0_); wu0 = __fadd_rn(wu0, b0_); }
+    if (lane >= dd && q1 == k1) { wl1 = __fadd_rn(wl1, a1_); wu1 = __fadd_rn(wu1, b1_); }
+  }
+  const int n0 = __shfl_down_sync(0xffffffffu, k0, 1), n1 = __shfl_down_sync(0xffffffffu, k1, 1);
+  const bool tail0 = k0 >= 0 && (lane == 31 || n0 != k0), tail1 = k1 >= 0 && (lane == 31 || n1 != k1);
+  float* bins = s_m[wid];
+  __syncwarp();                                // the zeros above are visible
+  // four phases in the order of a0_k4_c51 (lower terms of both chunks, then upper terms): within a
+  // phase every bin has at most one writer, so a plain read-modify-write is exact and deterministic
+  if (tail0) bins[k0] = __fadd_rn(bins[k0], wl0);
+  __syncwarp();
+  if (tail1) bins[k1] = __fadd_rn(bins[k1], wl1);
+  __syncwarp();
+  if (tail0) bins[k0 + 1] = __fadd_rn(bins[k0 + 1], wu0);
+  __syncwarp();
+  if (tail1) bins[k1 + 1] = __fadd_rn(bins[k1 + 1], wu1);
+  __syncwarp();
+  const float m0 = bins[lane], m1 = bins[lane + 32];
+  A0_TX(4);
+  // ---- cross-entropy with the online row, gradient through log_softmax (agent.py:266-268) -----------------
+  const float lse = logf(ose);
+  const float ls0 = (l0 - omx) - lse, ls1 = (l1 - omx) - lse;
+  float ce = 0.0f, msum = 0.0f;
+  if (in0) { ce += m0 * ls0; msum += m0; }
+  if (in1) { ce += m1 * ls1; msum += m1; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float a_ = __shfl_xor_sync(0xffffffffu, ce, o);
+    const float b_ = __shfl_xor_sync(0xffffffffu, msum, o);
+    ce += a_;
+    msum += b_;
+  }
+  A0_TX(5);
+  const float g0 = w * (expf(ls0) * msum - m0), g1 = w * (expf(ls1) * msum - m1);
+  __syncwarp();                                // every lane has read its bins
+  bins[lane] = in0 ? g0 : 0.0f;
+  bins[lane + 32] = in1 ? g1 : 0.0f;
+  if (target_prob) {
+    if (in0) target_prob[(size_t)b * M + lane] = m0;
+    if (in1) target_prob[(size_t)b * M + lane + 32] = m1;
+  }
+  __syncwarp();
+  // the sample's whole [A, M] gradient block: zeros except row a
+  const int AM = A * M, r0 = a * M;
+  float* gb = grad + (size_t)b * AM;
+  if ((AM & 3) == 0 && (((uintptr_t)grad) & 15) == 0) {
+    for (int v4 = lane; v4 < (AM >> 2); v4 += 32) {
+      const int e = 4 * v4 - r0;               // column of the first element if it lies in row a
+      float4 o4;
+      o4.x = (e >= 0 && e < M) ? bins[e] : 0.0f;
+      o4.y = (e + 1 >= 0 && e + 1 < M) ? bins[e + 1] : 0.0f;
+      o4.z = (e + 2 >= 0 && e + 2 < M) ? bins[e + 2] : 0.0f;
+      o4.w = (e + 3 >= 0 && e + 3 < M) ? bins[e + 3] : 0.0f;
+      reinterpret_cast<float4*>(gb)[v4] = o4;
+    }
+  } else {
+    for (int e = lane; e < AM; e += 32) {
+      const int col = e - r0;
+      gb[e] = (col >= 0 && col < M) ? bins[col] : 0.0f;
+    }
+  }
+  A0_TX(6);
+  if (lane == 0) a0_emit(c, b, -ce);
+  A0_TX(7);
+#ifdef A0_TRACE
+  _t2 = _t2 * 0 + (unsigned long long)_c0;
+#endif
+  if (threadIdx.x == 0) A0_TEND(4);
+}
+
+static int g_c51_fast = -1;
+static bool a0_option_c51_fast() {
+  if (g_c51_fast < 0) {
+    const char* e = getenv("A0_C51_FAST");
+    g_c51_fast = e ? (atoi(e) != 0) : 1;
+  }
+  return g_c51_fast != 0;
+}
+void a0_set_c51_fast(int on) { g_c51_fast = on != 0; }
 
 extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const float* tgt_logits,
                            const float* qsel, const float* atoms, int32_t M, float vmin, float vmax, float* grad,
@@ -365,6 +579,11 @@ extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const
   A0_REQUIRE(M >= 2 && M <= C51_MAXR * 32, "a0_loss_c51: num_atoms %d outside [2,%d]", M, C51_MAXR * 32);
   A0_REQUIRE(vmax > vmin, "a0_loss_c51: vmax must exceed vmin");
   if (c->B == 0) return A0_OK;
+  if (qsel && c->A <= C51_SPEC_A && M <= 64 && a0_option_c51_fast()) {
+    A0_LAUNCH(a0_k4_c51_fast, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
+              a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, grad, target_prob);
+    return A0_OK;
+  }
   A0_LAUNCH(a0_k4_c51, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
             a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, grad, target_prob);
   return A0_OK;

@@ -71,6 +71,10 @@ const char* a0_last_error(void);
  * 2048 marks and 2048 new frames) applies its marks and its append in ONE launch instead of
  * a0_pt_mark followed by a0_rb_append.  Same shard state either way.                              */
 #define A0_OPT_FUSED_INGEST 4
+/* A0_OPT_C51_FAST (default 1; A0_C51_FAST in the environment): a0_loss_c51 with qsel given, at most 6
+ * actions and at most 64 atoms runs the short-dependent-chain kernel; 0 forces the general kernel.
+ * Bit-identical outputs.                                                                         */
+#define A0_OPT_C51_FAST 5
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------

@@ -344,3 +344,43 @@ def test_fused_ingest_launch_and_dynamic_publication_equal_the_separate_launches
         lib.a0_set_option(4, 1)
     for a, b in zip(*states):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("A,M,B", [(4, 51, 32), (6, 64, 37), (3, 33, 5), (1, 2, 9), (5, 51, 512), (4, 32, 64)])
+def test_c51_short_chain_kernel_is_bit_identical_to_the_general_kernel_and_matches_the_oracle(A, M, B):
+    """a0_loss_c51 has a second kernel for the Atari shape (qsel given, A <= 6, M <= 64) whose dependent
+    instruction chain is shorter (local arg-max, paired reductions, u = l + 1, read-modify-write bins,
+    16-byte gradient stores).  A0_OPT_C51_FAST = 0 forces the general kernel: loss, gradient, priorities,
+    projected distribution and max_p must agree bit for bit, and both with the oracle to 1e-5 -- including
+    returns that clamp at the support's ends, terminal transitions (all mass to one bin), exact-integer
+    bin positions, ties in the selection values, unaligned gradient blocks (A*M not a multiple of 4)."""
+    from agent0_b200 import losses as L
+    lib = _lib.load()
+    rng = np.random.RandomState(A * M + B)
+    a = rng.randint(0, A, B).astype(np.int64)
+    r = rng.choice([-1.0, 0.0, 1.0, 9.99, -30.0, 30.0, 0.4, 2.0], B).astype(np.float32)
+    d = (rng.rand(B) < 0.3).astype(np.float32)
+    w = (rng.rand(B) + 0.05).astype(np.float32)
+    lg, tg = [(rng.randn(B, A, M) * 2).astype(np.float32) for _ in range(2)]
+    qs = rng.randn(B, A).astype(np.float32)
+    qs[::3] = np.round(qs[::3])                       # ties: the first maximum wins
+    atoms = np.linspace(-10, 10, M).astype(np.float32)
+    dv = lambda x: torch.as_tensor(x).cuda()
+    outs = []
+    try:
+        for fast in (1, 0):
+            assert lib.a0_set_option(5, fast) == 0
+            mp = torch.full((1,), 0.25, device="cuda")
+            o = L.c51_loss(dv(lg), dv(tg), dv(atoms), dv(a), dv(r), dv(d), dv(w), float(np.float32(0.99 ** 3)), -10.0, 10.0,
+                           qsel=dv(qs), want_target_prob=True, max_p=mp)
+            torch.cuda.synchronize()
+            outs.append((o, mp))
+    finally:
+        lib.a0_set_option(5, 1)
+    (f, mpf), (g, mpg) = outs
+    assert torch.equal(f.loss, g.loss) and torch.equal(f.grad, g.grad) and torch.equal(f.prio, g.prio)
+    assert torch.equal(f.target_prob, g.target_prob) and torch.equal(mpf, mpg)
+    loss, grad, m = OL.c51(lg, tg, qs, a, r, d, w, 0.99, 3, atoms, -10.0, 10.0)
+    np.testing.assert_allclose(_np(f.target_prob), m, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_np(f.loss), loss, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(_np(f.grad), grad, rtol=1e-5, atol=1e-5)

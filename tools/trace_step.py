@@ -1,0 +1,86 @@
+"""Device-side timeline of one replay+target step (the -DA0_TRACE build): per kernel launch, when its
+CTAs entered, passed griddepcontrol.wait / received their input, and finished (%globaltimer).
+Usage: A0_LIB=agent0_b200/libagent0_b200_trace.so python tools/trace_step.py [B] [L] [overlap 0/1]"""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("A0_LIB", os.path.join(ROOT, "agent0_b200", "libagent0_b200_trace.so"))
+import numpy as np
+import torch
+
+import bench as BN
+from agent0_b200 import _lib
+from agent0_b200.config import make_config
+from agent0_b200.replay import ReplayDataset
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+overlap = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
+lib = _lib.load()
+lib.a0_trace_set.restype = C.c_int
+lib.a0_trace_set.argtypes = [C.c_void_p, C.c_void_p]
+wl = dict(BN.WORKLOADS["c51_b32"]); wl["B"] = B
+cfg = make_config("c51", per=True, n_step=3, batch_size=B, replay_size=1_000_000, double_q=True, dueling=True, num_envs=16, action_dim=4)
+rp = ReplayDataset(cfg, native_nstep=True)
+BN.fill_shard(rp, 1_000_000, 16, 1234, torch)
+hp = BN.HotPath(rp, wl, L, 4, torch)
+hp.overlap_sg = overlap
+g = BN.capture_step(hp, torch)
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+NREC = 1 << 16
+buf = torch.zeros(NREC, 12, dtype=torch.int64, device="cuda")       # {t0, t1, t2, kid | blk << 32, x[4]}
+cur = torch.zeros(1, dtype=torch.int32, device="cuda")
+assert lib.a0_trace_set(buf.data_ptr(), cur.data_ptr()) == 0
+g.replay(); g.replay()
+torch.cuda.synchronize()
+n = int(cur.item())
+rec = buf[:n].cpu().numpy()
+lib.a0_trace_set(None, None)
+t0, t1, t2 = rec[:, 0], rec[:, 1], rec[:, 2]
+kid = (rec[:, 3] & 0xffffffff).astype(np.int64)
+# second replay only: split at the largest gap between K2a records
+k2 = np.sort(t0[kid == 2])
+cut = k2[len(k2) // 2]
+sel = t0 >= cut - 500
+t0, t1, t2, kid = t0[sel], t1[sel], t2[sel], kid[sel]
+xs = rec[sel][:, 4:12]
+base = t0.min()
+rows = []
+names = {2: "K2a", 3: "K3", 4: "K4", 5: "K2b"}
+if (kid == 4).any():
+    t2 = np.where(kid == 4, t0, t2)          # K4's t2 holds cycles, not time
+for k in (2, 3, 5):
+    m = kid == k
+    if m.any():
+        rows.append((names[k], int(m.sum()), (t0[m].min() - base) / 1e3, (np.median(t2[m]) - base) / 1e3, (t2[m].max() - base) / 1e3,
+                     (t1[m].max() - base) / 1e3))
+m = kid == 4
+o = np.argsort(t0[m])
+per = max(1, int(m.sum()) // L)
+for i in range(L):
+    s = o[i * per:(i + 1) * per]
+    if len(s):
+        rows.append((f"K4[{i}]", len(s), (t0[m][s].min() - base) / 1e3, (np.median(t2[m][s]) - base) / 1e3, (t2[m][s].max() - base) / 1e3,
+                     (t1[m][s].max() - base) / 1e3))
+rows.sort(key=lambda r: r[2])
+m4 = kid == 4
+if m4.any():
+    # K4 stores clock64 (SM cycles) at the wait's return in t2 and at eight points after it
+    c0 = rec[sel][:, 2][m4]
+    pts = np.concatenate([c0[:, None], xs[m4]], 1)
+    d = np.median(np.diff(pts, axis=1), 0)
+    lab = ["loads land", "arg-max | online max", "target softmax | online sum-exp", "projection arithmetic", "segmented scan + bins",
+           "CE | mass reductions", "gradient stores", "emit loss / priority / max_p"]
+    print("K4 (C51) warp-0 phases after griddepcontrol.wait, median SM cycles over", int(m4.sum()), "CTAs (1965 cycles = 1 us):")
+    print("   " + " | ".join(f"{l} {int(v)}" for l, v in zip(lab, d)) + f" | total {int(d.sum())}")
+print(f"B={B} L={L} overlap={overlap} records={n}; times in us from the first traced entry; globaltimer tick = "
+      f"{int(np.min(np.diff(np.unique(np.concatenate([t0, t1])))))} ns")
+print(f"{'kernel':8s} {'ctas':>5s} {'first entry':>12s} {'median ready':>13s} {'last ready':>11s} {'last exit':>10s}")
+for r in rows:
+    print(f"{r[0]:8s} {r[1]:5d} {r[2]:12.2f} {r[3]:13.2f} {r[4]:11.2f} {r[5]:10.2f}")
