@@ -130,6 +130,7 @@ enum { A0_PDL_K4 = 1, A0_PDL_K2 = 2, A0_PDL_K3 = 4, A0_PDL_K1 = 8, A0_PDL_FORCE 
 constexpr int A0_PDL_DEFAULT = A0_PDL_K4;   // measured: K4-only is best at B=32 and B=512 (profiles/r01_kernel_options.json)
 bool a0_pdl_enabled(int kernel_class);
 int a0_option_k2b_levels();
+constexpr int A0_K3_L2_DEFAULT = 4;              // L2 hints of the default gather (A0_OPT_K3_L2): auto
 constexpr int A0_K2B_BULK_MIN_DEFAULT = 2048;    // from this many indices (and >= 4 per 4096-leaf chunk): leaf writes + chunk rebuild on all SMs
 int a0_option_k2b_bulk_min();
 bool a0_option_fused_ingest();

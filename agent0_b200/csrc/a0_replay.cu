@@ -56,6 +56,20 @@ int a0_option_k2b_bulk_min() {
   }
   return g_k2b_bulk_min;
 }
+static int g_k3_l2 = -1;
+// Measured (B200, profiles/): with 640 transitions per launch (68 MB, half the L2) evict_first on both
+// directions shortens the batch-32 step by 6 % -- K4's inputs, the tree and the records stay in L2 -- and
+// the gather itself by 4 %; at 10 240 transitions (1.1 GB per launch) nothing else survives in L2 either
+// way and the hints cost 0.4 %.  "Auto" applies them while the launch moves less than the L2 holds.
+static int a0_option_k3_l2(int64_t launch_bytes) {
+  if (g_k3_l2 < 0) {
+    const char* e = getenv("A0_K3_L2");
+    g_k3_l2 = e ? atoi(e) : A0_K3_L2_DEFAULT;
+    if (g_k3_l2 < 0 || g_k3_l2 > 4) g_k3_l2 = A0_K3_L2_DEFAULT;
+  }
+  if (g_k3_l2 == 4) return launch_bytes <= (int64_t)100 << 20 ? 3 : 0;
+  return g_k3_l2;
+}
 static int g_fused_ingest = -1;
 bool a0_option_fused_ingest() {
   if (g_fused_ingest < 0) {
@@ -67,6 +81,11 @@ bool a0_option_fused_ingest() {
 extern "C" int a0_set_option(int32_t option, int64_t value) {
   if (option == A0_OPT_FUSED_INGEST) { g_fused_ingest = value != 0; return A0_OK; }
   if (option == A0_OPT_C51_FAST) { a0_set_c51_fast(value != 0); return A0_OK; }
+  if (option == A0_OPT_K3_L2) {
+    A0_REQUIRE(value >= 0 && value <= 4, "a0_set_option: A0_OPT_K3_L2 must be 0..4");
+    g_k3_l2 = (int)value;
+    return A0_OK;
+  }
   if (option == A0_OPT_PDL) { g_pdl = (int)value & 15; return A0_OK; }
   if (option == A0_OPT_K2B_LEVELS) {
     A0_REQUIRE(value == 3 || value == 4, "a0_set_option: A0_OPT_K2B_LEVELS must be 3 or 4");
@@ -254,6 +273,7 @@ struct A0GatherArgs {
   float* done32_out;
   int64_t* boot_out;
   long long* mail;       // != NULL: record positions arrive through the sampler's mailbox (a0_rb_sample_gather)
+  int32_t l2_hints;      // bit 0: frame reads evict_first, bit 1: output stores evict_first (A0_OPT_K3_L2)
 };
 
 // Walks the n-step window that starts at record p0 (whose info word is already loaded), writes
@@ -419,6 +439,25 @@ __device__ __forceinline__ void a0_mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void a0_bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
 }
+// The same copies with an L2 eviction-priority hint.  The gather streams: a sampled frame is read once
+// out of a multi-GB ring (no reuse before it is evicted anyway), so its lines are marked evict_first
+// and stop displacing what the step re-reads from L2 -- the sum-tree, the records, and the network
+// outputs K4 consumes (device timeline: K4's first loads land in 850 cycles without the gather's
+// traffic in L2 and 1500 with it).
+__device__ __forceinline__ uint64_t a0_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void a0_bulk_load_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void a0_bulk_store_hint(void* gdst, uint32_t smem_src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(gdst), "r"(smem_src), "r"(bytes), "l"(pol) : "memory");
+}
 
 // Distinct frames of the two stacks: uslot[u] = frame slot, dmask[u] = stack positions it fills.
 // a0_unique_add registers stack position j (fully unrolled: the arrays stay in registers).
@@ -490,6 +529,16 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   const A0RecInfo info0 = g.rec_info[p0];
   A0Spec sp;
   a0_spec_fetch(g, p0, sp);              // the guessed rest of the window, same round trip as the first record
+  const uint64_t pol = a0_policy_evict_first();
+  const bool hint_ld = g.l2_hints & 1, hint_st = g.l2_hints & 2;
+  auto load = [&](uint32_t dst, const void* src, uint32_t bar) {
+    if (hint_ld) a0_bulk_load_hint(dst, src, F, bar, pol);
+    else a0_bulk_load(dst, src, F, bar);
+  };
+  auto store = [&](void* dst, uint32_t src) {
+    if (hint_st) a0_bulk_store_hint(dst, src, F, pol);
+    else a0_bulk_store(dst, src, F);
+  };
   if (!g.mail) {
 #pragma unroll
     for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
@@ -509,7 +558,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   const int U0 = U;                      // <= A0_STACK == K3_RING
 #pragma unroll
   for (int u = 0; u < K3_RING; ++u)
-    if (u < U0) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
+    if (u < U0) load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, bar0 + 8 * u);
   // the n-step walk and the next stack, while those loads are in flight
   int4 sc;
   a0_walk_window_spec(g, b, p0, info0, sp, ok, sc);
@@ -524,7 +573,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   if (!ok && g.action_out) g.action_out[b] = -1;
 #pragma unroll
   for (int u = 0; u < K3_RING; ++u)
-    if (u >= U0 && u < U) a0_bulk_load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, F, bar0 + 8 * u);
+    if (u >= U0 && u < U) load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, bar0 + 8 * u);
   uint8_t* out = g.frames_out + (size_t)b * A0_SLOTS * F;
 #pragma unroll
   for (int u = 0; u < A0_SLOTS; ++u) {
@@ -534,11 +583,11 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < A0_SLOTS; ++j)
-        if (dmask[u] & (1u << j)) a0_bulk_store(out + (size_t)j * F, buf0 + r * F, F);
+        if (dmask[u] & (1u << j)) store(out + (size_t)j * F, buf0 + r * F);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       if (u + K3_RING < U) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        a0_bulk_load(buf0 + r * F, g.frames + (size_t)uslot[u + K3_RING] * F, F, bar0 + 8 * r);
+        load(buf0 + r * F, g.frames + (size_t)uslot[u + K3_RING] * F, bar0 + 8 * r);
       }
     }
   }
@@ -883,6 +932,7 @@ static int a0_gather_cvt(a0_replay_t* h, const int64_t* idx, int32_t count, int3
   g.frames_out = nullptr; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
   g.mail = nullptr;
+  g.l2_hints = 0;
   const size_t smem = (size_t)K3_RING * h->F;
   static thread_local size_t configured[64] = {0};       // one table per OutT instantiation
   if (h->device < 64 && configured[h->device] < smem) {
@@ -914,6 +964,7 @@ static int a0_k3_smem_attr(a0_replay_t* h, size_t smem) {
   static thread_local size_t configured[64] = {0};
   if (h->device < 64 && configured[h->device] < smem) {
     A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    A0_CUDA(cudaFuncSetAttribute(a0_k3_gather_tma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured[h->device] = smem;
   }
   return A0_OK;
@@ -930,6 +981,7 @@ int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int
   g.frames_out = out.frames; g.action_out = out.action; g.reward64_out = out.reward64;
   g.reward32_out = out.reward32; g.done8_out = out.done8; g.done32_out = out.done32; g.boot_out = out.boot;
   g.mail = mail;
+  g.l2_hints = a0_option_k3_l2((int64_t)count * 16 * h->F);
   const size_t smem = (size_t)K3_RING * h->F;
   int rc = a0_k3_smem_attr(h, smem);
   if (rc) return rc;
@@ -957,6 +1009,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
   g.mail = nullptr;
+  g.l2_hints = a0_option_k3_l2((int64_t)count * 16 * h->F);
   if (variant == 3) {
     const size_t smem = (size_t)K3S_RING * h->F;
     static thread_local size_t configured3[64] = {0};

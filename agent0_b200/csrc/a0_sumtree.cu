@@ -238,6 +238,17 @@ static int a0_sample_launch(a0_replay_t* h, const float* u, const A0Rng& rng, in
   A0_REQUIRE(total / batch <= A0_MAX_BATCHES, "%s: at most %d batches per call", who, A0_MAX_BATCHES);
   A0DeviceGuard guard(h->device);
   const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
+  if (mail) {
+    // The gather's CTAs (28 KB of shared memory each) can only join an SM whose shared-memory carve-out
+    // already fits them: an SM running sampler CTAs under the default (L1-heavy) carve-out is closed
+    // to them until it drains -- device timeline: only (148 - 80) x 7 = 476 of 640 gather CTAs started
+    // under the sampler, the rest 6 us later.  Same carve-out for both kernels: everything co-resides.
+    static thread_local bool carved[64] = {false};
+    if (h->device < 64 && !carved[h->device]) {
+      A0_CUDA(cudaFuncSetAttribute(a0_k2a_sample, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carved[h->device] = true;
+    }
+  }
   A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, A0_PDL_K2, h->tree, h->P, h->D, u, total, batch,
             top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter,
             reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr), rng, mail);
@@ -538,7 +549,13 @@ __device__ __forceinline__ void
 a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
               const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
               float alpha, float eps, float* __restrict__ max_p, int32_t* __restrict__ winner,
-              int32_t* __restrict__ dirty, int32_t chunk_log, const int cta, const int nctas, const A0Report rep) {
+              int32_t* __restrict__ dirty, int32_t chunk_log, const int cta, const int nctas, const A0Report rep,
+              unsigned long long* _tx = nullptr) {
+#ifdef A0_TRACE
+#define K2B_TX(i) do { if (_tx) _tx[i] = (unsigned long long)clock64(); } while (0)
+#else
+#define K2B_TX(i) do {} while (0)
+#endif
   const bool single = nctas == 1;
   const int gtid = cta * K2P_THREADS + threadIdx.x;
   const int gstride = nctas * K2P_THREADS;
@@ -578,6 +595,7 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     if ((threadIdx.x & 31) == 0) a0_atomic_max_pos(max_p, mx);   // max_p = max(max_p, max loss), replay.py:59
   }
   a0_cluster_sync(single);
+  K2B_TX(0);
 #pragma unroll
   for (int s = 0; s < K2P_PER_THREAD; ++s) {                 // write (the highest k wins)
     if (pos[s] < 0 || __ldcg(winner + pos[s]) != kk[s]) continue;
@@ -594,6 +612,7 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     if (dirty) dirty[pos[s] >> chunk_log] = 1;               // hybrid: a0_k2b_rebuild recomputes the touched chunks
   }
   a0_cluster_sync(single);
+  K2B_TX(1);
 #pragma unroll
   for (int s = 0; s < K2P_PER_THREAD; ++s)                   // release
     if (pos[s] >= 0) winner[pos[s]] = -1;
@@ -615,19 +634,23 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     depth -= first;
     shift += first;
     a0_cluster_sync(single);
+    K2B_TX(2);
   }
   while (depth > top) {
     a0_climb_all<K2P_LEVELS>(tree, P, pos, shift);
     depth -= K2P_LEVELS;
     shift += K2P_LEVELS;
     a0_cluster_sync(single);
+    K2B_TX(3);
   }
   // ---- dense part: CTA 0 rebuilds levels top-1 .. 0 from the 2^top nodes of level `top` -----------
   if (cta != 0 || top == 0) return;
   __shared__ float buf[2][1 << K2P_TOP];
   const int n = 1 << top;
+  K2B_TX(4);
   for (int i = threadIdx.x; i < n; i += K2P_THREADS) buf[0][i] = __ldcg(tree + n + i);
   __syncthreads();
+  K2B_TX(5);
   int cur = 0;
   for (int l = top - 1; l >= 0; --l) {
     const int cnt = 1 << l;
@@ -639,6 +662,7 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     __syncthreads();
     cur ^= 1;
   }
+  K2B_TX(6);
 }
 
 template <int K2P_LEVELS>
@@ -650,8 +674,15 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
   A0_T0();
   A0_PDL_PROLOGUE();
   A0_TMID();
+#ifdef A0_TRACE
+  const long long _c0 = clock64();
+  a0_paths_body<K2P_LEVELS>(tree, P, D, N, idx64, idx32, vals, count, mode, alpha, eps, max_p, winner, dirty, chunk_log,
+                            (int)blockIdx.x, (int)gridDim.x, rep, threadIdx.x == 0 ? _tx : nullptr);
+  _tx[7] = (unsigned long long)_c0;
+#else
   a0_paths_body<K2P_LEVELS>(tree, P, D, N, idx64, idx32, vals, count, mode, alpha, eps, max_p, winner, dirty, chunk_log,
                             (int)blockIdx.x, (int)gridDim.x, rep);
+#endif
   if (threadIdx.x == 0) A0_TEND(5);
 }
 

@@ -75,6 +75,11 @@ const char* a0_last_error(void);
  * actions and at most 64 atoms runs the short-dependent-chain kernel; 0 forces the general kernel.
  * Bit-identical outputs.                                                                         */
 #define A0_OPT_C51_FAST 5
+/* A0_OPT_K3_L2 (A0_K3_L2 in the environment): L2 eviction hints of the default gather's bulk copies.
+ * 0..3: bit 0 = frame reads marked evict_first, bit 1 = output stores marked evict_first;
+ * 4 (default) = both while one launch moves less than 100 MB (it then leaves the sum-tree, the
+ * records and the learner's tensors in L2), none for larger launches.  Results do not change.    */
+#define A0_OPT_K3_L2 6
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------

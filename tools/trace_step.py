@@ -20,6 +20,7 @@ from agent0_b200.replay import ReplayDataset
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 overlap = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
+k4_only = len(sys.argv) > 4 and sys.argv[4] == "k4only"      # the K4 chain alone: are its inputs L2 hits without K3's traffic?
 lib = _lib.load()
 lib.a0_trace_set.restype = C.c_int
 lib.a0_trace_set.argtypes = [C.c_void_p, C.c_void_p]
@@ -29,10 +30,25 @@ rp = ReplayDataset(cfg, native_nstep=True)
 BN.fill_shard(rp, 1_000_000, 16, 1234, torch)
 hp = BN.HotPath(rp, wl, L, 4, torch)
 hp.overlap_sg = overlap
-g = BN.capture_step(hp, torch)
+if k4_only:
+    hp.rp.push_dynamic()
+    hp.step(); hp.step()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        hp.sample()
+        for k in range(L):
+            hp.target_loss(k)
+else:
+    g = BN.capture_step(hp, torch)
 for _ in range(5):
     g.replay()
 torch.cuda.synchronize()
+if os.environ.get("A0_TOUCH_TREE"):            # experiment: pull the whole tree (and the claim scratch) into L2 once
+    _ = float(rp.tree.sum())
+    for _ in range(int(os.environ["A0_TOUCH_TREE"])):
+        g.replay()
+    torch.cuda.synchronize()
 NREC = 1 << 16
 buf = torch.zeros(NREC, 12, dtype=torch.int64, device="cuda")       # {t0, t1, t2, kid | blk << 32, x[4]}
 cur = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -79,6 +95,24 @@ if m4.any():
            "CE | mass reductions", "gradient stores", "emit loss / priority / max_p"]
     print("K4 (C51) warp-0 phases after griddepcontrol.wait, median SM cycles over", int(m4.sum()), "CTAs (1965 cycles = 1 us):")
     print("   " + " | ".join(f"{l} {int(v)}" for l, v in zip(lab, d)) + f" | total {int(d.sum())}")
+m3 = kid == 3
+if m3.any():
+    q = [0, 10, 50, 90, 100]
+    f = lambda a: " ".join("%.2f" % ((np.percentile(a, x) - base) / 1e3) for x in q)
+    print("K3 CTAs, percentiles", q, "(us): entry", f(t0[m3]), "| position known", f(t2[m3]), "| exit", f(t1[m3]))
+    ent = np.round((t0[m3] - base) / 1e3, 1)
+    vals, cnts = np.unique(ent, return_counts=True)
+    print("   entry-time histogram (us: CTAs):", ", ".join(f"{v}: {c}" for v, c in zip(vals, cnts)))
+    print("   per-CTA gather time (position known -> exit), us: median %.2f  p90 %.2f  max %.2f" % tuple(
+        np.percentile((t1[m3] - t2[m3]) / 1e3, [50, 90, 100])))
+m5 = kid == 5
+if m5.any():
+    x5 = xs[m5][0]
+    c0 = x5[7]
+    lab5 = ["claim", "leaf write", "release + first climb", "two 3-level climbs", "(to dense)", "dense load", "dense levels"]
+    pts = [c0] + [x5[i] for i in range(7)]
+    print("K2b (one CTA) phases, SM cycles: " + " | ".join(f"{l} {int(pts[i + 1] - pts[i])}" for i, l in enumerate(lab5)
+                                                                 if pts[i + 1] and pts[i]) + f" | total {int(x5[6] - c0)}")
 print(f"B={B} L={L} overlap={overlap} records={n}; times in us from the first traced entry; globaltimer tick = "
       f"{int(np.min(np.diff(np.unique(np.concatenate([t0, t1])))))} ns")
 print(f"{'kernel':8s} {'ctas':>5s} {'first entry':>12s} {'median ready':>13s} {'last ready':>11s} {'last exit':>10s}")
