@@ -11,6 +11,8 @@
 //   go left iff (t < left) || !(right > 0);  going right: t = fl32(t - left).
 // The tree (2P floats, 8 MB at 1 M leaves, 16.8 MB at 2 M) is L2-resident: these kernels are
 // latency-bound, not HBM-bound.
+#include <stdlib.h>
+
 #include "a0_common.cuh"
 #ifdef A0_TRACE
 A0_TRACE_SETTER(a0_trace_set_sumtree)
@@ -543,6 +545,46 @@ __device__ __forceinline__ void a0_climb_all(float* __restrict__ tree, int64_t P
   }
 }
 
+// Levels top-1 .. 0 from the 2^top nodes in heap[n .. 2n) (n = 2^top, heap in shared memory, one CTA of
+// 1024 threads), every node written to the tree.  With 4096 inputs: four per thread -- two levels
+// inside the thread, five by warp shuffles, one block barrier, the last five by warp 0: two 1024-thread
+// barriers (~300 cycles each, device timeline) instead of twelve.
+__device__ __forceinline__ void a0_dense_top(float* heap, int top, float* __restrict__ tree) {
+  const int tid = threadIdx.x;
+  const int n = 1 << top;
+  if (top == K2P_TOP) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const float4 q4 = *reinterpret_cast<const float4*>(heap + n + 4 * tid);
+    const float x0 = __fadd_rn(q4.x, q4.y), x1 = __fadd_rn(q4.z, q4.w);
+    *reinterpret_cast<float2*>(heap + (n >> 1) + 2 * tid) = make_float2(x0, x1);
+    float v = __fadd_rn(x0, x1);
+    heap[(n >> 2) + tid] = v;
+#pragma unroll
+    for (int j = 1; j <= 5; ++j) {
+      v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1 << (j - 1)));       // left child + right child
+      if ((lane & ((1 << j) - 1)) == 0) heap[(n >> (2 + j)) + (tid >> j)] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      v = heap[32 + lane];
+#pragma unroll
+      for (int j = 1; j <= 5; ++j) {
+        v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1 << (j - 1)));
+        if ((lane & ((1 << j) - 1)) == 0) heap[(32 >> j) + (lane >> j)] = v;
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int l = top - 1; l >= 0; --l) {
+      const int cnt = 1 << l;
+      for (int i = cnt + tid; i < 2 * cnt; i += (int)blockDim.x) heap[i] = __fadd_rn(heap[2 * i], heap[2 * i + 1]);
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += (int)blockDim.x)
+    if (i >= 1) tree[i] = heap[i];
+}
+
 // `cta` of `nctas` CTAs (one cluster when nctas > 1) run this body; the caller has executed the PDL prologue.
 template <int K2P_LEVELS>
 __device__ __forceinline__ void
@@ -584,6 +626,12 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
       }
     }
   }
+  // the leaf's current value is only compared with 0 (evicted since it was sampled?): nothing in this
+  // launch can turn a live leaf into 0 or back (mode 0), so it is fetched here, in the same memory round
+  // trip as the claim, instead of after the winner is known
+  float old_leaf[K2P_PER_THREAD];
+#pragma unroll
+  for (int s = 0; s < K2P_PER_THREAD; ++s) old_leaf[s] = (mode == 0 && pos[s] >= 0) ? __ldcg(tree + P + pos[s]) : 1.0f;
 #pragma unroll
   for (int s = 0; s < K2P_PER_THREAD; ++s)                   // claim
     if (pos[s] >= 0) atomicMax(winner + pos[s], kk[s]);
@@ -601,7 +649,7 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     if (pos[s] < 0 || __ldcg(winner + pos[s]) != kk[s]) continue;
     float v;
     if (mode == 0) {
-      if (!(__ldcg(tree + P + pos[s]) > 0.0f)) continue;    // evicted since it was sampled
+      if (!(old_leaf[s] > 0.0f)) continue;                  // evicted since it was sampled
       v = a0_priority(val[s], eps, alpha);
     } else if (mode == 1) {
       v = val[s] != 0.0f ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
@@ -645,23 +693,13 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   }
   // ---- dense part: CTA 0 rebuilds levels top-1 .. 0 from the 2^top nodes of level `top` -----------
   if (cta != 0 || top == 0) return;
-  __shared__ float buf[2][1 << K2P_TOP];
+  __shared__ __align__(16) float heap[2 << K2P_TOP];         // heap[i] = node i, i < 2n
   const int n = 1 << top;
   K2B_TX(4);
-  for (int i = threadIdx.x; i < n; i += K2P_THREADS) buf[0][i] = __ldcg(tree + n + i);
+  for (int i = threadIdx.x; i < n; i += K2P_THREADS) heap[n + i] = __ldcg(tree + n + i);
   __syncthreads();
   K2B_TX(5);
-  int cur = 0;
-  for (int l = top - 1; l >= 0; --l) {
-    const int cnt = 1 << l;
-    for (int i = threadIdx.x; i < cnt; i += K2P_THREADS) {
-      const float v = __fadd_rn(buf[cur][2 * i], buf[cur][2 * i + 1]);
-      buf[cur ^ 1][i] = v;
-      tree[cnt + i] = v;
-    }
-    __syncthreads();
-    cur ^= 1;
-  }
+  a0_dense_top(heap, top, tree);
   K2B_TX(6);
 }
 
@@ -686,43 +724,253 @@ a0_k2b_paths(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const in
   if (threadIdx.x == 0) A0_TEND(5);
 }
 
-// A small ingest in ONE launch: CTA 0 applies the marks to the tree (the single-CTA path climb above),
+// ------------------------------------------------------------------------------------------------
+// K2b for small counts (<= 1024 indices: the 640 sampled indices of a batch-32 Trainer.step, the marks
+// of a step's append).  The cluster path climb above communicates between its phases through global
+// memory: every phase is a store, a barrier and a dependent load -- two L2 traversals -- and the device
+// timeline (tools/trace_step.py) shows ~3000 SM cycles per phase, 20 000 for a 640-index update.
+// Here ONE CTA keeps everything it produces in shared memory:
+//   * the kernel's global LOADS are issued in two batches at the start (indices; then old leaf + the
+//     sibling of every node on the sparse part of the path + the 4096 nodes of level 12): two L2 round
+//     trips in total, nothing loaded later depends on anything stored by this kernel;
+//   * a shared-memory hash map node -> value holds every node this launch has recomputed.  Duplicate
+//     indices meet in the map (atomicMax ticket: the highest k wins, as `priority[ids] = ...` does);
+//     per level an index combines its node with the sibling's value -- from the map if this launch
+//     changed it, else the prefetched one -- and publishes the parent; phases are separated by
+//     __syncthreads() only;
+//   * levels 11..0 are rebuilt densely in a shared-memory heap and written out in one sweep; all
+//     global STORES are fire-and-forget.
+// Every node is still fl32(left + right) of its two children: the tree is bit-identical to the other
+// schedules' (tests).
+// ------------------------------------------------------------------------------------------------
+constexpr int K2S_THREADS = 1024;
+constexpr int K2S_SLOT_LOG = 14;
+constexpr int K2S_SLOTS = 1 << K2S_SLOT_LOG;          // 1024 indices x (<= 12 sparse levels + leaf) at load <= 0.81
+constexpr int K2S_MAX_SPARSE = 12;                    // D - 12 <= 12: trees of up to 2^24 leaves (the handle's limit)
+constexpr size_t K2S_SMEM = (size_t)K2S_SLOTS * 8;    // keys + values (128 KB); the dense heap (32 KB) reuses it
+
+__device__ __forceinline__ uint32_t a0_k2s_hash(uint32_t id) { return (id * 2654435761u) >> (32 - K2S_SLOT_LOG); }
+// slot of node `id`, claiming an empty one when it is not in the map yet (node ids are >= 1; 0 = empty)
+__device__ __forceinline__ uint32_t a0_k2s_insert(uint32_t* keys, uint32_t id) {
+  uint32_t s = a0_k2s_hash(id);
+  while (true) {
+    const uint32_t prev = atomicCAS(keys + s, 0u, id);
+    if (prev == 0u || prev == id) return s;
+    s = (s + 1) & (K2S_SLOTS - 1);
+  }
+}
+// slot of node `id`, or -1.  Entries are never removed, so a key inserted before the last barrier is
+// found before the probe reaches an empty slot, whatever is being inserted concurrently.
+__device__ __forceinline__ int a0_k2s_find(const volatile uint32_t* keys, uint32_t id) {
+  uint32_t s = a0_k2s_hash(id);
+  while (true) {
+    const uint32_t k = keys[s];
+    if (k == id) return (int)s;
+    if (k == 0u) return -1;
+    s = (s + 1) & (K2S_SLOTS - 1);
+  }
+}
+
+// A load the compiler may not sink to its first use: these are issued up front on purpose.
+__device__ __forceinline__ float a0_ld_now(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void
+a0_small_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
+              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+              float alpha, float eps, float* __restrict__ max_p, const A0Report rep, uint8_t* smem,
+              unsigned long long* _tx = nullptr) {
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* tval = keys + K2S_SLOTS;
+  float* heap = reinterpret_cast<float*>(smem);         // after the sparse levels: heap[i] = node i, i < 2n
+  const int tid = threadIdx.x;
+  const int top = D < K2P_TOP ? D : K2P_TOP;
+  const int S = D - top;                                // sparse levels D .. top+1 climb through the map
+  const int n = 1 << top;
+  // ---- loads that do not depend on the indices ------------------------------------------------------
+  const float maxp_in = __ldcg(max_p);
+  float dn[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dn[q] = (4 * tid + q < n) ? a0_ld_now(tree + n + 4 * tid + q) : 0.0f;
+  int64_t pos = -1;
+  float val = 0.0f;
+  if (tid < count) {
+    int64_t p;
+    bool set = true;
+    if (mode == 1) { const int32_t q = idx32[tid]; set = q >= 0; p = set ? q : ~q; }
+    else p = idx64[tid];
+    if (rep.idx) { rep.idx[tid] = p; rep.loss[tid] = vals[tid]; }
+    if (p >= 0 && p < N) {
+      pos = p;
+      val = mode == 1 ? (set ? 1.0f : 0.0f) : vals[tid];
+    }
+  }
+  {   // clear the map while those loads are in flight
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4* t4 = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < (int)(K2S_SMEM / 16); i += K2S_THREADS) t4[i] = z;
+  }
+  const bool valid = pos >= 0;
+  const uint32_t leaf = (uint32_t)(P + (valid ? pos : 0));
+  // ---- loads that depend on the index: the old leaf and the siblings along the sparse path -----------
+  float old_leaf = 0.0f, sib[K2S_MAX_SPARSE];
+#pragma unroll
+  for (int s = 0; s < K2S_MAX_SPARSE; ++s) sib[s] = 0.0f;
+  if (valid) {
+    old_leaf = a0_ld_now(tree + leaf);
+#pragma unroll
+    for (int s = 0; s < K2S_MAX_SPARSE; ++s)
+      if (s < S) sib[s] = a0_ld_now(tree + ((leaf >> s) ^ 1u));
+  }
+  if (mode == 0) {
+    const float mx = a0_warp_max(valid ? val : 0.0f);
+    if ((tid & 31) == 0) a0_atomic_max_pos(max_p, mx);      // max_p = max(max_p, max loss), replay.py:59
+  }
+  __syncthreads();                                          // the map is empty
+  K2B_TX(0);
+  uint32_t slot = 0;
+  if (valid) {
+    slot = a0_k2s_insert(keys, leaf);
+    atomicMax(tval + slot, (uint32_t)tid + 1u);             // duplicates: the highest k wins
+  }
+  __syncthreads();
+  const bool active = valid && tval[slot] == (uint32_t)tid + 1u;
+  __syncthreads();                                          // every ticket has been read
+  K2B_TX(1);
+  float myv = 0.0f;
+  if (active) {
+    bool store = true;
+    if (mode == 0) {
+      store = old_leaf > 0.0f;                              // evicted since it was sampled: the leaf stays 0
+      myv = store ? a0_priority(val, eps, alpha) : old_leaf;
+    } else if (mode == 1) {
+      myv = val != 0.0f ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
+    } else {
+      myv = val;
+    }
+    tval[slot] = __float_as_uint(myv);
+    if (store) __stcg(tree + leaf, myv);
+  }
+  __syncthreads();
+  K2B_TX(2);
+  // ---- sparse levels: parent = fl32(node + sibling), sibling from the map when this launch changed it --
+  uint32_t cur = leaf;
+  uint32_t onode[K2S_MAX_SPARSE];
+  float oval[K2S_MAX_SPARSE];
+#pragma unroll
+  for (int s = 0; s < K2S_MAX_SPARSE; ++s) {
+    if (s < S) {
+      if (active) {
+        const int f = a0_k2s_find(keys, cur ^ 1u);
+        const float sv = f >= 0 ? __uint_as_float(tval[f]) : sib[s];
+        myv = __fadd_rn(myv, sv);
+        cur >>= 1;
+        tval[a0_k2s_insert(keys, cur)] = __float_as_uint(myv);    // indices that share the parent store the same bits
+        onode[s] = cur;
+        oval[s] = myv;
+      }
+      __syncthreads();
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < K2S_MAX_SPARSE; ++s)
+      if (s < S) __stcg(tree + onode[s], oval[s]);
+  }
+  K2B_TX(3);
+  // ---- dense part: levels top-1 .. 0 in a shared-memory heap (the map is dead: same memory) ----------
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (4 * tid + q < n) heap[n + 4 * tid + q] = dn[q];
+  __syncthreads();
+  if (active) heap[cur] = myv;                              // cur is the index's level-`top` ancestor, in [n, 2n)
+  __syncthreads();
+  K2B_TX(4);
+  a0_dense_top(heap, top, tree);
+  K2B_TX(6);
+}
+
+__global__ void __launch_bounds__(K2S_THREADS)
+a0_k2b_small(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
+             const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+             float alpha, float eps, float* __restrict__ max_p, const A0Report rep) {
+  extern __shared__ __align__(16) uint8_t a0_k2s_smem[];
+  A0_T0();
+  A0_PDL_PROLOGUE();
+  A0_TMID();
+#ifdef A0_TRACE
+  const long long _c0 = clock64();
+  a0_small_body(tree, P, D, N, idx64, idx32, vals, count, mode, alpha, eps, max_p, rep, a0_k2s_smem, threadIdx.x == 0 ? _tx : nullptr);
+  _tx[7] = (unsigned long long)_c0;
+#else
+  a0_small_body(tree, P, D, N, idx64, idx32, vals, count, mode, alpha, eps, max_p, rep, a0_k2s_smem);
+#endif
+  if (threadIdx.x == 0) A0_TEND(5);
+}
+
+static int g_k2b_small = -1;
+static bool a0_option_k2b_small() {
+  if (g_k2b_small < 0) {
+    const char* e = getenv("A0_K2B_SMALL");
+    g_k2b_small = e ? (atoi(e) != 0) : 0;      // measured slower at 640 indices (shared-memory CAS throughput), see DESIGN.md
+  }
+  return g_k2b_small != 0;
+}
+void a0_set_k2b_small(int on) { g_k2b_small = on != 0; }
+
+template <typename K>
+static int a0_k2s_smem_attr(a0_replay_t* h, K kernel, bool* done) {
+  if (h->device < 64 && !done[h->device]) {
+    A0_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2S_SMEM));
+    done[h->device] = true;
+  }
+  return A0_OK;
+}
+
+// A small ingest in ONE launch: CTA 0 applies the marks to the tree (the shared-memory update above),
 // CTAs 1..n_new copy one new frame each, the rest scatter the record metadata (K1).  The two halves
-// touch disjoint state (tree / winner / max_p vs frames / records), so they need no ordering inside
-// the launch; everything that samples runs after it in stream order.  Thread 0 also publishes the
+// touch disjoint state (tree / max_p vs frames / records), so they need no ordering inside the
+// launch; everything that samples runs after it in stream order.  Thread 0 also publishes the
 // sampler's dynamic scalars when asked to.
-constexpr int K1M_MAX_MARKS = K2P_THREADS * K2P_PER_THREAD;     // what one CTA holds in registers
-constexpr int K1M_MAX_FRAMES = 2048;                            // larger appends: K1's own 128-thread CTAs
-__global__ void __launch_bounds__(K2P_THREADS)
+constexpr int K1M_MAX_MARKS = K2S_THREADS;                      // one mark per thread of CTA 0
+constexpr int K1M_MAX_FRAMES = 140;                             // one wave of CTAs (each reserves CTA 0's 128 KB); larger appends: K1's own launch
+__global__ void __launch_bounds__(K2S_THREADS)
 a0_k1_append_mark(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int32_t* __restrict__ marks,
-                  int32_t n_marks, float alpha, float* __restrict__ max_p, int32_t* __restrict__ winner,
+                  int32_t n_marks, float alpha, float* __restrict__ max_p,
                   uint8_t* __restrict__ frames, int32_t F, int64_t NF, const uint8_t* __restrict__ staged,
                   const int32_t* __restrict__ new_pos, int32_t n_new, int32_t* __restrict__ rec_slots,
                   A0RecInfo* __restrict__ rec_info, const int32_t* __restrict__ meta, int32_t m, const A0Dyn dyn) {
+  extern __shared__ __align__(16) uint8_t a0_k2s_smem[];
   A0_PDL_PROLOGUE();
   if (blockIdx.x == 0) {
     if (dyn.dyn && threadIdx.x == 0) { dyn.dyn[0] = dyn.top; dyn.dyn[1] = dyn.beta; dyn.dyn[2] = dyn.sum_offset; }
     const A0Report none = {nullptr, nullptr};
-    a0_paths_body<K2P_LEVELS_DEFAULT>(tree, P, D, N, nullptr, marks, nullptr, n_marks, 1, alpha, 0.0f, max_p, winner,
-                                      nullptr, 0, 0, 1, none);
+    a0_small_body(tree, P, D, N, nullptr, marks, nullptr, n_marks, 1, alpha, 0.0f, max_p, none, a0_k2s_smem);
     return;
   }
   const int blk = (int)blockIdx.x - 1;
   if (blk < n_new) {
-    a0_k1_copy_frame(frames, F, NF, staged, new_pos, blk, threadIdx.x, K2P_THREADS);
+    a0_k1_copy_frame(frames, F, NF, staged, new_pos, blk, threadIdx.x, K2S_THREADS);
     return;
   }
-  const int r = (blk - n_new) * K2P_THREADS + threadIdx.x;
+  const int r = (blk - n_new) * K2S_THREADS + threadIdx.x;
   if (r < m) a0_k1_write_record(rec_slots, rec_info, N, meta, r);
 }
 
 int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, float alpha, const uint8_t* new_frames,
                           const int32_t* new_frame_pos, int32_t n_new, const int32_t* rec_meta, int32_t m,
                           const A0Dyn& dyn, cudaStream_t stream) {
-  if (n_marks <= 0 || n_marks > K1M_MAX_MARKS || n_new > K1M_MAX_FRAMES) return A0_NOFIT;
-  const int blocks = 1 + n_new + (m + K2P_THREADS - 1) / K2P_THREADS;
-  A0_LAUNCH(a0_k1_append_mark, (unsigned)blocks, K2P_THREADS, 0, stream, 1, A0_PDL_K1, h->tree, h->P, h->D, h->N, marks, n_marks,
-            alpha, h->max_p, h->winner, h->frames, h->F, h->NF, new_frames, new_frame_pos, n_new, h->rec_slots, h->rec_info,
+  if (n_marks <= 0 || n_marks > K1M_MAX_MARKS || n_new > K1M_MAX_FRAMES || h->D - K2P_TOP > K2S_MAX_SPARSE) return A0_NOFIT;
+  static thread_local bool attr[64] = {false};
+  int rc = a0_k2s_smem_attr(h, a0_k1_append_mark, attr);
+  if (rc) return rc;
+  const int blocks = 1 + n_new + (m + K2S_THREADS - 1) / K2S_THREADS;
+  A0_LAUNCH(a0_k1_append_mark, (unsigned)blocks, K2S_THREADS, K2S_SMEM, stream, 1, A0_PDL_K1, h->tree, h->P, h->D, h->N, marks, n_marks,
+            alpha, h->max_p, h->frames, h->F, h->NF, new_frames, new_frame_pos, n_new, h->rec_slots, h->rec_info,
             rec_meta, m, dyn);
   return A0_OK;
 }
@@ -759,6 +1007,14 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
   // writes the leaves (claim / write / release, two cluster barriers) and the chunk rebuild runs on
   // all SMs -- measured 29 -> see DESIGN.md.  More than one cluster can hold: one CTA writes.
   const bool hybrid = count >= a0_option_k2b_bulk_min() && (int64_t)count >= 4 * chunks;
+  if (count <= K2S_THREADS && !hybrid && h->D - K2P_TOP <= K2S_MAX_SPARSE && a0_option_k2b_small()) {
+    static thread_local bool attr[64] = {false};
+    int rc = a0_k2s_smem_attr(h, a0_k2b_small, attr);
+    if (rc) return rc;
+    A0_LAUNCH(a0_k2b_small, 1, K2S_THREADS, K2S_SMEM, stream, 1, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32, vals, count, mode,
+              alpha, eps, h->max_p, rep);
+    return A0_OK;
+  }
   if (count <= K2P_MAX && !hybrid) return a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream, rep);
   if (count <= K2P_MAX) {
     int rc = a0_launch_paths(h, idx64, idx32, vals, count, mode, alpha, eps, stream, rep, h->dirty, chunk_log);

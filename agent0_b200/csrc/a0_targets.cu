@@ -399,7 +399,7 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
 __global__ void __launch_bounds__(C51_WARPS * 32)
 a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* __restrict__ tgt_logits,
                const float* __restrict__ qsel, const float* __restrict__ atoms, int32_t M, float vmin, float vmax,
-               float* __restrict__ grad, float* __restrict__ target_prob) {
+               float delta, float* __restrict__ grad, float* __restrict__ target_prob) {
   __shared__ float s_m[C51_WARPS][72];       // projected distribution (bin M may be touched when b rounds above M-1:
                                              // ignored, as in the reference's clamp), then the taken action's gradient row
   A0_T0();
@@ -469,15 +469,18 @@ a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* 
   }
   A0_TX(2);
   // ---- projection (agent.py:230-264) ---------------------------------------------------------------------
+  // The warp pays for IEEE division's slow path (a subroutine) if ANY lane's operands need it -- a zero
+  // numerator does: the idle lanes of the second atom chunk (p = 0), an atom clamped onto vmin.  Those
+  // lanes divide a harmless stand-in instead and select the exact answer (0) afterwards: same bits.
   const float gm = __fmul_rn(c.gamma_n, __fsub_rn(1.0f, d));
-  const float delta = (vmax - vmin) / (float)(M - 1);
   int k0 = -1, k1 = -1;                       // lower bin of atoms lane and lane + 32; the upper one is k + 1
   float wl0 = 0.0f, wu0 = 0.0f, wl1 = 0.0f, wu1 = 0.0f;
   {
-    const float pj0 = __fdiv_rn(p0, se), pj1 = __fdiv_rn(p1, se);
+    const float pj0 = p0 != 0.0f ? __fdiv_rn(p0, se) : 0.0f, pj1 = p1 != 0.0f ? __fdiv_rn(p1, se) : 0.0f;
     const float tz0 = fminf(fmaxf(__fadd_rn(r, __fmul_rn(gm, z0)), vmin), vmax);
     const float tz1 = fminf(fmaxf(__fadd_rn(r, __fmul_rn(gm, z1)), vmin), vmax);
-    const float bs0 = __fdiv_rn(__fsub_rn(tz0, vmin), delta), bs1 = __fdiv_rn(__fsub_rn(tz1, vmin), delta);
+    const float nu0 = __fsub_rn(tz0, vmin), nu1 = __fsub_rn(tz1, vmin);
+    const float bs0 = nu0 != 0.0f ? __fdiv_rn(nu0, delta) : 0.0f, bs1 = nu1 != 0.0f ? __fdiv_rn(nu1, delta) : 0.0f;
     const int c0 = max((int)ceilf(bs0) - 1, 0), c1 = max((int)ceilf(bs1) - 1, 0);
     if (in0) { k0 = c0; wl0 = __fmul_rn(pj0, __fsub_rn((float)(c0 + 1), bs0)); wu0 = __fmul_rn(pj0, __fsub_rn(bs0, (float)c0)); }
     if (in1) { k1 = c1; wl1 = __fmul_rn(pj1, __fsub_rn((float)(c1 + 1), bs1)); wu1 = __fmul_rn(pj1, __fsub_rn(bs1, (float)c1)); }
@@ -523,6 +526,7 @@ a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* 
     msum += b_;
   }
   A0_TX(5);
+  if (lane == 0) a0_emit(c, b, -ce);           // loss / priority / max_p leave before the gradient block does
   const float g0 = w * (expf(ls0) * msum - m0), g1 = w * (expf(ls1) * msum - m1);
   __syncwarp();                                // every lane has read its bins
   bins[lane] = in0 ? g0 : 0.0f;
@@ -552,7 +556,6 @@ a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* 
     }
   }
   A0_TX(6);
-  if (lane == 0) a0_emit(c, b, -ce);
   A0_TX(7);
 #ifdef A0_TRACE
   _t2 = _t2 * 0 + (unsigned long long)_c0;
@@ -580,8 +583,9 @@ extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const
   A0_REQUIRE(vmax > vmin, "a0_loss_c51: vmax must exceed vmin");
   if (c->B == 0) return A0_OK;
   if (qsel && c->A <= C51_SPEC_A && M <= 64 && a0_option_c51_fast()) {
+    const float delta = (vmax - vmin) / (float)(M - 1);      // the same float division the kernels do
     A0_LAUNCH(a0_k4_c51_fast, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
-              a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, grad, target_prob);
+              a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, delta, grad, target_prob);
     return A0_OK;
   }
   A0_LAUNCH(a0_k4_c51, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,

@@ -80,6 +80,10 @@ const char* a0_last_error(void);
  * 4 (default) = both while one launch moves less than 100 MB (it then leaves the sum-tree, the
  * records and the learner's tensors in L2), none for larger launches.  Results do not change.    */
 #define A0_OPT_K3_L2 6
+/* A0_OPT_K2B_SMALL (default 1; A0_K2B_SMALL in the environment): sum-tree writes of at most 1024
+ * indices run as one CTA that keeps the recomputed nodes in a shared-memory map (two L2 round trips
+ * in total) instead of the cluster path climb (one per phase).  Same tree either way.              */
+#define A0_OPT_K2B_SMALL 7
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------

@@ -264,31 +264,36 @@ def test_pdl_option_does_not_change_results():
 
 
 def test_k2b_schedules_build_the_same_tree():
-    """The three K2b schedules (cluster path climb / cluster leaf write + chunk rebuild on all SMs / one-CTA
-    write + rebuild) are selected by count and tree size; forced onto the same inputs through
-    A0_OPT_K2B_BULK_MIN they must leave bit-identical trees, duplicates and evicted leaves included."""
+    """The K2b schedules (one CTA with a shared-memory node map / cluster path climb / cluster leaf write +
+    chunk rebuild on all SMs / one-CTA write + rebuild) are selected by count and tree size; forced onto the
+    same inputs through A0_OPT_K2B_SMALL and A0_OPT_K2B_BULK_MIN they must leave bit-identical trees and
+    max_p, duplicates, out-of-range indices and evicted leaves included."""
     lib = _lib.load()
     N = 20000
-    rng = np.random.RandomState(3)
     trees = []
     try:
-        for bulk_min in (1 << 30, 1, 2048):                 # never hybrid / always (when >= 4 per chunk) / default
-            assert lib.a0_set_option(3, bulk_min) == 0
+        for small, bulk_min in ((1, 1 << 30), (0, 1 << 30), (0, 1), (1, 2048)):
+            assert lib.a0_set_option(7, small) == 0 and lib.a0_set_option(3, bulk_min) == 0
             rp = _replay(N, 1, 4)
             rp.set_priorities(torch.arange(N), torch.as_tensor((np.arange(N) % 97 + 1).astype(np.float32)))
             rp.set_priorities(torch.arange(0, N, 5), torch.zeros(N // 5))            # "evicted" leaves are skipped by updates
             r2 = np.random.RandomState(4)
-            for count in (40, 700, 5000, 16000):
+            for count in (1, 40, 700, 1024, 5000, 16000):
                 ids = r2.randint(0, N, count).astype(np.int64)
-                ids[-7:] = ids[3]
+                if count > 8:
+                    ids[-7:] = ids[3]
+                    ids[5] = N + 3                                                   # out of range: ignored
+                    ids[6:9] = ids[6] | 1                                            # siblings / shared parents
                 rp.update_priority(torch.as_tensor(ids), torch.as_tensor(np.abs(r2.randn(count)).astype(np.float32)))
-            trees.append(rp.tree.clone())
-            tr = trees[-1].cpu().numpy()
+            trees.append((rp.tree.clone(), float(rp.max_p_tensor)))
+            tr = trees[-1][0].cpu().numpy()
             for node in (1, 2, 77, rp.P // 2 + 5, rp.P - 1):
                 assert tr[node] == np.float32(tr[2 * node] + tr[2 * node + 1])
     finally:
         lib.a0_set_option(3, 2048)
-    assert torch.equal(trees[0], trees[1]) and torch.equal(trees[0], trees[2])
+        lib.a0_set_option(7, 1)
+    for t, mp in trees[1:]:
+        assert torch.equal(trees[0][0], t) and trees[0][1] == mp
     assert lib.a0_set_option(3, 0) == -1
 
 

@@ -1,6 +1,5 @@
-for m in 0 2 3; do
-A0_K3_L2=$m python bench.py --no-cpu-baseline --no-extra --workload c51_b512 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('b512 L2=$m value',d['value'],'ms',d['ms_per_step'],'k3 frac',d['roofline']['frac'])"
-done
-for m in 0 3; do
-A0_K3_L2=$m python bench.py --no-cpu-baseline --no-extra --workload qr_b512 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('qr512 L2=$m value',d['value'],'ms',d['ms_per_step'],'k3 frac',d['roofline']['frac'])"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/trace_step.py 32 20 1 2>&1 | grep "K2b\|K4 (C51)" -A1 | grep -v "^--"
+for sm in 0 1; do
+A0_K2B_SMALL=$sm python bench.py --no-cpu-baseline --no-extra 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('small=$sm value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'frac',d['roofline']['frac'])"
 done

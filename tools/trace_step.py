@@ -109,7 +109,9 @@ m5 = kid == 5
 if m5.any():
     x5 = xs[m5][0]
     c0 = x5[7]
-    lab5 = ["claim", "leaf write", "release + first climb", "two 3-level climbs", "(to dense)", "dense load", "dense levels"]
+    lab5 = ["loads + clear + barrier", "insert + ticket", "leaf value", "sparse levels", "heap fill", "dense levels", "write-out"] \
+        if os.environ.get("A0_K2B_SMALL", "0") != "0" else \
+        ["claim", "leaf write", "release + first climb", "two 3-level climbs", "(to dense)", "dense load", "dense levels"]
     pts = [c0] + [x5[i] for i in range(7)]
     print("K2b (one CTA) phases, SM cycles: " + " | ".join(f"{l} {int(pts[i + 1] - pts[i])}" for i, l in enumerate(lab5)
                                                                  if pts[i + 1] and pts[i]) + f" | total {int(x5[6] - c0)}")
