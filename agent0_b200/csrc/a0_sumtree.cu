@@ -545,43 +545,90 @@ __device__ __forceinline__ void a0_climb_all(float* __restrict__ tree, int64_t P
   }
 }
 
-// Levels top-1 .. 0 from the 2^top nodes in heap[n .. 2n) (n = 2^top, heap in shared memory, one CTA of
-// 1024 threads), every node written to the tree.  With 4096 inputs: four per thread -- two levels
-// inside the thread, five by warp shuffles, one block barrier, the last five by warp 0: two 1024-thread
-// barriers (~300 cycles each, device timeline) instead of twelve.
-__device__ __forceinline__ void a0_dense_top(float* heap, int top, float* __restrict__ tree) {
-  const int tid = threadIdx.x;
-  const int n = 1 << top;
-  if (top == K2P_TOP) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const float4 q4 = *reinterpret_cast<const float4*>(heap + n + 4 * tid);
-    const float x0 = __fadd_rn(q4.x, q4.y), x1 = __fadd_rn(q4.z, q4.w);
-    *reinterpret_cast<float2*>(heap + (n >> 1) + 2 * tid) = make_float2(x0, x1);
-    float v = __fadd_rn(x0, x1);
-    heap[(n >> 2) + tid] = v;
+// Reduces the 2^levels values in heap[n .. 2n) (n = 2^levels, heap in shared memory, heap[i] = node i of
+// the sub-tree) down to heap[1]; every thread of a 1024-thread CTA calls it.  A 1024-thread barrier
+// costs ~300 cycles here (device timeline), so levels are combined inside threads and by warp shuffles:
+// two block barriers for 4096 inputs (four per thread: two levels in the thread, five by shuffles,
+// barrier, five by warp 0), two for <= 1024 inputs, one per level only for 2048.
+template <int T>
+__device__ __forceinline__ void a0_heap_reduce(float* heap, int levels) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = 1 << levels;
+  constexpr int PER = 4096 / T;                    // inputs per thread at 4096
+  constexpr int LOGPER = PER == 4 ? 2 : PER == 8 ? 3 : PER == 16 ? 4 : 5;
+  constexpr int WARPS = T / 32;
+  constexpr int REM = WARPS == 32 ? 5 : WARPS == 16 ? 4 : WARPS == 8 ? 3 : 2;
+  static_assert(PER >= 4 && PER <= 32 && WARPS >= 4, "a0_heap_reduce: 128..1024 threads");
+  if (levels == 12) {
+    float v[PER];
 #pragma unroll
-    for (int j = 1; j <= 5; ++j) {
-      v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1 << (j - 1)));       // left child + right child
-      if ((lane & ((1 << j) - 1)) == 0) heap[(n >> (2 + j)) + (tid >> j)] = v;
+    for (int i = 0; i < PER / 4; ++i) {
+      const float4 q4 = *reinterpret_cast<const float4*>(heap + n + PER * tid + 4 * i);
+      v[4 * i] = q4.x; v[4 * i + 1] = q4.y; v[4 * i + 2] = q4.z; v[4 * i + 3] = q4.w;
+    }
+#pragma unroll
+    for (int lev = 1; lev <= LOGPER; ++lev) {      // levels inside the thread
+      const int cnt = PER >> lev;
+#pragma unroll
+      for (int i = 0; i < cnt; ++i) v[i] = __fadd_rn(v[2 * i], v[2 * i + 1]);
+      float* dst = heap + (n >> lev) + cnt * tid;
+#pragma unroll
+      for (int i = 0; i < cnt; ++i) dst[i] = v[i];
+    }
+    float x = v[0];
+#pragma unroll
+    for (int j = 1; j <= 5; ++j) {                 // five levels by warp shuffles
+      x = __fadd_rn(x, __shfl_down_sync(0xffffffffu, x, 1 << (j - 1)));       // left child + right child
+      if ((lane & ((1 << j) - 1)) == 0) heap[(n >> (LOGPER + j)) + (tid >> j)] = x;
     }
     __syncthreads();
-    if (warp == 0) {
-      v = heap[32 + lane];
+    if (warp == 0) {                               // the last REM levels: WARPS values
+      x = lane < WARPS ? heap[WARPS + lane] : 0.0f;
+#pragma unroll
+      for (int j = 1; j <= REM; ++j) {
+        x = __fadd_rn(x, __shfl_down_sync(0xffffffffu, x, 1 << (j - 1)));
+        if (lane < WARPS && (lane & ((1 << j) - 1)) == 0) heap[(WARPS >> j) + (lane >> j)] = x;
+      }
+    }
+    __syncthreads();
+  } else if (n <= T) {
+    float v = tid < n ? heap[n + tid] : 0.0f;
+    const int first = levels < 5 ? levels : 5;
+#pragma unroll
+    for (int j = 1; j <= 5; ++j) {
+      if (j <= first) {
+        v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1 << (j - 1)));
+        if (tid < n && (lane & ((1 << j) - 1)) == 0) heap[(n >> j) + (tid >> j)] = v;
+      }
+    }
+    __syncthreads();
+    const int rem = levels - first;                        // <= 5 levels left, 2^rem <= 32 values
+    if (warp == 0 && rem > 0) {
+      const int m = 1 << rem;
+      v = lane < m ? heap[m + lane] : 0.0f;
 #pragma unroll
       for (int j = 1; j <= 5; ++j) {
-        v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1 << (j - 1)));
-        if ((lane & ((1 << j) - 1)) == 0) heap[(32 >> j) + (lane >> j)] = v;
+        if (j <= rem) {
+          v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1 << (j - 1)));
+          if (lane < m && (lane & ((1 << j) - 1)) == 0) heap[(m >> j) + (lane >> j)] = v;
+        }
       }
     }
     __syncthreads();
   } else {
-    for (int l = top - 1; l >= 0; --l) {
+    for (int l = levels - 1; l >= 0; --l) {
       const int cnt = 1 << l;
-      for (int i = cnt + tid; i < 2 * cnt; i += (int)blockDim.x) heap[i] = __fadd_rn(heap[2 * i], heap[2 * i + 1]);
+      for (int i = cnt + tid; i < 2 * cnt; i += T) heap[i] = __fadd_rn(heap[2 * i], heap[2 * i + 1]);
       __syncthreads();
     }
   }
-  for (int i = tid; i < n; i += (int)blockDim.x)
+}
+// Levels top-1 .. 0 of the whole tree from its 2^top level-`top` nodes in heap[n .. 2n): reduce, write out.
+template <int T>
+__device__ __forceinline__ void a0_dense_top(float* heap, int top, float* __restrict__ tree) {
+  a0_heap_reduce<T>(heap, top);
+  const int n = 1 << top;
+  for (int i = threadIdx.x; i < n; i += T)
     if (i >= 1) tree[i] = heap[i];
 }
 
@@ -699,7 +746,7 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   for (int i = threadIdx.x; i < n; i += K2P_THREADS) heap[n + i] = __ldcg(tree + n + i);
   __syncthreads();
   K2B_TX(5);
-  a0_dense_top(heap, top, tree);
+  a0_dense_top<1024>(heap, top, tree);
   K2B_TX(6);
 }
 
@@ -890,7 +937,7 @@ a0_small_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   if (active) heap[cur] = myv;                              // cur is the index's level-`top` ancestor, in [n, 2n)
   __syncthreads();
   K2B_TX(4);
-  a0_dense_top(heap, top, tree);
+  a0_dense_top<1024>(heap, top, tree);
   K2B_TX(6);
 }
 
@@ -975,6 +1022,161 @@ int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, f
   return A0_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2b, one CTA per 4096-leaf chunk of the tree (trees of up to 2 M leaves: <= 512 CTAs, all resident).
+// The schedules above pay one L2 round trip and one barrier per PHASE (claim / write / release / three
+// climbs / dense top: ~3000 cycles each on the device timeline, 19 000 for 640 indices) because their
+// threads hand values to each other through global memory.  Here nothing a CTA needs is produced by
+// another CTA until the very end:
+//   * every CTA scans the whole index list (640 .. 16 384 entries, a few KB from L2) and keeps the
+//     entries that fall into its chunk; duplicates meet in a shared-memory ticket array (atomicMax:
+//     the highest k wins, as `priority[ids] = ...`);
+//   * it loads its 4096 leaves (one coalesced round trip, overlapped with the scan), overlays the new
+//     values, recomputes the chunk's 12 levels in shared memory (two block barriers) and writes back
+//     only the nodes on the updated paths;
+//   * the last CTA to finish (ticket) recomputes the levels above the chunk roots.
+// Two dependent L2 round trips + one grid-wide ticket for any number of indices.  Every node is
+// fl32(left + right) of its children, as everywhere else: the same tree, bit for bit (tests).
+// ------------------------------------------------------------------------------------------------
+constexpr int K2C_THREADS = 1024;                             // (256 fatter threads measured the same: 75.4 vs 74.9 us per step)
+constexpr int K2C_LOG = 12;                                  // leaves per chunk = 4096
+constexpr int K2C_MAX_COUNT = 2048;
+constexpr int K2C_MAX_CHUNKS = 592;                          // 148 SMs x 4: beyond that (> 2 M leaves) the other schedules run
+constexpr size_t K2C_SMEM = ((size_t)2 << K2C_LOG) * 4 + ((size_t)1 << K2C_LOG) * 4;    // heap + tickets = 48 KB
+
+__global__ void __launch_bounds__(K2C_THREADS)
+a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
+              const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
+              float alpha, float eps, float* __restrict__ max_p, unsigned int* __restrict__ ticket, const A0Report rep) {
+  extern __shared__ __align__(16) uint8_t a0_k2c_smem[];
+  __shared__ int s_dirty;
+  __shared__ bool s_last;
+  float* heap = reinterpret_cast<float*>(a0_k2c_smem);                      // heap[i] = node i of the chunk's sub-tree
+  int* win = reinterpret_cast<int*>(a0_k2c_smem + ((size_t)2 << K2C_LOG) * 4);
+  A0_T0();
+  A0_PDL_PROLOGUE();
+  A0_TMID();
+#ifdef A0_TRACE
+  const long long _c0 = clock64();
+#define K2C_TX(i) _tx[i] = (unsigned long long)clock64()
+#else
+#define K2C_TX(i) do {} while (0)
+#endif
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x;
+  const int clog = D < K2C_LOG ? D : K2C_LOG;
+  const int n = 1 << clog;
+  const int top_levels = D - clog;                           // depth of the chunk roots
+  const float maxp_in = __ldcg(max_p);
+  const int64_t lo = (int64_t)c << clog;                    // first leaf of the chunk
+  if (tid == 0) s_dirty = 0;
+  if (n >= 4) {
+    const float4* src = reinterpret_cast<const float4*>(tree + P + lo);
+    for (int i = tid; i < (n >> 2); i += K2C_THREADS) {
+      reinterpret_cast<float4*>(heap + n)[i] = __ldcg(src + i);
+      reinterpret_cast<int4*>(win)[i] = make_int4(-1, -1, -1, -1);
+    }
+  } else {
+    for (int i = tid; i < n; i += K2C_THREADS) {
+      heap[n + i] = __ldcg(tree + P + lo + i);
+      win[i] = -1;
+    }
+  }
+  auto position = [&](int k, bool& set) -> int64_t {
+    set = true;
+    if (mode == 1) { const int32_t q = idx32[k]; set = q >= 0; return set ? q : ~q; }
+    return idx64[k];
+  };
+  __syncthreads();
+  K2C_TX(0);
+  // ---- pass 1: tickets for the entries of this chunk (CTA 0 also: running max of the losses, report) --
+  float mx = 0.0f;
+  for (int k = tid; k < count; k += K2C_THREADS) {
+    bool set;
+    const int64_t p = position(k, set);
+    if (c == 0) {
+      if (rep.idx) { rep.idx[k] = p; rep.loss[k] = vals[k]; }
+      if (mode == 0 && p >= 0 && p < N) mx = fmaxf(mx, vals[k]);
+    }
+    if (p >= lo && p < lo + n && p < N) atomicMax(win + (int)(p - lo), k);
+  }
+  if (c == 0 && mode == 0) {
+    mx = a0_warp_max(mx);
+    if ((tid & 31) == 0) a0_atomic_max_pos(max_p, mx);      // max_p = max(max_p, max loss), replay.py:59
+  }
+  __syncthreads();
+  K2C_TX(1);
+  // ---- pass 2: the winners overlay their leaves ----------------------------------------------------------
+  for (int k = tid; k < count; k += K2C_THREADS) {
+    bool set;
+    const int64_t p = position(k, set);
+    if (!(p >= lo && p < lo + n && p < N)) continue;
+    const int l = (int)(p - lo);
+    if (win[l] != k) continue;
+    float v;
+    if (mode == 0) {
+      if (!(heap[n + l] > 0.0f)) continue;                  // evicted since it was sampled
+      v = a0_priority(vals[k], eps, alpha);
+    } else if (mode == 1) {
+      v = set ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
+    } else {
+      v = vals[k];
+    }
+    heap[n + l] = v;
+    __stcg(tree + P + p, v);
+    s_dirty = 1;
+  }
+  __syncthreads();
+  K2C_TX(2);
+  if (s_dirty) {
+    a0_heap_reduce<K2C_THREADS>(heap, clog);
+    K2C_TX(3);
+    // ---- pass 3: the nodes on the updated paths (chunk-local node h at local level j) ------------------
+    for (int k = tid; k < count; k += K2C_THREADS) {
+      bool set;
+      const int64_t p = position(k, set);
+      if (!(p >= lo && p < lo + n && p < N)) continue;
+      const int l = (int)(p - lo);
+      if (win[l] != k) continue;
+      for (int j = clog - 1; j >= 0; --j) {
+        const int h = (n + l) >> (clog - j);
+        const int64_t g = ((int64_t)1 << (top_levels + j)) + ((int64_t)c << j) + (h - (1 << j));
+        __stcg(tree + g, heap[h]);
+      }
+    }
+  }
+  K2C_TX(4);
+  if (top_levels == 0) return;                               // a single chunk: its root is the tree's root
+  // ---- the last CTA to finish recomputes the levels above the chunk roots --------------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  K2C_TX(5);
+  __threadfence();
+  const int nt = 1 << top_levels;                            // == gridDim.x chunk roots, <= K2C_MAX_CHUNKS rounded up
+  for (int i = tid; i < nt; i += K2C_THREADS) heap[nt + i] = __ldcg(tree + nt + i);
+  __syncthreads();
+  K2C_TX(6);
+  a0_dense_top<K2C_THREADS>(heap, top_levels, tree);
+  if (tid == 0) *ticket = 0u;
+#ifdef A0_TRACE
+  _tx[7] = (unsigned long long)_c0;
+#endif
+  if (tid == 0) A0_TEND(5);
+}
+
+static int g_k2b_chunks = -1;
+static bool a0_option_k2b_chunks() {
+  if (g_k2b_chunks < 0) {
+    const char* e = getenv("A0_K2B_CHUNKS");
+    g_k2b_chunks = e ? (atoi(e) != 0) : 1;
+  }
+  return g_k2b_chunks != 0;
+}
+void a0_set_k2b_chunks(int on) { g_k2b_chunks = on != 0; }
+
 static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
                            int32_t count, int32_t mode, float alpha, float eps, cudaStream_t stream,
                            const A0Report& rep, int32_t* dirty = nullptr, int32_t chunk_log = 0) {
@@ -1006,6 +1208,19 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
   // the tree (10 240 updates on a 1 M-leaf tree touch nearly every 4096-leaf chunk): the cluster only
   // writes the leaves (claim / write / release, two cluster barriers) and the chunk rebuild runs on
   // all SMs -- measured 29 -> see DESIGN.md.  More than one cluster can hold: one CTA writes.
+  if (count <= K2C_MAX_COUNT && chunks <= K2C_MAX_CHUNKS && a0_option_k2b_chunks()) {
+    // one CTA per 4096-leaf chunk in a single launch.  Measured: 640 indices on 1 M leaves 9.5 -> 8 us against
+    // the cluster climb; at 10 240 indices the leaf write + rebuild pair is faster (16.9 vs 21.5 us), so
+    // the chunk schedule is the default only up to 2048 indices
+    static thread_local bool attr[64] = {false};
+    if (h->device < 64 && !attr[h->device]) {
+      A0_CUDA(cudaFuncSetAttribute(a0_k2b_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2C_SMEM));
+      attr[h->device] = true;
+    }
+    A0_LAUNCH(a0_k2b_chunks, (unsigned)chunks, K2C_THREADS, K2C_SMEM, stream, 1, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32, vals,
+              count, mode, alpha, eps, h->max_p, h->counter + A0_MAX_BATCHES, rep);
+    return A0_OK;
+  }
   const bool hybrid = count >= a0_option_k2b_bulk_min() && (int64_t)count >= 4 * chunks;
   if (count <= K2S_THREADS && !hybrid && h->D - K2P_TOP <= K2S_MAX_SPARSE && a0_option_k2b_small()) {
     static thread_local bool attr[64] = {false};

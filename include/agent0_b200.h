@@ -80,10 +80,15 @@ const char* a0_last_error(void);
  * 4 (default) = both while one launch moves less than 100 MB (it then leaves the sum-tree, the
  * records and the learner's tensors in L2), none for larger launches.  Results do not change.    */
 #define A0_OPT_K3_L2 6
-/* A0_OPT_K2B_SMALL (default 1; A0_K2B_SMALL in the environment): sum-tree writes of at most 1024
- * indices run as one CTA that keeps the recomputed nodes in a shared-memory map (two L2 round trips
- * in total) instead of the cluster path climb (one per phase).  Same tree either way.              */
+/* A0_OPT_K2B_SMALL (default 0; A0_K2B_SMALL in the environment): sum-tree writes of at most 1024
+ * indices run as one CTA that keeps the recomputed nodes in a shared-memory hash map.  A measured
+ * alternative that lost (shared-memory CAS throughput); same tree either way.                     */
 #define A0_OPT_K2B_SMALL 7
+/* A0_OPT_K2B_CHUNKS (default 1; A0_K2B_CHUNKS in the environment): sum-tree writes of up to 2048
+ * indices on trees of up to 2 M leaves run as ONE launch with one CTA per 4096-leaf chunk (each scans
+ * the index list, recomputes its chunk in shared memory; the last CTA finishes the top levels); 0
+ * falls back to the cluster schedules selected by A0_OPT_K2B_BULK_MIN.  Same tree either way.       */
+#define A0_OPT_K2B_CHUNKS 8
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------

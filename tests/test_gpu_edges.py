@@ -264,21 +264,21 @@ def test_pdl_option_does_not_change_results():
 
 
 def test_k2b_schedules_build_the_same_tree():
-    """The K2b schedules (one CTA with a shared-memory node map / cluster path climb / cluster leaf write +
-    chunk rebuild on all SMs / one-CTA write + rebuild) are selected by count and tree size; forced onto the
-    same inputs through A0_OPT_K2B_SMALL and A0_OPT_K2B_BULK_MIN they must leave bit-identical trees and
+    """The K2b schedules (one CTA per chunk in a single launch / one CTA with a shared-memory node map / cluster
+    path climb / cluster leaf write + chunk rebuild on all SMs / one-CTA write + rebuild) are selected by count and
+    tree size; forced onto the same inputs through A0_OPT_K2B_CHUNKS, _SMALL and _BULK_MIN they must leave bit-identical trees and
     max_p, duplicates, out-of-range indices and evicted leaves included."""
     lib = _lib.load()
     N = 20000
     trees = []
     try:
-        for small, bulk_min in ((1, 1 << 30), (0, 1 << 30), (0, 1), (1, 2048)):
-            assert lib.a0_set_option(7, small) == 0 and lib.a0_set_option(3, bulk_min) == 0
+        for chunks, small, bulk_min in ((1, 0, 2048), (0, 1, 1 << 30), (0, 0, 1 << 30), (0, 0, 1), (0, 1, 2048)):
+            assert lib.a0_set_option(8, chunks) == 0 and lib.a0_set_option(7, small) == 0 and lib.a0_set_option(3, bulk_min) == 0
             rp = _replay(N, 1, 4)
             rp.set_priorities(torch.arange(N), torch.as_tensor((np.arange(N) % 97 + 1).astype(np.float32)))
             rp.set_priorities(torch.arange(0, N, 5), torch.zeros(N // 5))            # "evicted" leaves are skipped by updates
             r2 = np.random.RandomState(4)
-            for count in (1, 40, 700, 1024, 5000, 16000):
+            for count in (1, 40, 700, 1024, 2048, 5000, 16000):
                 ids = r2.randint(0, N, count).astype(np.int64)
                 if count > 8:
                     ids[-7:] = ids[3]
@@ -291,7 +291,8 @@ def test_k2b_schedules_build_the_same_tree():
                 assert tr[node] == np.float32(tr[2 * node] + tr[2 * node + 1])
     finally:
         lib.a0_set_option(3, 2048)
-        lib.a0_set_option(7, 1)
+        lib.a0_set_option(7, 0)
+        lib.a0_set_option(8, 1)
     for t, mp in trees[1:]:
         assert torch.equal(trees[0][0], t) and trees[0][1] == mp
     assert lib.a0_set_option(3, 0) == -1

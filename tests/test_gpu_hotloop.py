@@ -144,8 +144,9 @@ def test_prebound_loop_step_capture_and_single_launch_k4():
     assert torch.equal(loop.loss, per_batch[0]) and torch.equal(loop.grad, per_batch[1])
 
 
-@pytest.mark.parametrize("count,bulk_min", [(48, 2048), (640, 2048), (5000, 1), (5000, 1 << 30), (20000, 2048)])
-def test_update_report_hands_the_result_to_mapped_host_memory(count, bulk_min):
+@pytest.mark.parametrize("count,bulk_min,chunks", [(48, 2048, 1), (640, 2048, 1), (5000, 2048, 1), (48, 2048, 0), (640, 2048, 0),
+                                                   (5000, 1, 0), (5000, 1 << 30, 0), (20000, 2048, 1)])
+def test_update_report_hands_the_result_to_mapped_host_memory(count, bulk_min, chunks):
     """a0_pt_update_report = a0_pt_update + the step's (indices, losses) stored by the same kernel into
     page-locked host memory: same tree and max_p as the plain update under every K2b schedule
     (one CTA, cluster climb, cluster write + rebuild, one-CTA bulk write), host buffers equal to the
@@ -162,7 +163,7 @@ def test_update_report_hands_the_result_to_mapped_host_memory(count, bulk_min):
     loss = np.abs(rng.randn(count)).astype(np.float32) * 3
     trees = []
     try:
-        assert lib.a0_set_option(3, bulk_min) == 0
+        assert lib.a0_set_option(3, bulk_min) == 0 and lib.a0_set_option(8, chunks) == 0
         for report in (False, True):
             rp = ReplayDataset(cfg, native_nstep=True)
             rp.set_priorities(torch.arange(N), torch.as_tensor((np.arange(N) % 13 + 1).astype(np.float32)))
@@ -183,6 +184,7 @@ def test_update_report_hands_the_result_to_mapped_host_memory(count, bulk_min):
             trees.append((rp.tree.clone(), float(rp.max_p_tensor)))
     finally:
         lib.a0_set_option(3, 2048)
+        lib.a0_set_option(8, 1)
     assert torch.equal(trees[0][0], trees[1][0]) and trees[0][1] == trees[1][1]
     with pytest.raises(ValueError):
         _lib.host_map(torch.empty(4))                # a pageable tensor

@@ -109,7 +109,8 @@ m5 = kid == 5
 if m5.any():
     x5 = xs[m5][0]
     c0 = x5[7]
-    lab5 = ["loads + clear + barrier", "insert + ticket", "leaf value", "sparse levels", "heap fill", "dense levels", "write-out"] \
+    lab5 = ["leaves + init", "pass 1 (tickets)", "pass 2 (overlay)", "chunk reduce", "pass 3 (path stores)", "fence + ticket", "roots load"] \
+        if os.environ.get("A0_K2B_CHUNKS", "1") != "0" else ["loads + clear + barrier", "insert + ticket", "leaf value", "sparse levels", "heap fill", "dense levels", "write-out"] \
         if os.environ.get("A0_K2B_SMALL", "0") != "0" else \
         ["claim", "leaf write", "release + first climb", "two 3-level climbs", "(to dense)", "dense load", "dense levels"]
     pts = [c0] + [x5[i] for i in range(7)]
