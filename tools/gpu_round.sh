@@ -17,4 +17,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:a
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:a0_k3_gather -s 3 -c 2 \
     -o $OUT/k3_full python bench.py --steps 3 --warmup 3 --no-extra --no-cpu-baseline --no-graph \
     > $OUT/ncu_k3.log 2>&1
+python -m agent0_b200.build --trace > /dev/null 2>&1
+timeout 300 python tools/trace_step.py 32 20 1 > $OUT/timeline_c51_b32.txt 2>&1
+timeout 300 python tools/trace_step.py 32 20 0 > $OUT/timeline_c51_b32_no_overlap.txt 2>&1
+timeout 300 python tools/trace_step.py 512 20 1 > $OUT/timeline_c51_b512.txt 2>&1
 tail -3 $OUT/pytest_gpu.log; tail -2 $OUT/smoke.log; head -c 1500 $OUT/bench_default.json; echo; cat $OUT/bench_reference.json

@@ -100,7 +100,9 @@ if m3.any():
     q = [0, 10, 50, 90, 100]
     f = lambda a: " ".join("%.2f" % ((np.percentile(a, x) - base) / 1e3) for x in q)
     print("K3 CTAs, percentiles", q, "(us): entry", f(t0[m3]), "| position known", f(t2[m3]), "| exit", f(t1[m3]))
-    ent = np.round((t0[m3] - base) / 1e3, 1)
+    ent = (t0[m3] - base) / 1e3
+    width = max(0.1, float(np.ceil((ent.max() - ent.min()) / 30 * 10) / 10))        # at most ~30 bins
+    ent = np.round(np.floor(ent / width) * width, 1)
     vals, cnts = np.unique(ent, return_counts=True)
     print("   entry-time histogram (us: CTAs):", ", ".join(f"{v}: {c}" for v, c in zip(vals, cnts)))
     print("   per-CTA gather time (position known -> exit), us: median %.2f  p90 %.2f  max %.2f" % tuple(
