@@ -143,6 +143,7 @@ extern "C" int a0_loss_mdqn(const a0_loss_common_t* c, const float* q, const flo
 // ------------------------------------------------------------------------------------------------
 constexpr int C51_WARPS = 4;
 constexpr int C51_MAXR = 4;     // atoms per lane: M <= 128
+constexpr int C51_FAST_WARPS = 4;  // samples per CTA of the short-chain kernel
 constexpr int C51_SPEC_A = 6;   // speculative all-action row fetch up to this many actions
 
 // Adds v (keyed by destination bin) into bins[]: runs of equal adjacent keys are reduced with
@@ -393,14 +394,16 @@ a0_k4_c51(const A0Common c, const float* __restrict__ logits, const float* __res
 //     l = max(ceil(b) - 1, 0) and one key per atom drives the scan of both terms;
 //   * bins are written by read-modify-write in four fixed phases (one writer per bin and phase by
 //     construction) instead of shared-memory atomics (CAS loops);
-//   * cross-entropy and mass reduced together; the gradient block [A, M] of a sample leaves through
-//     shared memory as 16-byte stores when A*M is a multiple of 4 (204 floats at A = 4, M = 51).
+//   * cross-entropy and mass reduced together; the zeros of the sample's [A, M] gradient block (every
+//     row but the taken action's) are stored as soon as the action is known, under the latency of the
+//     input loads, so only row a is left after the arithmetic.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(C51_WARPS * 32)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* __restrict__ tgt_logits,
                const float* __restrict__ qsel, const float* __restrict__ atoms, int32_t M, float vmin, float vmax,
                float delta, float* __restrict__ grad, float* __restrict__ target_prob) {
-  __shared__ float s_m[C51_WARPS][72];       // projected distribution (bin M may be touched when b rounds above M-1:
+  __shared__ float s_m[WARPS][72];       // projected distribution (bin M may be touched when b rounds above M-1:
                                              // ignored, as in the reference's clamp), then the taken action's gradient row
   A0_T0();
   A0_PDL_PROLOGUE();
@@ -410,7 +413,7 @@ a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* 
 #endif
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
-  const int b = blockIdx.x * C51_WARPS + wid;
+  const int b = blockIdx.x * WARPS + wid;
   if (b >= c.B) return;
   const int A = c.A;
   const bool in0 = lane < M, in1 = lane + 32 < M;
@@ -433,6 +436,12 @@ a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* 
   const float z0 = in0 ? atoms[lane] : 0.0f, z1 = in1 ? atoms[lane + 32] : 0.0f;
   s_m[wid][lane] = 0.0f;
   s_m[wid][lane + 32] = 0.0f;
+  // The gradient block [A, M] of the sample is zero outside row a: those stores depend on nothing but
+  // `a`, so they go out now, under the latency of the loads above, and only row a is left for the end.
+  const int AM = A * M, r0 = a * M;
+  float* gb = grad + (size_t)b * AM;
+  for (int e = lane; e < AM; e += 32)
+    if (e < r0 || e >= r0 + M) gb[e] = 0.0f;
   // ---- action selection: first maximum, as torch.argmax (agent.py:224) ---------------------------------
   int a_star = 0;
   float best = qs[0];
@@ -528,32 +537,11 @@ a0_k4_c51_fast(const A0Common c, const float* __restrict__ logits, const float* 
   A0_TX(5);
   if (lane == 0) a0_emit(c, b, -ce);           // loss / priority / max_p leave before the gradient block does
   const float g0 = w * (expf(ls0) * msum - m0), g1 = w * (expf(ls1) * msum - m1);
-  __syncwarp();                                // every lane has read its bins
-  bins[lane] = in0 ? g0 : 0.0f;
-  bins[lane + 32] = in1 ? g1 : 0.0f;
+  if (in0) gb[r0 + lane] = g0;
+  if (in1) gb[r0 + lane + 32] = g1;
   if (target_prob) {
     if (in0) target_prob[(size_t)b * M + lane] = m0;
     if (in1) target_prob[(size_t)b * M + lane + 32] = m1;
-  }
-  __syncwarp();
-  // the sample's whole [A, M] gradient block: zeros except row a
-  const int AM = A * M, r0 = a * M;
-  float* gb = grad + (size_t)b * AM;
-  if ((AM & 3) == 0 && (((uintptr_t)grad) & 15) == 0) {
-    for (int v4 = lane; v4 < (AM >> 2); v4 += 32) {
-      const int e = 4 * v4 - r0;               // column of the first element if it lies in row a
-      float4 o4;
-      o4.x = (e >= 0 && e < M) ? bins[e] : 0.0f;
-      o4.y = (e + 1 >= 0 && e + 1 < M) ? bins[e + 1] : 0.0f;
-      o4.z = (e + 2 >= 0 && e + 2 < M) ? bins[e + 2] : 0.0f;
-      o4.w = (e + 3 >= 0 && e + 3 < M) ? bins[e + 3] : 0.0f;
-      reinterpret_cast<float4*>(gb)[v4] = o4;
-    }
-  } else {
-    for (int e = lane; e < AM; e += 32) {
-      const int col = e - r0;
-      gb[e] = (col >= 0 && col < M) ? bins[col] : 0.0f;
-    }
   }
   A0_TX(6);
   A0_TX(7);
@@ -584,8 +572,23 @@ extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const
   if (c->B == 0) return A0_OK;
   if (qsel && c->A <= C51_SPEC_A && M <= 64 && a0_option_c51_fast()) {
     const float delta = (vmax - vmin) / (float)(M - 1);      // the same float division the kernels do
-    A0_LAUNCH(a0_k4_c51_fast, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
-              a0_unpack(c), logits, tgt_logits, qsel, atoms, M, vmin, vmax, delta, grad, target_prob);
+    static int warps = 0;                                     // samples (= warps) per CTA: A0_C51_WARPS, measured default
+    if (!warps) {
+      const char* e = getenv("A0_C51_WARPS");
+      warps = e ? atoi(e) : C51_FAST_WARPS;
+      if (warps != 1 && warps != 2 && warps != 4 && warps != 8 && warps != 16 && warps != 32) warps = C51_FAST_WARPS;
+    }
+    const unsigned grid = (unsigned)((c->B + warps - 1) / warps);
+#define A0_C51_FAST_LAUNCH(W)                                                                                              \
+    A0_LAUNCH(a0_k4_c51_fast<W>, grid, W * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), logits, tgt_logits, qsel,   \
+              atoms, M, vmin, vmax, delta, grad, target_prob)
+    if (warps == 1) A0_C51_FAST_LAUNCH(1);
+    else if (warps == 2) A0_C51_FAST_LAUNCH(2);
+    else if (warps == 4) A0_C51_FAST_LAUNCH(4);
+    else if (warps == 8) A0_C51_FAST_LAUNCH(8);
+    else if (warps == 16) A0_C51_FAST_LAUNCH(16);
+    else A0_C51_FAST_LAUNCH(32);
+#undef A0_C51_FAST_LAUNCH
     return A0_OK;
   }
   A0_LAUNCH(a0_k4_c51, (unsigned)((c->B + C51_WARPS - 1) / C51_WARPS), C51_WARPS * 32, 0, (cudaStream_t)stream, 1, A0_PDL_K4,
