@@ -59,16 +59,10 @@ __device__ __forceinline__ float a0_td_target(float r, float d, float gamma_n, f
 // ------------------------------------------------------------------------------------------------
 constexpr int K4S_WARPS = 4;
 
-// log_softmax_stable (agent.py:116-119) over the lanes: (l - max) - tau * logsumexp((l - max)/tau)
-__device__ __forceinline__ float a0_tau_log_pi(float logit, bool valid, float tau, float* z_out) {
-  const float mx = a0_warp_max(valid ? logit : -INFINITY);
-  const float z = logit - mx;
-  const float s = __fdiv_rn(z, tau);                       // max over lanes of s is 0
-  const float se = a0_warp_sum(valid ? expf(s) : 0.0f);
-  *z_out = z;
-  return z - tau * logf(se);
-}
-
+// Every global load of the sample is issued up front (the taken action's Q-value comes from a shuffle of
+// the row, not from a second, action-dependent load), and M-DQN's independent reductions are advanced
+// together -- the two row maxima, then the three sums: 15 dependent shuffle steps instead of 30.  One
+// warp per sample: as for C51, the launch lasts as long as one warp's dependent chain.
 __global__ void __launch_bounds__(K4S_WARPS * 32)
 a0_k4_dqn(const A0Common c, const float* __restrict__ q, const float* __restrict__ qt_next,
           const float* __restrict__ qsel, const float* __restrict__ qt_cur, int32_t munchausen, float tau,
@@ -81,25 +75,46 @@ a0_k4_dqn(const A0Common c, const float* __restrict__ q, const float* __restrict
   const bool valid = lane < A;
   const size_t off = (size_t)b * A + lane;
   const float tn = valid ? qt_next[off] : 0.0f;
+  const float qv = valid ? q[off] : 0.0f;
+  const float sel_in = (!munchausen && qsel && valid) ? qsel[off] : 0.0f;
+  const float tc = (munchausen && valid) ? qt_cur[off] : 0.0f;
   const int a = (int)c.action[b];
+  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
   float boot, bonus = 0.0f;
   if (!munchausen) {
-    const float sel = valid ? (qsel ? qsel[off] : tn) : -INFINITY;
+    const float sel = valid ? (qsel ? sel_in : tn) : -INFINITY;
     const int a_star = a0_warp_argmax(sel, lane);
     boot = __shfl_sync(0xffffffffu, tn, a_star);
   } else {
-    float z;
-    const float tlp = a0_tau_log_pi(tn, valid, tau, &z);   // tau * log pi(.|s')
-    const float e = valid ? expf(z) : 0.0f;
-    const float p = __fdiv_rn(e, a0_warp_sum(e));          // softmax at temperature 1
+    // log_softmax_stable (agent.py:116-119) of both target rows: (l - max) - tau * logsumexp((l - max)/tau)
+    float mxn = valid ? tn : -INFINITY, mxc = valid ? tc : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float x_ = __shfl_xor_sync(0xffffffffu, mxn, o), y_ = __shfl_xor_sync(0xffffffffu, mxc, o);
+      mxn = fmaxf(mxn, x_);
+      mxc = fmaxf(mxc, y_);
+    }
+    const float zn = tn - mxn, zc = tc - mxc;
+    float sen = valid ? expf(__fdiv_rn(zn, tau)) : 0.0f;     // max over lanes of z/tau is 0
+    float sec = valid ? expf(__fdiv_rn(zc, tau)) : 0.0f;
+    const float e = valid ? expf(zn) : 0.0f;
+    float es = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float x_ = __shfl_xor_sync(0xffffffffu, sen, o), y_ = __shfl_xor_sync(0xffffffffu, sec, o);
+      const float z_ = __shfl_xor_sync(0xffffffffu, es, o);
+      sen += x_;
+      sec += y_;
+      es += z_;
+    }
+    const float tlp = zn - tau * logf(sen);                  // tau * log pi(.|s')
+    const float tlp_cur = zc - tau * logf(sec);
+    const float p = __fdiv_rn(e, es);                        // softmax at temperature 1
     boot = a0_warp_sum(valid ? p * (tn - tlp) : 0.0f);
-    float zc;
-    const float tlp_cur = a0_tau_log_pi(valid ? qt_cur[off] : 0.0f, valid, tau, &zc);
     const float at_a = __shfl_sync(0xffffffffu, tlp_cur, a);
     bonus = __fmul_rn(tau, fminf(fmaxf(at_a, lo), 0.0f));
   }
-  const float qa = q[(size_t)b * A + a];
-  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  const float qa = __shfl_sync(0xffffffffu, qv, a);
   const float T = munchausen
       ? __fadd_rn(__fadd_rn(r, bonus), __fmul_rn(__fmul_rn(c.gamma_n, __fsub_rn(1.0f, d)), boot))
       : a0_td_target(r, d, c.gamma_n, boot);
@@ -603,6 +618,8 @@ extern "C" int a0_loss_c51(const a0_loss_common_t* c, const float* logits, const
 //   loss_b = (1/Ni) sum_i sum_j |tau_j - 1[T_i < q_j]| * huber(q_j - T_i)
 //   grad_j = (w/Ni) sum_i |tau_j - 1[q_j - T_i > 0]| * clamp(q_j - T_i, -1, 1)
 // ------------------------------------------------------------------------------------------------
+constexpr int QH_SPEC_A = 8;     // all-action fetch of the quantile kernel (IQN/FQF layout) up to this many actions
+
 __device__ __forceinline__ float a0_block_sum(float v, float* red, int nwarps) {
   v = a0_warp_sum(v);
   __syncthreads();
@@ -613,6 +630,10 @@ __device__ __forceinline__ float a0_block_sum(float v, float* red, int nwarps) {
   return s;
 }
 
+// SPEC: the all-action fetch for IQN/FQF-sized samples (a separate instantiation, so that QR-200's
+// issue-bound pair loop keeps its register allocation: with both paths in one kernel it spilled inside
+// the loop and QR went from 10.6 to 14.6 us)
+template <bool SPEC>
 __global__ void __launch_bounds__(A0_MAX_QUANTILES)
 a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, const float* __restrict__ qt,
                const float* __restrict__ taus, const float* __restrict__ qsel, int32_t Ni, int32_t Nj,
@@ -634,6 +655,41 @@ a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, co
   const float* qb = q + (size_t)b * A * Nj;
   const float* tb = qt + (size_t)b * A * Ni;
 
+  float qj = 0.0f, tau = 0.0f, w;
+  int a;
+  if (SPEC) {
+    a = (int)c.action[b];
+    const float r = c.reward[b], d = c.done[b];
+    w = c.weight[b];
+    // IQN / FQF with few actions (64 x 64 or 32 x 32 pairs per sample: latency-bound, unlike QR-200):
+    // every thread fetches its quantile of ALL actions from both networks -- one [A]-row each in this
+    // layout -- and the A selection values (broadcast) in one batch of loads, then picks the taken and
+    // the arg-max action in registers: no second, action-dependent memory round trip, no shared-memory
+    // hand-off of the arg-max.
+    float qs[QH_SPEC_A], tv[QH_SPEC_A], qv[QH_SPEC_A];
+#pragma unroll
+    for (int a2 = 0; a2 < QH_SPEC_A; ++a2) {
+      const bool on = a2 < A;
+      qs[a2] = on ? qsel[(size_t)b * A + a2] : -INFINITY;
+      tv[a2] = (on && tid < Ni) ? tb[(size_t)tid * A + a2] : 0.0f;
+      qv[a2] = (on && tid < Nj) ? qb[(size_t)tid * A + a2] : 0.0f;
+    }
+    if (tid < Nj) tau = taus[(size_t)b * Nj + tid];
+    int a_star = 0;
+    float best = qs[0];
+#pragma unroll
+    for (int a2 = 1; a2 < QH_SPEC_A; ++a2)
+      if (qs[a2] > best) { best = qs[a2]; a_star = a2; }       // first maximum, as torch.argmax
+    float tsel = 0.0f;
+#pragma unroll
+    for (int a2 = 0; a2 < QH_SPEC_A; ++a2) {
+      if (a2 == a_star) tsel = tv[a2];
+      if (a2 == a) qj = qv[a2];
+    }
+    if (tid < Ni) sT[tid] = a0_td_target(r, d, c.gamma_n, tsel);
+    if (tid < Nj) sQ[tid] = qj;
+    __syncthreads();
+  } else {
   // ---- action selection ------------------------------------------------------------------------
   if (qsel) {
     if (wid == 0) {
@@ -656,16 +712,17 @@ a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, co
   }
   __syncthreads();
   const int a_star = s_astar;
-  const int a = (int)c.action[b];
-  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  a = (int)c.action[b];
+  const float r = c.reward[b], d = c.done[b];
+  w = c.weight[b];
   if (tid < Ni) sT[tid] = a0_td_target(r, d, c.gamma_n, tb[a_star * sA_t + tid * sN_t]);
-  float qj = 0.0f, tau = 0.0f;
   if (tid < Nj) {
     qj = qb[a * sA_q + tid * sN_q];
     tau = taus ? taus[(size_t)b * Nj + tid] : __fdiv_rn((float)(2 * tid + 1), 2.0f * (float)Nj);
     sQ[tid] = qj;
   }
   __syncthreads();
+  }
 
   // ---- pair loop ---------------------------------------------------------------------------------
   // With a = |u|, c = min(a, 1):  huber(u) = c * (a - c/2),  clamp(u, -1, 1) = copysign(c, u),
@@ -738,8 +795,12 @@ extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const
   if (c->B == 0) return A0_OK;
   int threads = Ni > Nj ? Ni : Nj;
   threads = ((threads + 31) / 32) * 32;
-  A0_LAUNCH(a0_k4_quantile, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt, taus,
-            qsel, Ni, Nj, grad, q_bar, taus_full, fraction_loss, grad_taus);
+  if (layout == 1 && qsel && c->A <= QH_SPEC_A && threads <= 64)
+    A0_LAUNCH(a0_k4_quantile<true>, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
+              taus, qsel, Ni, Nj, grad, q_bar, taus_full, fraction_loss, grad_taus);
+  else
+    A0_LAUNCH(a0_k4_quantile<false>, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
+              taus, qsel, Ni, Nj, grad, q_bar, taus_full, fraction_loss, grad_taus);
   return A0_OK;
 }
 
