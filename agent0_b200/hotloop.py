@@ -30,7 +30,7 @@ ALGOS = ("dqn", "mdqn", "c51", "qr", "iqn", "fqf")
 class ReplayTargetLoop:
     def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, n_step=None, double_q=True,
                  per=None, variant=0, discount=None, alpha=0.5, eps=0.01, c51=(51, -10.0, 10.0), mdqn=(0.03, -1.0),
-                 frames=None, rng_seed=None, overlap_sample_gather=True):
+                 frames=None, rng_seed=None, overlap_sample_gather=True, want_prio=False):
         """replay: ReplayDataset (native_nstep=True when n_step > 1).  outputs: dict of STATIC f32 device
         tensors holding the network outputs of all L*B sampled transitions, batch k in rows
         [k*B, (k+1)*B): ``online``, ``tgt_next`` (+ ``qsel`` [L*B,A] under double_q / for iqn, fqf;
@@ -39,6 +39,8 @@ class ReplayTargetLoop:
         [L*B, 8*F] output buffer for the gather (allocated if None).  rng_seed: the sampler draws its own
         uniforms (Philox inside K2a, device-resident call counter advanced by every launch/replay)
         instead of reading ``self.u``, which ``step()`` otherwise refills with ``uniform_()``.
+        want_prio: K4 also writes (loss+eps)^alpha per sample into ``self.newp`` (the loop itself does not need it:
+        K2b recomputes the priority from the loss).
         overlap_sample_gather: ``step()`` issues K2a and K3 through a0_rb_sample_gather (the gather runs
         under the sampler, fed draw by draw through a mailbox) instead of back to back; same results."""
         assert algo in ALGOS, algo
@@ -62,7 +64,7 @@ class ReplayTargetLoop:
         self.frames = frames if frames is not None else e(T, 8 * replay.F, dt=torch.uint8)
         self.act = e(T, dt=torch.int64); self.r64 = e(T, dt=torch.float64); self.r32 = e(T)
         self.d8 = e(T, dt=torch.uint8); self.d32 = e(T); self.boot = e(T, dt=torch.int64)
-        self.loss = e(T); self.newp = e(T)
+        self.loss = e(T); self.newp = e(T) if want_prio else None
         self.o = outputs
         self.grad = torch.empty_like(self.o["online"])
         self.frac = e(T) if algo == "fqf" else None
@@ -111,7 +113,7 @@ class ReplayTargetLoop:
         s = slice(lo, lo + count)
         p = lambda t: t[s].data_ptr()
         return _lib.LossCommon(B=count, A=self.A, action=p(self.act), reward=p(self.r32), done=p(self.d32), weight=p(self.w),
-                               gamma_n=self.gamma_n, alpha=self.alpha, eps=self.eps, loss=p(self.loss), prio=p(self.newp),
+                               gamma_n=self.gamma_n, alpha=self.alpha, eps=self.eps, loss=p(self.loss), prio=p(self.newp) if self.newp is not None else None,
                                max_p=self.rp.max_p_tensor.data_ptr()), s
 
     def _bind(self, lo, count):
