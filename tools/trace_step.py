@@ -105,6 +105,17 @@ if m3.any():
     ent = np.round(np.floor(ent / width) * width, 1)
     vals, cnts = np.unique(ent, return_counts=True)
     print("   entry-time histogram (us: CTAs):", ", ".join(f"{v}: {c}" for v, c in zip(vals, cnts)))
+    if os.environ.get("A0_TRACE_LATE"):
+        blk = (rec[sel][:, 3] >> 32).astype(np.int64)
+        o = np.argsort(-(t2[m3]))[:24]
+        k2 = kid == 2
+        k2blk = blk[k2]; k2t1 = t1[k2]
+        rows_ = []
+        for i in o:
+            bq = int(blk[m3][i])
+            j = np.flatnonzero(k2blk == (bq >> 3))
+            rows_.append((bq, round(float(t2[m3][i] - base) / 1e3, 2), round(float(k2t1[j[0]] - base) / 1e3, 2) if len(j) else None))
+        print("   latest positions (gather block, known at us, its sampler CTA's warp-0 idx-written at us):", rows_)
     print("   per-CTA gather time (position known -> exit), us: median %.2f  p90 %.2f  max %.2f" % tuple(
         np.percentile((t1[m3] - t2[m3]) / 1e3, [50, 90, 100])))
 m5 = kid == 5
