@@ -161,6 +161,7 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
     if (lane == 0) {
       const float wj = powf(__fmul_rn(top, __fdiv_rn(leaf_w, denom)), -beta);
       __stcg(weight_out + g, wj);
+      __threadfence();                   // the writer itself orders its weight before the CTA's ticket below
       s_w[warp] = wj;
     }
     __syncthreads();
@@ -177,6 +178,8 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
     __threadfence();
     const float inv = __fadd_rn(__ldcg(bmax + k), 1e-8f);
     for (int j = threadIdx.x; j < batch; j += K2A_WARPS * 32) w[j] = __fdiv_rn(__ldcg(w + j), inv);
+    __syncthreads();                   // every warp has read the batch maximum before thread 0 re-arms it (a slow
+                                       // warp would otherwise divide by 0 + 1e-8: seen under compute-sanitizer's timing)
     if (threadIdx.x == 0) {
       counter[k] = 0u; bmax[k] = 0.0f;
       if (rng_dev) a0_rng_done(rng, call, nbatches);    // this batch's CTAs have all arrived, hence all read the counter
@@ -211,6 +214,7 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
       if (j < batch) w[j] = __fdiv_rn(v[q], inv);
     }
   }
+  __syncwarp();                        // every lane holds the batch maximum before lane 0 re-arms it
   if (lane == 0) {
     counter[k] = 0u; bmax[k] = 0.0f;
     if (rng_dev) a0_rng_done(rng, call, nbatches);
