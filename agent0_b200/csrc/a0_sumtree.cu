@@ -161,7 +161,6 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
     if (lane == 0) {
       const float wj = powf(__fmul_rn(top, __fdiv_rn(leaf_w, denom)), -beta);
       __stcg(weight_out + g, wj);
-      __threadfence();                   // the writer itself orders its weight before the CTA's ticket below
       s_w[warp] = wj;
     }
     __syncthreads();
