@@ -38,6 +38,19 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.a0_rb_reset(None, None) == -1
     assert b"NULL" in lib.a0_last_error()
     assert lib.a0_pt_sample(None, None, 4, 2, 1.0, 0.4, 0.0, 0, None, None, None, None) == -1
+    # entry points added for the overlapped sampler/gather pair, the result report and the one-launch ingest
+    assert lib.a0_rb_sample_gather(None, None, 1, -1, 4, 2, 1.0, 0.4, 0.0, 0, None, None, None, 3, 0.99, None, None, None, None,
+                                   None, None, None, None) == -1
+    assert b"handle is NULL" in lib.a0_last_error()
+    assert lib.a0_pt_update_report(None, None, None, 4, 0.5, 0.01, None, None, None) == -1
+    assert lib.a0_host_map(None, None) == -1 and b"NULL" in lib.a0_last_error()
+    assert lib.a0_rb_ingest_steps_dyn(None, None, None, None, None, 0, None, None, None, 0, 0.5, 0.4, 0, None) == -1
+    assert lib.a0_rb_gather_bf16(None, None, 4, 3, 0.99, None, None, 0, None, None, None, None, None, None, None) == -1
+    for opt, bad in ((6, 9), (3, 0), (2, 5)):
+        assert lib.a0_set_option(opt, bad) == -1
+    for opt, ok in ((4, 1), (5, 1), (6, 4), (7, 0), (8, 1)):
+        assert lib.a0_set_option(opt, ok) == 0
+    assert lib.a0_set_option(99, 0) == -1 and b"unknown option" in lib.a0_last_error()
 
 
 def test_sass_uses_tma_bulk_copies():
