@@ -157,3 +157,40 @@ def fqf(q_hat, taus, taus_hat, q_next, q_bar, qsel, a, r, d, w, discount, n_step
     gt = np.zeros_like(taus)
     gt[:, 1:-1] = w[:, None] * g
     return loss, grad, frac.astype(f32), gt
+
+
+def huber_qr_sorted(qj, Ti, tauj, w):
+    """The quantile-Huber pair sums of agent.py:110-114 in O(N log N) per sample: SPECIFICATION of the planned
+    sorted-target K4, checked on the CPU against the pairwise form above.
+
+    qj [B,Nj] online quantiles, Ti [B,Ni] targets, tauj [B,Nj] (or [Nj]), w [B] IS weights.  Returns
+    (loss [B], grad [B,Nj]) = (huber_qr_loss, _huber_qr_grad).  For a fixed q the sorted targets split
+    into four ranges of u = q - T:  u >= 1 (linear, weight 1-tau), 0 < u < 1 (quadratic, 1-tau),
+    -1 < u <= 0 (quadratic, tau), u <= -1 (linear, tau); over each range the Huber terms are polynomials
+    in q whose coefficients are prefix sums of T and T^2.  The prefix sums are float64: the quadratic
+    ranges subtract numbers of size T^2 to obtain terms of size (q-T)^2."""
+    qj = np.asarray(qj, dtype=np.float64)
+    B, Nj = qj.shape
+    Ni = Ti.shape[1]
+    tau = np.broadcast_to(np.asarray(tauj, dtype=np.float64), (B, Nj))
+    loss = np.zeros(B, dtype=np.float64)
+    grad = np.zeros((B, Nj), dtype=np.float64)
+    for b in range(B):
+        T = np.sort(np.asarray(Ti[b], dtype=np.float64))
+        S1 = np.concatenate(([0.0], np.cumsum(T)))
+        S2 = np.concatenate(([0.0], np.cumsum(T * T)))
+        q = qj[b]
+        ia = np.searchsorted(T, q - 1.0, side="right")        # T <= q-1          : u >= 1
+        ib = np.searchsorted(T, q, side="left")               # q-1 < T < q       : 0 < u < 1
+        ic = np.searchsorted(T, q + 1.0, side="left")         # q <= T < q+1      : -1 < u <= 0
+        nA, nB, nC, nD = ia, ib - ia, ic - ib, Ni - ic
+        s1B, s2B = S1[ib] - S1[ia], S2[ib] - S2[ia]
+        s1C, s2C = S1[ic] - S1[ib], S2[ic] - S2[ib]
+        s1D = S1[Ni] - S1[ic]
+        A_ = nA * (q - 0.5) - S1[ia]
+        B_ = 0.5 * (nB * q * q - 2.0 * q * s1B + s2B)
+        C_ = 0.5 * (nC * q * q - 2.0 * q * s1C + s2C)
+        D_ = s1D - nD * (q + 0.5)
+        loss[b] = ((1.0 - tau[b]) * (A_ + B_) + tau[b] * (C_ + D_)).sum() / Ni
+        grad[b] = ((1.0 - tau[b]) * (nA + nB * q - s1B) + tau[b] * (nC * q - s1C - nD)) * (float(w[b]) / Ni)
+    return loss.astype(f32), grad.astype(f32)

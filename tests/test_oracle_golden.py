@@ -198,3 +198,27 @@ def test_philox4x32_10_known_answers():
     u = philox_uniform(1234, 5, 100000)
     assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
     assert not np.array_equal(u[:100], philox_uniform(1234, 6, 100)) and np.array_equal(u[:100], philox_uniform(1234, 5, 100))
+
+
+def test_sorted_target_form_of_the_quantile_huber_sums_matches_the_pairwise_form():
+    """oracle.losses.huber_qr_sorted (the O(N log N) specification of the planned QR-200 K4)
+    against the pairwise restatement of agent.py:110-114 that is pinned to the reference's own huber_qr_loss:
+    loss and gradient within 1e-5 relative, on QR-, IQN- and FQF-shaped inputs, with exact ties (T == q,
+    |q - T| == 1), repeated targets and far-apart values."""
+    from oracle import losses as OL
+    rng = np.random.RandomState(7)
+    for B, Ni, Nj, scale in ((6, 200, 200, 3.0), (5, 64, 64, 1.0), (4, 32, 32, 0.3), (3, 7, 5, 10.0)):
+        T = (rng.randn(B, Ni) * scale).astype(np.float32)
+        q = (rng.randn(B, Nj) * scale).astype(np.float32)
+        q[0, 0] = T[0, 0]                      # u == 0
+        q[0, 1] = T[0, 1] + np.float32(1.0)    # u == 1
+        if Nj > 2:
+            q[0, 2] = T[0, 2] - np.float32(1.0)
+        T[1, : Ni // 2] = T[1, 0]              # repeated targets
+        tau = rng.rand(B, Nj).astype(np.float32)
+        w = (rng.rand(B) + 0.1).astype(np.float32)
+        loss_ref = OL.huber_qr_loss(q[:, None, :], T[:, :, None], tau[:, None, :])
+        grad_ref = OL._huber_qr_grad(q, T, tau, w)
+        loss, grad = OL.huber_qr_sorted(q, T, tau, w)
+        np.testing.assert_allclose(loss, loss_ref, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(grad, grad_ref, rtol=1e-5, atol=2e-6)
