@@ -58,6 +58,12 @@ SIGNATURES = {
     "a0_dd_create": (_i32, [C.POINTER(_vp), _i32]),
     "a0_dd_destroy": (_i32, [_vp]),
     "a0_dd_resolve": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, C.POINTER(_i32)]),
+    "a0_ex_create": (_i32, [C.POINTER(_vp), _vp, _vp]),
+    "a0_ex_destroy": (_i32, [_vp]),
+    "a0_ex_extend": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp]),
+    "a0_ex_decode": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "a0_ex_resolve": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, C.POINTER(_i32)]),
+    "a0_ex_last_timing": (_i32, [_vp, _vp]),
     "a0_rb_ingest_plan": (_i32, [_vp, C.POINTER(Plan), _vp, _vp, _i32, _f32, _vp]),
     "a0_rb_ingest_steps": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _vp]),
     "a0_rb_ingest_steps_dyn": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _f32, _i32, _vp]),
@@ -74,6 +80,8 @@ SIGNATURES = {
     "a0_rb_gather": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "a0_rb_sample_gather": (_i32, [_vp, _vp, C.c_uint64, _i64, _i32, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _f64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "a0_rb_gather_unpaired": (_i32, [_vp, _i32, _vp, _vp]),
+    "a0_rb_check_fault": (_i32, [_vp]),
     "a0_rb_gather_f32": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "a0_rb_gather_bf16": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "a0_loss_dqn": (_i32, [C.POINTER(LossCommon), _vp, _vp, _vp, _vp, _vp]),
@@ -150,13 +158,31 @@ def host_map(t):
     return out.value
 
 
-class _DevView:
-    """Zero-copy torch view of handle-owned device memory via __cuda_array_interface__."""
+class HandleOwner:
+    """Owns an a0_replay_t: destroyed when the last reference goes -- the ReplayDataset's and those of
+    the tensors that view the handle's device memory."""
 
-    def __init__(self, address, shape, typestr):
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def __del__(self):
+        try:
+            if self.handle is not None and self.handle.value:
+                self.lib.a0_rb_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _DevView:
+    """Zero-copy torch view of handle-owned device memory via __cuda_array_interface__.  torch keeps the
+    exporting object alive for as long as the tensor's storage lives, and the object keeps ``owner``."""
+
+    def __init__(self, address, shape, typestr, owner=None):
+        self.owner = owner
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
                                          "data": (int(address), False), "version": 2}
 
 
-def device_view(address, shape, typestr, device):
-    return torch.as_tensor(_DevView(address, shape, typestr), device=device)
+def device_view(address, shape, typestr, device, owner=None):
+    return torch.as_tensor(_DevView(address, shape, typestr, owner), device=device)

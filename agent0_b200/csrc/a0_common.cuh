@@ -50,7 +50,12 @@ struct a0_replay {
                               // (0: not uniform); lets K3 fetch an n-step window without chasing links
   long long* mail;            // [mail_cap] sampler -> gather mailbox of a0_rb_sample_gather: draw g's record
   int64_t mail_cap;           // position + 1, 0 = empty; every word is consumed (reset) by the gather CTA
+  int32_t* fault_host;        // mapped page-locked word a kernel sets when it gives up (mailbox wait timed out);
+  int32_t* fault_dev;         // the next host call on the handle reports and clears it (a0_check_fault)
 };
+// A0_EFAULT if a kernel of an earlier call on this handle reported a device-side fault
+int a0_check_fault(a0_replay* h, const char* who);
+uint64_t a0_option_mail_timeout_ns();
 
 void a0_set_error(const char* fmt, ...);
 
@@ -195,10 +200,12 @@ struct A0DeviceGuard {
 // One staged frame into its ring slot with 16-byte vector loads/stores (7056 B = 441 uint4).
 __device__ __forceinline__ void a0_k1_copy_frame(uint8_t* __restrict__ frames, int32_t F, int64_t NF,
                                                  const uint8_t* __restrict__ staged, const int32_t* __restrict__ new_pos,
-                                                 int f, int tid, int nthreads) {
+                                                 const int32_t* __restrict__ src_idx, int f, int tid, int nthreads) {
   const int32_t pos = new_pos[f];
   if (pos < 0 || pos >= NF) return;
-  const uint4* src = reinterpret_cast<const uint4*>(staged + (size_t)f * F);
+  // src_idx (optional): frame f of the append sits at staged[src_idx[f]] (the decoded reference entries
+  // of a0_ex_extend, where only the de-duplicated frames are stored) instead of staged[f]
+  const uint4* src = reinterpret_cast<const uint4*>(staged + (size_t)(src_idx ? src_idx[f] : f) * F);
   uint4* dst = reinterpret_cast<uint4*>(frames + (size_t)pos * F);
   const int nvec = F >> 4;
   for (int i = tid; i < nvec; i += nthreads) dst[i] = __ldg(src + i);
@@ -230,11 +237,16 @@ struct A0Dyn {
 // Returns A0_NOFIT when the sizes do not fit the fused kernel (the caller then launches the two separately).
 constexpr int A0_NOFIT = -100;
 int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, float alpha, const uint8_t* new_frames,
-                          const int32_t* new_frame_pos, int32_t n_new, const int32_t* rec_meta, int32_t m,
-                          const A0Dyn& dyn, cudaStream_t stream);
+                          const int32_t* new_frame_pos, const int32_t* src_idx, int32_t n_new, const int32_t* rec_meta,
+                          int32_t m, const A0Dyn& dyn, cudaStream_t stream);
 // a0_replay.cu: a0_rb_append that also publishes the sampler's dynamic scalars
-int a0_append_launch(a0_replay* h, const uint8_t* new_frames, const int32_t* new_frame_pos, int32_t n_new,
-                     const int32_t* rec_meta, int32_t m, const A0Dyn& dyn, cudaStream_t stream);
+int a0_append_launch(a0_replay* h, const uint8_t* new_frames, const int32_t* new_frame_pos, const int32_t* src_idx,
+                     int32_t n_new, const int32_t* rec_meta, int32_t m, const A0Dyn& dyn, cudaStream_t stream);
+
+// a0_ingest.cu: executes an index plan (staged upload + K2b marks + K1 append); with FRAMES_ON_DEVICE and
+// new_frame_src the append reads frames[new_frame_src[j]] (the decoded entries of a0_ex_extend)
+int a0_ingest_plan_impl(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames, const int64_t* new_frame_src,
+                        int32_t flags, float alpha, a0_stream_t stream, const A0Dyn& dyn);
 
 // a0_sumtree.cu / a0_replay.cu: the two launches behind a0_rb_sample_gather (see there)
 struct A0GatherOut {
@@ -248,6 +260,57 @@ struct A0GatherOut {
 };
 int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int32_t count, int32_t n_step, double gamma,
                           const A0GatherOut& out, cudaStream_t stream);
+int a0_mail_reserve(a0_replay* h, int32_t total, cudaStream_t stream);
+
+__device__ __forceinline__ uint32_t a0_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- TMA helpers (cp.async.bulk + mbarrier, SASS: UBLKCP / SYNCS) -------------------------------
+__device__ __forceinline__ void a0_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void a0_fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void a0_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void a0_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void a0_bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+// The same copies with an L2 eviction-priority hint.  The gather streams: a sampled frame is read once
+// out of a multi-GB ring (no reuse before it is evicted anyway), so its lines are marked evict_first
+// and stop displacing what the step re-reads from L2 -- the sum-tree, the records, and the network
+// outputs K4 consumes (device timeline: K4's first loads land in 850 cycles without the gather's
+// traffic in L2 and 1500 with it).
+__device__ __forceinline__ uint64_t a0_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void a0_bulk_load_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void a0_bulk_store_hint(void* gdst, uint32_t smem_src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               ::"l"(gdst), "r"(smem_src), "r"(bytes), "l"(pol) : "memory");
+}
 
 // ---- small device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float a0_warp_max(float v) {
@@ -280,7 +343,11 @@ __device__ __forceinline__ float a0_priority(float loss, float eps, float alpha)
   float x = loss + eps;
   return alpha == 0.5f ? sqrtf(x) : powf(x, alpha);
 }
+// A priority update with a loss that is NaN, infinite or negative leaves the old leaf in place: the
+// reference skips the whole update when the loss is NaN (agent.py:150-152); inside a captured
+// CUDA graph there is no host guard, and one NaN leaf would poison every ancestor up to the root.
+__device__ __forceinline__ bool a0_loss_ok(float x) { return x >= 0.0f && x < __int_as_float(0x7f800000); }
 __device__ __forceinline__ void a0_atomic_max_pos(float* addr, float v) {
   // valid for non-negative floats: the int ordering equals the float ordering
-  if (v > 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  if (v > 0.0f && v < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
 }

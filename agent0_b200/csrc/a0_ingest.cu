@@ -371,21 +371,22 @@ static int a0_stage_reserve(a0_replay* h, int turn, size_t bytes) {
 
 // dyn.dyn != NULL: the launch that appends also publishes {top, beta, sum_offset} for the sampler
 // (what a0_rb_set_dynamic would otherwise launch a kernel for).
-static int a0_ingest_plan_impl(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames,
-                               const int64_t* new_frame_src, int32_t flags, float alpha, a0_stream_t stream_,
-                               const A0Dyn& dyn) {
+int a0_ingest_plan_impl(a0_replay_t* h, const a0_plan_t* plan, const uint8_t* frames,
+                        const int64_t* new_frame_src, int32_t flags, float alpha, a0_stream_t stream_,
+                        const A0Dyn& dyn) {
   A0_REQUIRE(h && plan, "a0_rb_ingest_plan: NULL argument");
   const int32_t n_new = plan->n_new, m = plan->m, k = plan->n_marks;
   if (n_new == 0 && m == 0 && k == 0) {
     if (!dyn.dyn) return A0_OK;
     A0DeviceGuard guard(h->device);
-    return a0_append_launch(h, nullptr, nullptr, 0, nullptr, 0, dyn, (cudaStream_t)stream_);
+    return a0_append_launch(h, nullptr, nullptr, nullptr, 0, nullptr, 0, dyn, (cudaStream_t)stream_);
   }
   A0_REQUIRE(n_new == 0 || frames, "a0_rb_ingest_plan: frames is NULL");
   const bool on_device = flags & A0_INGEST_FRAMES_ON_DEVICE;
   const bool pinned = flags & A0_INGEST_FRAMES_PINNED;
-  A0_REQUIRE(!(on_device || pinned) || new_frame_src == nullptr,
-             "a0_rb_ingest_plan: device/pinned frames must already be in allocation order");
+  A0_REQUIRE(!pinned || new_frame_src == nullptr, "a0_rb_ingest_plan: pinned frames must already be in allocation order");
+  // device frames + new_frame_src: the picks are uploaded as int32 and K1 reads frames[src[j]] (a0_ex_extend)
+  const bool dev_pick = on_device && new_frame_src != nullptr && n_new > 0;
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t F = (size_t)h->F;
@@ -403,12 +404,13 @@ static int a0_ingest_plan_impl(a0_replay_t* h, const a0_plan_t* plan, const uint
     if (stride >= 0) h->stride_hint = stride;
   }
   const bool stage_frames = n_new > 0 && !on_device && !pinned;
-  size_t sec[5];
+  size_t sec[6];
   sec[0] = 0;
   sec[1] = sec[0] + a0_up256(on_device ? 0 : (size_t)n_new * F);
   sec[2] = sec[1] + a0_up256((size_t)n_new * 4);
   sec[3] = sec[2] + a0_up256((size_t)m * A0_REC_META_I32 * 4);
-  sec[4] = sec[3] + a0_up256((size_t)k * 4);
+  sec[5] = sec[3] + a0_up256((size_t)k * 4);
+  sec[4] = sec[5] + a0_up256(dev_pick ? (size_t)n_new * 4 : 0);     // sec[4] stays "end of the upload"; [sec[5], sec[4]) = picks
   const int turn = h->staging_turn;
   h->staging_turn ^= 1;
   int rc = a0_stage_reserve(h, turn, sec[4]);
@@ -423,6 +425,10 @@ static int a0_ingest_plan_impl(a0_replay_t* h, const a0_plan_t* plan, const uint
   if (n_new) memcpy(s.host + sec[1], plan->new_frame_pos, (size_t)n_new * 4);
   if (m) memcpy(s.host + sec[2], plan->rec_meta, (size_t)m * A0_REC_META_I32 * 4);
   if (k) memcpy(s.host + sec[3], plan->marks, (size_t)k * 4);
+  if (dev_pick) {
+    int32_t* pick = reinterpret_cast<int32_t*>(s.host + sec[5]);
+    for (int32_t j = 0; j < n_new; ++j) pick[j] = (int32_t)new_frame_src[j];
+  }
   // The H2D copies may run on the shard's own copy stream, so that they overlap whatever `stream`
   // is still executing (the previous step's kernels); `stream` then waits for them.  The staging
   // buffer they fill was released by a0_stage_reserve (its last consumer has finished).
@@ -444,18 +450,19 @@ static int a0_ingest_plan_impl(a0_replay_t* h, const a0_plan_t* plan, const uint
   const uint8_t* dev_frames = n_new ? (on_device ? frames : s.dev + sec[0]) : nullptr;
   const int32_t* dev_pos = n_new ? (const int32_t*)(s.dev + sec[1]) : nullptr;
   const int32_t* dev_meta = m ? (const int32_t*)(s.dev + sec[2]) : nullptr;
+  const int32_t* dev_pick_idx = dev_pick ? (const int32_t*)(s.dev + sec[5]) : nullptr;
   A0_REQUIRE(((uintptr_t)dev_frames & 15) == 0, "a0_rb_ingest_plan: device frames must be 16-byte aligned");
   // A step-sized append (a few hundred marks, tens of frames) goes out as ONE launch: marks and
   // append touch disjoint state.  Bulk fills keep the two launches (cluster marks, 128-thread K1 CTAs).
-  rc = (k && a0_option_fused_ingest()) ? a0_launch_mark_append(h, (const int32_t*)(s.dev + sec[3]), k, alpha, dev_frames, dev_pos, n_new, dev_meta, m,
-                                                               dyn, stream)
+  rc = (k && a0_option_fused_ingest()) ? a0_launch_mark_append(h, (const int32_t*)(s.dev + sec[3]), k, alpha, dev_frames, dev_pos, dev_pick_idx, n_new,
+                                                               dev_meta, m, dyn, stream)
                                        : A0_NOFIT;
   if (rc == A0_NOFIT) {
     if (k) {
       rc = a0_pt_mark(h, (const int32_t*)(s.dev + sec[3]), k, alpha, stream_);
       if (rc) return rc;
     }
-    rc = a0_append_launch(h, dev_frames, dev_pos, n_new, dev_meta, m, dyn, stream);
+    rc = a0_append_launch(h, dev_frames, dev_pos, dev_pick_idx, n_new, dev_meta, m, dyn, stream);
   }
   if (rc) return rc;
   A0_CUDA(cudaEventRecord(s.event, stream));
@@ -477,6 +484,7 @@ static int a0_ingest_steps_impl(a0_replay_t* h, a0_index_t* ix, const int64_t* s
   A0_REQUIRE(h && ix, "%s: NULL handle", who);
   A0_REQUIRE(m >= 0, "%s: negative count", who);
   A0_REQUIRE(ix->N == h->N && ix->NF == h->NF, "%s: index and shard capacities differ", who);
+  { int frc = a0_check_fault(h, who); if (frc) return frc; }
   const size_t F = (size_t)h->F;
   const int64_t step = ix->max_chunk();
   size_t frame_off = 0;

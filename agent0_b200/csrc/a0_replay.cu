@@ -70,6 +70,30 @@ static int a0_option_k3_l2(int64_t launch_bytes) {
   if (g_k3_l2 == 4) return launch_bytes <= (int64_t)100 << 20 ? 3 : 0;
   return g_k3_l2;
 }
+static int64_t g_mail_timeout_us = -1;
+uint64_t a0_option_mail_timeout_ns() {
+  if (g_mail_timeout_us < 0) {
+    const char* e = getenv("A0_MAIL_TIMEOUT_US");
+    g_mail_timeout_us = e ? atoll(e) : 2000000;
+    if (g_mail_timeout_us < 1) g_mail_timeout_us = 1;
+  }
+  return (uint64_t)g_mail_timeout_us * 1000ull;
+}
+int a0_check_fault(a0_replay* h, const char* who) {
+  if (h && h->fault_host && *(volatile int32_t*)h->fault_host != 0) {
+    const int32_t code = *(volatile int32_t*)h->fault_host;
+    *(volatile int32_t*)h->fault_host = 0;
+    a0_set_error("%s: an earlier launch on this shard reported device fault %d (%s)", who, code,
+                 code == 1 ? "a gather CTA of a0_rb_sample_gather timed out waiting for its sampler: its outputs are invalid"
+                           : "unknown");
+    return A0_EFAULT;
+  }
+  return A0_OK;
+}
+extern "C" int a0_rb_check_fault(a0_replay_t* h) {
+  A0_REQUIRE(h != nullptr, "a0_rb_check_fault: handle is NULL");
+  return a0_check_fault(h, "a0_rb_check_fault");
+}
 static int g_fused_ingest = -1;
 bool a0_option_fused_ingest() {
   if (g_fused_ingest < 0) {
@@ -80,6 +104,11 @@ bool a0_option_fused_ingest() {
 }
 extern "C" int a0_set_option(int32_t option, int64_t value) {
   if (option == A0_OPT_FUSED_INGEST) { g_fused_ingest = value != 0; return A0_OK; }
+  if (option == A0_OPT_MAIL_TIMEOUT_US) {
+    A0_REQUIRE(value >= 1, "a0_set_option: A0_OPT_MAIL_TIMEOUT_US must be positive");
+    g_mail_timeout_us = value;
+    return A0_OK;
+  }
   if (option == A0_OPT_C51_FAST) { a0_set_c51_fast(value != 0); return A0_OK; }
   if (option == A0_OPT_K2B_SMALL) { a0_set_k2b_small(value != 0); return A0_OK; }
   if (option == A0_OPT_K2B_CHUNKS) { a0_set_k2b_chunks(value != 0); return A0_OK; }
@@ -155,6 +184,13 @@ extern "C" int a0_rb_create(a0_replay_t** out, int64_t rec_capacity, int64_t fra
     return e == cudaErrorMemoryAllocation ? A0_ENOMEM : (int)e;
   }
   h->dyn = h->max_p + 16;     // same 256-byte allocation
+  if (cudaHostAlloc((void**)&h->fault_host, 64, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&h->fault_dev, h->fault_host, 0) != cudaSuccess) {
+    a0_set_error("a0_rb_create: cannot allocate the mapped fault word: %s", cudaGetErrorString(cudaGetLastError()));
+    a0_rb_destroy(h);
+    return A0_ENOMEM;
+  }
+  memset(h->fault_host, 0, 64);
   int rc = a0_rb_reset(h, nullptr);
   if (rc != 0) { a0_rb_destroy(h); return rc; }
   A0_CUDA(cudaStreamSynchronize(nullptr));
@@ -167,6 +203,7 @@ extern "C" int a0_rb_destroy(a0_replay_t* h) {
   A0DeviceGuard guard(h->device);
   cudaFree(h->frames); cudaFree(h->rec_slots); cudaFree(h->rec_info); cudaFree(h->tree);
   cudaFree(h->max_p); cudaFree(h->winner); cudaFree(h->dirty); cudaFree(h->counter); cudaFree(h->mail);
+  if (h->fault_host) cudaFreeHost(h->fault_host);
   for (int t = 0; t < 2; ++t) {
     if (h->staging[t].event) { cudaEventSynchronize(h->staging[t].event); cudaEventDestroy(h->staging[t].event); }
     if (h->staging[t].copied) cudaEventDestroy(h->staging[t].copied);
@@ -216,29 +253,30 @@ constexpr int K1_THREADS = 128;
 
 __global__ void __launch_bounds__(K1_THREADS)
 a0_k1_append(uint8_t* __restrict__ frames, int32_t F, int64_t NF, const uint8_t* __restrict__ staged,
-             const int32_t* __restrict__ new_pos, int32_t n_new, int32_t* __restrict__ rec_slots,
-             A0RecInfo* __restrict__ rec_info, int64_t N, const int32_t* __restrict__ meta, int32_t m, const A0Dyn dyn) {
+             const int32_t* __restrict__ new_pos, const int32_t* __restrict__ src_idx, int32_t n_new,
+             int32_t* __restrict__ rec_slots, A0RecInfo* __restrict__ rec_info, int64_t N, const int32_t* __restrict__ meta,
+             int32_t m, const A0Dyn dyn) {
   A0_PDL_PROLOGUE();
   if (dyn.dyn && blockIdx.x == 0 && threadIdx.x == 0) {   // what a0_rb_set_dynamic would launch a kernel for
     dyn.dyn[0] = dyn.top; dyn.dyn[1] = dyn.beta; dyn.dyn[2] = dyn.sum_offset;
   }
   if ((int)blockIdx.x < n_new) {
-    a0_k1_copy_frame(frames, F, NF, staged, new_pos, blockIdx.x, threadIdx.x, K1_THREADS);
+    a0_k1_copy_frame(frames, F, NF, staged, new_pos, src_idx, blockIdx.x, threadIdx.x, K1_THREADS);
     return;
   }
   const int r = ((int)blockIdx.x - n_new) * K1_THREADS + threadIdx.x;
   if (r < m) a0_k1_write_record(rec_slots, rec_info, N, meta, r);
 }
 
-int a0_append_launch(a0_replay* h, const uint8_t* new_frames, const int32_t* new_frame_pos, int32_t n_new,
-                     const int32_t* rec_meta, int32_t m, const A0Dyn& dyn, cudaStream_t stream) {
+int a0_append_launch(a0_replay* h, const uint8_t* new_frames, const int32_t* new_frame_pos, const int32_t* src_idx,
+                     int32_t n_new, const int32_t* rec_meta, int32_t m, const A0Dyn& dyn, cudaStream_t stream) {
   int blocks = n_new + (m + K1_THREADS - 1) / K1_THREADS;
   if (blocks == 0) {
     if (!dyn.dyn) return A0_OK;
     blocks = 1;                                   // nothing to append: the launch only publishes the scalars
   }
   A0_LAUNCH(a0_k1_append, (unsigned)blocks, K1_THREADS, 0, stream, 1, A0_PDL_K1, h->frames, h->F, h->NF, new_frames,
-            new_frame_pos, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m, dyn);
+            new_frame_pos, src_idx, n_new, h->rec_slots, h->rec_info, h->N, rec_meta, m, dyn);
   return A0_OK;
 }
 
@@ -252,7 +290,7 @@ extern "C" int a0_rb_append(a0_replay_t* h, const uint8_t* new_frames, const int
   A0_REQUIRE(((uintptr_t)new_frames & 15) == 0, "a0_rb_append: new_frames must be 16-byte aligned");
   A0DeviceGuard guard(h->device);
   const A0Dyn none = {nullptr, 0.0f, 0.0f, 0.0f};
-  return a0_append_launch(h, new_frames, new_frame_pos, n_new, rec_meta, m, none, (cudaStream_t)stream_);
+  return a0_append_launch(h, new_frames, new_frame_pos, nullptr, n_new, rec_meta, m, none, (cudaStream_t)stream_);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,6 +313,8 @@ struct A0GatherArgs {
   float* done32_out;
   int64_t* boot_out;
   long long* mail;       // != NULL: record positions arrive through the sampler's mailbox (a0_rb_sample_gather)
+  int32_t* fault;        // mapped host word: set to 1 by a CTA whose mailbox word never arrived
+  unsigned long long mail_timeout_ns;
   int32_t l2_hints;      // bit 0: frame reads evict_first, bit 1: output stores evict_first (A0_OPT_K3_L2)
 };
 
@@ -411,56 +451,6 @@ __device__ __forceinline__ bool a0_resolve_window(const A0GatherArgs& g, int b, 
   return ok;
 }
 
-__device__ __forceinline__ uint32_t a0_smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-// ---- TMA helpers (cp.async.bulk + mbarrier, SASS: UBLKCP / SYNCS) -------------------------------
-__device__ __forceinline__ void a0_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void a0_fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void a0_bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void a0_mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void a0_bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
-}
-// The same copies with an L2 eviction-priority hint.  The gather streams: a sampled frame is read once
-// out of a multi-GB ring (no reuse before it is evicted anyway), so its lines are marked evict_first
-// and stop displacing what the step re-reads from L2 -- the sum-tree, the records, and the network
-// outputs K4 consumes (device timeline: K4's first loads land in 850 cycles without the gather's
-// traffic in L2 and 1500 with it).
-__device__ __forceinline__ uint64_t a0_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void a0_bulk_load_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t pol) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void a0_bulk_store_hint(void* gdst, uint32_t smem_src, uint32_t bytes, uint64_t pol) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-               ::"l"(gdst), "r"(smem_src), "r"(bytes), "l"(pol) : "memory");
-}
-
 // Distinct frames of the two stacks: uslot[u] = frame slot, dmask[u] = stack positions it fills.
 // a0_unique_add registers stack position j (fully unrolled: the arrays stay in registers).
 __device__ __forceinline__ void a0_unique_add(int32_t s, int j, int32_t (&uslot)[A0_SLOTS], uint32_t (&dmask)[A0_SLOTS],
@@ -514,12 +504,29 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
 #pragma unroll
     for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
     a0_fence_barrier_init();
+    // The poll is bounded: the paired sampler posts the word within microseconds; without it (a failed
+    // launch, a mis-paired caller) the CTA gives up after mail_timeout_ns, raises the handle's fault word
+    // (mapped host memory: the next host call reports it) and produces an invalid sample instead of hanging.
     long long v;
-    do {
+    unsigned long long t_start = 0;
+    unsigned spins = 0;
+    for (;;) {
       asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(g.mail + b) : "memory");
-    } while (v == 0);
-    asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(g.mail + b), "l"(0ll) : "memory");
-    p0 = v - 1;
+      if (v != 0) break;
+      if ((++spins & 255u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t_start == 0) t_start = now;
+        else if (now - t_start > g.mail_timeout_ns) break;
+      }
+    }
+    if (v != 0) {
+      asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(g.mail + b), "l"(0ll) : "memory");
+      p0 = v - 1;
+    } else {
+      if (g.fault) { *reinterpret_cast<volatile int32_t*>(g.fault) = 1; __threadfence_system(); }
+      p0 = -1;
+    }
   } else {
     A0_PDL_PROLOGUE();
     p0 = g.idx[b];
@@ -933,7 +940,7 @@ static int a0_gather_cvt(a0_replay_t* h, const int64_t* idx, int32_t count, int3
   g.stride_hint = (h->stride_hint > 0 && h->stride_hint < h->N) ? (int32_t)h->stride_hint : 0;
   g.frames_out = nullptr; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
-  g.mail = nullptr;
+  g.mail = nullptr; g.fault = nullptr; g.mail_timeout_ns = 0;
   g.l2_hints = 0;
   const size_t smem = (size_t)K3_RING * h->F;
   static thread_local size_t configured[64] = {0};       // one table per OutT instantiation
@@ -983,12 +990,23 @@ int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int
   g.frames_out = out.frames; g.action_out = out.action; g.reward64_out = out.reward64;
   g.reward32_out = out.reward32; g.done8_out = out.done8; g.done32_out = out.done32; g.boot_out = out.boot;
   g.mail = mail;
+  g.fault = h->fault_dev;
+  g.mail_timeout_ns = a0_option_mail_timeout_ns();
   g.l2_hints = a0_option_k3_l2((int64_t)count * 16 * h->F);
   const size_t smem = (size_t)K3_RING * h->F;
   int rc = a0_k3_smem_attr(h, smem);
   if (rc) return rc;
   A0_LAUNCH(a0_k3_gather_tma, (unsigned)count, 32, smem, stream, 1, A0_PDL_FORCE, g);
   return A0_OK;
+}
+
+extern "C" int a0_rb_gather_unpaired(a0_replay_t* h, int32_t count, uint8_t* frames_out, a0_stream_t stream_) {
+  A0_REQUIRE(h && frames_out && count > 0, "a0_rb_gather_unpaired: bad argument");
+  A0DeviceGuard guard(h->device);
+  int rc = a0_mail_reserve(h, count, (cudaStream_t)stream_);
+  if (rc) return rc;
+  const A0GatherOut out = {frames_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return a0_gather_launch_mail(h, nullptr, h->mail, count, 1, 0.99, out, (cudaStream_t)stream_);
 }
 
 extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, int32_t n_step, double gamma,
@@ -1002,6 +1020,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_gather: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
   A0_REQUIRE(((uintptr_t)frames_out & 15) == 0, "a0_rb_gather: frames_out must be 16-byte aligned");
   A0_REQUIRE(variant >= 0 && variant <= 3, "a0_rb_gather: unknown variant %d", variant);
+  { int frc = a0_check_fault(h, "a0_rb_gather"); if (frc) return frc; }
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
   A0GatherArgs g;
@@ -1010,7 +1029,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   g.stride_hint = (h->stride_hint > 0 && h->stride_hint < h->N) ? (int32_t)h->stride_hint : 0;
   g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
-  g.mail = nullptr;
+  g.mail = nullptr; g.fault = nullptr; g.mail_timeout_ns = 0;
   g.l2_hints = a0_option_k3_l2((int64_t)count * 16 * h->F);
   if (variant == 3) {
     const size_t smem = (size_t)K3S_RING * h->F;

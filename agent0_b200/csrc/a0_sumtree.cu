@@ -295,6 +295,20 @@ extern "C" int a0_pt_sample_rng(a0_replay_t* h, uint64_t seed, int64_t call, int
 // its drain, and the launch hand-over between the two kernels.  The gather ends with
 // griddepcontrol.wait, so "gather complete" still implies "sampler complete" for everything
 // downstream (K4 reads the weights).  Results are those of a0_pt_sample[_rng] + a0_rb_gather.
+// the mailbox of a0_rb_sample_gather: allocated on first use (or for a larger draw), not inside a graph capture
+int a0_mail_reserve(a0_replay* h, int32_t total, cudaStream_t stream) {
+  if (h->mail_cap >= total) return A0_OK;
+  int64_t cap = h->mail_cap > 0 ? h->mail_cap : 1024;
+  while (cap < total) cap *= 2;
+  A0_CUDA(cudaStreamSynchronize(stream));
+  if (h->mail) A0_CUDA(cudaFree(h->mail));
+  h->mail = nullptr; h->mail_cap = 0;
+  A0_CUDA(cudaMalloc((void**)&h->mail, (size_t)cap * sizeof(long long)));
+  A0_CUDA(cudaMemset(h->mail, 0, (size_t)cap * sizeof(long long)));
+  h->mail_cap = cap;
+  return A0_OK;
+}
+
 extern "C" int a0_rb_sample_gather(a0_replay_t* h, const float* u, uint64_t seed, int64_t call, int32_t total,
                                    int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
                                    int64_t* idx_out, float* prio_out, float* weight_out, int32_t n_step, double gamma,
@@ -306,18 +320,10 @@ extern "C" int a0_rb_sample_gather(a0_replay_t* h, const float* u, uint64_t seed
   A0_REQUIRE(idx_out && prio_out && frames_out, "a0_rb_sample_gather: idx_out, prio_out and frames_out are required");
   A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_sample_gather: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
   A0_REQUIRE(((uintptr_t)frames_out & 15) == 0, "a0_rb_sample_gather: frames_out must be 16-byte aligned");
+  { int frc = a0_check_fault(h, "a0_rb_sample_gather"); if (frc) return frc; }
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (h->mail_cap < total) {          // first use (or a larger draw): not inside a graph capture
-    int64_t cap = h->mail_cap > 0 ? h->mail_cap : 1024;
-    while (cap < total) cap *= 2;
-    A0_CUDA(cudaStreamSynchronize(stream));
-    if (h->mail) A0_CUDA(cudaFree(h->mail));
-    h->mail = nullptr; h->mail_cap = 0;
-    A0_CUDA(cudaMalloc((void**)&h->mail, (size_t)cap * sizeof(long long)));
-    A0_CUDA(cudaMemset(h->mail, 0, (size_t)cap * sizeof(long long)));
-    h->mail_cap = cap;
-  }
+  { int mrc = a0_mail_reserve(h, total, stream); if (mrc) return mrc; }
   A0Rng rng = {0ull, 0ll, nullptr, nullptr, nullptr};
   if (!u) {
     rng.seed = seed;
@@ -406,7 +412,7 @@ a0_k2b_write(float* __restrict__ tree, int64_t P, int32_t chunk_log, int64_t N, 
     if (__ldcg(winner + pos) != k) continue;
     float v;
     if (mode == 0) {
-      if (!(__ldcg(tree + P + pos) > 0.0f)) continue;      // evicted since it was sampled
+      if (!(__ldcg(tree + P + pos) > 0.0f) || !a0_loss_ok(vals[k])) continue;   // evicted since it was sampled / NaN loss
       v = a0_priority(vals[k], eps, alpha);
     } else if (mode == 1) {
       v = idx32[k] >= 0 ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
@@ -699,7 +705,7 @@ a0_paths_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     if (pos[s] < 0 || __ldcg(winner + pos[s]) != kk[s]) continue;
     float v;
     if (mode == 0) {
-      if (!(old_leaf[s] > 0.0f)) continue;                  // evicted since it was sampled
+      if (!(old_leaf[s] > 0.0f) || !a0_loss_ok(val[s])) continue;   // evicted since it was sampled / NaN loss
       v = a0_priority(val[s], eps, alpha);
     } else if (mode == 1) {
       v = val[s] != 0.0f ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
@@ -894,7 +900,7 @@ a0_small_body(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   if (active) {
     bool store = true;
     if (mode == 0) {
-      store = old_leaf > 0.0f;                              // evicted since it was sampled: the leaf stays 0
+      store = old_leaf > 0.0f && a0_loss_ok(val);           // evicted since it was sampled (the leaf stays 0) / NaN loss
       myv = store ? a0_priority(val, eps, alpha) : old_leaf;
     } else if (mode == 1) {
       myv = val != 0.0f ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
@@ -992,8 +998,9 @@ __global__ void __launch_bounds__(K2S_THREADS)
 a0_k1_append_mark(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int32_t* __restrict__ marks,
                   int32_t n_marks, float alpha, float* __restrict__ max_p,
                   uint8_t* __restrict__ frames, int32_t F, int64_t NF, const uint8_t* __restrict__ staged,
-                  const int32_t* __restrict__ new_pos, int32_t n_new, int32_t* __restrict__ rec_slots,
-                  A0RecInfo* __restrict__ rec_info, const int32_t* __restrict__ meta, int32_t m, const A0Dyn dyn) {
+                  const int32_t* __restrict__ new_pos, const int32_t* __restrict__ src_idx, int32_t n_new,
+                  int32_t* __restrict__ rec_slots, A0RecInfo* __restrict__ rec_info, const int32_t* __restrict__ meta,
+                  int32_t m, const A0Dyn dyn) {
   extern __shared__ __align__(16) uint8_t a0_k2s_smem[];
   A0_PDL_PROLOGUE();
   if (blockIdx.x == 0) {
@@ -1004,7 +1011,7 @@ a0_k1_append_mark(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, con
   }
   const int blk = (int)blockIdx.x - 1;
   if (blk < n_new) {
-    a0_k1_copy_frame(frames, F, NF, staged, new_pos, blk, threadIdx.x, K2S_THREADS);
+    a0_k1_copy_frame(frames, F, NF, staged, new_pos, src_idx, blk, threadIdx.x, K2S_THREADS);
     return;
   }
   const int r = (blk - n_new) * K2S_THREADS + threadIdx.x;
@@ -1012,15 +1019,15 @@ a0_k1_append_mark(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, con
 }
 
 int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, float alpha, const uint8_t* new_frames,
-                          const int32_t* new_frame_pos, int32_t n_new, const int32_t* rec_meta, int32_t m,
-                          const A0Dyn& dyn, cudaStream_t stream) {
+                          const int32_t* new_frame_pos, const int32_t* src_idx, int32_t n_new, const int32_t* rec_meta,
+                          int32_t m, const A0Dyn& dyn, cudaStream_t stream) {
   if (n_marks <= 0 || n_marks > K1M_MAX_MARKS || n_new > K1M_MAX_FRAMES || h->D - K2P_TOP > K2S_MAX_SPARSE) return A0_NOFIT;
   static thread_local bool attr[64] = {false};
   int rc = a0_k2s_smem_attr(h, a0_k1_append_mark, attr);
   if (rc) return rc;
   const int blocks = 1 + n_new + (m + K2S_THREADS - 1) / K2S_THREADS;
   A0_LAUNCH(a0_k1_append_mark, (unsigned)blocks, K2S_THREADS, K2S_SMEM, stream, 1, A0_PDL_K1, h->tree, h->P, h->D, h->N, marks, n_marks,
-            alpha, h->max_p, h->frames, h->F, h->NF, new_frames, new_frame_pos, n_new, h->rec_slots, h->rec_info,
+            alpha, h->max_p, h->frames, h->F, h->NF, new_frames, new_frame_pos, src_idx, n_new, h->rec_slots, h->rec_info,
             rec_meta, m, dyn);
   return A0_OK;
 }
@@ -1118,7 +1125,7 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     if (win[l] != k) continue;
     float v;
     if (mode == 0) {
-      if (!(heap[n + l] > 0.0f)) continue;                  // evicted since it was sampled
+      if (!(heap[n + l] > 0.0f) || !a0_loss_ok(vals[k])) continue;   // evicted since it was sampled / NaN loss
       v = a0_priority(vals[k], eps, alpha);
     } else if (mode == 1) {
       v = set ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
@@ -1250,6 +1257,7 @@ extern "C" int a0_pt_update(a0_replay_t* h, const int64_t* idx, const float* los
                             float eps, a0_stream_t stream) {
   A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_update: bad handle or count");
   A0_REQUIRE(count == 0 || (idx && loss), "a0_pt_update: NULL argument");
+  { int frc = a0_check_fault(h, "a0_pt_update"); if (frc) return frc; }
   return a0_launch_update(h, idx, nullptr, loss, count, 0, alpha, eps, stream);
 }
 // Device-visible alias of page-locked host memory (mapped under unified addressing: what cudaHostAlloc
@@ -1271,6 +1279,7 @@ extern "C" int a0_pt_update_report(a0_replay_t* h, const int64_t* idx, const flo
   A0_REQUIRE(count == 0 || (idx && loss), "a0_pt_update_report: NULL argument");
   A0_REQUIRE(idx_report && loss_report, "a0_pt_update_report: NULL report buffer (a0_pt_update reports nothing)");
   const A0Report rep = {idx_report, loss_report};
+  { int frc = a0_check_fault(h, "a0_pt_update_report"); if (frc) return frc; }
   return a0_launch_update(h, idx, nullptr, loss, count, 0, alpha, eps, stream, rep);
 }
 extern "C" int a0_pt_mark(a0_replay_t* h, const int32_t* pos, int32_t count, float alpha, a0_stream_t stream) {

@@ -114,7 +114,9 @@ class ReplayTargetLoop:
         p = lambda t: t[s].data_ptr()
         return _lib.LossCommon(B=count, A=self.A, action=p(self.act), reward=p(self.r32), done=p(self.d32), weight=p(self.w),
                                gamma_n=self.gamma_n, alpha=self.alpha, eps=self.eps, loss=p(self.loss), prio=p(self.newp) if self.newp is not None else None,
-                               max_p=self.rp.max_p_tensor.data_ptr()), s
+                               # uniform replay keeps no running max loss: a K4 that raised max_p would make later
+                               # appends heavier than earlier ones (leaf = max_p^alpha) and the draw non-uniform
+                               max_p=self.rp.max_p_tensor.data_ptr() if self.per else None), s
 
     def _bind(self, lo, count):
         """(function, argument tuple) of the K4 launch over rows [lo, lo+count): the a0_loss_common_t block

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ring_index import NativeContentDeduper, NativeRingIndex, stack_delta
+from .ring_index import NativeRingIndex, stack_delta
 
 Batch = namedtuple("Batch", ["frames", "actions", "rewards", "terminals", "priorities", "indices",
                              "weights", "rewards_f32", "terminals_f32", "boot_indices", "obs", "next_obs"],
@@ -111,7 +111,9 @@ class ReplayDataset:
             frame_capacity = int(self.size * 1.0625) + 65536 if self.size >= 65536 else 4 * self.size + 64
         self.index = NativeRingIndex(self.size, frame_capacity, self.n_gather, age_limit)
         self.prioritize = _is_prioritized(cfg)
-        self.alpha = float(cfg.replay.alpha) if self.prioritize else 1.0
+        # uniform replay: alpha = 0 makes every new leaf max_p^0 = 1 whatever max_p is (the reference's uniform
+        # policy never reads priorities, trainer.py:95-96), so the tree descent draws records uniformly
+        self.alpha = float(cfg.replay.alpha) if self.prioritize else 0.0
         self.eps = float(cfg.replay.eps)
         self.compat_sum = bool(compat_sum)
         self.gather_variant = int(gather_variant)
@@ -128,13 +130,16 @@ class ReplayDataset:
         self.h = h
         self.P = int(self.lib.a0_rb_tree_leaves(h))
         dev = self.device
-        self.frames = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_FRAMES), (frame_capacity, self.F), "|u1", dev)
-        self.tree = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_TREE), (2 * self.P,), "<f4", dev)
-        self.max_p_tensor = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_MAX_P), (1,), "<f4", dev)
+        # views of handle-owned memory keep the handle alive (owner=): a tensor handed to a learner or cached in
+        # a captured graph must never outlive the allocation it points into
+        self._owner = _lib.HandleOwner(self.lib, h)
+        self.frames = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_FRAMES), (frame_capacity, self.F), "|u1", dev, self._owner)
+        self.tree = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_TREE), (2 * self.P,), "<f4", dev, self._owner)
+        self.max_p_tensor = _lib.device_view(self.lib.a0_rb_ptr(h, _lib.PTR_MAX_P), (1,), "<f4", dev, self._owner)
         self.priority = _PrioritySum(self)
-        self._dedupe = NativeContentDeduper(self.index, self.F)   # reference-tuple ingest
-        self._lz4 = None
-        self._scratch = None
+        ex = C.c_void_p()
+        _lib.check(self.lib.a0_ex_create(C.byref(ex), h, self.index.h), "a0_ex_create")
+        self._ex = ex                                             # reference-tuple ingest (K6)
 
     # ------------------------------------------------------------------ reference surface
     def __len__(self):
@@ -157,63 +162,67 @@ class ReplayDataset:
 
     def __del__(self):
         try:
-            if getattr(self, "h", None) is not None and self.h.value:
-                self.lib.a0_rb_destroy(self.h)
-                self.h = None
+            if getattr(self, "_ex", None) is not None and self._ex.value:
+                self.lib.a0_ex_destroy(self._ex)
+                self._ex = None
+            self.h = None          # a0_rb_destroy runs when the last view of the shard's memory is gone (HandleOwner)
+            self._owner = None
         except Exception:
             pass
 
     # ------------------------------------------------------------------ ingest: reference tuples
-    def _decompress_into(self, blob, row):
-        """One reference entry (raw bytes / ndarray / python-lz4 block, agent.py:80) into row u8[8*F]."""
-        want = row.size
-        if isinstance(blob, np.ndarray):
-            row[:] = blob.reshape(-1)
-        elif len(blob) == want:
-            row[:] = np.frombuffer(blob, dtype=np.uint8)
-        else:
-            if self._lz4 is None:
-                try:
-                    from lz4.block import decompress as _d
-                    self._lz4 = lambda b, r: r.__setitem__(slice(None), np.frombuffer(_d(b), dtype=np.uint8))
-                except Exception:
-                    self._lz4 = _liblz4_block_decompress_into
-            self._lz4(blob, row)
-
     def extend(self, transitions, streams=None):
         """Reference-compatible ingest (replay.py:45-53): a list of (frames, action, reward, done)
-        with frames = the 8-frame blob concat(st, st_next) (raw bytes/ndarray or lz4 block,
-        agent.py:78-81).  Entries arrive step-major, env-minor, so entry i belongs to stream
-        i % num_envs unless ``streams`` says otherwise.  Frames already held for the stream's
-        previous entry are not stored again (native content de-duplication, a0_dd_resolve)."""
+        with frames = the 8-frame blob concat(st, st_next) as the reference actor ships it -- a
+        python-lz4 block (agent.py:78-81) -- or the same 8 frames uncompressed (bytes / ndarray).
+        Entries arrive step-major, env-minor, so entry i belongs to stream i % num_envs unless
+        ``streams`` says otherwise.  One C call (a0_ex_extend): the compressed bytes are copied to
+        the device, decoded and de-duplicated there (K6: a frame already held for the stream's
+        previous entry is not stored again; matches are byte-verified, so they are bit-exact),
+        and the new frames are appended from the decoded scratch by K1."""
         m = len(transitions)
         if m == 0:
             return
+        if self.n_gather != 1:
+            raise RuntimeError("extend() takes the reference actor's already n-step-folded entries; this shard was built "
+                               "with native_nstep=True and folds n_step_q records again at gather time -- feed it with "
+                               "append_steps / ShardActor instead")
+        blobs, action, reward, done = zip(*transitions)
+        if not all(type(b) is bytes for b in blobs):
+            blobs = [b if isinstance(b, (bytes, bytearray)) else np.ascontiguousarray(b, dtype=np.uint8).tobytes() for b in blobs]
+        lens = np.fromiter(map(len, blobs), dtype=np.int64, count=m)
+        joined = b"".join(blobs)
         if streams is None:
             streams = np.arange(m, dtype=np.int64) % self.num_envs
-        streams = np.asarray(streams, dtype=np.int64)
-        if self._scratch is None or self._scratch.shape[0] < m:      # reused: no page faults after the first call
-            self._scratch = np.empty((m, 8 * self.F), dtype=np.uint8)
-        frames = self._scratch[:m]
-        for i, t in enumerate(transitions):
-            self._decompress_into(t[0], frames[i])
-        frames = frames.reshape(m, 8, self.F)
-        action = np.fromiter((int(t[1]) for t in transitions), dtype=np.int64, count=m)
-        reward = np.fromiter((float(t[2]) for t in transitions), dtype=np.float64, count=m)
-        done = np.fromiter((bool(t[3]) for t in transitions), dtype=np.bool_, count=m)
-        step = self.index.max_chunk
-        for lo in range(0, m, step):
-            hi = min(m, lo + step)
-            self._extend_chunk(streams[lo:hi], frames[lo:hi], action[lo:hi], reward[lo:hi], done[lo:hi])
+        streams = np.ascontiguousarray(streams, dtype=np.int64)
+        action = np.asarray(action, dtype=np.int64)
+        reward = np.asarray(reward, dtype=np.float64)
+        done = np.asarray(done, dtype=np.bool_)
+        assert len(streams) == m
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.a0_ex_extend(self._ex, joined, lens.ctypes.data, streams.ctypes.data, action.ctypes.data,
+                                             reward.ctypes.data, done.ctypes.data, m, self.alpha,
+                                             _lib.stream_ptr(self.device)), "a0_ex_extend")
         if self.prioritize:
             self.beta = self.beta_schedule(m)
 
-    def _extend_chunk(self, streams, frames, action, reward, done):
-        fs8, new_src = self._dedupe.resolve(streams, frames)
-        plan = self.index.plan_native(streams, fs8, len(new_src), action, reward, done)
-        flat = np.ascontiguousarray(frames).reshape(len(streams) * 8, self.F)
-        self._ingest_plan(plan, flat.ctypes.data, new_src, 0)
-        self._dedupe.detach(streams)
+    def extend_timing(self):
+        """Microseconds of the last ``extend``: host staging, wait for the device decode + label, host
+        resolve + plan, append launches, device time of decode + label, entries."""
+        out = np.zeros(6, dtype=np.float32)
+        _lib.check(self.lib.a0_ex_last_timing(self._ex, out.ctypes.data), "a0_ex_last_timing")
+        return dict(zip(("stage_us", "wait_us", "plan_us", "launch_us", "device_decode_label_us", "entries"), out.tolist()))
+
+    def decode_entries(self, blobs):
+        """K6a alone (tests, bench): python-lz4 blocks -> u8 [m, 8*F] on the device + i32 status per entry."""
+        m = len(blobs)
+        lens = np.fromiter(map(len, blobs), dtype=np.int64, count=m)
+        out = torch.empty((m, 8 * self.F), dtype=torch.uint8, device=self.device)
+        status = np.zeros(m, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.a0_ex_decode(self._ex, b"".join(blobs), lens.ctypes.data, m, out.data_ptr(), status.ctypes.data,
+                                             _lib.stream_ptr(self.device)), "a0_ex_decode")
+        return out, status
 
     def _ingest_plan(self, plan, frames_ptr, new_src, flags):
         src = None
@@ -453,24 +462,3 @@ class ReplayDataset:
         with torch.cuda.device(dev):
             _lib.check(self.lib.a0_pt_set(self.h, ids.data_ptr(), values.data_ptr(), ids.numel(),
                                           _lib.stream_ptr(dev)), "a0_pt_set")
-
-
-def _liblz4_block_decompress_into(blob, row):
-    """python-lz4 block format (4-byte little-endian size prefix + raw LZ4 block) via the system
-    liblz4, straight into ``row`` (u8, contiguous), for blobs produced by the reference actor's
-    lz4.block.compress (agent.py:80) when the python package is absent."""
-    lib = _liblz4_block_decompress_into.lib
-    if lib is None:
-        lib = _liblz4_block_decompress_into.lib = C.CDLL("liblz4.so.1")
-        lib.LZ4_decompress_safe.restype = C.c_int
-        lib.LZ4_decompress_safe.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
-    blob = bytes(blob)
-    size = int.from_bytes(blob[:4], "little")
-    if size != row.size:
-        raise RuntimeError(f"lz4 block holds {size} bytes, expected {row.size}")
-    n = lib.LZ4_decompress_safe(blob[4:], row.ctypes.data, len(blob) - 4, size)
-    if n != size:
-        raise RuntimeError("lz4 block decompression failed")
-
-
-_liblz4_block_decompress_into.lib = None

@@ -10,6 +10,10 @@ sample several batches ahead with a fork-time snapshot of the priorities (SURVEY
 """
 from __future__ import annotations
 
+from collections import deque
+
+import torch
+
 from .learner import make_learner
 from .replay import NORM_RECIP, ReplayDataset, split_batches
 
@@ -89,7 +93,11 @@ class Trainer:
         self._graphed = None
         self.num_transitions = cfg.actor.sample_steps * cfg.actor.num_envs
         self.frame_count = 0
-        self.Ls, self.FLs, self.Rs, self.Qs = [], [], [], []
+        # the reference keeps every value ever logged (trainer.py:45-47) but only ever reads the last 20 / 100:
+        # bounded deques of device scalars, reduced with ONE read-back per step
+        self.Ls, self.FLs = deque(maxlen=20), deque(maxlen=20)
+        self.Rs, self.Qs = deque(maxlen=20), deque(maxlen=100)
+        self.R_max = None
 
     def learn(self, learner_steps=None):
         """The inner loop (trainer.py:82-109).  Returns per-update (q_loss, fraction_loss) device
@@ -122,7 +130,13 @@ class Trainer:
                     self.Ls.append(q_loss.mean())
                 if fraction_loss is not None:
                     self.FLs.append(fraction_loss.mean())
-        mean = lambda xs, k: float(sum(float(x) for x in xs[-k:]) / len(xs[-k:])) if xs else None
-        return dict(frames=self.frame_count, fraction_loss=mean(self.FLs, 20), loss=mean(self.Ls, 20),
-                    return_train=mean(self.Rs, 20), return_train_max=max(self.Rs) if self.Rs else None,
-                    qmax=mean(self.Qs, 100))
+        if returns:
+            self.R_max = max(max(returns), self.R_max if self.R_max is not None else max(returns))
+        hmean = lambda xs: float(sum(float(x) for x in xs) / len(xs)) if xs else None
+        # one device->host read for both loss means (the reference syncs once per update, agent.py:163-169)
+        dev = [torch.stack(tuple(xs)).mean() for xs in (self.Ls, self.FLs) if xs]
+        vals = torch.stack(dev).tolist() if dev else []
+        loss = vals.pop(0) if self.Ls else None
+        frac = vals.pop(0) if self.FLs else None
+        return dict(frames=self.frame_count, fraction_loss=frac, loss=loss, return_train=hmean(self.Rs),
+                    return_train_max=self.R_max, qmax=hmean(self.Qs))

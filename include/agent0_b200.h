@@ -11,7 +11,9 @@
  *
  * Reference interfaces replaced (paths relative to the reference repo):
  *   agent0/deepq/replay.py:15-27   ReplayDataset.__init__          -> a0_rb_create / a0_rb_destroy
- *   agent0/deepq/replay.py:45-53   ReplayDataset.extend            -> a0_ix_plan + a0_rb_ingest_plan
+ *   agent0/deepq/replay.py:45-53   ReplayDataset.extend            -> a0_ex_extend (the reference's lz4 entries,
+ *                                                                     decoded and de-duplicated on the device),
+ *                                                                     a0_ix_plan + a0_rb_ingest_plan
  *                                                                     (= a0_pt_mark + a0_rb_append), or
  *                                                                     a0_rb_ingest_steps for 1-step actors
  *   agent0/deepq/replay.py:39-43   ReplayDataset.__iter__ (draw)   -> a0_pt_sample
@@ -45,6 +47,7 @@ typedef void* a0_stream_t;               /* cudaStream_t */
 #define A0_OK 0
 #define A0_EINVAL (-1)
 #define A0_ENOMEM (-2)
+#define A0_EFAULT (-3)      /* a kernel of an EARLIER call on this handle gave up (see A0_OPT_MAIL_TIMEOUT_US) */
 #define A0_STACK 4          /* frames per observation stack (FrameStack(4), atari_wrappers.py:62) */
 #define A0_SLOTS 8          /* obs stack + next-obs stack */
 #define A0_MAX_NSTEP 16
@@ -89,6 +92,13 @@ const char* a0_last_error(void);
  * the index list, recomputes its chunk in shared memory; the last CTA finishes the top levels); 0
  * falls back to the cluster schedules selected by A0_OPT_K2B_BULK_MIN.  Same tree either way.       */
 #define A0_OPT_K2B_CHUNKS 8
+/* A0_OPT_MAIL_TIMEOUT_US (default 2 000 000; A0_MAIL_TIMEOUT_US in the environment): how long a gather CTA of
+ * a0_rb_sample_gather polls its mailbox word before it gives up.  The paired sampler posts every word
+ * within microseconds; a CTA that still has nothing after this long was launched without its sampler
+ * (a failed launch, a mis-paired caller), sets the handle's fault word and exits instead of spinning
+ * forever.  The next a0_rb_sample_gather / a0_rb_gather / a0_pt_sample / a0_pt_update on the handle
+ * returns A0_EFAULT (and clears the word).                                                          */
+#define A0_OPT_MAIL_TIMEOUT_US 9
 int a0_set_option(int32_t option, int64_t value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------
@@ -174,12 +184,48 @@ int a0_dd_destroy(a0_dedupe_t* dd);
 int a0_dd_resolve(a0_dedupe_t* dd, a0_index_t* ix, const int64_t* stream, const uint8_t* frames,
                   int32_t m, int64_t* fs8_out, int64_t* new_src_out, int32_t* n_new_out);
 
+/* ---- K6: ReplayDataset.extend with the entries still compressed (agent0/deepq/replay.py:45-53) --------
+ * The reference actor ships every transition as (lz4.block.compress(concat(st, st_next)), a, r, d)
+ * (agent0/deepq/agent.py:78-81): a python-lz4 block = 4-byte little-endian decoded size + one raw LZ4
+ * block of 8 frames.  a0_ex_extend takes m such entries exactly as they arrive -- `blobs` is their
+ * concatenation in host memory, blob_len[i] the length of entry i (an entry of exactly 8*frame_bytes is
+ * taken as uncompressed) -- copies only the COMPRESSED bytes to the device, decodes them there (one warp
+ * per entry, output staged in shared memory), labels every frame with the first byte-identical frame of
+ * its stream's previous entry / its own entry (hash gate + full compare, so a match is always
+ * bit-exact), reads 8 label bytes per entry back, resolves them against the ring index on the host
+ * (a0_ex_resolve: the decisions of a0_dd_resolve) and appends the new frames straight from the decoded
+ * scratch (K2b marks + K1).  stream[i] = the actor env entry i comes from (entry order inside a stream is
+ * its time order); action / reward / done as a0_ix_plan.  The index must have been created with
+ * n_step = 1: reference entries are already n-step folded.  Synchronises `cuda_stream` once per 2048
+ * entries (the labels); the appends themselves are stream-ordered.  A malformed block fails the call
+ * with A0_EINVAL before anything of its batch is committed.
+ * a0_ex_create: h may be NULL for host-only use of a0_ex_resolve (tests of the rule without a GPU).   */
+typedef struct a0_extend a0_extend_t;
+int a0_ex_create(a0_extend_t** out, a0_replay_t* h, a0_index_t* ix);
+int a0_ex_destroy(a0_extend_t* ex);
+int a0_ex_extend(a0_extend_t* ex, const uint8_t* blobs /* host */, const int64_t* blob_len /* host [m] */,
+                 const int64_t* stream, const int64_t* action, const double* reward, const uint8_t* done,
+                 int32_t m, float alpha, a0_stream_t cuda_stream);
+/* The decode kernel alone: frames_out dev u8[m][8][frame_bytes], status_out host i32[m] (0 = ok,
+ * 1 bad size prefix, 2 truncated input, 3 output overrun, 4 bad match offset, 5 short output).      */
+int a0_ex_decode(a0_extend_t* ex, const uint8_t* blobs /* host */, const int64_t* blob_len /* host [m] */,
+                 int32_t m, uint8_t* frames_out /* dev */, int32_t* status_out /* host */,
+                 a0_stream_t cuda_stream);
+/* Host rule: labels u8[m][8] (0..7 = identical to that frame of the stream's previous entry, 8+c =
+ * identical to frame c <= j of its own entry; always the FIRST identical candidate in that order)
+ * -> fs8_out / new_src_out / n_new_out exactly as a0_dd_resolve produces them from the bytes.        */
+int a0_ex_resolve(a0_extend_t* ex, const int64_t* stream, const uint8_t* labels, int32_t m,
+                  int64_t* fs8_out, int64_t* new_src_out, int32_t* n_new_out);
+/* microseconds of the last a0_ex_extend / a0_ex_decode call: {host staging, wait for decode + label,
+ * host resolve + plan, append launches, device time of decode + label (CUDA events), entries}       */
+int a0_ex_last_timing(a0_extend_t* ex, float* out6);
+
 /* ---- staged ingest: execute a plan on the device ------------------------------------------------
  * One pinned H2D copy of {frames, positions, record metadata, marks} from a double-buffered
  * staging area owned by the handle, then a0_pt_mark and a0_rb_append on `stream`.  frames:
  * host u8[*][frame_bytes]; new_frame_src (host, optional) picks the n_new frames to store, in
  * allocation order, out of it (NULL: the first n_new).  Flags: FRAMES_ON_DEVICE = frames is a
- * device pointer already in allocation order; FRAMES_PINNED = frames is page-locked host memory
+ * device pointer (with new_frame_src: K1 reads frames[new_frame_src[j]]; without: allocation order); FRAMES_PINNED = frames is page-locked host memory
  * in allocation order that stays untouched until `stream` has passed this call (it is copied by
  * DMA straight from there, no staging memcpy); COPY_STREAM = the H2D copies are issued on a
  * copy stream owned by the handle and `stream` waits for them, so the DMA overlaps the kernels
@@ -291,6 +337,14 @@ int a0_rb_sample_gather(a0_replay_t* h, const float* u /* dev [total] or NULL */
                         float* weight_out, int32_t n_step, double gamma, uint8_t* frames_out,
                         int64_t* action_out, double* reward64_out, float* reward32_out,
                         uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream);
+
+/* TEST HOOK: the gather half of a0_rb_sample_gather launched WITHOUT its sampler -- what a failed sampler
+ * launch or a mis-paired caller would leave behind.  Every CTA times out (A0_OPT_MAIL_TIMEOUT_US), the
+ * kernel ends, and the next call on the handle returns A0_EFAULT.  Never call it on a production path. */
+int a0_rb_gather_unpaired(a0_replay_t* h, int32_t count, uint8_t* frames_out, a0_stream_t stream);
+/* A0_EFAULT (once) if a kernel of an earlier call reported a fault, else A0_OK.  Reads a mapped host word:
+ * no synchronisation, so synchronise the stream first to observe the kernels queued on it.           */
+int a0_rb_check_fault(a0_replay_t* h);
 
 /* K3 with the learner's input conversion fused in (agent.py:129-135: reshape, .float(), .div(255),
  * split into obs / next_obs).  obs_out, next_out: f32 [count][4][frame_bytes], contiguous, ready

@@ -390,3 +390,32 @@ def test_c51_short_chain_kernel_is_bit_identical_to_the_general_kernel_and_match
     np.testing.assert_allclose(_np(f.target_prob), m, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(_np(f.loss), loss, rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(_np(f.grad), grad, rtol=1e-5, atol=1e-5)
+
+
+def test_unpaired_mailbox_gather_times_out_instead_of_hanging():
+    """The gather half of a0_rb_sample_gather launched without its sampler (what a failed sampler launch or
+    a mis-paired caller would leave): every CTA gives up after A0_OPT_MAIL_TIMEOUT_US, the kernel ends, the
+    handle reports A0_EFAULT exactly once, and the shard keeps working."""
+    import time
+
+    from agent0_b200.replay import ReplayDataset
+    from agent0_b200.synth import fill_shard_synthetic
+    lib = _lib.load()
+    cfg = make_config("c51", per=True, n_step=1, batch_size=8, replay_size=256, num_envs=2)
+    rp = ReplayDataset(cfg, native_nstep=True)
+    fill_shard_synthetic(rp, 128, 2, 3)
+    out = torch.empty(8, 8 * rp.F, dtype=torch.uint8, device="cuda")
+    A0_OPT_MAIL_TIMEOUT_US = 9
+    _lib.check(lib.a0_set_option(A0_OPT_MAIL_TIMEOUT_US, 20000), "a0_set_option")
+    try:
+        t0 = time.perf_counter()
+        _lib.check(lib.a0_rb_gather_unpaired(rp.h, 8, out.data_ptr(), _lib.stream_ptr(rp.device)), "a0_rb_gather_unpaired")
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 5.0
+        with pytest.raises(RuntimeError, match="timed out waiting for its sampler"):
+            rp.gather(torch.arange(4, device="cuda"))
+        assert lib.a0_rb_check_fault(rp.h) == 0                     # reported once, then cleared
+        b = rp.sample(8, k_batches=2, seed=3)                        # the shard still works
+        assert b.frames.shape[0] == 16 and int(b.indices.min()) >= 0
+    finally:
+        _lib.check(lib.a0_set_option(A0_OPT_MAIL_TIMEOUT_US, 2000000), "a0_set_option")

@@ -279,3 +279,48 @@ def test_overlapped_sample_gather_equals_the_two_separate_launches(Bn, k, per):
     if per:
         w = lb.w.view(k, Bn).max(dim=1)[0]
         assert torch.allclose(w, torch.ones_like(w), atol=1e-6)
+
+
+def test_uniform_replay_stays_uniform_under_the_loop():
+    """Uniform replay (BASELINE configs[0]: DQN, n_step=1): the loop's K4 must not raise the shard's running
+    max loss, and appended records must get leaf 1.0 whatever max_p holds -- otherwise the tree descent
+    draws newer records more often than older ones.  Leaves all equal 1 after steps and appends; the
+    draw's empirical law is flat; a NaN / inf loss leaves a prioritized tree finite."""
+    from agent0_b200.hotloop import ReplayTargetLoop
+    from agent0_b200.replay import ReplayDataset
+    cfg = make_config("dqn", per=False, n_step=1, batch_size=B, replay_size=2048, double_q=False, dueling=False, num_envs=8,
+                      action_dim=A)
+    rp = ReplayDataset(cfg, native_nstep=True)
+    fill_shard_synthetic(rp, 1024, 8, 5)
+    o = _outputs("dqn", B * L)
+    o["online"] *= 50                                        # losses far above 1: what used to inflate max_p
+    loop = ReplayTargetLoop(rp, "dqn", B, L, A, o, n_step=1, double_q=False, rng_seed=11)
+    rp.push_dynamic()
+    for _ in range(4):
+        loop.step()
+    assert float(loop.loss.max()) > 1.0
+    assert rp.max_p == 1.0
+    rp.max_p_tensor.fill_(37.0)                              # even a poisoned max_p must not show in new leaves
+    streams = np.arange(64, dtype=np.int64) % 8
+    frames = torch.randint(0, 256, (64, rp.F), dtype=torch.uint8, device="cuda")
+    rp.append_steps(streams, np.ones(64, dtype=np.int64), frames, np.zeros(64, dtype=np.int64), np.zeros(64), np.zeros(64, dtype=bool))
+    leaves = rp.priority.leaves()[:rp.size].cpu().numpy()
+    live = rp.index.sampleable
+    assert (leaves[live] == 1.0).all() and (leaves[~live] == 0.0).all()
+    rp.push_dynamic()
+    counts = torch.zeros(rp.size, device="cuda")
+    for _ in range(200):
+        loop.step()
+        counts.index_add_(0, loop.idx, torch.ones_like(loop.idx, dtype=torch.float32))
+    c = counts.cpu().numpy()[live]
+    n_draws, n_live = 200 * B * L, int(live.sum())
+    lam = n_draws / n_live
+    assert abs(c[:n_live // 2].sum() / n_draws - 0.5) < 0.02 and c.max() < lam + 8 * np.sqrt(lam) + 8
+    # a prioritized shard survives a NaN and an infinite loss: the old leaves stay, the root stays finite
+    rp2 = _shard("dqn")
+    before = rp2.priority.leaves().clone()
+    ids = torch.tensor([5, 6, 7, 8], device="cuda")
+    rp2.update_priority(ids, torch.tensor([float("nan"), float("inf"), -1.0, 2.0], device="cuda"))
+    after = rp2.priority.leaves()
+    assert torch.equal(after[:8][5:8], before[:8][5:8]) and abs(float(after[8]) - (2.0 + 0.01) ** 0.5) < 1e-6
+    assert np.isfinite(float(rp2.priority_sum())) and np.isfinite(rp2.max_p)
