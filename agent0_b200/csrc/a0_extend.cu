@@ -44,24 +44,28 @@ enum { A0_LZ_OK = 0, A0_LZ_BAD_SIZE = 1, A0_LZ_INPUT_OVERRUN = 2, A0_LZ_OUTPUT_O
        A0_LZ_SHORT_OUTPUT = 5 };
 
 // ------------------------------------------------------------------------------------------------
-// device: copies inside one warp
+// device: copies inside one warp.  The decoded entry lives in the CTA's dynamic shared memory; the
+// helpers index the array directly (a pointer parameter made the compiler rebuild the generic->shared
+// address inside every loop iteration: S2R SR_CgaCtaId + LEA per byte, ncu source view).
 // ------------------------------------------------------------------------------------------------
+extern __shared__ __align__(128) uint8_t a0_k6_out[];
+
 // `len` literal bytes from the compressed stream (global memory, any alignment) to out[op..]
-__device__ __forceinline__ void a0_k6_copy_in(uint8_t* out, int op, const uint8_t* __restrict__ src, int len, int lane) {
+__device__ __forceinline__ void a0_k6_copy_in(int op, const uint8_t* __restrict__ src, int len, int lane) {
   if (len < 128) {
-#pragma unroll 1
-    for (int i = lane; i < len; i += 32) out[op + i] = src[i];
+#pragma unroll 2
+    for (int i = lane; i < len; i += 32) a0_k6_out[op + i] = src[i];
     return;
   }
   // destination-aligned 32-bit words; a source word is assembled from two aligned loads
   const int head = (4 - (op & 3)) & 3;
-  if (lane < head) out[op + lane] = src[lane];
+  if (lane < head) a0_k6_out[op + lane] = src[lane];
   const uint8_t* s2 = src + head;
   const int d2 = op + head, rem = len - head, nw = rem >> 2;
   const uintptr_t sa = (uintptr_t)s2;
   const uint32_t sh = (uint32_t)(sa & 3) * 8;
   const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
-  uint32_t* dw = reinterpret_cast<uint32_t*>(out + d2);
+  uint32_t* dw = reinterpret_cast<uint32_t*>(a0_k6_out + d2);
   if (sh == 0) {
 #pragma unroll 4
     for (int k = lane; k < nw; k += 32) dw[k] = sw[k];
@@ -70,94 +74,101 @@ __device__ __forceinline__ void a0_k6_copy_in(uint8_t* out, int op, const uint8_
     for (int k = lane; k < nw; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], sh);
   }
   const int tail = rem & 3;
-  if (lane < tail) out[d2 + 4 * nw + lane] = s2[4 * nw + lane];
+  if (lane < tail) a0_k6_out[d2 + 4 * nw + lane] = s2[4 * nw + lane];
 }
 
 // LZ4 match: `ml` bytes from out[op - off ..] to out[op ..]; the ranges overlap when off < ml (the
 // copy then repeats the last `off` bytes).  Everything before `op` is visible (the caller synchronised).
-__device__ __forceinline__ void a0_k6_copy_match(uint8_t* out, int op, int off, int ml, int lane) {
+__device__ __forceinline__ void a0_k6_copy_match(int op, int off, int ml, int lane) {
   const int sp = op - off;
   if (off >= ml) {
     // disjoint ranges: no ordering needed between iterations
     if (ml < 128) {
-#pragma unroll 1
-      for (int i = lane; i < ml; i += 32) out[op + i] = out[sp + i];
+#pragma unroll 2
+      for (int i = lane; i < ml; i += 32) a0_k6_out[op + i] = a0_k6_out[sp + i];
       return;
     }
     const int head = (4 - (op & 3)) & 3;
-    if (lane < head) out[op + lane] = out[sp + lane];
+    if (lane < head) a0_k6_out[op + lane] = a0_k6_out[sp + lane];
     const int d2 = op + head, s2 = sp + head, rem = ml - head, nw = rem >> 2;
     const uint32_t sh = (uint32_t)(s2 & 3) * 8;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(out + (s2 & ~3));
-    uint32_t* dw = reinterpret_cast<uint32_t*>(out + d2);
-    // the second source word of the last destination word may be the first destination word (off >= ml
-    // keeps every byte that is actually used in front of op): reading it early or late is harmless only
-    // if it is not used, which sh == 0 guarantees; with sh != 0 the bytes taken from it lie before op + head
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(a0_k6_out + (s2 & ~3));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(a0_k6_out + d2);
+    // with sh != 0 the second source word of the last destination words may already be destination (off >= ml
+    // only keeps the bytes that are USED in front of op): the bytes taken from it lie before op, the rest of
+    // the word is shifted out, so reading it early or late is harmless
     if (sh == 0) {
 #pragma unroll 4
       for (int k = lane; k < nw; k += 32) dw[k] = sw[k];
     } else {
-#pragma unroll 1
+#pragma unroll 2
       for (int k = lane; k < nw; k += 32) {
         const uint32_t lo = sw[k], hi = sw[k + 1];
         dw[k] = __funnelshift_r(lo, hi, sh);
       }
     }
     const int tail = rem & 3;
-    if (lane < tail) out[d2 + 4 * nw + lane] = out[s2 + 4 * nw + lane];
+    if (lane < tail) a0_k6_out[d2 + 4 * nw + lane] = a0_k6_out[s2 + 4 * nw + lane];
     return;
   }
-  if (off >= 32) {
-    // overlapping, period >= one warp: an iteration reads what earlier iterations wrote
-#pragma unroll 1
-    for (int base = 0; base < ml; base += 32) {
-      const int i = base + lane;
-      if (i < ml) out[op + i] = out[sp + i];
-      __syncwarp();
-    }
-    return;
-  }
-  // period < 32: every byte comes from the `off` bytes in front of op, which are complete
-  if (ml >= 64 && (off == 1 || off == 2 || off == 4)) {
+  // Overlapping match: the output repeats the `off` bytes in front of op, which are complete, so byte i
+  // comes from out[sp + i mod off] and NO iteration depends on another (copying "what earlier iterations
+  // wrote" needed a warp barrier per 32 bytes: 13 instructions per iteration, 16 % of the kernel on
+  // Atari-like frames whose rows repeat with period 84).
+  if (ml >= 32 && (off == 1 || off == 2 || off == 4)) {
     const int head = (4 - (op & 3)) & 3;
     uint32_t w = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w |= (uint32_t)out[sp + ((head + q) & (off - 1))] << (8 * q);
-    if (lane < head) out[op + lane] = out[sp + (lane & (off - 1))];
+    for (int q = 0; q < 4; ++q) w |= (uint32_t)a0_k6_out[sp + ((head + q) & (off - 1))] << (8 * q);
     const int d2 = op + head, rem = ml - head, nw = rem >> 2;
-    uint32_t* dw = reinterpret_cast<uint32_t*>(out + d2);
-    // the pattern bytes were read above (sp .. op); the first stores may overwrite nothing in front of op
+    const int tail = rem & 3;
+    if (lane < head) a0_k6_out[op + lane] = (uint8_t)(w >> (8 * ((lane + 4 - head) & 3)));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(a0_k6_out + d2);
 #pragma unroll 4
     for (int k = lane; k < nw; k += 32) dw[k] = w;
-    const int tail = rem & 3;
-    if (lane < tail) out[d2 + 4 * nw + lane] = (uint8_t)(w >> (8 * lane));
+    if (lane < tail) a0_k6_out[d2 + 4 * nw + lane] = (uint8_t)(w >> (8 * lane));
     return;
   }
-#pragma unroll 1
-  for (int i = lane; i < ml; i += 32) out[op + i] = out[sp + (i % off)];
+  int s, step;
+  if (off >= 32) { s = lane; step = 32; if (step >= off) step -= off; }
+  else { s = lane % off; step = 32 % off; }
+#pragma unroll 4
+  for (int i = lane; i < ml; i += 32) {
+    a0_k6_out[op + i] = a0_k6_out[sp + s];
+    s += step;
+    if (s >= off) s -= off;
+  }
 }
 
-__device__ __forceinline__ unsigned long long a0_k6_mix(unsigned long long h) {
-  h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 29;
+__device__ __forceinline__ uint32_t a0_k6_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__device__ __forceinline__ uint32_t a0_k6_mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
 }
-// 64-bit content hash of one frame held in shared memory (a gate in front of the byte compare, nothing
-// depends on its exact value outside this file).  Lanes are seeded differently, so equal words in
-// different places do not cancel in the final xor.
-__device__ __forceinline__ unsigned long long a0_k6_frame_hash(const uint32_t* w, int nwords, int lane) {
-  unsigned long long h0 = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)(lane + 1) * 0xC2B2AE3D27D4EB4Full);
-  unsigned long long h1 = ~h0;
-  int i = lane;
+// 64-bit content hash of one frame held in shared memory (a gate in front of the byte compare: nothing
+// depends on its value outside this file).  Four independent 32-bit multiply-rotate streams over 16-byte
+// vector loads -- three instructions per word (the first version's 64-bit multiplies were a fifth of the
+// kernel's instructions).  Lanes are seeded differently, so equal words in different places do not cancel
+// in the final xor across the warp.
+__device__ __forceinline__ unsigned long long a0_k6_frame_hash(const uint8_t* frame, int nvec, int lane) {
+  uint32_t h0 = 0x9E3779B1u * (uint32_t)(lane + 1), h1 = 0x85EBCA77u * (uint32_t)(lane + 33);
+  uint32_t h2 = 0xC2B2AE3Du * (uint32_t)(lane + 65), h3 = 0x27D4EB2Fu * (uint32_t)(lane + 97);
+  const uint4* v4 = reinterpret_cast<const uint4*>(frame);
 #pragma unroll 2
-  for (; i + 32 < nwords; i += 64) {
-    h0 = (h0 ^ w[i]) * 0x9FB21C651E98DF25ull; h0 = (h0 << 29) | (h0 >> 35);
-    h1 = (h1 ^ w[i + 32]) * 0x9FB21C651E98DF25ull; h1 = (h1 << 29) | (h1 >> 35);
+  for (int i = lane; i < nvec; i += 32) {
+    const uint4 v = v4[i];
+    h0 = a0_k6_rotl((h0 ^ v.x) * 0x9E3779B1u, 13);
+    h1 = a0_k6_rotl((h1 ^ v.y) * 0x85EBCA77u, 15);
+    h2 = a0_k6_rotl((h2 ^ v.z) * 0xC2B2AE3Du, 17);
+    h3 = a0_k6_rotl((h3 ^ v.w) * 0x27D4EB2Fu, 11);
   }
-  if (i < nwords) { h0 = (h0 ^ w[i]) * 0x9FB21C651E98DF25ull; h0 = (h0 << 29) | (h0 >> 35); }
-  unsigned long long h = a0_k6_mix(h0 + 3ull * h1);
+  uint32_t lo = a0_k6_mix32(h0 + 0x165667B1u * h2), hi = a0_k6_mix32(h1 + 0x9E3779B1u * h3);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, o);
-  return a0_k6_mix(h);
+  for (int o = 16; o > 0; o >>= 1) {
+    lo ^= __shfl_xor_sync(0xffffffffu, lo, o);
+    hi ^= __shfl_xor_sync(0xffffffffu, hi, o);
+  }
+  return ((unsigned long long)a0_k6_mix32(hi ^ 0x5bd1e995u) << 32) | a0_k6_mix32(lo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,8 +177,6 @@ __device__ __forceinline__ unsigned long long a0_k6_frame_hash(const uint32_t* w
 __global__ void __launch_bounds__(32)
 a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ desc, int32_t F, uint8_t* __restrict__ dec,
                  unsigned long long* __restrict__ hash, int32_t* __restrict__ status) {
-  extern __shared__ __align__(128) uint8_t a0_k6_out[];
-  uint8_t* out = a0_k6_out;
   const int t = blockIdx.x, lane = threadIdx.x;
   const A0ExDesc d = desc[t];
   const uint8_t* __restrict__ in = comp + d.off;
@@ -176,7 +185,7 @@ a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ 
   if (n == total) {
     // raw entry (ndarray / bytes of the decoded size): blob starts are 16-byte aligned in the staged block
     const uint4* s = reinterpret_cast<const uint4*>(in);
-    uint4* o = reinterpret_cast<uint4*>(out);
+    uint4* o = reinterpret_cast<uint4*>(a0_k6_out);
 #pragma unroll 4
     for (int i = lane; i < (total >> 4); i += 32) o[i] = __ldg(s + i);
   } else {
@@ -206,7 +215,7 @@ a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ 
       if (ll > 0) {
         if (ll > n - ip) { err = A0_LZ_INPUT_OVERRUN; break; }
         if (ll > total - op) { err = A0_LZ_OUTPUT_OVERRUN; break; }
-        a0_k6_copy_in(out, op, in + ip, ll, lane);
+        a0_k6_copy_in(op, in + ip, ll, lane);
         ip += ll;
         op += ll;
       }
@@ -228,24 +237,24 @@ a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ 
       if (off == 0 || off > op) { err = A0_LZ_BAD_OFFSET; break; }
       if (ml > total - op) { err = A0_LZ_OUTPUT_OVERRUN; break; }
       __syncwarp();                              // everything written so far is visible to every lane
-      a0_k6_copy_match(out, op, off, ml, lane);
+      a0_k6_copy_match(op, off, ml, lane);
       op += ml;
     }
     if (err == A0_LZ_OK && op != total) err = A0_LZ_SHORT_OUTPUT;
   }
   __syncwarp();
   if (lane == 0) status[t] = err;
-  const int nwords = F >> 2;
+  const int nvec = F >> 4;
 #pragma unroll 1
   for (int f = 0; f < A0_SLOTS; ++f) {
-    const unsigned long long h = a0_k6_frame_hash(reinterpret_cast<const uint32_t*>(out + (size_t)f * F), nwords, lane);
+    const unsigned long long h = a0_k6_frame_hash(a0_k6_out + (size_t)f * F, nvec, lane);
     if (lane == 0) hash[(size_t)t * A0_SLOTS + f] = h;
   }
   // the whole entry leaves the SM as one bulk copy (shared -> global through the async proxy)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
   if (lane == 0) {
-    a0_bulk_store(dec + (size_t)t * total, a0_smem_u32(out), (uint32_t)total);
+    a0_bulk_store(dec + (size_t)t * total, a0_smem_u32(a0_k6_out), (uint32_t)total);
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }

@@ -777,6 +777,175 @@ a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, co
   }
 }
 
+// ---- QR-sized samples: the same pair sums in O(N log N) ------------------------------------------------------
+// 200 x 200 pairs at 8 issue slots each made QR-200 the one kernel of the path bound by arithmetic (10.4 us per
+// batch of 512, 0.32 of the FP32 peak).  For a fixed online quantile q the targets split, once SORTED, into four
+// contiguous ranges of u = q - T:
+//     A: T <= q-1  (u >= 1,  |u| - 1/2, weight 1-tau)      B: q-1 < T < q   (0 < u < 1,  u^2/2, weight 1-tau)
+//     C: q <= T < q+1 (-1 < u <= 0, u^2/2, weight tau)      D: T >= q+1      (u <= -1, |u| - 1/2, weight tau)
+// and over a range the Huber terms are polynomials in q whose coefficients are the range's count, sum T and
+// sum T^2 -- differences of prefix sums.  (At u = +-1 and u = 0 neighbouring ranges give the same value and the
+// same clamp, so which side a boundary target falls on does not matter.)  Per sample: sort the Ni targets (warp
+// bitonic networks in registers, then three merge levels in shared memory where every element finds its rank in
+// the sibling run by binary search -- no compare-exchange stages, three barriers), prefix sums of T and T^2, and
+// per online quantile three binary searches plus ~25 flops.  The prefix sums and the polynomial are evaluated in
+// float64: the quadratic ranges subtract numbers of size N*T^2 to get terms of size (q-T)^2 <= 1.  The summation
+// order differs from the reference's pairwise sum, so this kernel lives under the 1e-5 relative contract (it is
+// closer to the exact sum than the fp32 pairwise form); oracle.losses.huber_qr_sorted is its specification.
+constexpr int QS_THREADS = A0_MAX_QUANTILES;     // 256 = 8 sorted runs of one warp each
+static_assert(QS_THREADS == 256, "the merge tree below is written for 8 warps");
+
+template <int S_LOG>
+__device__ __forceinline__ void a0_qs_merge(const float* __restrict__ src, float* __restrict__ dst, int tid) {
+  constexpr int S = 1 << S_LOG;
+  const int r = tid >> S_LOG, p = tid & (S - 1);
+  const float x = src[tid];
+  const float* sib = src + ((r ^ 1) << S_LOG);
+  const bool right = r & 1;                       // ties: the left run's elements go first (unique ranks)
+  int lo = 0;
+#pragma unroll
+  for (int step = S >> 1; step > 0; step >>= 1) {
+    const float v = sib[lo + step - 1];
+    if (right ? (v <= x) : (v < x)) lo += step;
+  }
+  const float v = sib[lo];
+  if (right ? (v <= x) : (v < x)) ++lo;
+  dst[((r >> 1) << (S_LOG + 1)) + p + lo] = x;
+}
+
+__global__ void __launch_bounds__(QS_THREADS)
+a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict__ q, const float* __restrict__ qt,
+                      const float* __restrict__ taus, const float* __restrict__ qsel, int32_t Ni, int32_t Nj,
+                      float* __restrict__ grad) {
+  __shared__ float bufA[QS_THREADS], bufB[QS_THREADS];
+  __shared__ double S1[QS_THREADS + 1], S2[QS_THREADS + 1];
+  __shared__ double ws1[QS_THREADS / 32], ws2[QS_THREADS / 32];
+  __shared__ float sMean[A0_MAX_ACTIONS];
+  __shared__ float red[QS_THREADS / 32];
+  __shared__ int s_astar;
+  A0_PDL_PROLOGUE();
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int nwarps = QS_THREADS / 32;
+  const int A = c.A;
+  const size_t sN_q = layout == 0 ? 1 : (size_t)A, sA_q = layout == 0 ? (size_t)Nj : 1;
+  const size_t sN_t = layout == 0 ? 1 : (size_t)A, sA_t = layout == 0 ? (size_t)Ni : 1;
+  const float* qb = q + (size_t)b * A * Nj;
+  const float* tb = qt + (size_t)b * A * Ni;
+  // ---- action selection (as a0_k4_quantile) ------------------------------------------------------------
+  if (qsel) {
+    if (wid == 0) {
+      const int as = a0_warp_argmax(lane < A ? qsel[(size_t)b * A + lane] : -INFINITY, lane);
+      if (lane == 0) s_astar = as;
+    }
+  } else {
+    for (int a2 = wid; a2 < A; a2 += nwarps) {
+      float s = 0.0f;
+      for (int i = lane; i < Ni; i += 32) s += tb[a2 * sA_t + i * sN_t];
+      s = a0_warp_sum(s);
+      if (lane == 0) sMean[a2] = __fdiv_rn(s, (float)Ni);
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const int as = a0_warp_argmax(lane < A ? sMean[lane] : -INFINITY, lane);
+      if (lane == 0) s_astar = as;
+    }
+  }
+  const int a = (int)c.action[b];
+  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
+  float qj = 0.0f, tau = 0.0f;
+  if (tid < Nj) {
+    qj = qb[a * sA_q + tid * sN_q];
+    tau = taus ? taus[(size_t)b * Nj + tid] : __fdiv_rn((float)(2 * tid + 1), 2.0f * (float)Nj);
+  }
+  __syncthreads();
+  const int a_star = s_astar;
+  // ---- sort the targets: one bitonic network per warp, then merge 32 -> 64 -> 128 -> 256 ------------------
+  float x = tid < Ni ? a0_td_target(r, d, c.gamma_n, tb[a_star * sA_t + tid * sN_t]) : INFINITY;   // pads sort to the end
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float y = __shfl_xor_sync(0xffffffffu, x, j);
+      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+      x = (lower == up) ? fminf(x, y) : fmaxf(x, y);
+    }
+  }
+  bufA[tid] = x;
+  __syncthreads();
+  a0_qs_merge<5>(bufA, bufB, tid);
+  __syncthreads();
+  a0_qs_merge<6>(bufB, bufA, tid);
+  __syncthreads();
+  a0_qs_merge<7>(bufA, bufB, tid);
+  __syncthreads();
+  // ---- prefix sums of T and T^2 over the sorted targets (float64) -----------------------------------------
+  {
+    const double y = tid < Ni ? (double)bufB[tid] : 0.0;
+    double p1 = y, p2 = y * y;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t1 = __shfl_up_sync(0xffffffffu, p1, o), t2 = __shfl_up_sync(0xffffffffu, p2, o);
+      if (lane >= o) { p1 += t1; p2 += t2; }
+    }
+    if (lane == 31) { ws1[wid] = p1; ws2[wid] = p2; }
+    __syncthreads();
+    double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < nwarps; ++w2)
+      if (w2 < wid) { b1 += ws1[w2]; b2 += ws2[w2]; }
+    S1[tid + 1] = p1 + b1;
+    S2[tid + 1] = p2 + b2;
+    if (tid == 0) { S1[0] = 0.0; S2[0] = 0.0; }
+  }
+  __syncthreads();
+  // ---- per online quantile: the three range boundaries, then the closed form ---------------------------------
+  float lsum = 0.0f, gsum = 0.0f;
+  if (tid < Nj) {
+    const float qm = qj - 1.0f, qp = qj + 1.0f;
+    int ia = 0, ib = 0, ic = 0;                   // #{T <= q-1}, #{T < q}, #{T < q+1}
+#pragma unroll
+    for (int step = QS_THREADS >> 1; step > 0; step >>= 1) {
+      const float va = bufB[ia + step - 1], vb = bufB[ib + step - 1], vc = bufB[ic + step - 1];
+      if (va <= qm) ia += step;
+      if (vb < qj) ib += step;
+      if (vc < qp) ic += step;
+    }
+    if (bufB[ia] <= qm) ++ia;
+    if (bufB[ib] < qj) ++ib;
+    if (bufB[ic] < qp) ++ic;
+    ia = min(ia, Ni); ib = min(max(ib, ia), Ni); ic = min(max(ic, ib), Ni);
+    const double qd = (double)qj, td = (double)tau;
+    const double nA = (double)ia, nB = (double)(ib - ia), nC = (double)(ic - ib), nD = (double)(Ni - ic);
+    const double s1a = S1[ia], s1b = S1[ib], s1c = S1[ic];
+    const double s1B = s1b - s1a, s2B = S2[ib] - S2[ia];
+    const double s1C = s1c - s1b, s2C = S2[ic] - S2[ib];
+    const double s1D = S1[Ni] - s1c;
+    const double A_ = nA * (qd - 0.5) - s1a;
+    const double B_ = 0.5 * ((nB * qd - 2.0 * s1B) * qd + s2B);
+    const double C_ = 0.5 * ((nC * qd - 2.0 * s1C) * qd + s2C);
+    const double D_ = s1D - nD * (qd + 0.5);
+    lsum = (float)((1.0 - td) * (A_ + B_) + td * (C_ + D_));
+    gsum = (float)((1.0 - td) * (nA + nB * qd - s1B) + td * (nC * qd - s1C - nD));
+  }
+  const float total = a0_block_sum(lsum, red, nwarps);
+  float* gb = grad + (size_t)b * A * Nj;
+  for (int i = tid; i < A * Nj; i += QS_THREADS) gb[i] = 0.0f;
+  __syncthreads();
+  if (tid < Nj) gb[a * sA_q + tid * sN_q] = __fdiv_rn(w, (float)Ni) * gsum;
+  if (tid == 0) a0_emit(c, b, __fdiv_rn(total, (float)Ni));
+}
+
+static int g_qh_sorted = -1;
+static bool a0_option_qh_sorted() {
+  if (g_qh_sorted < 0) {
+    const char* e = getenv("A0_QH_SORTED");
+    g_qh_sorted = e ? (atoi(e) != 0) : 1;
+  }
+  return g_qh_sorted != 0;
+}
+void a0_set_qh_sorted(int on) { g_qh_sorted = on != 0; }
+
 extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const float* q, const float* qt,
                                 const float* taus, const float* qsel, int32_t Ni, int32_t Nj, float* grad,
                                 const float* q_bar, const float* taus_full, float* fraction_loss,
@@ -795,6 +964,11 @@ extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const
   if (c->B == 0) return A0_OK;
   int threads = Ni > Nj ? Ni : Nj;
   threads = ((threads + 31) / 32) * 32;
+  if (!q_bar && Ni > 64 && Nj > 64 && a0_option_qh_sorted()) {      // QR-sized: O(N log N) sorted-target form
+    A0_LAUNCH(a0_k4_quantile_sorted, (unsigned)c->B, QS_THREADS, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
+              taus, qsel, Ni, Nj, grad);
+    return A0_OK;
+  }
   if (layout == 1 && qsel && c->A <= QH_SPEC_A && threads <= 64)
     A0_LAUNCH(a0_k4_quantile<true>, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
               taus, qsel, Ni, Nj, grad, q_bar, taus_full, fraction_loss, grad_taus);

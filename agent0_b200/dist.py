@@ -61,6 +61,102 @@ class FlatGradBucket:
         return None
 
 
+class OverlappedGradBucket(FlatGradBucket):
+    """The same flat buffer, all-reduced in ``n_buckets`` pieces WHILE the backward pass is still running
+    ("one flat bucket, overlap with backward").  Parameters keep their registration order in the
+    buffer (encoder first, head last); autograd produces gradients in the opposite order, so the buffer is cut
+    into contiguous ranges from the END: bucket 0 = the head and the big fully-connected layer (6.9 of the
+    7.3 MB of the deepq nets), ready before the convolution backward -- the expensive part -- has started, so
+    its NCCL call runs under it; the last bucket (the convolutions, 0.3 MB) is what stays exposed, at launch
+    latency.  A post-accumulate hook on every parameter counts its bucket down and issues
+    ``all_reduce(async_op=True)`` when the bucket is complete; ``wait()`` joins them before the optimizer step.
+    Works under CUDA-graph capture (the collectives are captured on NCCL's stream as parallel branches) and
+    with gloo on CPU tensors (tests).  Same sums as the single call, bit for bit per element: every element
+    is still reduced exactly once over the same ranks."""
+
+    def __init__(self, params, process_group=None, n_buckets=2, min_bucket_elems=32768, split_frac=0.5):
+        super().__init__(params, process_group)
+        sizes = [p.numel() for p in self.params]
+        total = sum(sizes)
+        # contiguous parameter ranges, cut from the end: a bucket closes at the first parameter after which at most
+        # split_frac of what was left remains for the earlier layers (deepq nets: right below the 3136x512 layer),
+        # and never holds fewer than min_bucket_elems elements
+        bounds = [len(self.params)]
+        if n_buckets > 1 and total > 2 * min_bucket_elems:
+            acc, target = 0, total
+            for i in range(len(self.params) - 1, 0, -1):
+                acc += sizes[i]
+                rest = total - sum(sizes[i:])
+                if len(bounds) < n_buckets and acc >= min_bucket_elems and 0 < rest <= split_frac * target:
+                    bounds.append(i)
+                    target, acc = rest, 0
+        bounds.append(0)
+        bounds = sorted(set(bounds), reverse=True)
+        self.buckets = []                                  # (param_lo, param_hi, elem_lo, elem_hi), latest layers first
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        for hi, lo in zip(bounds[:-1], bounds[1:]):
+            self.buckets.append((lo, hi, offs[lo], offs[hi]))
+        self._bucket_of = {}
+        for b, (lo, hi, _, _) in enumerate(self.buckets):
+            for i in range(lo, hi):
+                self._bucket_of[id(self.params[i])] = b
+        self._left = [hi - lo for lo, hi, _, _ in self.buckets]
+        self._handles = []
+        self.enabled = True                                # False: no collectives (bench: the step without the exchange)
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def zero_(self):
+        self.flat.zero_()
+        self._left = [hi - lo for lo, hi, _, _ in self.buckets]
+        self._handles = []
+
+    def _hook(self, p):
+        b = self._bucket_of[id(p)]
+        self._left[b] -= 1
+        if self._left[b] == 0 and self.enabled:
+            _, _, lo, hi = self.buckets[b]
+            self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def wait(self):
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    def all_reduce(self, async_op=False):
+        """After backward: buckets whose hooks did not fire (a parameter without a gradient this step) are reduced
+        now, then everything is joined."""
+        if self.world > 1 and self.enabled:
+            for b, left in enumerate(self._left):
+                if left > 0:
+                    _, _, lo, hi = self.buckets[b]
+                    self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+                    self._left[b] = 0
+        self.wait()
+        return None
+
+
+def global_batch_is_weights(prio, local_sum, beta, batch, process_group=None):
+    """IS weights normalised over the GLOBAL batch (trainer.py:91-94 for G shards sampled in parallel).
+
+    Rank r draws its B transitions from its own shard with P(i) = p_i / S_r / G (S_r = the shard's priority sum),
+    so the weight that corrects towards the uniform law over all N records is (N * P(i))^-beta = c * u_i with
+    u_i = (p_i / S_r)^-beta and c = (N / G)^-beta common to every rank.  The reference divides by the maximum over
+    the batch; for one learner at batch G*B that maximum runs over all ranks' draws: ONE all-reduce(MAX) of L
+    floats per draw.  (With the shard-local maximum -- the default, no collective on the data path -- S_r cancels
+    inside a rank's batch but differs between ranks.)  ``prio`` f32 [L*B] priorities of the sampled records
+    (K2a's prio_out), ``local_sum`` the shard's root.  Returns w [L*B] with max over the global batch = 1/(1+1e-8/c...)
+    i.e. u / (max_global u + 1e-8) -- c cancels except against the 1e-8, exactly as top/S do in the reference."""
+    u = (prio / local_sum).pow(-float(beta)).view(-1, int(batch))
+    mx = u.max(dim=1)[0].contiguous()
+    if process_group is not None and dist.get_world_size(process_group) > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=process_group)
+    return (u / (mx.unsqueeze(1) + 1e-8)).view(-1)
+
+
 def global_priority_stats(local_sum, local_top, process_group=None):
     """Sum of priorities and number of sampleable records over all shards (one 2-float SUM
     all-reduce).  Passing ``top=global_top`` and ``sum_offset=global_sum - local_sum`` to

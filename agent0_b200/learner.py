@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import losses as L
-from .dist import FlatGradBucket, adam_eps
+from .dist import FlatGradBucket, OverlappedGradBucket, adam_eps
 from .model import DeepQNet
 
 
@@ -64,8 +64,10 @@ class BaseLearner:
         self.alpha, self.eps = float(cfg.replay.alpha), float(cfg.replay.eps)
         self.max_p = max_p                      # device scalar shared with the replay shard (optional)
         self.nan_guard = not self.capturable    # agent.py:152-158 (costs one device->host sync per update)
-        # one flat gradient bucket: zeroed with one memset, all-reduced with one NCCL call
-        self.bucket = FlatGradBucket(list(self.model.params()), process_group)
+        # one flat gradient buffer, zeroed with one memset; with a process group it is all-reduced in two pieces
+        # from backward hooks, so the NCCL calls run under the convolution backward (dist.OverlappedGradBucket)
+        self.bucket = OverlappedGradBucket(list(self.model.params()), process_group) if self.world > 1 \
+            else FlatGradBucket(list(self.model.params()), process_group)
 
     # ---- helpers ----------------------------------------------------------------------------------
     def _kw(self):

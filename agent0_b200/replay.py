@@ -431,6 +431,12 @@ class ReplayDataset:
             _lib.stream_ptr(dev)), "a0_rb_gather_bf16" if bf16 else "a0_rb_gather_f32")
         return Batch(None, act, r64, d8, prio, idx, weights, r32, d32, boot, obs, nxt)
 
+    def global_is_weights(self, prio, batch, process_group):
+        """IS weights of a draw re-normalised over the GLOBAL batch of all shards (dist.global_batch_is_weights:
+        one all-reduce(MAX) of k_batches floats); the default weights of ``sample`` are normalised per shard."""
+        from .dist import global_batch_is_weights
+        return global_batch_is_weights(prio, self.tree[1], self.beta, batch, process_group)
+
     def is_weights(self, prio, batch):
         """trainer.py:91-94 with torch ops (used only when indices are given explicitly; the
         sampled path gets its weights from the K2a epilogue)."""

@@ -76,13 +76,19 @@ class GraphedUpdates:
 
 class Trainer:
     def __init__(self, cfg, process_group=None, native_nstep=False, graph=False, fused_input=False, sampler_seed=None,
-                 **replay_kw):
+                 global_is_max=False, **replay_kw):
         """graph=True: the learner updates of a step run as one CUDA-graph replay (GraphedUpdates).
         fused_input=True: K3 writes the learner's normalised f32 obs / next_obs directly
         (a0_rb_gather_f32) instead of u8 frames that torch then casts, divides and splits
         (agent.py:129-135); ``x * fl(1/255)``, i.e. bit-identical to torch's CUDA ``.div(255)``.
         sampler_seed: the prioritized draw takes its uniforms from the sampler's own Philox generator
-        (a0_pt_sample_rng) instead of torch's CUDA generator."""
+        (a0_pt_sample_rng) instead of torch's CUDA generator.
+        native_nstep=True needs a ShardActor / append_steps feed: ``step(transitions)`` takes the reference actor's
+        already n-step-folded tuples, which such a shard refuses.
+        global_is_max (with process_group): the IS weights of every draw are normalised by the maximum over the
+        GLOBAL batch of all ranks (one all-reduce(MAX) of learner_steps floats per draw) instead of per shard."""
+        self.pg = process_group
+        self.global_is_max = bool(global_is_max) and process_group is not None
         self.cfg = cfg
         self.sampler_seed = sampler_seed
         self.normalized = NORM_RECIP if fused_input else None
@@ -111,7 +117,10 @@ class Trainer:
                                                sampler_seed=self.sampler_seed)
             return self._graphed.run()
         out = []
-        for b in split_batches(self.replay.sample(B, k_batches=L, normalized=self.normalized, seed=self.sampler_seed), B):
+        drawn = self.replay.sample(B, k_batches=L, normalized=self.normalized, seed=self.sampler_seed)
+        if self.global_is_max and self.replay.prioritize:
+            drawn = drawn._replace(weights=self.replay.global_is_weights(drawn.priorities, B, self.pg))
+        for b in split_batches(drawn, B):
             result = self.learner.train(_learner_data(b))
             self.replay.update_priority(result["indices"], result["q_loss"])
             out.append((result["q_loss"], result["fraction_loss"]))

@@ -2,7 +2,8 @@
 """bench.py -- replay sample+target throughput of the agent0 deepq hot path on B200.
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path (one rank per GPU)
-  python bench.py --impl reference --steps K --warmup W    the reference's CPU pipeline (port)
+  python bench.py --impl reference --steps K --warmup W    the reference's own CPU pipeline (oracle/_ref: the unmodified
+                                                           reference; the restated port where it cannot run)
 
 One "step" = the inner loop of the reference's Trainer.step (agent0/deepq/trainer.py:82-104) with
 the CNN excluded (network outputs pre-generated): draw L = learner_steps batches of B transitions
@@ -57,10 +58,13 @@ def parse():
     p.add_argument("--actions", type=int, default=4)
     p.add_argument("--no-extra", action="store_true", help="skip the secondary workloads and sweeps")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-learner", action="store_true", help="skip the data-parallel learner-step measurement (learner_scaling)")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--torch-rng", action="store_true", help="uniforms from torch.Tensor.uniform_ (one more launch per step) instead of the sampler's own Philox")
     p.add_argument("--variant", type=int, default=0, help="K3 variant: 0 TMA ring, 1 LDG/STG, 2 TMA full staging, 3 TMA two CTAs per transition")
-    p.add_argument("--cpu-entries", type=int, default=16384, help="deque entries for the CPU baseline sample")
+    p.add_argument("--cpu-entries", type=int, default=1_000_000, help="entries in the CPU arm's lz4 deque (replay.py:18: 1 M)")
+    p.add_argument("--cpu-distinct", type=int, default=16384, help="distinct lz4 blobs behind those entries (the deque holds references)")
+    p.add_argument("--min-seconds", type=float, default=0.25, help="repeat the --steps block until this much device time (value) / wall clock (e2e)")
     p.add_argument("--cpu-workers", type=int, default=-1, help="--impl reference DataLoader workers (-1: all cores)")
     return p.parse_args()
 
@@ -186,7 +190,12 @@ def HotPath(rp, wl, L, A, torch, variant=0):
     return make_hotpath(rp, wl, L, A, torch, variant)
 
 
-def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
+def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None, min_seconds=0.0, reduce_max=None, stats=None):
+    """Device time of ONE block of exactly ``steps`` steps (CUDA events on the launching stream, barrier +
+    synchronize on both sides).  The block is repeated until ``min_seconds`` of device time have been measured
+    -- 20 steps of the batch-32 workload are 1.4 ms, too little for one number -- and the MEDIAN block is
+    returned; ``stats`` receives every block's seconds.  ``reduce_max(t)``: max over ranks of one block's time
+    (so every rank sees the same totals and runs the same number of blocks)."""
     step_fn = step_fn or hp.step
     hp.rp.push_dynamic()
     for _ in range(3):
@@ -201,15 +210,34 @@ def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None):
     for _ in range(warmup):
         runner()
     torch.cuda.synchronize()
-    barrier()
+    blocks, total = [], 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        runner()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    return e0.elapsed_time(e1) / 1e3
+    while True:
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            runner()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        dt = e0.elapsed_time(e1) / 1e3
+        if reduce_max is not None:
+            dt = reduce_max(dt)
+        blocks.append(dt)
+        total += dt
+        if total >= min_seconds or len(blocks) >= 2000:
+            break
+    if stats is not None:
+        stats.extend(blocks)
+    return float(np.median(blocks))
+
+
+def block_stats(blocks, units_per_block):
+    """median / p10 / p90 of the per-block rates."""
+    r = np.sort(units_per_block / np.asarray(blocks, dtype=np.float64))
+    q = lambda p: float(r[min(len(r) - 1, int(round(p * (len(r) - 1))))])
+    return {"blocks": len(r), "timed_region_s": round(float(np.sum(blocks)), 4), "rate_median": round(float(np.median(r)), 1),
+            "rate_p10": round(q(0.1), 1), "rate_p90": round(q(0.9), 1)}
 
 
 EMIT = print
@@ -250,7 +278,7 @@ def time_kernel(fn, reps, torch):
     return e0.elapsed_time(e1) / 1e3 / (rounds * INNER)
 
 
-def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True, fused=True):
+def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True, fused=True, min_seconds=0.0, stats=None):
     """The headline end-to-end number: one Trainer.step-shaped pass driven through the C ABI with
     HOST buffers.  Per step: new transitions (replay ratio 8 samples per insert) are ingested from
     page-locked host memory (a0_rb_ingest_steps_dyn: index update, H2D DMA, K2b marks + K1 in one
@@ -269,7 +297,8 @@ def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True, fu
     prefetch queue, utils.py:59-61).  Every step's H2D input copy and D2H result read, and the
     final drain, are inside the timed region either way.  ``copy_stream``: the ingest's H2D DMA
     runs on the shard's copy stream so it overlaps the previous step's kernels.
-    Wall clock around the whole loop."""
+    Wall clock around a block of ``steps`` steps; the block is repeated until ``min_seconds`` of wall clock
+    have been measured and the median block rate is returned (``stats`` receives every block's seconds)."""
     rp, L, B = hp.rp, hp.L, hp.B
     total = hp.total
     new_per_step = max(16, total // 8)
@@ -327,15 +356,96 @@ def e2e_cabi(hp, steps, warmup, torch, graph=True, depth=2, copy_stream=True, fu
 
     run(warmup)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    run(steps)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    blocks, spent = [], 0.0
+    while True:
+        t0 = time.perf_counter()
+        run(steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        blocks.append(dt)
+        spent += dt
+        if spent >= min_seconds or len(blocks) >= 2000:
+            break
     assert all(torch.isfinite(x).all() for x in loss_host) and acc[1] < rp.size and np.isfinite(acc[0])
     if fused:       # what reached the host is what the device holds
         last = (steps - 1) % depth
         assert torch.equal(loss_host[last], hp.loss.cpu()) and torch.equal(idx_host[last], hp.idx.cpu())
-    return total * steps / dt, h2d, d2h
+    if stats is not None:
+        stats.extend(blocks)
+    return total * steps / float(np.median(blocks)), h2d, d2h
+
+
+def reference_entries(count, n_step, E=16, seed=77):
+    """``count`` reference actor tuples (lz4.block.compress(concat(st, st_next)), a, r, d) (agent.py:78-81) from the
+    synthetic Atari-like stream, in the actor's order (step-major, env-minor)."""
+    from agent0_b200.synth import record_stream
+    from oracle import cpu_path as CP, reference_replay as OR_
+    s_ = record_stream(E, count // E + n_step + 2, seed=seed)
+    fr_, a_, r_, d_ = OR_.pack_nstep(s_["obs"], s_["action"], s_["reward"], s_["done"], n_step, 0.99)
+    z = CP.lz4()
+    return [(z.compress(fr_[i].tobytes()), a_[i], r_[i], d_[i]) for i in range(count)]
+
+
+def e2e_extend(wl, L, A, steps, torch, min_seconds, entries, per_step=1280, ring=200_000):
+    """The drop-in shape of a Trainer.step (trainer.py:74-104), end to end through the public API with HOST
+    inputs: ``replay.extend(list of the actor's lz4 tuples)`` -- 80 steps x 16 envs = 1280 entries, what the
+    reference actor ships per step (config.py:111-112) -- then the L batches drawn, gathered, run through K4 and
+    written back (one CUDA-graph replay), losses + indices read by the host (double-buffered).  The compressed
+    bytes cross PCIe, K6 decodes and de-duplicates on the device.  Returns sampled transitions per second,
+    inserted transitions per second, and the extend() call's own milliseconds."""
+    from agent0_b200.config import make_config
+    from agent0_b200.replay import ReplayDataset
+    cfg = make_config(wl["algo"], per=wl["per"], n_step=wl["n"], batch_size=wl["B"], replay_size=ring, double_q=wl["double"],
+                      dueling=True, num_envs=16, action_dim=A)
+    rq = ReplayDataset(cfg)                                   # reference entries: already n-step folded
+    calls = len(entries) // per_step
+    assert calls >= 4
+    rq.extend(entries[:per_step])
+    from agent0_b200.hotloop import ReplayTargetLoop
+    hp = ReplayTargetLoop(rq, wl["algo"], wl["B"], L, A, net_outputs(wl["algo"], L * wl["B"], A, torch, rq.device), n_step=1,
+                          double_q=wl["double"], per=wl["per"], discount=0.99, rng_seed=RNG_SEED)
+    rep = hp.bind_report(2)
+    hp.capture_reporting()
+    ev = [torch.cuda.Event() for _ in range(2)]
+    acc = [0.0]
+    ext_ms = []
+
+    def run(n, c0):
+        for s in range(n):
+            slot = s % 2
+            if s >= 2:
+                ev[slot].synchronize()
+                acc[0] += float(rep[slot][1][0])
+            c = (c0 + s) % calls
+            t0 = time.perf_counter()
+            rq.extend(entries[c * per_step:(c + 1) * per_step])
+            ext_ms.append((time.perf_counter() - t0) * 1e3)
+            hp.run(slot=slot)
+            ev[slot].record()
+        for s in range(max(0, n - 2), n):
+            ev[s % 2].synchronize()
+            acc[0] += float(rep[s % 2][1][0])
+
+    run(3, 1)
+    torch.cuda.synchronize()
+    ext_ms.clear()
+    blocks, spent, c0 = [], 0.0, 4
+    while True:
+        t0 = time.perf_counter()
+        run(steps, c0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        blocks.append(dt); spent += dt; c0 += steps
+        if spent >= min_seconds or len(blocks) >= 200:
+            break
+    assert np.isfinite(acc[0])
+    med = float(np.median(blocks))
+    return {"value": round(hp.total * steps / med, 1), "inserts_per_s": round(per_step * steps / med, 1),
+            "extend_ms": round(float(np.median(ext_ms)), 3), "entries_per_extend": per_step,
+            "h2d_bytes_per_step": int(sum(len(e[0]) for e in entries[:per_step]) + per_step * 24),
+            "d2h_bytes_per_step": hp.total * 12 + per_step * 12, "timing": rq.extend_timing(), "blocks": len(blocks)}
+
+
 
 
 def e2e_loop(rp, wl, L, A, steps, warmup, torch):
@@ -398,6 +508,25 @@ def e2e_loop(rp, wl, L, A, steps, warmup, torch):
     return total * steps / dt, h2d, d2h
 
 
+def shared_config(wl, L, A, ring, args):
+    """The keys BOTH arms print under ``config`` (same workload, same sizes): the driver compares them."""
+    return {"workload": wl["desc"], "learner_steps_per_step": L, "transitions_per_step_per_gpu": L * wl["B"],
+            "ring_transitions_per_gpu": ring, "actions": A, "cpu_entries": args.cpu_entries,
+            "l2": "inputs larger than L2 (random reads over the multi-GB frame ring; K3's timed launches rotate over > 700 MB "
+                  "of outputs and 20 index sets); not applicable to the CPU arm"}
+
+
+def make_shard(wl, ring, A, rank, torch, variant=0):
+    from agent0_b200.config import make_config
+    from agent0_b200.replay import ReplayDataset
+    cfg = make_config(wl["algo"], per=wl["per"], n_step=wl["n"], batch_size=wl["B"], replay_size=ring,
+                      double_q=wl["double"], dueling=True, num_envs=16, action_dim=A)
+    t0 = time.perf_counter()
+    rp = ReplayDataset(cfg, native_nstep=True, gather_variant=variant)
+    fill_shard(rp, ring, 16, 1234 + rank, torch)
+    return rp, time.perf_counter() - t0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -410,8 +539,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
-    from agent0_b200.config import make_config
-    from agent0_b200.replay import ReplayDataset
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     wl = WORKLOADS[args.workload]
     L, A = args.learner_steps, args.actions
     global RNG_SEED
@@ -420,26 +554,20 @@ def run_ours(args):
     elif RNG_SEED is not None:
         RNG_SEED += rank
     ring = args.total_ring // world if args.total_ring else args.ring
-    cfg = make_config(wl["algo"], per=wl["per"], n_step=wl["n"], batch_size=wl["B"], replay_size=ring,
-                      double_q=wl["double"], dueling=True, num_envs=16, action_dim=A)
-    t_fill = time.perf_counter()
-    rp = ReplayDataset(cfg, native_nstep=True, gather_variant=args.variant)
-    fill_shard(rp, ring, 16, 1234 + rank, torch)
-    t_fill = time.perf_counter() - t_fill
+    rp, t_fill = make_shard(wl, ring, A, rank, torch, args.variant)
     hp = HotPath(rp, wl, L, A, torch, variant=args.variant)
 
+    blocks = []
     with ClockSampler(local) as clk:
-        secs = time_graphed(hp, args.steps, args.warmup, torch, not args.no_graph, barrier)
-    t = torch.tensor([secs], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    secs = float(t.item())
+        secs = time_graphed(hp, args.steps, args.warmup, torch, not args.no_graph, barrier, min_seconds=args.min_seconds,
+                            reduce_max=reduce_max, stats=blocks)
     total = hp.total
     value = total * args.steps * world / secs
+    timing = block_stats(blocks, total * args.steps * world)
 
     # ---- roofline of the dominant kernel (K3), same launch shape, fresh indices every launch -------
     hp.draw_pool()
-    k3 = time_kernel(lambda i: hp.gather(pool=i), max(40, min(args.steps, 200)), torch)
+    k3 = time_kernel(lambda i: hp.gather(pool=i), max(200, min(args.steps, 400)), torch)
     bpt = bytes_per_transition(wl["n"])
     peaks = {}
     try:
@@ -448,88 +576,104 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bpt * total / k3 / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json"))).get(f"{total}")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json")))
+        traffic, traffic_src = tj.get(f"{total}"), tj.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": ["a0_k3_gather_tma", "a0_k3_gather_ldg", "a0_k3_gather_tma_full", "a0_k3_gather_tma_split"][args.variant],
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                 "bytes_per_launch": bpt * total, "launch_us": round(k3 * 1e6, 2), "transitions_per_launch": total}
 
     # ---- e2e through the public API -----------------------------------------------------------------
     barrier()
-    e2e_steps = max(20, args.steps // 2)
-    e2e_v, h2d, d2h = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph, depth=2, copy_stream=True)
-    barrier()
-    e2e_sync, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph, depth=1, copy_stream=False)
-    barrier()
-    e2e_eager, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=False, depth=2, copy_stream=True)
-    barrier()
-    e2e_sep, _, _ = e2e_cabi(hp, e2e_steps, 5, torch, graph=not args.no_graph, depth=2, copy_stream=True, fused=False)
-    barrier()
-    e2e_py, _, _ = e2e_loop(rp, wl, L, A, max(10, args.steps // 4), 3, torch)
-    t = torch.tensor([e2e_v, e2e_py, e2e_eager, e2e_sync, e2e_sep], device="cuda", dtype=torch.float64)
+    e2e_blocks = []
+    e2e_v, h2d, d2h = e2e_cabi(hp, args.steps, 5, torch, graph=not args.no_graph, depth=2, copy_stream=True,
+                               min_seconds=args.min_seconds, stats=e2e_blocks)
+    e2e_timing = block_stats(e2e_blocks, total * args.steps)
+    side = [0.0, 0.0, 0.0, 0.0]
+    if not args.no_extra:
+        short = min(args.min_seconds, 0.1)
+        barrier()
+        side[0], _, _ = e2e_cabi(hp, args.steps, 5, torch, graph=not args.no_graph, depth=1, copy_stream=False, min_seconds=short)
+        barrier()
+        side[1], _, _ = e2e_cabi(hp, args.steps, 5, torch, graph=False, depth=2, copy_stream=True, min_seconds=short)
+        barrier()
+        side[2], _, _ = e2e_cabi(hp, args.steps, 5, torch, graph=not args.no_graph, depth=2, copy_stream=True, fused=False, min_seconds=short)
+        barrier()
+        side[3], _, _ = e2e_loop(rp, wl, L, A, max(10, args.steps), 3, torch)
+    t = torch.tensor([e2e_v] + side, device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    e2e_v, e2e_py, e2e_eager, e2e_sync, e2e_sep = (float(x) for x in t.tolist())
+    e2e_v, e2e_sync, e2e_eager, e2e_sep, e2e_py = (float(x) for x in t.tolist())
 
-    extra = {}
+    extra, configs, ext = {}, [], None
     if world > 1:
-        # the learner's only exchange step: one SUM all-reduce of the flat gradient bucket
-        # (C51 dueling: 1 814 943 fp32 parameters).  Reported beside the replay+target numbers, not
-        # inside them: with the CNN excluded there is no backward pass for it to overlap with.
-        bucket = torch.zeros(1_814_943, dtype=torch.float32, device="cuda")
-        for _ in range(5):
-            dist.all_reduce(bucket)
-        torch.cuda.synchronize(); barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(50):
-            dist.all_reduce(bucket)
-        e1.record(); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        us = float(t.item())
-        extra["grad_allreduce"] = {"bytes": bucket.numel() * 4, "us_per_call": round(us, 2),
-                                   "bus_GBps": round(2 * (world - 1) / world * bucket.numel() * 4 / (us * 1e-6) / 1e9, 1),
-                                   "per_step_us_if_not_overlapped": round(us * L, 1)}
+        extra["grad_allreduce"] = grad_allreduce_probe(torch, dist, world, barrier, L)
     if not args.no_extra and rank == 0 and world == 1:
-        extra = extras(rp, args, torch, peak)
+        entries = reference_entries(5 * 1280, wl["n"])
+        ext = e2e_extend(wl, L, A, max(4, min(args.steps, 20)), torch, args.min_seconds, entries)
+        configs.append({"workload": args.workload, "desc": wl["desc"], "value": round(value, 1),
+                        "ms_per_step": round(secs / args.steps * 1e3, 5), "k3_frac": roofline["frac"], "ring": ring})
+        extra = extras(rp, args, torch, peak, configs, entries)
+        del rp, hp
+        torch.cuda.empty_cache()
+        extras_other_shards(args, torch, peak, configs)
+    learner = None
+    if not args.no_extra and not args.no_learner:
+        try:
+            learner = learner_scaling(args, torch, dist, world, rank, barrier, reduce_max, A)
+        except Exception as e:      # measurement only: the replay+target line must still be printed
+            learner = {"error": repr(e)[:400]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(wl, L, A, args, workers=0)
 
     if rank == 0:
+        e2e = {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "timing": e2e_timing,
+               "path": "agent0_b200 public API over the C ABI (ReplayDataset.append_steps + hotloop.ReplayTargetLoop): ingest from pinned host buffers "
+                       "(H2D DMA on the shard's copy stream; marks + append + top/beta publication in one launch) + one CUDA-graph "
+                       "replay of the C-ABI launches per step; losses and indices stored by the K2b launch into double-buffered "
+                       "mapped pinned host memory (a0_pt_update_report), the host reads step s-1's result while step s runs "
+                       "(final drain inside the timed region)"}
+        if not args.no_extra:
+            e2e.update({"separate_launches_value": round(e2e_sep, 1),
+                        "separate_launches_path": "same loop with a0_rb_set_dynamic as its own launch and two device-to-host copies queued behind the graph",
+                        "sync_every_step_value": round(e2e_sync, 1),
+                        "sync_every_step_path": "same, but the host waits for each step's losses before starting the next (depth 1)",
+                        "cabi_eager_value": round(e2e_eager, 1),
+                        "python_api_value": round(e2e_py, 1),
+                        "python_api_path": "ReplayDataset.append_steps/sample/update_priority + agent0_b200.losses wrappers"})
+        if ext is not None:
+            e2e.update({"extend_api_value": ext["value"], "extend_api_inserts_per_s": ext["inserts_per_s"],
+                        "extend_api_extend_ms": ext["extend_ms"], "extend_api_h2d_bytes_per_step": ext["h2d_bytes_per_step"],
+                        "extend_api_d2h_bytes_per_step": ext["d2h_bytes_per_step"], "extend_api_phase_us": ext["timing"],
+                        "extend_api_path": "the drop-in shape of Trainer.step: ReplayDataset.extend(1280 reference tuples = lz4 blocks of concat(st, st_next), "
+                                           "agent.py:78-81) -- compressed bytes over PCIe, LZ4 decode + de-duplication on the device (K6), K2b marks + K1 -- "
+                                           "then the same CUDA-graph replay of the L batches and the double-buffered result read-back; 640 sampled per "
+                                           "1280 inserted transitions at batch 32, as the reference's own step does"})
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 frames / f32 targets / f64 n-step returns",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "learner_steps_per_step": L, "transitions_per_step_per_gpu": total,
-                       "ring_transitions_per_gpu": ring, "frame_ring_GB_per_gpu": round(rp.index.NF * F_BYTES / 1e9, 2),
-                       "actions": A, "cuda_graph": not args.no_graph,
-                       "uniforms": "torch uniform_ launch" if RNG_SEED is None else "Philox4x32-10 inside K2a (a0_pt_sample_rng)", "sharding": f"{world} independent shards, no data-path collective",
-                       "l2_note": "inputs larger than L2: gathers are random reads over the multi-GB frame ring",
-                       "fill_seconds": round(t_fill, 1)},
+            "config": shared_config(wl, L, A, ring, args),
+            "timing": dict(timing, note=f"the block of --steps {args.steps} steps was repeated until {args.min_seconds} s of device time; value = median block"),
+            "timed_region_s": timing["timed_region_s"],
+            "run": {"frame_ring_GB_per_gpu": round((ring * 1.0625 + 65536) * F_BYTES / 1e9, 2), "cuda_graph": not args.no_graph,
+                    "uniforms": "torch uniform_ launch" if RNG_SEED is None else "Philox4x32-10 inside K2a (a0_pt_sample_rng)",
+                    "sharding": f"{world} independent shards, no data-path collective", "fill_seconds": round(t_fill, 1)},
             "clocks": clk.summary(),
-            "e2e": {"value": round(e2e_v, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "agent0_b200 public API over the C ABI (ReplayDataset.append_steps + hotloop.ReplayTargetLoop): ingest from pinned host buffers "
-                            "(H2D DMA on the shard's copy stream; marks + append + top/beta publication in one launch) + one CUDA-graph "
-                            "replay of the C-ABI launches per step; losses and indices stored by the K2b launch into double-buffered "
-                            "mapped pinned host memory (a0_pt_update_report), the host reads step s-1's result while step s runs "
-                            "(final drain inside the timed region)",
-                    "separate_launches_value": round(e2e_sep, 1),
-                    "separate_launches_path": "same loop with a0_rb_set_dynamic as its own launch and two device-to-host copies queued behind the graph",
-                    "sync_every_step_value": round(e2e_sync, 1),
-                    "sync_every_step_path": "same, but the host waits for each step's losses before starting the next (depth 1)",
-                    "cabi_eager_value": round(e2e_eager, 1),
-                    "python_api_value": round(e2e_py, 1),
-                    "python_api_path": "ReplayDataset.append_steps/sample/update_priority + agent0_b200.losses wrappers"},
-            "gpu_launches": hp.launches_per_step * args.steps,
+            "e2e": e2e,
+            "gpu_launches": hp_launches(wl, L) * args.steps * len(blocks),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "configs": configs,
+            "learner_scaling": learner,
             "extra": extra,
         }
         EMIT(json.dumps(line))
@@ -538,28 +682,134 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def extras(rp, args, torch, peak):
-    """Secondary numbers: the other BASELINE configs on the same shard, and K3 GB/s by launch size."""
+def learner_scaling(args, torch, dist, world, rank, barrier, reduce_max, A, algo="c51", B=512, L=20, ring=200_000):
+    """configs[4]: sharded PER replay + DATA-PARALLEL LEARNER, the gradient all-reduce INSIDE the timed region.
+    One learner update = draw + gather (K2a, K3-f32) -> Nature-CNN forward (online, target, double-Q selection) -> K4 ->
+    backward from the kernel's gradient -> NCCL all-reduce(SUM) of the flat gradient buffer, issued bucket by bucket
+    from backward hooks (dist.OverlappedGradBucket: 6.9 MB under the convolution backward, 0.3 MB exposed) -> Adam ->
+    K2b; L = 20 updates per Trainer.learn() replayed as one CUDA graph, per-GPU batch fixed (weak scaling).  The same
+    loop is timed a second time with the collectives switched off: the difference is the exposed all-reduce time."""
+    from agent0_b200.config import make_config
+    from agent0_b200.synth import fill_shard_synthetic
+    from agent0_b200.trainer import Trainer
+    pg = dist.group.WORLD if world > 1 else None
+    out = {"algo": algo, "batch_per_gpu": B, "global_batch": B * world, "updates_per_learn": L, "n_gpus": world,
+           "ring_per_gpu": ring}
+
+    def build(exchange, graph):
+        cfg = make_config(algo, per=True, n_step=3, batch_size=B, double_q=True, dueling=True, replay_size=ring, num_envs=16,
+                          action_dim=A)
+        cfg.learner.learner_steps = L
+        cfg.learner.target_update_freq = 500
+        tr = Trainer(cfg, process_group=pg, native_nstep=True, graph=graph, fused_input=True, sampler_seed=4242 + rank)
+        if world > 1:
+            tr.learner.bucket.enabled = exchange
+        fill_shard_synthetic(tr.replay, ring, 16, 77 + rank)
+        return tr
+
+    def timed(tr, calls=4, blocks=3):
+        for _ in range(3):
+            tr.learn()
+        torch.cuda.synchronize()
+        ts = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(blocks):
+            barrier()
+            e0.record()
+            for _ in range(calls):
+                tr.learn()
+            e1.record()
+            torch.cuda.synchronize()
+            barrier()
+            ts.append(reduce_max(e0.elapsed_time(e1) / 1e3))
+        return float(np.median(ts)) / (calls * L)
+
+    graph = not args.no_graph
+    try:
+        tr = build(True, graph)
+        sec = timed(tr)
+    except Exception as e:
+        if not graph:
+            raise
+        out["graph_capture_error"] = repr(e)[:300]
+        graph = False
+        torch.cuda.synchronize()
+        tr = build(True, False)
+        sec = timed(tr)
+    out.update({"cuda_graph": graph, "ms_per_update": round(sec * 1e3, 4), "value": round(B * world / sec, 1), "unit": "transitions/s through the learner (CNN included)"})
+    if world > 1:
+        bk = tr.learner.bucket
+        out["allreduce_buckets_bytes"] = [int(hi - lo) * 4 for _, _, lo, hi in bk.buckets]
+        del tr
+        torch.cuda.empty_cache()
+        tr2 = build(False, graph)
+        sec0 = timed(tr2)
+        out["ms_per_update_without_allreduce"] = round(sec0 * 1e3, 4)
+        out["exposed_allreduce_us_per_update"] = round((sec - sec0) * 1e6, 2)
+        del tr2
+    else:
+        del tr
+    torch.cuda.empty_cache()
+    return out
+
+
+def hp_launches(wl, L):
+    return 2 + L + (1 if wl["per"] else 0)
+
+
+def grad_allreduce_probe(torch, dist, world, barrier, L):
+    """The learner's only exchange step timed alone: one SUM all-reduce of the flat gradient bucket
+    (C51 dueling: 1 814 943 fp32 parameters).  The learner-step scaling with the all-reduce INSIDE the timed
+    region is the learner_* workloads' job (--workload learner_c51_b512)."""
+    bucket = torch.zeros(1_814_943, dtype=torch.float32, device="cuda")
+    for _ in range(5):
+        dist.all_reduce(bucket)
+    torch.cuda.synchronize(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        dist.all_reduce(bucket)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    us = float(t.item())
+    return {"bytes": bucket.numel() * 4, "us_per_call": round(us, 2),
+            "bus_GBps": round(2 * (world - 1) / world * bucket.numel() * 4 / (us * 1e-6) / 1e9, 1),
+            "per_step_us_if_not_overlapped": round(us * L, 1)}
+
+
+def time_workload(rp, name, args, torch, peak, L, A):
+    """One BASELINE config on an existing shard: the step as a graph (median of blocks), K3 roofline, K4/K2 launch times."""
+    wl = WORKLOADS[name]
+    hp = HotPath(rp, wl, L, A, torch, variant=args.variant)
+    bl = []
+    secs = time_graphed(hp, 20, 5, torch, not args.no_graph, lambda: None, min_seconds=min(args.min_seconds, 0.15), stats=bl)
+    secs_fused = time_graphed(hp, 20, 5, torch, not args.no_graph, lambda: None, step_fn=hp.step_fused_k4, min_seconds=0.02)
+    hp.draw_pool()
+    k4 = time_kernel(lambda i: hp.loss_k(i % L), 100, torch)
+    k3 = time_kernel(lambda i: hp.gather(pool=i), 60, torch)
+    k2a = time_kernel(lambda i: hp.sample(), 60, torch)
+    k2b = time_kernel(lambda i: hp.update(), 60, torch) if wl["per"] else 0.0
+    gb = bytes_per_transition(wl["n"]) * hp.total / k3 / 1e9
+    full = {"transitions_per_s": round(hp.total * 20 / secs, 1), "ms_per_step": round(secs / 20 * 1e3, 4),
+            "transitions_per_s_one_k4_launch_for_all_batches": round(hp.total * 20 / secs_fused, 1),
+            "k4_us_per_batch": round(k4 * 1e6, 2), "k3_us": round(k3 * 1e6, 2), "k3_GBps": round(gb, 1),
+            "k2a_us": round(k2a * 1e6, 2), "k2b_us": round(k2b * 1e6, 2), "desc": wl["desc"], "blocks": len(bl)}
+    compact = {"workload": name, "desc": wl["desc"], "value": full["transitions_per_s"], "ms_per_step": full["ms_per_step"],
+               "k3_frac": round(gb / peak, 4), "k4_us": full["k4_us_per_batch"], "ring": rp.size}
+    del hp
+    return full, compact
+
+
+def extras(rp, args, torch, peak, configs, entries):
+    """Secondary numbers on the headline shard: the batch-512 configs that share it, K3 GB/s by launch size, the fused
+    f32 gather, K1 and K6 as kernels."""
     out = {"workloads": {}, "k3_sweep": []}
     L, A = args.learner_steps, args.actions
-    for name in ("c51_b32", "c51_b512", "qr_b512", "iqn_b512", "fqf_b512", "mdqn_b512", "dqn_b32_uniform"):
-        wl = WORKLOADS[name]
-        if not wl["per"]:
-            continue        # the shard was built prioritized; the uniform config is a parity-test case
-        hp = HotPath(rp, wl, L, A, torch, variant=args.variant)
-        secs = time_graphed(hp, 50, 5, torch, not args.no_graph, lambda: None)
-        secs_fused = time_graphed(hp, 50, 5, torch, not args.no_graph, lambda: None, step_fn=hp.step_fused_k4)
-        hp.draw_pool()
-        k4 = time_kernel(lambda i: hp.loss_k(i % L), 60, torch)
-        k3 = time_kernel(lambda i: hp.gather(pool=i), 40, torch)
-        k2a = time_kernel(lambda i: hp.sample(), 40, torch)
-        k2b = time_kernel(lambda i: hp.update(), 40, torch)
-        out["workloads"][name] = {"transitions_per_s": round(hp.total * 50 / secs, 1), "ms_per_step": round(secs / 50 * 1e3, 4),
-                                  "transitions_per_s_one_k4_launch_for_all_batches": round(hp.total * 50 / secs_fused, 1),
-                                  "k4_us_per_batch": round(k4 * 1e6, 2), "k3_us": round(k3 * 1e6, 2),
-                                  "k3_GBps": round(bytes_per_transition(wl["n"]) * hp.total / k3 / 1e9, 1),
-                                  "k2a_us": round(k2a * 1e6, 2), "k2b_us": round(k2b * 1e6, 2), "desc": wl["desc"]}
-        del hp
+    for name in ("c51_b512", "qr_b512", "iqn_b512"):
+        full, compact = time_workload(rp, name, args, torch, peak, L, A)
+        out["workloads"][name] = full
+        configs.append(compact)
     # K3 with the learner's input conversion fused in (a0_rb_gather_f32) against the three-pass
     # alternative it replaces: K3 to u8, then torch's .float() and .div(255) (agent.py:129-135)
     out["k3_f32"] = []
@@ -590,28 +840,46 @@ def extras(rp, args, torch, peak):
                               "fused_GBps": round(by * count / t_f / 1e9, 1), "frac_of_measured_peak": round(by * count / t_f / 1e9 / peak, 4),
                               "bytes_per_transition": by})
         del hp, obs, nxt
-    # the drop-in ingest: ReplayDataset.extend with what the reference actor ships per Trainer.step --
-    # 80 steps x 16 envs = 1280 lz4 blocks of concat(st, st_next) (agent.py:78-81, config.py:111-112)
+    # K1 as a kernel: a bulk append of 65 536 staged frames (device-resident staging, as the shard fill does):
+    # F read + F written per frame
+    try:
+        nfr = 65536
+        stage = torch.randint(0, 256, (nfr, F_BYTES), dtype=torch.uint8, device=rp.device)
+        pos = (torch.randperm(rp.index.NF, device=rp.device)[:nfr]).to(torch.int32).contiguous()
+
+        def k1(i):
+            LB.check(lib.a0_rb_append(rp.h, stage.data_ptr(), pos.data_ptr(), nfr, None, 0, LB.stream_ptr(rp.device)), "a0_rb_append")
+        t1 = time_kernel(k1, 40, torch)
+        out["k1_roofline"] = {"kernel": "a0_k1_append", "frames_per_launch": nfr, "bytes_per_launch": 2 * nfr * F_BYTES,
+                              "launch_us": round(t1 * 1e6, 2), "achieved_GBps": round(2 * nfr * F_BYTES / t1 / 1e9, 1),
+                              "frac_of_measured_peak": round(2 * nfr * F_BYTES / t1 / 1e9 / peak, 4),
+                              "note": "scattered ring slots; the staged frames were just read by the previous launch, so part of the read side hits L2"}
+        del stage, pos
+    except Exception as e:      # measurement only
+        out["k1_roofline"] = {"error": repr(e)}
+    # the drop-in ingest alone: ReplayDataset.extend with what the reference actor ships per Trainer.step
     try:
         from agent0_b200.config import make_config
         from agent0_b200.replay import ReplayDataset
-        from agent0_b200.synth import record_stream
-        from oracle import cpu_path as CP, reference_replay as OR_
-        s_ = record_stream(16, 4 * 80 + 2, seed=77)
-        fr_, a_, r_, d_ = OR_.pack_nstep(s_["obs"], s_["action"], s_["reward"], s_["done"], 3, 0.99)
-        z = CP.lz4()
-        tup = [(z.compress(fr_[i].tobytes()), a_[i], r_[i], d_[i]) for i in range(4 * 1280)]
         rq = ReplayDataset(make_config("c51", per=True, n_step=3, batch_size=32, replay_size=100_000, num_envs=16))
-        rq.extend(tup[:1280])
-        ms = []
-        for i in (1, 2, 3):                      # the first timed call still pays one-off allocations
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            rq.extend(tup[i * 1280:(i + 1) * 1280])
-            torch.cuda.synchronize()
-            ms.append(round((time.perf_counter() - t0) * 1e3, 2))
-        out["compat_extend"] = {"transitions": 1280, "ms": min(ms), "ms_all_calls": ms,
-                                "note": "lz4 decode + native content de-duplication + staged H2D + K2b marks + K1, one call"}
+        rq.extend(entries[:1280])
+        ms, tm = [], None
+        for rep_ in range(3):
+            for i in (1, 2, 3, 4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                rq.extend(entries[i * 1280:(i + 1) * 1280])
+                torch.cuda.synchronize()
+                ms.append(round((time.perf_counter() - t0) * 1e3, 3))
+                tm = rq.extend_timing()
+        blob = float(np.mean([len(e[0]) for e in entries]))
+        out["compat_extend"] = {"transitions": 1280, "ms": float(np.median(ms)), "ms_min": min(ms), "ms_all_calls": ms, "mean_blob_bytes": round(blob, 1),
+                                "phase_us_last_call": tm,
+                                "k6_decode_label": {"device_us": tm["device_decode_label_us"], "decoded_bytes": 1280 * 8 * F_BYTES,
+                                                    "decoded_GBps": round(1280 * 8 * F_BYTES / (tm["device_decode_label_us"] * 1e-6) / 1e9, 1),
+                                                    "bound": "one warp's dependent instruction chain per entry (LZ4 sequences are serial); not HBM"},
+                                "note": "one a0_ex_extend call: compressed bytes staged + copied, K6 LZ4 decode + labels on the device, 8 label bytes "
+                                        "per entry read back, host resolve + plan, K2b marks + K1 from the decoded scratch"}
         del rq
     except Exception as e:          # measurement only
         out["compat_extend"] = {"error": repr(e)}
@@ -624,107 +892,142 @@ def extras(rp, args, torch, peak):
             gb = bytes_per_transition(3) * count / dt / 1e9
             out["k3_sweep"].append({"transitions": count, "variant": ["tma_ring4", "ldg", "tma_full8", "tma_split2"][variant], "us": round(dt * 1e6, 2),
                                     "GBps": round(gb, 1), "frac_of_measured_peak": round(gb / peak, 4)})
+    del hp
     return out
 
 
+def extras_other_shards(args, torch, peak, configs):
+    """The configs that need their own shard: configs[3] (FQF, M-DQN on a 2 M-transition shard) and configs[0]
+    (DQN, uniform replay, n_step = 1) -- built after the headline shard has been released."""
+    L, A = args.learner_steps, args.actions
+    for names, ring in ((("fqf_b512", "mdqn_b512"), 2_000_000), (("dqn_b32_uniform",), 1_000_000)):
+        try:
+            rp, _ = make_shard(WORKLOADS[names[0]], ring, A, 0, torch, args.variant)
+            for name in names:
+                _, compact = time_workload(rp, name, args, torch, peak, L, A)
+                configs.append(compact)
+            del rp
+            torch.cuda.empty_cache()
+        except Exception as e:      # measurement only
+            configs.append({"workload": names[0], "error": repr(e)})
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_baseline(wl, L, A, args, workers):
-    """The reference's host pipeline (oracle/cpu_path.py) on a bounded sample of the same workload."""
-    import torch
+def cpu_entries_for(wl, args):
+    """The distinct lz4 tuples behind the CPU arm's deque (Actor.sample's packing, agent.py:64-81)."""
     from agent0_b200.synth import record_stream
     from oracle import cpu_path as CP
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(1 if workers == 0 else cores)
-    B, algo = wl["B"], wl["algo"]
     E = 16
-    T = max(8, args.cpu_entries // E)
-    s = record_stream(E, T, seed=1234)
+    s = record_stream(E, max(8, args.cpu_distinct // E) + wl["n"], seed=1234)
+    tmp = CP.CpuReplay(args.cpu_distinct + 64, False)
+    CP.fill_replay(tmp, s, wl["n"])
+    return list(tmp.data)
+
+
+def cpu_port(wl, L, A, args, entries):
+    """oracle/cpu_path.py: the reference's pipeline restated, on a deque of args.cpu_entries entries."""
+    import torch
+    from oracle import cpu_path as CP
+    B, algo = wl["B"], wl["algo"]
     rp = CP.CpuReplay(1_000_000, wl["per"])      # 1 M-slot priority vector as in the reference
-    n_entries = CP.fill_replay(rp, s, wl["n"])
-    fetch, loader = CP.make_fetcher(rp, B, workers)
+    rep = -(-args.cpu_entries // len(entries))
+    rp.extend((entries * rep)[:args.cpu_entries])
     o_all = net_outputs(algo, L * B, A, torch, "cpu")
     extra = dict(atoms=o_all.pop("atoms")) if algo == "c51" else {}
     if not (wl["double"] or algo in ("iqn", "fqf")):
         o_all["qsel"] = None
-
-    def outs(it):
-        sl = slice(it * B, (it + 1) * B)
-        return {k: (v[sl].clone() if v is not None else None) for k, v in o_all.items()}
+    outs = lambda it: {k: (v[it * B:(it + 1) * B].clone() if v is not None else None) for k, v in o_all.items()}
     gam = 0.99 ** wl["n"]
-    step = lambda: CP.trainer_step(rp, fetch, outs, algo, L, gam, extra=extra)
-    # calibrate to roughly 10-20 s of CPU work
+    return rp, (lambda fetch: CP.trainer_step(rp, fetch, outs, algo, L, gam, extra=extra))
+
+
+def cpu_baseline(wl, L, A, args, workers):
+    """The reference's host pipeline (oracle/cpu_path.py, single thread) on a bounded sample of the same workload."""
+    import torch
+    from oracle import cpu_path as CP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(1)
+    entries = cpu_entries_for(wl, args)
+    rp, mk = cpu_port(wl, L, A, args, entries)
+    fetch, loader = CP.make_fetcher(rp, wl["B"], 0)
+    step = lambda: mk(fetch)
     t0 = time.perf_counter(); step(); one = time.perf_counter() - t0
-    steps = int(max(3, min(400, 12.0 / max(one, 1e-3))))
+    steps = int(max(3, min(400, 12.0 / max(one, 1e-3))))      # ~12 s of CPU work
     n, dt = CP.time_steps(step, steps, 1)
-    del loader
-    return {"value": round(n / dt, 1), "unit": UNIT, "cores": 1 if workers == 0 else min(cores, workers) + 1,
-            "kind": "port", "host_cores_available": cores,
-            "sample": f"{steps} Trainer.step loops x {L} batches x {B} on a {n_entries}-entry lz4 deque "
-                      f"({'single thread' if workers == 0 else str(workers) + ' DataLoader workers'}; "
-                      f"the reference at 1 M entries pays a slower deque[idx])"}
+    return {"value": round(n / dt, 1), "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": cores,
+            "sample": f"{steps} Trainer.step loops x {L} batches x {wl['B']}, single thread, in-process fetch, on a "
+                      f"{len(rp.data)}-entry lz4 deque ({len(entries)} distinct blobs) + torch CPU loss (1 intra-op thread); "
+                      f"oracle/cpu_path.py; the all-cores run of the unmodified reference is `bench.py --impl reference`"}
 
 
 def run_reference(args):
+    """The reference arm: the UNMODIFIED reference (oracle/_ref, see oracle/ref_arm.py) through its own
+    Trainer.step -- ReplayDataset, DataLoaderX(num_workers=2, pin_memory) + DataPrefetcher, learner.train, update_priority --
+    with all host threads torch wants; the restated port (oracle/cpu_path.py) is timed beside it as a cross-check, and is
+    the arm itself for the workloads whose networks the table stub does not cover (IQN, FQF) or when oracle/_ref is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
     L, A = args.learner_steps, args.actions
     cores = os.cpu_count() or 1
-    workers = cores if args.cpu_workers < 0 else args.cpu_workers
-    workers = max(1, min(workers, 64))
     import torch
-    from agent0_b200.synth import record_stream
     from oracle import cpu_path as CP
+    from oracle import ref_arm as RA
     B, algo = wl["B"], wl["algo"]
-    E = 16
-    s = record_stream(E, max(8, args.cpu_entries // E), seed=1234)
-    rp = CP.CpuReplay(1_000_000, wl["per"])
-    n_entries = CP.fill_replay(rp, s, wl["n"])
-    o_all = net_outputs(algo, L * B, A, torch, "cpu")
-    extra = dict(atoms=o_all.pop("atoms")) if algo == "c51" else {}
-    if not (wl["double"] or algo in ("iqn", "fqf")):
-        o_all["qsel"] = None
-    outs = lambda it: {k: (v[it * B:(it + 1) * B].clone() if v is not None else None) for k, v in o_all.items()}
-    # The reference ships num_workers=2 and torch's default intra-op threads (= cores).  At batch 32
-    # the worker IPC and thread fan-out can cost more than they buy, so the arm calibrates over
-    # {in-process, 2 workers (the reference's setting), all cores} x {1, all} intra-op threads on
-    # a few steps and times the fastest: the baseline is the best the host path can do here.
-    cands = [(w, t) for w in sorted({0, 2, workers}) for t in sorted({1, cores})]
-    if args.cpu_workers >= 0:
-        cands = [(args.cpu_workers, t) for t in sorted({1, cores})]
-    best, tried = None, []
-    for w, t in cands:
-        torch.set_num_threads(t)
-        fetch, loader = CP.make_fetcher(rp, B, w)
-        step = lambda: CP.trainer_step(rp, fetch, outs, algo, L, 0.99 ** wl["n"], extra=extra)
-        n, dt = CP.time_steps(step, 3, 1)
-        tried.append({"workers": w, "intra_op_threads": t, "transitions_per_s": round(n / dt, 1)})
-        if best is None or n / dt > best[0]:
-            best = (n / dt, w, t)
-        del fetch, loader, step
-    _, workers, threads = best
-    torch.set_num_threads(threads)
-    fetch, loader = CP.make_fetcher(rp, B, workers)
-    step = lambda: CP.trainer_step(rp, fetch, outs, algo, L, 0.99 ** wl["n"], extra=extra)
+    entries = cpu_entries_for(wl, args)
     steps = max(1, min(args.steps, 200))
-    n, dt = CP.time_steps(step, steps, max(1, min(args.warmup, 5)))
-    v = round(n / dt, 1)
-    used = max(threads, workers + 1)
-    sample = (f"{steps} Trainer.step loops x {L} batches x {B} through the reference's DataLoader pump "
-              f"({'in-process, num_workers=0' if workers == 0 else str(workers) + ' worker processes'}) on a {n_entries}-entry "
-              f"lz4 deque + torch CPU loss ({threads} intra-op threads); fastest of {tried}")
-    cores_used = used
+    warm = max(1, min(args.warmup, 5))
+    # ---- the port, all intra-op threads, in-process fetch and the reference's 2 workers: cross-check ----------------
+    torch.set_num_threads(cores)
+    rp, mk = cpu_port(wl, L, A, args, entries)
+    port = {}
+    for w in (0, 2):
+        fetch, loader = CP.make_fetcher(rp, B, w)
+        n, dt = CP.time_steps(lambda: mk(fetch), max(2, min(steps, 5)), 1)
+        port[f"workers_{w}"] = round(n / dt, 1)
+        del fetch, loader
+    del rp, mk
+    kind, v, ms, sample, used = "port", None, None, None, None
+    if RA.available() and algo in RA.SUPPORTED:
+        o = net_outputs(algo, L * B, A, torch, "cpu")
+        if not wl["double"]:
+            o["qsel"] = None
+        tr = RA.make_trainer(algo, wl["per"], wl["n"], wl["double"], B, L, A, o, replay_size=1_000_000)
+        n_entries = RA.fill(tr, entries, args.cpu_entries)
+        for _ in range(warm):
+            RA.step(tr)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            RA.step(tr)
+        dt = time.perf_counter() - t0
+        v, ms, kind = round(L * B * steps / dt, 1), dt / steps * 1e3, "reference"
+        used = min(cores, 2 + 1 + 1 + torch.get_num_threads())
+        sample = (f"{steps} calls of the unmodified reference's Trainer.step (oracle/_ref, trainer.py:74-119): {L} x [DataLoaderX("
+                  f"shuffle, num_workers=2, pin_memory={torch.cuda.is_available()}) + DataPrefetcher fetch of {B} entries from a {n_entries}-entry "
+                  f"lz4 deque ({len(entries)} distinct blobs), .float(), IS weights over the 1 M-slot priority vector, {algo.upper()}Learner.train "
+                  f"with table-lookup networks (CNN excluded on both arms), update_priority]; torch intra-op threads = {torch.get_num_threads()}; "
+                  f"port cross-check (oracle/cpu_path.py, same deque): {port} transitions/s")
+    else:
+        best = max(port, key=port.get)
+        w = int(best.split("_")[1])
+        rp, mk = cpu_port(wl, L, A, args, entries)
+        fetch, loader = CP.make_fetcher(rp, B, w)
+        n, dt = CP.time_steps(lambda: mk(fetch), steps, warm)
+        v, ms = round(n / dt, 1), dt / steps * 1e3
+        used = min(cores, max(torch.get_num_threads(), w + 1))
+        why = "oracle/_ref is absent" if not RA.available() else f"the table-network stub does not cover {algo}"
+        sample = (f"{steps} Trainer.step loops x {L} batches x {B} through the restated pipeline (oracle/cpu_path.py; {why}) with "
+                  f"{'in-process fetch' if w == 0 else str(w) + ' DataLoader workers'} on a {len(rp.data)}-entry lz4 deque; calibration {port}")
     EMIT(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8 frames / f32 targets / f64 n-step returns", "data": "synthetic",
-        "config": {"workload": wl["desc"], "learner_steps_per_step": L, "transitions_per_step_per_gpu": L * B},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores_used, "host_cores_available": cores, "kind": "port",
-                         "sample": sample},
+        "config": shared_config(wl, L, A, args.total_ring // max(1, args.gpus) if args.total_ring else args.ring, args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "host_cores_available": cores, "kind": kind, "sample": sample,
+                         "port_crosscheck": port},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
-    del loader
 
 
 def _json_only_stdout():

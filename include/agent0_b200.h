@@ -92,6 +92,11 @@ const char* a0_last_error(void);
  * the index list, recomputes its chunk in shared memory; the last CTA finishes the top levels); 0
  * falls back to the cluster schedules selected by A0_OPT_K2B_BULK_MIN.  Same tree either way.       */
 #define A0_OPT_K2B_CHUNKS 8
+/* A0_OPT_QH_SORTED (default 1; A0_QH_SORTED in the environment): a0_loss_quantile with more than 64 target
+ * and more than 64 online quantiles and no FQF fraction term (QR-200) evaluates the pair sums in
+ * O(N log N) from the sorted targets (float64 prefix sums); 0 forces the O(N^2) pair loop.  The two agree to
+ * ~1e-6 relative (different summation order), both within the 1e-5 contract.                          */
+#define A0_OPT_QH_SORTED 10
 /* A0_OPT_MAIL_TIMEOUT_US (default 2 000 000; A0_MAIL_TIMEOUT_US in the environment): how long a gather CTA of
  * a0_rb_sample_gather polls its mailbox word before it gives up.  The paired sampler posts every word
  * within microseconds; a CTA that still has nothing after this long was launched without its sampler

@@ -20,3 +20,12 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return load
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Worst relative errors seen by the GPU parity tests (tests/parity.py) -> profiles/parity_r02.json."""
+    try:
+        from tests import parity
+        parity.dump(ROOT)
+    except Exception:
+        pass

@@ -11,8 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from agent0_b200.dist import (FlatGradBucket, adam_eps, global_priority_stats, local_streams, shard_capacity,
-                              shard_of_stream)
+from agent0_b200.dist import (FlatGradBucket, OverlappedGradBucket, adam_eps, global_batch_is_weights,
+                              global_priority_stats, local_streams, shard_capacity, shard_of_stream)
 
 WORLD = 2
 
@@ -64,6 +64,25 @@ def _worker(rank, port, out):
         for p in net.parameters():                       # gradients are still views of the flat buffer
             assert p.grad.data_ptr() >= bucket.flat.data_ptr()
         flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        # the same three updates with the gradient exchange issued from backward hooks, bucket by bucket
+        net2 = _net(7)
+        ob = OverlappedGradBucket(list(net2.parameters()), dist.group.WORLD, n_buckets=2, min_bucket_elems=64, split_frac=0.8)
+        assert len(ob.buckets) == 2 and ob.buckets[0][3] == ob.flat.numel() and ob.buckets[-1][2] == 0
+        opt2 = torch.optim.Adam(net2.parameters(), 1e-3, eps=adam_eps(B, WORLD))
+        for it in range(3):
+            _update(net2, ob, opt2, *_batch(100 * it + rank, B))
+            assert not ob._handles and all(n == 0 for n in ob._left)
+        flat2 = torch.cat([p.detach().reshape(-1) for p in net2.parameters()])
+        ob.enabled = False                                  # the switch bench.py uses to time the step without the exchange
+        g0 = ob.flat.clone()
+        _update(net2, ob, opt2, *_batch(999 + rank, B))
+        local_only = ob.flat.clone()
+        # IS weights normalised over the global batch: one MAX all-reduce of L floats
+        gen = torch.Generator().manual_seed(40 + rank)
+        prio = torch.rand(3 * B, generator=gen) + 0.05
+        s_r = torch.tensor(10.0 + 5 * rank)
+        w_glob = global_batch_is_weights(prio, s_r, 0.6, B, dist.group.WORLD)
+        w_loc = global_batch_is_weights(prio, s_r, 0.6, B, None)
         # sharding: every stream is owned by exactly one rank; the shards' sampleable counts add up
         from agent0_b200.ring_index import NativeRingIndex
         E, T, n = 6, 40, 3
@@ -93,7 +112,9 @@ def _worker(rank, port, out):
         sent = broadcast_model(model, src=0, process_group=dist.group.WORLD)
         after = torch.cat([t.reshape(-1).float() for t in flat_state(model)])
         out[rank] = dict(model_before=before.numpy(), model_after=after.numpy(), model_bytes=sent,
-                         params=flat.numpy(), top_sum=float(tops.item()), local_top=ix.top,
+                         params=flat.numpy(), params_overlapped=flat2.numpy(), grad_local_only=local_only.numpy(),
+                         w_glob=w_glob.numpy(), w_loc=w_loc.numpy(), prio=prio.numpy(), s_r=float(s_r),
+                         top_sum=float(tops.item()), local_top=ix.top,
                          stats=(float(s_g), float(top_g)), streams=mine)
     finally:
         dist.destroy_process_group()
@@ -141,3 +162,25 @@ def test_broadcast_model_replaces_state_dict_shipping(gloo_run):
     assert np.array_equal(r0["model_after"], r0["model_before"])               # the source is unchanged
     assert np.array_equal(r1["model_after"], r0["model_before"])               # the actor rank now holds the learner's net
     assert r0["model_bytes"] == r1["model_bytes"] == (len(r0["model_before"]) - 1) * 4 + 8
+
+
+def test_overlapped_bucket_equals_the_single_all_reduce(gloo_run):
+    """Gradients exchanged bucket by bucket from backward hooks give the parameters of the one-call exchange,
+    bit for bit; with the exchange switched off the ranks' gradients differ (so the switch really skips it)."""
+    for r in range(WORLD):
+        assert np.array_equal(gloo_run[r]["params_overlapped"], gloo_run[r]["params"])
+    assert not np.array_equal(gloo_run[0]["grad_local_only"], gloo_run[1]["grad_local_only"])
+
+
+def test_global_batch_is_weights(gloo_run):
+    """w = u / (max over BOTH ranks' batches of u + 1e-8), u = (p / S_r)^-beta (dist.global_batch_is_weights)."""
+    B, beta = 8, 0.6
+    u = [(gloo_run[r]["prio"] / gloo_run[r]["s_r"]) ** (-beta) for r in range(WORLD)]
+    mx = np.maximum(u[0].reshape(3, B).max(1), u[1].reshape(3, B).max(1))
+    for r in range(WORLD):
+        want = (u[r].reshape(3, B) / (mx[:, None] + 1e-8)).reshape(-1)
+        np.testing.assert_allclose(gloo_run[r]["w_glob"], want, rtol=1e-6)
+        local = (u[r].reshape(3, B) / (u[r].reshape(3, B).max(1)[:, None] + 1e-8)).reshape(-1)
+        np.testing.assert_allclose(gloo_run[r]["w_loc"], local, rtol=1e-6)
+    both = np.concatenate([gloo_run[r]["w_glob"].reshape(3, B) for r in range(WORLD)], axis=1)
+    assert np.allclose(both.max(1), 1.0, atol=1e-6) and (both <= 1.0 + 1e-6).all()

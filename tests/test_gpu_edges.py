@@ -11,6 +11,7 @@ from agent0_b200 import _lib
 from agent0_b200.config import make_config
 from oracle import losses as OL
 from oracle import reference_replay as OR
+from tests import parity
 
 pytestmark = pytest.mark.gpu
 
@@ -224,9 +225,9 @@ def test_c51_limits(A, M):
     out = L.c51_loss(dv(lg), dv(tg), dv(atoms), dv(a), dv(r), dv(d), dv(w), float(np.float32(0.99)), -10.0, 10.0,
                      want_target_prob=True)
     loss, grad, m = OL.c51(lg, tg, None, a, r, d, w, 0.99, 1, atoms, -10.0, 10.0)
-    np.testing.assert_allclose(_np(out.target_prob), m, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(_np(out.loss), loss, rtol=1e-5, atol=2e-6)
-    np.testing.assert_allclose(_np(out.grad), grad, rtol=1e-5, atol=1e-5)
+    parity.close("c51.target_prob[limits]", out.target_prob, m)
+    parity.close("c51.loss[limits]", out.loss, loss)
+    parity.close("c51.grad[limits]", out.grad, grad)
 
 
 def test_quantile_limits_256_and_1():
@@ -239,8 +240,8 @@ def test_quantile_limits_256_and_1():
         q, tn = [(rng.randn(B, A, N) * 3).astype(np.float32) for _ in range(2)]
         out = L.qr_loss(dv(q), dv(tn), dv(a), dv(r), dv(d), dv(w), float(np.float32(0.99 ** 3)))
         loss, grad = OL.qr(q, tn, None, a, r, d, w, 0.99, 3)
-        np.testing.assert_allclose(_np(out.loss), loss, rtol=1e-5, atol=2e-6)
-        np.testing.assert_allclose(_np(out.grad), grad, rtol=1e-5, atol=1e-5)
+        parity.close("quantile.loss[limits]", out.loss, loss)
+        parity.close("quantile.grad[limits]", out.grad, grad)
     with pytest.raises(RuntimeError, match="outside"):
         L.qr_loss(torch.zeros(2, 2, 257).cuda(), torch.zeros(2, 2, 257).cuda(), torch.zeros(2).long().cuda(), torch.zeros(2).cuda(),
                   torch.zeros(2).cuda(), torch.ones(2).cuda(), 0.99)
@@ -387,9 +388,9 @@ def test_c51_short_chain_kernel_is_bit_identical_to_the_general_kernel_and_match
     assert torch.equal(f.loss, g.loss) and torch.equal(f.grad, g.grad) and torch.equal(f.prio, g.prio)
     assert torch.equal(f.target_prob, g.target_prob) and torch.equal(mpf, mpg)
     loss, grad, m = OL.c51(lg, tg, qs, a, r, d, w, 0.99, 3, atoms, -10.0, 10.0)
-    np.testing.assert_allclose(_np(f.target_prob), m, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(_np(f.loss), loss, rtol=1e-5, atol=2e-6)
-    np.testing.assert_allclose(_np(f.grad), grad, rtol=1e-5, atol=1e-5)
+    parity.close("c51.target_prob[fast kernel]", f.target_prob, m)
+    parity.close("c51.loss[fast kernel]", f.loss, loss)
+    parity.close("c51.grad[fast kernel]", f.grad, grad)
 
 
 def test_unpaired_mailbox_gather_times_out_instead_of_hanging():

@@ -86,7 +86,8 @@ def test_decode_reports_malformed_blocks():
     total = 8 * 64
     rp = _replay(64, hw=hw)
     rng = np.random.RandomState(2)
-    good, want = LZ.encode_sequences(_random_sequences(rng, total, [1, 5, 40]))
+    seqs = _random_sequences(rng, total - 12, [1, 5, 40])
+    good, want = LZ.encode_sequences([(b"abcdefgh", 3, 4)] + seqs)      # a first sequence with a short literal run
     bad = [good, good[:len(good) // 2], (total + 16).to_bytes(4, "little") + good[4:], b"\x00\x02\x00", good[:4]]
     b2 = bytearray(good)
     # first sequence: token, literals, offset -> an offset larger than what has been produced
@@ -151,7 +152,8 @@ def test_extend_takes_the_decisions_of_the_host_deduper(n, N, age, calls):
         assert np.array_equal(_np(b.frames), fr[q])
         assert np.array_equal(_np(b.actions), a[q]) and np.array_equal(_np(b.terminals), d[q])
         assert np.array_equal(_np(b.rewards).view(np.int64), r[q].view(np.int64))
-    assert rp.index.head_fs < 3 * M                                        # ~1-2 stored frames per entry, not 8
+    if age is None:
+        assert rp.index.head_fs < 3 * M                                    # ~1-2 stored frames per entry, not 8
     t = rp.extend_timing()
     assert t["entries"] == calls[-1] and t["device_decode_label_us"] > 0
 
