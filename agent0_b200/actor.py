@@ -94,13 +94,22 @@ class ShardActor:
     concatenates the two 4-frame stacks and lz4-compresses 56 448 bytes per transition (agent.py:64-81);
     here each 1-step transition is appended to the HBM ring as it happens (only its new frames cross
     PCIe) and K3 folds the n steps at gather time.  ``envs`` is the vector env of
-    ``make_atari`` (reset() -> (obs, info); step(a) -> (obs, reward, terminal, truncated, info))."""
+    ``make_atari`` (reset() -> (obs, info); step(a) -> (obs, reward, terminal, truncated, info)).
+
+    Warm-up entries are REJECTED, not emulated: during the first n-1 steps of its lifetime the reference
+    actor's tracker holds fewer than n transitions and it still emits an entry per env and step
+    (agent.py:64-73) -- (obs_0, a_0, an L-step return with L = k+1 < n, obs_{k+1}) -- which its learner
+    then bootstraps with gamma**n as if n steps had passed (agent.py:183).  A ring of 1-step records
+    gathered with a fixed window has no such entry: record (e, 0) becomes sampleable once its (n-1)-th
+    successor exists and then equals the reference's entry of step n-1.  ``warmup_entries_skipped`` counts
+    what the reference would have emitted in addition: (n-1) * num_envs per actor lifetime, out of 1e7."""
 
     def __init__(self, cfg, envs, policy, replay):
         assert replay.n_gather == int(cfg.learner.n_step_q), "construct the ReplayDataset with native_nstep=True"
         self.cfg, self.envs, self.policy, self.replay = cfg, envs, policy, replay
         self.obs, _ = envs.reset()
         self.steps = 0
+        self.warmup_entries_skipped = 0
 
     def reset(self):
         self.obs, _ = self.envs.reset()
@@ -119,6 +128,8 @@ class ShardActor:
             done = np.logical_or(terminal, info["life_loss"]) if "life_loss" in info else terminal
             done = np.logical_and(done, np.logical_not(truncated))
             self.replay.append_vector_step(np.asarray(self.obs), action, reward, done, np.asarray(obs_next))
+            if self.steps < int(cfg.learner.n_step_q):      # the reference's tracker is still shorter than n here
+                self.warmup_entries_skipped += len(action)
             count += len(action)
             self.obs = obs_next
             qs.append(qt_max)

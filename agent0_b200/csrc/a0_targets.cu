@@ -792,46 +792,59 @@ a0_k4_quantile(const A0Common c, int32_t layout, const float* __restrict__ q, co
 // float64: the quadratic ranges subtract numbers of size N*T^2 to get terms of size (q-T)^2 <= 1.  The summation
 // order differs from the reference's pairwise sum, so this kernel lives under the 1e-5 relative contract (it is
 // closer to the exact sum than the fp32 pairwise form); oracle.losses.huber_qr_sorted is its specification.
-constexpr int QS_THREADS = A0_MAX_QUANTILES;     // 256 = 8 sorted runs of one warp each
-static_assert(QS_THREADS == 256, "the merge tree below is written for 8 warps");
+constexpr int QS_MAX = A0_MAX_QUANTILES;         // 256 = 8 sorted runs of one warp each
+static_assert(QS_MAX == 256, "the merge tree below is written for 8 runs of 32");
 
+// smallest float greater than x (x finite): "v <= x" becomes "v < next_up(x)", so both tie rules of the merge are
+// one comparison
+__device__ __forceinline__ float a0_qs_next_up(float x) {
+  const uint32_t b = __float_as_uint(x);
+  if (x == 0.0f) return __uint_as_float(1u);
+  return __uint_as_float((b >> 31) ? b - 1u : b + 1u);
+}
+// Padding above the Ni real targets: finite, larger than any real target, DISTINCT and increasing with the index,
+// so that pads never tie with each other (tied elements of a right run count "<=", which a pad run would not
+// survive) and always sort to the end in index order.
+__device__ __forceinline__ float a0_qs_pad(int idx) { return __uint_as_float(0x7f7fff00u + (uint32_t)idx); }
+
+// One merge level: element x at src[tid] (runs of S sorted values) finds how many elements of its sibling run
+// precede it -- binary search with a running pointer: LDS [p + imm], FSETP, predicated add per step -- and is
+// written to its rank in the merged run of 2S.  x_up = next_up(x).
 template <int S_LOG>
-__device__ __forceinline__ void a0_qs_merge(const float* __restrict__ src, float* __restrict__ dst, int tid) {
+__device__ __forceinline__ void a0_qs_merge(const float* __restrict__ src, float* __restrict__ dst, int tid, float x, float x_up) {
   constexpr int S = 1 << S_LOG;
   const int r = tid >> S_LOG, p = tid & (S - 1);
-  const float x = src[tid];
   const float* sib = src + ((r ^ 1) << S_LOG);
-  const bool right = r & 1;                       // ties: the left run's elements go first (unique ranks)
-  int lo = 0;
+  const float xc = (r & 1) ? x_up : x;            // ties: the left run's elements go first (unique ranks)
+  const float* q = sib;
 #pragma unroll
-  for (int step = S >> 1; step > 0; step >>= 1) {
-    const float v = sib[lo + step - 1];
-    if (right ? (v <= x) : (v < x)) lo += step;
-  }
-  const float v = sib[lo];
-  if (right ? (v <= x) : (v < x)) ++lo;
-  dst[((r >> 1) << (S_LOG + 1)) + p + lo] = x;
+  for (int step = S >> 1; step > 0; step >>= 1)
+    if (q[step - 1] < xc) q += step;
+  if (q[0] < xc) ++q;
+  dst[((r >> 1) << (S_LOG + 1)) + p + (int)(q - sib)] = x;
 }
 
-__global__ void __launch_bounds__(QS_THREADS)
+__global__ void __launch_bounds__(QS_MAX)
 a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict__ q, const float* __restrict__ qt,
                       const float* __restrict__ taus, const float* __restrict__ qsel, int32_t Ni, int32_t Nj,
                       float* __restrict__ grad) {
-  __shared__ float bufA[QS_THREADS], bufB[QS_THREADS];
-  __shared__ double S1[QS_THREADS + 1], S2[QS_THREADS + 1];
-  __shared__ double ws1[QS_THREADS / 32], ws2[QS_THREADS / 32];
+  __shared__ float bufA[QS_MAX], bufB[QS_MAX];
+  __shared__ __align__(16) double S1[QS_MAX + 2], S2[QS_MAX + 2];
+  __shared__ __align__(16) double ws1[QS_MAX / 32], ws2[QS_MAX / 32];
   __shared__ float sMean[A0_MAX_ACTIONS];
-  __shared__ float red[QS_THREADS / 32];
+  __shared__ float red[QS_MAX / 32];
   __shared__ int s_astar;
   A0_PDL_PROLOGUE();
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int nwarps = QS_THREADS / 32;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;      // 32 * ceil(max(Ni, Nj) / 32): 7 warps for QR-200
   const int A = c.A;
   const size_t sN_q = layout == 0 ? 1 : (size_t)A, sA_q = layout == 0 ? (size_t)Nj : 1;
   const size_t sN_t = layout == 0 ? 1 : (size_t)A, sA_t = layout == 0 ? (size_t)Ni : 1;
   const float* qb = q + (size_t)b * A * Nj;
   const float* tb = qt + (size_t)b * A * Ni;
+  // runs without threads (beyond blockDim) hold pads in both buffers: they are never moved and never counted
+  for (int i = nthreads + tid; i < QS_MAX; i += nthreads) { bufA[i] = a0_qs_pad(i); bufB[i] = a0_qs_pad(i); }
   // ---- action selection (as a0_k4_quantile) ------------------------------------------------------------
   if (qsel) {
     if (wid == 0) {
@@ -861,23 +874,25 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
   __syncthreads();
   const int a_star = s_astar;
   // ---- sort the targets: one bitonic network per warp, then merge 32 -> 64 -> 128 -> 256 ------------------
-  float x = tid < Ni ? a0_td_target(r, d, c.gamma_n, tb[a_star * sA_t + tid * sN_t]) : INFINITY;   // pads sort to the end
+  float x = tid < Ni ? a0_td_target(r, d, c.gamma_n, tb[a_star * sA_t + tid * sN_t]) : a0_qs_pad(tid);
 #pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
+  for (int lk = 1; lk <= 5; ++lk) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const float y = __shfl_xor_sync(0xffffffffu, x, j);
-      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
-      x = (lower == up) ? fminf(x, y) : fmaxf(x, y);
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const float y = __shfl_xor_sync(0xffffffffu, x, 1 << lj);
+      // keep the minimum iff bit lj and bit lk of the lane agree (ascending blocks of 2^lk; lk = 5: the whole warp)
+      const bool keep_min = (((lane ^ (lane >> (lk - lj))) >> lj) & 1) == 0;
+      x = keep_min ? fminf(x, y) : fmaxf(x, y);
     }
   }
+  const float x_up = a0_qs_next_up(x);
   bufA[tid] = x;
   __syncthreads();
-  a0_qs_merge<5>(bufA, bufB, tid);
+  a0_qs_merge<5>(bufA, bufB, tid, x, x_up);
   __syncthreads();
-  a0_qs_merge<6>(bufB, bufA, tid);
+  a0_qs_merge<6>(bufB, bufA, tid, x, x_up);
   __syncthreads();
-  a0_qs_merge<7>(bufA, bufB, tid);
+  a0_qs_merge<7>(bufA, bufB, tid, x, x_up);
   __syncthreads();
   // ---- prefix sums of T and T^2 over the sorted targets (float64) -----------------------------------------
   {
@@ -892,7 +907,7 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
     __syncthreads();
     double b1 = 0.0, b2 = 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < nwarps; ++w2)
+    for (int w2 = 0; w2 < QS_MAX / 32 - 1; ++w2)
       if (w2 < wid) { b1 += ws1[w2]; b2 += ws2[w2]; }
     S1[tid + 1] = p1 + b1;
     S2[tid + 1] = p2 + b2;
@@ -902,18 +917,18 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
   // ---- per online quantile: the three range boundaries, then the closed form ---------------------------------
   float lsum = 0.0f, gsum = 0.0f;
   if (tid < Nj) {
-    const float qm = qj - 1.0f, qp = qj + 1.0f;
-    int ia = 0, ib = 0, ic = 0;                   // #{T <= q-1}, #{T < q}, #{T < q+1}
+    const float qm_up = a0_qs_next_up(qj - 1.0f), qp = qj + 1.0f;
+    const float *pa = bufB, *pb = bufB, *pc = bufB;   // -> #{T <= q-1}, #{T < q}, #{T < q+1}
 #pragma unroll
-    for (int step = QS_THREADS >> 1; step > 0; step >>= 1) {
-      const float va = bufB[ia + step - 1], vb = bufB[ib + step - 1], vc = bufB[ic + step - 1];
-      if (va <= qm) ia += step;
-      if (vb < qj) ib += step;
-      if (vc < qp) ic += step;
+    for (int step = QS_MAX >> 1; step > 0; step >>= 1) {
+      if (pa[step - 1] < qm_up) pa += step;
+      if (pb[step - 1] < qj) pb += step;
+      if (pc[step - 1] < qp) pc += step;
     }
-    if (bufB[ia] <= qm) ++ia;
-    if (bufB[ib] < qj) ++ib;
-    if (bufB[ic] < qp) ++ic;
+    if (pa[0] < qm_up) ++pa;
+    if (pb[0] < qj) ++pb;
+    if (pc[0] < qp) ++pc;
+    int ia = (int)(pa - bufB), ib = (int)(pb - bufB), ic = (int)(pc - bufB);
     ia = min(ia, Ni); ib = min(max(ib, ia), Ni); ic = min(max(ic, ib), Ni);
     const double qd = (double)qj, td = (double)tau;
     const double nA = (double)ia, nB = (double)(ib - ia), nC = (double)(ic - ib), nD = (double)(Ni - ic);
@@ -930,7 +945,7 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
   }
   const float total = a0_block_sum(lsum, red, nwarps);
   float* gb = grad + (size_t)b * A * Nj;
-  for (int i = tid; i < A * Nj; i += QS_THREADS) gb[i] = 0.0f;
+  for (int i = tid; i < A * Nj; i += nthreads) gb[i] = 0.0f;
   __syncthreads();
   if (tid < Nj) gb[a * sA_q + tid * sN_q] = __fdiv_rn(w, (float)Ni) * gsum;
   if (tid == 0) a0_emit(c, b, __fdiv_rn(total, (float)Ni));
@@ -965,7 +980,7 @@ extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const
   int threads = Ni > Nj ? Ni : Nj;
   threads = ((threads + 31) / 32) * 32;
   if (!q_bar && Ni > 64 && Nj > 64 && a0_option_qh_sorted()) {      // QR-sized: O(N log N) sorted-target form
-    A0_LAUNCH(a0_k4_quantile_sorted, (unsigned)c->B, QS_THREADS, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
+    A0_LAUNCH(a0_k4_quantile_sorted, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
               taus, qsel, Ni, Nj, grad);
     return A0_OK;
   }

@@ -249,3 +249,78 @@ class ReplayTargetLoop:
             self.graph.replay()
         else:
             self.step(slot=slot)
+
+
+class StaleByOneLoop:
+    """Opt-in schedule of the same inner loop with the priority write-back of step s taken off the critical
+    path: K2b(s) runs on a side stream WHILE step s+1 draws and gathers (K2a + K3), so step s+1 samples with
+    priorities that are one step stale.  The reference itself samples with stale priorities -- its 2 DataLoader
+    workers and 3-deep prefetch queue draw several batches ahead of the updates (trainer.py:64-70,83-87; SURVEY
+    Q4) -- so this is inside its semantics, but it is NOT the default: ``ReplayTargetLoop`` applies every update
+    before the next draw and is what the parity tests and bench.py's ``value`` use.
+
+    Two ``ReplayTargetLoop`` buffer sets alternate (step s writes set s % 2); graph p replays
+        main stream:  K2a + K3 into set p  ->  K4 x L on set p
+        side stream:  K2b on set 1-p (the previous step's indices and losses)
+    and joins both.  Updates are applied in step order (each K2b waits for its predecessor through the graph
+    replays), duplicates keep last-writer-wins, the tree stays node == fl32(left + right) at every replay
+    boundary.  A draw that races with a write-back can see a parent that is newer or older than its children:
+    every decision of the descent still moves to a child whose mass was positive when it was read, and K2b never
+    zeroes a leaf, so every drawn index is a live record (tested)."""
+
+    def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, **kw):
+        kw = dict(kw)
+        kw.setdefault("rng_seed", 1)
+        self.loops = [ReplayTargetLoop(replay, algo, batch_size, learner_steps, action_dim, outputs, **kw) for _ in range(2)]
+        self.rp = replay
+        self.total = self.loops[0].total
+        self.side = torch.cuda.Stream(device=replay.device)
+        self.graphs = None
+        self.s = 0
+        self.launches_per_step = self.loops[0].launches_per_step
+
+    def _step(self, p, first=False):
+        cur, prev = self.loops[p], self.loops[1 - p]
+        main = torch.cuda.current_stream(self.rp.device)
+        if not first:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                prev.update()
+        cur.sample_gather() if cur.overlap_sg else (cur.sample(), cur.gather())
+        for k in range(cur.L):
+            cur.target_loss(k)
+        if not first:
+            main.wait_stream(self.side)
+
+    def capture(self, warm=2):
+        self.rp.push_dynamic()
+        self._step(0, first=True)
+        for i in range(warm):
+            self._step((i + 1) % 2)
+        torch.cuda.synchronize(self.rp.device)
+        self.s = warm + 1
+        self.graphs = {}
+        for q in range(2):                              # the graph that writes buffer set q (steps with s % 2 == q)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step(q)
+            self.graphs[q] = g
+        return self.graphs
+
+    def run(self, publish=True):
+        """One step (replays the graph of the current parity); the step's own write-back happens during the next."""
+        if publish:
+            self.rp.push_dynamic()
+        if self.graphs is None:
+            self._step(self.s % 2, first=self.s == 0)
+        else:
+            self.graphs[self.s % 2].replay()
+        self.s += 1
+
+    def current(self):
+        """The buffer set the LAST run() wrote (indices, losses, gradients ...)."""
+        return self.loops[(self.s - 1) % 2]
+
+    def flush(self):
+        """Apply the write-back of the last step (nothing is pending afterwards)."""
+        self.current().update()

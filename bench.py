@@ -810,6 +810,35 @@ def extras(rp, args, torch, peak, configs, entries):
         full, compact = time_workload(rp, name, args, torch, peak, L, A)
         out["workloads"][name] = full
         configs.append(compact)
+    # the opt-in schedule that takes K2b off the critical path (hotloop.StaleByOneLoop): step s+1 draws while step s's
+    # priorities are written back, i.e. with priorities one step stale -- the reference's prefetch queue does the same
+    try:
+        from agent0_b200.hotloop import StaleByOneLoop
+        wl = WORKLOADS[args.workload]
+        sl = StaleByOneLoop(rp, wl["algo"], wl["B"], L, A, net_outputs(wl["algo"], L * wl["B"], A, torch, rp.device), n_step=wl["n"],
+                            double_q=wl["double"], per=wl["per"], discount=0.99, rng_seed=RNG_SEED)
+        sl.capture()
+        for _ in range(10):
+            sl.run(publish=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bl = []
+        while sum(bl) < 0.1:
+            e0.record()
+            for _ in range(20):
+                sl.run(publish=False)
+            e1.record()
+            torch.cuda.synchronize()
+            bl.append(e0.elapsed_time(e1) / 1e3)
+        sl.flush()
+        med = float(np.median(bl))
+        out["stale_by_one_schedule"] = {"workload": args.workload, "transitions_per_s": round(sl.total * 20 / med, 1),
+                                        "ms_per_step": round(med / 20 * 1e3, 5), "blocks": len(bl),
+                                        "note": "opt-in: K2b(s) on a side stream under K2a + K3 of step s+1 (priorities one step stale, as the "
+                                                "reference's 3-deep prefetch); not the headline semantics"}
+        del sl
+    except Exception as e:      # measurement only
+        out["stale_by_one_schedule"] = {"error": repr(e)[:300]}
     # K3 with the learner's input conversion fused in (a0_rb_gather_f32) against the three-pass
     # alternative it replaces: K3 to u8, then torch's .float() and .div(255) (agent.py:129-135)
     out["k3_f32"] = []

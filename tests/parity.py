@@ -58,6 +58,12 @@ def dump(root):
     doc = {"contract": f"|got-ref| <= {RTOL:g} * max(|ref|, {FLOOR:g} * max|ref|) per element (tests/parity.py)",
            "note": "max_rel_err_floor_1e-3 is the same measure with a 1e-3 denominator floor, for information",
            "worst": {k: {kk: (float(f"{vv:.3e}") if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in sorted(RECORD.items())}}
+    if os.path.exists(os.path.join(root, "profiles", "parity_r02.json")):      # a partial run (-k ...) keeps the other entries
+        try:
+            old = json.load(open(os.path.join(root, "profiles", "parity_r02.json")))["worst"]
+            doc["worst"] = dict(sorted({**old, **doc["worst"]}.items()))
+        except Exception:
+            pass
     for d in ("profiles", "gpurun_out"):
         try:
             os.makedirs(os.path.join(root, d), exist_ok=True)

@@ -143,6 +143,9 @@ def test_shard_actor_fills_the_ring_like_the_reference_actor_fills_its_deque(gol
     count, rs, qs = actor.sample(1.0)
     assert count == T * E and len(qs) == T and rs == []
     assert rp.top == (T - n + 1) * E
+    # the reference emitted T*E entries: its first (n-1)*E are warm-up entries (tracker shorter than n,
+    # agent.py:64-73), which the ring rejects and counts
+    assert actor.warmup_entries_skipped == (n - 1) * E == len(g["entry_action"]) - rp.top
     ks, es = np.meshgrid(np.arange(n - 1, T), np.arange(E), indexing="ij")
     ref_i = (ks * E + es).reshape(-1)
     pos = torch.as_tensor(((ks - n + 1) * E + es).reshape(-1), device="cuda")

@@ -149,3 +149,61 @@ def test_sampling_law_at_scale(shard):
         draws += B * K
     freq = counts / draws
     assert float((freq - mass).abs().max()) < 4 * float((mass.max() / draws).sqrt())
+
+
+def test_duplicates_per_batch_against_the_reference_draw_without_replacement(shard):
+    """The reference's sampler interface draws WITHOUT replacement (torch.multinomial(priority[:top], B, False),
+    replay.py:41-43: no index twice in a batch, at the price of a law that is no longer P(i) ~ p_i once a heavy
+    record has been taken); the stratified tree descent draws WITH replacement and keeps the law.  The figure
+    that separates the two is the duplicate rate inside a batch of 512, measured here on three priority
+    vectors and written to profiles/parity_r02.json:
+      spread   |N(0,1)|-shaped priorities (the shard as built): no stratum is narrower than a leaf
+      peaked   1 % of the records at 100x the rest
+      extreme  100 records hold 90 % of the mass (each spans ~4.6 strata: those draws MUST repeat)
+    and checked against what the stratification implies: a record of mass m is drawn at most
+    ceil(m * B / total) + 1 times per batch."""
+    from tests import parity
+    rp, _, _ = shard
+    dev = rp.device
+    leaves = rp.priority.leaves()
+    live = torch.nonzero(leaves > 0).squeeze(1)
+    saved = leaves[live].clone()
+    g = torch.Generator(device=dev).manual_seed(9)
+    out = {}
+
+    def measure(tag):
+        total = float(rp.priority_sum())
+        dup, worst, bound_ok = 0, 0, True
+        for it in range(5):
+            b = rp.sample(B, k_batches=K, seed=1234, call=it)
+            idx = b.indices.view(K, B)
+            for k in range(K):
+                u, c = torch.unique(idx[k], return_counts=True)
+                dup += B - u.numel()
+                worst = max(worst, int(c.max()))
+                cap = torch.ceil(leaves[u].double() * B / total) + 1
+                bound_ok &= bool((c.double() <= cap).all())
+        out[tag] = {"duplicate_fraction_per_batch_of_512": round(dup / (5 * K * B), 5), "max_repeats_of_one_record": worst,
+                    "reference_multinomial_without_replacement": 0.0}
+        assert bound_ok, tag
+
+    try:
+        measure("spread")
+        ones = torch.ones(live.numel(), device=dev)
+        heavy = torch.randperm(live.numel(), device=dev, generator=g)[:live.numel() // 100]
+        v = ones.clone(); v[heavy] = 100.0
+        for lo in range(0, live.numel(), 1 << 20):
+            rp.set_priorities(live[lo:lo + (1 << 20)], v[lo:lo + (1 << 20)])
+        measure("peaked_1pct_at_100x")
+        v = ones.clone()
+        v[heavy[:100]] = 0.9 / 0.1 * float(live.numel() - 100) / 100.0
+        for lo in range(0, live.numel(), 1 << 20):
+            rp.set_priorities(live[lo:lo + (1 << 20)], v[lo:lo + (1 << 20)])
+        measure("extreme_100_records_hold_90pct")
+    finally:
+        for lo in range(0, live.numel(), 1 << 20):
+            rp.set_priorities(live[lo:lo + (1 << 20)], saved[lo:lo + (1 << 20)])
+    assert out["spread"]["duplicate_fraction_per_batch_of_512"] < 0.01
+    assert out["peaked_1pct_at_100x"]["duplicate_fraction_per_batch_of_512"] < 0.05
+    assert 0.5 < out["extreme_100_records_hold_90pct"]["duplicate_fraction_per_batch_of_512"] < 0.9
+    parity.RECORD["k2a.duplicates_in_a_batch (with-replacement stratified draw vs replay.py:41-43)"] = out

@@ -324,3 +324,55 @@ def test_uniform_replay_stays_uniform_under_the_loop():
     after = rp2.priority.leaves()
     assert torch.equal(after[:8][5:8], before[:8][5:8]) and abs(float(after[8]) - (2.0 + 0.01) ** 0.5) < 1e-6
     assert np.isfinite(float(rp2.priority_sum())) and np.isfinite(rp2.max_p)
+
+
+def test_stale_by_one_schedule_keeps_the_tree_consistent_and_the_default_unchanged():
+    """hotloop.StaleByOneLoop (opt-in): the write-back of step s runs on a side stream under the draw + gather of
+    step s+1.  Every drawn index is a live record, the tree is node == fl32(left + right) after every replay, the
+    last step's leaves hold its priorities after flush(), and max_p follows the largest loss seen.  The default
+    loop on a twin shard (same fill, same seeds) is untouched by the existence of the schedule: its results equal
+    a second default run bit for bit."""
+    from agent0_b200.hotloop import ReplayTargetLoop, StaleByOneLoop
+    T = B * L
+    o = _outputs("c51", T)
+    rp = _shard("c51")
+    loop = StaleByOneLoop(rp, "c51", B, L, A, o, n_step=3, rng_seed=5)
+    loop.capture()
+    P = rp.P
+    live = torch.as_tensor(np.asarray(rp.index.sampleable), device="cuda")
+    seen_max = 1.0
+    for it in range(12):
+        loop.run()
+        torch.cuda.synchronize()
+        cur = loop.current()
+        assert bool(live[cur.idx].all()) and bool(torch.isfinite(cur.loss).all()) and bool((cur.w > 0).all())
+        t = rp.tree
+        assert torch.equal(t[1:P], t[2:2 * P:2] + t[3:2 * P:2])
+        seen_max = max(seen_max, float(cur.loss.max()))
+    last = loop.current()
+    before_flush = rp.priority.leaves()[last.idx].clone()
+    loop.flush()
+    torch.cuda.synchronize()
+    idx, loss = last.idx.cpu().numpy(), last.loss.cpu().numpy()
+    want = {}
+    for i, l in zip(idx, loss):                      # duplicates: the last writer wins
+        want[int(i)] = np.sqrt(np.float32(l) + np.float32(0.01))
+    leaves = rp.priority.leaves().cpu().numpy()
+    np.testing.assert_allclose([leaves[i] for i in want], list(want.values()), rtol=1e-6)
+    assert not torch.equal(before_flush, rp.priority.leaves()[last.idx])          # the write-back really was pending
+    assert rp.max_p >= seen_max * (1 - 1e-6)          # K4 raises it as it goes (the captured warm-up steps count too)
+    t = rp.tree
+    assert torch.equal(t[1:P], t[2:2 * P:2] + t[3:2 * P:2])
+    # the default schedule: two identical runs on twin shards
+    res = []
+    for _ in range(2):
+        rq = _shard("c51")
+        lp = ReplayTargetLoop(rq, "c51", B, L, A, o, n_step=3, rng_seed=5)
+        rq.rng_seek(0)
+        lp.capture()
+        rq.rng_seek(0)
+        for _ in range(3):
+            lp.run()
+        torch.cuda.synchronize()
+        res.append((lp.idx.clone(), lp.loss.clone(), rq.tree.clone()))
+    assert all(torch.equal(a_, b_) for a_, b_ in zip(res[0], res[1]))

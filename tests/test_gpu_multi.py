@@ -97,3 +97,53 @@ def test_two_gpu_learner_equals_one_learner_at_double_batch(algo):
         np.testing.assert_allclose(got, res["q_loss"].cpu().numpy(), rtol=2e-3, atol=1e-5)
     want = torch.cat([p.detach().reshape(-1) for p in ref.model.parameters()]).cpu().numpy()
     np.testing.assert_allclose(out[0]["params"], want, rtol=2e-3, atol=2e-5)
+
+
+def _trainer_worker(rank, port, graph, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=torch.device("cuda", rank))
+    try:
+        from agent0_b200.config import make_config
+        from agent0_b200.synth import fill_shard_synthetic
+        from agent0_b200.trainer import Trainer
+        B, L = 32, 4
+        cfg = make_config("c51", per=True, n_step=3, batch_size=B, double_q=True, dueling=True, replay_size=4096, num_envs=8)
+        cfg.learner.learner_steps = L
+        cfg.learner.target_update_freq = 8
+        torch.manual_seed(3)                                   # both replicas start from the same weights
+        tr = Trainer(cfg, process_group=dist.group.WORLD, native_nstep=True, graph=graph, fused_input=True,
+                     sampler_seed=100 + rank, global_is_max=not graph)
+        fill_shard_synthetic(tr.replay, 4096, 8, 20 + rank)     # every rank its own shard
+        bk = tr.learner.bucket
+        assert len(bk.buckets) == 2 and bk.world == 2
+        losses = []
+        for it in range(4):                                    # graph: call 1 runs eagerly and captures, 2..4 replay
+            outs = tr.learn()
+            losses.append(torch.stack([q.mean() for q, _ in outs]).cpu().numpy())
+        torch.cuda.synchronize()
+        params = torch.cat([p.detach().reshape(-1) for p in tr.learner.model.parameters()]).cpu().numpy()
+        tgt = torch.cat([p.detach().reshape(-1) for p in tr.learner.model_target.parameters()]).cpu().numpy()
+        out[rank] = dict(params=params, target=tgt, losses=np.stack(losses), steps=tr.learner.update_steps)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda_graph"])
+def test_two_gpu_trainer_with_overlapped_allreduce_keeps_replicas_identical(graph):
+    """Trainer.learn on two ranks, each sampling its own shard: the gradient buckets are all-reduced from backward
+    hooks (dist.OverlappedGradBucket) -- eagerly, and captured inside the CUDA graph of the 4 updates -- so the two
+    replicas take the same steps: parameters and target networks stay bit-identical, losses differ (different
+    shards) and are finite.  The eager run also normalises the IS weights over the global batch (global_is_max)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_trainer_worker, args=(_free_port(), graph, out), nprocs=2, join=True)
+    out = dict(out)
+    assert out[0]["steps"] == out[1]["steps"] == 16
+    assert np.array_equal(out[0]["params"], out[1]["params"]) and np.array_equal(out[0]["target"], out[1]["target"])
+    assert np.isfinite(out[0]["losses"]).all() and np.isfinite(out[1]["losses"]).all()
+    assert not np.array_equal(out[0]["losses"], out[1]["losses"])
