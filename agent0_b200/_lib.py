@@ -61,6 +61,7 @@ SIGNATURES = {
     "a0_ex_create": (_i32, [C.POINTER(_vp), _vp, _vp]),
     "a0_ex_destroy": (_i32, [_vp]),
     "a0_ex_extend": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp]),
+    "a0_ex_extend_v": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp]),
     "a0_ex_decode": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "a0_ex_resolve": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, C.POINTER(_i32)]),
     "a0_ex_last_timing": (_i32, [_vp, _vp]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "a0_pt_mark": (_i32, [_vp, _vp, _i32, _f32, _vp]),
     "a0_pt_update": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _vp]),
     "a0_pt_update_report": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp]),
+    "a0_pt_update_overlapped": (_i32, [_vp, _vp, _vp, _i32, _f32, _f32, _vp, _vp, _vp]),
     "a0_host_map": (_i32, [_vp, C.POINTER(_vp)]),
     "a0_pt_set": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "a0_rb_set_dynamic": (_i32, [_vp, _f32, _f32, _f32, _vp]),
@@ -111,6 +113,30 @@ def load():
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+_pyingest = False
+
+
+def pyingest():
+    """The CPython-API marshalling helper (csrc/a0_pyingest.c -> _a0_pyingest.so, loaded with PyDLL), or None when
+    it has not been built: ``ReplayDataset.extend`` then unpacks the tuples in Python (same C ABI call after that)."""
+    global _pyingest
+    if _pyingest is False:
+        path = os.path.join(_PKG, "_a0_pyingest.so")
+        _pyingest = None
+        if os.path.exists(path):
+            try:
+                h = C.PyDLL(path)
+                h.a0_py_unpack.restype = _i64
+                h.a0_py_unpack.argtypes = [C.py_object, _i64, _vp, _vp, _vp, _vp, _vp, _vp]
+                h.a0_py_release.restype = None
+                h.a0_py_release.argtypes = [_i64, _vp]
+                h.a0_py_buffer_size.restype = _i64
+                _pyingest = h
+            except OSError:
+                _pyingest = None
+    return _pyingest
 
 
 def check(rc, what):

@@ -19,6 +19,7 @@ def _stale():
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
         os.path.join(PKG, "..", "include", "agent0_b200.h"), os.path.abspath(__file__)]
+    deps = [d for d in deps if not d.endswith("a0_pyingest.c")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -43,5 +44,23 @@ def build(force=False, verbose=False, trace=False):
     return TRACE_LIB if trace else LIB
 
 
+PYINGEST_SRC = os.path.join(CSRC, "a0_pyingest.c")
+PYINGEST_LIB = os.path.join(PKG, "_a0_pyingest.so")
+
+
+def build_pyingest(force=False):
+    """The CPython-API marshalling helper of ReplayDataset.extend (host glue, plain gcc, no CUDA)."""
+    import sysconfig
+    if not force and os.path.exists(PYINGEST_LIB) and os.path.getmtime(PYINGEST_LIB) >= os.path.getmtime(PYINGEST_SRC):
+        return PYINGEST_LIB
+    inc = sysconfig.get_paths()["include"]
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", inc, PYINGEST_SRC, "-o", PYINGEST_LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return PYINGEST_LIB
+
+
 if __name__ == "__main__":
+    build_pyingest(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -1057,14 +1057,19 @@ constexpr size_t K2C_SMEM = ((size_t)2 << K2C_LOG) * 4 + ((size_t)1 << K2C_LOG) 
 __global__ void __launch_bounds__(K2C_THREADS)
 a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
               const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
-              float alpha, float eps, float* __restrict__ max_p, unsigned int* __restrict__ ticket, const A0Report rep) {
+              float alpha, float eps, float* __restrict__ max_p, unsigned int* __restrict__ ticket, const A0Report rep,
+              int32_t early) {
   extern __shared__ __align__(16) uint8_t a0_k2c_smem[];
   __shared__ int s_dirty;
   __shared__ bool s_last;
   float* heap = reinterpret_cast<float*>(a0_k2c_smem);                      // heap[i] = node i of the chunk's sub-tree
   int* win = reinterpret_cast<int*>(a0_k2c_smem + ((size_t)2 << K2C_LOG) * 4);
   A0_T0();
-  A0_PDL_PROLOGUE();
+  // early (a0_pt_update_overlapped): launched programmatically under its predecessor -- the last K4 of a step -- the
+  // kernel loads its leaves and builds its tickets (positions only) while that kernel is still running, and waits
+  // for it only where the loss values are first needed.  Everything OLDER than the predecessor is complete when
+  // this grid starts (the predecessor triggered after its own wait), which is what the caller guarantees for idx.
+  if (!early) A0_PDL_PROLOGUE();
   A0_TMID();
 #ifdef A0_TRACE
   const long long _c0 = clock64();
@@ -1077,7 +1082,6 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   const int clog = D < K2C_LOG ? D : K2C_LOG;
   const int n = 1 << clog;
   const int top_levels = D - clog;                           // depth of the chunk roots
-  const float maxp_in = __ldcg(max_p);
   const int64_t lo = (int64_t)c << clog;                    // first leaf of the chunk
   if (tid == 0) s_dirty = 0;
   if (n >= 4) {
@@ -1099,20 +1103,26 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   };
   __syncthreads();
   K2C_TX(0);
-  // ---- pass 1: tickets for the entries of this chunk (CTA 0 also: running max of the losses, report) --
-  float mx = 0.0f;
+  // ---- pass 1: tickets for the entries of this chunk (positions only) ---------------------------------
   for (int k = tid; k < count; k += K2C_THREADS) {
     bool set;
     const int64_t p = position(k, set);
-    if (c == 0) {
+    if (p >= lo && p < lo + n && p < N) atomicMax(win + (int)(p - lo), k);
+  }
+  if (early) A0_PDL_PROLOGUE();                              // from here on the values (losses, max_p) are read
+  const float maxp_in = __ldcg(max_p);
+  if (c == 0) {                                              // CTA 0 also: running max of the losses, report
+    float mx = 0.0f;
+    for (int k = tid; k < count; k += K2C_THREADS) {
+      bool set;
+      const int64_t p = position(k, set);
       if (rep.idx) { rep.idx[k] = p; rep.loss[k] = vals[k]; }
       if (mode == 0 && p >= 0 && p < N) mx = fmaxf(mx, vals[k]);
     }
-    if (p >= lo && p < lo + n && p < N) atomicMax(win + (int)(p - lo), k);
-  }
-  if (c == 0 && mode == 0) {
-    mx = a0_warp_max(mx);
-    if ((tid & 31) == 0) a0_atomic_max_pos(max_p, mx);      // max_p = max(max_p, max loss), replay.py:59
+    if (mode == 0) {
+      mx = a0_warp_max(mx);
+      if ((tid & 31) == 0) a0_atomic_max_pos(max_p, mx);    // max_p = max(max_p, max loss), replay.py:59
+    }
   }
   __syncthreads();
   K2C_TX(1);
@@ -1208,7 +1218,7 @@ static int a0_launch_paths(a0_replay_t* h, const int64_t* idx64, const int32_t* 
 
 static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t* idx32, const float* vals,
                             int32_t count, int32_t mode, float alpha, float eps, a0_stream_t stream_,
-                            const A0Report rep = {nullptr, nullptr}) {
+                            const A0Report rep = {nullptr, nullptr}, bool early = false) {
   if (count == 0) return A0_OK;
   A0DeviceGuard guard(h->device);
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1227,8 +1237,8 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
       A0_CUDA(cudaFuncSetAttribute(a0_k2b_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2C_SMEM));
       attr[h->device] = true;
     }
-    A0_LAUNCH(a0_k2b_chunks, (unsigned)chunks, K2C_THREADS, K2C_SMEM, stream, 1, A0_PDL_K2, h->tree, h->P, h->D, h->N, idx64, idx32, vals,
-              count, mode, alpha, eps, h->max_p, h->counter + A0_MAX_BATCHES, rep);
+    A0_LAUNCH(a0_k2b_chunks, (unsigned)chunks, K2C_THREADS, K2C_SMEM, stream, 1, early ? A0_PDL_FORCE : A0_PDL_K2, h->tree, h->P, h->D, h->N,
+              idx64, idx32, vals, count, mode, alpha, eps, h->max_p, h->counter + A0_MAX_BATCHES, rep, (int32_t)(early ? 1 : 0));
     return A0_OK;
   }
   const bool hybrid = count >= a0_option_k2b_bulk_min() && (int64_t)count >= 4 * chunks;
@@ -1259,6 +1269,15 @@ extern "C" int a0_pt_update(a0_replay_t* h, const int64_t* idx, const float* los
   A0_REQUIRE(count == 0 || (idx && loss), "a0_pt_update: NULL argument");
   { int frc = a0_check_fault(h, "a0_pt_update"); if (frc) return frc; }
   return a0_launch_update(h, idx, nullptr, loss, count, 0, alpha, eps, stream);
+}
+extern "C" int a0_pt_update_overlapped(a0_replay_t* h, const int64_t* idx, const float* loss, int32_t count, float alpha,
+                                       float eps, int64_t* idx_report, float* loss_report, a0_stream_t stream) {
+  A0_REQUIRE(h != nullptr && count >= 0, "a0_pt_update_overlapped: bad handle or count");
+  A0_REQUIRE(count == 0 || (idx && loss), "a0_pt_update_overlapped: NULL argument");
+  A0_REQUIRE((idx_report == nullptr) == (loss_report == nullptr), "a0_pt_update_overlapped: give both report buffers or none");
+  { int frc = a0_check_fault(h, "a0_pt_update_overlapped"); if (frc) return frc; }
+  const A0Report rep = {idx_report, loss_report};
+  return a0_launch_update(h, idx, nullptr, loss, count, 0, alpha, eps, stream, rep, true);
 }
 // Device-visible alias of page-locked host memory (mapped under unified addressing: what cudaHostAlloc
 // and torch's pin_memory give), for the report buffers of a0_pt_update_report.  Not a stream

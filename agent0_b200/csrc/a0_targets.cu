@@ -807,13 +807,14 @@ __device__ __forceinline__ float a0_qs_next_up(float x) {
 // survive) and always sort to the end in index order.
 __device__ __forceinline__ float a0_qs_pad(int idx) { return __uint_as_float(0x7f7fff00u + (uint32_t)idx); }
 
-// One merge level: element x at src[tid] (runs of S sorted values) finds how many elements of its sibling run
-// precede it -- binary search with a running pointer: LDS [p + imm], FSETP, predicated add per step -- and is
-// written to its rank in the merged run of 2S.  x_up = next_up(x).
+// One merge level: the thread's element x, currently at src[pos] (runs of S sorted values), finds how many
+// elements of its sibling run precede it -- binary search with a running pointer: LDS [p + imm], FSETP, predicated
+// add per step -- and moves to its rank in the merged run of 2S (returned: the thread keeps its element in a
+// register and follows its position, so no level re-reads it).  x_up = next_up(x).
 template <int S_LOG>
-__device__ __forceinline__ void a0_qs_merge(const float* __restrict__ src, float* __restrict__ dst, int tid, float x, float x_up) {
+__device__ __forceinline__ int a0_qs_merge(const float* __restrict__ src, float* __restrict__ dst, int pos, float x, float x_up) {
   constexpr int S = 1 << S_LOG;
-  const int r = tid >> S_LOG, p = tid & (S - 1);
+  const int r = pos >> S_LOG, p = pos & (S - 1);
   const float* sib = src + ((r ^ 1) << S_LOG);
   const float xc = (r & 1) ? x_up : x;            // ties: the left run's elements go first (unique ranks)
   const float* q = sib;
@@ -821,7 +822,9 @@ __device__ __forceinline__ void a0_qs_merge(const float* __restrict__ src, float
   for (int step = S >> 1; step > 0; step >>= 1)
     if (q[step - 1] < xc) q += step;
   if (q[0] < xc) ++q;
-  dst[((r >> 1) << (S_LOG + 1)) + p + (int)(q - sib)] = x;
+  const int out = ((r >> 1) << (S_LOG + 1)) + p + (int)(q - sib);
+  dst[out] = x;
+  return out;
 }
 
 __global__ void __launch_bounds__(QS_MAX)
@@ -888,11 +891,11 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
   const float x_up = a0_qs_next_up(x);
   bufA[tid] = x;
   __syncthreads();
-  a0_qs_merge<5>(bufA, bufB, tid, x, x_up);
+  int pos = a0_qs_merge<5>(bufA, bufB, tid, x, x_up);
   __syncthreads();
-  a0_qs_merge<6>(bufB, bufA, tid, x, x_up);
+  pos = a0_qs_merge<6>(bufB, bufA, pos, x, x_up);
   __syncthreads();
-  a0_qs_merge<7>(bufA, bufB, tid, x, x_up);
+  a0_qs_merge<7>(bufA, bufB, pos, x, x_up);
   __syncthreads();
   // ---- prefix sums of T and T^2 over the sorted targets (float64) -----------------------------------------
   {

@@ -14,6 +14,28 @@ import torch
 import torch.distributed as dist
 
 
+def init_nccl(device_index, high_priority=True):
+    """torch.distributed over NCCL for the data-parallel learner, one process per GPU (RANK / WORLD_SIZE /
+    MASTER_* from the environment).  high_priority: NCCL's kernels run on a high-priority stream, so the
+    all-reduce of the first gradient bucket is scheduled as soon as an SM frees up under the convolution backward
+    it overlaps, instead of queueing behind that kernel's remaining CTAs."""
+    opts = None
+    if high_priority:
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            opts = None
+    dev = torch.device("cuda", int(device_index))
+    if opts is not None:
+        try:
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+            return dist.group.WORLD
+        except TypeError:
+            pass
+    dist.init_process_group("nccl", device_id=dev)
+    return dist.group.WORLD
+
+
 def shard_of_stream(stream, world):
     """Actor stream (env) id -> owning rank."""
     return int(stream) % int(world)

@@ -30,7 +30,7 @@ ALGOS = ("dqn", "mdqn", "c51", "qr", "iqn", "fqf")
 class ReplayTargetLoop:
     def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, n_step=None, double_q=True,
                  per=None, variant=0, discount=None, alpha=0.5, eps=0.01, c51=(51, -10.0, 10.0), mdqn=(0.03, -1.0),
-                 frames=None, rng_seed=None, overlap_sample_gather=True, want_prio=False):
+                 frames=None, rng_seed=None, overlap_sample_gather=True, want_prio=False, early_update=True):
         """replay: ReplayDataset (native_nstep=True when n_step > 1).  outputs: dict of STATIC f32 device
         tensors holding the network outputs of all L*B sampled transitions, batch k in rows
         [k*B, (k+1)*B): ``online``, ``tgt_next`` (+ ``qsel`` [L*B,A] under double_q / for iqn, fqf;
@@ -50,6 +50,7 @@ class ReplayTargetLoop:
         self.dev = dev = replay.device
         self.variant = int(variant)
         self.overlap_sg = bool(overlap_sample_gather) and int(variant) == 0
+        self.early_update = bool(early_update)      # step(): K2b starts under the last K4 (a0_pt_update_overlapped)
         self.rng_seed = None if rng_seed is None else int(rng_seed) & 0xFFFFFFFFFFFFFFFF
         self.n = int(n_step if n_step is not None else replay.n_gather)
         self.gamma = float(discount if discount is not None else replay.gamma)
@@ -178,9 +179,16 @@ class ReplayTargetLoop:
         self._report_dev = [(_lib.host_map(i), _lib.host_map(l)) for i, l in self.report]
         return self.report
 
-    def update(self, slot=None):
+    def update(self, slot=None, after_k4=False):
         """K2b: priority[idx] = (loss+eps)^alpha for all L batches, max_p (replay.py:55-59).  ``slot``:
         also hand indices and losses to the host through report buffer ``slot`` (bind_report)."""
+        if self.per and self.early_update and after_k4:
+            # the launch before this one is the step's last K4 and the indices were written by the draw, several
+            # launches earlier: K2b may start under that K4 (a0_pt_update_overlapped)
+            ri, rl = self._report_dev[slot] if slot is not None else (None, None)
+            _lib.check(self.lib.a0_pt_update_overlapped(self.rp.h, self.idx.data_ptr(), self.loss.data_ptr(), self.total, self.alpha,
+                                                        self.eps, ri, rl, self._st()), "a0_pt_update_overlapped")
+            return
         if self.per and slot is not None:
             ri, rl = self._report_dev[slot]
             _lib.check(self.lib.a0_pt_update_report(self.rp.h, self.idx.data_ptr(), self.loss.data_ptr(), self.total, self.alpha,
@@ -207,7 +215,7 @@ class ReplayTargetLoop:
         else:
             for k in range(self.L):
                 self.target_loss(k)
-        self.update(slot)
+        self.update(slot, after_k4=True)
 
     def capture(self, warm=3, fused_k4=False):
         """Warm up, then capture one step into a CUDA graph (returned; also kept as ``self.graph``)."""

@@ -66,7 +66,9 @@ class BaseLearner:
         self.nan_guard = not self.capturable    # agent.py:152-158 (costs one device->host sync per update)
         # one flat gradient buffer, zeroed with one memset; with a process group it is all-reduced in two pieces
         # from backward hooks, so the NCCL calls run under the convolution backward (dist.OverlappedGradBucket)
-        self.bucket = OverlappedGradBucket(list(self.model.params()), process_group) if self.world > 1 \
+        import os
+        nb = int(os.environ.get("A0_GRAD_BUCKETS", "2"))        # 1: one all-reduce after the backward pass (nothing overlapped)
+        self.bucket = OverlappedGradBucket(list(self.model.params()), process_group, n_buckets=nb) if self.world > 1 \
             else FlatGradBucket(list(self.model.params()), process_group)
 
     # ---- helpers ----------------------------------------------------------------------------------

@@ -187,24 +187,58 @@ class ReplayDataset:
             raise RuntimeError("extend() takes the reference actor's already n-step-folded entries; this shard was built "
                                "with native_nstep=True and folds n_step_q records again at gather time -- feed it with "
                                "append_steps / ShardActor instead")
-        blobs, action, reward, done = zip(*transitions)
-        if not all(type(b) is bytes for b in blobs):
-            blobs = [b if isinstance(b, (bytes, bytearray)) else np.ascontiguousarray(b, dtype=np.uint8).tobytes() for b in blobs]
-        lens = np.fromiter(map(len, blobs), dtype=np.int64, count=m)
-        joined = b"".join(blobs)
         if streams is None:
-            streams = np.arange(m, dtype=np.int64) % self.num_envs
-        streams = np.ascontiguousarray(streams, dtype=np.int64)
-        action = np.asarray(action, dtype=np.int64)
-        reward = np.asarray(reward, dtype=np.float64)
-        done = np.asarray(done, dtype=np.bool_)
+            streams = self._default_streams(m)
+        else:
+            streams = np.ascontiguousarray(streams, dtype=np.int64)
         assert len(streams) == m
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.a0_ex_extend(self._ex, joined, lens.ctypes.data, streams.ctypes.data, action.ctypes.data,
-                                             reward.ctypes.data, done.ctypes.data, m, self.alpha,
-                                             _lib.stream_ptr(self.device)), "a0_ex_extend")
+        helper = _lib.pyingest()
+        if helper is not None:
+            # the tuples are unpacked by a C loop over the list (csrc/a0_pyingest.c); the blobs are copied once,
+            # from where the actor left them into the page-locked staging block
+            w = self._unpack_ws(m, helper)
+            if helper.a0_py_unpack(transitions, m, w["ptrs"].ctypes.data, w["lens"].ctypes.data, w["action"].ctypes.data,
+                                   w["reward"].ctypes.data, w["done"].ctypes.data, w["views"].ctypes.data) != m:
+                raise RuntimeError("extend(): could not unpack the transitions")      # (a Python exception is normally set)
+            try:
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.a0_ex_extend_v(self._ex, w["ptrs"].ctypes.data, w["lens"].ctypes.data, streams.ctypes.data,
+                                                       w["action"].ctypes.data, w["reward"].ctypes.data, w["done"].ctypes.data, m,
+                                                       self.alpha, _lib.stream_ptr(self.device)), "a0_ex_extend")
+            finally:
+                helper.a0_py_release(m, w["views"].ctypes.data)
+        else:
+            blobs, action, reward, done = zip(*transitions)
+            if not all(type(b) is bytes for b in blobs):
+                blobs = [b if isinstance(b, (bytes, bytearray)) else np.ascontiguousarray(b, dtype=np.uint8).tobytes() for b in blobs]
+            lens = np.fromiter(map(len, blobs), dtype=np.int64, count=m)
+            joined = b"".join(blobs)
+            action = np.asarray(action, dtype=np.int64)
+            reward = np.asarray(reward, dtype=np.float64)
+            done = np.asarray(done, dtype=np.bool_)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.a0_ex_extend(self._ex, joined, lens.ctypes.data, streams.ctypes.data, action.ctypes.data,
+                                                 reward.ctypes.data, done.ctypes.data, m, self.alpha,
+                                                 _lib.stream_ptr(self.device)), "a0_ex_extend")
         if self.prioritize:
             self.beta = self.beta_schedule(m)
+
+    def _default_streams(self, m):
+        """entry i of an extend() call belongs to stream i % num_envs (the actor's order, agent.py:78)"""
+        s = getattr(self, "_streams_cache", None)
+        if s is None or len(s) < m:
+            s = self._streams_cache = np.arange(max(m, 4096), dtype=np.int64) % self.num_envs
+        return s[:m]
+
+    def _unpack_ws(self, m, helper):
+        w = getattr(self, "_unpack_cache", None)
+        if w is None or len(w["lens"]) < m:
+            cap = max(m, 2048)
+            w = self._unpack_cache = dict(ptrs=np.zeros(cap, dtype=np.uint64), lens=np.zeros(cap, dtype=np.int64),
+                                          action=np.zeros(cap, dtype=np.int64), reward=np.zeros(cap, dtype=np.float64),
+                                          done=np.zeros(cap, dtype=np.uint8),
+                                          views=np.zeros(cap * int(helper.a0_py_buffer_size()), dtype=np.uint8))
+        return w
 
     def extend_timing(self):
         """Microseconds of the last ``extend``: host staging, wait for the device decode + label, host

@@ -536,7 +536,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (ours) needs a GPU: there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from agent0_b200.dist import init_nccl
+        init_nccl(local, high_priority=os.environ.get("A0_NCCL_HIGH_PRIORITY", "1") != "0")
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
     def reduce_max(x):

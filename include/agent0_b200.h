@@ -97,6 +97,11 @@ const char* a0_last_error(void);
  * O(N log N) from the sorted targets (float64 prefix sums); 0 forces the O(N^2) pair loop.  The two agree to
  * ~1e-6 relative (different summation order), both within the 1e-5 contract.                          */
 #define A0_OPT_QH_SORTED 10
+/* A0_OPT_K6_SPLIT (default 1; A0_K6_SPLIT in the environment): the LZ4 decode of a0_ex_extend / a0_ex_decode runs
+ * as a producer/consumer pair of warps per entry (one parses the compressed stream and posts sequence
+ * descriptors through a shared-memory ring, the other copies); 0 selects the one-warp kernel.  Same bytes,
+ * hashes and status codes.                                                                              */
+#define A0_OPT_K6_SPLIT 11
 /* A0_OPT_MAIL_TIMEOUT_US (default 2 000 000; A0_MAIL_TIMEOUT_US in the environment): how long a gather CTA of
  * a0_rb_sample_gather polls its mailbox word before it gives up.  The paired sampler posts every word
  * within microseconds; a CTA that still has nothing after this long was launched without its sampler
@@ -211,6 +216,12 @@ int a0_ex_destroy(a0_extend_t* ex);
 int a0_ex_extend(a0_extend_t* ex, const uint8_t* blobs /* host */, const int64_t* blob_len /* host [m] */,
                  const int64_t* stream, const int64_t* action, const double* reward, const uint8_t* done,
                  int32_t m, float alpha, a0_stream_t cuda_stream);
+/* The same call with the entries where they lie: blob_ptr[i] points at entry i (e.g. the bytes objects of the
+ * reference's list), so the only copy on the host is the one into the page-locked staging block.        */
+int a0_ex_extend_v(a0_extend_t* ex, const uint8_t* const* blob_ptr /* host [m] */,
+                   const int64_t* blob_len /* host [m] */, const int64_t* stream, const int64_t* action,
+                   const double* reward, const uint8_t* done, int32_t m, float alpha,
+                   a0_stream_t cuda_stream);
 /* The decode kernel alone: frames_out dev u8[m][8][frame_bytes], status_out host i32[m] (0 = ok,
  * 1 bad size prefix, 2 truncated input, 3 output overrun, 4 bad match offset, 5 short output).      */
 int a0_ex_decode(a0_extend_t* ex, const uint8_t* blobs /* host */, const int64_t* blob_len /* host [m] */,
@@ -279,6 +290,15 @@ int a0_pt_set(a0_replay_t* h, const int64_t* idx /* dev */, const float* value /
 int a0_pt_update_report(a0_replay_t* h, const int64_t* idx /* dev */, const float* loss /* dev */,
                         int32_t count, float alpha, float eps, int64_t* idx_report /* dev-visible */,
                         float* loss_report /* dev-visible */, a0_stream_t stream);
+/* a0_pt_update[_report] for the end of a Trainer.step, where the kernel launched immediately before this call on
+ * `stream` is the last K4 and idx was written several launches earlier (by the draw): the update is launched
+ * programmatically under that kernel, loads its leaves and sorts out duplicates (positions only) while it is
+ * still running, and waits for it only where the loss values are first read.  THE CALLER GUARANTEES that idx is
+ * not produced by the immediately preceding launch on the stream (loss may be).  Report buffers optional (both
+ * or none).  Same tree, same max_p, same reports as a0_pt_update_report.                                  */
+int a0_pt_update_overlapped(a0_replay_t* h, const int64_t* idx /* dev */, const float* loss /* dev */,
+                            int32_t count, float alpha, float eps, int64_t* idx_report, float* loss_report,
+                            a0_stream_t stream);
 /* Device-visible alias of page-locked host memory (cudaHostAlloc / cudaHostRegister with mapping,
  * torch's pin_memory); fails for pageable memory.  Not a stream operation: call it once per
  * buffer, outside CUDA-graph capture.                                                          */

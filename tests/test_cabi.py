@@ -59,3 +59,38 @@ def test_sass_uses_tma_bulk_copies():
     out = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
     assert "UBLKCP" in out and "SYNCS" in out       # cp.async.bulk + mbarrier in the K3 gather
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
+
+
+def test_pyingest_helper_unpacks_the_reference_tuples():
+    """csrc/a0_pyingest.c (host glue of ReplayDataset.extend, CPython API): pointers, lengths and the three scalar
+    columns of a list of reference tuples -- bytes, bytearray and ndarray blobs, numpy and Python scalars -- and a
+    TypeError for a malformed entry."""
+    import ctypes as C
+
+    import numpy as np
+
+    from agent0_b200 import _lib, build
+    build.build_pyingest()
+    h = _lib.pyingest()
+    assert h is not None
+    rng = np.random.RandomState(0)
+    ent = []
+    for i in range(50):
+        blob = rng.randint(0, 256, rng.randint(1, 300), dtype=np.uint8)
+        ent.append(((blob.tobytes(), bytearray(blob.tobytes()), blob)[i % 3], (np.int64(i % 5), i % 5)[i % 2], (np.float64(i) / 7, i / 7)[i % 2],
+                    (np.bool_(i % 4 == 0), i % 4 == 0)[i % 2]))
+    m = len(ent)
+    ptrs = np.zeros(m, np.uint64); lens = np.zeros(m, np.int64); a = np.zeros(m, np.int64); r = np.zeros(m); d = np.zeros(m, np.uint8)
+    views = np.zeros(m * int(h.a0_py_buffer_size()), np.uint8)
+    assert h.a0_py_unpack(ent, m, ptrs.ctypes.data, lens.ctypes.data, a.ctypes.data, r.ctypes.data, d.ctypes.data, views.ctypes.data) == m
+    try:
+        for i, (blob, ai, ri, di) in enumerate(ent):
+            assert C.string_at(int(ptrs[i]), int(lens[i])) == bytes(blob)
+            assert a[i] == int(ai) and r[i] == float(ri) and d[i] == int(bool(di))
+    finally:
+        h.a0_py_release(m, views.ctypes.data)
+    import pytest
+    with pytest.raises(TypeError, match="entry 1 is not"):
+        h.a0_py_unpack([ent[0], (b"x", 1, 2.0)], 2, ptrs.ctypes.data, lens.ctypes.data, a.ctypes.data, r.ctypes.data, d.ctypes.data, views.ctypes.data)
+    with pytest.raises(TypeError):
+        h.a0_py_unpack([(b"x", "left", 2.0, False)], 1, ptrs.ctypes.data, lens.ctypes.data, a.ctypes.data, r.ctypes.data, d.ctypes.data, views.ctypes.data)
