@@ -811,18 +811,20 @@ __device__ __forceinline__ float a0_qs_pad(int idx) { return __uint_as_float(0x7
 // elements of its sibling run precede it -- binary search with a running pointer: LDS [p + imm], FSETP, predicated
 // add per step -- and moves to its rank in the merged run of 2S (returned: the thread keeps its element in a
 // register and follows its position, so no level re-reads it).  x_up = next_up(x).
+// (Indices, not pointers: with 32-bit indices into the static shared arrays every step is LDS [R + imm], FSETP and a
+// predicated add; generic 64-bit pointers cost two more instructions per step -- ncu source view.)
 template <int S_LOG>
 __device__ __forceinline__ int a0_qs_merge(const float* __restrict__ src, float* __restrict__ dst, int pos, float x, float x_up) {
   constexpr int S = 1 << S_LOG;
   const int r = pos >> S_LOG, p = pos & (S - 1);
-  const float* sib = src + ((r ^ 1) << S_LOG);
+  const int sib = (r ^ 1) << S_LOG;
   const float xc = (r & 1) ? x_up : x;            // ties: the left run's elements go first (unique ranks)
-  const float* q = sib;
+  int lo = sib;
 #pragma unroll
   for (int step = S >> 1; step > 0; step >>= 1)
-    if (q[step - 1] < xc) q += step;
-  if (q[0] < xc) ++q;
-  const int out = ((r >> 1) << (S_LOG + 1)) + p + (int)(q - sib);
+    lo += (src[lo + step - 1] < xc) ? step : 0;
+  lo += (src[lo] < xc) ? 1 : 0;
+  const int out = ((r >> 1) << (S_LOG + 1)) + p + (lo - sib);
   dst[out] = x;
   return out;
 }
@@ -842,8 +844,8 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;      // 32 * ceil(max(Ni, Nj) / 32): 7 warps for QR-200
   const int A = c.A;
-  const size_t sN_q = layout == 0 ? 1 : (size_t)A, sA_q = layout == 0 ? (size_t)Nj : 1;
-  const size_t sN_t = layout == 0 ? 1 : (size_t)A, sA_t = layout == 0 ? (size_t)Ni : 1;
+  const int sN_q = layout == 0 ? 1 : A, sA_q = layout == 0 ? Nj : 1;       // 32-bit strides inside one sample's block
+  const int sN_t = layout == 0 ? 1 : A, sA_t = layout == 0 ? Ni : 1;
   const float* qb = q + (size_t)b * A * Nj;
   const float* tb = qt + (size_t)b * A * Ni;
   // runs without threads (beyond blockDim) hold pads in both buffers: they are never moved and never counted
@@ -921,17 +923,16 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
   float lsum = 0.0f, gsum = 0.0f;
   if (tid < Nj) {
     const float qm_up = a0_qs_next_up(qj - 1.0f), qp = qj + 1.0f;
-    const float *pa = bufB, *pb = bufB, *pc = bufB;   // -> #{T <= q-1}, #{T < q}, #{T < q+1}
+    int ia = 0, ib = 0, ic = 0;                       // -> #{T <= q-1}, #{T < q}, #{T < q+1}
 #pragma unroll
     for (int step = QS_MAX >> 1; step > 0; step >>= 1) {
-      if (pa[step - 1] < qm_up) pa += step;
-      if (pb[step - 1] < qj) pb += step;
-      if (pc[step - 1] < qp) pc += step;
+      ia += (bufB[ia + step - 1] < qm_up) ? step : 0;
+      ib += (bufB[ib + step - 1] < qj) ? step : 0;
+      ic += (bufB[ic + step - 1] < qp) ? step : 0;
     }
-    if (pa[0] < qm_up) ++pa;
-    if (pb[0] < qj) ++pb;
-    if (pc[0] < qp) ++pc;
-    int ia = (int)(pa - bufB), ib = (int)(pb - bufB), ic = (int)(pc - bufB);
+    ia += (bufB[ia] < qm_up) ? 1 : 0;
+    ib += (bufB[ib] < qj) ? 1 : 0;
+    ic += (bufB[ic] < qp) ? 1 : 0;
     ia = min(ia, Ni); ib = min(max(ib, ia), Ni); ic = min(max(ic, ib), Ni);
     const double qd = (double)qj, td = (double)tau;
     const double nA = (double)ia, nB = (double)(ib - ia), nC = (double)(ic - ib), nD = (double)(Ni - ic);

@@ -739,6 +739,13 @@ def learner_scaling(args, torch, dist, world, rank, barrier, reduce_max, A, algo
         sec = timed(tr)
     out.update({"cuda_graph": graph, "ms_per_update": round(sec * 1e3, 4), "value": round(B * world / sec, 1), "unit": "transitions/s through the learner (CNN included)"})
     if world > 1:
+        # the replicas took the same steps: the bit patterns of all parameters sum to the same integer on every rank
+        bits = torch.cat([p.detach().reshape(-1) for p in tr.learner.model.parameters()]).view(torch.int32).long().sum().reshape(1)
+        lo, hi = bits.clone(), bits.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["replicas_bit_identical"] = bool(lo.item() == hi.item())
+        out["updates_taken"] = int(tr.learner.update_steps)
         bk = tr.learner.bucket
         out["allreduce_buckets_bytes"] = [int(hi - lo) * 4 for _, _, lo, hi in bk.buckets]
         del tr
