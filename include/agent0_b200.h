@@ -94,8 +94,10 @@ const char* a0_last_error(void);
 #define A0_OPT_K2B_CHUNKS 8
 /* A0_OPT_QH_SORTED (default 1; A0_QH_SORTED in the environment): a0_loss_quantile with more than 64 target
  * and more than 64 online quantiles and no FQF fraction term (QR-200) evaluates the pair sums in
- * O(N log N) from the sorted targets (float64 prefix sums); 0 forces the O(N^2) pair loop.  The two agree to
- * ~1e-6 relative (different summation order), both within the 1e-5 contract.                          */
+ * O(N log N) from the sorted targets (float64 prefix sums): 1 = one CTA per sample, merge sort in shared
+ * memory; 2 = one warp per sample, the targets sorted in registers (measured alternative: fewer instructions,
+ * longer chain, slower at batch 512); 0 forces the O(N^2) pair loop.  All
+ * agree to ~1e-6 relative (different summation order), within the 1e-5 contract.                      */
 #define A0_OPT_QH_SORTED 10
 /* A0_OPT_K6_SPLIT (default 1; A0_K6_SPLIT in the environment): the LZ4 decode of a0_ex_extend / a0_ex_decode runs
  * as a producer/consumer pair of warps per entry (one parses the compressed stream and posts sequence

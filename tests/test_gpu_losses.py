@@ -145,13 +145,13 @@ def test_c51_oracle(B, A, M, double):
     close("c51.target_prob.sum", out.target_prob.sum(-1), np.ones(B))
 
 
-@pytest.mark.parametrize("sorted_form", [1, 0], ids=["sorted", "pairwise"])
+@pytest.mark.parametrize("sorted_form", [1, 2, 0], ids=["sorted_cta", "sorted_warp", "pairwise"])
 @pytest.mark.parametrize("B,A,N,double", [(512, 4, 200, True), (16, 18, 200, False), (8, 4, 7, False), (64, 6, 256, True),
                                           (32, 4, 65, False), (40, 4, 129, True)])
 def test_qr_oracle(B, A, N, double, sorted_form):
-    """Both evaluations of the pair sums -- the O(N log N) sorted-target kernel (default above 64 quantiles)
-    and the O(N^2) pair loop -- against the pairwise numpy oracle, and the sorted kernel against its own
-    specification (oracle.losses.huber_qr_sorted, float64 prefix sums)."""
+    """All evaluations of the pair sums -- the O(N log N) sorted-target kernels (one CTA per sample: the default
+    above 64 quantiles; one warp per sample) and the O(N^2) pair loop -- against the pairwise numpy oracle, and the
+    sorted kernels against their own specification (oracle.losses.huber_qr_sorted, float64 prefix sums)."""
     from agent0_b200 import _lib
     from agent0_b200 import losses as L
     A0_OPT_QH_SORTED = 10
@@ -170,16 +170,16 @@ def test_qr_oracle(B, A, N, double, sorted_form):
     finally:
         _lib.check(_lib.load().a0_set_option(A0_OPT_QH_SORTED, 1), "a0_set_option")
     loss, grad = OL.qr(q, tn, qs if double else None, a, r, d, w, 0.99, 3)
-    tag = "sorted" if sorted_form and N > 64 else "pairwise"
+    tag = ("pairwise", "sorted, CTA per sample", "sorted, warp per sample")[sorted_form] if N > 64 else "pairwise"
     close(f"qr.loss[{tag}]", out.loss, loss); close(f"qr.grad[{tag}]", out.grad, grad)
-    if tag == "sorted":
+    if tag != "pairwise":
         bi = np.arange(B)
         a_star = np.argmax(qs, -1) if double else np.argmax(tn.mean(-1, dtype=np.float32), -1)
         T = OL._td_target(r[:, None], d[:, None], OL._G(0.99, 3), tn[bi, a_star])
         tau = ((2 * np.arange(N) + 1).astype(np.float32) / np.float32(2.0 * N)).astype(np.float32)
         l2, g2 = OL.huber_qr_sorted(q[bi, a], T, tau, w)
-        close("qr.loss[sorted vs its specification]", out.loss, l2)
-        close("qr.grad[sorted vs its specification]", out.grad.cpu().numpy()[bi, a], g2)
+        close(f"qr.loss[{tag} vs its specification]", out.loss, l2)
+        close(f"qr.grad[{tag} vs its specification]", out.grad.cpu().numpy()[bi, a], g2)
 
 
 @pytest.mark.parametrize("B,A,N,Nd", [(512, 4, 64, 64), (8, 18, 64, 32), (5, 6, 8, 24)])

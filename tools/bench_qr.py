@@ -20,7 +20,7 @@ a = torch.randint(0, A, (B,), device="cuda")
 r = torch.randn(B, device="cuda"); d = (torch.rand(B, device="cuda") < 0.1).float(); w = torch.rand(B, device="cuda") + 0.1
 gam = float(np.float32(0.99 ** 3))
 res = {}
-for name, opt in (("sorted", 1), ("pairwise", 0)):
+for name, opt in (("sorted_cta_per_sample", 1), ("sorted_warp_per_sample", 2), ("pairwise", 0)):
     lib.a0_set_option(10, opt)
     from agent0_b200.hotloop import ReplayTargetLoop  # noqa: F401  (same C entry point; here through the wrappers)
     outs = [L.qr_loss(q[i], tn[i], a, r, d, w, gam, qsel=qs[i]) for i in range(2)]
