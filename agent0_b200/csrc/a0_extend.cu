@@ -43,7 +43,7 @@ struct __align__(16) A0ExDesc {
 };
 
 enum { A0_LZ_OK = 0, A0_LZ_BAD_SIZE = 1, A0_LZ_INPUT_OVERRUN = 2, A0_LZ_OUTPUT_OVERRUN = 3, A0_LZ_BAD_OFFSET = 4,
-       A0_LZ_SHORT_OUTPUT = 5, A0_LZ_INTERNAL = 6 };
+       A0_LZ_SHORT_OUTPUT = 5 };
 
 // ------------------------------------------------------------------------------------------------
 // device: copies inside one warp.  The decoded entry lives in the CTA's dynamic shared memory; the
@@ -263,156 +263,6 @@ a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K6a, second form (default): the same decode as a PRODUCER / CONSUMER pair of warps per entry.
-// ncu on the one-warp kernel: 25 000 warp-instructions per entry -- about 140 per LZ4 sequence, half of them
-// the parse (token, length extensions, offset, bounds checks) and half the copies -- issued by ONE warp per
-// scheduler (56 KB of shared memory per entry: 4 entries per SM), i.e. at the latency of a dependent chain:
-// 17 % issue utilisation, 135 us per entry.  The parse needs none of the decoded bytes, so it moves to its own
-// warp: lane 0 of warp 0 walks the compressed stream, validates every sequence and posts
-// {literal source, literal length, match offset, match length} descriptors into a 32-entry shared-memory
-// ring; warp 1 takes them in order and does the copies with all 32 lanes.  The two chains now run
-// concurrently on different schedulers, the ring hides the jitter between them, both warps hash half of the
-// frames at the end.  Same bytes, same hashes, same status codes as the one-warp kernel (A0_OPT_K6_SPLIT = 0
-// selects it; tests run both).
-// ------------------------------------------------------------------------------------------------
-struct __align__(16) A0Seq { uint32_t lit_src, lit_len, off, ml; };     // ml == 0: last sequence; off == ~0u: error, ml = status
-constexpr int K6_RING = 32;
-constexpr uint32_t K6_ERR = 0xffffffffu;
-
-__global__ void __launch_bounds__(64)
-a0_k6_lz4_decode2(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ desc, int32_t F, uint8_t* __restrict__ dec,
-                  unsigned long long* __restrict__ hash, int32_t* __restrict__ status, int32_t sleep_ns) {
-  const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const A0ExDesc d = desc[t];
-  const uint8_t* __restrict__ in = comp + d.off;
-  const int n = d.len, total = A0_SLOTS * F;
-  A0Seq* ring = reinterpret_cast<A0Seq*>(a0_k6_out + total);
-  volatile uint32_t* cnt = reinterpret_cast<volatile uint32_t*>(ring + K6_RING);    // [0] produced, [1] consumed
-  if (threadIdx.x == 0) { cnt[0] = 0u; cnt[1] = 0u; }
-  __syncthreads();
-  int err = A0_LZ_OK;
-  if (n == total) {
-    const uint4* s = reinterpret_cast<const uint4*>(in);
-    uint4* o = reinterpret_cast<uint4*>(a0_k6_out);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < (total >> 4); i += 64) o[i] = __ldg(s + i);
-  } else if (warp == 0) {
-    // ---- producer: one lane parses and validates (every operation of the parse is scalar) ---------------------
-#pragma unroll 1
-    for (int o = lane * 128; o < n; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + o));
-    if (lane == 0) {
-      uint32_t prod = 0;
-      auto push = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t e) {
-        // (bounded: a consumer that never drains the ring -- a bug, not an input -- must not hang the device)
-        for (uint32_t spin = 0; prod - cnt[1] >= (uint32_t)K6_RING && spin < (1u << 22); ++spin)
-          if (sleep_ns) __nanosleep(sleep_ns);
-        ring[prod % K6_RING] = A0Seq{a, b, c, e};
-        __threadfence_block();
-        cnt[0] = ++prod;
-      };
-      int perr = A0_LZ_OK;
-      if (n < 5) perr = A0_LZ_BAD_SIZE;
-      else {
-        const uint32_t size = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 24);
-        if (size != (uint32_t)total) perr = A0_LZ_BAD_SIZE;
-      }
-      int ip = 4, op = 0;
-#pragma unroll 1
-      while (perr == A0_LZ_OK) {
-        if (ip >= n) { perr = A0_LZ_INPUT_OVERRUN; break; }
-        const uint32_t tok = in[ip++];
-        int ll = (int)(tok >> 4);
-        if (ll == 15) {
-          uint32_t x;
-          do {
-            if (ip >= n) { perr = A0_LZ_INPUT_OVERRUN; break; }
-            x = in[ip++];
-            ll += (int)x;
-          } while (x == 255u);
-          if (perr) break;
-        }
-        const int lit_src = ip;
-        if (ll > 0) {
-          if (ll > n - ip) { perr = A0_LZ_INPUT_OVERRUN; break; }
-          if (ll > total - op) { perr = A0_LZ_OUTPUT_OVERRUN; break; }
-          ip += ll;
-          op += ll;
-        }
-        if (ip >= n) {                               // the last sequence ends after its literals
-          if (op != total) { perr = A0_LZ_SHORT_OUTPUT; break; }
-          push((uint32_t)lit_src, (uint32_t)ll, 0u, 0u);
-          break;
-        }
-        if (n - ip < 2) { perr = A0_LZ_INPUT_OVERRUN; break; }
-        const int off = (int)in[ip] | ((int)in[ip + 1] << 8);
-        ip += 2;
-        int ml = (int)(tok & 15u);
-        if (ml == 15) {
-          uint32_t x;
-          do {
-            if (ip >= n) { perr = A0_LZ_INPUT_OVERRUN; break; }
-            x = in[ip++];
-            ml += (int)x;
-          } while (x == 255u);
-          if (perr) break;
-        }
-        ml += 4;
-        if (off == 0 || off > op) { perr = A0_LZ_BAD_OFFSET; break; }
-        if (ml > total - op) { perr = A0_LZ_OUTPUT_OVERRUN; break; }
-        push((uint32_t)lit_src, (uint32_t)ll, (uint32_t)off, (uint32_t)ml);
-        op += ml;
-      }
-      if (perr != A0_LZ_OK) push(0u, 0u, K6_ERR, (uint32_t)perr);
-    }
-  } else {
-    // ---- consumer: the copies, sequence by sequence ---------------------------------------------------------
-    uint32_t cons = 0;
-    int op = 0;
-#pragma unroll 1
-    for (;;) {
-      if (lane == 0) {
-        uint32_t spin = 0;
-        while (cnt[0] <= cons && spin < (1u << 22)) { if (sleep_ns) __nanosleep(sleep_ns); ++spin; }
-        if (cnt[0] <= cons) {                        // the producer stopped without a final descriptor: give up
-          ring[cons % K6_RING] = A0Seq{0u, 0u, K6_ERR, (uint32_t)A0_LZ_INTERNAL};
-        }
-        __threadfence_block();
-      }
-      __syncwarp();
-      const A0Seq s = ring[cons % K6_RING];
-      __syncwarp();                                // every lane holds the descriptor: its slot may be reused
-      ++cons;
-      if (lane == 0) cnt[1] = cons;
-      if (s.off == K6_ERR) { err = (int)s.ml; break; }
-      if (s.lit_len) {
-        a0_k6_copy_in(op, in + s.lit_src, (int)s.lit_len, lane);
-        op += (int)s.lit_len;
-      }
-      if (s.ml == 0u) break;
-      __syncwarp();                                // everything written so far is visible to every lane
-      a0_k6_copy_match(op, (int)s.off, (int)s.ml, lane);
-      op += (int)s.ml;
-    }
-    if (lane == 0) status[t] = err;
-  }
-  if (n == total && threadIdx.x == 0) status[t] = A0_LZ_OK;
-  __syncthreads();
-  const int nvec = F >> 4;
-#pragma unroll 1
-  for (int f = warp; f < A0_SLOTS; f += 2) {
-    const unsigned long long h = a0_k6_frame_hash(a0_k6_out + (size_t)f * F, nvec, lane);
-    if (lane == 0) hash[(size_t)t * A0_SLOTS + f] = h;
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    a0_bulk_store(dec + (size_t)t * total, a0_smem_u32(a0_k6_out), (uint32_t)total);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // K6b: canonical labels.  label[t][j] in 0..7: frame j equals frame `label` of the previous entry of its
 // stream; 8..15: equals frame label-8 of its own entry (8+j: a frame seen for the first time).  The label
 // is the FIRST byte-identical candidate in that order, so two frames are identical iff their labels are.
@@ -500,16 +350,6 @@ struct a0_extend {
   float timing[6] = {0, 0, 0, 0, 0, 0};  // last call, microseconds: stage, wait (decode+label on the device), resolve+plan,
                                          // launches, device decode+label (CUDA events), entries
 };
-
-static int g_k6_split = -1;
-static bool a0_option_k6_split() {
-  if (g_k6_split < 0) {
-    const char* e = getenv("A0_K6_SPLIT");
-    g_k6_split = e ? (atoi(e) != 0) : 0;      // measured (B200, 1280 Atari-like entries): 640 us against 320 us for the one-warp kernel
-  }
-  return g_k6_split != 0;
-}
-void a0_set_k6_split(int on) { g_k6_split = on != 0; }
 
 constexpr int32_t A0_EX_BATCH = 2048;    // entries decoded per round (scratch: 2048 * 56 448 B = 116 MB)
 
@@ -635,8 +475,6 @@ static int a0_ex_reserve(a0_extend* ex, int32_t mb, size_t stage_bytes, int32_t 
   if (!ex->smem_set) {
     A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)entry));
     A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(entry + K6_RING * sizeof(A0Seq) + 16)));
-    A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ex->smem_set = true;
   }
   return A0_OK;
@@ -664,7 +502,6 @@ static const char* a0_lz_error(int code) {
     case A0_LZ_OUTPUT_OVERRUN: return "block decodes to more than 8 frames";
     case A0_LZ_BAD_OFFSET: return "match offset points before the start of the block";
     case A0_LZ_SHORT_OUTPUT: return "block decodes to fewer than 8 frames";
-    case A0_LZ_INTERNAL: return "decoder gave up waiting for its parser (internal error)";
     default: return "unknown";
   }
 }
@@ -729,11 +566,7 @@ static int a0_ex_run_batch(a0_extend* ex, const uint8_t* blobs, const uint8_t* c
   A0_CUDA(cudaEventRecord(ex->ev0, cs));
   const A0ExDesc* d_desc = reinterpret_cast<const A0ExDesc*>(ex->d_stage + L.desc);
   int32_t* d_status = reinterpret_cast<int32_t*>(ex->d_back + (size_t)ex->cap * A0_SLOTS);
-  if (a0_option_k6_split())
-    A0_LAUNCH(a0_k6_lz4_decode2, (unsigned)mb, 64, entry + K6_RING * sizeof(A0Seq) + 16, cs, 1, 0, ex->d_stage, d_desc, ex->F, ex->d_dec,
-              ex->d_hash, d_status, (int32_t)(getenv("A0_K6_SLEEP") ? atoi(getenv("A0_K6_SLEEP")) : 0));
-  else
-    A0_LAUNCH(a0_k6_lz4_decode, (unsigned)mb, 32, entry, cs, 1, 0, ex->d_stage, d_desc, ex->F, ex->d_dec, ex->d_hash, d_status);
+  A0_LAUNCH(a0_k6_lz4_decode, (unsigned)mb, 32, entry, cs, 1, 0, ex->d_stage, d_desc, ex->F, ex->d_dec, ex->d_hash, d_status);
   if (with_labels)
     A0_LAUNCH(a0_k6_label, (unsigned)mb, K6L_THREADS, 0, cs, 1, 0, ex->d_dec, ex->d_hash, d_desc, ex->F, ex->d_tail_frames,
               ex->d_tail_hash, ex->d_back);

@@ -117,7 +117,6 @@ extern "C" int a0_set_option(int32_t option, int64_t value) {
     a0_set_qh_sorted((int)value);
     return A0_OK;
   }
-  if (option == A0_OPT_K6_SPLIT) { a0_set_k6_split(value != 0); return A0_OK; }
   if (option == A0_OPT_K3_L2) {
     A0_REQUIRE(value >= 0 && value <= 4, "a0_set_option: A0_OPT_K3_L2 must be 0..4");
     g_k3_l2 = (int)value;

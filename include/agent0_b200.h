@@ -99,11 +99,6 @@ const char* a0_last_error(void);
  * longer chain, slower at batch 512); 0 forces the O(N^2) pair loop.  All
  * agree to ~1e-6 relative (different summation order), within the 1e-5 contract.                      */
 #define A0_OPT_QH_SORTED 10
-/* A0_OPT_K6_SPLIT (default 1; A0_K6_SPLIT in the environment): the LZ4 decode of a0_ex_extend / a0_ex_decode runs
- * as a producer/consumer pair of warps per entry (one parses the compressed stream and posts sequence
- * descriptors through a shared-memory ring, the other copies); 0 selects the one-warp kernel.  Same bytes,
- * hashes and status codes.                                                                              */
-#define A0_OPT_K6_SPLIT 11
 /* A0_OPT_MAIL_TIMEOUT_US (default 2 000 000; A0_MAIL_TIMEOUT_US in the environment): how long a gather CTA of
  * a0_rb_sample_gather polls its mailbox word before it gives up.  The paired sampler posts every word
  * within microseconds; a CTA that still has nothing after this long was launched without its sampler

@@ -420,3 +420,29 @@ def test_unpaired_mailbox_gather_times_out_instead_of_hanging():
         assert b.frames.shape[0] == 16 and int(b.indices.min()) >= 0
     finally:
         _lib.check(lib.a0_set_option(A0_OPT_MAIL_TIMEOUT_US, 2000000), "a0_set_option")
+
+
+def test_views_of_shard_memory_keep_the_shard_alive():
+    """replay.frames / tree / max_p_tensor are torch views of handle-owned device memory: a tensor handed to a learner
+    or cached in a captured graph must keep the allocation alive after the ReplayDataset object is gone
+    (a0_rb_destroy runs when the last view dies, _lib.HandleOwner)."""
+    import gc
+    import weakref
+
+    from agent0_b200.replay import ReplayDataset
+    from agent0_b200.synth import fill_shard_synthetic
+    cfg = make_config("c51", per=True, n_step=1, batch_size=8, replay_size=256, num_envs=2)
+    rp = ReplayDataset(cfg, native_nstep=True)
+    fill_shard_synthetic(rp, 128, 2, 3)
+    owner = weakref.ref(rp._owner)
+    max_p, leaves = rp.max_p_tensor, rp.priority.leaves()
+    want = leaves.clone()
+    del rp
+    gc.collect()
+    assert owner() is not None                              # the views hold the handle
+    max_p.fill_(3.0)
+    torch.cuda.synchronize()
+    assert float(max_p.item()) == 3.0 and torch.equal(leaves, want)
+    del max_p, leaves
+    gc.collect()
+    assert owner() is None                                   # last view gone: the shard has been destroyed
