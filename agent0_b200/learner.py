@@ -50,9 +50,14 @@ class BaseLearner:
             raise RuntimeError("agent0_b200 learners run their target/loss rules in CUDA kernels; "
                                "there is no CPU path (use the reference learner on CPU)")
         self.model = DeepQNet(cfg).to(self.device)
-        self.model_target = copy.deepcopy(self.model)       # agent.py:100 (no RNG consumed)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        if self.world > 1:
+            # data-parallel replicas start from rank 0's weights (whatever each process's RNG drew), then stay
+            # identical because every step applies the same all-reduced gradient
+            from .actor import broadcast_model
+            broadcast_model(self.model, src=0, process_group=process_group)
+        self.model_target = copy.deepcopy(self.model)       # agent.py:100 (no RNG consumed)
         self.optimizer = torch.optim.Adam(list(self.model.params()), cfg.learner.learning_rate,
                                           eps=adam_eps(cfg.learner.batch_size, self.world), capturable=self.capturable)
         if self.capturable:
