@@ -143,6 +143,7 @@ void a0_set_c51_fast(int on);
 void a0_set_k2b_small(int on);
 void a0_set_k2b_chunks(int on);
 void a0_set_qh_sorted(int on);
+void a0_set_k6_global(int on);
 
 // (Measured alternative: launch_dependents BEFORE the wait lets a whole chain of dependent kernels
 // become resident launches ahead.  It does not lower the ~2.85 us per-link cost of the batch-32 K4

@@ -51,23 +51,28 @@ enum { A0_LZ_OK = 0, A0_LZ_BAD_SIZE = 1, A0_LZ_INPUT_OVERRUN = 2, A0_LZ_OUTPUT_O
 // address inside every loop iteration: S2R SR_CgaCtaId + LEA per byte, ncu source view).
 // ------------------------------------------------------------------------------------------------
 extern __shared__ __align__(128) uint8_t a0_k6_out[];
+// K6_AT(i): byte i of the entry being decoded -- in the CTA's shared memory (GLOBAL = false, the default kernel) or
+// straight in the scratch buffer in HBM/L2 (GLOBAL = true, the all-entries-resident variant below)
+#define K6_AT(i) (*(GLOBAL ? gout + (i) : a0_k6_out + (i)))
+#define K6_PTR(i) (GLOBAL ? gout + (i) : a0_k6_out + (i))
 
 // `len` literal bytes from the compressed stream (global memory, any alignment) to out[op..]
-__device__ __forceinline__ void a0_k6_copy_in(int op, const uint8_t* __restrict__ src, int len, int lane) {
+template <bool GLOBAL>
+__device__ __forceinline__ void a0_k6_copy_in(uint8_t* gout, int op, const uint8_t* __restrict__ src, int len, int lane) {
   if (len < 128) {
 #pragma unroll 2
-    for (int i = lane; i < len; i += 32) a0_k6_out[op + i] = src[i];
+    for (int i = lane; i < len; i += 32) K6_AT(op + i) = src[i];
     return;
   }
   // destination-aligned 32-bit words; a source word is assembled from two aligned loads
   const int head = (4 - (op & 3)) & 3;
-  if (lane < head) a0_k6_out[op + lane] = src[lane];
+  if (lane < head) K6_AT(op + lane) = src[lane];
   const uint8_t* s2 = src + head;
   const int d2 = op + head, rem = len - head, nw = rem >> 2;
   const uintptr_t sa = (uintptr_t)s2;
   const uint32_t sh = (uint32_t)(sa & 3) * 8;
   const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(sa & ~(uintptr_t)3);
-  uint32_t* dw = reinterpret_cast<uint32_t*>(a0_k6_out + d2);
+  uint32_t* dw = reinterpret_cast<uint32_t*>(K6_PTR(d2));
   if (sh == 0) {
 #pragma unroll 4
     for (int k = lane; k < nw; k += 32) dw[k] = sw[k];
@@ -76,26 +81,27 @@ __device__ __forceinline__ void a0_k6_copy_in(int op, const uint8_t* __restrict_
     for (int k = lane; k < nw; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], sh);
   }
   const int tail = rem & 3;
-  if (lane < tail) a0_k6_out[d2 + 4 * nw + lane] = s2[4 * nw + lane];
+  if (lane < tail) K6_AT(d2 + 4 * nw + lane) = s2[4 * nw + lane];
 }
 
 // LZ4 match: `ml` bytes from out[op - off ..] to out[op ..]; the ranges overlap when off < ml (the
 // copy then repeats the last `off` bytes).  Everything before `op` is visible (the caller synchronised).
-__device__ __forceinline__ void a0_k6_copy_match(int op, int off, int ml, int lane) {
+template <bool GLOBAL>
+__device__ __forceinline__ void a0_k6_copy_match(uint8_t* gout, int op, int off, int ml, int lane) {
   const int sp = op - off;
   if (off >= ml) {
     // disjoint ranges: no ordering needed between iterations
     if (ml < 128) {
 #pragma unroll 2
-      for (int i = lane; i < ml; i += 32) a0_k6_out[op + i] = a0_k6_out[sp + i];
+      for (int i = lane; i < ml; i += 32) K6_AT(op + i) = K6_AT(sp + i);
       return;
     }
     const int head = (4 - (op & 3)) & 3;
-    if (lane < head) a0_k6_out[op + lane] = a0_k6_out[sp + lane];
+    if (lane < head) K6_AT(op + lane) = K6_AT(sp + lane);
     const int d2 = op + head, s2 = sp + head, rem = ml - head, nw = rem >> 2;
     const uint32_t sh = (uint32_t)(s2 & 3) * 8;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(a0_k6_out + (s2 & ~3));
-    uint32_t* dw = reinterpret_cast<uint32_t*>(a0_k6_out + d2);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(K6_PTR((s2 & ~3)));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(K6_PTR(d2));
     // with sh != 0 the second source word of the last destination words may already be destination (off >= ml
     // only keeps the bytes that are USED in front of op): the bytes taken from it lie before op, the rest of
     // the word is shifted out, so reading it early or late is harmless
@@ -110,7 +116,7 @@ __device__ __forceinline__ void a0_k6_copy_match(int op, int off, int ml, int la
       }
     }
     const int tail = rem & 3;
-    if (lane < tail) a0_k6_out[d2 + 4 * nw + lane] = a0_k6_out[s2 + 4 * nw + lane];
+    if (lane < tail) K6_AT(d2 + 4 * nw + lane) = K6_AT(s2 + 4 * nw + lane);
     return;
   }
   // Overlapping match: the output repeats the `off` bytes in front of op, which are complete, so byte i
@@ -121,14 +127,14 @@ __device__ __forceinline__ void a0_k6_copy_match(int op, int off, int ml, int la
     const int head = (4 - (op & 3)) & 3;
     uint32_t w = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w |= (uint32_t)a0_k6_out[sp + ((head + q) & (off - 1))] << (8 * q);
+    for (int q = 0; q < 4; ++q) w |= (uint32_t)K6_AT(sp + ((head + q) & (off - 1))) << (8 * q);
     const int d2 = op + head, rem = ml - head, nw = rem >> 2;
     const int tail = rem & 3;
-    if (lane < head) a0_k6_out[op + lane] = (uint8_t)(w >> (8 * ((lane + 4 - head) & 3)));
-    uint32_t* dw = reinterpret_cast<uint32_t*>(a0_k6_out + d2);
+    if (lane < head) K6_AT(op + lane) = (uint8_t)(w >> (8 * ((lane + 4 - head) & 3)));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(K6_PTR(d2));
 #pragma unroll 4
     for (int k = lane; k < nw; k += 32) dw[k] = w;
-    if (lane < tail) a0_k6_out[d2 + 4 * nw + lane] = (uint8_t)(w >> (8 * lane));
+    if (lane < tail) K6_AT(d2 + 4 * nw + lane) = (uint8_t)(w >> (8 * lane));
     return;
   }
   int s, step;
@@ -136,7 +142,7 @@ __device__ __forceinline__ void a0_k6_copy_match(int op, int off, int ml, int la
   else { s = lane % off; step = 32 % off; }
 #pragma unroll 4
   for (int i = lane; i < ml; i += 32) {
-    a0_k6_out[op + i] = a0_k6_out[sp + s];
+    K6_AT(op + i) = K6_AT(sp + s);
     s += step;
     if (s >= off) s -= off;
   }
@@ -176,18 +182,24 @@ __device__ __forceinline__ unsigned long long a0_k6_frame_hash(const uint8_t* fr
 // ------------------------------------------------------------------------------------------------
 // K6a: LZ4 block decode, one warp per reference entry
 // ------------------------------------------------------------------------------------------------
+// GLOBAL = false (default): the entry is decoded in shared memory and leaves as one bulk copy.  GLOBAL = true
+// (A0_OPT_K6_GLOBAL): it is decoded in place in the scratch buffer -- matches read back what the warp just wrote,
+// through L1/L2 -- which needs no shared memory, so ALL entries of a call are resident at once (8-9 warps per SM
+// instead of 4) at the price of a longer round trip per match.
+template <bool GLOBAL>
 __global__ void __launch_bounds__(32)
-a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ desc, int32_t F, uint8_t* __restrict__ dec,
-                 unsigned long long* __restrict__ hash, int32_t* __restrict__ status) {
+a0_k6_lz4_decode_t(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ desc, int32_t F, uint8_t* __restrict__ dec,
+                   unsigned long long* __restrict__ hash, int32_t* __restrict__ status) {
   const int t = blockIdx.x, lane = threadIdx.x;
   const A0ExDesc d = desc[t];
   const uint8_t* __restrict__ in = comp + d.off;
   const int n = d.len, total = A0_SLOTS * F;
+  uint8_t* gout = dec + (size_t)t * total;
   int err = A0_LZ_OK;
   if (n == total) {
     // raw entry (ndarray / bytes of the decoded size): blob starts are 16-byte aligned in the staged block
     const uint4* s = reinterpret_cast<const uint4*>(in);
-    uint4* o = reinterpret_cast<uint4*>(a0_k6_out);
+    uint4* o = reinterpret_cast<uint4*>(K6_PTR(0));
 #pragma unroll 4
     for (int i = lane; i < (total >> 4); i += 32) o[i] = __ldg(s + i);
   } else {
@@ -217,7 +229,7 @@ a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ 
       if (ll > 0) {
         if (ll > n - ip) { err = A0_LZ_INPUT_OVERRUN; break; }
         if (ll > total - op) { err = A0_LZ_OUTPUT_OVERRUN; break; }
-        a0_k6_copy_in(op, in + ip, ll, lane);
+        a0_k6_copy_in<GLOBAL>(gout, op, in + ip, ll, lane);
         ip += ll;
         op += ll;
       }
@@ -239,7 +251,7 @@ a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ 
       if (off == 0 || off > op) { err = A0_LZ_BAD_OFFSET; break; }
       if (ml > total - op) { err = A0_LZ_OUTPUT_OVERRUN; break; }
       __syncwarp();                              // everything written so far is visible to every lane
-      a0_k6_copy_match(op, off, ml, lane);
+      a0_k6_copy_match<GLOBAL>(gout, op, off, ml, lane);
       op += ml;
     }
     if (err == A0_LZ_OK && op != total) err = A0_LZ_SHORT_OUTPUT;
@@ -249,18 +261,20 @@ a0_k6_lz4_decode(const uint8_t* __restrict__ comp, const A0ExDesc* __restrict__ 
   const int nvec = F >> 4;
 #pragma unroll 1
   for (int f = 0; f < A0_SLOTS; ++f) {
-    const unsigned long long h = a0_k6_frame_hash(a0_k6_out + (size_t)f * F, nvec, lane);
+    const unsigned long long h = a0_k6_frame_hash(K6_PTR((size_t)f * F), nvec, lane);
     if (lane == 0) hash[(size_t)t * A0_SLOTS + f] = h;
   }
+  if (GLOBAL) return;                              // decoded in place
   // the whole entry leaves the SM as one bulk copy (shared -> global through the async proxy)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
   if (lane == 0) {
-    a0_bulk_store(dec + (size_t)t * total, a0_smem_u32(a0_k6_out), (uint32_t)total);
+    a0_bulk_store(gout, a0_smem_u32(a0_k6_out), (uint32_t)total);
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // K6b: canonical labels.  label[t][j] in 0..7: frame j equals frame `label` of the previous entry of its
@@ -350,6 +364,16 @@ struct a0_extend {
   float timing[6] = {0, 0, 0, 0, 0, 0};  // last call, microseconds: stage, wait (decode+label on the device), resolve+plan,
                                          // launches, device decode+label (CUDA events), entries
 };
+
+static int g_k6_global = -1;
+static bool a0_option_k6_global() {
+  if (g_k6_global < 0) {
+    const char* e = getenv("A0_K6_GLOBAL");
+    g_k6_global = e ? (atoi(e) != 0) : 0;
+  }
+  return g_k6_global != 0;
+}
+void a0_set_k6_global(int on) { g_k6_global = on != 0; }
 
 constexpr int32_t A0_EX_BATCH = 2048;    // entries decoded per round (scratch: 2048 * 56 448 B = 116 MB)
 
@@ -473,8 +497,8 @@ static int a0_ex_reserve(a0_extend* ex, int32_t mb, size_t stage_bytes, int32_t 
     ex->d_tail_frames = nf; ex->d_tail_hash = nh; ex->slot_cap = cap;
   }
   if (!ex->smem_set) {
-    A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)entry));
-    A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)entry));
+    A0_CUDA(cudaFuncSetAttribute(a0_k6_lz4_decode_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ex->smem_set = true;
   }
   return A0_OK;
@@ -566,7 +590,10 @@ static int a0_ex_run_batch(a0_extend* ex, const uint8_t* blobs, const uint8_t* c
   A0_CUDA(cudaEventRecord(ex->ev0, cs));
   const A0ExDesc* d_desc = reinterpret_cast<const A0ExDesc*>(ex->d_stage + L.desc);
   int32_t* d_status = reinterpret_cast<int32_t*>(ex->d_back + (size_t)ex->cap * A0_SLOTS);
-  A0_LAUNCH(a0_k6_lz4_decode, (unsigned)mb, 32, entry, cs, 1, 0, ex->d_stage, d_desc, ex->F, ex->d_dec, ex->d_hash, d_status);
+  if (a0_option_k6_global())
+    A0_LAUNCH(a0_k6_lz4_decode_t<true>, (unsigned)mb, 32, 0, cs, 1, 0, ex->d_stage, d_desc, ex->F, ex->d_dec, ex->d_hash, d_status);
+  else
+    A0_LAUNCH(a0_k6_lz4_decode_t<false>, (unsigned)mb, 32, entry, cs, 1, 0, ex->d_stage, d_desc, ex->F, ex->d_dec, ex->d_hash, d_status);
   if (with_labels)
     A0_LAUNCH(a0_k6_label, (unsigned)mb, K6L_THREADS, 0, cs, 1, 0, ex->d_dec, ex->d_hash, d_desc, ex->F, ex->d_tail_frames,
               ex->d_tail_hash, ex->d_back);

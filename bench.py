@@ -614,6 +614,7 @@ def run_ours(args):
     extra, configs, ext = {}, [], None
     if world > 1:
         extra["grad_allreduce"] = grad_allreduce_probe(torch, dist, world, barrier, L)
+        extra["weight_broadcast"] = weight_broadcast_probe(torch, dist, world, barrier, A)
     if not args.no_extra and rank == 0 and world == 1:
         entries = reference_entries(5 * 1280, wl["n"])
         ext = e2e_extend(wl, L, A, max(4, min(args.steps, 20)), torch, args.min_seconds, entries)
@@ -784,6 +785,30 @@ def grad_allreduce_probe(torch, dist, world, barrier, L):
     return {"bytes": bucket.numel() * 4, "us_per_call": round(us, 2),
             "bus_GBps": round(2 * (world - 1) / world * bucket.numel() * 4 / (us * 1e-6) / 1e9, 1),
             "per_step_us_if_not_overlapped": round(us * L, 1)}
+
+
+def weight_broadcast_probe(torch, dist, world, barrier, A):
+    """SURVEY 8f-3 on hardware: the learner's weights handed to the other ranks (where on-box actors hold their copy of the
+    net) with ONE flat NCCL broadcast (actor.broadcast_model) instead of a pickled state_dict per actor call
+    (agent0/deepq/launch.py:33-36,56-61).  C51 dueling net, device time, max over ranks."""
+    from agent0_b200.actor import broadcast_model
+    from agent0_b200.config import make_config
+    from agent0_b200.model import DeepQNet
+    model = DeepQNet(make_config("c51", dueling=True, action_dim=A)).cuda()
+    sent = 0
+    for _ in range(3):
+        sent = broadcast_model(model, src=0, process_group=dist.group.WORLD)
+    torch.cuda.synchronize(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        broadcast_model(model, src=0, process_group=dist.group.WORLD)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 20 * 1e3], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    us = float(t.item())
+    return {"bytes": int(sent), "us_per_broadcast": round(us, 1), "GBps": round(sent / (us * 1e-6) / 1e9, 1),
+            "note": "pack (torch.cat) + one NCCL broadcast + unpack in place; the reference pickles a state_dict over courier RPC per actor call"}
 
 
 def time_workload(rp, name, args, torch, peak, L, A):

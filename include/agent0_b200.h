@@ -99,6 +99,11 @@ const char* a0_last_error(void);
  * longer chain, slower at batch 512); 0 forces the O(N^2) pair loop.  All
  * agree to ~1e-6 relative (different summation order), within the 1e-5 contract.                      */
 #define A0_OPT_QH_SORTED 10
+/* A0_OPT_K6_GLOBAL (default 0; A0_K6_GLOBAL in the environment): the LZ4 decode of a0_ex_extend / a0_ex_decode
+ * writes its output in place in the scratch buffer (matches read back through L1/L2) instead of staging the
+ * entry in shared memory: no shared memory, so every entry of a call is resident at once.  Same bytes, hashes
+ * and status codes.                                                                                    */
+#define A0_OPT_K6_GLOBAL 11
 /* A0_OPT_MAIL_TIMEOUT_US (default 2 000 000; A0_MAIL_TIMEOUT_US in the environment): how long a gather CTA of
  * a0_rb_sample_gather polls its mailbox word before it gives up.  The paired sampler posts every word
  * within microseconds; a CTA that still has nothing after this long was launched without its sampler

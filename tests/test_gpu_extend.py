@@ -50,8 +50,20 @@ def _random_sequences(rng, total, periods):
     return seqs
 
 
+A0_OPT_K6_GLOBAL = 11
+
+
+@pytest.fixture(params=[0, 1], ids=["shared_memory", "in_place"])
+def k6_kernel(request):
+    """Both forms of the decode kernel: output staged in shared memory (default) and decoded in place in the scratch."""
+    from agent0_b200 import _lib
+    _lib.check(_lib.load().a0_set_option(A0_OPT_K6_GLOBAL, request.param), "a0_set_option")
+    yield request.param
+    _lib.check(_lib.load().a0_set_option(A0_OPT_K6_GLOBAL, 0), "a0_set_option")
+
+
 @pytest.mark.parametrize("hw", [(84, 84), (16, 16), (8, 8)])
-def test_decode_equals_the_oracle(hw):
+def test_decode_equals_the_oracle(hw, k6_kernel):
     """liblz4-compressed entries (synthetic Atari-like stacks, noise, constant screens) and hand-built
     blocks -- overlapping matches of every period 1..40 and beyond, long literal and match runs, length
     fields on every extension boundary, raw (uncompressed) entries -- decode to the oracle's bytes."""
@@ -81,7 +93,7 @@ def test_decode_equals_the_oracle(hw):
         assert got[i].tobytes() == w, f"entry {i} differs"
 
 
-def test_decode_reports_malformed_blocks():
+def test_decode_reports_malformed_blocks(k6_kernel):
     hw = (8, 8)
     total = 8 * 64
     rp = _replay(64, hw=hw)
