@@ -125,7 +125,8 @@ def test_decode_reports_malformed_blocks(k6_kernel):
     assert rp.top == 1
 
 
-@pytest.mark.parametrize("n,N,age,calls", [(3, 4096, None, (1280, 640, 37, 1, 300)), (1, 96, 12, (50, 7, 120, 33, 200, 64))])
+@pytest.mark.parametrize("n,N,age,calls", [(3, 4096, None, (1280, 640, 37, 1, 300)), (1, 96, 12, (50, 7, 120, 33, 200, 64)),
+                                          (3, 8192, None, (2500, 100))])      # 2500 > 2048: two decode batches inside one call
 def test_extend_takes_the_decisions_of_the_host_deduper(n, N, age, calls):
     """The same lz4 entries through ReplayDataset.extend (device decode + labels + a0_ex_resolve) and
     through the host specification (liblz4 decode + a0_dd_resolve + a0_ix_plan on a twin index): the same
