@@ -16,6 +16,7 @@ A0_MAX_NSTEP = 16
 A0_MAX_ACTIONS = 32
 A0_MAX_QUANTILES = 256
 PTR_FRAMES, PTR_REC_SLOTS, PTR_REC_INFO, PTR_TREE, PTR_MAX_P = range(5)
+OPT_PDL = 1          # include/agent0_b200.h: A0_OPT_PDL (mask of kernel classes launched programmatically; bit 0 = K4)
 
 _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
@@ -42,6 +43,7 @@ SIGNATURES = {
     "a0_version": (_i32, []),
     "a0_last_error": (C.c_char_p, []),
     "a0_set_option": (_i32, [_i32, _i64]),
+    "a0_get_option": (_i32, [_i32, C.POINTER(C.c_int64)]),
     "a0_rb_create": (_i32, [C.POINTER(_vp), _i64, _i64, _i32, _i32]),
     "a0_rb_destroy": (_i32, [_vp]),
     "a0_rb_reset": (_i32, [_vp, _vp]),
@@ -82,6 +84,8 @@ SIGNATURES = {
     "a0_rb_gather": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "a0_rb_sample_gather": (_i32, [_vp, _vp, C.c_uint64, _i64, _i32, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _i32, _f64,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "a0_rb_sample_mail": (_i32, [_vp, _vp, C.c_uint64, _i64, _i32, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "a0_rb_gather_mail": (_i32, [_vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "a0_rb_gather_unpaired": (_i32, [_vp, _i32, _vp, _vp]),
     "a0_rb_check_fault": (_i32, [_vp]),
     "a0_rb_gather_f32": (_i32, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

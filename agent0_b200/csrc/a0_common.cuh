@@ -50,6 +50,8 @@ struct a0_replay {
                               // (0: not uniform); lets K3 fetch an n-step window without chasing links
   long long* mail;            // [mail_cap] sampler -> gather mailbox of a0_rb_sample_gather: draw g's record
   int64_t mail_cap;           // position + 1, 0 = empty; every word is consumed (reset) by the gather CTA
+  int64_t mail_total;         // draws of the last a0_rb_sample_mail (its gather waves pick their L2 policy by the whole draw)
+  int32_t progress_dirty;     // a windowed gather wave failed to launch: the next a0_rb_sample_mail re-arms the progress word
   int32_t* fault_host;        // mapped page-locked word a kernel sets when it gives up (mailbox wait timed out);
   int32_t* fault_dev;         // the next host call on the handle reports and clears it (a0_check_fault)
 };
@@ -142,6 +144,7 @@ bool a0_option_fused_ingest();
 void a0_set_c51_fast(int on);
 void a0_set_k2b_small(int on);
 void a0_set_k2b_chunks(int on);
+void a0_set_k2b_sparse(int max_paths);
 void a0_set_qh_sorted(int on);
 void a0_set_k6_global(int on);
 
@@ -261,7 +264,8 @@ struct A0GatherOut {
   int64_t* boot;
 };
 int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int32_t count, int32_t n_step, double gamma,
-                          const A0GatherOut& out, cudaStream_t stream);
+                          const A0GatherOut& out, cudaStream_t stream, int64_t policy_count = 0, int32_t window = 0, int32_t gbase = 0);
+constexpr int A0_K3_PROGRESS = 2 * A0_MAX_BATCHES + 40;      // counter[] word: completed draws of the current windowed gather
 int a0_mail_reserve(a0_replay* h, int32_t total, cudaStream_t stream);
 
 __device__ __forceinline__ uint32_t a0_smem_u32(const void* p) {

@@ -102,6 +102,13 @@ bool a0_option_fused_ingest() {
   }
   return g_fused_ingest != 0;
 }
+extern "C" int a0_get_option(int32_t option, int64_t* value) {
+  A0_REQUIRE(value != nullptr, "a0_get_option: value is NULL");
+  if (option == A0_OPT_PDL) { a0_pdl_enabled(0); *value = g_pdl; return A0_OK; }      // resolves the environment default first
+  a0_set_error("a0_get_option: option %d cannot be read back", option);
+  return A0_EINVAL;
+}
+
 extern "C" int a0_set_option(int32_t option, int64_t value) {
   if (option == A0_OPT_FUSED_INGEST) { g_fused_ingest = value != 0; return A0_OK; }
   if (option == A0_OPT_MAIL_TIMEOUT_US) {
@@ -112,6 +119,11 @@ extern "C" int a0_set_option(int32_t option, int64_t value) {
   if (option == A0_OPT_C51_FAST) { a0_set_c51_fast(value != 0); return A0_OK; }
   if (option == A0_OPT_K2B_SMALL) { a0_set_k2b_small(value != 0); return A0_OK; }
   if (option == A0_OPT_K2B_CHUNKS) { a0_set_k2b_chunks(value != 0); return A0_OK; }
+  if (option == A0_OPT_K2B_SPARSE) {
+    A0_REQUIRE(value >= 0 && value <= 32, "a0_set_option: A0_OPT_K2B_SPARSE must be 0..32");
+    a0_set_k2b_sparse((int)value);
+    return A0_OK;
+  }
   if (option == A0_OPT_K6_GLOBAL) { a0_set_k6_global(value != 0); return A0_OK; }
   if (option == A0_OPT_QH_SORTED) {
     A0_REQUIRE(value >= 0 && value <= 2, "a0_set_option: A0_OPT_QH_SORTED must be 0, 1 or 2");
@@ -148,6 +160,7 @@ __global__ void a0_fill_i32(int32_t* p, int64_t n, int32_t v) {
 }
 __global__ void a0_init_scalars(float* max_p) {
   *max_p = 1.0f;
+  for (int i = 1; i < 16; ++i) max_p[i] = 0.0f;              // padding up to the dyn words: defined, so shard states compare
   max_p[16] = 0.0f; max_p[17] = 1.0f; max_p[18] = 0.0f;     // dyn = {top, beta, sum_offset}
 }
 
@@ -322,6 +335,12 @@ struct A0GatherArgs {
   int32_t* fault;        // mapped host word: set to 1 by a CTA whose mailbox word never arrived
   unsigned long long mail_timeout_ns;
   int32_t l2_hints;      // bit 0: frame reads evict_first, bit 1: output stores evict_first (A0_OPT_K3_L2)
+  // ordered fetch (a0_rb_gather_mail with a window): draw gbase + blockIdx.x starts its frame traffic only when at most
+  // `window` draws beyond the completed ones are in flight, so the FIRST batches of a draw complete first instead of all
+  // resident CTAs sharing the bandwidth and finishing together.  progress counts completed draws of the whole sampler
+  // call (gtotal); the last one re-arms it.
+  unsigned int* progress;
+  int32_t window, gbase, gtotal;
 };
 
 // Walks the n-step window that starts at record p0 (whose info word is already loaded), writes
@@ -544,6 +563,27 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   const A0RecInfo info0 = g.rec_info[p0];
   A0Spec sp;
   a0_spec_fetch(g, p0, sp);              // the guessed rest of the window, same round trip as the first record
+  if (g.progress && g.window > 0) {
+    // the record loads above are in flight; the frame traffic waits for this draw's turn.  Bounded like the mailbox
+    // poll: giving up only costs the ordering, not the result.
+    const int need = g.gbase + b - g.window + 1;
+    if (need > 0) {
+      unsigned long long t_start = 0;
+      unsigned spins = 0;
+      for (;;) {
+        unsigned int done;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(g.progress) : "memory");
+        if ((int)done >= need) break;
+        __nanosleep(32);
+        if ((++spins & 255u) == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t_start == 0) t_start = now;
+          else if (now - t_start > g.mail_timeout_ns) break;
+        }
+      }
+    }
+  }
   const uint64_t pol = a0_policy_evict_first();
   const bool hint_ld = g.l2_hints & 1, hint_st = g.l2_hints & 2;
   auto load = [&](uint32_t dst, const void* src, uint32_t bar) {
@@ -607,6 +647,10 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
     }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (g.progress) {
+    const unsigned int old = atomicAdd(g.progress, 1u);
+    if (old == (unsigned int)g.gtotal - 1u) *reinterpret_cast<volatile unsigned int*>(g.progress) = 0u;   // every draw done: nobody polls any more
+  }
   A0_TEND(3);
   if (g.mail) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
@@ -947,6 +991,7 @@ static int a0_gather_cvt(a0_replay_t* h, const int64_t* idx, int32_t count, int3
   g.frames_out = nullptr; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
   g.mail = nullptr; g.fault = nullptr; g.mail_timeout_ns = 0;
+  g.progress = nullptr; g.window = 0; g.gbase = 0; g.gtotal = 0;
   g.l2_hints = 0;
   const size_t smem = (size_t)K3_RING * h->F;
   static thread_local size_t configured[64] = {0};       // one table per OutT instantiation
@@ -988,7 +1033,7 @@ static int a0_k3_smem_attr(a0_replay_t* h, size_t smem) {
 // The gather half of a0_rb_sample_gather: variant 0 taking its record positions from the mailbox, always
 // launched with programmatic stream serialization so that it becomes resident under the sampler.
 int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int32_t count, int32_t n_step, double gamma,
-                          const A0GatherOut& out, cudaStream_t stream) {
+                          const A0GatherOut& out, cudaStream_t stream, int64_t policy_count, int32_t window, int32_t gbase) {
   A0GatherArgs g;
   g.frames = h->frames; g.rec_slots = h->rec_slots; g.rec_info = h->rec_info; g.idx = idx;
   g.N = h->N; g.NF = h->NF; g.F = h->F; g.count = count; g.n_step = n_step; g.gamma = gamma;
@@ -996,9 +1041,12 @@ int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int
   g.frames_out = out.frames; g.action_out = out.action; g.reward64_out = out.reward64;
   g.reward32_out = out.reward32; g.done8_out = out.done8; g.done32_out = out.done32; g.boot_out = out.boot;
   g.mail = mail;
+  g.progress = window > 0 ? h->counter + A0_K3_PROGRESS : nullptr;
+  g.window = window; g.gbase = gbase; g.gtotal = (int32_t)policy_count;
   g.fault = h->fault_dev;
   g.mail_timeout_ns = a0_option_mail_timeout_ns();
-  g.l2_hints = a0_option_k3_l2((int64_t)count * 16 * h->F);
+  // a wave of a larger draw (a0_rb_gather_mail) takes the L2 policy of the whole draw
+  g.l2_hints = a0_option_k3_l2((policy_count > count ? policy_count : (int64_t)count) * 16 * h->F);
   const size_t smem = (size_t)K3_RING * h->F;
   int rc = a0_k3_smem_attr(h, smem);
   if (rc) return rc;
@@ -1036,6 +1084,7 @@ extern "C" int a0_rb_gather(a0_replay_t* h, const int64_t* idx, int32_t count, i
   g.frames_out = frames_out; g.action_out = action_out; g.reward64_out = reward64_out;
   g.reward32_out = reward32_out; g.done8_out = done8_out; g.done32_out = done32_out; g.boot_out = boot_out;
   g.mail = nullptr; g.fault = nullptr; g.mail_timeout_ns = 0;
+  g.progress = nullptr; g.window = 0; g.gbase = 0; g.gtotal = 0;
   g.l2_hints = a0_option_k3_l2((int64_t)count * 16 * h->F);
   if (variant == 3) {
     const size_t smem = (size_t)K3S_RING * h->F;

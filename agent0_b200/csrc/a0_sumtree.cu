@@ -340,6 +340,68 @@ extern "C" int a0_rb_sample_gather(a0_replay_t* h, const float* u, uint64_t seed
   return rc;
 }
 
+// The same pair with the gather cut into WAVES (consecutive ranges of the draw, one launch each), so that a
+// consumer on another stream can start on the first batches while the later ones are still being fetched:
+//   a0_rb_sample_mail            the sampler, posting every draw's record position to the mailbox
+//   a0_rb_gather_mail (x waves)  draws [lo, lo + count): launched programmatically under its predecessor on the
+//                                stream (the sampler or the previous wave), fed through the mailbox
+// Every wave lets its successor launch at once and ends with griddepcontrol.wait, so waves complete in launch
+// order and "wave j complete" implies "sampler complete" (weights) and "waves < j complete".
+extern "C" int a0_rb_sample_mail(a0_replay_t* h, const float* u, uint64_t seed, int64_t call, int32_t total,
+                                 int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
+                                 int64_t* idx_out, float* prio_out, float* weight_out, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_sample_mail: handle is NULL");
+  A0_REQUIRE(total >= 0 && batch > 0 && total % batch == 0, "a0_rb_sample_mail: total %d must be a multiple of batch %d", total, batch);
+  if (total == 0) return A0_OK;
+  A0_REQUIRE(idx_out && prio_out, "a0_rb_sample_mail: idx_out and prio_out are required");
+  { int frc = a0_check_fault(h, "a0_rb_sample_mail"); if (frc) return frc; }
+  A0DeviceGuard guard(h->device);
+  { int mrc = a0_mail_reserve(h, total, (cudaStream_t)stream_); if (mrc) return mrc; }
+  if (h->progress_dirty) {
+    A0_CUDA(cudaMemsetAsync(h->counter + A0_K3_PROGRESS, 0, sizeof(unsigned int), (cudaStream_t)stream_));
+    h->progress_dirty = 0;
+  }
+  A0Rng rng = {0ull, 0ll, nullptr, nullptr, nullptr};
+  if (!u) {
+    rng.seed = seed;
+    rng.call = call;
+    rng.call_dev = reinterpret_cast<unsigned long long*>(h->counter + K2A_RNG_CALL);
+    rng.ticket = h->counter + K2A_RNG_TICKET;
+  }
+  h->mail_total = total;
+  return a0_sample_launch(h, u, rng, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, stream_,
+                          "a0_rb_sample_mail", h->mail);
+}
+
+extern "C" int a0_rb_gather_mail(a0_replay_t* h, int32_t lo, int32_t count, int32_t window, int32_t n_step, double gamma,
+                                 uint8_t* frames_out, int64_t* action_out, double* reward64_out, float* reward32_out,
+                                 uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream_) {
+  A0_REQUIRE(h != nullptr, "a0_rb_gather_mail: handle is NULL");
+  A0_REQUIRE(lo >= 0 && count >= 0, "a0_rb_gather_mail: negative range");
+  A0_REQUIRE(window >= 0, "a0_rb_gather_mail: negative window");
+  if (count == 0) return A0_OK;
+  A0_REQUIRE(frames_out != nullptr, "a0_rb_gather_mail: frames_out is required");
+  A0_REQUIRE(n_step >= 1 && n_step <= A0_MAX_NSTEP, "a0_rb_gather_mail: n_step %d outside [1,%d]", n_step, A0_MAX_NSTEP);
+  A0_REQUIRE(((uintptr_t)frames_out & 15) == 0, "a0_rb_gather_mail: frames_out must be 16-byte aligned");
+  A0_REQUIRE(h->mail != nullptr && (int64_t)lo + count <= h->mail_cap,
+             "a0_rb_gather_mail: draws [%d, %d) lie outside the mailbox of the last a0_rb_sample_mail", lo, lo + count);
+  A0DeviceGuard guard(h->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // the outputs are the bases of the whole draw's buffers: this wave writes rows [lo, lo + count)
+  const A0GatherOut out = {frames_out + (size_t)lo * A0_SLOTS * h->F, action_out ? action_out + lo : nullptr,
+                           reward64_out ? reward64_out + lo : nullptr, reward32_out ? reward32_out + lo : nullptr,
+                           done8_out ? done8_out + lo : nullptr, done32_out ? done32_out + lo : nullptr,
+                           boot_out ? boot_out + lo : nullptr};
+  A0_REQUIRE((int64_t)lo + count <= h->mail_total, "a0_rb_gather_mail: draws [%d, %d) lie beyond the %lld draws of the last a0_rb_sample_mail",
+             lo, lo + count, (long long)h->mail_total);
+  int rc = a0_gather_launch_mail(h, nullptr, h->mail + lo, count, n_step, gamma, out, stream, h->mail_total, window, lo);
+  if (rc) {
+    cudaMemsetAsync(h->mail + lo, 0, (size_t)count * sizeof(long long), stream);   // nobody will consume the posted words
+    if (window > 0) h->progress_dirty = 1;                                         // nor count these draws as complete
+  }
+  return rc;
+}
+
 __global__ void a0_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
 
 extern "C" int a0_pt_rng_seek(a0_replay_t* h, uint64_t call, a0_stream_t stream_) {
@@ -1053,15 +1115,18 @@ constexpr int K2C_LOG = 12;                                  // leaves per chunk
 constexpr int K2C_MAX_COUNT = 2048;
 constexpr int K2C_MAX_CHUNKS = 592;                          // 148 SMs x 4: beyond that (> 2 M leaves) the other schedules run
 constexpr size_t K2C_SMEM = ((size_t)2 << K2C_LOG) * 4 + ((size_t)1 << K2C_LOG) * 4;    // heap + tickets = 48 KB
+constexpr int K2C_SPARSE_MAX = 32;                           // updated leaves per chunk climbed path by path (one lane each)
 
 __global__ void __launch_bounds__(K2C_THREADS)
 a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const int64_t* __restrict__ idx64,
               const int32_t* __restrict__ idx32, const float* __restrict__ vals, int32_t count, int32_t mode,
               float alpha, float eps, float* __restrict__ max_p, unsigned int* __restrict__ ticket, const A0Report rep,
-              int32_t early) {
+              int32_t early, int32_t sparse_max) {
   extern __shared__ __align__(16) uint8_t a0_k2c_smem[];
   __shared__ int s_dirty;
   __shared__ bool s_last;
+  __shared__ int s_nwin;                                     // distinct leaves of this chunk in the index list
+  __shared__ int s_list[K2C_SPARSE_MAX];
   float* heap = reinterpret_cast<float*>(a0_k2c_smem);                      // heap[i] = node i of the chunk's sub-tree
   int* win = reinterpret_cast<int*>(a0_k2c_smem + ((size_t)2 << K2C_LOG) * 4);
   A0_T0();
@@ -1083,7 +1148,7 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   const int n = 1 << clog;
   const int top_levels = D - clog;                           // depth of the chunk roots
   const int64_t lo = (int64_t)c << clog;                    // first leaf of the chunk
-  if (tid == 0) s_dirty = 0;
+  if (tid == 0) { s_dirty = 0; s_nwin = 0; }
   if (n >= 4) {
     const float4* src = reinterpret_cast<const float4*>(tree + P + lo);
     for (int i = tid; i < (n >> 2); i += K2C_THREADS) {
@@ -1108,6 +1173,38 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     bool set;
     const int64_t p = position(k, set);
     if (p >= lo && p < lo + n && p < N) atomicMax(win + (int)(p - lo), k);
+  }
+  // ---- few updated leaves (the usual case: 640 indices over 256 chunks): instead of recomputing the chunk's 4095
+  //      inner nodes, each updated path is climbed on its own -- 12 adds -- from the siblings along it.  The sibling
+  //      leaf is in shared memory already; the inner siblings are fetched from the tree here, one round trip for
+  //      all paths and levels at once (thread = (path, level)), into their places in the chunk heap.  A sibling that
+  //      lies on ANOTHER updated path is overwritten by that path's climb before it is read (levels are separated
+  //      by a warp barrier).  The tree's invariant (node == fl32(left + right)) makes the fetched values exactly
+  //      what the full recomputation would produce: the same tree, bit for bit.
+  bool sparse = false;
+  if (sparse_max > 0) {
+    __syncthreads();                                         // tickets final
+    for (int k = tid; k < count; k += K2C_THREADS) {
+      bool set;
+      const int64_t p = position(k, set);
+      if (!(p >= lo && p < lo + n && p < N)) continue;
+      const int l = (int)(p - lo);
+      if (win[l] != k) continue;
+      const int slot = atomicAdd(&s_nwin, 1);
+      if (slot < K2C_SPARSE_MAX) s_list[slot] = l;
+    }
+    __syncthreads();
+    const int nwin = s_nwin;
+    sparse = nwin <= sparse_max;                             // CTA-uniform
+    if (sparse && nwin > 0) {
+      for (int t = tid; t < nwin * 16; t += K2C_THREADS) {
+        const int j = t & 15;                                // level of the sibling: 1 .. clog-1 (level clog = leaves)
+        if (j < 1 || j >= clog) continue;
+        const int l = s_list[t >> 4];
+        const int sib = ((n + l) >> (clog - j)) ^ 1;
+        heap[sib] = __ldcg(tree + (((int64_t)1 << (top_levels + j)) + ((int64_t)c << j) + (sib - (1 << j))));
+      }
+    }
   }
   if (early) A0_PDL_PROLOGUE();                              // from here on the values (losses, max_p) are read
   const float maxp_in = __ldcg(max_p);
@@ -1148,7 +1245,24 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   }
   __syncthreads();
   K2C_TX(2);
-  if (s_dirty) {
+  if (s_dirty && sparse) {
+    // every listed path (its leaf rewritten or not: an unchanged path recomputes the values it already holds),
+    // one lane each, level by level; two lanes that share an ancestor write it the same value
+    if (tid < 32) {
+      const int nwin = s_nwin;
+      const int l = tid < nwin ? s_list[tid] : -1;
+      for (int j = clog - 1; j >= 0; --j) {
+        if (l >= 0) {
+          const int h = (n + l) >> (clog - j);
+          const float v = __fadd_rn(heap[2 * h], heap[2 * h + 1]);
+          heap[h] = v;
+          __stcg(tree + (((int64_t)1 << (top_levels + j)) + ((int64_t)c << j) + (h - (1 << j))), v);
+        }
+        __syncwarp();
+      }
+    }
+    K2C_TX(3);
+  } else if (s_dirty) {
     a0_heap_reduce<K2C_THREADS>(heap, clog);
     K2C_TX(3);
     // ---- pass 3: the nodes on the updated paths (chunk-local node h at local level j) ------------------
@@ -1187,6 +1301,16 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   if (tid == 0) A0_TEND(5);
 }
 
+static int g_k2b_sparse = -1;      // updated leaves per chunk up to which a0_k2b_chunks climbs path by path (0: always the full chunk)
+static int a0_option_k2b_sparse() {
+  if (g_k2b_sparse < 0) {
+    const char* e = getenv("A0_K2B_SPARSE");
+    g_k2b_sparse = e ? atoi(e) : K2C_SPARSE_MAX;
+    if (g_k2b_sparse < 0 || g_k2b_sparse > K2C_SPARSE_MAX) g_k2b_sparse = K2C_SPARSE_MAX;
+  }
+  return g_k2b_sparse;
+}
+void a0_set_k2b_sparse(int v) { g_k2b_sparse = v < 0 ? 0 : (v > K2C_SPARSE_MAX ? K2C_SPARSE_MAX : v); }
 static int g_k2b_chunks = -1;
 static bool a0_option_k2b_chunks() {
   if (g_k2b_chunks < 0) {
@@ -1238,7 +1362,8 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
       attr[h->device] = true;
     }
     A0_LAUNCH(a0_k2b_chunks, (unsigned)chunks, K2C_THREADS, K2C_SMEM, stream, 1, early ? A0_PDL_FORCE : A0_PDL_K2, h->tree, h->P, h->D, h->N,
-              idx64, idx32, vals, count, mode, alpha, eps, h->max_p, h->counter + A0_MAX_BATCHES, rep, (int32_t)(early ? 1 : 0));
+              idx64, idx32, vals, count, mode, alpha, eps, h->max_p, h->counter + A0_MAX_BATCHES, rep, (int32_t)(early ? 1 : 0),
+              (int32_t)a0_option_k2b_sparse());
     return A0_OK;
   }
   const bool hybrid = count >= a0_option_k2b_bulk_min() && (int64_t)count >= 4 * chunks;

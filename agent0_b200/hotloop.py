@@ -30,7 +30,8 @@ ALGOS = ("dqn", "mdqn", "c51", "qr", "iqn", "fqf")
 class ReplayTargetLoop:
     def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, n_step=None, double_q=True,
                  per=None, variant=0, discount=None, alpha=0.5, eps=0.01, c51=(51, -10.0, 10.0), mdqn=(0.03, -1.0),
-                 frames=None, rng_seed=None, overlap_sample_gather=True, want_prio=False, early_update=True):
+                 frames=None, rng_seed=None, overlap_sample_gather=True, want_prio=False, early_update=True,
+                 gather_waves="auto", pdl_at_joins=False, gather_window="auto", k4_priority=True):
         """replay: ReplayDataset (native_nstep=True when n_step > 1).  outputs: dict of STATIC f32 device
         tensors holding the network outputs of all L*B sampled transitions, batch k in rows
         [k*B, (k+1)*B): ``online``, ``tgt_next`` (+ ``qsel`` [L*B,A] under double_q / for iqn, fqf;
@@ -42,7 +43,20 @@ class ReplayTargetLoop:
         want_prio: K4 also writes (loss+eps)^alpha per sample into ``self.newp`` (the loop itself does not need it:
         K2b recomputes the priority from the loss).
         overlap_sample_gather: ``step()`` issues K2a and K3 through a0_rb_sample_gather (the gather runs
-        under the sampler, fed draw by draw through a mailbox) instead of back to back; same results."""
+        under the sampler, fed draw by draw through a mailbox) instead of back to back; same results.
+        gather_waves: the gather of the L batches is cut into waves (a0_rb_sample_mail + one a0_rb_gather_mail per
+        wave) on a side stream, and batch k's K4 waits only for the wave that holds batch k -- the later batches
+        are fetched UNDER the target kernels of the earlier ones (what the reference's DataPrefetcher does with its
+        3-deep queue, utils.py:45-61).  "auto": doubling waves of 1, 1, 2, 4 ... batches when a batch is small
+        (the K4 chain is the longer side), one wave per batch when a batch moves more than ~10 MB; a list gives
+        the wave sizes in batches; None/0: one gather launch on the caller's stream.  Same results either way.
+        gather_window: ordered fetch inside the waves (a0_rb_gather_mail's ``window``): at most that many draws beyond
+        the completed ones are in flight, so the first batches complete first.  "auto": 128 with the doubling plan (small
+        batches, all gather CTAs resident at once), 400 with one wave per batch (a shallower HBM queue: the K4 launches
+        that run under the gather keep pace with its waves); 0: no limit.
+        k4_priority: K4 and K2b run on a high-priority stream of the loop (the gather's CTAs queue for every free slot of
+        every SM; without priority the target kernels' CTAs wait behind them), joined back into the caller's stream.
+        pdl_at_joins: the K4 that waits for a wave keeps its programmatic-launch attribute (measured option)."""
         assert algo in ALGOS, algo
         self.lib = _lib.load()
         self.rp, self.algo, self.B, self.L, self.A = replay, algo, int(batch_size), int(learner_steps), int(action_dim)
@@ -70,7 +84,20 @@ class ReplayTargetLoop:
         self.grad = torch.empty_like(self.o["online"])
         self.frac = e(T) if algo == "fqf" else None
         self.gtau = e(T, self.o["taus"].shape[1]) if algo == "fqf" else None
-        self.launches_per_step = 2 + self.L + (1 if self.per else 0)     # our kernels (uniform_ is torch's)
+        self.waves = self._wave_plan(gather_waves) if self.overlap_sg else None
+        self.pdl_at_joins = bool(pdl_at_joins)
+        if self.waves:
+            self.side = torch.cuda.Stream(device=dev)
+            self.fast = torch.cuda.Stream(device=dev, priority=-1) if k4_priority else None
+            self.wave_ev = [torch.cuda.Event() for _ in self.waves]
+            self._join = {b0: j for j, (b0, _, _, _) in enumerate(self.waves)}      # first batch of wave j -> j
+            per_batch = all(w[1] == 1 for w in self.waves)
+            # measured on B200 (profiles/r02s3_gather_waves_ab.json): 128 draws in flight feed a batch-32 K4 chain in order
+            # at 67.9 us per step (96: 71.4, no limit: 71.0); 400 of the ~1036 resident gather CTAs in flight keep the
+            # batch-512 step's K4 launches on pace with the waves at 216 us (no limit: 238, 320: 233, 480: 223)
+            self.window = (400 if per_batch else 128) if gather_window == "auto" else int(gather_window or 0)
+        n_gather = len(self.waves) if self.waves else 1
+        self.launches_per_step = 1 + n_gather + self.L + (1 if self.per else 0)     # our kernels (uniform_ is torch's)
         self._k4 = None
         self._k4_all = None
         self.graph = None
@@ -109,6 +136,53 @@ class ReplayTargetLoop:
             float(rp.beta), 0.0, 0 if self.per else 1, self.idx.data_ptr(), self.prio.data_ptr(), self.w.data_ptr(), self.n,
             self.gamma, self.frames.data_ptr(), self.act.data_ptr(), self.r64.data_ptr(), self.r32.data_ptr(),
             self.d8.data_ptr(), self.d32.data_ptr(), self.boot.data_ptr(), self._st()), "a0_rb_sample_gather")
+
+    def _wave_plan(self, spec):
+        """[(first batch, batches, first draw, draws)] per wave, or None for a single gather launch."""
+        if not spec or self.L < 2:
+            return None
+        if isinstance(spec, str):
+            assert spec == "auto", spec
+            if self.B * 16 * self.rp.F >= 10_000_000:       # a batch's gather outlasts a K4: one wave per batch
+                sizes = [1] * self.L
+            else:                                           # the K4 chain is the longer side: 1, 1, 2, 4, ... batches
+                sizes, w = [1], 1
+                while sum(sizes) < self.L:
+                    sizes.append(min(w, self.L - sum(sizes)))
+                    w *= 2
+                if len(sizes) > 1 and sizes[-1] < sizes[-2]:        # a short tail joins the wave before it
+                    tail = sizes.pop()
+                    sizes[-1] += tail
+        else:
+            sizes = [int(x) for x in spec]
+            assert all(x > 0 for x in sizes) and sum(sizes) == self.L, "gather_waves must be positive batch counts that sum to learner_steps"
+        if len(sizes) < 2:
+            return None
+        plan, b0 = [], 0
+        for n in sizes:
+            plan.append((b0, n, b0 * self.B, n * self.B))
+            b0 += n
+        return plan
+
+    def sample_gather_waves(self):
+        """K2a + the gather in waves on the side stream (a0_rb_sample_mail, a0_rb_gather_mail per wave, an event after
+        each): same outputs as sample_gather().  The caller's stream joins wave by wave (``_wait_wave``)."""
+        rp, lib = self.rp, self.lib
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)           # everything before this step (the previous write-back, the ingest)
+        with torch.cuda.stream(self.side):
+            st = self._st()
+            _lib.check(lib.a0_rb_sample_mail(rp.h, None if self.rng_seed is not None else self.u.data_ptr(), self.rng_seed or 0, -1,
+                                             self.total, self.B, -1.0, float(rp.beta), 0.0, 0 if self.per else 1, self.idx.data_ptr(),
+                                             self.prio.data_ptr(), self.w.data_ptr(), st), "a0_rb_sample_mail")
+            for j, (_, _, lo, cnt) in enumerate(self.waves):
+                _lib.check(lib.a0_rb_gather_mail(rp.h, lo, cnt, self.window, self.n, self.gamma, self.frames.data_ptr(), self.act.data_ptr(),
+                                                 self.r64.data_ptr(), self.r32.data_ptr(), self.d8.data_ptr(), self.d32.data_ptr(),
+                                                 self.boot.data_ptr(), st), "a0_rb_gather_mail")
+                self.wave_ev[j].record(self.side)
+
+    def _wait_wave(self, j):
+        torch.cuda.current_stream(self.dev).wait_event(self.wave_ev[j])
 
     def _common(self, lo, count):
         s = slice(lo, lo + count)
@@ -202,9 +276,49 @@ class ReplayTargetLoop:
             self.report[slot][1].copy_(self.loss, non_blocking=True)
 
     # ------------------------------------------------------------------ whole steps
-    def step(self, fused_k4=False, slot=None):
+    def _targets_and_update(self, fused_k4, slot, update=True):
+        """The K4 launches of a step whose gather runs in waves (each waits for the wave that holds its batch), then K2b."""
+        if fused_k4:
+            for j in range(len(self.waves)):
+                self._wait_wave(j)
+            self.target_loss_all()
+        else:
+            for k in range(self.L):
+                j = self._join.get(k)
+                if j is None:
+                    self.target_loss(k)
+                    continue
+                # the K4 that joins wave j has TWO predecessors (the previous K4, the wave): launched without the
+                # programmatic attribute unless pdl_at_joins
+                self._wait_wave(j)
+                if self.pdl_at_joins:
+                    self.target_loss(k)
+                else:
+                    mask = C.c_int64(0)
+                    _lib.check(self.lib.a0_get_option(_lib.OPT_PDL, C.byref(mask)), "a0_get_option")
+                    self.lib.a0_set_option(_lib.OPT_PDL, mask.value & ~1)
+                    try:
+                        self.target_loss(k)
+                    finally:
+                        self.lib.a0_set_option(_lib.OPT_PDL, mask.value)
+        if update:
+            self.update(slot, after_k4=True)
+
+    def step(self, fused_k4=False, slot=None, update=True):
+        """update=False: everything but the priority write-back (StaleByOneLoop issues it during the next step)."""
         if self.rng_seed is None:
             self.u.uniform_()
+        if self.waves:
+            self.sample_gather_waves()
+            if self.fast is None:
+                self._targets_and_update(fused_k4, slot, update)
+                return
+            main = torch.cuda.current_stream(self.dev)
+            self.fast.wait_stream(main)           # the network outputs, the previous step
+            with torch.cuda.stream(self.fast):
+                self._targets_and_update(fused_k4, slot, update)
+            main.wait_stream(self.fast)
+            return
         if self.overlap_sg:
             self.sample_gather()
         else:
@@ -215,7 +329,8 @@ class ReplayTargetLoop:
         else:
             for k in range(self.L):
                 self.target_loss(k)
-        self.update(slot, after_k4=True)
+        if update:
+            self.update(slot, after_k4=True)
 
     def capture(self, warm=3, fused_k4=False):
         """Warm up, then capture one step into a CUDA graph (returned; also kept as ``self.graph``)."""
@@ -294,9 +409,7 @@ class StaleByOneLoop:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 prev.update()
-        cur.sample_gather() if cur.overlap_sg else (cur.sample(), cur.gather())
-        for k in range(cur.L):
-            cur.target_loss(k)
+        cur.step(update=False)               # K2a + gather (in waves) + K4 x L into set p
         if not first:
             main.wait_stream(self.side)
 

@@ -65,6 +65,11 @@ def parse():
     p.add_argument("--cpu-entries", type=int, default=1_000_000, help="entries in the CPU arm's lz4 deque (replay.py:18: 1 M)")
     p.add_argument("--cpu-distinct", type=int, default=16384, help="distinct lz4 blobs behind those entries (the deque holds references)")
     p.add_argument("--min-seconds", type=float, default=0.25, help="repeat the --steps block until this much device time (value) / wall clock (e2e)")
+    p.add_argument("--gather-waves", default="auto", help="gather schedule of the step: auto (waves on a side stream, K4 of batch k waits "
+                   "for its wave only), none (one gather launch before the first K4), or wave sizes in batches, e.g. 1,1,2,4,12")
+    p.add_argument("--gather-window", default="auto", help="ordered fetch inside the gather waves: draws in flight beyond the completed ones (auto | 0 = no limit | n)")
+    p.add_argument("--no-k4-priority", action="store_true", help="K4 + K2b on the caller's stream instead of the loop's high-priority stream")
+    p.add_argument("--pdl-at-joins", action="store_true", help="the K4 that joins a gather wave keeps its programmatic-launch attribute")
     p.add_argument("--cpu-workers", type=int, default=-1, help="--impl reference DataLoader workers (-1: all cores)")
     return p.parse_args()
 
@@ -146,8 +151,9 @@ def bytes_per_transition(n):
     return (4 + min(n, 4) + 8) * F_BYTES
 
 
-def make_hotpath(rp, wl, L, A, torch, variant=0):
+def make_hotpath(rp, wl, L, A, torch, variant=0, waves=None):
     from agent0_b200.hotloop import ReplayTargetLoop
+    waves = GATHER_WAVES if waves is None else (None if waves == "none" else waves)
 
     class HotPath(ReplayTargetLoop):
         """agent0_b200.hotloop.ReplayTargetLoop (the package's pre-bound form of the Trainer.step inner
@@ -162,7 +168,8 @@ def make_hotpath(rp, wl, L, A, torch, variant=0):
             self.frames_pool = torch.empty(self.n_out, T, 8 * F_BYTES, dtype=torch.uint8, device=rp.device)
             super().__init__(rp, wl["algo"], wl["B"], L, A, net_outputs(wl["algo"], T, A, torch, rp.device), n_step=wl["n"],
                              double_q=wl["double"], per=wl["per"], variant=variant, discount=0.99, frames=self.frames_pool[0],
-                             rng_seed=RNG_SEED)
+                             rng_seed=RNG_SEED, gather_waves=waves, pdl_at_joins=PDL_AT_JOINS,
+                             gather_window=GATHER_WINDOW, k4_priority=K4_PRIORITY)
             self.wl, self.idx_pool = wl, None
 
         def draw_pool(self):
@@ -186,8 +193,8 @@ def make_hotpath(rp, wl, L, A, torch, variant=0):
     return HotPath()
 
 
-def HotPath(rp, wl, L, A, torch, variant=0):
-    return make_hotpath(rp, wl, L, A, torch, variant)
+def HotPath(rp, wl, L, A, torch, variant=0, waves=None):
+    return make_hotpath(rp, wl, L, A, torch, variant, waves)
 
 
 def time_graphed(hp, steps, warmup, torch, use_graph, barrier, step_fn=None, min_seconds=0.0, reduce_max=None, stats=None):
@@ -242,6 +249,10 @@ def block_stats(blocks, units_per_block):
 
 EMIT = print
 INNER = 20
+GATHER_WAVES = "auto"    # --gather-waves
+PDL_AT_JOINS = False     # --pdl-at-joins
+GATHER_WINDOW = "auto"   # --gather-window
+K4_PRIORITY = True       # --no-k4-priority
 RNG_SEED = 20261017      # the sampler draws its own uniforms (Philox inside K2a); None: torch's uniform_ + a0_pt_sample
 
 
@@ -549,7 +560,11 @@ def run_ours(args):
 
     wl = WORKLOADS[args.workload]
     L, A = args.learner_steps, args.actions
-    global RNG_SEED
+    global RNG_SEED, GATHER_WAVES, PDL_AT_JOINS, GATHER_WINDOW, K4_PRIORITY
+    GATHER_WINDOW = "auto" if args.gather_window == "auto" else int(args.gather_window)
+    K4_PRIORITY = not args.no_k4_priority
+    PDL_AT_JOINS = bool(args.pdl_at_joins)
+    GATHER_WAVES = None if args.gather_waves == "none" else ("auto" if args.gather_waves == "auto" else [int(x) for x in args.gather_waves.split(",")])
     if args.torch_rng:
         RNG_SEED = None
     elif RNG_SEED is not None:
@@ -565,6 +580,9 @@ def run_ours(args):
     total = hp.total
     value = total * args.steps * world / secs
     timing = block_stats(blocks, total * args.steps * world)
+    launches_per_step = hp.launches_per_step
+    wave_sizes = [w[1] for w in hp.waves] if hp.waves else None
+    wave_window = hp.window if hp.waves else None
 
     # ---- roofline of the dominant kernel (K3), same launch shape, fresh indices every launch -------
     hp.draw_pool()
@@ -668,10 +686,12 @@ def run_ours(args):
             "timed_region_s": timing["timed_region_s"],
             "run": {"frame_ring_GB_per_gpu": round((ring * 1.0625 + 65536) * F_BYTES / 1e9, 2), "cuda_graph": not args.no_graph,
                     "uniforms": "torch uniform_ launch" if RNG_SEED is None else "Philox4x32-10 inside K2a (a0_pt_sample_rng)",
+                    "gather_waves_batches": wave_sizes, "gather_window_draws": wave_window,
+                    "k4_stream": "high-priority stream of the loop" if (wave_sizes and K4_PRIORITY) else "caller's stream",
                     "sharding": f"{world} independent shards, no data-path collective", "fill_seconds": round(t_fill, 1)},
             "clocks": clk.summary(),
             "e2e": e2e,
-            "gpu_launches": hp_launches(wl, L) * args.steps * len(blocks),
+            "gpu_launches": launches_per_step * args.steps * len(blocks),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "configs": configs,
@@ -818,6 +838,11 @@ def time_workload(rp, name, args, torch, peak, L, A):
     bl = []
     secs = time_graphed(hp, 20, 5, torch, not args.no_graph, lambda: None, min_seconds=min(args.min_seconds, 0.15), stats=bl)
     secs_fused = time_graphed(hp, 20, 5, torch, not args.no_graph, lambda: None, step_fn=hp.step_fused_k4, min_seconds=0.02)
+    secs_one = None
+    if hp.waves:         # the same step with ONE gather launch in front of the first K4 (the round-1/2 schedule)
+        hp1 = HotPath(rp, wl, L, A, torch, variant=args.variant, waves="none")
+        secs_one = time_graphed(hp1, 20, 5, torch, not args.no_graph, lambda: None, min_seconds=0.03)
+        del hp1
     hp.draw_pool()
     k4 = time_kernel(lambda i: hp.loss_k(i % L), 100, torch)
     k3 = time_kernel(lambda i: hp.gather(pool=i), 60, torch)
@@ -827,7 +852,10 @@ def time_workload(rp, name, args, torch, peak, L, A):
     full = {"transitions_per_s": round(hp.total * 20 / secs, 1), "ms_per_step": round(secs / 20 * 1e3, 4),
             "transitions_per_s_one_k4_launch_for_all_batches": round(hp.total * 20 / secs_fused, 1),
             "k4_us_per_batch": round(k4 * 1e6, 2), "k3_us": round(k3 * 1e6, 2), "k3_GBps": round(gb, 1),
-            "k2a_us": round(k2a * 1e6, 2), "k2b_us": round(k2b * 1e6, 2), "desc": wl["desc"], "blocks": len(bl)}
+            "k2a_us": round(k2a * 1e6, 2), "k2b_us": round(k2b * 1e6, 2), "desc": wl["desc"], "blocks": len(bl),
+            "gather_waves_batches": [w[1] for w in hp.waves] if hp.waves else None,
+            "transitions_per_s_single_gather_launch": round(hp.total * 20 / secs_one, 1) if secs_one else None,
+            "step_GBps": round(bytes_per_transition(wl["n"]) * hp.total * 20 / secs / 1e9, 1)}
     compact = {"workload": name, "desc": wl["desc"], "value": full["transitions_per_s"], "ms_per_step": full["ms_per_step"],
                "k3_frac": round(gb / peak, 4), "k4_us": full["k4_us_per_batch"], "ring": rp.size}
     del hp
@@ -843,6 +871,17 @@ def extras(rp, args, torch, peak, configs, entries):
         full, compact = time_workload(rp, name, args, torch, peak, L, A)
         out["workloads"][name] = full
         configs.append(compact)
+    # the headline workload with ONE gather launch in front of the first K4 (the schedule of rounds 1-2), for comparison
+    try:
+        wl = WORKLOADS[args.workload]
+        hp1 = HotPath(rp, wl, L, A, torch, variant=args.variant, waves="none")
+        s1 = time_graphed(hp1, 20, 5, torch, not args.no_graph, lambda: None, min_seconds=0.05)
+        out["single_gather_launch"] = {"workload": args.workload, "transitions_per_s": round(hp1.total * 20 / s1, 1),
+                                       "ms_per_step": round(s1 / 20 * 1e3, 5),
+                                       "note": "gather_waves=None: K2a + one K3 launch complete before the first K4 starts"}
+        del hp1
+    except Exception as e:
+        out["single_gather_launch"] = {"error": repr(e)[:300]}
     # the opt-in schedule that takes K2b off the critical path (hotloop.StaleByOneLoop): step s+1 draws while step s's
     # priorities are written back, i.e. with priorities one step stale -- the reference's prefetch queue does the same
     try:

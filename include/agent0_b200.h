@@ -92,6 +92,11 @@ const char* a0_last_error(void);
  * the index list, recomputes its chunk in shared memory; the last CTA finishes the top levels); 0
  * falls back to the cluster schedules selected by A0_OPT_K2B_BULK_MIN.  Same tree either way.       */
 #define A0_OPT_K2B_CHUNKS 8
+/* A0_OPT_K2B_SPARSE (0..32, default 32; A0_K2B_SPARSE in the environment): a chunk CTA of the schedule above whose
+ * chunk holds at most this many updated leaves climbs each updated path on its own (12 adds per path, the inner
+ * siblings fetched from the tree in one round trip) instead of recomputing all 4095 inner nodes of the chunk in
+ * shared memory; 0 = always recompute the whole chunk.  Same tree either way (node == fl32(left + right)).     */
+#define A0_OPT_K2B_SPARSE 12
 /* A0_OPT_QH_SORTED (default 1; A0_QH_SORTED in the environment): a0_loss_quantile with more than 64 target
  * and more than 64 online quantiles and no FQF fraction term (QR-200) evaluates the pair sums in
  * O(N log N) from the sorted targets (float64 prefix sums): 1 = one CTA per sample, merge sort in shared
@@ -112,6 +117,9 @@ const char* a0_last_error(void);
  * returns A0_EFAULT (and clears the word).                                                          */
 #define A0_OPT_MAIL_TIMEOUT_US 9
 int a0_set_option(int32_t option, int64_t value);
+/* Reads an option back (A0_OPT_PDL only: a caller that launches ONE kernel without the programmatic attribute --
+ * the K4 that joins a gather wave from another stream -- restores the mask it found).                     */
+int a0_get_option(int32_t option, int64_t* value);
 
 /* ---- shard lifetime -------------------------------------------------------------------------
  * rec_capacity   transitions kept (cfg.replay.size); indices returned by a0_pt_sample are record
@@ -364,6 +372,31 @@ int a0_rb_sample_gather(a0_replay_t* h, const float* u /* dev [total] or NULL */
                         float* weight_out, int32_t n_step, double gamma, uint8_t* frames_out,
                         int64_t* action_out, double* reward64_out, float* reward32_out,
                         uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream);
+
+/* The same pair with the gather cut into WAVES -- consecutive ranges of the draw, one launch each -- so that
+ * the consumer of the first batches (the K4 launches of Trainer.step's inner loop, trainer.py:82-104, on another
+ * stream) starts while the later batches are still being fetched: the reference's DataPrefetcher does the same
+ * with its 3-deep queue (utils.py:45-61).
+ *   a0_rb_sample_mail   the sampler of a0_rb_sample_gather alone: every draw's record position is posted to the
+ *                       handle's mailbox (same arguments and results as a0_pt_sample / a0_pt_sample_rng)
+ *   a0_rb_gather_mail   the gather of draws [lo, lo + count) of that sampler call; the output pointers are the
+ *                       bases of the WHOLE draw's buffers (this wave writes rows [lo, lo + count)).  Must be queued
+ *                       on the sampler's stream, directly after it or after the previous wave, and every draw must
+ *                       be covered by exactly one wave before the next a0_rb_sample_mail.
+ * window > 0 (the same value for every wave of a draw): ORDERED fetch -- a draw starts its frame traffic only when
+ * at most `window` draws beyond the completed ones are in flight, so the first batches complete first (a consumer
+ * that needs ~2 us per batch is fed in order) instead of every resident CTA sharing the bandwidth and all batches
+ * finishing together; 0: no limit (launches too large to be resident at once are ordered by the hardware anyway).
+ * Waves complete in launch order, and a complete wave implies a complete sampler (weights, priorities): an
+ * event recorded after wave j is what the consumer of its batches waits for.  Same results as
+ * a0_rb_sample_gather.  The first a0_rb_sample_mail (and any with a larger total) allocates the mailbox and must
+ * not be inside a CUDA-graph capture.                                                                    */
+int a0_rb_sample_mail(a0_replay_t* h, const float* u /* dev [total] or NULL */, uint64_t seed, int64_t call,
+                      int32_t total, int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
+                      int64_t* idx_out, float* prio_out, float* weight_out, a0_stream_t stream);
+int a0_rb_gather_mail(a0_replay_t* h, int32_t lo, int32_t count, int32_t window, int32_t n_step, double gamma,
+                      uint8_t* frames_out, int64_t* action_out, double* reward64_out, float* reward32_out,
+                      uint8_t* done8_out, float* done32_out, int64_t* boot_out, a0_stream_t stream);
 
 /* TEST HOOK: the gather half of a0_rb_sample_gather launched WITHOUT its sampler -- what a failed sampler
  * launch or a mis-paired caller would leave behind.  Every CTA times out (A0_OPT_MAIL_TIMEOUT_US), the

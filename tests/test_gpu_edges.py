@@ -273,8 +273,12 @@ def test_k2b_schedules_build_the_same_tree():
     N = 20000
     trees = []
     try:
-        for chunks, small, bulk_min in ((1, 0, 2048), (0, 1, 1 << 30), (0, 0, 1 << 30), (0, 0, 1), (0, 1, 2048)):
+        # sparse: the chunk schedule climbs up to that many updated paths per chunk one by one (A0_OPT_K2B_SPARSE), else
+        # recomputes the whole chunk
+        for chunks, small, bulk_min, sparse in ((1, 0, 2048, 32), (1, 0, 2048, 0), (1, 0, 2048, 3), (0, 1, 1 << 30, 32), (0, 0, 1 << 30, 32),
+                                               (0, 0, 1, 32), (0, 1, 2048, 32)):
             assert lib.a0_set_option(8, chunks) == 0 and lib.a0_set_option(7, small) == 0 and lib.a0_set_option(3, bulk_min) == 0
+            assert lib.a0_set_option(12, sparse) == 0
             rp = _replay(N, 1, 4)
             rp.set_priorities(torch.arange(N), torch.as_tensor((np.arange(N) % 97 + 1).astype(np.float32)))
             rp.set_priorities(torch.arange(0, N, 5), torch.zeros(N // 5))            # "evicted" leaves are skipped by updates
@@ -294,6 +298,8 @@ def test_k2b_schedules_build_the_same_tree():
         lib.a0_set_option(3, 2048)
         lib.a0_set_option(7, 0)
         lib.a0_set_option(8, 1)
+        lib.a0_set_option(12, 32)
+    assert lib.a0_set_option(12, 33) == -1
     for t, mp in trees[1:]:
         assert torch.equal(trees[0][0], t) and trees[0][1] == mp
     assert lib.a0_set_option(3, 0) == -1

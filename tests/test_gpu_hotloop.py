@@ -116,7 +116,7 @@ def test_prebound_loop_equals_general_api_and_graph_replays_identically(algo):
         assert torch.equal(loop.act, batch.actions) and torch.equal(loop.d8.bool(), batch.terminals)
         assert torch.equal(loop.loss, loss_ref) and torch.equal(loop.grad, grad_ref)
         assert torch.equal(rp.tree, rp_a.tree) and float(rp.max_p_tensor) == float(rp_a.max_p_tensor)
-        assert loop.launches_per_step == L + 3
+        assert loop.launches_per_step == 1 + (len(loop.waves) if loop.waves else 1) + L + 1
 
 
 def test_prebound_loop_step_capture_and_single_launch_k4():
@@ -226,6 +226,82 @@ def test_reporting_graphs_with_ingest_published_scalars_equal_the_plain_loop():
         assert torch.equal(la.idx, lb.idx) and torch.equal(la.loss, lb.loss) and torch.equal(la.w, lb.w)
         assert torch.equal(rp_a.tree, rp_b.tree)
     assert len({int(rep[0][0][0]), int(rep[1][0][0])}) == 2 or not torch.equal(rep[0][0], rep[1][0])
+
+
+@pytest.mark.parametrize("Bn,k,per,waves,pdl,window,prio", [
+    (32, 20, True, "auto", False, "auto", True), (32, 20, True, [1, 1, 2, 16], True, 8, True), (512, 4, True, "auto", False, "auto", True),
+    (12, 5, True, [2, 3], False, 1, False), (32, 6, False, "auto", False, 40, True), (16, 3, True, [1, 2], True, 0, False),
+    (64, 20, True, [1] * 20, False, 700, True)])
+def test_gather_waves_equal_the_single_gather_launch(Bn, k, per, waves, pdl, window, prio):
+    """gather_waves: K2a and the gather cut into waves run on a side stream (a0_rb_sample_mail + a0_rb_gather_mail per wave),
+    batch k's K4 waits only for the wave that holds it.  Against the same loop with ONE gather launch on a twin shard with
+    the same sampler seed: identical draws, stacks, n-step scalars, losses, gradients and tree -- eagerly, step after step,
+    and as a captured graph (the side-stream branch becomes part of the graph).  window: the ordered fetch inside the waves
+    (at most that many draws beyond the completed ones in flight; 1 = strictly one after the other); prio: K4 + K2b on the
+    loop's high-priority stream."""
+    from agent0_b200.hotloop import ReplayTargetLoop
+    T = Bn * k
+    o = _outputs("c51", T)
+    rp_a, rp_b = _shard("c51"), _shard("c51")
+    la = ReplayTargetLoop(rp_a, "c51", Bn, k, A, o, n_step=3, per=per, rng_seed=9, gather_waves=None)
+    lb = ReplayTargetLoop(rp_b, "c51", Bn, k, A, o, n_step=3, per=per, rng_seed=9, gather_waves=waves, pdl_at_joins=pdl,
+                          gather_window=window, k4_priority=prio)
+    if window == "auto":
+        assert lb.window == (400 if Bn >= 256 else 128)
+    assert la.waves is None and lb.waves is not None and sum(w[1] for w in lb.waves) == k and sum(w[3] for w in lb.waves) == T
+    if waves == "auto":
+        assert [w[1] for w in lb.waves] == ([1] * k if Bn >= 256 else {20: [1, 1, 2, 4, 12], 6: [1, 1, 2, 2]}[k])
+    assert lb.launches_per_step == 1 + len(lb.waves) + k + (1 if per else 0)
+    fields = ("idx", "prio", "w", "frames", "act", "r64", "r32", "d8", "d32", "boot", "loss", "grad")
+
+    def same():
+        torch.cuda.synchronize()
+        for f in fields:
+            assert torch.equal(getattr(la, f), getattr(lb, f)), f
+        assert torch.equal(rp_a.tree, rp_b.tree) and float(rp_a.max_p_tensor) == float(rp_b.max_p_tensor)
+
+    rp_a.push_dynamic(); rp_b.push_dynamic()
+    rp_a.rng_seek(0); rp_b.rng_seek(0)
+    for _ in range(3):                                     # eager: the side stream forks from and joins the caller's stream
+        lb.frames.zero_(); lb.idx.fill_(-1); lb.loss.fill_(-1.0)
+        la.step(); lb.step()
+        same()
+    lb.step(fused_k4=True); la.step(fused_k4=True)         # one K4 launch for all batches waits for the last wave
+    same()
+    la.capture(warm=1); lb.capture(warm=1)
+    for _ in range(4):
+        lb.frames.zero_(); lb.loss.fill_(-1.0)
+        la.run(); lb.run()
+        same()
+    if per:
+        w = lb.w.view(k, Bn).max(dim=1)[0]
+        assert torch.allclose(w, torch.ones_like(w), atol=1e-6)
+    from agent0_b200 import _lib
+    mask = __import__("ctypes").c_int64(-1)
+    assert _lib.load().a0_get_option(_lib.OPT_PDL, __import__("ctypes").byref(mask)) == 0 and mask.value == 1     # restored after the joins
+
+
+def test_gather_mail_argument_errors():
+    from agent0_b200 import _lib
+    lib = _lib.load()
+    rp = _shard("c51")
+    out = torch.empty(64, 8 * rp.F, dtype=torch.uint8, device="cuda")
+    st = _lib.stream_ptr(rp.device)
+    idx = torch.empty(64, dtype=torch.int64, device="cuda"); pr = torch.empty(64, device="cuda")
+    assert lib.a0_rb_sample_mail(None, None, 1, 0, 64, 32, 4096.0, 0.4, 0.0, 0, idx.data_ptr(), pr.data_ptr(), None, st) == -1
+    assert lib.a0_rb_sample_mail(rp.h, None, 1, 0, 60, 32, 4096.0, 0.4, 0.0, 0, idx.data_ptr(), pr.data_ptr(), None, st) == -1
+    assert lib.a0_rb_sample_mail(rp.h, None, 1, 0, 64, 32, 4096.0, 0.4, 0.0, 0, None, pr.data_ptr(), None, st) == -1
+    assert lib.a0_rb_gather_mail(rp.h, 0, 32, 0, 3, 0.99, None, None, None, None, None, None, None, st) == -1
+    assert lib.a0_rb_gather_mail(rp.h, -1, 32, 0, 3, 0.99, out.data_ptr(), None, None, None, None, None, None, st) == -1
+    assert lib.a0_rb_gather_mail(rp.h, 0, 32, 0, 17, 0.99, out.data_ptr(), None, None, None, None, None, None, st) == -1
+    # a wave beyond the mailbox of the last a0_rb_sample_mail (none yet on this handle, or a shorter draw)
+    assert lib.a0_rb_gather_mail(rp.h, 1 << 20, 32, 0, 3, 0.99, out.data_ptr(), None, None, None, None, None, None, st) == -1
+    assert b"mailbox" in lib.a0_last_error()
+    assert lib.a0_rb_gather_mail(rp.h, 0, 32, -1, 3, 0.99, out.data_ptr(), None, None, None, None, None, None, st) == -1
+    assert lib.a0_rb_gather_mail(rp.h, 0, 0, 0, 3, 0.99, out.data_ptr(), None, None, None, None, None, None, st) == 0
+    v = __import__("ctypes").c_int64(0)
+    assert lib.a0_get_option(99, __import__("ctypes").byref(v)) == -1 and lib.a0_get_option(1, None) == -1
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("Bn,k,per", [(32, 20, True), (512, 4, True), (12, 3, True), (32, 2, False)])

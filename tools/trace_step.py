@@ -28,7 +28,10 @@ wl = dict(BN.WORKLOADS["c51_b32"]); wl["B"] = B
 cfg = make_config("c51", per=True, n_step=3, batch_size=B, replay_size=1_000_000, double_q=True, dueling=True, num_envs=16, action_dim=4)
 rp = ReplayDataset(cfg, native_nstep=True)
 BN.fill_shard(rp, 1_000_000, 16, 1234, torch)
-hp = BN.HotPath(rp, wl, L, 4, torch)
+BN.GATHER_WINDOW = "auto" if os.environ.get("A0_GATHER_WINDOW", "auto") == "auto" else int(os.environ["A0_GATHER_WINDOW"])
+BN.K4_PRIORITY = os.environ.get("A0_K4_PRIORITY", "1") != "0"
+_w = os.environ.get("A0_GATHER_WAVES", "auto")             # auto | none | 1,1,2,16 ...: the gather schedule of the step
+hp = BN.HotPath(rp, wl, L, 4, torch, waves=_w if _w in ("auto", "none") else [int(x) for x in _w.split(",")])
 hp.overlap_sg = overlap
 if k4_only:
     hp.rp.push_dynamic()
@@ -129,7 +132,7 @@ if m5.any():
     pts = [c0] + [x5[i] for i in range(7)]
     print("K2b (one CTA) phases, SM cycles: " + " | ".join(f"{l} {int(pts[i + 1] - pts[i])}" for i, l in enumerate(lab5)
                                                                  if pts[i + 1] and pts[i]) + f" | total {int(x5[6] - c0)}")
-print(f"B={B} L={L} overlap={overlap} records={n}; times in us from the first traced entry; globaltimer tick = "
+print(f"B={B} L={L} overlap={overlap} gather waves (batches)={[w[1] for w in hp.waves] if hp.waves else None} records={n}; times in us from the first traced entry; globaltimer tick = "
       f"{int(np.min(np.diff(np.unique(np.concatenate([t0, t1])))))} ns")
 print(f"{'kernel':8s} {'ctas':>5s} {'first entry':>12s} {'median ready':>13s} {'last ready':>11s} {'last exit':>10s}")
 for r in rows:
