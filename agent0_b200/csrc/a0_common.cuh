@@ -145,6 +145,7 @@ void a0_set_c51_fast(int on);
 void a0_set_k2b_small(int on);
 void a0_set_k2b_chunks(int on);
 void a0_set_k2b_sparse(int max_paths);
+void a0_set_k2a_rounds(int on);
 void a0_set_qh_sorted(int on);
 void a0_set_k6_global(int on);
 

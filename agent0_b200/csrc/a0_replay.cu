@@ -119,6 +119,7 @@ extern "C" int a0_set_option(int32_t option, int64_t value) {
   if (option == A0_OPT_C51_FAST) { a0_set_c51_fast(value != 0); return A0_OK; }
   if (option == A0_OPT_K2B_SMALL) { a0_set_k2b_small(value != 0); return A0_OK; }
   if (option == A0_OPT_K2B_CHUNKS) { a0_set_k2b_chunks(value != 0); return A0_OK; }
+  if (option == A0_OPT_K2A_ROUNDS) { a0_set_k2a_rounds(value != 0); return A0_OK; }
   if (option == A0_OPT_K2B_SPARSE) {
     A0_REQUIRE(value >= 0 && value <= 32, "a0_set_option: A0_OPT_K2B_SPARSE must be 0..32");
     a0_set_k2b_sparse((int)value);
@@ -509,9 +510,13 @@ __device__ __forceinline__ int a0_unique_frames(const int32_t (&slot)[A0_SLOTS],
 // are issued as soon as the first record is known, so the dependent walk along the n-step links
 // (two more HBM round trips at n = 3) overlaps the first 28 KB of frame traffic.
 constexpr int K3_RING = 4;
-__global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
+// (A ring of 8 -- every distinct frame of a transition in flight at once, 56 KB, 4 CTAs per SM -- was measured for the
+// ordered waves of a small draw, where a CTA's own latency is what the first K4 waits for: no difference, 68.17 us per
+// batch-32 step either way; the latency is the record fetch, the first loads and the store drain, not the refills.)
+template <int RING>
+__device__ __forceinline__ void a0_k3_gather_body(const A0GatherArgs& g) {
   extern __shared__ __align__(128) uint8_t a0_smem[];
-  __shared__ __align__(8) uint64_t bars[K3_RING];
+  __shared__ __align__(8) uint64_t bars[RING];
   if (threadIdx.x != 0) return;
   A0_T0();
   const int b = blockIdx.x;
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
     // imply the sampler's (weights, priorities), which is what the successors rely on.
     asm volatile("griddepcontrol.launch_dependents;");
 #pragma unroll
-    for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
+    for (int r = 0; r < RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
     a0_fence_barrier_init();
     // The poll is bounded: the paired sampler posts the word within microseconds; without it (a failed
     // launch, a mis-paired caller) the CTA gives up after mail_timeout_ns, raises the handle's fault word
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   };
   if (!g.mail) {
 #pragma unroll
-    for (int r = 0; r < K3_RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
+    for (int r = 0; r < RING; ++r) a0_mbar_init(bar0 + 8 * r, 1);
     a0_fence_barrier_init();
   }
   int32_t uslot[A0_SLOTS];
@@ -610,9 +615,9 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
       a0_unique_add(s4[j], j, uslot, dmask, U);
     }
   }
-  const int U0 = U;                      // <= A0_STACK == K3_RING
+  const int U0 = U;                      // <= A0_STACK <= RING
 #pragma unroll
-  for (int u = 0; u < K3_RING; ++u)
+  for (int u = 0; u < RING; ++u)
     if (u < U0) load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, bar0 + 8 * u);
   // the n-step walk and the next stack, while those loads are in flight
   int4 sc;
@@ -627,22 +632,22 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   }
   if (!ok && g.action_out) g.action_out[b] = -1;
 #pragma unroll
-  for (int u = 0; u < K3_RING; ++u)
+  for (int u = 0; u < RING; ++u)
     if (u >= U0 && u < U) load(buf0 + u * F, g.frames + (size_t)uslot[u] * F, bar0 + 8 * u);
   uint8_t* out = g.frames_out + (size_t)b * A0_SLOTS * F;
 #pragma unroll
   for (int u = 0; u < A0_SLOTS; ++u) {
     if (u < U) {
-      const int r = u % K3_RING;
-      a0_mbar_wait(bar0 + 8 * r, (u / K3_RING) & 1);
+      const int r = u % RING;
+      a0_mbar_wait(bar0 + 8 * r, (u / RING) & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < A0_SLOTS; ++j)
         if (dmask[u] & (1u << j)) store(out + (size_t)j * F, buf0 + r * F);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      if (u + K3_RING < U) {
+      if (u + RING < U) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        load(buf0 + r * F, g.frames + (size_t)uslot[u + K3_RING] * F, bar0 + 8 * r);
+        load(buf0 + r * F, g.frames + (size_t)uslot[u + RING] * F, bar0 + 8 * r);
       }
     }
   }
@@ -654,6 +659,8 @@ __global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) {
   A0_TEND(3);
   if (g.mail) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+
+__global__ void __launch_bounds__(32) a0_k3_gather_tma(const A0GatherArgs g) { a0_k3_gather_body<K3_RING>(g); }
 
 // Variant 3: the same data movement split over TWO CTAs per transition (even / odd distinct
 // frames), each with a two-buffer ring (14 KB): 2x finer work units even out the SM load of a
@@ -1029,7 +1036,6 @@ static int a0_k3_smem_attr(a0_replay_t* h, size_t smem) {
   }
   return A0_OK;
 }
-
 // The gather half of a0_rb_sample_gather: variant 0 taking its record positions from the mailbox, always
 // launched with programmatic stream serialization so that it becomes resident under the sampler.
 int a0_gather_launch_mail(a0_replay* h, const int64_t* idx, long long* mail, int32_t count, int32_t n_step, double gamma,

@@ -62,29 +62,21 @@ __device__ __forceinline__ void a0_rng_done(const A0Rng& rng, unsigned long long
   }
 }
 
-__global__ void __launch_bounds__(K2A_WARPS * 32)
-a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
-              int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
-              int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
-              unsigned int* counter, float* bmax, const float* __restrict__ dyn, const A0Rng rng,
-              long long* __restrict__ mail) {
-  A0_T0();
-  A0_PDL_PROLOGUE();
-  A0_TMID();
-  if (dyn) {            // top / beta / sum_offset live on the device (a0_rb_set_dynamic): graph-replay safe
-    top = __ldcg(dyn);
-    beta = __ldcg(dyn + 1);
-    sum_offset = __ldcg(dyn + 2);
-  }
-  // Device-resident call counter (rng.call < 0): every warp reads it before anything else; it is
-  // advanced for the next launch / graph replay only after every CTA has reported in below
-  // (a0_rng_done), i.e. after every warp of the launch has read it.
-  const bool rng_dev = u == nullptr && rng.call < 0;
-  const unsigned long long call = rng_dev ? __ldcg(rng.call_dev) : (unsigned long long)rng.call;
+// One unit of the sampler: the 8 draws [8 * unit, 8 * unit + 8), one per warp (descent, mailbox, IS-weight epilogue).
+// `units` = units of the whole launch (a CTA runs `rounds` of them, a0_k2a_sample below).
+__device__ __forceinline__ void
+a0_k2a_unit(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
+            int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
+            int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
+            unsigned int* counter, float* bmax, const A0Rng& rng, long long* __restrict__ mail, const bool rng_dev,
+            const unsigned long long call, const float root, const int unit, const unsigned int units
+#ifdef A0_TRACE
+            , const unsigned long long _t0, const unsigned long long _t2, const unsigned long long (&_tx)[8]
+#endif
+            ) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int g = blockIdx.x * K2A_WARPS + warp;
-  const float root = __ldcg(tree + 1);
+  const int g = unit * K2A_WARPS + warp;
   float leaf_w = 0.0f;
   if (g < total) {
     const int b = g % batch;
@@ -140,7 +132,7 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
     if (uniform && weight_out && g < total && lane == 0) weight_out[g] = 1.0f;   // ReplayEnum.uniform: weights = 1 (trainer.py:95-96)
     if (rng_dev) {
       __syncthreads();                                  // every warp of this CTA has read the counter
-      if (threadIdx.x == 0) a0_rng_done(rng, call, gridDim.x);
+      if (threadIdx.x == 0) a0_rng_done(rng, call, units);
     }
     return;
   }
@@ -220,6 +212,54 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
   }
 }
 
+// The launch: CTA c runs units c, c + gridDim.x, ... (`rounds` of them); one round by default.  A0_OPT_K2A_ROUNDS
+// (measured alternative, off): 20 x 512 draws are 10 240 warps on 9 472 warp slots, and the gather that is launched
+// under the sampler can only start once EVERY sampler CTA has started -- with one round its first CTAs enter 11 us
+// after the sampler's (device timeline), with two rounds 1.3 us after.  The early CTAs only poll their mailbox
+// sooner, though: the sampler itself takes 27 instead of 17 us and the batch-512 step does not get shorter (233.9
+// against 231.8 us), so the option stays off.
+__global__ void __launch_bounds__(K2A_WARPS * 32)
+a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float* __restrict__ u, int32_t total,
+              int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
+              int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
+              unsigned int* counter, float* bmax, const float* __restrict__ dyn, const A0Rng rng,
+              long long* __restrict__ mail, int32_t rounds) {
+  A0_T0();
+  A0_PDL_PROLOGUE();
+  A0_TMID();
+  if (dyn) {            // top / beta / sum_offset live on the device (a0_rb_set_dynamic): graph-replay safe
+    top = __ldcg(dyn);
+    beta = __ldcg(dyn + 1);
+    sum_offset = __ldcg(dyn + 2);
+  }
+  // Device-resident call counter (rng.call < 0): every warp reads it before anything else; it is
+  // advanced for the next launch / graph replay only after every unit has reported in
+  // (a0_rng_done), i.e. after every warp of the launch has read it.
+  const bool rng_dev = u == nullptr && rng.call < 0;
+  const unsigned long long call = rng_dev ? __ldcg(rng.call_dev) : (unsigned long long)rng.call;
+  const float root = __ldcg(tree + 1);
+  const unsigned int units = gridDim.x * (unsigned int)rounds;
+  for (int r = 0; r < rounds; ++r) {
+    a0_k2a_unit(tree, P, D, u, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, counter, bmax, rng,
+                mail, rng_dev, call, root, r * (int)gridDim.x + (int)blockIdx.x, units
+#ifdef A0_TRACE
+                , _t0, _t2, _tx
+#endif
+                );
+    if (r + 1 < rounds) __syncthreads();            // the unit's shared words are reused by the next one
+  }
+}
+
+static int g_k2a_rounds = -1;      // A0_OPT_K2A_ROUNDS: a sampler launch too large to be resident at once runs several units per CTA
+static bool a0_option_k2a_rounds() {
+  if (g_k2a_rounds < 0) {
+    const char* e = getenv("A0_K2A_ROUNDS");
+    g_k2a_rounds = e ? (atoi(e) != 0) : 0;
+  }
+  return g_k2a_rounds != 0;
+}
+void a0_set_k2a_rounds(int on) { g_k2a_rounds = on != 0; }
+
 __global__ void a0_set_dyn(float* dyn, float top, float beta, float sum_offset) {
   dyn[0] = top; dyn[1] = beta; dyn[2] = sum_offset;
 }
@@ -242,7 +282,23 @@ static int a0_sample_launch(a0_replay_t* h, const float* u, const A0Rng& rng, in
   A0_REQUIRE(idx_out && prio_out, "%s: NULL argument", who);
   A0_REQUIRE(total / batch <= A0_MAX_BATCHES, "%s: at most %d batches per call", who, A0_MAX_BATCHES);
   A0DeviceGuard guard(h->device);
-  const int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
+  int blocks = (total + K2A_WARPS - 1) / K2A_WARPS;
+  int rounds = 1;
+  {
+    // all CTAs resident at once (8 CTAs of 8 warps per SM), see a0_k2a_sample
+    static thread_local int sms[64] = {0};
+    int n_sm = 148;
+    if (h->device < 64) {
+      if (!sms[h->device]) A0_CUDA(cudaDeviceGetAttribute(&sms[h->device], cudaDevAttrMultiProcessorCount, h->device));
+      n_sm = sms[h->device];
+    }
+    const int resident = n_sm * (2048 / (K2A_WARPS * 32));
+    if (blocks > resident && a0_option_k2a_rounds()) {
+      for (int r = 2; r <= 8; ++r)
+        if (blocks % r == 0 && blocks / r <= resident) { rounds = r; break; }
+    }
+    blocks /= rounds;
+  }
   if (mail) {
     // The gather's CTAs (28 KB of shared memory each) can only join an SM whose shared-memory carve-out
     // already fits them: an SM running sampler CTAs under the default (L1-heavy) carve-out is closed
@@ -256,7 +312,8 @@ static int a0_sample_launch(a0_replay_t* h, const float* u, const A0Rng& rng, in
   }
   A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, A0_PDL_K2, h->tree, h->P, h->D, u, total, batch,
             top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter,
-            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr), rng, mail);
+            reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr), rng, mail,
+            (int32_t)rounds);
   return A0_OK;
 }
 

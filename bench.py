@@ -69,7 +69,7 @@ def parse():
                    "for its wave only), none (one gather launch before the first K4), or wave sizes in batches, e.g. 1,1,2,4,12")
     p.add_argument("--gather-window", default="auto", help="ordered fetch inside the gather waves: draws in flight beyond the completed ones (auto | 0 = no limit | n)")
     p.add_argument("--no-k4-priority", action="store_true", help="K4 + K2b on the caller's stream instead of the loop's high-priority stream")
-    p.add_argument("--pdl-at-joins", action="store_true", help="the K4 that joins a gather wave keeps its programmatic-launch attribute")
+    p.add_argument("--no-pdl-at-joins", action="store_true", help="the K4 that joins a gather wave is launched without its programmatic-launch attribute")
     p.add_argument("--cpu-workers", type=int, default=-1, help="--impl reference DataLoader workers (-1: all cores)")
     return p.parse_args()
 
@@ -250,7 +250,7 @@ def block_stats(blocks, units_per_block):
 EMIT = print
 INNER = 20
 GATHER_WAVES = "auto"    # --gather-waves
-PDL_AT_JOINS = False     # --pdl-at-joins
+PDL_AT_JOINS = True      # --no-pdl-at-joins
 GATHER_WINDOW = "auto"   # --gather-window
 K4_PRIORITY = True       # --no-k4-priority
 RNG_SEED = 20261017      # the sampler draws its own uniforms (Philox inside K2a); None: torch's uniform_ + a0_pt_sample
@@ -563,7 +563,7 @@ def run_ours(args):
     global RNG_SEED, GATHER_WAVES, PDL_AT_JOINS, GATHER_WINDOW, K4_PRIORITY
     GATHER_WINDOW = "auto" if args.gather_window == "auto" else int(args.gather_window)
     K4_PRIORITY = not args.no_k4_priority
-    PDL_AT_JOINS = bool(args.pdl_at_joins)
+    PDL_AT_JOINS = not args.no_pdl_at_joins
     GATHER_WAVES = None if args.gather_waves == "none" else ("auto" if args.gather_waves == "auto" else [int(x) for x in args.gather_waves.split(",")])
     if args.torch_rng:
         RNG_SEED = None

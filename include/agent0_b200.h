@@ -97,6 +97,11 @@ const char* a0_last_error(void);
  * siblings fetched from the tree in one round trip) instead of recomputing all 4095 inner nodes of the chunk in
  * shared memory; 0 = always recompute the whole chunk.  Same tree either way (node == fl32(left + right)).     */
 #define A0_OPT_K2B_SPARSE 12
+/* A0_OPT_K2A_ROUNDS (default 0; A0_K2A_ROUNDS in the environment): a sampler launch with more CTAs than the device
+ * holds at once (20 x 512 draws: 1280 CTAs on 1184 slots) runs two or more 8-draw units per CTA so that the whole
+ * grid -- and with it the gather launched under it -- is resident from the start.  Same draws and weights; a
+ * measured alternative that did not shorten the batch-512 step.                                          */
+#define A0_OPT_K2A_ROUNDS 13
 /* A0_OPT_QH_SORTED (default 1; A0_QH_SORTED in the environment): a0_loss_quantile with more than 64 target
  * and more than 64 online quantiles and no FQF fraction term (QR-200) evaluates the pair sums in
  * O(N log N) from the sorted targets (float64 prefix sums): 1 = one CTA per sample, merge sort in shared

@@ -231,7 +231,7 @@ def test_reporting_graphs_with_ingest_published_scalars_equal_the_plain_loop():
 @pytest.mark.parametrize("Bn,k,per,waves,pdl,window,prio", [
     (32, 20, True, "auto", False, "auto", True), (32, 20, True, [1, 1, 2, 16], True, 8, True), (512, 4, True, "auto", False, "auto", True),
     (12, 5, True, [2, 3], False, 1, False), (32, 6, False, "auto", False, 40, True), (16, 3, True, [1, 2], True, 0, False),
-    (64, 20, True, [1] * 20, False, 700, True)])
+    (64, 20, True, [1] * 20, False, 700, True), (512, 8, True, "auto", True, "auto", True)])
 def test_gather_waves_equal_the_single_gather_launch(Bn, k, per, waves, pdl, window, prio):
     """gather_waves: K2a and the gather cut into waves run on a side stream (a0_rb_sample_mail + a0_rb_gather_mail per wave),
     batch k's K4 waits only for the wave that holds it.  Against the same loop with ONE gather launch on a twin shard with
@@ -266,8 +266,14 @@ def test_gather_waves_equal_the_single_gather_launch(Bn, k, per, waves, pdl, win
         lb.frames.zero_(); lb.idx.fill_(-1); lb.loss.fill_(-1.0)
         la.step(); lb.step()
         same()
-    lb.step(fused_k4=True); la.step(fused_k4=True)         # one K4 launch for all batches waits for the last wave
+    lb.step(fused_k4=True); la.step(fused_k4=True)         # one K4 launch for all batches waits for every wave
     same()
+    if per:                                                # the result hand-over to mapped host memory
+        rep = lb.bind_report(1)
+        rep[0][0].fill_(-7); rep[0][1].fill_(-7.0)
+        la.step(); lb.step(slot=0)
+        same()
+        assert torch.equal(rep[0][0], lb.idx.cpu()) and torch.equal(rep[0][1], lb.loss.cpu())
     la.capture(warm=1); lb.capture(warm=1)
     for _ in range(4):
         lb.frames.zero_(); lb.loss.fill_(-1.0)
@@ -279,6 +285,44 @@ def test_gather_waves_equal_the_single_gather_launch(Bn, k, per, waves, pdl, win
     from agent0_b200 import _lib
     mask = __import__("ctypes").c_int64(-1)
     assert _lib.load().a0_get_option(_lib.OPT_PDL, __import__("ctypes").byref(mask)) == 0 and mask.value == 1     # restored after the joins
+
+
+def test_sampler_units_per_cta_draw_the_same_batches():
+    """A0_OPT_K2A_ROUNDS: 20 x 512 draws as 640 CTAs of two 8-draw units instead of 1280 CTAs of one -- the same indices,
+    priorities and IS weights, with caller-supplied uniforms and with the sampler's own generator (whose call counter
+    advances once per launch either way)."""
+    from agent0_b200 import _lib
+    from agent0_b200.hotloop import ReplayTargetLoop
+    lib = _lib.load()
+    rp = _shard("c51")
+    Bn, k = 512, 20
+    o = _outputs("dqn", Bn * k)
+    la = ReplayTargetLoop(rp, "dqn", Bn, k, A, o, n_step=3, gather_waves=None)
+    lb = ReplayTargetLoop(rp, "dqn", Bn, k, A, o, n_step=3, gather_waves=None)
+    rp.push_dynamic()
+    la.u.uniform_(generator=torch.Generator("cuda").manual_seed(3)); lb.u.copy_(la.u)
+    try:
+        la.sample()
+        assert lib.a0_set_option(13, 1) == 0
+        lb.sample()
+        torch.cuda.synchronize()
+        for f in ("idx", "prio", "w"):
+            assert torch.equal(getattr(la, f), getattr(lb, f)), f
+        la.rng_seed = lb.rng_seed = 77
+        for call in (5, 6):
+            lib.a0_set_option(13, 0)
+            rp.rng_seek(call); la.sample()
+            lib.a0_set_option(13, 1)
+            rp.rng_seek(call); lb.idx.fill_(-1); lb.sample_gather()
+            lb.sample()                                    # the counter advanced by exactly one per launch: this is call + 1
+            torch.cuda.synchronize()
+            lib.a0_set_option(13, 0)
+            rp.rng_seek(call + 1); la.sample()
+            torch.cuda.synchronize()
+            for f in ("idx", "prio", "w"):
+                assert torch.equal(getattr(la, f), getattr(lb, f)), f
+    finally:
+        lib.a0_set_option(13, 0)
 
 
 def test_gather_mail_argument_errors():
