@@ -24,6 +24,7 @@ A0_TRACE_SETTER(a0_trace_set_sumtree)
 // sub-heap node h for h = 2..31) and walks it through shuffles, with exactly the scalar arithmetic.
 // ------------------------------------------------------------------------------------------------
 constexpr int K2A_WARPS = 8;
+constexpr int K2A_TOP = 10;         // tree levels every sampler CTA copies to shared memory (8 KB) before its descents
 
 // Philox4x32-10 (Salmon et al., SC'11; the generator behind curand and torch's CUDA RNG), first
 // output word.  The sampler's own uniforms: draw g of call c under seed s is
@@ -69,7 +70,8 @@ a0_k2a_unit(const float* __restrict__ tree, int64_t P, int32_t D, const float* _
             int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
             int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
             unsigned int* counter, float* bmax, const A0Rng& rng, long long* __restrict__ mail, const bool rng_dev,
-            const unsigned long long call, const float root, const int unit, const unsigned int units
+            const unsigned long long call, const float root, const int unit, const unsigned int units,
+            const float* __restrict__ s_top, const int top_levels
 #ifdef A0_TRACE
             , const unsigned long long _t0, const unsigned long long _t2, const unsigned long long (&_tx)[8]
 #endif
@@ -93,6 +95,18 @@ a0_k2a_unit(const float* __restrict__ tree, int64_t P, int32_t D, const float* _
     int64_t v = 1;          // current node, warp-uniform
     float leaf = root;
     int left = D;
+    if (top_levels > 0) {
+      // the first levels from the CTA's shared-memory copy of the top of the tree: the same comparisons and
+      // subtractions, one L2 round trip (the copy) instead of two
+      int h = 1;
+      for (int s = 0; s < top_levels; ++s) {
+        const float L = s_top[2 * h], R = s_top[2 * h + 1];
+        if (t < L || !(R > 0.0f)) { h = 2 * h; leaf = L; }
+        else { t = __fsub_rn(t, L); h = 2 * h + 1; leaf = R; }
+      }
+      v = h;
+      left = D - top_levels;
+    }
     while (left > 0) {
       const int c = left < 5 ? left : 5;
       // sub-heap node h lives at tree[(v << l) + (h - (1 << l))], l = floor(log2 h)
@@ -223,7 +237,7 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
               int32_t batch, float top, float beta, float sum_offset, int32_t uniform,
               int64_t* __restrict__ idx_out, float* __restrict__ prio_out, float* __restrict__ weight_out,
               unsigned int* counter, float* bmax, const float* __restrict__ dyn, const A0Rng rng,
-              long long* __restrict__ mail, int32_t rounds) {
+              long long* __restrict__ mail, int32_t rounds, int32_t top_levels) {
   A0_T0();
   A0_PDL_PROLOGUE();
   A0_TMID();
@@ -237,11 +251,19 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
   // (a0_rng_done), i.e. after every warp of the launch has read it.
   const bool rng_dev = u == nullptr && rng.call < 0;
   const unsigned long long call = rng_dev ? __ldcg(rng.call_dev) : (unsigned long long)rng.call;
-  const float root = __ldcg(tree + 1);
+  // levels 0 .. top_levels of the tree (nodes 1 .. 2^(top_levels+1) - 1) into shared memory, once per CTA
+  __shared__ __align__(16) float s_top[2 << K2A_TOP];
+  if (top_levels > 0) {
+    const int n4 = (2 << top_levels) >> 2;
+    for (int i = threadIdx.x; i < n4; i += K2A_WARPS * 32)
+      reinterpret_cast<float4*>(s_top)[i] = __ldcg(reinterpret_cast<const float4*>(tree) + i);
+    __syncthreads();
+  }
+  const float root = top_levels > 0 ? s_top[1] : __ldcg(tree + 1);
   const unsigned int units = gridDim.x * (unsigned int)rounds;
   for (int r = 0; r < rounds; ++r) {
     a0_k2a_unit(tree, P, D, u, total, batch, top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, counter, bmax, rng,
-                mail, rng_dev, call, root, r * (int)gridDim.x + (int)blockIdx.x, units
+                mail, rng_dev, call, root, r * (int)gridDim.x + (int)blockIdx.x, units, s_top, top_levels
 #ifdef A0_TRACE
                 , _t0, _t2, _tx
 #endif
@@ -250,6 +272,14 @@ a0_k2a_sample(const float* __restrict__ tree, int64_t P, int32_t D, const float*
   }
 }
 
+static int g_k2a_top = -1;         // A0_K2A_TOP=0: every level of the descent from L2 (the round-1/2 sampler)
+static bool a0_option_k2a_top() {
+  if (g_k2a_top < 0) {
+    const char* e = getenv("A0_K2A_TOP");
+    g_k2a_top = e ? (atoi(e) != 0) : 1;
+  }
+  return g_k2a_top != 0;
+}
 static int g_k2a_rounds = -1;      // A0_OPT_K2A_ROUNDS: a sampler launch too large to be resident at once runs several units per CTA
 static bool a0_option_k2a_rounds() {
   if (g_k2a_rounds < 0) {
@@ -313,7 +343,7 @@ static int a0_sample_launch(a0_replay_t* h, const float* u, const A0Rng& rng, in
   A0_LAUNCH(a0_k2a_sample, (unsigned)blocks, K2A_WARPS * 32, 0, (cudaStream_t)stream_, 1, A0_PDL_K2, h->tree, h->P, h->D, u, total, batch,
             top, beta, sum_offset, uniform, idx_out, prio_out, weight_out, h->counter,
             reinterpret_cast<float*>(h->counter + A0_MAX_BATCHES + 16), (const float*)(top < 0.0f ? h->dyn : nullptr), rng, mail,
-            (int32_t)rounds);
+            (int32_t)rounds, (int32_t)(a0_option_k2a_top() ? (h->D < K2A_TOP ? (h->D >= 1 ? h->D : 0) : K2A_TOP) : 0));
   return A0_OK;
 }
 

@@ -829,6 +829,12 @@ __device__ __forceinline__ int a0_qs_merge(const float* __restrict__ src, float*
   return out;
 }
 
+// SPEC (qsel given, A <= QH_SPEC_A): every thread fetches its quantile of ALL actions from both networks together with
+// the selection values, the taken action and the scalars in ONE batch of loads and picks in registers -- no arg-max
+// hand-off through shared memory, no second (action-dependent) memory round trip -- and the sample's gradient block is
+// zeroed under the latency of those loads.  Under the gather's traffic (the K4 launches of a batch-512 step run while
+// the later batches are being fetched) a dependent round trip costs several microseconds, not 0.4.
+template <bool SPEC, int AMAX>
 __global__ void __launch_bounds__(QS_MAX)
 a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict__ q, const float* __restrict__ qt,
                       const float* __restrict__ taus, const float* __restrict__ qsel, int32_t Ni, int32_t Nj,
@@ -850,6 +856,36 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
   const float* tb = qt + (size_t)b * A * Ni;
   // runs without threads (beyond blockDim) hold pads in both buffers: they are never moved and never counted
   for (int i = nthreads + tid; i < QS_MAX; i += nthreads) { bufA[i] = a0_qs_pad(i); bufB[i] = a0_qs_pad(i); }
+  float* gb = grad + (size_t)b * A * Nj;
+  int a;
+  float w, qj = 0.0f, tau = 0.0f, x;
+  if (SPEC) {
+    float qs[AMAX], tv[AMAX], qv[AMAX];
+#pragma unroll
+    for (int a2 = 0; a2 < AMAX; ++a2) {
+      const bool on = a2 < A;
+      qs[a2] = on ? qsel[(size_t)b * A + a2] : -INFINITY;
+      tv[a2] = (on && tid < Ni) ? tb[a2 * sA_t + tid * sN_t] : 0.0f;
+      qv[a2] = (on && tid < Nj) ? qb[a2 * sA_q + tid * sN_q] : 0.0f;
+    }
+    a = (int)c.action[b];
+    const float r = c.reward[b], d = c.done[b];
+    w = c.weight[b];
+    if (tid < Nj) tau = taus ? taus[(size_t)b * Nj + tid] : __fdiv_rn((float)(2 * tid + 1), 2.0f * (float)Nj);
+    for (int i = tid; i < A * Nj; i += nthreads) gb[i] = 0.0f;      // the taken action's entries are rewritten after the barriers below
+    int a_star = 0;
+    float best = qs[0];
+#pragma unroll
+    for (int a2 = 1; a2 < AMAX; ++a2)
+      if (qs[a2] > best) { best = qs[a2]; a_star = a2; }       // first maximum, as torch.argmax
+    float tsel = 0.0f;
+#pragma unroll
+    for (int a2 = 0; a2 < AMAX; ++a2) {
+      if (a2 == a_star) tsel = tv[a2];
+      if (a2 == a) qj = qv[a2];
+    }
+    x = tid < Ni ? a0_td_target(r, d, c.gamma_n, tsel) : a0_qs_pad(tid);
+  } else {
   // ---- action selection (as a0_k4_quantile) ------------------------------------------------------------
   if (qsel) {
     if (wid == 0) {
@@ -869,17 +905,18 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
       if (lane == 0) s_astar = as;
     }
   }
-  const int a = (int)c.action[b];
-  const float r = c.reward[b], d = c.done[b], w = c.weight[b];
-  float qj = 0.0f, tau = 0.0f;
+  a = (int)c.action[b];
+  const float r = c.reward[b], d = c.done[b];
+  w = c.weight[b];
   if (tid < Nj) {
     qj = qb[a * sA_q + tid * sN_q];
     tau = taus ? taus[(size_t)b * Nj + tid] : __fdiv_rn((float)(2 * tid + 1), 2.0f * (float)Nj);
   }
   __syncthreads();
   const int a_star = s_astar;
+  x = tid < Ni ? a0_td_target(r, d, c.gamma_n, tb[a_star * sA_t + tid * sN_t]) : a0_qs_pad(tid);
+  }
   // ---- sort the targets: one bitonic network per warp, then merge 32 -> 64 -> 128 -> 256 ------------------
-  float x = tid < Ni ? a0_td_target(r, d, c.gamma_n, tb[a_star * sA_t + tid * sN_t]) : a0_qs_pad(tid);
 #pragma unroll
   for (int lk = 1; lk <= 5; ++lk) {
 #pragma unroll
@@ -948,9 +985,10 @@ a0_k4_quantile_sorted(const A0Common c, int32_t layout, const float* __restrict_
     gsum = (float)((1.0 - td) * (nA + nB * qd - s1B) + td * (nC * qd - s1C - nD));
   }
   const float total = a0_block_sum(lsum, red, nwarps);
-  float* gb = grad + (size_t)b * A * Nj;
-  for (int i = tid; i < A * Nj; i += nthreads) gb[i] = 0.0f;
-  __syncthreads();
+  if (!SPEC) {
+    for (int i = tid; i < A * Nj; i += nthreads) gb[i] = 0.0f;
+    __syncthreads();
+  }
   if (tid < Nj) gb[a * sA_q + tid * sN_q] = __fdiv_rn(w, (float)Ni) * gsum;
   if (tid == 0) a0_emit(c, b, __fdiv_rn(total, (float)Ni));
 }
@@ -1106,6 +1144,14 @@ a0_k4_quantile_warp(const A0Common c, int32_t layout, const float* __restrict__ 
   if (lane == 0) a0_emit(c, b, __fdiv_rn(total, (float)Ni));
 }
 
+static int g_qh_spec = -1;         // A0_QH_SPEC=0: the sorted QR kernel without the all-action fetch (measured alternative)
+static bool a0_option_qh_spec() {
+  if (g_qh_spec < 0) {
+    const char* e = getenv("A0_QH_SPEC");
+    g_qh_spec = e ? (atoi(e) != 0) : 1;
+  }
+  return g_qh_spec != 0;
+}
 static int g_qh_sorted = -1;
 static int a0_option_qh_sorted() {
   if (g_qh_sorted < 0) {
@@ -1141,8 +1187,15 @@ extern "C" int a0_loss_quantile(const a0_loss_common_t* c, int32_t layout, const
     return A0_OK;
   }
   if (!q_bar && Ni > 64 && Nj > 64 && a0_option_qh_sorted() == 1) { // QR-sized: O(N log N) sorted-target form, one CTA per sample
-    A0_LAUNCH(a0_k4_quantile_sorted, (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
-              taus, qsel, Ni, Nj, grad);
+    if (qsel && c->A <= 4 && a0_option_qh_spec())
+      A0_LAUNCH((a0_k4_quantile_sorted<true, 4>), (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
+                taus, qsel, Ni, Nj, grad);
+    else if (qsel && c->A <= QH_SPEC_A && a0_option_qh_spec())
+      A0_LAUNCH((a0_k4_quantile_sorted<true, QH_SPEC_A>), (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
+                taus, qsel, Ni, Nj, grad);
+    else
+      A0_LAUNCH((a0_k4_quantile_sorted<false, 1>), (unsigned)c->B, (unsigned)threads, 0, (cudaStream_t)stream, 1, A0_PDL_K4, a0_unpack(c), layout, q, qt,
+                taus, qsel, Ni, Nj, grad);
     return A0_OK;
   }
   if (layout == 1 && qsel && c->A <= QH_SPEC_A && threads <= 64)
