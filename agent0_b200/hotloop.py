@@ -27,11 +27,44 @@ from . import _lib
 ALGOS = ("dqn", "mdqn", "c51", "qr", "iqn", "fqf")
 
 
+def wave_plan(L, B, frame_bytes, spec="auto"):
+    """The gather waves of a draw of L batches of B transitions: [(first batch, batches, first draw, draws)] per wave, or
+    None for a single gather launch.  spec "auto": one wave per batch when a batch's gather (16 frames of traffic per
+    transition) moves 10 MB or more -- it then outlasts a K4 launch, and the target kernels hide under the following
+    waves; otherwise the K4 chain is the longer side and the waves only have to stay ahead of it: 1, 1, 2, 4, ...
+    batches (a tail shorter than its predecessor joins it).  A list gives the wave sizes in batches; None / 0 / a single
+    wave / L < 2: no waves."""
+    if not spec or L < 2:
+        return None
+    if isinstance(spec, str):
+        assert spec == "auto", spec
+        if B * 16 * frame_bytes >= 10_000_000:
+            sizes = [1] * L
+        else:
+            sizes, w = [1], 1
+            while sum(sizes) < L:
+                sizes.append(min(w, L - sum(sizes)))
+                w *= 2
+            if len(sizes) > 1 and sizes[-1] < sizes[-2]:
+                tail = sizes.pop()
+                sizes[-1] += tail
+    else:
+        sizes = [int(x) for x in spec]
+        assert all(x > 0 for x in sizes) and sum(sizes) == L, "gather_waves must be positive batch counts that sum to learner_steps"
+    if len(sizes) < 2:
+        return None
+    plan, b0 = [], 0
+    for n in sizes:
+        plan.append((b0, n, b0 * B, n * B))
+        b0 += n
+    return plan
+
+
 class ReplayTargetLoop:
     def __init__(self, replay, algo, batch_size, learner_steps, action_dim, outputs, n_step=None, double_q=True,
                  per=None, variant=0, discount=None, alpha=0.5, eps=0.01, c51=(51, -10.0, 10.0), mdqn=(0.03, -1.0),
                  frames=None, rng_seed=None, overlap_sample_gather=True, want_prio=False, early_update=True,
-                 gather_waves="auto", pdl_at_joins=True, gather_window="auto", k4_priority=True):
+                 gather_waves="auto", pdl_at_joins=True, gather_window="auto", k4_priority=True, waves_when_eager=False):
         """replay: ReplayDataset (native_nstep=True when n_step > 1).  outputs: dict of STATIC f32 device
         tensors holding the network outputs of all L*B sampled transitions, batch k in rows
         [k*B, (k+1)*B): ``online``, ``tgt_next`` (+ ``qsel`` [L*B,A] under double_q / for iqn, fqf;
@@ -56,6 +89,10 @@ class ReplayTargetLoop:
         that run under the gather keep pace with its waves); 0: no limit.
         k4_priority: K4 and K2b run on a high-priority stream of the loop (the gather's CTAs queue for every free slot of
         every SM; without priority the target kernels' CTAs wait behind them), joined back into the caller's stream.
+        waves_when_eager: the waves are a schedule for the CAPTURED step (one graph replay per step).  Issued eagerly a
+        step is bound by the host's launch path (~25 ctypes calls at batch 32), and the waves' extra launches, events and
+        stream switches cost more there than the overlap returns (2.7 against 4.6 M transitions/s), so outside a capture
+        ``step()`` issues the single gather launch unless this is set (the tests set it).
         pdl_at_joins: the K4 that waits for a wave keeps its programmatic-launch attribute (it executes griddepcontrol.wait
         before it reads anything, so every predecessor is complete whichever way the edge is typed): 67.2 against 68.2 us
         per batch-32 step.  False: those K4 launches are plain stream-ordered launches."""
@@ -88,6 +125,7 @@ class ReplayTargetLoop:
         self.gtau = e(T, self.o["taus"].shape[1]) if algo == "fqf" else None
         self.waves = self._wave_plan(gather_waves) if self.overlap_sg else None
         self.pdl_at_joins = bool(pdl_at_joins)
+        self.waves_when_eager = bool(waves_when_eager)
         if self.waves:
             self.side = torch.cuda.Stream(device=dev)
             self.fast = torch.cuda.Stream(device=dev, priority=-1) if k4_priority else None
@@ -140,31 +178,7 @@ class ReplayTargetLoop:
             self.d8.data_ptr(), self.d32.data_ptr(), self.boot.data_ptr(), self._st()), "a0_rb_sample_gather")
 
     def _wave_plan(self, spec):
-        """[(first batch, batches, first draw, draws)] per wave, or None for a single gather launch."""
-        if not spec or self.L < 2:
-            return None
-        if isinstance(spec, str):
-            assert spec == "auto", spec
-            if self.B * 16 * self.rp.F >= 10_000_000:       # a batch's gather outlasts a K4: one wave per batch
-                sizes = [1] * self.L
-            else:                                           # the K4 chain is the longer side: 1, 1, 2, 4, ... batches
-                sizes, w = [1], 1
-                while sum(sizes) < self.L:
-                    sizes.append(min(w, self.L - sum(sizes)))
-                    w *= 2
-                if len(sizes) > 1 and sizes[-1] < sizes[-2]:        # a short tail joins the wave before it
-                    tail = sizes.pop()
-                    sizes[-1] += tail
-        else:
-            sizes = [int(x) for x in spec]
-            assert all(x > 0 for x in sizes) and sum(sizes) == self.L, "gather_waves must be positive batch counts that sum to learner_steps"
-        if len(sizes) < 2:
-            return None
-        plan, b0 = [], 0
-        for n in sizes:
-            plan.append((b0, n, b0 * self.B, n * self.B))
-            b0 += n
-        return plan
+        return wave_plan(self.L, self.B, self.rp.F, spec)
 
     def sample_gather_waves(self):
         """K2a + the gather in waves on the side stream (a0_rb_sample_mail, a0_rb_gather_mail per wave, an event after
@@ -311,7 +325,7 @@ class ReplayTargetLoop:
         """update=False: everything but the priority write-back (StaleByOneLoop issues it during the next step)."""
         if self.rng_seed is None:
             self.u.uniform_()
-        if self.waves:
+        if self.waves and (self.waves_when_eager or torch.cuda.is_current_stream_capturing()):
             self.sample_gather_waves()
             if self.fast is None:
                 self._targets_and_update(fused_k4, slot, update)

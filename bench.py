@@ -68,6 +68,8 @@ def parse():
     p.add_argument("--gather-waves", default="auto", help="gather schedule of the step: auto (waves on a side stream, K4 of batch k waits "
                    "for its wave only), none (one gather launch before the first K4), or wave sizes in batches, e.g. 1,1,2,4,12")
     p.add_argument("--gather-window", default="auto", help="ordered fetch inside the gather waves: draws in flight beyond the completed ones (auto | 0 = no limit | n)")
+    p.add_argument("--eager-waves", action="store_true", help="with --no-graph: issue the gather waves eagerly too (the ncu launch list of the "
+                   "captured schedule; by default an eagerly issued step uses the single gather launch, see hotloop.ReplayTargetLoop)")
     p.add_argument("--no-k4-priority", action="store_true", help="K4 + K2b on the caller's stream instead of the loop's high-priority stream")
     p.add_argument("--no-pdl-at-joins", action="store_true", help="the K4 that joins a gather wave is launched without its programmatic-launch attribute")
     p.add_argument("--cpu-workers", type=int, default=-1, help="--impl reference DataLoader workers (-1: all cores)")
@@ -169,7 +171,7 @@ def make_hotpath(rp, wl, L, A, torch, variant=0, waves=None):
             super().__init__(rp, wl["algo"], wl["B"], L, A, net_outputs(wl["algo"], T, A, torch, rp.device), n_step=wl["n"],
                              double_q=wl["double"], per=wl["per"], variant=variant, discount=0.99, frames=self.frames_pool[0],
                              rng_seed=RNG_SEED, gather_waves=waves, pdl_at_joins=PDL_AT_JOINS,
-                             gather_window=GATHER_WINDOW, k4_priority=K4_PRIORITY)
+                             gather_window=GATHER_WINDOW, k4_priority=K4_PRIORITY, waves_when_eager=EAGER_WAVES)
             self.wl, self.idx_pool = wl, None
 
         def draw_pool(self):
@@ -253,6 +255,7 @@ GATHER_WAVES = "auto"    # --gather-waves
 PDL_AT_JOINS = True      # --no-pdl-at-joins
 GATHER_WINDOW = "auto"   # --gather-window
 K4_PRIORITY = True       # --no-k4-priority
+EAGER_WAVES = False      # --eager-waves
 RNG_SEED = 20261017      # the sampler draws its own uniforms (Philox inside K2a); None: torch's uniform_ + a0_pt_sample
 
 
@@ -560,7 +563,8 @@ def run_ours(args):
 
     wl = WORKLOADS[args.workload]
     L, A = args.learner_steps, args.actions
-    global RNG_SEED, GATHER_WAVES, PDL_AT_JOINS, GATHER_WINDOW, K4_PRIORITY
+    global RNG_SEED, GATHER_WAVES, PDL_AT_JOINS, GATHER_WINDOW, K4_PRIORITY, EAGER_WAVES
+    EAGER_WAVES = bool(args.eager_waves)
     GATHER_WINDOW = "auto" if args.gather_window == "auto" else int(args.gather_window)
     K4_PRIORITY = not args.no_k4_priority
     PDL_AT_JOINS = not args.no_pdl_at_joins

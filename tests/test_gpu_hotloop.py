@@ -245,7 +245,7 @@ def test_gather_waves_equal_the_single_gather_launch(Bn, k, per, waves, pdl, win
     rp_a, rp_b = _shard("c51"), _shard("c51")
     la = ReplayTargetLoop(rp_a, "c51", Bn, k, A, o, n_step=3, per=per, rng_seed=9, gather_waves=None)
     lb = ReplayTargetLoop(rp_b, "c51", Bn, k, A, o, n_step=3, per=per, rng_seed=9, gather_waves=waves, pdl_at_joins=pdl,
-                          gather_window=window, k4_priority=prio)
+                          gather_window=window, k4_priority=prio, waves_when_eager=True)
     if window == "auto":
         assert lb.window == (400 if Bn >= 256 else 128)
     assert la.waves is None and lb.waves is not None and sum(w[1] for w in lb.waves) == k and sum(w[3] for w in lb.waves) == T

@@ -3,7 +3,7 @@
 # headline workload with learner_scaling, and configs[4] (batch 512, 8 M transitions sharded over the GPUs)
 set -u
 N=${1:-2}
-OUT=gpurun_out/r02m_n$N
+OUT=gpurun_out/r02s3m_n$N
 mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1
 if [ "$N" = "2" ]; then
