@@ -71,7 +71,11 @@ class FlatGradBucket:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # the view takes the parameter's own (dense) strides, so a channels-last convolution weight gets a
+            # channels-last gradient and autograd's layout contract holds; the flat order inside the range follows memory
+            seg = self.flat[off:off + p.numel()]
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            p.grad = seg.as_strided(p.size(), p.stride()) if (dense and not p.is_contiguous()) else seg.view_as(p)
             off += p.numel()
 
     def zero_(self):

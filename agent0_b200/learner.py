@@ -37,13 +37,21 @@ def _algo_name(cfg):
 
 
 class BaseLearner:
-    def __init__(self, cfg, process_group=None, device=None, max_p=None, capturable=False):
+    def __init__(self, cfg, process_group=None, device=None, max_p=None, capturable=False, amp_dtype=None, channels_last=False):
         """capturable=True makes ``update`` CUDA-graph safe (trainer.GraphedUpdates): device-side
         optimizer step counters, IQN/FQF taus from the device generator instead of the CPU one
         (SURVEY Q13 is then not reproduced draw for draw) and no NaN guard (its host sync cannot be
-        captured)."""
+        captured).
+        amp_dtype=torch.bfloat16 (opt-in): the networks run under ``torch.autocast`` in bf16 -- on
+        obs / next_obs that K3 already wrote as bf16 (a0_rb_gather_bf16, ``Trainer(amp=True)``) -- while parameters,
+        Adam, the K4 rules (fed ``output.float()``) and every priority stay fp32.  NOT the reference's arithmetic:
+        losses agree with the fp32 learner to bf16 rounding of the network outputs, not to 1e-5, so it is off by
+        default and outside the parity contract."""
         self.cfg = cfg
         self.capturable = bool(capturable)
+        assert amp_dtype in (None, torch.bfloat16), "amp_dtype: None (the reference's fp32) or torch.bfloat16"
+        self.amp_dtype = amp_dtype
+        self.channels_last = bool(channels_last)    # measured option: NHWC convolutions (obs converted by torch, one extra pass)
         dv = device if device is not None else getattr(cfg.device, "value", cfg.device)
         self.device = torch.device(dv)
         if self.device.type != "cuda":
@@ -57,6 +65,8 @@ class BaseLearner:
             # identical because every step applies the same all-reduced gradient
             from .actor import broadcast_model
             broadcast_model(self.model, src=0, process_group=process_group)
+        if self.channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
         self.model_target = copy.deepcopy(self.model)       # agent.py:100 (no RNG consumed)
         self.optimizer = torch.optim.Adam(list(self.model.params()), cfg.learner.learning_rate,
                                           eps=adam_eps(cfg.learner.batch_size, self.world), capturable=self.capturable)
@@ -90,6 +100,12 @@ class BaseLearner:
     def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
         raise NotImplementedError
 
+    @staticmethod
+    def _f32(x):
+        """A network output as the fp32 tensor K4 reads (and whose gradient K4 writes); under autocast a cast node
+        of the graph, so that ``net_out.backward(grad)`` flows back into the bf16 network."""
+        return x if x is None or x.dtype == torch.float32 else x.float()
+
     def train(self, data):
         """agent.py:124-169: one update, then the periodic target sync."""
         result = self.update(data)
@@ -112,13 +128,16 @@ class BaseLearner:
             obs, next_obs = frames          # f32 [B,4,H,W] pair from the fused gather (ReplayDataset.sample(normalized=))
         else:
             obs, next_obs = self.split_frames(frames.to(dev, non_blocking=True))
+        if self.channels_last:
+            obs, next_obs = obs.contiguous(memory_format=torch.channels_last), next_obs.contiguous(memory_format=torch.channels_last)
         actions = actions.to(dev, non_blocking=True).long()
         rewards = rewards.to(dev, non_blocking=True).float()
         terminals = terminals.to(dev, non_blocking=True).float()
         weights = weights.to(dev, non_blocking=True).float()
 
         self.bucket.zero_()
-        out, net_out = self.train_step(obs, actions, rewards, terminals, next_obs, weights)
+        with torch.autocast("cuda", dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
+            out, net_out = self.train_step(obs, actions, rewards, terminals, next_obs, weights)
         q_loss, fraction_loss = out.loss, out.fraction_loss
         skip = bool(torch.isnan(q_loss).any()) if self.nan_guard else False
         if not skip:
@@ -137,9 +156,9 @@ class DQNLearner(BaseLearner):
 
     def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
         with torch.no_grad():
-            qt_next = self.model_target(next_obs)
-            qsel = self.model.qval(next_obs) if self.cfg.learner.double_q else None
-        q = self.model(obs)
+            qt_next = self._f32(self.model_target(next_obs))
+            qsel = self._f32(self.model.qval(next_obs)) if self.cfg.learner.double_q else None
+        q = self._f32(self.model(obs))
         return L.dqn_loss(q, qt_next, actions, rewards, terminals, weights, self.gamma_n, qsel=qsel, **self._kw()), q
 
 
@@ -149,9 +168,9 @@ class MDQNLearner(BaseLearner):
     def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
         c = self.cfg.learner.mdqn
         with torch.no_grad():
-            qt_next = self.model_target(next_obs)
-            qt_cur = self.model_target(obs)
-        q = self.model(obs)
+            qt_next = self._f32(self.model_target(next_obs))
+            qt_cur = self._f32(self.model_target(obs))
+        q = self._f32(self.model(obs))
         return L.mdqn_loss(q, qt_next, qt_cur, actions, rewards, terminals, weights, self.gamma_n,
                            tau=c.tau, lo=c.lo, **self._kw()), q
 
@@ -162,9 +181,9 @@ class C51Learner(BaseLearner):
     def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
         c = self.cfg.learner.c51
         with torch.no_grad():
-            tgt = self.model_target(next_obs)
-            qsel = self.model.qval(next_obs) if self.cfg.learner.double_q else None
-        logits = self.model(obs)
+            tgt = self._f32(self.model_target(next_obs))
+            qsel = self._f32(self.model.qval(next_obs)) if self.cfg.learner.double_q else None
+        logits = self._f32(self.model(obs))
         return L.c51_loss(logits, tgt, self.model.head.atoms, actions, rewards, terminals, weights, self.gamma_n,
                           c.vmin, c.vmax, qsel=qsel, **self._kw()), logits
 
@@ -174,9 +193,9 @@ class QRLearner(BaseLearner):
 
     def train_step(self, obs, actions, rewards, terminals, next_obs, weights):
         with torch.no_grad():
-            qt_next = self.model_target(next_obs)
-            qsel = self.model.qval(next_obs) if self.cfg.learner.double_q else None
-        q = self.model(obs)
+            qt_next = self._f32(self.model_target(next_obs))
+            qsel = self._f32(self.model.qval(next_obs)) if self.cfg.learner.double_q else None
+        q = self._f32(self.model(obs))
         return L.qr_loss(q, qt_next, actions, rewards, terminals, weights, self.gamma_n, qsel=qsel, **self._kw()), q
 
 
@@ -193,7 +212,9 @@ class IQNLearner(BaseLearner):
             else:
                 qsel = self.model_target.head.qval(next_convs, n=c.K)
             qt_next, _ = self.model_target.head(next_convs, n=c.N_dash)
+            qsel, qt_next = self._f32(qsel), self._f32(qt_next)
         q, taus = self.model.head(self.model.encoder(obs), n=c.N)
+        q, taus = self._f32(q), self._f32(taus)
         return L.iqn_loss(q, taus, qt_next, qsel, actions, rewards, terminals, weights, self.gamma_n, **self._kw()), q
 
 
@@ -221,6 +242,8 @@ class FQFLearner(BaseLearner):
                 qsel = self.model_target.head.qval(next_convs)
             qt_next, _ = self.model_target.head(next_convs, taus=taus_hat)
             q_bar, _ = head(convs, taus=taus[:, 1:-1])
+            qsel, qt_next, q_bar = self._f32(qsel), self._f32(qt_next), self._f32(q_bar)
+        q_hat, taus, taus_hat = self._f32(q_hat), self._f32(taus), self._f32(taus_hat)
         out = L.fqf_loss(q_hat, taus, taus_hat, qt_next, q_bar, qsel, actions, rewards, terminals, weights,
                          self.gamma_n, **self._kw())
         # fraction step first (agent.py:139-148): only fraction_net receives this gradient

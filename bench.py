@@ -722,12 +722,12 @@ def learner_scaling(args, torch, dist, world, rank, barrier, reduce_max, A, algo
     out = {"algo": algo, "batch_per_gpu": B, "global_batch": B * world, "updates_per_learn": L, "n_gpus": world,
            "ring_per_gpu": ring}
 
-    def build(exchange, graph):
+    def build(exchange, graph, amp=False):
         cfg = make_config(algo, per=True, n_step=3, batch_size=B, double_q=True, dueling=True, replay_size=ring, num_envs=16,
                           action_dim=A)
         cfg.learner.learner_steps = L
         cfg.learner.target_update_freq = 500
-        tr = Trainer(cfg, process_group=pg, native_nstep=True, graph=graph, fused_input=True, sampler_seed=4242 + rank)
+        tr = Trainer(cfg, process_group=pg, native_nstep=True, graph=graph, fused_input=True, sampler_seed=4242 + rank, amp=amp)
         if world > 1:
             tr.learner.bucket.enabled = exchange
         fill_shard_synthetic(tr.replay, ring, 16, 77 + rank)
@@ -782,6 +782,15 @@ def learner_scaling(args, torch, dist, world, rank, barrier, reduce_max, A, algo
         del tr2
     else:
         del tr
+    torch.cuda.empty_cache()
+    try:        # the opt-in mixed-precision learner (bf16 gather + bf16 autocast, channels-last; fp32 weights, K4, Adam): not the reference's arithmetic
+        tr3 = build(True, graph, amp=True)
+        sec3 = timed(tr3)
+        out["bf16_channels_last_ms_per_update"] = round(sec3 * 1e3, 4)
+        out["bf16_channels_last_value"] = round(B * world / sec3, 1)
+        del tr3
+    except Exception as e:
+        out["bf16_channels_last_error"] = repr(e)[:300]
     torch.cuda.empty_cache()
     return out
 

@@ -178,3 +178,69 @@ def test_trainer_with_the_samplers_own_generator_draws_fresh_batches_per_replay(
     P = tr.replay.P
     for node in (1, 2, 3, P // 2, P - 1):
         assert tree[node] == np.float32(tree[2 * node] + tree[2 * node + 1])
+
+
+@pytest.mark.parametrize("algo", sorted(CASES))
+def test_bf16_autocast_learner_tracks_the_fp32_learner(golden, algo):
+    """Opt-in mixed precision: the networks under bf16 autocast, K4 / Adam / priorities in fp32.
+    NOT the reference's arithmetic -- so the check is the one a mixed-precision path can meet: from the same initial
+    weights and the same batch the first per-sample losses agree with the fp32 learner to bf16 rounding of the network
+    outputs, gradients flow (parameters move, fp32 master weights), everything stays finite over three updates."""
+    from agent0_b200.config import make_config
+    from agent0_b200.learner import make_learner
+    g = golden(f"learner_{algo}")
+    entries = golden("replay_n3")
+    double, dueling = CASES[algo]
+    B = int(g["batch"])
+    cfg = make_config(algo, per=True, n_step=3, batch_size=B, double_q=double, dueling=dueling, replay_size=256)
+    cfg.learner.target_update_freq = 2
+    torch.manual_seed(int(g["seed"]))
+    ref = make_learner(cfg)
+    torch.manual_seed(int(g["seed"]))
+    amp = make_learner(cfg, amp_dtype=torch.bfloat16)
+    assert all(torch.equal(a, b) for a, b in zip(ref.model.parameters(), amp.model.parameters()))
+    p0 = [p.detach().clone() for p in amp.model.parameters()]
+    for it in range(3):
+        idx = g[f"idx{it}"]
+        data = (torch.from_numpy(entries["entry_frames"][idx]).cuda(), torch.from_numpy(entries["entry_action"][idx]).cuda(),
+                torch.from_numpy(entries["entry_reward"][idx]).cuda(), torch.from_numpy(entries["entry_done"][idx]).cuda(),
+                torch.from_numpy(g[f"w{it}"]).cuda(), torch.from_numpy(idx).cuda())
+        if algo in ("iqn", "fqf"):
+            torch.manual_seed(100 + it)             # the tau draws come from the CPU generator (SURVEY Q13)
+        r32 = ref.train(data)
+        if algo in ("iqn", "fqf"):
+            torch.manual_seed(100 + it)
+        r16 = amp.train(data)
+        a, b = r16["q_loss"].float().cpu().numpy(), r32["q_loss"].cpu().numpy()
+        assert r16["q_loss"].dtype == torch.float32 and np.isfinite(a).all()
+        if it == 0:                                 # later updates start from slightly different weights
+            assert abs(a.mean() - b.mean()) <= 3e-2 * abs(b.mean()) + 1e-3, (a.mean(), b.mean())
+            assert np.abs(a - b).max() <= 0.1 * np.abs(b).max() + 1e-2
+    moved = sum(float((p.detach() - q).abs().sum()) for p, q in zip(amp.model.parameters(), p0))
+    assert moved > 0 and all(p.dtype == torch.float32 and torch.isfinite(p).all() for p in amp.model.parameters())
+    assert amp.update_steps == 3
+
+
+def test_amp_trainer_consumes_the_bf16_gather_eagerly_and_graphed():
+    """Trainer(amp=True): K3 writes obs / next_obs as bf16 (a0_rb_gather_bf16) and the learner consumes them under
+    autocast; as a CUDA graph the L updates replay with finite losses and priorities that keep changing."""
+    from agent0_b200.config import make_config
+    from agent0_b200.synth import fill_shard_synthetic
+    from agent0_b200.trainer import Trainer
+    for graph in (False, True):
+        cfg = make_config("c51", per=True, n_step=3, batch_size=16, double_q=True, dueling=True, replay_size=4096, num_envs=8)
+        cfg.learner.learner_steps = 4
+        cfg.learner.target_update_freq = 8
+        tr = Trainer(cfg, native_nstep=True, graph=graph, amp=True, sampler_seed=3)
+        fill_shard_synthetic(tr.replay, 4096, 8, 1)
+        root0 = float(tr.replay.tree[1])
+        for _ in range(3):
+            outs = tr.learn()
+        torch.cuda.synchronize()
+        assert len(outs) == 4 and all(torch.isfinite(q).all() and q.dtype == torch.float32 for q, _ in outs)
+        assert tr.learner.update_steps == 12 and float(tr.replay.tree[1]) != root0
+        if graph:
+            assert tr._graphed.static.obs.dtype == torch.bfloat16
+        tree = tr.replay.tree.cpu().numpy()
+        for node in (1, 2, 3, tr.replay.P // 2, tr.replay.P - 1):
+            assert tree[node] == np.float32(tree[2 * node] + tree[2 * node + 1])
