@@ -207,3 +207,58 @@ def test_duplicates_per_batch_against_the_reference_draw_without_replacement(sha
     assert out["peaked_1pct_at_100x"]["duplicate_fraction_per_batch_of_512"] < 0.05
     assert 0.5 < out["extreme_100_records_hold_90pct"]["duplicate_fraction_per_batch_of_512"] < 0.9
     parity.RECORD["k2a.duplicates_in_a_batch (with-replacement stratified draw vs replay.py:41-43)"] = out
+
+
+def test_waved_graphed_step_at_full_size(shard):
+    """The default schedule of hotloop.ReplayTargetLoop at BASELINE size (QR-200, 20 x 512 draws on the 2 M shard): the
+    gather in 20 waves with the ordered-fetch window on a side stream, each K4 joined to its wave, captured as one CUDA
+    graph.  Against the same draw issued as ONE eager gather launch (same sampler seed and call number): indices, stacks,
+    n-step scalars, IS weights, losses and gradients bit-identical; the stacks equal the torch rebuild from the raw
+    shard; after the step's write-back every tree node is still fl32(left + right)."""
+    from agent0_b200.hotloop import ReplayTargetLoop
+    rp, slots, info = shard
+    dev = rp.device
+    T, A, Nq = B * K, 4, 200
+    g = torch.Generator(device=dev).manual_seed(21)
+    o = {"online": torch.randn(T, A, Nq, device=dev, generator=g) * 3, "tgt_next": torch.randn(T, A, Nq, device=dev, generator=g) * 3,
+         "qsel": torch.randn(T, A, device=dev, generator=g)}
+    la = ReplayTargetLoop(rp, "qr", B, K, A, o, n_step=n, rng_seed=33, gather_waves=None)
+    lb = ReplayTargetLoop(rp, "qr", B, K, A, o, n_step=n, rng_seed=33)
+    assert lb.waves is not None and len(lb.waves) == K and lb.window == 400 and la.waves is None
+    rp.push_dynamic()
+    la.step(update=False); lb.step(update=False)            # warm-up: allocations, function attributes
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        lb.step(update=False)
+    for call in (700, 701):
+        rp.rng_seek(call)
+        la.step(update=False)
+        rp.rng_seek(call)
+        lb.frames.zero_(); lb.loss.fill_(-1.0)
+        gr.replay()
+        torch.cuda.synchronize()
+        for f in ("idx", "prio", "w", "frames", "act", "r64", "r32", "d8", "d32", "boot", "loss", "grad"):
+            assert torch.equal(getattr(la, f), getattr(lb, f)), f
+    p0 = lb.idx
+    p2 = info[info[p0, 3].long(), 3].long()
+    sl = torch.cat((slots[p0, :4], slots[p2, 4:]), dim=1).long()
+    assert torch.equal(lb.frames, rp.frames[sl.reshape(-1)].view(T, 8 * FB))
+    wmax = lb.w.view(K, B).max(dim=1)[0]
+    assert float(wmax.min()) > 0.999999 and float(wmax.max()) <= 1.0 and bool(torch.isfinite(lb.loss).all())
+    # the whole step, write-back included, as the captured graph bench.py replays
+    lb.capture(warm=1)
+    root0 = float(rp.tree[1])
+    for _ in range(3):
+        lb.run()
+    torch.cuda.synchronize()
+    t, P = rp.tree, rp.P
+    assert torch.equal(t[1:P], t[2:2 * P:2] + t[3:2 * P:2]) and float(t[1]) != root0
+    leaves = rp.priority.leaves()
+    want = (lb.loss + 0.01).sqrt()                         # (loss + eps)^alpha of the last step, later batches win duplicates
+    last = {}
+    for j, i in enumerate(lb.idx.tolist()):
+        last[i] = j
+    ii = torch.tensor(list(last.keys()), device=dev)
+    jj = torch.tensor(list(last.values()), device=dev)
+    torch.testing.assert_close(leaves[ii], want[jj], rtol=1e-6, atol=0)
