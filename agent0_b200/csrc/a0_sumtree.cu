@@ -1199,9 +1199,10 @@ int a0_launch_mark_append(a0_replay* h, const int32_t* marks, int32_t n_marks, f
 // ------------------------------------------------------------------------------------------------
 constexpr int K2C_THREADS = 1024;                             // (256 fatter threads measured the same: 75.4 vs 74.9 us per step)
 constexpr int K2C_LOG = 12;                                  // leaves per chunk = 4096
-constexpr int K2C_MAX_COUNT = 2048;
+constexpr int K2C_MAX_COUNT_DEFAULT = 16384;                 // A0_K2B_CHUNK_MAX: largest index list this schedule takes (2048 before the match list)
 constexpr int K2C_MAX_CHUNKS = 592;                          // 148 SMs x 4: beyond that (> 2 M leaves) the other schedules run
-constexpr size_t K2C_SMEM = ((size_t)2 << K2C_LOG) * 4 + ((size_t)1 << K2C_LOG) * 4;    // heap + tickets = 48 KB
+constexpr int K2C_MATCH_CAP = 1024;                          // entries of the index list a chunk remembers from its one scan
+constexpr size_t K2C_SMEM = ((size_t)2 << K2C_LOG) * 4 + ((size_t)1 << K2C_LOG) * 4 + (size_t)K2C_MATCH_CAP * 8;    // heap + tickets + match list = 56 KB
 constexpr int K2C_SPARSE_MAX = 32;                           // updated leaves per chunk climbed path by path (one lane each)
 
 __global__ void __launch_bounds__(K2C_THREADS)
@@ -1213,9 +1214,12 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   __shared__ int s_dirty;
   __shared__ bool s_last;
   __shared__ int s_nwin;                                     // distinct leaves of this chunk in the index list
+  __shared__ int s_nmatch;                                   // entries of the index list that fall into this chunk
   __shared__ int s_list[K2C_SPARSE_MAX];
   float* heap = reinterpret_cast<float*>(a0_k2c_smem);                      // heap[i] = node i of the chunk's sub-tree
   int* win = reinterpret_cast<int*>(a0_k2c_smem + ((size_t)2 << K2C_LOG) * 4);
+  int* m_k = win + ((size_t)1 << K2C_LOG);                   // the chunk's entries, remembered by the one scan of the list:
+  int* m_l = m_k + K2C_MATCH_CAP;                            // index k, leaf l (bit 31: an "unset" mark)
   A0_T0();
   // early (a0_pt_update_overlapped): launched programmatically under its predecessor -- the last K4 of a step -- the
   // kernel loads its leaves and builds its tickets (positions only) while that kernel is still running, and waits
@@ -1235,7 +1239,7 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   const int n = 1 << clog;
   const int top_levels = D - clog;                           // depth of the chunk roots
   const int64_t lo = (int64_t)c << clog;                    // first leaf of the chunk
-  if (tid == 0) { s_dirty = 0; s_nwin = 0; }
+  if (tid == 0) { s_dirty = 0; s_nwin = 0; s_nmatch = 0; }
   if (n >= 4) {
     const float4* src = reinterpret_cast<const float4*>(tree + P + lo);
     for (int i = tid; i < (n >> 2); i += K2C_THREADS) {
@@ -1255,12 +1259,41 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   };
   __syncthreads();
   K2C_TX(0);
-  // ---- pass 1: tickets for the entries of this chunk (positions only) ---------------------------------
+  // ---- pass 1: the ONE scan of the index list: tickets for the entries of this chunk (positions only), and the
+  //      entries themselves into the match list, so that the later passes walk a few dozen entries instead of
+  //      re-reading the whole list (three scans of 10 240 indices by each of 256 CTAs were what kept this schedule
+  //      behind the leaf-write + rebuild pair at batch 512).  A chunk with more entries than the list holds falls
+  //      back to re-scanning.
   for (int k = tid; k < count; k += K2C_THREADS) {
     bool set;
     const int64_t p = position(k, set);
-    if (p >= lo && p < lo + n && p < N) atomicMax(win + (int)(p - lo), k);
+    if (p >= lo && p < lo + n && p < N) {
+      const int l = (int)(p - lo);
+      atomicMax(win + l, k);
+      const int slot = atomicAdd(&s_nmatch, 1);
+      if (slot < K2C_MATCH_CAP) { m_k[slot] = k; m_l[slot] = set ? l : (l | (int)0x80000000); }
+    }
   }
+  __syncthreads();                                           // tickets and match list final
+  const int nmatch = s_nmatch;
+  const bool listed = nmatch <= K2C_MATCH_CAP;               // CTA-uniform
+  // body(k, l, set) for every entry of this chunk that holds its leaf's ticket (the highest k of its duplicates)
+  auto for_each_winner = [&](auto&& body) {
+    if (listed) {
+      for (int i = tid; i < nmatch; i += K2C_THREADS) {
+        const int k = m_k[i], lw = m_l[i], l = lw & 0x7fffffff;
+        if (win[l] == k) body(k, l, lw >= 0);
+      }
+    } else {
+      for (int k = tid; k < count; k += K2C_THREADS) {
+        bool set;
+        const int64_t p = position(k, set);
+        if (!(p >= lo && p < lo + n && p < N)) continue;
+        const int l = (int)(p - lo);
+        if (win[l] == k) body(k, l, set);
+      }
+    }
+  };
   // ---- few updated leaves (the usual case: 640 indices over 256 chunks): instead of recomputing the chunk's 4095
   //      inner nodes, each updated path is climbed on its own -- 12 adds -- from the siblings along it.  The sibling
   //      leaf is in shared memory already; the inner siblings are fetched from the tree here, one round trip for
@@ -1270,16 +1303,10 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   //      what the full recomputation would produce: the same tree, bit for bit.
   bool sparse = false;
   if (sparse_max > 0) {
-    __syncthreads();                                         // tickets final
-    for (int k = tid; k < count; k += K2C_THREADS) {
-      bool set;
-      const int64_t p = position(k, set);
-      if (!(p >= lo && p < lo + n && p < N)) continue;
-      const int l = (int)(p - lo);
-      if (win[l] != k) continue;
+    for_each_winner([&](int, int l, bool) {
       const int slot = atomicAdd(&s_nwin, 1);
       if (slot < K2C_SPARSE_MAX) s_list[slot] = l;
-    }
+    });
     __syncthreads();
     const int nwin = s_nwin;
     sparse = nwin <= sparse_max;                             // CTA-uniform
@@ -1311,15 +1338,10 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   __syncthreads();
   K2C_TX(1);
   // ---- pass 2: the winners overlay their leaves ----------------------------------------------------------
-  for (int k = tid; k < count; k += K2C_THREADS) {
-    bool set;
-    const int64_t p = position(k, set);
-    if (!(p >= lo && p < lo + n && p < N)) continue;
-    const int l = (int)(p - lo);
-    if (win[l] != k) continue;
+  for_each_winner([&](int k, int l, bool set) {
     float v;
     if (mode == 0) {
-      if (!(heap[n + l] > 0.0f) || !a0_loss_ok(vals[k])) continue;   // evicted since it was sampled / NaN loss
+      if (!(heap[n + l] > 0.0f) || !a0_loss_ok(vals[k])) return;     // evicted since it was sampled / NaN loss
       v = a0_priority(vals[k], eps, alpha);
     } else if (mode == 1) {
       v = set ? (alpha == 0.5f ? sqrtf(maxp_in) : powf(maxp_in, alpha)) : 0.0f;
@@ -1327,9 +1349,9 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
       v = vals[k];
     }
     heap[n + l] = v;
-    __stcg(tree + P + p, v);
+    __stcg(tree + P + lo + l, v);
     s_dirty = 1;
-  }
+  });
   __syncthreads();
   K2C_TX(2);
   if (s_dirty && sparse) {
@@ -1353,18 +1375,13 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
     a0_heap_reduce<K2C_THREADS>(heap, clog);
     K2C_TX(3);
     // ---- pass 3: the nodes on the updated paths (chunk-local node h at local level j) ------------------
-    for (int k = tid; k < count; k += K2C_THREADS) {
-      bool set;
-      const int64_t p = position(k, set);
-      if (!(p >= lo && p < lo + n && p < N)) continue;
-      const int l = (int)(p - lo);
-      if (win[l] != k) continue;
+    for_each_winner([&](int, int l, bool) {
       for (int j = clog - 1; j >= 0; --j) {
         const int h = (n + l) >> (clog - j);
         const int64_t g = ((int64_t)1 << (top_levels + j)) + ((int64_t)c << j) + (h - (1 << j));
         __stcg(tree + g, heap[h]);
       }
-    }
+    });
   }
   K2C_TX(4);
   if (top_levels == 0) return;                               // a single chunk: its root is the tree's root
@@ -1388,6 +1405,15 @@ a0_k2b_chunks(float* __restrict__ tree, int64_t P, int32_t D, int64_t N, const i
   if (tid == 0) A0_TEND(5);
 }
 
+static int g_k2b_chunk_max = -1;   // largest index list the one-launch chunk schedule takes (A0_K2B_CHUNK_MAX)
+static int a0_option_k2b_chunk_max() {
+  if (g_k2b_chunk_max < 0) {
+    const char* e = getenv("A0_K2B_CHUNK_MAX");
+    g_k2b_chunk_max = e ? atoi(e) : K2C_MAX_COUNT_DEFAULT;
+    if (g_k2b_chunk_max < 0) g_k2b_chunk_max = K2C_MAX_COUNT_DEFAULT;
+  }
+  return g_k2b_chunk_max;
+}
 static int g_k2b_sparse = -1;      // updated leaves per chunk up to which a0_k2b_chunks climbs path by path (0: always the full chunk)
 static int a0_option_k2b_sparse() {
   if (g_k2b_sparse < 0) {
@@ -1439,10 +1465,11 @@ static int a0_launch_update(a0_replay_t* h, const int64_t* idx64, const int32_t*
   // the tree (10 240 updates on a 1 M-leaf tree touch nearly every 4096-leaf chunk): the cluster only
   // writes the leaves (claim / write / release, two cluster barriers) and the chunk rebuild runs on
   // all SMs -- measured 29 -> see DESIGN.md.  More than one cluster can hold: one CTA writes.
-  if (count <= K2C_MAX_COUNT && chunks <= K2C_MAX_CHUNKS && a0_option_k2b_chunks()) {
+  if (count <= a0_option_k2b_chunk_max() && chunks <= K2C_MAX_CHUNKS && a0_option_k2b_chunks()) {
     // one CTA per 4096-leaf chunk in a single launch.  Measured: 640 indices on 1 M leaves 9.5 -> 8 us against
-    // the cluster climb; at 10 240 indices the leaf write + rebuild pair is faster (16.9 vs 21.5 us), so
-    // the chunk schedule is the default only up to 2048 indices
+    // the cluster climb.  With three scans of the index list per CTA the leaf write + rebuild pair was faster at
+    // 10 240 indices (16.9 vs 21.5 us), so this schedule stopped at 2048; with ONE scan and a match list it takes
+    // 11.9 us there and is the default up to 16 384 indices (A0_K2B_CHUNK_MAX)
     static thread_local bool attr[64] = {false};
     if (h->device < 64 && !attr[h->device]) {
       A0_CUDA(cudaFuncSetAttribute(a0_k2b_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2C_SMEM));

@@ -87,9 +87,10 @@ const char* a0_last_error(void);
  * indices run as one CTA that keeps the recomputed nodes in a shared-memory hash map.  A measured
  * alternative that lost (shared-memory CAS throughput); same tree either way.                     */
 #define A0_OPT_K2B_SMALL 7
-/* A0_OPT_K2B_CHUNKS (default 1; A0_K2B_CHUNKS in the environment): sum-tree writes of up to 2048
- * indices on trees of up to 2 M leaves run as ONE launch with one CTA per 4096-leaf chunk (each scans
- * the index list, recomputes its chunk in shared memory; the last CTA finishes the top levels); 0
+/* A0_OPT_K2B_CHUNKS (default 1; A0_K2B_CHUNKS in the environment): sum-tree writes of up to 16 384
+ * indices (A0_K2B_CHUNK_MAX in the environment) on trees of up to 2 M leaves run as ONE launch with one CTA
+ * per 4096-leaf chunk (each scans the index list once, remembers its own entries, recomputes its chunk -- or
+ * only the updated paths, A0_OPT_K2B_SPARSE -- in shared memory; the last CTA finishes the top levels); 0
  * falls back to the cluster schedules selected by A0_OPT_K2B_BULK_MIN.  Same tree either way.       */
 #define A0_OPT_K2B_CHUNKS 8
 /* A0_OPT_K2B_SPARSE (0..32, default 32; A0_K2B_SPARSE in the environment): a chunk CTA of the schedule above whose
