@@ -444,9 +444,17 @@ extern "C" int a0_rb_sample_mail(a0_replay_t* h, const float* u, uint64_t seed, 
   { int frc = a0_check_fault(h, "a0_rb_sample_mail"); if (frc) return frc; }
   A0DeviceGuard guard(h->device);
   { int mrc = a0_mail_reserve(h, total, (cudaStream_t)stream_); if (mrc) return mrc; }
-  if (h->progress_dirty) {
-    A0_CUDA(cudaMemsetAsync(h->counter + A0_K3_PROGRESS, 0, sizeof(unsigned int), (cudaStream_t)stream_));
-    h->progress_dirty = 0;
+  {
+    // The ordered fetch's progress word is re-armed by the last draw of every sampler call, which holds as long as every
+    // draw is gathered exactly once.  An eagerly issued call can be left half done (an exception between two wave
+    // launches, a failed launch), so outside a stream capture the word is cleared here; a captured graph launches all of
+    // its waves or none.  A stale word could only cost the ordering and bounded polls, never a result.
+    cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream_, &cst);
+    if (cst == cudaStreamCaptureStatusNone || h->progress_dirty) {
+      A0_CUDA(cudaMemsetAsync(h->counter + A0_K3_PROGRESS, 0, sizeof(unsigned int), (cudaStream_t)stream_));
+      h->progress_dirty = 0;
+    }
   }
   A0Rng rng = {0ull, 0ll, nullptr, nullptr, nullptr};
   if (!u) {
