@@ -131,7 +131,7 @@ class ReplayTargetLoop:
             self.fast = torch.cuda.Stream(device=dev, priority=-1) if k4_priority else None
             self.wave_ev = [torch.cuda.Event() for _ in self.waves]
             self._join = {b0: j for j, (b0, _, _, _) in enumerate(self.waves)}      # first batch of wave j -> j
-            per_batch = all(w[1] == 1 for w in self.waves)
+            per_batch = self.B * 16 * replay.F >= 10_000_000     # wave_plan's criterion: a batch's gather outlasts a K4
             # measured on B200 (profiles/r02s3_gather_waves_ab.json): 128 draws in flight feed a batch-32 K4 chain in order
             # at 67.9 us per step (96: 71.4, no limit: 71.0); 400 of the ~1036 resident gather CTAs in flight keep the
             # batch-512 step's K4 launches on pace with the waves at 216 us (no limit: 238, 320: 233, 480: 223)
